@@ -1,0 +1,192 @@
+"""ctypes mirror of include/bvio.h (struct layouts only, no compute).
+
+Used by the Python host-side tests/bench to call the C-ABI of libbvio.so (the
+product) and, in tests only, liboracle.so (the checker) with identical inputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class Preint(C.Structure):
+    _fields_ = [("delta_p", C.c_double * 3), ("delta_q", C.c_double * 4), ("delta_v", C.c_double * 3),
+                ("lin_ba", C.c_double * 3), ("lin_bg", C.c_double * 3), ("sum_dt", C.c_double),
+                ("jacobian", C.c_double * 225), ("covariance", C.c_double * 225)]
+
+
+assert C.sizeof(Preint) == 467 * 8
+
+
+class Prior(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nblocks", C.c_int32), ("block_kind", c_int32_p), ("block_frame", c_int32_p),
+                ("block_idx", c_int32_p), ("x0", c_double_p), ("lin_jac", c_double_p), ("lin_res", c_double_p)]
+
+
+class WindowS(C.Structure):
+    _fields_ = [("K", C.c_int32), ("para_pose", c_double_p), ("para_speed_bias", c_double_p),
+                ("para_ex_pose", c_double_p), ("para_td", c_double_p), ("L", C.c_int32),
+                ("inv_depth", c_double_p), ("lm_obs_offset", c_int32_p), ("obs_frame", c_int32_p),
+                ("obs_xy", c_double_p), ("obs_vel", c_double_p), ("obs_td", c_double_p), ("obs_row", c_double_p),
+                ("preint", C.POINTER(Preint)), ("prior", C.POINTER(Prior))]
+
+
+class Opts(C.Structure):
+    _fields_ = [("max_iters", C.c_int32), ("max_time_s", C.c_double), ("estimate_extrinsic", C.c_int32),
+                ("estimate_td", C.c_int32), ("focal_length", C.c_double), ("cauchy_a", C.c_double),
+                ("G", C.c_double * 3), ("TR", C.c_double), ("ROW", C.c_double),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double),
+                ("min_relative_decrease", C.c_double), ("strategy", C.c_int32), ("jacobi_scaling", C.c_int32)]
+
+
+class Summary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("num_accepted", C.c_int32), ("num_rejected", C.c_int32),
+                ("termination", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("final_radius", C.c_double), ("final_gradient_max", C.c_double), ("device_ms", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class PriorOut(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nblocks", C.c_int32), ("block_kind", c_int32_p), ("block_frame", c_int32_p),
+                ("block_idx", c_int32_p), ("x0", c_double_p), ("lin_jac", c_double_p), ("lin_res", c_double_p),
+                ("cap_n", C.c_int32), ("cap_blocks", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class SelectIn(C.Structure):
+    _fields_ = [("H", C.c_int32), ("horizon_pos", c_double_p), ("horizon_quat", c_double_p),
+                ("q_ic", C.c_double * 4), ("t_ic", C.c_double * 3), ("cam", Camera),
+                ("nr_imu", C.c_int32), ("delta_imu", C.c_double), ("acc_var", C.c_double),
+                ("acc_bias_var", C.c_double),
+                ("N", C.c_int32), ("cand_id", c_int32_p), ("cand_xy", c_double_p), ("cand_prob", c_double_p),
+                ("U", C.c_int32), ("used_id", c_int32_p), ("used_xy", c_double_p),
+                ("C", C.c_int32), ("cloud_xy", c_double_p), ("cloud_depth", c_double_p),
+                ("kappa", C.c_int32)]
+
+
+class SelectSummary(C.Structure):
+    _fields_ = [("n_selected", C.c_int32), ("n_candidates_valid", C.c_int32), ("candidates_scored", C.c_int64),
+                ("final_logdet", C.c_double), ("min_margin", C.c_double), ("device_ms", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+def dptr(a: np.ndarray):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_double_p)
+
+
+def iptr(a: np.ndarray):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_int32_p)
+
+
+def default_opts(**kw) -> Opts:
+    """EuRoC values: config/euroc/euroc_config.yaml:54-63, parameters.h:13; Ceres 1.14 defaults."""
+    o = Opts()
+    o.max_iters = 8
+    o.max_time_s = 0.0
+    o.estimate_extrinsic = 0
+    o.estimate_td = 0
+    o.focal_length = 460.0
+    o.cauchy_a = 1.0
+    o.G[0], o.G[1], o.G[2] = 0.0, 0.0, 9.81007
+    o.TR, o.ROW = 0.0, 480.0
+    o.function_tolerance = 1e-6
+    o.gradient_tolerance = 1e-10
+    o.parameter_tolerance = 1e-8
+    o.initial_radius = 1e4
+    o.min_relative_decrease = 1e-3
+    o.strategy = 0
+    o.jacobi_scaling = 1
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class WindowHandle:
+    """Owns the numpy buffers a bvio_window points into (state arrays are copies: in/out)."""
+
+    def __init__(self, w):
+        self.src = w
+        self.pose = np.ascontiguousarray(w.para_pose, np.float64).copy()
+        self.sb = np.ascontiguousarray(w.para_speed_bias, np.float64).copy()
+        self.ex = np.ascontiguousarray(w.para_ex_pose, np.float64).copy()
+        self.td = np.ascontiguousarray(w.para_td, np.float64).copy()
+        self.inv = np.ascontiguousarray(w.inv_depth, np.float64).copy()
+        self.off = np.ascontiguousarray(w.lm_obs_offset, np.int32)
+        self.frame = np.ascontiguousarray(w.obs_frame, np.int32)
+        self.xy = np.ascontiguousarray(w.obs_xy, np.float64)
+        self.pre = np.ascontiguousarray(w.preint, np.float64)
+        s = WindowS()
+        s.K = w.K
+        s.para_pose, s.para_speed_bias = dptr(self.pose), dptr(self.sb)
+        s.para_ex_pose, s.para_td = dptr(self.ex), dptr(self.td)
+        s.L = len(self.inv)
+        s.inv_depth = dptr(self.inv)
+        s.lm_obs_offset, s.obs_frame, s.obs_xy = iptr(self.off), iptr(self.frame), dptr(self.xy)
+        s.obs_vel = s.obs_td = s.obs_row = None
+        s.preint = C.cast(self.pre.ctypes.data, C.POINTER(Preint))
+        self.prior_s = None
+        if w.prior is not None:
+            p = w.prior
+            self._pk = np.ascontiguousarray(p["block_kind"], np.int32)
+            self._pf = np.ascontiguousarray(p["block_frame"], np.int32)
+            self._pi = np.ascontiguousarray(p["block_idx"], np.int32)
+            self._px0 = np.ascontiguousarray(p["x0"], np.float64)
+            self._pj = np.ascontiguousarray(p["lin_jac"], np.float64)
+            self._pr = np.ascontiguousarray(p["lin_res"], np.float64)
+            ps = Prior()
+            ps.n, ps.nblocks = int(p["n"]), len(self._pk)
+            ps.block_kind, ps.block_frame, ps.block_idx = iptr(self._pk), iptr(self._pf), iptr(self._pi)
+            ps.x0, ps.lin_jac, ps.lin_res = dptr(self._px0), dptr(self._pj), dptr(self._pr)
+            self.prior_s = ps
+            s.prior = C.pointer(ps)
+        else:
+            s.prior = None
+        self.s = s
+
+    def state_vector(self):
+        return np.concatenate([self.pose.ravel(), self.sb.ravel(), self.ex, self.inv])
+
+
+class SelectHandle:
+    def __init__(self, p):
+        self.src = p
+        f64 = lambda a: np.ascontiguousarray(a, np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        self.pos, self.quat = f64(p.horizon_pos), f64(p.horizon_quat)
+        self.cid, self.cxy, self.cp = i32(p.cand_id), f64(p.cand_xy), f64(p.cand_prob)
+        self.uid, self.uxy = i32(p.used_id), f64(p.used_xy).reshape(-1, 2)
+        self.clxy, self.cld = f64(p.cloud_xy).reshape(-1, 2), f64(p.cloud_depth)
+        s = SelectIn()
+        s.H = p.H
+        s.horizon_pos, s.horizon_quat = dptr(self.pos), dptr(self.quat)
+        for i in range(4):
+            s.q_ic[i] = p.q_ic[i]
+        for i in range(3):
+            s.t_ic[i] = p.t_ic[i]
+        for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "width", "height"):
+            setattr(s.cam, k, p.cam[k])
+        s.nr_imu, s.delta_imu, s.acc_var, s.acc_bias_var = p.nr_imu, p.delta_imu, p.acc_var, p.acc_bias_var
+        s.N, s.cand_id, s.cand_xy, s.cand_prob = len(self.cid), iptr(self.cid), dptr(self.cxy), dptr(self.cp)
+        s.U = len(self.uid)
+        s.used_id = iptr(self.uid) if s.U else None
+        s.used_xy = dptr(self.uxy) if s.U else None
+        s.C = len(self.cld)
+        s.cloud_xy = dptr(self.clxy) if s.C else None
+        s.cloud_depth = dptr(self.cld) if s.C else None
+        s.kappa = p.kappa
+        self.s = s

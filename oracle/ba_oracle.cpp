@@ -1,0 +1,909 @@
+// oracle/ba_oracle.cpp -- CPU restatement of Estimator::optimization()'s numerical path.
+// TEST INFRASTRUCTURE ONLY; parity unpinned (see oracle/oracle.h).
+//
+// Follows, line by line where the arithmetic is observable:
+//   ProjectionFactor::Evaluate          vins_estimator/src/factor/projection_factor.cpp:21-121
+//   IMUFactor::Evaluate                 vins_estimator/src/factor/imu_factor.h:19-179
+//   IntegrationBase::evaluate/propagate vins_estimator/src/factor/integration_base.h:54-186
+//   MarginalizationFactor::Evaluate     vins_estimator/src/factor/marginalization_factor.cpp:333-381
+//   ResidualBlockInfo::Evaluate (loss)  vins_estimator/src/factor/marginalization_factor.cpp:37-68
+//   PoseLocalParameterization::Plus     vins_estimator/src/factor/pose_local_parameterization.cpp:3-18
+//   problem structure                   vins_estimator/src/estimator.cpp:661-809
+//   double2vector                       vins_estimator/src/estimator.cpp:521-555
+// The trust-region loop restates Ceres Solver 1.14 (un-vendored dependency,
+// vins_estimator/CMakeLists.txt:23): TrustRegionMinimizer + DENSE_SCHUR +
+// LevenbergMarquardtStrategy / DoglegStrategy(TRADITIONAL_DOGLEG), Jacobi scaling on.
+#include "oracle.h"
+#include "linalg.hpp"
+#include <cstdio>
+#include <cstdlib>
+#include <chrono>
+#include <vector>
+
+using namespace orc;
+
+namespace {
+
+inline V3 v3(const double* p) { return {p[0], p[1], p[2]}; }
+inline Q4 q4(const double* p) { return {p[0], p[1], p[2], p[3]}; }  // x y z w
+
+// ---------------------------------------------------------------------------
+// a2: ProjectionFactor::Evaluate
+// ---------------------------------------------------------------------------
+void projection_eval(V3 pts_i, V3 pts_j, V3 Pi, Q4 Qi, V3 Pj, Q4 Qj, V3 tic, Q4 qic, double inv_dep_i,
+                     double sqrt_info, double res[2], double* Ji, double* Jj, double* Jex, double* Jf) {
+  V3 pts_camera_i = pts_i / inv_dep_i;
+  V3 pts_imu_i = qrot(qic, pts_camera_i) + tic;
+  V3 pts_w = qrot(Qi, pts_imu_i) + Pi;
+  V3 pts_imu_j = qrot(qinv(Qj), pts_w - Pj);
+  V3 pts_camera_j = qrot(qinv(qic), pts_imu_j - tic);
+  double dep_j = pts_camera_j.z;
+  res[0] = sqrt_info * ((pts_camera_j.x / dep_j) - pts_j.x);
+  res[1] = sqrt_info * ((pts_camera_j.y / dep_j) - pts_j.y);
+  if (!Ji && !Jj && !Jex && !Jf) return;
+
+  M3 Ri = qmat(Qi), Rj = qmat(Qj), ric = qmat(qic);
+  double reduce[2][3] = {{1. / dep_j, 0, -pts_camera_j.x / (dep_j * dep_j)},
+                         {0, 1. / dep_j, -pts_camera_j.y / (dep_j * dep_j)}};
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 3; b++) reduce[a][b] *= sqrt_info;
+  auto mul23 = [&](const M3& m, double out[2][3]) {
+    for (int a = 0; a < 2; a++)
+      for (int b = 0; b < 3; b++) out[a][b] = reduce[a][0] * m[0][b] + reduce[a][1] * m[1][b] + reduce[a][2] * m[2][b];
+  };
+  M3 ricT = transpose(ric), RjT = transpose(Rj);
+  if (Ji) {
+    M3 left = ricT * RjT;
+    M3 right = ricT * RjT * Ri * (-skew(pts_imu_i));
+    double l[2][3], r[2][3];
+    mul23(left, l); mul23(right, r);
+    for (int a = 0; a < 2; a++) {
+      for (int b = 0; b < 3; b++) { Ji[a * 7 + b] = l[a][b]; Ji[a * 7 + 3 + b] = r[a][b]; }
+      Ji[a * 7 + 6] = 0;
+    }
+  }
+  if (Jj) {
+    M3 left = ricT * (-RjT);
+    M3 right = ricT * skew(pts_imu_j);
+    double l[2][3], r[2][3];
+    mul23(left, l); mul23(right, r);
+    for (int a = 0; a < 2; a++) {
+      for (int b = 0; b < 3; b++) { Jj[a * 7 + b] = l[a][b]; Jj[a * 7 + 3 + b] = r[a][b]; }
+      Jj[a * 7 + 6] = 0;
+    }
+  }
+  if (Jex) {
+    M3 left = ricT * (RjT * Ri - eye3());
+    M3 tmp_r = ricT * RjT * Ri * ric;
+    M3 right = (-tmp_r) * skew(pts_camera_i) + skew(tmp_r * pts_camera_i) +
+               skew(ricT * (RjT * (Ri * tic + Pi - Pj) - tic));
+    double l[2][3], r[2][3];
+    mul23(left, l); mul23(right, r);
+    for (int a = 0; a < 2; a++) {
+      for (int b = 0; b < 3; b++) { Jex[a * 7 + b] = l[a][b]; Jex[a * 7 + 3 + b] = r[a][b]; }
+      Jex[a * 7 + 6] = 0;
+    }
+  }
+  if (Jf) {
+    M3 m = ricT * RjT * Ri * ric;
+    V3 v = m * pts_i;
+    for (int a = 0; a < 2; a++)
+      Jf[a] = (reduce[a][0] * v.x + reduce[a][1] * v.y + reduce[a][2] * v.z) * -1.0 / (inv_dep_i * inv_dep_i);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// a3: IMUFactor::Evaluate
+// ---------------------------------------------------------------------------
+void imu_sqrt_info(const double cov[225], double si[225]) {
+  double inv[225];
+  lu_inverse(cov, 15, inv);
+  // Eigen::LLT reads only the lower triangle of its argument
+  double l[225];
+  std::memcpy(l, inv, sizeof l);
+  cholesky(l, 15);
+  for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) si[i * 15 + j] = (j >= i) ? l[j * 15 + i] : 0.0;  // L^T
+}
+
+// Qleft / Qright bottom-right 3x3 (utility.h:49-67). q is w-first 4x4 in the reference;
+// bottomRightCorner<3,3> = w I +/- skew(vec)
+inline M3 qleft_br(Q4 q) { return q.w * eye3() + skew(qvec(q)); }
+inline M3 qright_br(Q4 q) { return q.w * eye3() - skew(qvec(q)); }
+// (Qleft(a) * Qright(b)).bottomRightCorner<3,3>() with the full 4x4 product
+M3 qleft_qright_br(Q4 a, Q4 b) {
+  double La[4][4], Rb[4][4];
+  V3 av = qvec(a), bv = qvec(b);
+  M3 la = qleft_br(a), rb = qright_br(b);
+  La[0][0] = a.w; Rb[0][0] = b.w;
+  for (int i = 0; i < 3; i++) {
+    La[0][1 + i] = -av[i]; La[1 + i][0] = av[i];
+    Rb[0][1 + i] = -bv[i]; Rb[1 + i][0] = bv[i];
+    for (int j = 0; j < 3; j++) { La[1 + i][1 + j] = la[i][j]; Rb[1 + i][1 + j] = rb[i][j]; }
+  }
+  M3 out;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0;
+      for (int k = 0; k < 4; k++) s += La[1 + i][k] * Rb[k][1 + j];
+      out[i][j] = s;
+    }
+  return out;
+}
+
+void imu_eval(const bvio_preint* pre, V3 G, const double* pose_i, const double* sb_i, const double* pose_j,
+              const double* sb_j, const double* sqrt_info /*15x15 row-major*/, double res[15], double* Jpi,
+              double* Jsbi, double* Jpj, double* Jsbj) {
+  V3 Pi = v3(pose_i), Pj = v3(pose_j);
+  Q4 Qi = q4(pose_i + 3), Qj = q4(pose_j + 3);
+  V3 Vi = v3(sb_i), Bai = v3(sb_i + 3), Bgi = v3(sb_i + 6);
+  V3 Vj = v3(sb_j), Baj = v3(sb_j + 3), Bgj = v3(sb_j + 6);
+  const double* J = pre->jacobian;
+  auto blk = [&](int r, int c) {
+    M3 m;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m[i][j] = J[(r + i) * 15 + c + j];
+    return m;
+  };
+  M3 dp_dba = blk(0, 9), dp_dbg = blk(0, 12), dq_dbg = blk(3, 12), dv_dba = blk(6, 9), dv_dbg = blk(6, 12);
+  V3 lin_ba = v3(pre->lin_ba), lin_bg = v3(pre->lin_bg);
+  V3 dba = Bai - lin_ba, dbg = Bgi - lin_bg;
+  Q4 delta_q = q4(pre->delta_q);
+  V3 delta_p = v3(pre->delta_p), delta_v = v3(pre->delta_v);
+  double sum_dt = pre->sum_dt;
+  // IntegrationBase::evaluate, integration_base.h:160-186
+  Q4 corrected_delta_q = qmul(delta_q, deltaQ(dq_dbg * dbg));
+  V3 corrected_delta_v = delta_v + dv_dba * dba + dv_dbg * dbg;
+  V3 corrected_delta_p = delta_p + dp_dba * dba + dp_dbg * dbg;
+  double r[15];
+  V3 rp = qrot(qinv(Qi), 0.5 * G * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt) - corrected_delta_p;
+  V3 rq = 2.0 * qvec(qmul(qinv(corrected_delta_q), qmul(qinv(Qi), Qj)));
+  V3 rv = qrot(qinv(Qi), G * sum_dt + Vj - Vi) - corrected_delta_v;
+  V3 rba = Baj - Bai, rbg = Bgj - Bgi;
+  for (int i = 0; i < 3; i++) { r[i] = rp[i]; r[3 + i] = rq[i]; r[6 + i] = rv[i]; r[9 + i] = rba[i]; r[12 + i] = rbg[i]; }
+  for (int i = 0; i < 15; i++) {
+    double s = 0;
+    for (int k = 0; k < 15; k++) s += sqrt_info[i * 15 + k] * r[k];
+    res[i] = s;
+  }
+  if (!Jpi && !Jsbi && !Jpj && !Jsbj) return;
+  auto put = [](double* M, int cols, int r0, int c0, const M3& m) {
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) M[(r0 + i) * cols + c0 + j] = m[i][j];
+  };
+  auto premul = [&](double* M, int cols) {  // M = sqrt_info * M
+    std::vector<double> t(15 * cols);
+    for (int i = 0; i < 15; i++)
+      for (int j = 0; j < cols; j++) {
+        double s = 0;
+        for (int k = 0; k < 15; k++) s += sqrt_info[i * 15 + k] * M[k * cols + j];
+        t[i * cols + j] = s;
+      }
+    std::memcpy(M, t.data(), sizeof(double) * 15 * cols);
+  };
+  M3 RiT = qmat(qinv(Qi));
+  if (Jpi) {
+    std::memset(Jpi, 0, sizeof(double) * 15 * 7);
+    put(Jpi, 7, 0, 0, -RiT);
+    put(Jpi, 7, 0, 3, skew(qrot(qinv(Qi), 0.5 * G * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt)));
+    put(Jpi, 7, 3, 3, -qleft_qright_br(qmul(qinv(Qj), Qi), corrected_delta_q));
+    put(Jpi, 7, 6, 3, skew(qrot(qinv(Qi), G * sum_dt + Vj - Vi)));
+    premul(Jpi, 7);
+  }
+  if (Jsbi) {
+    std::memset(Jsbi, 0, sizeof(double) * 15 * 9);
+    put(Jsbi, 9, 0, 0, -sum_dt * RiT);
+    put(Jsbi, 9, 0, 3, -dp_dba);
+    put(Jsbi, 9, 0, 6, -dp_dbg);
+    put(Jsbi, 9, 3, 6, -(qleft_br(qmul(qmul(qinv(Qj), Qi), delta_q)) * dq_dbg));
+    put(Jsbi, 9, 6, 0, -RiT);
+    put(Jsbi, 9, 6, 3, -dv_dba);
+    put(Jsbi, 9, 6, 6, -dv_dbg);
+    put(Jsbi, 9, 9, 3, -eye3());
+    put(Jsbi, 9, 12, 6, -eye3());
+    premul(Jsbi, 9);
+  }
+  if (Jpj) {
+    std::memset(Jpj, 0, sizeof(double) * 15 * 7);
+    put(Jpj, 7, 0, 0, RiT);
+    put(Jpj, 7, 3, 3, qleft_br(qmul(qmul(qinv(corrected_delta_q), qinv(Qi)), Qj)));
+    premul(Jpj, 7);
+  }
+  if (Jsbj) {
+    std::memset(Jsbj, 0, sizeof(double) * 15 * 9);
+    put(Jsbj, 9, 6, 0, RiT);
+    put(Jsbj, 9, 9, 3, eye3());
+    put(Jsbj, 9, 12, 6, eye3());
+    premul(Jsbj, 9);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// a4: MarginalizationFactor::Evaluate
+// ---------------------------------------------------------------------------
+inline int blk_global(int kind) { return kind == BVIO_BLK_SPEEDBIAS ? 9 : (kind == BVIO_BLK_TD ? 1 : 7); }
+inline int blk_local(int kind) { return kind == BVIO_BLK_SPEEDBIAS ? 9 : (kind == BVIO_BLK_TD ? 1 : 6); }
+const double* blk_ptr(const bvio_window* w, int kind, int frame) {
+  switch (kind) {
+    case BVIO_BLK_POSE: return w->para_pose + 7 * frame;
+    case BVIO_BLK_SPEEDBIAS: return w->para_speed_bias + 9 * frame;
+    case BVIO_BLK_EXPOSE: return w->para_ex_pose;
+    default: return w->para_td;
+  }
+}
+void prior_eval(const bvio_prior* p, const bvio_window* w, double* res, double* dx) {
+  int n = p->n;
+  const double* x0 = p->x0;
+  for (int b = 0; b < p->nblocks; b++) {
+    int kind = p->block_kind[b], size = blk_global(kind), idx = p->block_idx[b];
+    const double* x = blk_ptr(w, kind, p->block_frame[b]);
+    if (size != 7) {
+      for (int i = 0; i < size; i++) dx[idx + i] = x[i] - x0[i];
+    } else {
+      for (int i = 0; i < 3; i++) dx[idx + i] = x[i] - x0[i];
+      Q4 dq = qmul(qinv(q4(x0 + 3)), q4(x + 3));
+      V3 v = 2.0 * qvec(dq);
+      if (!(dq.w >= 0)) v = -v;
+      for (int i = 0; i < 3; i++) dx[idx + 3 + i] = v[i];
+    }
+    x0 += size;
+  }
+  for (int i = 0; i < n; i++) {
+    double s = p->lin_res[i];
+    for (int k = 0; k < n; k++) s += p->lin_jac[k * n + i] * dx[k];  // column-major
+    res[i] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// problem, normal equations, Schur
+// ---------------------------------------------------------------------------
+struct Layout {
+  int K, L, np, ex_off, est_ex;
+};
+Layout layout(const bvio_window* w, const bvio_opts* o) {
+  Layout l;
+  l.K = w->K; l.L = w->L; l.est_ex = o->estimate_extrinsic != 0;
+  l.ex_off = 15 * w->K;
+  l.np = 15 * w->K + (l.est_ex ? 6 : 0);
+  return l;
+}
+
+struct Normal {
+  std::vector<double> Hpp, bp, h, b, w, wex;  // w: 6 per observation (obs 0 = anchor frame)
+  double cost;
+};
+
+inline void cauchy(double a, double s, double rho[3]) {
+  // ceres::CauchyLoss::Evaluate: b = a^2, c = 1/b
+  double bb = a * a, c = 1.0 / bb;
+  double sum = 1.0 + s * c, inv = 1.0 / sum;
+  rho[0] = bb * std::log(sum);
+  rho[1] = std::max(std::numeric_limits<double>::min(), inv);
+  rho[2] = -c * (inv * inv);
+}
+
+double visual_cost(const bvio_window* w, const bvio_opts* o) {
+  double sqrt_info = o->focal_length / 1.5, cost = 0;
+  V3 tic = v3(w->para_ex_pose); Q4 qic = q4(w->para_ex_pose + 3);
+  for (int l = 0; l < w->L; l++) {
+    int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
+    int fi = w->obs_frame[o0];
+    V3 pts_i{w->obs_xy[2 * o0], w->obs_xy[2 * o0 + 1], 1.0};
+    for (int k = o0 + 1; k < o1; k++) {
+      int fj = w->obs_frame[k];
+      V3 pts_j{w->obs_xy[2 * k], w->obs_xy[2 * k + 1], 1.0};
+      double r[2];
+      projection_eval(pts_i, pts_j, v3(w->para_pose + 7 * fi), q4(w->para_pose + 7 * fi + 3),
+                      v3(w->para_pose + 7 * fj), q4(w->para_pose + 7 * fj + 3), tic, qic, w->inv_depth[l],
+                      sqrt_info, r, nullptr, nullptr, nullptr, nullptr);
+      double rho[3];
+      cauchy(o->cauchy_a, r[0] * r[0] + r[1] * r[1], rho);
+      cost += 0.5 * rho[0];
+    }
+  }
+  return cost;
+}
+
+struct ImuCache { std::vector<double> sqrt_info; };  // [K][225]
+void build_imu_cache(const bvio_window* w, ImuCache& c) {
+  c.sqrt_info.assign(225 * w->K, 0.0);
+  for (int j = 1; j < w->K; j++)
+    if (!(w->preint[j].sum_dt > 10.0)) imu_sqrt_info(w->preint[j].covariance, &c.sqrt_info[225 * j]);
+}
+
+double imu_prior_cost(const bvio_window* w, const bvio_opts* o, const ImuCache& ic) {
+  double cost = 0;
+  V3 G = v3(o->G);
+  for (int j = 1; j < w->K; j++) {
+    if (w->preint[j].sum_dt > 10.0) continue;
+    double r[15];
+    imu_eval(&w->preint[j], G, w->para_pose + 7 * (j - 1), w->para_speed_bias + 9 * (j - 1), w->para_pose + 7 * j,
+             w->para_speed_bias + 9 * j, &ic.sqrt_info[225 * j], r, nullptr, nullptr, nullptr, nullptr);
+    for (int i = 0; i < 15; i++) cost += 0.5 * r[i] * r[i];
+  }
+  if (w->prior) {
+    int n = w->prior->n;
+    std::vector<double> r(n), dx(n);
+    prior_eval(w->prior, w, r.data(), dx.data());
+    for (int i = 0; i < n; i++) cost += 0.5 * r[i] * r[i];
+  }
+  return cost;
+}
+
+void linearize(const bvio_window* w, const bvio_opts* o, const ImuCache& ic, const Layout& ly, Normal& N) {
+  int np = ly.np, L = ly.L, nobs = w->lm_obs_offset[L];
+  N.Hpp.assign((size_t)np * np, 0.0);
+  N.bp.assign(np, 0.0);
+  N.h.assign(L, 0.0);
+  N.b.assign(L, 0.0);
+  N.w.assign((size_t)6 * nobs, 0.0);
+  N.wex.assign((size_t)6 * L, 0.0);
+  N.cost = 0;
+  double sqrt_info = o->focal_length / 1.5;
+  V3 tic = v3(w->para_ex_pose); Q4 qic = q4(w->para_ex_pose + 3);
+  double* H = N.Hpp.data();
+  auto addblk = [&](int r0, const double* A, int c0, const double* B) {  // H[r0.., c0..] += A^T B (2x6 each)
+    for (int a = 0; a < 6; a++)
+      for (int b = 0; b < 6; b++) H[(size_t)(r0 + a) * np + c0 + b] += A[a] * B[b] + A[6 + a] * B[6 + b];
+  };
+  // ---- visual factors (estimator.cpp:710-755) with Cauchy loss corrector
+  for (int l = 0; l < L; l++) {
+    int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
+    int fi = w->obs_frame[o0];
+    V3 pts_i{w->obs_xy[2 * o0], w->obs_xy[2 * o0 + 1], 1.0};
+    for (int k = o0 + 1; k < o1; k++) {
+      int fj = w->obs_frame[k];
+      V3 pts_j{w->obs_xy[2 * k], w->obs_xy[2 * k + 1], 1.0};
+      double r[2], Ji[14], Jj[14], Jex[14], Jf[2];
+      projection_eval(pts_i, pts_j, v3(w->para_pose + 7 * fi), q4(w->para_pose + 7 * fi + 3),
+                      v3(w->para_pose + 7 * fj), q4(w->para_pose + 7 * fj + 3), tic, qic, w->inv_depth[l],
+                      sqrt_info, r, Ji, Jj, ly.est_ex ? Jex : nullptr, Jf);
+      double rho[3], s = r[0] * r[0] + r[1] * r[1];
+      cauchy(o->cauchy_a, s, rho);
+      N.cost += 0.5 * rho[0];
+      // Corrector (marginalization_factor.cpp:37-68 == ceres::internal::Corrector): rho'' <= 0 branch
+      double sr = std::sqrt(rho[1]);
+      double A[12], B[12], E[12], c[2];
+      for (int a = 0; a < 2; a++) {
+        for (int b = 0; b < 6; b++) {
+          A[a * 6 + b] = sr * Ji[a * 7 + b];
+          B[a * 6 + b] = sr * Jj[a * 7 + b];
+          E[a * 6 + b] = ly.est_ex ? sr * Jex[a * 7 + b] : 0.0;
+        }
+        c[a] = sr * Jf[a];
+        r[a] *= sr;
+      }
+      int ri = 15 * fi, rj = 15 * fj;
+      addblk(ri, A, ri, A); addblk(rj, B, rj, B); addblk(ri, A, rj, B); addblk(rj, B, ri, A);
+      for (int a = 0; a < 6; a++) {
+        N.bp[ri + a] += A[a] * r[0] + A[6 + a] * r[1];
+        N.bp[rj + a] += B[a] * r[0] + B[6 + a] * r[1];
+        N.w[(size_t)6 * o0 + a] += A[a] * c[0] + A[6 + a] * c[1];
+        N.w[(size_t)6 * k + a] += B[a] * c[0] + B[6 + a] * c[1];
+      }
+      if (ly.est_ex) {
+        int re = ly.ex_off;
+        addblk(re, E, re, E); addblk(ri, A, re, E); addblk(re, E, ri, A); addblk(rj, B, re, E); addblk(re, E, rj, B);
+        for (int a = 0; a < 6; a++) {
+          N.bp[re + a] += E[a] * r[0] + E[6 + a] * r[1];
+          N.wex[(size_t)6 * l + a] += E[a] * c[0] + E[6 + a] * c[1];
+        }
+      }
+      N.h[l] += c[0] * c[0] + c[1] * c[1];
+      N.b[l] += c[0] * r[0] + c[1] * r[1];
+    }
+  }
+  // ---- IMU factors (estimator.cpp:702-709)
+  V3 G = v3(o->G);
+  for (int j = 1; j < w->K; j++) {
+    if (w->preint[j].sum_dt > 10.0) continue;
+    int i = j - 1;
+    double r[15], Jpi[105], Jsbi[135], Jpj[105], Jsbj[135];
+    imu_eval(&w->preint[j], G, w->para_pose + 7 * i, w->para_speed_bias + 9 * i, w->para_pose + 7 * j,
+             w->para_speed_bias + 9 * j, &ic.sqrt_info[225 * j], r, Jpi, Jsbi, Jpj, Jsbj);
+    double J[15][30];
+    for (int a = 0; a < 15; a++) {
+      for (int b = 0; b < 6; b++) { J[a][b] = Jpi[a * 7 + b]; J[a][15 + b] = Jpj[a * 7 + b]; }
+      for (int b = 0; b < 9; b++) { J[a][6 + b] = Jsbi[a * 9 + b]; J[a][21 + b] = Jsbj[a * 9 + b]; }
+    }
+    int r0 = 15 * i;
+    for (int a = 0; a < 30; a++) {
+      for (int b = 0; b < 30; b++) {
+        double s = 0;
+        for (int k = 0; k < 15; k++) s += J[k][a] * J[k][b];
+        H[(size_t)(r0 + a) * np + r0 + b] += s;
+      }
+      double s = 0;
+      for (int k = 0; k < 15; k++) { s += J[k][a] * r[k]; }
+      N.bp[r0 + a] += s;
+    }
+    for (int k = 0; k < 15; k++) N.cost += 0.5 * r[k] * r[k];
+  }
+  // ---- marginalization prior (estimator.cpp:694-700)
+  if (w->prior) {
+    const bvio_prior* p = w->prior;
+    int n = p->n;
+    std::vector<double> r(n), dx(n);
+    prior_eval(p, w, r.data(), dx.data());
+    for (int i = 0; i < n; i++) N.cost += 0.5 * r[i] * r[i];
+    // column -> state index map (-1: constant block, column dropped)
+    std::vector<int> map(n, -1);
+    for (int b = 0; b < p->nblocks; b++) {
+      int kind = p->block_kind[b], loc = blk_local(kind), base = -1;
+      if (kind == BVIO_BLK_POSE) base = 15 * p->block_frame[b];
+      else if (kind == BVIO_BLK_SPEEDBIAS) base = 15 * p->block_frame[b] + 6;
+      else if (kind == BVIO_BLK_EXPOSE) base = ly.est_ex ? ly.ex_off : -1;
+      for (int i = 0; i < loc; i++) map[p->block_idx[b] + i] = base < 0 ? -1 : base + i;
+    }
+    for (int a = 0; a < n; a++) {
+      if (map[a] < 0) continue;
+      const double* ca = p->lin_jac + (size_t)a * n;
+      double s = 0;
+      for (int k = 0; k < n; k++) s += ca[k] * r[k];
+      N.bp[map[a]] += s;
+      for (int b = 0; b < n; b++) {
+        if (map[b] < 0) continue;
+        const double* cb = p->lin_jac + (size_t)b * n;
+        double t = 0;
+        for (int k = 0; k < n; k++) t += ca[k] * cb[k];
+        H[(size_t)map[a] * np + map[b]] += t;
+      }
+    }
+  }
+}
+
+// Solve (H + diag(dd)) [dp; dl] = rhs sign: returns x with (H+D) x = -g   (g = [bp; b])
+bool schur_solve(const bvio_window* w, const Layout& ly, const Normal& N, const double* ddp, const double* ddl,
+                 double* dp, double* dl, std::vector<double>* S_out = nullptr, std::vector<double>* g_out = nullptr) {
+  int np = ly.np, L = ly.L;
+  std::vector<double> S(N.Hpp), g(N.bp);
+  for (int i = 0; i < np; i++) S[(size_t)i * np + i] += ddp ? ddp[i] : 0.0;
+  std::vector<int> idx;
+  std::vector<double> wv;
+  for (int l = 0; l < L; l++) {
+    int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
+    double hl = N.h[l] + (ddl ? ddl[l] : 0.0);
+    if (!(hl > 0)) continue;
+    idx.clear(); wv.clear();
+    for (int k = o0; k < o1; k++)
+      for (int a = 0; a < 6; a++) { idx.push_back(15 * w->obs_frame[k] + a); wv.push_back(N.w[(size_t)6 * k + a]); }
+    if (ly.est_ex)
+      for (int a = 0; a < 6; a++) { idx.push_back(ly.ex_off + a); wv.push_back(N.wex[(size_t)6 * l + a]); }
+    double inv = 1.0 / hl;
+    int m = (int)idx.size();
+    for (int a = 0; a < m; a++) {
+      double wa = wv[a] * inv;
+      for (int b = 0; b < m; b++) S[(size_t)idx[a] * np + idx[b]] -= wa * wv[b];
+      g[idx[a]] -= wa * N.b[l];
+    }
+  }
+  if (S_out) *S_out = S;
+  if (g_out) *g_out = g;
+  if (!dp) return true;
+  std::vector<double> Lc(S);
+  if (!cholesky(Lc.data(), np)) return false;
+  for (int i = 0; i < np; i++) dp[i] = -g[i];
+  chol_solve(Lc.data(), np, dp);
+  for (int l = 0; l < L; l++) {
+    int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
+    double hl = N.h[l] + (ddl ? ddl[l] : 0.0);
+    if (!(hl > 0)) { dl[l] = 0; continue; }
+    double s = N.b[l];
+    for (int k = o0; k < o1; k++)
+      for (int a = 0; a < 6; a++) s += N.w[(size_t)6 * k + a] * dp[15 * w->obs_frame[k] + a];
+    if (ly.est_ex)
+      for (int a = 0; a < 6; a++) s += N.wex[(size_t)6 * l + a] * dp[ly.ex_off + a];
+    dl[l] = -s / hl;
+  }
+  return true;
+}
+
+// x^T H x for the full (undamped) Hessian, x = [xp; xl]
+double quad_form(const bvio_window* w, const Layout& ly, const Normal& N, const double* xp, const double* xl) {
+  int np = ly.np;
+  double q = 0;
+  for (int i = 0; i < np; i++) {
+    double s = 0;
+    for (int j = 0; j < np; j++) s += N.Hpp[(size_t)i * np + j] * xp[j];
+    q += xp[i] * s;
+  }
+  for (int l = 0; l < ly.L; l++) {
+    int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
+    double s = 0;
+    for (int k = o0; k < o1; k++)
+      for (int a = 0; a < 6; a++) s += N.w[(size_t)6 * k + a] * xp[15 * w->obs_frame[k] + a];
+    if (ly.est_ex)
+      for (int a = 0; a < 6; a++) s += N.wex[(size_t)6 * l + a] * xp[ly.ex_off + a];
+    q += 2.0 * xl[l] * s + N.h[l] * xl[l] * xl[l];
+  }
+  return q;
+}
+
+// a5: PoseLocalParameterization::Plus + Euclidean blocks
+void apply_plus(const bvio_window* src, bvio_window* dst, const Layout& ly, const double* dp, const double* dl) {
+  auto pose_plus = [](const double* x, const double* d, double* out) {
+    for (int i = 0; i < 3; i++) out[i] = x[i] + d[i];
+    Q4 q = qnormalized(qmul(q4(x + 3), deltaQ(v3(d + 3))));
+    out[3] = q.x; out[4] = q.y; out[5] = q.z; out[6] = q.w;
+  };
+  for (int i = 0; i < ly.K; i++) {
+    pose_plus(src->para_pose + 7 * i, dp + 15 * i, dst->para_pose + 7 * i);
+    for (int a = 0; a < 9; a++) dst->para_speed_bias[9 * i + a] = src->para_speed_bias[9 * i + a] + dp[15 * i + 6 + a];
+  }
+  if (ly.est_ex) pose_plus(src->para_ex_pose, dp + ly.ex_off, dst->para_ex_pose);
+  else std::memcpy(dst->para_ex_pose, src->para_ex_pose, 7 * sizeof(double));
+  for (int l = 0; l < ly.L; l++) dst->inv_depth[l] = src->inv_depth[l] + dl[l];
+}
+
+struct Scratch {  // candidate state storage
+  std::vector<double> pose, sb, ex, td, inv;
+  bvio_window view;
+  void init(const bvio_window* w) {
+    pose.assign(w->para_pose, w->para_pose + 7 * w->K);
+    sb.assign(w->para_speed_bias, w->para_speed_bias + 9 * w->K);
+    ex.assign(w->para_ex_pose, w->para_ex_pose + 7);
+    td.assign(1, w->para_td ? w->para_td[0] : 0.0);
+    inv.assign(w->inv_depth, w->inv_depth + w->L);
+    view = *w;
+    view.para_pose = pose.data(); view.para_speed_bias = sb.data(); view.para_ex_pose = ex.data();
+    view.para_td = td.data(); view.inv_depth = inv.data();
+  }
+};
+
+void state_norms(const bvio_window* x, const bvio_window* c, const Layout& ly, double* x_norm, double* step_norm) {
+  double xn = 0, sn = 0;
+  auto acc = [&](const double* a, const double* b, int n) {
+    for (int i = 0; i < n; i++) { xn += a[i] * a[i]; sn += (a[i] - b[i]) * (a[i] - b[i]); }
+  };
+  acc(x->para_pose, c->para_pose, 7 * ly.K);
+  acc(x->para_speed_bias, c->para_speed_bias, 9 * ly.K);
+  if (ly.est_ex) acc(x->para_ex_pose, c->para_ex_pose, 7);
+  acc(x->inv_depth, c->inv_depth, ly.L);
+  *x_norm = std::sqrt(xn);
+  *step_norm = std::sqrt(sn);
+}
+
+void copy_state(const bvio_window* src, bvio_window* dst, const Layout& ly) {
+  std::memcpy(dst->para_pose, src->para_pose, sizeof(double) * 7 * ly.K);
+  std::memcpy(dst->para_speed_bias, src->para_speed_bias, sizeof(double) * 9 * ly.K);
+  std::memcpy(dst->para_ex_pose, src->para_ex_pose, sizeof(double) * 7);
+  std::memcpy(dst->inv_depth, src->inv_depth, sizeof(double) * ly.L);
+}
+
+}  // namespace
+
+// ===========================================================================
+// exported
+// ===========================================================================
+extern "C" {
+
+void oracle_projection_factor(const double pts_i[3], const double pts_j[3], const double pose_i[7],
+                              const double pose_j[7], const double ex_pose[7], double inv_dep, double sqrt_info,
+                              double res[2], double* jac_i, double* jac_j, double* jac_ex, double* jac_f) {
+  projection_eval(v3(pts_i), v3(pts_j), v3(pose_i), q4(pose_i + 3), v3(pose_j), q4(pose_j + 3), v3(ex_pose),
+                  q4(ex_pose + 3), inv_dep, sqrt_info, res, jac_i, jac_j, jac_ex, jac_f);
+}
+
+void oracle_imu_sqrt_info(const double cov[225], double sqrt_info[225]) { imu_sqrt_info(cov, sqrt_info); }
+
+void oracle_imu_factor(const bvio_preint* pre, const double G[3], const double pose_i[7], const double sb_i[9],
+                       const double pose_j[7], const double sb_j[9], double res[15], double* jac_pi,
+                       double* jac_sbi, double* jac_pj, double* jac_sbj) {
+  double si[225];
+  imu_sqrt_info(pre->covariance, si);
+  imu_eval(pre, v3(G), pose_i, sb_i, pose_j, sb_j, si, res, jac_pi, jac_sbi, jac_pj, jac_sbj);
+}
+
+void oracle_prior_residual(const bvio_prior* prior, const bvio_window* w, double* res, double* dx) {
+  prior_eval(prior, w, res, dx);
+}
+
+// a3in: IntegrationBase::propagate / midPointIntegration (integration_base.h:54-158)
+void oracle_preint_propagate(bvio_preint* pre, double dt, const double acc_0[3], const double gyr_0[3],
+                             const double acc_1[3], const double gyr_1[3], double acc_n, double gyr_n, double acc_w,
+                             double gyr_w) {
+  V3 a0 = v3(acc_0), g0 = v3(gyr_0), a1 = v3(acc_1), g1 = v3(gyr_1);
+  V3 ba = v3(pre->lin_ba), bg = v3(pre->lin_bg);
+  Q4 dq = q4(pre->delta_q);
+  V3 dpv = v3(pre->delta_p), dv = v3(pre->delta_v);
+  V3 un_acc_0 = qrot(dq, a0 - ba);
+  V3 un_gyr = 0.5 * (g0 + g1) - bg;
+  Q4 rq = qmul(dq, Q4{un_gyr.x * dt / 2, un_gyr.y * dt / 2, un_gyr.z * dt / 2, 1.0});
+  V3 un_acc_1 = qrot(rq, a1 - ba);
+  V3 un_acc = 0.5 * (un_acc_0 + un_acc_1);
+  V3 rp = dpv + dv * dt + 0.5 * un_acc * dt * dt;
+  V3 rv = dv + un_acc * dt;
+  V3 w_x = 0.5 * (g0 + g1) - bg, a0x = a0 - ba, a1x = a1 - ba;
+  M3 Rw = skew(w_x), Ra0 = skew(a0x), Ra1 = skew(a1x), I = eye3();
+  M3 Rq = qmat(dq), Rr = qmat(rq);
+  double F[15][15] = {{0}}, V[15][18] = {{0}};
+  auto putF = [&](int r, int c, const M3& m) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[r + i][c + j] = m[i][j]; };
+  auto putV = [&](int r, int c, const M3& m) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[r + i][c + j] = m[i][j]; };
+  putF(0, 0, I);
+  putF(0, 3, (-0.25 * dt * dt) * (Rq * Ra0) + (-0.25 * dt * dt) * (Rr * Ra1 * (I - dt * Rw)));
+  putF(0, 6, dt * I);
+  putF(0, 9, (-0.25 * dt * dt) * (Rq + Rr));
+  putF(0, 12, (-0.25 * dt * dt * -dt) * (Rr * Ra1));
+  putF(3, 3, I - dt * Rw);
+  putF(3, 12, (-dt) * I);
+  putF(6, 3, (-0.5 * dt) * (Rq * Ra0) + (-0.5 * dt) * (Rr * Ra1 * (I - dt * Rw)));
+  putF(6, 6, I);
+  putF(6, 9, (-0.5 * dt) * (Rq + Rr));
+  putF(6, 12, (-0.5 * dt * -dt) * (Rr * Ra1));
+  putF(9, 9, I);
+  putF(12, 12, I);
+  M3 v03 = (0.25 * dt * dt * 0.5 * dt) * ((-1.0 * Rr) * Ra1);
+  M3 v63 = (0.5 * dt * 0.5 * dt) * ((-1.0 * Rr) * Ra1);
+  putV(0, 0, (0.25 * dt * dt) * Rq);
+  putV(0, 3, v03);
+  putV(0, 6, (0.25 * dt * dt) * Rr);
+  putV(0, 9, v03);
+  putV(3, 3, (0.5 * dt) * I);
+  putV(3, 9, (0.5 * dt) * I);
+  putV(6, 0, (0.5 * dt) * Rq);
+  putV(6, 3, v63);
+  putV(6, 6, (0.5 * dt) * Rr);
+  putV(6, 9, v63);
+  putV(9, 12, dt * I);
+  putV(12, 15, dt * I);
+  double noise[18];
+  for (int i = 0; i < 3; i++) {
+    noise[i] = acc_n * acc_n; noise[3 + i] = gyr_n * gyr_n; noise[6 + i] = acc_n * acc_n;
+    noise[9 + i] = gyr_n * gyr_n; noise[12 + i] = acc_w * acc_w; noise[15 + i] = gyr_w * gyr_w;
+  }
+  double Jn[225], FC[225], Cn[225];
+  for (int i = 0; i < 15; i++)
+    for (int j = 0; j < 15; j++) {
+      double s = 0, t = 0;
+      for (int k = 0; k < 15; k++) { s += F[i][k] * pre->jacobian[k * 15 + j]; t += F[i][k] * pre->covariance[k * 15 + j]; }
+      Jn[i * 15 + j] = s; FC[i * 15 + j] = t;
+    }
+  for (int i = 0; i < 15; i++)
+    for (int j = 0; j < 15; j++) {
+      double s = 0;
+      for (int k = 0; k < 15; k++) s += FC[i * 15 + k] * F[j][k];
+      for (int k = 0; k < 18; k++) s += V[i][k] * noise[k] * V[j][k];
+      Cn[i * 15 + j] = s;
+    }
+  std::memcpy(pre->jacobian, Jn, sizeof Jn);
+  std::memcpy(pre->covariance, Cn, sizeof Cn);
+  Q4 qn = qnormalized(rq);
+  pre->delta_q[0] = qn.x; pre->delta_q[1] = qn.y; pre->delta_q[2] = qn.z; pre->delta_q[3] = qn.w;
+  for (int i = 0; i < 3; i++) { pre->delta_p[i] = rp[i]; pre->delta_v[i] = rv[i]; }
+  pre->sum_dt += dt;
+}
+
+double oracle_cost(const bvio_window* w, const bvio_opts* opts) {
+  ImuCache ic;
+  build_imu_cache(w, ic);
+  return visual_cost(w, opts) + imu_prior_cost(w, opts, ic);
+}
+
+int oracle_linearize(const bvio_window* w, const bvio_opts* opts, double* S, double* g, double* h, double* b,
+                     double* cost) {
+  if (opts->estimate_td) return BVIO_ERR_UNSUPPORTED;
+  Layout ly = layout(w, opts);
+  ImuCache ic;
+  build_imu_cache(w, ic);
+  Normal N;
+  linearize(w, opts, ic, ly, N);
+  std::vector<double> Sv, gv;
+  schur_solve(w, ly, N, nullptr, nullptr, nullptr, nullptr, &Sv, &gv);
+  if (S) std::memcpy(S, Sv.data(), sizeof(double) * ly.np * ly.np);
+  if (g) std::memcpy(g, gv.data(), sizeof(double) * ly.np);
+  if (h) std::memcpy(h, N.h.data(), sizeof(double) * ly.L);
+  if (b) std::memcpy(b, N.b.data(), sizeof(double) * ly.L);
+  if (cost) *cost = N.cost;
+  return BVIO_OK;
+}
+
+int oracle_optimize(bvio_window* w, const bvio_opts* o, bvio_summary* sum) {
+  if (o->estimate_td) return BVIO_ERR_UNSUPPORTED;
+  auto t_start = std::chrono::steady_clock::now();
+  Layout ly = layout(w, o);
+  int np = ly.np, L = ly.L;
+  ImuCache ic;
+  build_imu_cache(w, ic);
+  Normal N;
+  linearize(w, o, ic, ly, N);
+  double cost = N.cost;
+  bvio_summary s{};
+  s.initial_cost = cost;
+  s.termination = BVIO_TERM_MAX_ITERS;
+
+  // Jacobi scaling, computed once at iteration 0: 1/(1+sqrt(diag(J^T J)))
+  std::vector<double> sp(np, 1.0), sl(L, 1.0);
+  if (o->jacobi_scaling) {
+    for (int i = 0; i < np; i++) sp[i] = 1.0 / (1.0 + std::sqrt(N.Hpp[(size_t)i * np + i]));
+    for (int l = 0; l < L; l++) sl[l] = 1.0 / (1.0 + std::sqrt(N.h[l]));
+  }
+  auto gmax = [&]() {
+    double m = 0;
+    for (int i = 0; i < np; i++) m = std::max(m, std::fabs(N.bp[i]));
+    for (int l = 0; l < L; l++) m = std::max(m, std::fabs(N.b[l]));
+    return m;
+  };
+  s.final_gradient_max = gmax();
+  double radius = o->initial_radius, decrease_factor = 2.0, mu = 1e-8;
+  const double min_diag = 1e-6, max_diag = 1e32;
+  Scratch cand;
+  cand.init(w);
+  std::vector<double> dp(np), dl(L), ddp(np), ddl(L);
+  // dogleg state (scaled "y = D x_s" space, x_s = x / scale)
+  bool reuse = false;
+  std::vector<double> gn_p(np), gn_l(L), gr_p(np), gr_l(L), Dp(np), Dl(L);
+  double alpha = 0, dogleg_step_norm = 0;
+  int invalid_run = 0;
+
+  bool done = s.final_gradient_max <= o->gradient_tolerance;
+  if (done) s.termination = BVIO_TERM_GRADIENT_TOL;
+  while (!done && s.iterations < o->max_iters) {
+    if (o->max_time_s > 0) {
+      double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+      if (el >= o->max_time_s) { s.termination = BVIO_TERM_TIME; break; }
+    }
+    s.iterations++;
+    bool valid = true;
+    if (o->strategy == BVIO_STRATEGY_LM) {
+      // LevenbergMarquardtStrategy::ComputeStep in unscaled coordinates:
+      // D_s^2 = clamp(diag(J_s^T J_s))/radius  ->  D^2 = D_s^2 / scale^2
+      for (int i = 0; i < np; i++) {
+        double d = sp[i] * sp[i] * N.Hpp[(size_t)i * np + i];
+        ddp[i] = std::min(std::max(d, min_diag), max_diag) / (radius * sp[i] * sp[i]);
+      }
+      for (int l = 0; l < L; l++) {
+        double d = sl[l] * sl[l] * N.h[l];
+        ddl[l] = std::min(std::max(d, min_diag), max_diag) / (radius * sl[l] * sl[l]);
+      }
+      valid = schur_solve(w, ly, N, ddp.data(), ddl.data(), dp.data(), dl.data());
+    } else {
+      // DoglegStrategy::ComputeStep (TRADITIONAL_DOGLEG)
+      if (!reuse) {
+        for (int i = 0; i < np; i++)
+          Dp[i] = std::sqrt(std::min(std::max(sp[i] * sp[i] * N.Hpp[(size_t)i * np + i], min_diag), max_diag));
+        for (int l = 0; l < L; l++) Dl[l] = std::sqrt(std::min(std::max(sl[l] * sl[l] * N.h[l], min_diag), max_diag));
+        // gradient in y space: D^-1 J_s^T r
+        double gsq = 0;
+        for (int i = 0; i < np; i++) { gr_p[i] = sp[i] * N.bp[i] / Dp[i]; gsq += gr_p[i] * gr_p[i]; }
+        for (int l = 0; l < L; l++) { gr_l[l] = sl[l] * N.b[l] / Dl[l]; gsq += gr_l[l] * gr_l[l]; }
+        // Cauchy point: alpha = |g|^2 / |J_s D^-1 g|^2 ; J_s D^-1 g = J (scale * g / D)
+        std::vector<double> tp(np), tl(L);
+        for (int i = 0; i < np; i++) tp[i] = sp[i] * gr_p[i] / Dp[i];
+        for (int l = 0; l < L; l++) tl[l] = sl[l] * gr_l[l] / Dl[l];
+        alpha = gsq / quad_form(w, ly, N, tp.data(), tl.data());
+        // Gauss-Newton step with mu-regularisation
+        bool ok = false;
+        while (true) {
+          for (int i = 0; i < np; i++) ddp[i] = mu * Dp[i] * Dp[i] / (sp[i] * sp[i]);
+          for (int l = 0; l < L; l++) ddl[l] = mu * Dl[l] * Dl[l] / (sl[l] * sl[l]);
+          ok = schur_solve(w, ly, N, ddp.data(), ddl.data(), dp.data(), dl.data());
+          if (ok) break;
+          mu *= 10.0;
+          if (mu > 1.0) break;
+        }
+        if (!ok) valid = false;
+        // y-space GN step = D * (x / scale)
+        for (int i = 0; i < np; i++) gn_p[i] = Dp[i] * dp[i] / sp[i];
+        for (int l = 0; l < L; l++) gn_l[l] = Dl[l] * dl[l] / sl[l];
+        reuse = true;
+      }
+      if (valid) {
+        double gn_norm = 0, g_norm = 0;
+        for (int i = 0; i < np; i++) { gn_norm += gn_p[i] * gn_p[i]; g_norm += gr_p[i] * gr_p[i]; }
+        for (int l = 0; l < L; l++) { gn_norm += gn_l[l] * gn_l[l]; g_norm += gr_l[l] * gr_l[l]; }
+        gn_norm = std::sqrt(gn_norm); g_norm = std::sqrt(g_norm);
+        double ca, cb;  // step_y = ca * gradient + cb * gn
+        if (gn_norm <= radius) { ca = 0; cb = 1; dogleg_step_norm = gn_norm; }
+        else if (g_norm * alpha >= radius) { ca = -(radius / g_norm); cb = 0; dogleg_step_norm = radius; }
+        else {
+          double b_dot_a = 0;
+          for (int i = 0; i < np; i++) b_dot_a += -alpha * gr_p[i] * gn_p[i];
+          for (int l = 0; l < L; l++) b_dot_a += -alpha * gr_l[l] * gn_l[l];
+          double a_sq = alpha * alpha * g_norm * g_norm;
+          double bma_sq = a_sq - 2 * b_dot_a + gn_norm * gn_norm;
+          double c = b_dot_a - a_sq;
+          double d = std::sqrt(c * c + bma_sq * (radius * radius - a_sq));
+          double beta = (c <= 0) ? (d - c) / bma_sq : (radius * radius - a_sq) / (d + c);
+          ca = -alpha * (1.0 - beta); cb = beta;
+          double nn = 0;
+          for (int i = 0; i < np; i++) { double v = ca * gr_p[i] + cb * gn_p[i]; nn += v * v; }
+          for (int l = 0; l < L; l++) { double v = ca * gr_l[l] + cb * gn_l[l]; nn += v * v; }
+          dogleg_step_norm = std::sqrt(nn);
+        }
+        for (int i = 0; i < np; i++) dp[i] = sp[i] * (ca * gr_p[i] + cb * gn_p[i]) / Dp[i];
+        for (int l = 0; l < L; l++) dl[l] = sl[l] * (ca * gr_l[l] + cb * gn_l[l]) / Dl[l];
+      }
+    }
+    double model_change = 0;
+    if (valid) {
+      double gd = 0;
+      for (int i = 0; i < np; i++) gd += N.bp[i] * dp[i];
+      for (int l = 0; l < L; l++) gd += N.b[l] * dl[l];
+      model_change = -gd - 0.5 * quad_form(w, ly, N, dp.data(), dl.data());
+      if (!(model_change > 0)) valid = false;
+    }
+    if (!valid) {
+      s.num_rejected++;
+      if (++invalid_run >= 5) { s.termination = BVIO_TERM_FAILURE; break; }
+      if (o->strategy == BVIO_STRATEGY_LM) { radius /= decrease_factor; decrease_factor *= 2; }
+      else { mu *= 10.0; reuse = false; }
+      if (radius < 1e-32) { s.termination = BVIO_TERM_FAILURE; break; }
+      continue;
+    }
+    invalid_run = 0;
+    apply_plus(w, &cand.view, ly, dp.data(), dl.data());
+    double cand_cost = visual_cost(&cand.view, o) + imu_prior_cost(&cand.view, o, ic);
+    double x_norm, step_norm;
+    state_norms(w, &cand.view, ly, &x_norm, &step_norm);
+    if (step_norm <= o->parameter_tolerance * (x_norm + o->parameter_tolerance)) {
+      s.termination = BVIO_TERM_PARAMETER_TOL; break;
+    }
+    double cost_change = cost - cand_cost;
+    if (std::fabs(cost_change) <= o->function_tolerance * cost) { s.termination = BVIO_TERM_FUNCTION_TOL; break; }
+    double rho = cost_change / model_change;
+    if (getenv("ORACLE_TRACE")) fprintf(stderr, "it %d cost %.9g cand %.9g model %.3g rho %.3g radius %.3g mu %.1g stepn %.3g gmax %.3g\n", s.iterations, cost, cand_cost, model_change, rho, radius, mu, dogleg_step_norm, s.final_gradient_max);
+    if (std::isfinite(cand_cost) && rho > o->min_relative_decrease) {
+      s.num_accepted++;
+      copy_state(&cand.view, w, ly);
+      cost = cand_cost;
+      linearize(w, o, ic, ly, N);
+      s.final_gradient_max = gmax();
+      if (s.final_gradient_max <= o->gradient_tolerance) { s.termination = BVIO_TERM_GRADIENT_TOL; break; }
+      if (o->strategy == BVIO_STRATEGY_LM) {
+        double t = 2.0 * rho - 1.0;
+        radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - t * t * t));
+        decrease_factor = 2.0;
+      } else {
+        if (rho < 0.25) radius *= 0.5;
+        if (rho > 0.75) radius = std::max(radius, 3.0 * dogleg_step_norm);
+        mu = std::max(1e-8, 2.0 * mu / 10.0);
+        reuse = false;
+      }
+    } else {
+      s.num_rejected++;
+      if (o->strategy == BVIO_STRATEGY_LM) { radius /= decrease_factor; decrease_factor *= 2; }
+      else { radius *= 0.5; reuse = true; }
+      if (radius < 1e-32) { s.termination = BVIO_TERM_FAILURE; break; }
+    }
+  }
+  s.final_cost = cost;
+  s.final_radius = radius;
+  s.device_ms = 0;
+  if (sum) *sum = s;
+  return std::isfinite(cost) ? BVIO_OK : BVIO_ERR_NUMERIC;
+}
+
+// a8: Estimator::double2vector gauge re-anchoring (estimator.cpp:521-555)
+static V3 R2ypr(const M3& R) {  // utility.h:69-85 (degrees)
+  V3 n{R[0][0], R[1][0], R[2][0]}, o{R[0][1], R[1][1], R[2][1]}, a{R[0][2], R[1][2], R[2][2]};
+  double y = std::atan2(n.y, n.x);
+  double p = std::atan2(-n.z, n.x * std::cos(y) + n.y * std::sin(y));
+  double r = std::atan2(a.x * std::sin(y) - a.y * std::cos(y), -o.x * std::sin(y) + o.y * std::cos(y));
+  return V3{y, p, r} / M_PI * 180.0;
+}
+static M3 ypr2R(V3 ypr) {  // utility.h:87-112
+  double y = ypr.x / 180.0 * M_PI, p = ypr.y / 180.0 * M_PI, r = ypr.z / 180.0 * M_PI;
+  M3 Rz = {{{std::cos(y), -std::sin(y), 0}, {std::sin(y), std::cos(y), 0}, {0, 0, 1}}};
+  M3 Ry = {{{std::cos(p), 0., std::sin(p)}, {0., 1., 0.}, {-std::sin(p), 0., std::cos(p)}}};
+  M3 Rx = {{{1., 0., 0.}, {0., std::cos(r), -std::sin(r)}, {0., std::sin(r), std::cos(r)}}};
+  return Rz * Ry * Rx;
+}
+void oracle_double2vector(const double pre_pose0[7], int K, double* para_pose, double* para_speed_bias) {
+  M3 Rs0 = qmat(q4(pre_pose0 + 3));
+  V3 origin_R0 = R2ypr(Rs0), origin_P0 = v3(pre_pose0);
+  M3 R00 = qmat(q4(para_pose + 3));
+  V3 origin_R00 = R2ypr(R00);
+  double y_diff = origin_R0.x - origin_R00.x;
+  M3 rot_diff = ypr2R(V3{y_diff, 0, 0});
+  if (std::fabs(std::fabs(origin_R0.y) - 90) < 1.0 || std::fabs(std::fabs(origin_R00.y) - 90) < 1.0)
+    rot_diff = Rs0 * transpose(R00);
+  V3 p0 = v3(para_pose);
+  for (int i = 0; i < K; i++) {
+    M3 R = rot_diff * qmat(qnormalized(q4(para_pose + 7 * i + 3)));
+    V3 P = rot_diff * (v3(para_pose + 7 * i) - p0) + origin_P0;
+    V3 Vv = rot_diff * v3(para_speed_bias + 9 * i);
+    Q4 q = qfrommat(R);
+    double* pp = para_pose + 7 * i;
+    pp[0] = P.x; pp[1] = P.y; pp[2] = P.z; pp[3] = q.x; pp[4] = q.y; pp[5] = q.z; pp[6] = q.w;
+    para_speed_bias[9 * i] = Vv.x; para_speed_bias[9 * i + 1] = Vv.y; para_speed_bias[9 * i + 2] = Vv.z;
+  }
+}
+
+}  // extern "C"

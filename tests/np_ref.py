@@ -1,0 +1,410 @@
+"""Independent numpy/scipy restatement of the reference hot path (second opinion for
+the C++ oracle; SURVEY.md section 8c "Oracle plan").  Written with rotation
+matrices and dense linear algebra on purpose, so that it shares no code structure
+with oracle/*.cpp.  Reference citations as in oracle/ba_oracle.cpp / sel_oracle.cpp.
+"""
+import numpy as np
+
+
+def skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0.0]])
+
+
+def R_of(q):  # q = x y z w, unit
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def qmul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def qinv(q):
+    return np.array([-q[0], -q[1], -q[2], q[3]]) / np.dot(q, q)
+
+
+def Qleft(q):  # w-first 4x4, utility.h:49-57
+    x, y, z, w = q
+    m = np.zeros((4, 4))
+    m[0, 0] = w
+    m[0, 1:] = -np.array([x, y, z])
+    m[1:, 0] = [x, y, z]
+    m[1:, 1:] = w * np.eye(3) + skew([x, y, z])
+    return m
+
+
+def Qright(q):
+    x, y, z, w = q
+    m = np.zeros((4, 4))
+    m[0, 0] = w
+    m[0, 1:] = -np.array([x, y, z])
+    m[1:, 0] = [x, y, z]
+    m[1:, 1:] = w * np.eye(3) - skew([x, y, z])
+    return m
+
+
+def pose_plus(x, d):
+    out = np.array(x, float).copy()
+    out[:3] += d[:3]
+    q = qmul(x[3:], np.array([d[3] / 2, d[4] / 2, d[5] / 2, 1.0]))
+    out[3:] = q / np.linalg.norm(q)
+    return out
+
+
+# ---------------------------------------------------------------------------
+def projection(pts_i, pts_j, pose_i, pose_j, ex, inv_dep, sqrt_info=460.0 / 1.5, jac=True):
+    Pi, Ri = pose_i[:3], R_of(pose_i[3:])
+    Pj, Rj = pose_j[:3], R_of(pose_j[3:])
+    tic, ric = ex[:3], R_of(ex[3:])
+    pci = np.array([pts_i[0], pts_i[1], 1.0]) / inv_dep
+    pii = ric @ pci + tic
+    pw = Ri @ pii + Pi
+    pij = Rj.T @ (pw - Pj)
+    pcj = ric.T @ (pij - tic)
+    dep = pcj[2]
+    r = sqrt_info * (pcj[:2] / dep - np.asarray(pts_j[:2]))
+    if not jac:
+        return r
+    red = sqrt_info * np.array([[1 / dep, 0, -pcj[0] / dep ** 2], [0, 1 / dep, -pcj[1] / dep ** 2]])
+    Ji = red @ np.hstack([ric.T @ Rj.T, ric.T @ Rj.T @ Ri @ -skew(pii)])
+    Jj = red @ np.hstack([ric.T @ -Rj.T, ric.T @ skew(pij)])
+    tmp_r = ric.T @ Rj.T @ Ri @ ric
+    Jex = red @ np.hstack([ric.T @ (Rj.T @ Ri - np.eye(3)),
+                           -tmp_r @ skew(pci) + skew(tmp_r @ pci) + skew(ric.T @ (Rj.T @ (Ri @ tic + Pi - Pj) - tic))])
+    Jf = red @ (tmp_r @ np.array([pts_i[0], pts_i[1], 1.0])) * -1.0 / inv_dep ** 2
+    return r, Ji, Jj, Jex, Jf
+
+
+def unpack_preint(row):
+    return dict(delta_p=row[0:3], delta_q=row[3:7], delta_v=row[7:10], lin_ba=row[10:13], lin_bg=row[13:16],
+                sum_dt=row[16], jacobian=row[17:242].reshape(15, 15), covariance=row[242:467].reshape(15, 15))
+
+
+def imu_sqrt_info(cov):
+    return np.linalg.cholesky(np.linalg.inv(cov)).T
+
+
+def imu(pre, G, pose_i, sb_i, pose_j, sb_j, jac=True):
+    Pi, Qi, Pj, Qj = pose_i[:3], pose_i[3:], pose_j[:3], pose_j[3:]
+    Vi, Bai, Bgi = sb_i[:3], sb_i[3:6], sb_i[6:9]
+    Vj, Baj, Bgj = sb_j[:3], sb_j[3:6], sb_j[6:9]
+    J = pre["jacobian"]
+    dp_dba, dp_dbg, dq_dbg, dv_dba, dv_dbg = J[0:3, 9:12], J[0:3, 12:15], J[3:6, 12:15], J[6:9, 9:12], J[6:9, 12:15]
+    dba, dbg = Bai - pre["lin_ba"], Bgi - pre["lin_bg"]
+    th = dq_dbg @ dbg
+    cq = qmul(pre["delta_q"], np.array([th[0] / 2, th[1] / 2, th[2] / 2, 1.0]))
+    cv = pre["delta_v"] + dv_dba @ dba + dv_dbg @ dbg
+    cp = pre["delta_p"] + dp_dba @ dba + dp_dbg @ dbg
+    dt = pre["sum_dt"]
+    Ri = R_of(Qi)
+    G = np.asarray(G)
+    r = np.zeros(15)
+    r[0:3] = Ri.T @ (0.5 * G * dt * dt + Pj - Pi - Vi * dt) - cp
+    r[3:6] = 2 * qmul(qinv(cq), qmul(qinv(Qi), Qj))[:3]
+    r[6:9] = Ri.T @ (G * dt + Vj - Vi) - cv
+    r[9:12] = Baj - Bai
+    r[12:15] = Bgj - Bgi
+    si = imu_sqrt_info(pre["covariance"])
+    if not jac:
+        return si @ r
+    Jpi = np.zeros((15, 6))
+    Jpi[0:3, 0:3] = -Ri.T
+    Jpi[0:3, 3:6] = skew(Ri.T @ (0.5 * G * dt * dt + Pj - Pi - Vi * dt))
+    Jpi[3:6, 3:6] = -(Qleft(qmul(qinv(Qj), Qi)) @ Qright(cq))[1:, 1:]
+    Jpi[6:9, 3:6] = skew(Ri.T @ (G * dt + Vj - Vi))
+    Jsi = np.zeros((15, 9))
+    Jsi[0:3, 0:3] = -Ri.T * dt
+    Jsi[0:3, 3:6] = -dp_dba
+    Jsi[0:3, 6:9] = -dp_dbg
+    Jsi[3:6, 6:9] = -Qleft(qmul(qmul(qinv(Qj), Qi), pre["delta_q"]))[1:, 1:] @ dq_dbg
+    Jsi[6:9, 0:3] = -Ri.T
+    Jsi[6:9, 3:6] = -dv_dba
+    Jsi[6:9, 6:9] = -dv_dbg
+    Jsi[9:12, 3:6] = -np.eye(3)
+    Jsi[12:15, 6:9] = -np.eye(3)
+    Jpj = np.zeros((15, 6))
+    Jpj[0:3, 0:3] = Ri.T
+    Jpj[3:6, 3:6] = Qleft(qmul(qmul(qinv(cq), qinv(Qi)), Qj))[1:, 1:]
+    Jsj = np.zeros((15, 9))
+    Jsj[6:9, 0:3] = Ri.T
+    Jsj[9:12, 3:6] = np.eye(3)
+    Jsj[12:15, 6:9] = np.eye(3)
+    return si @ r, si @ Jpi, si @ Jsi, si @ Jpj, si @ Jsj
+
+
+def prior_residual(prior, w):
+    n = prior["n"]
+    dx = np.zeros(n)
+    off = 0
+    for kind, frame, idx in zip(prior["block_kind"], prior["block_frame"], prior["block_idx"]):
+        if kind == 0:
+            x, x0 = w.para_pose[frame], prior["x0"][off:off + 7]
+            dx[idx:idx + 3] = x[:3] - x0[:3]
+            dq = qmul(qinv(x0[3:]), x[3:])
+            v = 2 * dq[:3]
+            dx[idx + 3:idx + 6] = v if dq[3] >= 0 else -v
+            off += 7
+        elif kind == 1:
+            dx[idx:idx + 9] = w.para_speed_bias[frame] - prior["x0"][off:off + 9]
+            off += 9
+        elif kind == 2:
+            x, x0 = w.para_ex_pose, prior["x0"][off:off + 7]
+            dx[idx:idx + 3] = x[:3] - x0[:3]
+            dq = qmul(qinv(x0[3:]), x[3:])
+            v = 2 * dq[:3]
+            dx[idx + 3:idx + 6] = v if dq[3] >= 0 else -v
+            off += 7
+        else:
+            dx[idx] = w.para_td[0] - prior["x0"][off]
+            off += 1
+    Jm = np.asarray(prior["lin_jac"]).reshape(n, n, order="F")
+    return prior["lin_res"] + Jm @ dx, dx, Jm
+
+
+def full_system(w, G=(0, 0, 9.81007), sqrt_info=460.0 / 1.5, cauchy_a=1.0):
+    """Dense weighted Jacobian/residual of the whole window in local coordinates
+    [15*K pose/speed-bias | L inverse depths]; extrinsics fixed.  Returns J, r, cost."""
+    K, L = w.K, len(w.inv_depth)
+    npar = 15 * K
+    rows, res = [], []
+    cost = 0.0
+    for l in range(L):
+        o0, o1 = w.lm_obs_offset[l], w.lm_obs_offset[l + 1]
+        fi = w.obs_frame[o0]
+        for k in range(o0 + 1, o1):
+            fj = w.obs_frame[k]
+            r, Ji, Jj, _, Jf = projection(w.obs_xy[o0], w.obs_xy[k], w.para_pose[fi], w.para_pose[fj],
+                                          w.para_ex_pose, w.inv_depth[l], sqrt_info)
+            s = r @ r
+            rho0 = cauchy_a ** 2 * np.log1p(s / cauchy_a ** 2)
+            rho1 = 1.0 / (1.0 + s / cauchy_a ** 2)
+            cost += 0.5 * rho0
+            sr = np.sqrt(rho1)
+            blk = np.zeros((2, npar + L))
+            blk[:, 15 * fi:15 * fi + 6] += sr * Ji
+            blk[:, 15 * fj:15 * fj + 6] += sr * Jj
+            blk[:, npar + l] = sr * Jf
+            rows.append(blk)
+            res.append(sr * r)
+    for j in range(1, K):
+        pre = unpack_preint(w.preint[j])
+        if pre["sum_dt"] > 10.0:
+            continue
+        i = j - 1
+        r, Jpi, Jsi, Jpj, Jsj = imu(pre, G, w.para_pose[i], w.para_speed_bias[i], w.para_pose[j], w.para_speed_bias[j])
+        blk = np.zeros((15, npar + L))
+        blk[:, 15 * i:15 * i + 6] = Jpi
+        blk[:, 15 * i + 6:15 * i + 15] = Jsi
+        blk[:, 15 * j:15 * j + 6] = Jpj
+        blk[:, 15 * j + 6:15 * j + 15] = Jsj
+        rows.append(blk)
+        res.append(r)
+        cost += 0.5 * r @ r
+    if w.prior is not None:
+        r, dx, Jm = prior_residual(w.prior, w)
+        n = w.prior["n"]
+        blk = np.zeros((n, npar + L))
+        for kind, frame, idx in zip(w.prior["block_kind"], w.prior["block_frame"], w.prior["block_idx"]):
+            if kind == 0:
+                blk[:, 15 * frame:15 * frame + 6] = Jm[:, idx:idx + 6]
+            elif kind == 1:
+                blk[:, 15 * frame + 6:15 * frame + 15] = Jm[:, idx:idx + 9]
+        rows.append(blk)
+        res.append(r)
+        cost += 0.5 * r @ r
+    return np.vstack(rows), np.concatenate(res), cost
+
+
+def reduced_system(w, **kw):
+    J, r, cost = full_system(w, **kw)
+    npar = 15 * w.K
+    Hf = J.T @ J
+    gf = J.T @ r
+    Hpp, Hpl, hl = Hf[:npar, :npar], Hf[:npar, npar:], np.diag(Hf[npar:, npar:])
+    S = Hpp - (Hpl / hl) @ Hpl.T
+    g = gf[:npar] - (Hpl / hl) @ gf[npar:]
+    return S, g, hl, gf[npar:], cost
+
+
+def apply_delta(w, d):
+    """x (+) d in local coordinates; returns a new window copy."""
+    K, L = w.K, len(w.inv_depth)
+    c = w.copy()
+    for i in range(K):
+        c.para_pose[i] = pose_plus(w.para_pose[i], d[15 * i:15 * i + 6])
+        c.para_speed_bias[i] = w.para_speed_bias[i] + d[15 * i + 6:15 * i + 15]
+    c.inv_depth = w.inv_depth + d[15 * K:15 * K + L]
+    return c
+
+
+def solve_gn(w, iters=60, tol=1e-13, **kw):
+    """Plain damped Gauss-Newton on the dense system (completely different solver from
+    the oracle's LM/dogleg): pins the FIXED POINT the other solvers must reach."""
+    lam = 1e-4
+    J, r, cost = full_system(w, **kw)
+    for _ in range(iters):
+        H = J.T @ J
+        g = J.T @ r
+        if np.max(np.abs(g)) < tol:
+            break
+        while True:
+            d = -np.linalg.solve(H + lam * np.diag(np.diag(H)), g)
+            c = apply_delta(w, d)
+            Jc, rc, costc = full_system(c, **kw)
+            if costc < cost or lam > 1e8:
+                break
+            lam *= 10
+        w, J, r, cost = c, Jc, rc, costc
+        lam = max(lam / 10, 1e-12)
+    return w, cost, np.max(np.abs(J.T @ r))
+
+
+# ---------------------------------------------------------------------------
+# selector
+# ---------------------------------------------------------------------------
+def slerp(a, t, b):
+    d = float(np.dot(a, b))
+    ad = abs(d)
+    if ad >= 1.0 - np.finfo(float).eps:
+        s0, s1 = 1.0 - t, t
+    else:
+        th = np.arccos(ad)
+        s0, s1 = np.sin((1 - t) * th) / np.sin(th), np.sin(t * th) / np.sin(th)
+    if d < 0:
+        s1 = -s1
+    return s0 * a + s1 * b
+
+
+def linear_imu_matrices(Qi, Qj, nr, dImu, accVar, biasVar):
+    Nij, Mij = np.zeros((3, 3)), np.zeros((3, 3))
+    c11 = c12 = 0.0
+    for i in range(nr):
+        R = R_of(slerp(Qi, i / nr, Qj))
+        jkh = nr - i - 0.5
+        Nij += jkh * R
+        Mij += R
+        c11 += jkh * jkh
+        c12 += jkh
+    cov = np.zeros((9, 9))
+    I = np.eye(3)
+    cov[0:3, 0:3] = I * nr * c11 * dImu ** 4 * accVar
+    cov[0:3, 3:6] = I * c12 * dImu ** 3 * accVar
+    cov[3:6, 0:3] = cov[0:3, 3:6].T
+    cov[3:6, 3:6] = I * nr * dImu ** 2 * accVar
+    cov[6:9, 6:9] = I * nr * biasVar
+    A = -np.eye(9)
+    A[0:3, 3:6] = -I * nr * dImu
+    A[0:3, 6:9] = Nij * dImu ** 2
+    A[3:6, 6:9] = Mij * dImu
+    return np.linalg.inv(cov), A, cov
+
+
+def omega_imu(p):
+    H = p.H
+    D = 9 * (H + 1)
+    Om = np.zeros((D, D))
+    for h in range(1, H + 1):
+        W, A, _ = linear_imu_matrices(p.horizon_quat[h - 1], p.horizon_quat[h], p.nr_imu, p.delta_imu,
+                                      p.acc_var, p.acc_bias_var)
+        a, b = 9 * (h - 1), 9 * h
+        Om[a:a + 9, a:a + 9] += A.T @ W @ A
+        Om[a:a + 9, b:b + 9] += A.T @ W
+        Om[b:b + 9, a:a + 9] += (A.T @ W).T
+        Om[b:b + 9, b:b + 9] += W
+    Om[:9, :9] += np.eye(9)
+    return Om
+
+
+def space_to_plane(cam, P):
+    mx, my = P[0] / P[2], P[1] / P[2]
+    k1, k2, p1, p2 = cam["k1"], cam["k2"], cam["p1"], cam["p2"]
+    rho2 = mx * mx + my * my
+    rad = k1 * rho2 + k2 * rho2 * rho2
+    dx = mx * rad + 2 * p1 * mx * my + p2 * (rho2 + 2 * mx * mx)
+    dy = my * rad + 2 * p2 * mx * my + p1 * (rho2 + 2 * my * my)
+    return np.array([cam["fx"] * (mx + dx) + cam["cx"], cam["fy"] * (my + dy) + cam["cy"]])
+
+
+def feature_C(p, xy):
+    """Compact 3H x 3H information block of one feature (None when numVisible == 1)."""
+    H = p.H
+    Ric = R_of(p.q_ic)
+    R1 = R_of(p.horizon_quat[1])
+    t1 = p.horizon_pos[1] + R1 @ p.t_ic
+    Rwc1 = R1 @ Ric
+    if len(p.cloud_depth) == 0:
+        d = 1.0
+    else:
+        d2 = ((p.cloud_xy - xy) ** 2).sum(1)
+        d = p.cloud_depth[int(np.argmin(d2))]
+    f = np.array([xy[0], xy[1], 1.0])
+    f = f / np.linalg.norm(f) * d
+    pell = t1 + Rwc1 @ f
+    Ch = [np.zeros((3, 3)) for _ in range(H)]
+    nvis = 1
+    for h in range(2, H + 1):
+        Rh = R_of(p.horizon_quat[h])
+        th = p.horizon_pos[h] + Rh @ p.t_ic
+        Rwch = Rh @ Ric
+        u = Rwch.T @ (pell - th)
+        u = u / np.linalg.norm(u)
+        px = space_to_plane(p.cam, u)
+        uu, vv = int(np.round(px[0])), int(np.round(px[1]))
+        if not (0 <= uu < p.cam["width"] and 0 <= vv < p.cam["height"]):
+            continue
+        B = skew(u) @ (Rwch @ Ric).T      # the reference's double q_IC (feature_selector.cpp:304)
+        Ch[h - 1] = B.T @ B
+        nvis += 1
+    if nvis == 1:
+        return None
+    B = skew(f / np.linalg.norm(f)) @ (Rwc1 @ Ric).T
+    Ch[0] = B.T @ B
+    W = np.linalg.inv(sum(Ch))
+    G = np.vstack(Ch)
+    Cm = -G @ W @ G.T
+    for h in range(H):
+        Cm[3 * h:3 * h + 3, 3 * h:3 * h + 3] += Ch[h]
+    return Cm
+
+
+def pos_index(H):
+    return np.concatenate([9 * h + np.arange(3) for h in range(1, H + 1)])
+
+
+def greedy_select(p, exhaustive=True):
+    """Greedy log-det selection on dense matrices with numpy slogdet (every candidate
+    scored every round).  Returns ids, values, per-round margins."""
+    H = p.H
+    D = 9 * (H + 1)
+    P = pos_index(H)
+    M = omega_imu(p)
+    for xy in p.used_xy:
+        Cm = feature_C(p, xy)
+        if Cm is not None:
+            M[np.ix_(P, P)] += Cm
+    Cs = [feature_C(p, xy) for xy in p.cand_xy]
+    alive = [i for i, c in enumerate(Cs) if c is not None]
+    ids, vals, margins = [], [], []
+    for _ in range(p.kappa):
+        best, bi, second = -1.0, -1, -np.inf
+        for i in alive:
+            A = M.copy()
+            A[np.ix_(P, P)] += p.cand_prob[i] * Cs[i]
+            v = np.linalg.slogdet(A)[1]
+            if v > best:
+                second, best, bi = best, v, i
+            elif v > second:
+                second = v
+        if bi < 0:
+            continue
+        M[np.ix_(P, P)] += p.cand_prob[bi] * Cs[bi]
+        alive.remove(bi)
+        ids.append(int(p.cand_id[bi]))
+        vals.append(best)
+        margins.append(best - second)
+    return ids, vals, margins
