@@ -1,0 +1,105 @@
+// ba.h -- device-side data layout of a batch of sliding windows in HBM, shared by the host
+// API (bvio_api.cu) and the BA kernels (ba_kernels.cu).
+//
+// State layout (DESIGN.md "Data layout in HBM"): reduced system dimension np = 15*K, frame-major
+// 15-blocks [dp(3) dtheta(3) dv(3) dba(3) dbg(3)].  Visual factors only touch the 6 pose dims of
+// each frame, so the landmark-parallel Schur kernel produces a compact 6K x 6K block matrix.
+#pragma once
+#include "common.cuh"
+
+namespace bvio {
+
+constexpr int IMU_REC = 288;      // doubles per compact IMU record (287 used, padded to 16 B multiple)
+// compact IMU record offsets (doubles)
+constexpr int IR_DP = 0, IR_DQ = 3, IR_DV = 7, IR_BA = 10, IR_BG = 13, IR_DT = 16, IR_DPDBA = 17, IR_DPDBG = 26,
+              IR_DQDBG = 35, IR_DVDBA = 44, IR_DVDBG = 53, IR_SQ = 62;  // sqrt_info 15x15 row-major at 62..286
+constexpr int PREINT_DOUBLES = 467;   // sizeof(bvio_preint)/8
+constexpr int IMU_OUT = 496;          // per IMU factor: J^T J lower packed (465) + J^T r (30) + cost (1)
+
+constexpr int PRIOR_MAXB = 32;    // max kept parameter blocks in a prior
+constexpr int BA_THREADS = 256;   // linearize / cost kernels
+constexpr int SOLVE_THREADS = 512;
+
+struct BaCtrl {                   // per-window LM state, lives in HBM
+  double cost;                    // cost at X[cur]
+  double cand_cost;
+  double radius, decrease_factor;
+  double model_pose;              // pose part of the model cost change
+  double gmax;                    // max |gradient| at X[cur]
+  double initial_cost;
+  double rho;
+  int cur;                        // which of the two state buffers is current
+  int done, termination;
+  int iterations, accepted, rejected;
+  int first;                      // 1 until the first linearization has fixed the Jacobi scaling
+  int solve_ok;                   // a step was computed this pass (Cholesky succeeded)
+  int invalid_run;
+  int stepped;                    // this pass computed a step that the cost kernel must judge
+  unsigned int ticket;            // CTAs of the cost kernel that finished (last one decides)
+  int pad;
+};
+
+// per-(window,tile) output record of ba_linearize, in doubles:
+//   [0 .. NPb*36)   S blocks (frame p >= q), 6x6 row-major each: visual H_pp minus the Schur term
+//   then 6K: reduced gradient, 6K: unreduced gradient, 6K: diag of visual H_pp (no Schur term)
+//   then 4 scalars: cost, max |b_l|, pad, pad
+__host__ __device__ inline int tile_rec_doubles(int K) { return (K * (K + 1) / 2) * 36 + 18 * K + 4; }
+// per-(window,tile) output record of ba_cost: cost, model_lm, step2, x2
+constexpr int COST_REC = 4;
+
+struct BaBatch {                  // all pointers are device pointers
+  int B, K, np, T;                // windows, keyframes, reduced dimension, landmark tiles per window
+  int total_L, total_obs, nmax;   // nmax = max prior dimension (row stride of the prior arrays)
+  int nwarps_lin;                 // warps per CTA in ba_linearize (bounded by shared memory)
+  int undamped;                   // debug: linearize without LM damping (bvio_debug_linearize)
+  // solver options
+  int max_iters, jacobi_scaling;
+  double sqrt_info, cauchy_a, G[3];
+  double function_tolerance, gradient_tolerance, parameter_tolerance, initial_radius, min_relative_decrease;
+  // structure
+  const int* lm_base;             // [B+1] first global landmark of each window
+  const int* lm_off;              // [total_L+1] CSR: global observation offsets
+  const int* obs_frame;           // [total_obs]
+  const double2* obs_xy;          // [total_obs]
+  // state, double buffered
+  double* pose[2];                // [B][K][7]
+  double* sb[2];                  // [B][K][9]
+  double* ex;                     // [B][7] (constant: estimate_extrinsic = 0 on the device path)
+  double* invd[2];                // [total_L]
+  const double* pose0; const double* sb0; const double* invd0;   // uploaded initial state (for reset)
+  double* pose_out; double* sb_out; double* invd_out;            // final state gathered from X[cur]
+  // IMU
+  const double* preint_raw;       // [B][K][467] as uploaded (bvio_preint)
+  double* imu;                    // [B][K][IMU_REC] compact records (entry 0 unused); sum_dt > 10 => skipped
+  double* imu_out;                // [B][K][IMU_OUT]
+  // prior
+  const int* pr_n; const int* pr_nb;       // [B]
+  const int* pr_kind; const int* pr_frame; const int* pr_idx;   // [B][PRIOR_MAXB]
+  const double* pr_x0;            // [B][PRIOR_MAXB*9]
+  const double* pr_jac;           // [B][nmax*nmax] column-major n x n
+  const double* pr_res;           // [B][nmax]
+  double* pr_H;                   // [B][nmax*nmax] J^T J (symmetric)
+  int* pr_map;                    // [B][nmax] prior column -> reduced state index (-1: constant block)
+  double* pr_out;                 // [B][nmax+1] J^T r at X[cur], then 0.5 |r|^2
+  // linearization products
+  double* h; double* b; double* sl2;   // [total_L]
+  double* w;                      // [total_obs][6]
+  double* tile_out;               // [B][T][tile_rec_doubles(K)]
+  double* cost_out;               // [B][T+1][COST_REC]
+  double* delta_p;                // [B][np]
+  double* scale_p;                // [B][np] Jacobi scaling of the pose/speed-bias columns
+  double* dbg_S; double* dbg_g;   // [B][np*np], [B][np] (debug linearize only, else null)
+  BaCtrl* ctrl;                   // [B]
+};
+
+// launchers (ba_kernels.cu); all asynchronous on `st`; return number of kernels launched
+int ba_launch_prepare(const BaBatch& bt, cudaStream_t st);
+int ba_launch_reset(const BaBatch& bt, cudaStream_t st);
+int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step);
+int ba_launch_finish(const BaBatch& bt, cudaStream_t st);
+size_t ba_linearize_smem_bytes(int K, int nwarps);
+int ba_pick_linearize_warps(int K);
+size_t ba_solve_smem_bytes(int K);
+int ba_configure(void);   // cudaFuncSetAttribute for the big-smem kernels; returns cudaError_t
+
+}  // namespace bvio

@@ -1,0 +1,429 @@
+// ba_api.cu -- C-ABI of the bundle-adjustment path (include/bvio.h): context, batch upload,
+// solve, download.  Host code only packs the caller's arrays into one pinned slab, issues one
+// H2D copy, launches the kernels of ba_kernels.cu and copies the result back; there is no CPU
+// compute path (Estimator::optimization(), vins_estimator/src/estimator.cpp:661-814).
+#include "ba.h"
+#include "ctx.h"
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+using namespace bvio;
+
+struct bvio_batch {
+  BaBatch bt;
+  Slab slab;
+  bool from_cache = false;
+  size_t in_bytes = 0;                 // [0, in_bytes): inputs, mirrored on the host
+  size_t out_off = 0, out_bytes = 0;   // [out_off, out_off+out_bytes): outputs, mirrored on the host
+  size_t o_pose_out = 0, o_sb_out = 0, o_invd_out = 0, o_ctrl = 0;
+  std::vector<int> lm_base;
+  cudaGraphExec_t graph = nullptr;
+  bool use_graph = true;
+  int launches_per_solve = 0;
+  int debug = 0;
+};
+
+extern "C" {
+
+int bvio_abi_version(void) { return BVIO_ABI_VERSION; }
+
+void bvio_default_opts(bvio_opts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof *o);
+  o->max_iters = 8;               // config/euroc/euroc_config.yaml:55
+  o->max_time_s = 0.0;
+  o->estimate_extrinsic = 0;      // euroc_config.yaml:25
+  o->estimate_td = 0;             // euroc_config.yaml:72
+  o->focal_length = 460.0;        // parameters.h:13
+  o->cauchy_a = 1.0;              // estimator.cpp:666
+  o->G[0] = 0; o->G[1] = 0; o->G[2] = 9.81007;   // euroc_config.yaml:63
+  o->TR = 0.0; o->ROW = 480.0;
+  o->function_tolerance = 1e-6;   // Ceres defaults (estimator.cpp:794-806 leaves them untouched)
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->initial_radius = 1e4;
+  o->min_relative_decrease = 1e-3;
+  o->strategy = BVIO_STRATEGY_LM;
+  o->jacobi_scaling = 1;
+}
+
+int bvio_create(int device, bvio_ctx** out) {
+  if (!out) return BVIO_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return BVIO_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return BVIO_ERR_CUDA;
+  bvio_ctx* c = new (std::nothrow) bvio_ctx();
+  if (!c) return BVIO_ERR_INVALID;
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return BVIO_ERR_CUDA; }
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      ba_configure() != 0) {
+    delete c;
+    return BVIO_ERR_CUDA;
+  }
+  *out = c;
+  return BVIO_OK;
+}
+
+void bvio_sel_ctx_destroy(bvio_ctx* ctx);   // sel_api.cu
+
+void bvio_destroy(bvio_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  bvio_sel_ctx_destroy(ctx);
+  ctx->ba_cache.release();
+  ctx->sel_cache.release();
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* bvio_last_error(const bvio_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* bvio_stream(bvio_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t bvio_launch_count(const bvio_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+static int validate(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* o, int K0) {
+  if (!w || !o) return fail(ctx, BVIO_ERR_INVALID, "null window/opts");
+  if (o->estimate_extrinsic || o->estimate_td)
+    return fail(ctx, BVIO_ERR_UNSUPPORTED, "estimate_extrinsic / estimate_td are not implemented on the device path");
+  if (o->strategy != BVIO_STRATEGY_LM)
+    return fail(ctx, BVIO_ERR_UNSUPPORTED, "device path implements BVIO_STRATEGY_LM only");
+  if (w->K < 2 || w->K > BVIO_KMAX) return fail(ctx, BVIO_ERR_INVALID, "K out of range [2,16]");
+  if (w->K != K0) return fail(ctx, BVIO_ERR_INVALID, "all windows of a batch must have the same K");
+  if (w->L < 0 || !w->para_pose || !w->para_speed_bias || !w->para_ex_pose || !w->preint)
+    return fail(ctx, BVIO_ERR_INVALID, "null state / preint arrays");
+  if (w->L > 0 && (!w->inv_depth || !w->lm_obs_offset || !w->obs_frame || !w->obs_xy))
+    return fail(ctx, BVIO_ERR_INVALID, "null landmark arrays");
+  if (w->L > 0 && w->lm_obs_offset[0] != 0) return fail(ctx, BVIO_ERR_INVALID, "lm_obs_offset[0] != 0");
+  for (int l = 0; l < w->L; l++) {
+    int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1], n = o1 - o0;
+    if (n < 2 || n > BVIO_KMAX) return fail(ctx, BVIO_ERR_INVALID, "landmark needs 2..16 observations");
+    for (int k = o0; k < o1; k++) {
+      int f = w->obs_frame[k];
+      if (f < 0 || f >= w->K || (k > o0 && f <= w->obs_frame[k - 1]))
+        return fail(ctx, BVIO_ERR_INVALID, "obs_frame must be strictly ascending within [0,K)");
+    }
+  }
+  if (w->prior) {
+    const bvio_prior* p = w->prior;
+    if (p->n < 0 || p->n > 256 || p->nblocks < 0 || p->nblocks > PRIOR_MAXB)
+      return fail(ctx, BVIO_ERR_INVALID, "prior dimension out of range");
+    for (int b = 0; b < p->nblocks; b++) {
+      int kind = p->block_kind[b], loc = kind == BVIO_BLK_SPEEDBIAS ? 9 : (kind == BVIO_BLK_TD ? 1 : 6);
+      if (kind < 0 || kind > 3 || p->block_idx[b] < 0 || p->block_idx[b] + loc > p->n)
+        return fail(ctx, BVIO_ERR_INVALID, "prior block out of range");
+      if ((kind == BVIO_BLK_POSE || kind == BVIO_BLK_SPEEDBIAS) && (p->block_frame[b] < 0 || p->block_frame[b] >= w->K))
+        return fail(ctx, BVIO_ERR_INVALID, "prior block frame out of range");
+    }
+  }
+  return BVIO_OK;
+}
+
+static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_opts* o, bool use_cache, int debug,
+                       bvio_batch** out) {
+  if (!ctx || !ws || B < 1 || !o || !out) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  const int K = ws[0].K;
+  int total_L = 0, total_obs = 0, nmax = 1, maxL = 0;
+  for (int b = 0; b < B; b++) {
+    int rc = validate(ctx, ws + b, o, K);
+    if (rc) return rc;
+    total_L += ws[b].L;
+    total_obs += ws[b].L ? ws[b].lm_obs_offset[ws[b].L] : 0;
+    maxL = std::max(maxL, ws[b].L);
+    if (ws[b].prior) nmax = std::max(nmax, ws[b].prior->n);
+  }
+  bvio_batch* bb = new (std::nothrow) bvio_batch();
+  if (!bb) return fail(ctx, BVIO_ERR_INVALID, "out of host memory");
+  BaBatch& bt = bb->bt;
+  memset(&bt, 0, sizeof bt);
+  bt.B = B; bt.K = K; bt.np = 15 * K; bt.total_L = total_L; bt.total_obs = total_obs; bt.nmax = nmax;
+  bt.nwarps_lin = ba_pick_linearize_warps(K);
+  int T = (maxL + 4 * bt.nwarps_lin - 1) / (4 * bt.nwarps_lin);
+  int Tcap = std::max(1, (2 * ctx->sm_count + B - 1) / B);
+  T = std::max(1, std::min(std::min(T, Tcap), 32));
+  bt.T = T;
+  bt.undamped = debug;
+  bt.max_iters = o->max_iters; bt.jacobi_scaling = o->jacobi_scaling;
+  bt.sqrt_info = o->focal_length / 1.5;   // estimator.cpp:17
+  bt.cauchy_a = o->cauchy_a;
+  for (int i = 0; i < 3; i++) bt.G[i] = o->G[i];
+  bt.function_tolerance = o->function_tolerance; bt.gradient_tolerance = o->gradient_tolerance;
+  bt.parameter_tolerance = o->parameter_tolerance; bt.initial_radius = o->initial_radius;
+  bt.min_relative_decrease = o->min_relative_decrease;
+  bb->debug = debug;
+
+  // ---- carve: inputs | outputs | scratch
+  Carver cv;
+  const size_t D = sizeof(double), I = sizeof(int);
+  size_t o_lm_base = cv.take((B + 1) * I), o_lm_off = cv.take((total_L + 1) * I), o_obs_frame = cv.take(total_obs * I);
+  size_t o_obs_xy = cv.take((size_t)total_obs * 2 * D);
+  size_t o_pose0 = cv.take((size_t)B * K * 7 * D), o_sb0 = cv.take((size_t)B * K * 9 * D), o_ex = cv.take((size_t)B * 7 * D);
+  size_t o_invd0 = cv.take((size_t)total_L * D);
+  size_t o_preint = cv.take((size_t)B * K * PREINT_DOUBLES * D);
+  size_t o_pr_n = cv.take(B * I), o_pr_nb = cv.take(B * I);
+  size_t o_pr_kind = cv.take((size_t)B * PRIOR_MAXB * I), o_pr_frame = cv.take((size_t)B * PRIOR_MAXB * I);
+  size_t o_pr_idx = cv.take((size_t)B * PRIOR_MAXB * I);
+  size_t o_pr_x0 = cv.take((size_t)B * PRIOR_MAXB * 9 * D);
+  size_t o_pr_jac = cv.take((size_t)B * nmax * nmax * D), o_pr_res = cv.take((size_t)B * nmax * D);
+  bb->in_bytes = cv.off;
+  bb->out_off = cv.off;
+  bb->o_pose_out = cv.take((size_t)B * K * 7 * D);
+  bb->o_sb_out = cv.take((size_t)B * K * 9 * D);
+  bb->o_invd_out = cv.take((size_t)total_L * D);
+  bb->o_ctrl = cv.take((size_t)B * sizeof(BaCtrl));
+  bb->out_bytes = cv.off - bb->out_off;
+  const size_t h_bytes = cv.off;
+  size_t o_pose[2], o_sb[2], o_invd[2];
+  for (int k = 0; k < 2; k++) {
+    o_pose[k] = cv.take((size_t)B * K * 7 * D); o_sb[k] = cv.take((size_t)B * K * 9 * D);
+    o_invd[k] = cv.take((size_t)total_L * D);
+  }
+  size_t o_imu = cv.take((size_t)B * K * IMU_REC * D), o_imu_out = cv.take((size_t)B * K * IMU_OUT * D);
+  size_t o_pr_H = cv.take((size_t)B * nmax * nmax * D), o_pr_map = cv.take((size_t)B * nmax * I);
+  size_t o_pr_out = cv.take((size_t)B * (nmax + 1) * D);
+  size_t o_h = cv.take((size_t)total_L * D), o_b = cv.take((size_t)total_L * D), o_sl2 = cv.take((size_t)total_L * D);
+  size_t o_w = cv.take((size_t)total_obs * 6 * D);
+  size_t o_tile = cv.take((size_t)B * T * tile_rec_doubles(K) * D);
+  size_t o_cost = cv.take((size_t)B * (T + 1) * COST_REC * D);
+  size_t o_dp = cv.take((size_t)B * bt.np * D), o_sp = cv.take((size_t)B * bt.np * D);
+  size_t o_dbgS = 0, o_dbgg = 0;
+  if (debug) { o_dbgS = cv.take((size_t)B * bt.np * bt.np * D); o_dbgg = cv.take((size_t)B * bt.np * D); }
+  const size_t d_bytes = cv.off;
+
+  cudaError_t ce;
+  if (use_cache) ce = slab_acquire(ctx->ba_cache, ctx->ba_cache_busy, d_bytes, h_bytes, bb->slab, bb->from_cache);
+  else {
+    bool dummy_busy = true;
+    Slab none;
+    ce = slab_acquire(none, dummy_busy, d_bytes, h_bytes, bb->slab, bb->from_cache);
+  }
+  if (ce != cudaSuccess) { delete bb; return fail(ctx, BVIO_ERR_CUDA, std::string("slab alloc: ") + cudaGetErrorString(ce)); }
+  char* d = bb->slab.d;
+  char* h = bb->slab.h;
+
+  // ---- pack the host mirror
+  int* h_lm_base = (int*)(h + o_lm_base);
+  int* h_lm_off = (int*)(h + o_lm_off);
+  int* h_obs_frame = (int*)(h + o_obs_frame);
+  double* h_obs_xy = (double*)(h + o_obs_xy);
+  double* h_pose0 = (double*)(h + o_pose0);
+  double* h_sb0 = (double*)(h + o_sb0);
+  double* h_ex = (double*)(h + o_ex);
+  double* h_invd0 = (double*)(h + o_invd0);
+  double* h_pre = (double*)(h + o_preint);
+  int* h_pr_n = (int*)(h + o_pr_n);
+  int* h_pr_nb = (int*)(h + o_pr_nb);
+  int* h_pr_kind = (int*)(h + o_pr_kind);
+  int* h_pr_frame = (int*)(h + o_pr_frame);
+  int* h_pr_idx = (int*)(h + o_pr_idx);
+  double* h_pr_x0 = (double*)(h + o_pr_x0);
+  double* h_pr_jac = (double*)(h + o_pr_jac);
+  double* h_pr_res = (double*)(h + o_pr_res);
+  bb->lm_base.resize(B + 1);
+  int lb = 0, ob = 0;
+  for (int b = 0; b < B; b++) {
+    const bvio_window& w = ws[b];
+    h_lm_base[b] = lb; bb->lm_base[b] = lb;
+    int nobs = w.L ? w.lm_obs_offset[w.L] : 0;
+    for (int l = 0; l < w.L; l++) h_lm_off[lb + l] = ob + w.lm_obs_offset[l];
+    if (nobs) {
+      memcpy(h_obs_frame + ob, w.obs_frame, nobs * I);
+      memcpy(h_obs_xy + (size_t)2 * ob, w.obs_xy, (size_t)nobs * 2 * D);
+    }
+    memcpy(h_pose0 + (size_t)b * K * 7, w.para_pose, (size_t)K * 7 * D);
+    memcpy(h_sb0 + (size_t)b * K * 9, w.para_speed_bias, (size_t)K * 9 * D);
+    memcpy(h_ex + (size_t)b * 7, w.para_ex_pose, 7 * D);
+    if (w.L) memcpy(h_invd0 + lb, w.inv_depth, (size_t)w.L * D);
+    memcpy(h_pre + (size_t)b * K * PREINT_DOUBLES, w.preint, (size_t)K * sizeof(bvio_preint));
+    h_pr_n[b] = 0; h_pr_nb[b] = 0;
+    if (w.prior) {
+      const bvio_prior* p = w.prior;
+      h_pr_n[b] = p->n; h_pr_nb[b] = p->nblocks;
+      const double* x0 = p->x0;
+      for (int k = 0; k < p->nblocks; k++) {
+        int kind = p->block_kind[k], gs = kind == BVIO_BLK_SPEEDBIAS ? 9 : (kind == BVIO_BLK_TD ? 1 : 7);
+        h_pr_kind[b * PRIOR_MAXB + k] = kind;
+        h_pr_frame[b * PRIOR_MAXB + k] = p->block_frame[k];
+        h_pr_idx[b * PRIOR_MAXB + k] = p->block_idx[k];
+        double* dst = h_pr_x0 + (size_t)(b * PRIOR_MAXB + k) * 9;
+        for (int i = 0; i < 9; i++) dst[i] = i < gs ? x0[i] : 0.0;
+        x0 += gs;
+      }
+      memcpy(h_pr_jac + (size_t)b * nmax * nmax, p->lin_jac, (size_t)p->n * p->n * D);
+      memcpy(h_pr_res + (size_t)b * nmax, p->lin_res, (size_t)p->n * D);
+    }
+    lb += w.L; ob += nobs;
+  }
+  h_lm_base[B] = lb; bb->lm_base[B] = lb;
+  h_lm_off[total_L] = ob;
+
+  bt.lm_base = (const int*)(d + o_lm_base); bt.lm_off = (const int*)(d + o_lm_off);
+  bt.obs_frame = (const int*)(d + o_obs_frame); bt.obs_xy = (const double2*)(d + o_obs_xy);
+  bt.pose0 = (const double*)(d + o_pose0); bt.sb0 = (const double*)(d + o_sb0); bt.ex = (double*)(d + o_ex);
+  bt.invd0 = (const double*)(d + o_invd0); bt.preint_raw = (const double*)(d + o_preint);
+  bt.pr_n = (const int*)(d + o_pr_n); bt.pr_nb = (const int*)(d + o_pr_nb);
+  bt.pr_kind = (const int*)(d + o_pr_kind); bt.pr_frame = (const int*)(d + o_pr_frame); bt.pr_idx = (const int*)(d + o_pr_idx);
+  bt.pr_x0 = (const double*)(d + o_pr_x0); bt.pr_jac = (const double*)(d + o_pr_jac); bt.pr_res = (const double*)(d + o_pr_res);
+  bt.pose_out = (double*)(d + bb->o_pose_out); bt.sb_out = (double*)(d + bb->o_sb_out);
+  bt.invd_out = (double*)(d + bb->o_invd_out); bt.ctrl = (BaCtrl*)(d + bb->o_ctrl);
+  for (int k = 0; k < 2; k++) {
+    bt.pose[k] = (double*)(d + o_pose[k]); bt.sb[k] = (double*)(d + o_sb[k]); bt.invd[k] = (double*)(d + o_invd[k]);
+  }
+  bt.imu = (double*)(d + o_imu); bt.imu_out = (double*)(d + o_imu_out);
+  bt.pr_H = (double*)(d + o_pr_H); bt.pr_map = (int*)(d + o_pr_map); bt.pr_out = (double*)(d + o_pr_out);
+  bt.h = (double*)(d + o_h); bt.b = (double*)(d + o_b); bt.sl2 = (double*)(d + o_sl2); bt.w = (double*)(d + o_w);
+  bt.tile_out = (double*)(d + o_tile); bt.cost_out = (double*)(d + o_cost);
+  bt.delta_p = (double*)(d + o_dp); bt.scale_p = (double*)(d + o_sp);
+  bt.dbg_S = debug ? (double*)(d + o_dbgS) : nullptr;
+  bt.dbg_g = debug ? (double*)(d + o_dbgg) : nullptr;
+
+  cudaError_t e = cudaMemcpyAsync(d, h, bb->in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) { ctx->launches += ba_launch_prepare(bt, ctx->stream); e = cudaGetLastError(); }
+  if (e != cudaSuccess) {
+    slab_release(bb->slab, ctx->ba_cache_busy, bb->from_cache);
+    delete bb;
+    return fail(ctx, BVIO_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e));
+  }
+  *out = bb;
+  return BVIO_OK;
+}
+
+static int enqueue_solve(bvio_ctx* ctx, bvio_batch* bb, cudaStream_t st) {
+  int n = 0;
+  n += ba_launch_reset(bb->bt, st);
+  for (int it = 0; it < bb->bt.max_iters; it++) n += ba_launch_iteration(bb->bt, st, true);
+  n += ba_launch_iteration(bb->bt, st, false);   // final linearization: gradient norm of the result
+  n += ba_launch_finish(bb->bt, st);
+  return n;
+}
+
+extern "C" {
+
+int bvio_batch_upload(bvio_ctx* ctx, const bvio_window* windows, int32_t B, const bvio_opts* opts, bvio_batch** out) {
+  return upload_impl(ctx, windows, B, opts, false, 0, out);
+}
+
+int bvio_batch_solve(bvio_ctx* ctx, bvio_batch* bb) {
+  if (!ctx || !bb) return fail(ctx, BVIO_ERR_INVALID, "null batch");
+  cudaSetDevice(ctx->device);
+  BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (bb->use_graph) {
+    if (!bb->graph) {
+      cudaGraph_t g = nullptr;
+      BVIO_CUDA_OK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      bb->launches_per_solve = enqueue_solve(ctx, bb, ctx->stream);
+      BVIO_CUDA_OK(ctx, cudaStreamEndCapture(ctx->stream, &g));
+      BVIO_CUDA_OK(ctx, cudaGraphInstantiate(&bb->graph, g, 0));
+      cudaGraphDestroy(g);
+      // the event recorded before the capture is still valid; re-record so ev0 directly precedes the launch
+      BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    }
+    BVIO_CUDA_OK(ctx, cudaGraphLaunch(bb->graph, ctx->stream));
+    ctx->launches += bb->launches_per_solve;
+  } else {
+    ctx->launches += enqueue_solve(ctx, bb, ctx->stream);
+  }
+  BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  BVIO_CUDA_OK(ctx, cudaGetLastError());
+  return BVIO_OK;
+}
+
+int bvio_batch_download(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, bvio_summary* summaries) {
+  if (!ctx || !bb) return fail(ctx, BVIO_ERR_INVALID, "null batch");
+  cudaSetDevice(ctx->device);
+  char* ho = bb->slab.h + bb->out_off;
+  BVIO_CUDA_OK(ctx, cudaMemcpyAsync(ho, bb->slab.d + bb->out_off, bb->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  BVIO_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  const BaBatch& bt = bb->bt;
+  const double* pose = (const double*)(bb->slab.h + bb->o_pose_out);
+  const double* sb = (const double*)(bb->slab.h + bb->o_sb_out);
+  const double* invd = (const double*)(bb->slab.h + bb->o_invd_out);
+  const BaCtrl* ctrl = (const BaCtrl*)(bb->slab.h + bb->o_ctrl);
+  int rc = BVIO_OK;
+  for (int b = 0; b < bt.B; b++) {
+    if (windows) {
+      bvio_window& w = windows[b];
+      memcpy(w.para_pose, pose + (size_t)b * bt.K * 7, (size_t)bt.K * 7 * sizeof(double));
+      memcpy(w.para_speed_bias, sb + (size_t)b * bt.K * 9, (size_t)bt.K * 9 * sizeof(double));
+      int L = bb->lm_base[b + 1] - bb->lm_base[b];
+      if (L) memcpy(w.inv_depth, invd + bb->lm_base[b], (size_t)L * sizeof(double));
+    }
+    const BaCtrl& c = ctrl[b];
+    if (summaries) {
+      bvio_summary& s = summaries[b];
+      s.iterations = c.iterations; s.num_accepted = c.accepted; s.num_rejected = c.rejected;
+      s.termination = c.termination; s.initial_cost = c.initial_cost; s.final_cost = c.cost;
+      s.final_radius = c.radius; s.final_gradient_max = c.gmax; s.device_ms = ms;
+    }
+    if (!(c.cost == c.cost) || c.cost > 1.79e308) rc = BVIO_ERR_NUMERIC;
+  }
+  if (rc) return fail(ctx, rc, "non-finite cost");
+  return BVIO_OK;
+}
+
+void bvio_batch_free(bvio_ctx* ctx, bvio_batch* bb) {
+  if (!bb) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (bb->graph) cudaGraphExecDestroy(bb->graph);
+  bool dummy = true;
+  slab_release(bb->slab, ctx ? ctx->ba_cache_busy : dummy, bb->from_cache);
+  delete bb;
+}
+
+int bvio_optimize_batch(bvio_ctx* ctx, bvio_window* windows, int32_t B, const bvio_opts* opts, bvio_summary* summaries) {
+  bvio_batch* bb = nullptr;
+  int rc = upload_impl(ctx, windows, B, opts, true, 0, &bb);
+  if (rc) return rc;
+  bb->use_graph = false;   // one-shot: direct launches beat capture + instantiate
+  rc = bvio_batch_solve(ctx, bb);
+  if (rc == BVIO_OK) rc = bvio_batch_download(ctx, bb, windows, summaries);
+  bvio_batch_free(ctx, bb);
+  return rc;
+}
+
+int bvio_optimize(bvio_ctx* ctx, bvio_window* window, const bvio_opts* opts, bvio_summary* summary) {
+  return bvio_optimize_batch(ctx, window, 1, opts, summary);
+}
+
+int bvio_debug_linearize(bvio_ctx* ctx, const bvio_window* window, const bvio_opts* opts, double* S, double* g,
+                         double* h, double* b, double* cost) {
+  bvio_batch* bb = nullptr;
+  int rc = upload_impl(ctx, window, 1, opts, false, 1, &bb);
+  if (rc) return rc;
+  const BaBatch& bt = bb->bt;
+  ctx->launches += ba_launch_reset(bt, ctx->stream);
+  ctx->launches += ba_launch_iteration(bt, ctx->stream, true);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && S) e = cudaMemcpy(S, bt.dbg_S, sizeof(double) * bt.np * bt.np, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && g) e = cudaMemcpy(g, bt.dbg_g, sizeof(double) * bt.np, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && h && bt.total_L) e = cudaMemcpy(h, bt.h, sizeof(double) * bt.total_L, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && b && bt.total_L) e = cudaMemcpy(b, bt.b, sizeof(double) * bt.total_L, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && cost) {
+    BaCtrl c;
+    e = cudaMemcpy(&c, bt.ctrl, sizeof c, cudaMemcpyDeviceToHost);
+    *cost = c.cost;
+  }
+  bvio_batch_free(ctx, bb);
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("debug_linearize: ") + cudaGetErrorString(e));
+  return BVIO_OK;
+}
+
+int bvio_marginalize(bvio_ctx* ctx, const bvio_window*, const bvio_opts*, int32_t, bvio_prior_out*) {
+  return fail(ctx, BVIO_ERR_UNSUPPORTED, "bvio_marginalize: not implemented yet (SURVEY.md row f1)");
+}
+
+}  // extern "C"

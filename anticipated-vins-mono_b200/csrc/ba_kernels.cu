@@ -1,0 +1,1045 @@
+// ba_kernels.cu -- sliding-window bundle adjustment on sm_100a (FP64, no tensor cores: the
+// blocks are 2x6 / 6x6 / 15x15 and irregular).  Replaces what ceres::Solve does for the problem
+// Estimator::optimization() builds (vins_estimator/src/estimator.cpp:661-809):
+//
+//   ba_prepare    once per upload: IMU sqrt-information (imu_factor.h:64), prior J^T J
+//   ba_linearize  ProjectionFactor::Evaluate (projection_factor.cpp:21-121) + Cauchy corrector
+//                 (marginalization_factor.cpp:37-68) one warp per landmark (lane = factor), per-landmark
+//                 J^T J / J^T r reduction and Schur elimination of the inverse depth; one extra CTA per
+//                 window evaluates the IMU factors (imu_factor.h:19-179) and the marginalization prior
+//                 (marginalization_factor.cpp:333-381)
+//   ba_solve      one CTA per window: assemble the 15K x 15K reduced system in shared memory, LM damping
+//                 (Ceres LevenbergMarquardtStrategy), blocked Cholesky, back substitution
+//   ba_cost       back-substitute the inverse depths, PoseLocalParameterization::Plus
+//                 (pose_local_parameterization.cpp:3-18), residual-only cost at the candidate, and the
+//                 trust-region accept/reject decision (last CTA of the window)
+//
+// All reductions run in a fixed order: results are bit-reproducible run to run.
+#include "ba.h"
+#include <float.h>
+
+namespace bvio {
+
+// local block-pair table: pair index -> (a, b), a >= b, for up to BVIO_KMAX observations/frames
+__constant__ unsigned char c_triA[BVIO_KMAX * (BVIO_KMAX + 1) / 2];
+__constant__ unsigned char c_triB[BVIO_KMAX * (BVIO_KMAX + 1) / 2];
+// packed-lower decode for 30x30 IMU blocks
+__constant__ unsigned char c_tri30A[465];
+__constant__ unsigned char c_tri30B[465];
+
+constexpr int FR = 12;            // per-frame staged state: R (9, row-major) + P (3)
+constexpr int STG = 29;           // per-factor staging stride (28 used; odd => conflict-free)
+
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
+
+__device__ __forceinline__ void tile_range(const BaBatch& bt, int w, int t, int& l0, int& l1) {
+  int base = bt.lm_base[w], Lw = bt.lm_base[w + 1] - base;
+  int tl = (Lw + bt.T - 1) / bt.T;
+  l0 = base + min(Lw, t * tl);
+  l1 = base + min(Lw, (t + 1) * tl);
+}
+
+// stage R,P of the K frames of window w (state buffer `buf`) and the extrinsics into shared memory
+__device__ __forceinline__ void stage_frames(const BaBatch& bt, int w, const double* pose, double* sFr, double* sEx) {
+  for (int k = threadIdx.x; k <= bt.K; k += blockDim.x) {
+    const double* p = (k < bt.K) ? pose + (size_t)(w * bt.K + k) * 7 : bt.ex + (size_t)w * 7;
+    double* o = (k < bt.K) ? sFr + k * FR : sEx;
+    qmat(q4{p[3], p[4], p[5], p[6]}, o);
+    o[9] = p[0]; o[10] = p[1]; o[11] = p[2];
+  }
+}
+
+struct ProjGeom {   // what both the residual-only and the full evaluation need
+  d3 pimu_i, pimu_j, pcj;
+};
+
+// residual of one ProjectionFactor (projection_factor.cpp:35-49) with staged rotation matrices
+__device__ __forceinline__ ProjGeom proj_geom(const double* Fi, const double* Fj, const double* Ex, double xi,
+                                              double yi, double lam) {
+  ProjGeom g;
+  double il = 1.0 / lam;
+  d3 pci{xi * il, yi * il, il};
+  d3 tic{Ex[9], Ex[10], Ex[11]};
+  g.pimu_i = mv3(Ex, pci) + tic;
+  d3 pw = mv3(Fi, g.pimu_i) + d3{Fi[9], Fi[10], Fi[11]};
+  g.pimu_j = mtv3(Fj, pw - d3{Fj[9], Fj[10], Fj[11]});
+  g.pcj = mtv3(Ex, g.pimu_j - tic);
+  return g;
+}
+
+__device__ __forceinline__ void cauchy(double a, double s, double& rho0, double& rho1) {
+  double bb = a * a, c = 1.0 / bb;
+  double sum = 1.0 + s * c, inv = 1.0 / sum;
+  rho0 = bb * log(sum);
+  rho1 = fmax(DBL_MIN, inv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// IMU factor: raw residual (15) and, optionally, raw Jacobian (15 x 30, columns [pose_i sb_i pose_j sb_j]
+// in local 6/9/6/9 coordinates) before whitening.  One thread per factor.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put3(double* J, int r0, int c0, const double* m, double s) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) J[(r0 + i) * 30 + c0 + j] = s * m[i * 3 + j];
+}
+__device__ __forceinline__ void skew3(d3 v, double* m) {
+  m[0] = 0; m[1] = -v.z; m[2] = v.y; m[3] = v.z; m[4] = 0; m[5] = -v.x; m[6] = -v.y; m[7] = v.x; m[8] = 0;
+}
+// (Qleft(a) * Qright(b)).bottomRightCorner<3,3>()  (utility.h:49-67)
+__device__ __forceinline__ void qleft_qright_br(q4 a, q4 b, double* out) {
+  double la[9], rb[9], sa[9], sb[9];
+  skew3(d3{a.x, a.y, a.z}, sa);
+  skew3(d3{b.x, b.y, b.z}, sb);
+#pragma unroll
+  for (int i = 0; i < 9; i++) { la[i] = sa[i]; rb[i] = -sb[i]; }
+  la[0] += a.w; la[4] += a.w; la[8] += a.w;
+  rb[0] += b.w; rb[4] += b.w; rb[8] += b.w;
+  mm3(la, rb, out);
+  const double av[3] = {a.x, a.y, a.z}, bv[3] = {b.x, b.y, b.z};
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) out[i * 3 + j] -= av[i] * bv[j];
+}
+__device__ __forceinline__ void qleft_br(q4 a, double* out) {
+  skew3(d3{a.x, a.y, a.z}, out);
+  out[0] += a.w; out[4] += a.w; out[8] += a.w;
+}
+
+__device__ void imu_raw(const double* rec, const double* G, const double* pi, const double* sbi, const double* pj,
+                        const double* sbj, double* r /*[15]*/, double* J /*[15*30] zeroed, or null*/) {
+  d3 Pi{pi[0], pi[1], pi[2]}, Pj{pj[0], pj[1], pj[2]};
+  q4 Qi{pi[3], pi[4], pi[5], pi[6]}, Qj{pj[3], pj[4], pj[5], pj[6]};
+  d3 Vi{sbi[0], sbi[1], sbi[2]}, Bai{sbi[3], sbi[4], sbi[5]}, Bgi{sbi[6], sbi[7], sbi[8]};
+  d3 Vj{sbj[0], sbj[1], sbj[2]}, Baj{sbj[3], sbj[4], sbj[5]}, Bgj{sbj[6], sbj[7], sbj[8]};
+  d3 g{G[0], G[1], G[2]};
+  double dt = rec[IR_DT];
+  d3 dba = Bai - d3{rec[IR_BA], rec[IR_BA + 1], rec[IR_BA + 2]};
+  d3 dbg = Bgi - d3{rec[IR_BG], rec[IR_BG + 1], rec[IR_BG + 2]};
+  q4 dq{rec[IR_DQ], rec[IR_DQ + 1], rec[IR_DQ + 2], rec[IR_DQ + 3]};
+  // IntegrationBase::evaluate (integration_base.h:160-186)
+  d3 th = mv3(rec + IR_DQDBG, dbg);
+  q4 cdq = qmul(dq, q4{th.x / 2, th.y / 2, th.z / 2, 1.0});
+  d3 cdv = d3{rec[IR_DV], rec[IR_DV + 1], rec[IR_DV + 2]} + mv3(rec + IR_DVDBA, dba) + mv3(rec + IR_DVDBG, dbg);
+  d3 cdp = d3{rec[IR_DP], rec[IR_DP + 1], rec[IR_DP + 2]} + mv3(rec + IR_DPDBA, dba) + mv3(rec + IR_DPDBG, dbg);
+  q4 Qii = qinv(Qi);
+  d3 tp = qrot(Qii, (0.5 * dt * dt) * g + Pj - Pi - dt * Vi);
+  d3 tv = qrot(Qii, dt * g + Vj - Vi);
+  d3 rp = tp - cdp, rv = tv - cdv;
+  q4 qe = qmul(qinv(cdq), qmul(Qii, Qj));
+  r[0] = rp.x; r[1] = rp.y; r[2] = rp.z;
+  r[3] = 2 * qe.x; r[4] = 2 * qe.y; r[5] = 2 * qe.z;
+  r[6] = rv.x; r[7] = rv.y; r[8] = rv.z;
+  r[9] = Baj.x - Bai.x; r[10] = Baj.y - Bai.y; r[11] = Baj.z - Bai.z;
+  r[12] = Bgj.x - Bgi.x; r[13] = Bgj.y - Bgi.y; r[14] = Bgj.z - Bgi.z;
+  if (!J) return;
+  double RiT[9], m[9], m2[9];
+  qmat(Qii, RiT);
+  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  // pose_i: columns 0..5
+  put3(J, 0, 0, RiT, -1.0);
+  skew3(tp, m); put3(J, 0, 3, m, 1.0);
+  qleft_qright_br(qmul(qinv(Qj), Qi), cdq, m); put3(J, 3, 3, m, -1.0);
+  skew3(tv, m); put3(J, 6, 3, m, 1.0);
+  // speed-bias_i: columns 6..14
+  put3(J, 0, 6, RiT, -dt);
+  put3(J, 0, 9, rec + IR_DPDBA, -1.0);
+  put3(J, 0, 12, rec + IR_DPDBG, -1.0);
+  qleft_br(qmul(qmul(qinv(Qj), Qi), dq), m); mm3(m, rec + IR_DQDBG, m2); put3(J, 3, 12, m2, -1.0);
+  put3(J, 6, 6, RiT, -1.0);
+  put3(J, 6, 9, rec + IR_DVDBA, -1.0);
+  put3(J, 6, 12, rec + IR_DVDBG, -1.0);
+  put3(J, 9, 9, I3, -1.0);
+  put3(J, 12, 12, I3, -1.0);
+  // pose_j: columns 15..20
+  put3(J, 0, 15, RiT, 1.0);
+  qleft_br(qmul(qmul(qinv(cdq), Qii), Qj), m); put3(J, 3, 18, m, 1.0);
+  // speed-bias_j: columns 21..29
+  put3(J, 6, 21, RiT, 1.0);
+  put3(J, 9, 24, I3, 1.0);
+  put3(J, 12, 27, I3, 1.0);
+}
+
+// MarginalizationFactor::Evaluate residual: dx per kept block, r = r0 + J dx. Block-cooperative.
+// sdx, sr: shared [nmax]. Returns nothing; caller syncs.
+__device__ void prior_residual(const BaBatch& bt, int w, const double* pose, const double* sb, double* sdx,
+                               double* sr) {
+  int n = bt.pr_n[w], nb = bt.pr_nb[w];
+  for (int bidx = threadIdx.x; bidx < nb; bidx += blockDim.x) {
+    int kind = bt.pr_kind[w * PRIOR_MAXB + bidx], fr = bt.pr_frame[w * PRIOR_MAXB + bidx];
+    int idx = bt.pr_idx[w * PRIOR_MAXB + bidx];
+    const double* x0 = bt.pr_x0 + (size_t)(w * PRIOR_MAXB + bidx) * 9;
+    const double* x = kind == 0 ? pose + (size_t)(w * bt.K + fr) * 7
+                      : kind == 1 ? sb + (size_t)(w * bt.K + fr) * 9 : bt.ex + (size_t)w * 7;
+    if (kind == 1) {
+      for (int i = 0; i < 9; i++) sdx[idx + i] = x[i] - x0[i];
+    } else if (kind == 3) {
+      sdx[idx] = 0.0;   // td is constant on the device path
+    } else {
+      for (int i = 0; i < 3; i++) sdx[idx + i] = x[i] - x0[i];
+      q4 dq = qmul(qinv(q4{x0[3], x0[4], x0[5], x0[6]}), q4{x[3], x[4], x[5], x[6]});
+      double s = (dq.w >= 0) ? 2.0 : -2.0;
+      sdx[idx + 3] = s * dq.x; sdx[idx + 4] = s * dq.y; sdx[idx + 5] = s * dq.z;
+    }
+  }
+  __syncthreads();
+  const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double s = bt.pr_res[(size_t)w * bt.nmax + i];
+    for (int k = 0; k < n; k++) s += Jc[(size_t)k * n + i] * sdx[k];
+    sr[i] = s;
+  }
+  __syncthreads();
+}
+
+// =============================================================================================
+// prepare
+// =============================================================================================
+__global__ void __launch_bounds__(BA_THREADS) ba_prepare_kernel(BaBatch bt) {
+  const int w = blockIdx.x, K = bt.K;
+  __shared__ double sU[8][15 * 16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- compact IMU records; sqrt_info = LLT(cov^-1).matrixL().transpose() (imu_factor.h:64), computed
+  //      as the inverse of the upper "reverse Cholesky" factor of cov (cov = U~ U~^T  =>
+  //      cov^-1 = U~^-T U~^-1, and U~^-1 is upper triangular with positive diagonal = L^T by uniqueness).
+  for (int j = 1 + warp; j < K; j += 8) {
+    const double* raw = bt.preint_raw + (size_t)(w * K + j) * PREINT_DOUBLES;
+    double* rec = bt.imu + (size_t)(w * K + j) * IMU_REC;
+    for (int i = lane; i < 17; i += 32) rec[i] = raw[i];   // delta_p,q,v, lin_ba, lin_bg, sum_dt
+    const double* Jb = raw + 17;
+    for (int i = lane; i < 45; i += 32) {
+      int blk = i / 9, e = i - blk * 9, r = e / 3, c = e - r * 3;
+      const int r0[5] = {0, 0, 3, 6, 6}, c0[5] = {9, 12, 12, 9, 12};
+      rec[IR_DPDBA + i] = Jb[(r0[blk] + r) * 15 + c0[blk] + c];
+    }
+    const double* cov = raw + 17 + 225;
+    double* U = sU[warp];   // 15 x 16 (padded)
+    for (int i = lane; i < 225; i += 32) U[(i / 15) * 16 + (i % 15)] = cov[i];
+    __syncwarp();
+    for (int c = 14; c >= 0; c--) {
+      double d = U[c * 16 + c];
+      for (int k = c + 1; k < 15; k++) d -= U[c * 16 + k] * U[c * 16 + k];
+      d = sqrt(d);
+      double v = 0;
+      if (lane < c) {
+        v = U[lane * 16 + c];
+        for (int k = c + 1; k < 15; k++) v -= U[lane * 16 + k] * U[c * 16 + k];
+        v /= d;
+      }
+      __syncwarp();
+      if (lane < c) U[lane * 16 + c] = v;
+      if (lane == c) U[c * 16 + c] = d;
+      __syncwarp();
+    }
+    // X = U~^-1 (upper): lane = column
+    if (lane < 15) {
+      int c = lane;
+      double x[15];
+#pragma unroll
+      for (int i = 0; i < 15; i++) x[i] = 0;
+#pragma unroll
+      for (int i = 14; i >= 0; i--) {
+        if (i == c) x[i] = 1.0 / U[i * 16 + i];
+        else if (i < c) {
+          double s = 0;
+#pragma unroll
+          for (int k = i + 1; k < 15; k++) if (k <= c) s += U[i * 16 + k] * x[k];
+          x[i] = -s / U[i * 16 + i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 15; i++) rec[IR_SQ + i * 15 + c] = x[i];
+    }
+    __syncwarp();
+  }
+  // ---- prior: column map and H = J^T J
+  int n = bt.pr_n[w], nb = bt.pr_nb[w];
+  int* map = bt.pr_map + (size_t)w * bt.nmax;
+  for (int i = threadIdx.x; i < bt.nmax; i += blockDim.x) map[i] = -1;
+  __syncthreads();
+  for (int bidx = threadIdx.x; bidx < nb; bidx += blockDim.x) {
+    int kind = bt.pr_kind[w * PRIOR_MAXB + bidx], fr = bt.pr_frame[w * PRIOR_MAXB + bidx];
+    int idx = bt.pr_idx[w * PRIOR_MAXB + bidx];
+    int loc = kind == 1 ? 9 : (kind == 3 ? 1 : 6);
+    int base = kind == 0 ? 15 * fr : (kind == 1 ? 15 * fr + 6 : -1);   // EXPOSE / TD constant here
+    for (int i = 0; i < loc; i++) map[idx + i] = base < 0 ? -1 : base + i;
+  }
+  const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
+  double* H = bt.pr_H + (size_t)w * bt.nmax * bt.nmax;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    int a = e / n, b2 = e - a * n;
+    double s = 0;
+    for (int k = 0; k < n; k++) s += Jc[(size_t)a * n + k] * Jc[(size_t)b2 * n + k];
+    H[(size_t)a * bt.nmax + b2] = s;
+  }
+}
+
+__global__ void ba_reset_kernel(BaBatch bt) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = i; k < (size_t)bt.B * bt.K * 7; k += stride) bt.pose[0][k] = bt.pose0[k];
+  for (size_t k = i; k < (size_t)bt.B * bt.K * 9; k += stride) bt.sb[0][k] = bt.sb0[k];
+  for (size_t k = i; k < (size_t)bt.total_L; k += stride) bt.invd[0][k] = bt.invd0[k];
+  for (size_t k = i; k < (size_t)bt.B; k += stride) {
+    BaCtrl c;
+    c.cost = 0; c.cand_cost = 0; c.radius = bt.initial_radius; c.decrease_factor = 2.0;
+    c.model_pose = 0; c.gmax = 0; c.initial_cost = 0; c.rho = 0;
+    c.cur = 0; c.done = 0; c.termination = 0 /*MAX_ITERS*/; c.iterations = 0; c.accepted = 0; c.rejected = 0;
+    c.first = 1; c.solve_ok = 0; c.invalid_run = 0; c.stepped = 0; c.ticket = 0; c.pad = 0;
+    bt.ctrl[k] = c;
+  }
+}
+
+__global__ void ba_finish_kernel(BaBatch bt) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  const size_t np7 = (size_t)bt.K * 7, np9 = (size_t)bt.K * 9;
+  for (size_t k = i; k < (size_t)bt.B * np7; k += stride) bt.pose_out[k] = bt.pose[bt.ctrl[k / np7].cur][k];
+  for (size_t k = i; k < (size_t)bt.B * np9; k += stride) bt.sb_out[k] = bt.sb[bt.ctrl[k / np9].cur][k];
+  for (int w = blockIdx.x; w < bt.B; w += gridDim.x) {
+    int cur = bt.ctrl[w].cur;
+    for (int l = bt.lm_base[w] + threadIdx.x; l < bt.lm_base[w + 1]; l += blockDim.x) bt.invd_out[l] = bt.invd[cur][l];
+  }
+}
+
+// =============================================================================================
+// linearize: visual tiles (blockIdx.x < T) + IMU/prior CTA (blockIdx.x == T)
+// =============================================================================================
+__device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* sm) {
+  const int K = bt.K, nf = K - 1;
+  double* sJ = sm;                      // [nf][450] raw Jacobians
+  double* sJ2 = sJ + nf * 450;          // [nf][450] whitened
+  double* sR = sJ2 + nf * 450;          // [nf][15] raw
+  double* sR2 = sR + nf * 15;           // [nf][15] whitened
+  double* sdx = sR2 + nf * 15;          // [nmax]
+  double* spr = sdx + bt.nmax;          // [nmax]
+  const double* pose = bt.pose[cur];
+  const double* sb = bt.sb[cur];
+  for (int i = threadIdx.x; i < nf * 450; i += blockDim.x) sJ[i] = 0.0;
+  __syncthreads();
+  if (threadIdx.x < nf) {
+    int f = threadIdx.x, j = f + 1;
+    const double* rec = bt.imu + (size_t)(w * K + j) * IMU_REC;
+    if (!(rec[IR_DT] > 10.0))
+      imu_raw(rec, bt.G, pose + (size_t)(w * K + j - 1) * 7, sb + (size_t)(w * K + j - 1) * 9,
+              pose + (size_t)(w * K + j) * 7, sb + (size_t)(w * K + j) * 9, sR + f * 15, sJ + f * 450);
+    else
+      for (int i = 0; i < 15; i++) sR[f * 15 + i] = 0.0;
+  }
+  __syncthreads();
+  // whiten: J2 = SI * J, r2 = SI * r (SI upper triangular)
+  for (int e = threadIdx.x; e < nf * 465; e += blockDim.x) {
+    int f = e / 465, o = e - f * 465;
+    const double* SI = bt.imu + (size_t)(w * K + f + 1) * IMU_REC + IR_SQ;
+    int i = o / 31, c = o - i * 31;
+    double s = 0;
+    if (c < 30) {
+      for (int k = i; k < 15; k++) s += SI[i * 15 + k] * sJ[f * 450 + k * 30 + c];
+      sJ2[f * 450 + i * 30 + c] = s;
+    } else {
+      for (int k = i; k < 15; k++) s += SI[i * 15 + k] * sR[f * 15 + k];
+      sR2[f * 15 + i] = s;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nf * IMU_OUT; e += blockDim.x) {
+    int f = e / IMU_OUT, o = e - f * IMU_OUT;
+    const double* J = sJ2 + f * 450;
+    const double* r = sR2 + f * 15;
+    double s = 0;
+    if (o < 465) {
+      int a = c_tri30A[o], b2 = c_tri30B[o];
+      for (int k = 0; k < 15; k++) s += J[k * 30 + a] * J[k * 30 + b2];
+    } else if (o < 495) {
+      int a = o - 465;
+      for (int k = 0; k < 15; k++) s += J[k * 30 + a] * r[k];
+    } else {
+      for (int k = 0; k < 15; k++) s += r[k] * r[k];
+      s *= 0.5;
+    }
+    bt.imu_out[(size_t)(w * K + f + 1) * IMU_OUT + o] = s;
+  }
+  // prior
+  int n = bt.pr_n[w];
+  double* po = bt.pr_out + (size_t)w * (bt.nmax + 1);
+  if (n > 0) {
+    prior_residual(bt, w, pose, sb, sdx, spr);
+    const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+      double s = 0;
+      for (int k = 0; k < n; k++) s += Jc[(size_t)a * n + k] * spr[k];
+      po[a] = s;
+    }
+    if (threadIdx.x == 0) {
+      double c = 0;
+      for (int k = 0; k < n; k++) c += spr[k] * spr[k];
+      po[bt.nmax] = 0.5 * c;
+    }
+  } else if (threadIdx.x == 0) {
+    po[bt.nmax] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(BA_THREADS) ba_linearize_kernel(BaBatch bt) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.y, t = blockIdx.x;
+  BaCtrl* ctrl = bt.ctrl + w;
+  if (ctrl->done) return;
+  const int cur = ctrl->cur;
+  if (t == bt.T) { imu_prior_linearize(bt, w, cur, sm); return; }
+
+  const int K = bt.K, K6 = 6 * K, NPb = K * (K + 1) / 2;
+  const int REC = NPb * 36 + 3 * K6;
+  const int NW = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sFr = sm;                       // K * FR
+  double* sEx = sFr + K * FR;             // FR
+  double* sScal = sEx + FR;               // 2 * NW (cost, gmax per warp)
+  const int per_warp = REC + (BVIO_KMAX - 1) * STG + BVIO_KMAX * 6 + 36 + 6 + BVIO_KMAX /*frames as doubles*/;
+  double* mine = sScal + 2 * 8 + (size_t)warp * per_warp;
+  double* acc = mine;                     // [NPb*36]
+  double* gred = acc + NPb * 36;          // [K6]
+  double* bpv = gred + K6;                // [K6]
+  double* dgh = bpv + K6;                 // [K6]
+  double* stage = dgh + K6;               // [(KMAX-1)*STG]
+  double* wv = stage + (BVIO_KMAX - 1) * STG;   // [KMAX*6]
+  double* AtA = wv + BVIO_KMAX * 6;       // [36]
+  double* gA = AtA + 36;                  // [6]
+  int* sfr = reinterpret_cast<int*>(gA + 6);    // [KMAX] ints (fits in KMAX doubles)
+
+  stage_frames(bt, w, bt.pose[cur], sFr, sEx);
+  for (int i = lane; i < REC; i += 32) acc[i] = 0.0;
+  __syncthreads();
+
+  const double radius = ctrl->radius;
+  const int first = ctrl->first;
+  const double* invd = bt.invd[cur];
+  int l0, l1;
+  tile_range(bt, w, t, l0, l1);
+  double cost_w = 0.0, gmax_w = 0.0;
+
+  for (int l = l0 + warp; l < l1; l += NW) {
+    const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0, nfac = n - 1;
+    const double lam = invd[l];
+    const double2 pi = bt.obs_xy[o0];
+    int myfr = 0;
+    if (lane < n) { myfr = bt.obs_frame[o0 + lane]; sfr[lane] = myfr; }
+    const int fi = __shfl_sync(0xffffffffu, myfr, 0);
+    const int fj = __shfl_down_sync(0xffffffffu, myfr, 1);   // frame of observation lane+1
+    double cc0 = 0, cc1 = 0, rr0 = 0, rr1 = 0, fcost = 0;
+    double wB[6] = {0, 0, 0, 0, 0, 0};
+    if (lane < nfac) {
+      const double2 pj = bt.obs_xy[o0 + 1 + lane];
+      const double* Fi = sFr + fi * FR;
+      const double* Fj = sFr + fj * FR;
+      ProjGeom g = proj_geom(Fi, Fj, sEx, pi.x, pi.y, lam);
+      const double inv = 1.0 / g.pcj.z, si = bt.sqrt_info;
+      double r0 = si * (g.pcj.x * inv - pj.x), r1 = si * (g.pcj.y * inv - pj.y);
+      // reduce (2x3) * ric^T -> Gm (2x3); Gm * Rj^T -> Q (2x3)
+      double red[2][3] = {{si * inv, 0.0, -si * g.pcj.x * inv * inv}, {0.0, si * inv, -si * g.pcj.y * inv * inv}};
+      double Gm[2][3], Q[2][3];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          Gm[a][c] = red[a][0] * sEx[c * 3 + 0] + red[a][1] * sEx[c * 3 + 1] + red[a][2] * sEx[c * 3 + 2];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) Q[a][c] = Gm[a][0] * Fj[c * 3 + 0] + Gm[a][1] * Fj[c * 3 + 1] + Gm[a][2] * Fj[c * 3 + 2];
+      double s = r0 * r0 + r1 * r1, rho0, rho1;
+      cauchy(bt.cauchy_a, s, rho0, rho1);
+      fcost = 0.5 * rho0;
+      const double sr = sqrt(rho1);
+      double* st = stage + lane * STG;
+      const d3 tic{sEx[9], sEx[10], sEx[11]};
+      const d3 dimu = g.pimu_i - tic;
+      double Jf[2];
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+        // u = Ri^T Q[a]^T
+        d3 u = mtv3(Fi, d3{Q[a][0], Q[a][1], Q[a][2]});
+        d3 jr = cross3(g.pimu_i, u);                                   // -(Q Ri skew(pts_imu_i)) row
+        d3 jjr = cross3(d3{Gm[a][0], Gm[a][1], Gm[a][2]}, g.pimu_j);   // (Gm skew(pts_imu_j)) row
+        st[a * 6 + 0] = sr * Q[a][0]; st[a * 6 + 1] = sr * Q[a][1]; st[a * 6 + 2] = sr * Q[a][2];
+        st[a * 6 + 3] = sr * jr.x; st[a * 6 + 4] = sr * jr.y; st[a * 6 + 5] = sr * jr.z;
+        st[12 + a * 6 + 0] = -sr * Q[a][0]; st[12 + a * 6 + 1] = -sr * Q[a][1]; st[12 + a * 6 + 2] = -sr * Q[a][2];
+        st[12 + a * 6 + 3] = sr * jjr.x; st[12 + a * 6 + 4] = sr * jjr.y; st[12 + a * 6 + 5] = sr * jjr.z;
+        Jf[a] = -dot3(u, dimu) / lam;
+      }
+      cc0 = sr * Jf[0]; cc1 = sr * Jf[1]; rr0 = sr * r0; rr1 = sr * r1;
+      st[24] = cc0; st[25] = cc1; st[26] = rr0; st[27] = rr1;
+#pragma unroll
+      for (int k = 0; k < 6; k++) wB[k] = st[12 + k] * cc0 + st[18 + k] * cc1;
+    }
+    double h = warp_sum(cc0 * cc0 + cc1 * cc1);
+    double b = warp_sum(cc0 * rr0 + cc1 * rr1);
+    cost_w += warp_sum(fcost);
+    __syncwarp();
+    // anchor-side reductions over the factors: AtA (36), wA (6), gA (6)
+    for (int e = lane; e < 48; e += 32) {
+      double s = 0;
+      if (e < 36) {
+        int r = e / 6, c = e - r * 6;
+        for (int f = 0; f < nfac; f++) { const double* st = stage + f * STG; s += st[r] * st[c] + st[6 + r] * st[6 + c]; }
+        AtA[e] = s;
+      } else if (e < 42) {
+        int r = e - 36;
+        for (int f = 0; f < nfac; f++) { const double* st = stage + f * STG; s += st[r] * st[24] + st[6 + r] * st[25]; }
+        wv[r] = s;
+      } else {
+        int r = e - 42;
+        for (int f = 0; f < nfac; f++) { const double* st = stage + f * STG; s += st[r] * st[26] + st[6 + r] * st[27]; }
+        gA[r] = s;
+      }
+    }
+    if (lane < nfac) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) wv[(lane + 1) * 6 + k] = wB[k];
+    }
+    __syncwarp();
+    // LM damping of the eliminated block (Ceres LevenbergMarquardtStrategy with Jacobi scaling)
+    double sl2 = 1.0;
+    if (bt.jacobi_scaling) {
+      if (first) { double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
+      else sl2 = bt.sl2[l];
+    }
+    double ddl = fmin(fmax(sl2 * h, 1e-6), 1e32) / (radius * sl2);
+    double inv_hd = 1.0 / (h + ddl);
+    if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
+    gmax_w = fmax(gmax_w, fabs(b));
+    if (lane == 0) {
+      bt.h[l] = h; bt.b[l] = b;
+      if (first) bt.sl2[l] = sl2;
+    }
+    for (int e = lane; e < n * 6; e += 32) bt.w[(size_t)o0 * 6 + e] = wv[e];
+    // accumulate this landmark's (J^T J - w w^T / (h + d)) into the warp's private S blocks
+    const int E = (n * (n + 1) / 2) * 36;
+    for (int e = lane; e < E; e += 32) {
+      int pr = e / 36, rc = e - pr * 36, r = rc / 6, c = rc - r * 6;
+      int a = c_triA[pr], b2 = c_triB[pr];
+      int fa = sfr[a], fb = sfr[b2];
+      double val = -wv[a * 6 + r] * wv[b2 * 6 + c] * inv_hd;
+      if (b2 == 0) {
+        if (a == 0) val += AtA[rc];
+        else { const double* st = stage + (a - 1) * STG; val += st[12 + r] * st[c] + st[18 + r] * st[6 + c]; }
+      } else if (a == b2) {
+        const double* st = stage + (a - 1) * STG;
+        val += st[12 + r] * st[12 + c] + st[18 + r] * st[18 + c];
+      }
+      acc[tri(fa, fb) * 36 + rc] += val;
+    }
+    for (int e = lane; e < n * 6; e += 32) {
+      int a = e / 6, r = e - a * 6;
+      int idx = sfr[a] * 6 + r;
+      double gv, dv;
+      if (a == 0) { gv = gA[r]; dv = AtA[r * 7]; }
+      else {
+        const double* st = stage + (a - 1) * STG;
+        gv = st[12 + r] * st[26] + st[18 + r] * st[27];
+        dv = st[12 + r] * st[12 + r] + st[18 + r] * st[18 + r];
+      }
+      bpv[idx] += gv;
+      gred[idx] += gv - wv[e] * b * inv_hd;
+      dgh[idx] += dv;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) { sScal[warp] = cost_w; sScal[8 + warp] = gmax_w; }
+  __syncthreads();
+  // fixed-order reduction over the warps, one tile record to HBM
+  double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(K);
+  const double* base = sScal + 16;
+  for (int i = threadIdx.x; i < REC; i += blockDim.x) {
+    double s = 0;
+    for (int q = 0; q < NW; q++) s += base[(size_t)q * per_warp + i];
+    out[i] = s;
+  }
+  if (threadIdx.x == 0) {
+    double c = 0, g = 0;
+    for (int q = 0; q < NW; q++) { c += sScal[q]; g = fmax(g, sScal[8 + q]); }
+    out[REC] = c; out[REC + 1] = g; out[REC + 2] = 0; out[REC + 3] = 0;
+  }
+}
+
+// =============================================================================================
+// solve: one CTA per window
+// =============================================================================================
+__global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_kernel(BaBatch bt, int with_step) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.x, K = bt.K, np = bt.np, K6 = 6 * K, NPb = K * (K + 1) / 2;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  BaCtrl* ctrl = bt.ctrl + w;
+  if (ctrl->done) return;
+  const int N1 = np + 1;                          // augmented dimension
+  double* S = sm;                                 // packed lower (N1)(N1+1)/2
+  double* bp = S + (size_t)N1 * (N1 + 1) / 2;     // [np] unreduced gradient
+  double* gr = bp + np;                           // [np] reduced gradient
+  double* dH = gr + np;                           // [np] diag of the undamped, unreduced H_pp
+  double* ddp = dH + np;                          // [np]
+  double* yv = ddp + np;                          // [np]
+  double* red = yv + np;                          // [32]
+  __shared__ int s_fail;
+  const int REC = NPb * 36 + 3 * K6;
+  const int TREC = tile_rec_doubles(K);
+  const double* tiles = bt.tile_out + (size_t)w * bt.T * TREC;
+  const double* imo = bt.imu_out + (size_t)w * K * IMU_OUT;
+  const int n = bt.pr_n[w];
+  const int* map = bt.pr_map + (size_t)w * bt.nmax;
+  const double* pH = bt.pr_H + (size_t)w * bt.nmax * bt.nmax;
+  const double* po = bt.pr_out + (size_t)w * (bt.nmax + 1);
+
+  for (int i = tid; i < N1 * (N1 + 1) / 2; i += nthr) S[i] = 0.0;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  // visual blocks
+  for (int idx = tid; idx < NPb * 36; idx += nthr) {
+    double s = 0;
+    for (int t = 0; t < bt.T; t++) s += tiles[(size_t)t * TREC + idx];
+    int blk = idx / 36, rc = idx - blk * 36, r = rc / 6, c = rc - r * 6;
+    int p = c_triA[blk], q = c_triB[blk];
+    if (p == q && c > r) continue;
+    S[tri(15 * p + r, 15 * q + c)] = s;
+  }
+  __syncthreads();
+  // IMU blocks: odd then even factors (consecutive factors overlap on one frame block)
+  for (int par = 0; par < 2; par++) {
+    for (int e = tid; e < (K - 1) * 465; e += nthr) {
+      int f = e / 465, o = e - f * 465, j = f + 1;
+      if ((j & 1) != par) continue;
+      int a = c_tri30A[o], b2 = c_tri30B[o];
+      S[tri(15 * (j - 1) + a, 15 * (j - 1) + b2)] += imo[(size_t)j * IMU_OUT + o];
+    }
+    __syncthreads();
+  }
+  // prior
+  for (int e = tid; e < n * n; e += nthr) {
+    int a = e / n, b2 = e - a * n;
+    int ra = map[a], rb = map[b2];
+    if (ra < 0 || rb < 0 || ra < rb) continue;
+    S[tri(ra, rb)] += pH[(size_t)a * bt.nmax + b2];
+  }
+  // vectors
+  for (int i = tid; i < np; i += nthr) {
+    int p = i / 15, r = i - p * 15;
+    double g1 = 0, g2 = 0, d = 0;
+    if (r < 6) {
+      for (int t = 0; t < bt.T; t++) {
+        const double* rec = tiles + (size_t)t * TREC + NPb * 36;
+        g2 += rec[6 * p + r]; g1 += rec[K6 + 6 * p + r]; d += rec[2 * K6 + 6 * p + r];
+      }
+    }
+    if (p + 1 < K) { const double* o = imo + (size_t)(p + 1) * IMU_OUT; g1 += o[465 + r]; g2 += o[465 + r]; d += o[tri(r, r)]; }
+    if (p >= 1) { const double* o = imo + (size_t)p * IMU_OUT; g1 += o[465 + 15 + r]; g2 += o[465 + 15 + r]; d += o[tri(15 + r, 15 + r)]; }
+    for (int a = 0; a < n; a++)
+      if (map[a] == i) { g1 += po[a]; g2 += po[a]; d += pH[(size_t)a * bt.nmax + a]; }
+    bp[i] = g1; gr[i] = g2; dH[i] = d;
+  }
+  __syncthreads();
+  // gradient max-norm, cost on the first pass
+  double m = 0;
+  for (int i = tid; i < np; i += nthr) m = fmax(m, fabs(bp[i]));
+  for (int t = tid; t < bt.T; t += nthr) m = fmax(m, tiles[(size_t)t * TREC + REC + 1]);
+  m = block_max(m, red);
+  const int first = ctrl->first;
+  const double radius = ctrl->radius;
+  __syncthreads();
+  if (first || bt.undamped) {
+    for (int i = tid; i < np; i += nthr) bt.scale_p[(size_t)w * np + i] = bt.jacobi_scaling ? 1.0 / (1.0 + sqrt(dH[i])) : 1.0;
+  }
+  if (tid == 0) {
+    ctrl->gmax = m;
+    if (first) {
+      double c = 0;
+      for (int t = 0; t < bt.T; t++) c += tiles[(size_t)t * TREC + REC];
+      for (int j = 1; j < K; j++) c += imo[(size_t)j * IMU_OUT + 495];
+      c += po[bt.nmax];
+      ctrl->cost = c; ctrl->initial_cost = c; ctrl->first = 0;
+    }
+  }
+  if (bt.undamped) {   // debug path: dump the undamped reduced system
+    __syncthreads();
+    if (bt.dbg_S) {
+      double* dS = bt.dbg_S + (size_t)w * np * np;
+      for (int e = tid; e < np * np; e += nthr) {
+        int i = e / np, j = e - i * np;
+        dS[e] = (i >= j) ? S[tri(i, j)] : S[tri(j, i)];
+      }
+      for (int i = tid; i < np; i += nthr) bt.dbg_g[(size_t)w * np + i] = gr[i];
+    }
+    return;
+  }
+  // termination tests that need the fresh gradient (oracle_optimize order)
+  int stop = 0;
+  if (m <= bt.gradient_tolerance) stop = 2;            // BVIO_TERM_GRADIENT_TOL
+  else if (ctrl->iterations >= bt.max_iters || !with_step) stop = -1;   // MAX_ITERS (termination already 0)
+  if (stop) {
+    __syncthreads();
+    if (tid == 0) { ctrl->done = 1; if (stop > 0) ctrl->termination = stop; ctrl->stepped = 0; }
+    return;
+  }
+  // damping + augmented row
+  for (int i = tid; i < np; i += nthr) {
+    double sp = first ? (bt.jacobi_scaling ? 1.0 / (1.0 + sqrt(dH[i])) : 1.0) : bt.scale_p[(size_t)w * np + i];
+    double sp2 = sp * sp;
+    double d = fmin(fmax(sp2 * dH[i], 1e-6), 1e32) / (radius * sp2);
+    ddp[i] = d;
+    S[tri(i, i)] += d;
+    S[tri(np, i)] = -gr[i];
+  }
+  __syncthreads();
+  // blocked Cholesky (15-wide panels) of the augmented matrix: the last row becomes y = L^-1 (-g)
+  for (int kb = 0; kb < K; kb++) {
+    const int j0 = 15 * kb;
+    if (tid < 32) {
+      for (int j = 0; j < 15; j++) {
+        double d = S[tri(j0 + j, j0 + j)];
+        if (!(d > 0.0)) { if (tid == 0) s_fail = 1; d = 1.0; }
+        d = sqrt(d);
+        __syncwarp();
+        if (tid == j) S[tri(j0 + j, j0 + j)] = d;
+        if (tid > j && tid < 15) S[tri(j0 + tid, j0 + j)] /= d;
+        __syncwarp();
+        // trailing update inside the diagonal block
+        for (int e = tid; e < 105; e += 32) {
+          int a = c_triA[e], b2 = c_triB[e];   // a >= b2 in 0..13
+          int i = j + 1 + a, k2 = j + 1 + b2;
+          if (i < 15) S[tri(j0 + i, j0 + k2)] -= S[tri(j0 + i, j0 + j)] * S[tri(j0 + k2, j0 + j)];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (s_fail) break;
+    // panel: rows below the diagonal block (incl. the augmented row)
+    for (int i = j0 + 15 + tid; i <= np; i += nthr) {
+      double x[15];
+      double* row = S + tri(i, j0);
+#pragma unroll
+      for (int c = 0; c < 15; c++) {
+        double v = row[c];
+        const double* lr = S + tri(j0 + c, j0);
+#pragma unroll
+        for (int q = 0; q < 15; q++) if (q < c) v -= x[q] * lr[q];
+        x[c] = v / lr[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 15; c++) row[c] = x[c];
+    }
+    __syncthreads();
+    // trailing update
+    const int r0 = j0 + 15, mrows = np + 1 - r0;
+    const int tot = mrows * (mrows + 1) / 2;
+    for (int e = tid; e < tot; e += nthr) {
+      int ii = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while (ii * (ii + 1) / 2 > e) ii--;
+      while ((ii + 1) * (ii + 2) / 2 <= e) ii++;
+      int kk = e - ii * (ii + 1) / 2;
+      const double* ri = S + tri(r0 + ii, j0);
+      const double* rk = S + tri(r0 + kk, j0);
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < 15; c++) s += ri[c] * rk[c];
+      S[tri(r0 + ii, r0 + kk)] -= s;
+    }
+    __syncthreads();
+  }
+  if (s_fail) {
+    if (tid == 0) { ctrl->solve_ok = 0; ctrl->stepped = 1; ctrl->iterations++; }
+    return;
+  }
+  // back substitution L^T dp = y (warp 0)
+  for (int i = tid; i < np; i += nthr) yv[i] = S[tri(np, i)];
+  __syncthreads();
+  if (tid < 32) {
+    for (int i = np - 1; i >= 0; i--) {
+      const double* row = S + tri(i, 0);
+      double di = yv[i] / row[i];
+      __syncwarp();
+      for (int k = tid; k < i; k += 32) yv[k] -= row[k] * di;
+      if (tid == 0) yv[i] = di;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // step + pose part of the model cost change:  -g^T d - 1/2 d^T H d = -1/2 g^T d + 1/2 d^T D d
+  double mp = 0;
+  for (int i = tid; i < np; i += nthr) {
+    double d = yv[i];
+    bt.delta_p[(size_t)w * np + i] = d;
+    mp += -0.5 * bp[i] * d + 0.5 * ddp[i] * d * d;
+  }
+  mp = block_sum(mp, red);
+  if (tid == 0) { ctrl->model_pose = mp; ctrl->solve_ok = 1; ctrl->stepped = 1; ctrl->iterations++; }
+}
+
+// =============================================================================================
+// cost at the candidate + accept/reject
+// =============================================================================================
+__device__ void decide(const BaBatch& bt, int w) {
+  BaCtrl* c = bt.ctrl + w;
+  c->stepped = 0;
+  c->ticket = 0;
+  bool valid = c->solve_ok != 0;
+  double cv = 0, ml = 0, s2 = 0, x2 = 0;
+  if (valid) {
+    const volatile double* co = bt.cost_out + (size_t)w * (bt.T + 1) * COST_REC;
+    for (int t = 0; t <= bt.T; t++) { cv += co[t * COST_REC]; ml += co[t * COST_REC + 1]; s2 += co[t * COST_REC + 2]; x2 += co[t * COST_REC + 3]; }
+  }
+  double model = c->model_pose + ml;
+  if (valid && !(model > 0)) valid = false;
+  if (!valid) {
+    c->rejected++;
+    if (++c->invalid_run >= 5) { c->done = 1; c->termination = 4; return; }
+    c->radius /= c->decrease_factor; c->decrease_factor *= 2;
+    if (c->radius < 1e-32) { c->done = 1; c->termination = 4; }
+    return;
+  }
+  c->invalid_run = 0;
+  c->cand_cost = cv;
+  double step_norm = sqrt(s2), x_norm = sqrt(x2);
+  if (step_norm <= bt.parameter_tolerance * (x_norm + bt.parameter_tolerance)) { c->done = 1; c->termination = 3; return; }
+  double cost_change = c->cost - cv;
+  if (fabs(cost_change) <= bt.function_tolerance * c->cost) { c->done = 1; c->termination = 1; return; }
+  double rho = cost_change / model;
+  c->rho = rho;
+  if (isfinite(cv) && rho > bt.min_relative_decrease) {
+    c->accepted++;
+    c->cur ^= 1;
+    c->cost = cv;
+    double t = 2.0 * rho - 1.0;
+    c->radius = fmin(1e16, c->radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+    c->decrease_factor = 2.0;
+  } else {
+    c->rejected++;
+    c->radius /= c->decrease_factor; c->decrease_factor *= 2;
+    if (c->radius < 1e-32) { c->done = 1; c->termination = 4; }
+  }
+}
+
+__global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.y, t = blockIdx.x, K = bt.K, np = bt.np;
+  BaCtrl* ctrl = bt.ctrl + w;
+  if (ctrl->done || !ctrl->stepped) return;
+  if (!ctrl->solve_ok) {
+    if (t == 0 && threadIdx.x == 0) decide(bt, w);
+    return;
+  }
+  const int cur = ctrl->cur, nxt = cur ^ 1;
+  double* sdp = sm;                 // [np]
+  double* sPose = sdp + np;         // [K*7] candidate poses
+  double* sFr = sPose + K * 7;      // [K*FR]
+  double* sEx = sFr + K * FR;       // [FR]
+  double* red = sEx + FR;           // [16*4 + 32]
+  double* extra = red + 96;         // IMU/prior CTA scratch
+  __shared__ int s_last;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) sdp[i] = bt.delta_p[(size_t)w * np + i];
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    pose_plus(bt.pose[cur] + (size_t)(w * K + k) * 7, sdp + 15 * k, sPose + k * 7);
+  __syncthreads();
+  double* co = bt.cost_out + (size_t)(w * (bt.T + 1) + t) * COST_REC;
+  if (t < bt.T) {
+    for (int k = threadIdx.x; k <= K; k += blockDim.x) {
+      const double* p = (k < K) ? sPose + k * 7 : bt.ex + (size_t)w * 7;
+      double* o = (k < K) ? sFr + k * FR : sEx;
+      qmat(q4{p[3], p[4], p[5], p[6]}, o);
+      o[9] = p[0]; o[10] = p[1]; o[11] = p[2];
+    }
+    __syncthreads();
+    const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15, NG = blockDim.x >> 4;
+    const unsigned gmask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+    const double radius = ctrl->radius;
+    int l0, l1;
+    tile_range(bt, w, t, l0, l1);
+    double a_cost = 0, a_model = 0, a_s2 = 0, a_x2 = 0;
+    for (int l = l0 + grp; l < l1; l += NG) {
+      const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0;
+      const double lam = bt.invd[cur][l], h = bt.h[l], b = bt.b[l];
+      int myfr = 0;
+      double part = 0;
+      if (l16 < n) {
+        myfr = bt.obs_frame[o0 + l16];
+        const double* wp = bt.w + (size_t)(o0 + l16) * 6;
+        const double* d = sdp + 15 * myfr;
+#pragma unroll
+        for (int k = 0; k < 6; k++) part += wp[k] * d[k];
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, 16);
+      const int fi = __shfl_sync(gmask, myfr, 0, 16);
+      double sl2 = bt.jacobi_scaling ? bt.sl2[l] : 1.0;
+      double ddl = fmin(fmax(sl2 * h, 1e-6), 1e32) / (radius * sl2);
+      double dl = -(b + part) / (h + ddl);
+      double lamc = lam + dl;
+      double fc = 0;
+      if (l16 >= 1 && l16 < n) {
+        const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + l16];
+        ProjGeom g = proj_geom(sFr + fi * FR, sFr + myfr * FR, sEx, pi.x, pi.y, lamc);
+        double inv = 1.0 / g.pcj.z;
+        double r0 = bt.sqrt_info * (g.pcj.x * inv - pj.x), r1 = bt.sqrt_info * (g.pcj.y * inv - pj.y);
+        double rho0, rho1;
+        cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
+        fc = 0.5 * rho0;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) fc += __shfl_xor_sync(gmask, fc, o, 16);
+      if (l16 == 0) {
+        bt.invd[nxt][l] = lamc;
+        a_cost += fc;
+        a_model += -0.5 * b * dl + 0.5 * ddl * dl * dl;
+        a_s2 += dl * dl;
+        a_x2 += lam * lam;
+      }
+    }
+    if (l16 == 0) { red[grp * 4] = a_cost; red[grp * 4 + 1] = a_model; red[grp * 4 + 2] = a_s2; red[grp * 4 + 3] = a_x2; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double s = 0;
+      for (int g = 0; g < NG; g++) s += red[g * 4 + threadIdx.x];
+      co[threadIdx.x] = s;
+    }
+  } else {
+    // candidate poses / speed-biases to the other buffer, IMU + prior cost, pose part of the norms
+    double* sSb = extra;                   // [K*9]
+    double* sR = sSb + K * 9;              // [(K-1)*15]
+    double* sdx = sR + (K - 1) * 15;       // [nmax]
+    double* spr = sdx + bt.nmax;           // [nmax]
+    double* pn = bt.pose[nxt] + (size_t)w * K * 7;
+    double* sn = bt.sb[nxt] + (size_t)w * K * 9;
+    const double* pc = bt.pose[cur] + (size_t)w * K * 7;
+    const double* sc = bt.sb[cur] + (size_t)w * K * 9;
+    double s2 = 0, x2 = 0;
+    for (int i = threadIdx.x; i < K * 7; i += blockDim.x) {
+      double v = sPose[i], o = pc[i];
+      pn[i] = v; s2 += (o - v) * (o - v); x2 += o * o;
+    }
+    for (int i = threadIdx.x; i < K * 9; i += blockDim.x) {
+      int k = i / 9, r = i - k * 9;
+      double o = sc[i], v = o + sdp[15 * k + 6 + r];
+      sSb[i] = v; sn[i] = v; s2 += (o - v) * (o - v); x2 += o * o;
+    }
+    s2 = block_sum(s2, red);
+    x2 = block_sum(x2, red + 32);
+    __syncthreads();
+    if (threadIdx.x < K - 1) {
+      int j = threadIdx.x + 1;
+      const double* rec = bt.imu + (size_t)(w * K + j) * IMU_REC;
+      double* r = sR + threadIdx.x * 15;
+      if (!(rec[IR_DT] > 10.0)) {
+        double raw[15];
+        imu_raw(rec, bt.G, sPose + (j - 1) * 7, sSb + (j - 1) * 9, sPose + j * 7, sSb + j * 9, raw, nullptr);
+        const double* SI = rec + IR_SQ;
+        for (int i = 0; i < 15; i++) {
+          double s = 0;
+          for (int k = i; k < 15; k++) s += SI[i * 15 + k] * raw[k];
+          r[i] = s;
+        }
+      } else {
+        for (int i = 0; i < 15; i++) r[i] = 0;
+      }
+    }
+    __syncthreads();
+    double c = 0;
+    for (int i = threadIdx.x; i < (K - 1) * 15; i += blockDim.x) c += 0.5 * sR[i] * sR[i];
+    int n = bt.pr_n[w];
+    if (n > 0) {
+      // prior_residual reads the state from global memory laid out [B][K][..]; the candidate was just
+      // written to the nxt buffers by this CTA
+      __threadfence_block();
+      __syncthreads();
+      prior_residual(bt, w, bt.pose[nxt], bt.sb[nxt], sdx, spr);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) c += 0.5 * spr[i] * spr[i];
+    }
+    c = block_sum(c, red);
+    if (threadIdx.x == 0) { co[0] = c; co[1] = 0; co[2] = s2; co[3] = x2; }
+  }
+  // last CTA of this window decides
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned old = atomicAdd(&ctrl->ticket, 1u);
+    s_last = (old == (unsigned)bt.T);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    decide(bt, w);
+  }
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+static size_t imu_prior_smem(int K, int nmax) { return sizeof(double) * ((size_t)(K - 1) * (900 + 30) + 2 * nmax); }
+
+size_t ba_linearize_smem_bytes(int K, int nwarps) {
+  int NPb = K * (K + 1) / 2, REC = NPb * 36 + 18 * K;
+  size_t per_warp = REC + (BVIO_KMAX - 1) * STG + BVIO_KMAX * 6 + 36 + 6 + BVIO_KMAX;
+  return sizeof(double) * ((size_t)(K + 1) * FR + 16 + per_warp * nwarps);
+}
+int ba_pick_linearize_warps(int K) {
+  int nw = 8;
+  while (nw > 1 && ba_linearize_smem_bytes(K, nw) > 216 * 1024) nw--;
+  return nw;
+}
+size_t ba_solve_smem_bytes(int K) {
+  int np = 15 * K, N1 = np + 1;
+  return sizeof(double) * ((size_t)N1 * (N1 + 1) / 2 + 5 * np + 32);
+}
+static size_t cost_smem(int K, int nmax) {
+  return sizeof(double) * ((size_t)15 * K + K * 7 + (K + 1) * FR + 96 + K * 9 + (K - 1) * 15 + 2 * nmax);
+}
+
+static bool g_tables_done = false;
+int ba_configure(void) {
+  if (!g_tables_done) {
+    unsigned char ta[BVIO_KMAX * (BVIO_KMAX + 1) / 2], tb[BVIO_KMAX * (BVIO_KMAX + 1) / 2];
+    int e = 0;
+    for (int a = 0; a < BVIO_KMAX; a++) for (int b = 0; b <= a; b++) { ta[e] = a; tb[e] = b; e++; }
+    unsigned char ua[465], ub[465];
+    e = 0;
+    for (int a = 0; a < 30; a++) for (int b = 0; b <= a; b++) { ua[e] = a; ub[e] = b; e++; }
+    cudaError_t err;
+    if ((err = cudaMemcpyToSymbol(c_triA, ta, sizeof ta)) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_triB, tb, sizeof tb)) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_tri30A, ua, sizeof ua)) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_tri30B, ub, sizeof ub)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
+    g_tables_done = true;
+  }
+  return 0;
+}
+
+int ba_launch_prepare(const BaBatch& bt, cudaStream_t st) {
+  ba_prepare_kernel<<<bt.B, BA_THREADS, 0, st>>>(bt);
+  return 1;
+}
+int ba_launch_reset(const BaBatch& bt, cudaStream_t st) {
+  size_t work = (size_t)bt.B * bt.K * 9;
+  if ((size_t)bt.total_L > work) work = bt.total_L;
+  int blocks = (int)((work + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  ba_reset_kernel<<<blocks, 256, 0, st>>>(bt);
+  return 1;
+}
+int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step) {
+  size_t s1 = ba_linearize_smem_bytes(bt.K, bt.nwarps_lin), s1b = imu_prior_smem(bt.K, bt.nmax);
+  if (s1b > s1) s1 = s1b;
+  ba_linearize_kernel<<<dim3(bt.T + 1, bt.B), 32 * bt.nwarps_lin, s1, st>>>(bt);
+  ba_solve_kernel<<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.K), st>>>(bt, with_step ? 1 : 0);
+  if (!with_step || bt.undamped) return 2;
+  ba_cost_kernel<<<dim3(bt.T + 1, bt.B), BA_THREADS, cost_smem(bt.K, bt.nmax), st>>>(bt);
+  return 3;
+}
+int ba_launch_finish(const BaBatch& bt, cudaStream_t st) {
+  int blocks = bt.B < 1184 ? bt.B : 1184;
+  ba_finish_kernel<<<blocks, 256, 0, st>>>(bt);
+  return 1;
+}
+
+}  // namespace bvio

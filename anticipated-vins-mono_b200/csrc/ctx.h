@@ -1,0 +1,97 @@
+// ctx.h -- host-side context shared by the C-ABI translation units (ba_api.cu, sel_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/bvio.h"
+
+struct ncclComm;
+
+namespace bvio {
+
+// one device slab + one pinned host slab carved into aligned sub-arrays
+struct Slab {
+  char* d = nullptr;
+  char* h = nullptr;       // pinned mirror of the first h_bytes (inputs + outputs, not scratch)
+  size_t d_bytes = 0, h_bytes = 0;
+  void release() {
+    if (d) cudaFree(d);
+    if (h) cudaFreeHost(h);
+    d = h = nullptr; d_bytes = h_bytes = 0;
+  }
+};
+
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~size_t(255);
+    return o;
+  }
+};
+
+}  // namespace bvio
+
+struct bvio_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int sm_count = 0;
+  // grow-only slab caches so that one-shot calls (bvio_optimize / bvio_select at frame rate) do not
+  // pay cudaMalloc + cudaMallocHost every call
+  bvio::Slab ba_cache, sel_cache;
+  bool ba_cache_busy = false, sel_cache_busy = false;
+  // multi-GPU selector
+  ncclComm* comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+namespace bvio {
+
+// take a slab of at least (d_bytes, h_bytes): from the cache when it is free and large enough
+inline cudaError_t slab_acquire(Slab& cache, bool& busy, size_t d_bytes, size_t h_bytes, Slab& out, bool& from_cache) {
+  if (!busy) {
+    if (cache.d_bytes < d_bytes || cache.h_bytes < h_bytes) {
+      size_t nd = d_bytes > cache.d_bytes ? d_bytes + d_bytes / 4 : cache.d_bytes;
+      size_t nh = h_bytes > cache.h_bytes ? h_bytes + h_bytes / 4 : cache.h_bytes;
+      cache.release();
+      cudaError_t e = cudaMalloc((void**)&cache.d, nd);
+      if (e != cudaSuccess) return e;
+      e = cudaMallocHost((void**)&cache.h, nh);
+      if (e != cudaSuccess) { cache.release(); return e; }
+      cache.d_bytes = nd; cache.h_bytes = nh;
+    }
+    out = cache; busy = true; from_cache = true;
+    return cudaSuccess;
+  }
+  from_cache = false;
+  out = Slab();
+  cudaError_t e = cudaMalloc((void**)&out.d, d_bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaMallocHost((void**)&out.h, h_bytes);
+  if (e != cudaSuccess) { out.release(); return e; }
+  out.d_bytes = d_bytes; out.h_bytes = h_bytes;
+  return cudaSuccess;
+}
+inline void slab_release(Slab& s, bool& busy, bool from_cache) {
+  if (from_cache) busy = false;
+  else s.release();
+  s = Slab();
+}
+
+inline int fail(bvio_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define BVIO_CUDA_OK(ctx, expr)                                                                     \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return bvio::fail(ctx, BVIO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));   \
+  } while (0)
+
+}  // namespace bvio

@@ -1,0 +1,165 @@
+"""GPU parity suite for the BA path: libbvio.so (through the C-ABI) against the CPU oracle on the
+same seeded windows.  Tolerances: 1e-6 relative on the final state vector (BASELINE.json
+north_star); linearization products to 1e-9 of their max-norm (different summation order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = dict(max_iters=50, function_tolerance=1e-14, gradient_tolerance=1e-12, parameter_tolerance=1e-14)
+
+
+@pytest.fixture(scope="module")
+def env(pkg, oracle):
+    ctx = pkg.lib.Context(0)
+    yield pkg.abi, pkg.synth, oracle, ctx
+    ctx.close()
+
+
+def _linearize_both(env, w):
+    abi, synth, orc, ctx = env
+    o = abi.default_opts()
+    h1, h2 = abi.WindowHandle(w), abi.WindowHandle(w)
+    np_ = 15 * w.K
+    L = w.L
+    out = {}
+    for name, fn, hh in (("gpu", None, h1), ("cpu", orc.oracle_linearize, h2)):
+        S, g, h, b, c = np.zeros((np_, np_)), np.zeros(np_), np.zeros(L), np.zeros(L), np.zeros(1)
+        if name == "gpu":
+            ctx.check(ctx.L.bvio_debug_linearize(ctx.h, C.byref(hh.s), C.byref(o), abi.dptr(S), abi.dptr(g),
+                                                 abi.dptr(h), abi.dptr(b), abi.dptr(c)), "debug_linearize")
+        else:
+            assert fn(C.byref(hh.s), C.byref(o), abi.dptr(S), abi.dptr(g), abi.dptr(h), abi.dptr(b), abi.dptr(c)) == 0
+        out[name] = (S, g, h, b, c[0])
+    return out
+
+
+@pytest.mark.parametrize("seed,K,L,prior", [(0, 11, 150, "frame0"), (1, 11, 150, "none"), (2, 2, 20, "none"),
+                                            (3, 5, 37, "frame0"), (4, 11, 1500, "frame0"), (5, 16, 64, "frame0")])
+def test_linearize_matches_oracle(env, seed, K, L, prior):
+    abi, synth, orc, ctx = env
+    kw = dict(track_min=2, track_max=2) if K == 2 else {}
+    w = synth.make_window(seed=seed, K=K, L=L, prior=prior, **kw)
+    r = _linearize_both(env, w)
+    (S1, g1, h1, b1, c1), (S2, g2, h2, b2, c2) = r["gpu"], r["cpu"]
+    assert np.isfinite(S1).all()
+    assert abs(c1 - c2) <= 1e-11 * abs(c2)
+    assert np.abs(h1 - h2).max() <= 1e-11 * np.abs(h2).max()
+    assert np.abs(b1 - b2).max() <= 1e-10 * max(np.abs(b2).max(), 1.0)
+    # S entries are differences of nearly equal sums (gauge directions): scale by the unreduced diagonal
+    assert np.abs(S1 - S2).max() <= 1e-9 * np.abs(S2).max()
+    assert np.abs(g1 - g2).max() <= 1e-9 * max(np.abs(g2).max(), 1.0)
+    assert np.abs(S1 - S1.T).max() == 0.0
+
+
+def _solve_both(env, w, opts_kw):
+    abi, synth, orc, ctx = env
+    o = abi.default_opts(**opts_kw)
+    hg, ho = abi.WindowHandle(w), abi.WindowHandle(w)
+    sg, so = abi.Summary(), abi.Summary()
+    ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(hg.s), C.byref(o), C.byref(sg)), "bvio_optimize")
+    assert orc.oracle_optimize(C.byref(ho.s), C.byref(o), C.byref(so)) == 0
+    return hg, ho, sg, so
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_config2_converged_state_matches_oracle(env, seed):
+    """BASELINE config 2: 11-kf / 150-feature window, LM to convergence."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=seed, K=11, L=150)
+    hg, ho, sg, so = _solve_both(env, w, TIGHT)
+    xg, xo = hg.state_vector(), ho.state_vector()
+    rel = np.linalg.norm(xg - xo) / np.linalg.norm(xo)
+    assert rel < 1e-6, (rel, sg.as_dict(), so.as_dict())
+    # per-block check as well: poses, speed/bias, inverse depths each to 1e-6 of their own norm
+    for a, b in ((hg.pose, ho.pose), (hg.sb, ho.sb), (hg.inv, ho.inv)):
+        assert np.linalg.norm(a - b) <= 1e-6 * np.linalg.norm(b)
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    assert abs(sg.initial_cost - so.initial_cost) <= 1e-10 * so.initial_cost
+    assert sg.final_cost < sg.initial_cost
+
+
+def test_config1_one_iteration_plumbing(env):
+    """BASELINE config 1: 2-keyframe, 20-feature window, exactly one GN/LM iteration."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=1, K=2, L=20, track_min=2, track_max=2, prior="frame0")
+    hg, ho, sg, so = _solve_both(env, w, dict(max_iters=1))
+    assert sg.iterations == so.iterations == 1
+    assert sg.num_accepted == so.num_accepted
+    xg, xo = hg.state_vector(), ho.state_vector()
+    assert np.linalg.norm(xg - xo) <= 1e-9 * np.linalg.norm(xo)
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * abs(so.final_cost)
+
+
+def test_default_opts_trajectory_matches_oracle(env):
+    """Reference budget (8 iterations, Ceres default tolerances): same iteration count / termination."""
+    abi, synth, orc, ctx = env
+    for seed in range(3):
+        w = synth.make_window(seed=10 + seed, K=11, L=150)
+        hg, ho, sg, so = _solve_both(env, w, {})
+        assert (sg.iterations, sg.num_accepted, sg.num_rejected, sg.termination) == \
+               (so.iterations, so.num_accepted, so.num_rejected, so.termination), (sg.as_dict(), so.as_dict())
+        xg, xo = hg.state_vector(), ho.state_vector()
+        assert np.linalg.norm(xg - xo) <= 1e-8 * np.linalg.norm(xo)
+
+
+def test_stress_window_1500_features(env):
+    """BASELINE config 3: 11-kf / 1500-feature window."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=7, K=11, L=1500, track_min=6)
+    hg, ho, sg, so = _solve_both(env, w, TIGHT)
+    xg, xo = hg.state_vector(), ho.state_vector()
+    assert np.linalg.norm(xg - xo) <= 1e-6 * np.linalg.norm(xo)
+
+
+def test_batch_equals_single(env):
+    """B windows in one launch sequence give bit-identical results to B single calls (fixed-order reductions)."""
+    abi, synth, orc, ctx = env
+    ws = [synth.make_window(seed=20 + i, K=11, L=100 + 17 * i) for i in range(5)]
+    o = abi.default_opts(max_iters=6)
+    singles = []
+    for w in ws:
+        h = abi.WindowHandle(w)
+        s = abi.Summary()
+        ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(o), C.byref(s)), "optimize")
+        singles.append((h.state_vector().copy(), s.final_cost))
+    hs = [abi.WindowHandle(w) for w in ws]
+    arr = (abi.WindowS * len(ws))(*[h.s for h in hs])
+    sums = (abi.Summary * len(ws))()
+    ctx.check(ctx.L.bvio_optimize_batch(ctx.h, arr, len(ws), C.byref(o), sums), "optimize_batch")
+    for h, (x, c), s in zip(hs, singles, sums):
+        # tile partition depends on the batch size, so reductions are reordered: not bit-equal, but tight
+        assert np.linalg.norm(h.state_vector() - x) <= 1e-9 * np.linalg.norm(x)
+        assert abs(s.final_cost - c) <= 1e-9 * c
+
+
+def test_resident_batch_is_deterministic(env):
+    abi, synth, orc, ctx = env
+    ws = [synth.make_window(seed=30 + i, K=11, L=150) for i in range(4)]
+    o = abi.default_opts()
+    hs = [abi.WindowHandle(w) for w in ws]
+    arr = (abi.WindowS * len(ws))(*[h.s for h in hs])
+    sums = (abi.Summary * len(ws))()
+    bh = C.c_void_p()
+    ctx.check(ctx.L.bvio_batch_upload(ctx.h, arr, len(ws), C.byref(o), C.byref(bh)), "upload")
+    res = []
+    for rep in range(3):
+        ctx.check(ctx.L.bvio_batch_solve(ctx.h, bh), "solve")
+        ctx.check(ctx.L.bvio_batch_download(ctx.h, bh, arr, sums), "download")
+        res.append(np.concatenate([h.state_vector() for h in hs]).copy())
+    ctx.L.bvio_batch_free(ctx.h, bh)
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[1], res[2])
+    assert ctx.L.bvio_launch_count(ctx.h) > 0
+
+
+def test_rejects_unsupported_and_invalid(env):
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=0, K=4, L=10)
+    h = abi.WindowHandle(w)
+    s = abi.Summary()
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(estimate_td=1)), C.byref(s)) == -4
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(strategy=1)), C.byref(s)) == -4
+    h.frame[1] = h.frame[0]   # not strictly ascending
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts()), C.byref(s)) == -1
