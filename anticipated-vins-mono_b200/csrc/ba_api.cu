@@ -98,7 +98,7 @@ static int validate(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* o, int
     return fail(ctx, BVIO_ERR_UNSUPPORTED, "estimate_extrinsic / estimate_td are not implemented on the device path");
   if (o->strategy != BVIO_STRATEGY_LM)
     return fail(ctx, BVIO_ERR_UNSUPPORTED, "device path implements BVIO_STRATEGY_LM only");
-  if (w->K < 2 || w->K > BVIO_KMAX) return fail(ctx, BVIO_ERR_INVALID, "K out of range [2,16]");
+  if (w->K < 2 || w->K > BVIO_KMAX - 1) return fail(ctx, BVIO_ERR_INVALID, "K out of range [2,15] (reduced system must fit one CTA's shared memory)");
   if (w->K != K0) return fail(ctx, BVIO_ERR_INVALID, "all windows of a batch must have the same K");
   if (w->L < 0 || !w->para_pose || !w->para_speed_bias || !w->para_ex_pose || !w->preint)
     return fail(ctx, BVIO_ERR_INVALID, "null state / preint arrays");
@@ -407,7 +407,8 @@ int bvio_debug_linearize(bvio_ctx* ctx, const bvio_window* window, const bvio_op
   const BaBatch& bt = bb->bt;
   ctx->launches += ba_launch_reset(bt, ctx->stream);
   ctx->launches += ba_launch_iteration(bt, ctx->stream, true);
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess && S) e = cudaMemcpy(S, bt.dbg_S, sizeof(double) * bt.np * bt.np, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && g) e = cudaMemcpy(g, bt.dbg_g, sizeof(double) * bt.np, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && h && bt.total_L) e = cudaMemcpy(h, bt.h, sizeof(double) * bt.total_L, cudaMemcpyDeviceToHost);

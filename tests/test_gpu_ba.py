@@ -37,7 +37,7 @@ def _linearize_both(env, w):
 
 
 @pytest.mark.parametrize("seed,K,L,prior", [(0, 11, 150, "frame0"), (1, 11, 150, "none"), (2, 2, 20, "none"),
-                                            (3, 5, 37, "frame0"), (4, 11, 1500, "frame0"), (5, 16, 64, "frame0")])
+                                            (3, 5, 37, "frame0"), (4, 11, 1500, "frame0"), (5, 15, 64, "frame0")])
 def test_linearize_matches_oracle(env, seed, K, L, prior):
     abi, synth, orc, ctx = env
     kw = dict(track_min=2, track_max=2) if K == 2 else {}
