@@ -1,15 +1,331 @@
-// sel_api.cu -- placeholder until the selector kernels land (next commit).
+// sel_api.cu -- C-ABI of the anticipated feature selector (include/bvio.h):
+// FeatureSelector::select's numerical part, vins_estimator/src/feature_selector.cpp:139-170.
+// Host code packs the inputs into one pinned slab, issues one H2D copy, launches the kernels of
+// sel_kernels.cu (one per greedy round) and reads back the selected indices.  Multi-GPU: one
+// process per GPU, candidates sharded by contiguous blocks, one ncclAllGather of the per-rank
+// winner records per round.  NCCL is resolved with dlopen at bvio_comm_init so that the library
+// has no link-time dependency on it.
+#include "sel.h"
 #include "ctx.h"
+#include <dlfcn.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
 using namespace bvio;
-extern "C" {
-void bvio_sel_ctx_destroy(bvio_ctx*) {}
-int bvio_select(bvio_ctx* ctx, const bvio_select_in*, int32_t*, double*, bvio_select_summary*) { return fail(ctx, BVIO_ERR_UNSUPPORTED, "selector not built"); }
-int bvio_nccl_unique_id(void*) { return BVIO_ERR_UNSUPPORTED; }
-int bvio_comm_init(bvio_ctx* ctx, const void*, int32_t, int32_t) { return fail(ctx, BVIO_ERR_UNSUPPORTED, "selector not built"); }
-int bvio_select_sharded(bvio_ctx* ctx, const bvio_select_in*, int32_t*, double*, bvio_select_summary*) { return fail(ctx, BVIO_ERR_UNSUPPORTED, "selector not built"); }
-int bvio_select_upload(bvio_ctx* ctx, const bvio_select_in*, bvio_selprob**) { return fail(ctx, BVIO_ERR_UNSUPPORTED, "selector not built"); }
-int bvio_select_run(bvio_ctx* ctx, bvio_selprob*) { return fail(ctx, BVIO_ERR_UNSUPPORTED, "selector not built"); }
-int bvio_select_fetch(bvio_ctx* ctx, bvio_selprob*, int32_t*, double*, bvio_select_summary*) { return fail(ctx, BVIO_ERR_UNSUPPORTED, "selector not built"); }
-void bvio_select_free(bvio_ctx*, bvio_selprob*) {}
-int bvio_debug_build_delta(bvio_ctx* ctx, const bvio_select_in*, double*, int32_t*, double*) { return fail(ctx, BVIO_ERR_UNSUPPORTED, "selector not built"); }
+
+// ---- minimal NCCL surface (ABI-stable since NCCL 2.x) ---------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+  int (*CommInitRank)(ncclComm**, int, nccl_uid_t, int) = nullptr;
+  int (*CommDestroy)(ncclComm*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static const int kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0;
+
+static bool nccl_load() {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+  if (!lib) return false;
+  NcclApi a;
+  a.lib = lib;
+  a.GetUniqueId = (int (*)(nccl_uid_t*))dlsym(lib, "ncclGetUniqueId");
+  a.CommInitRank = (int (*)(ncclComm**, int, nccl_uid_t, int))dlsym(lib, "ncclCommInitRank");
+  a.CommDestroy = (int (*)(ncclComm*))dlsym(lib, "ncclCommDestroy");
+  a.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm*, cudaStream_t))dlsym(lib, "ncclAllGather");
+  a.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+  a.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.AllReduce) return false;
+  g_nccl = a;
+  return true;
 }
+
+namespace bvio {
+int sel_launch_counts(const SelProb& sp, unsigned long long* buf, int dir, cudaStream_t st);   // sel_kernels.cu
+}
+
+struct bvio_selprob {
+  SelProb sp;
+  Slab slab;
+  bool from_cache = false;
+  size_t in_bytes = 0, out_off = 0, out_bytes = 0;
+  size_t o_out_idx = 0, o_out_val = 0, o_ctrl = 0;
+  std::vector<int32_t> cand_id;
+  unsigned long long* counts = nullptr;   // [2] device (sharded finalize)
+  cudaGraphExec_t graph = nullptr;
+  bool use_graph = true;
+  bool sharded = false;
+  int launches_per_run = 0;
+};
+
+static int sel_validate(bvio_ctx* ctx, const bvio_select_in* in) {
+  if (!ctx || !in) return fail(ctx, BVIO_ERR_INVALID, "null argument");
+  if (in->H < 1 || in->H > BVIO_HMAX) return fail(ctx, BVIO_ERR_INVALID, "H out of range [1,16]");
+  if (!in->horizon_pos || !in->horizon_quat) return fail(ctx, BVIO_ERR_INVALID, "null horizon");
+  if (in->N < 0 || in->U < 0 || in->C < 0 || in->kappa < 0 || in->nr_imu < 1)
+    return fail(ctx, BVIO_ERR_INVALID, "negative size / nr_imu < 1");
+  if (in->N > 0 && (!in->cand_id || !in->cand_xy || !in->cand_prob)) return fail(ctx, BVIO_ERR_INVALID, "null candidates");
+  if (in->U > 0 && !in->used_xy) return fail(ctx, BVIO_ERR_INVALID, "null used_xy");
+  if (in->C > 0 && (!in->cloud_xy || !in->cloud_depth)) return fail(ctx, BVIO_ERR_INVALID, "null cloud");
+  return BVIO_OK;
+}
+
+static int sel_upload_impl(bvio_ctx* ctx, const bvio_select_in* in, bool use_cache, bool sharded, bvio_selprob** out) {
+  int rc = sel_validate(ctx, in);
+  if (rc) return rc;
+  if (!out) return fail(ctx, BVIO_ERR_INVALID, "null out");
+  *out = nullptr;
+  if (sharded && !ctx->comm) return fail(ctx, BVIO_ERR_NCCL, "bvio_comm_init has not been called");
+  cudaSetDevice(ctx->device);
+  if (sel_configure() != 0) return fail(ctx, BVIO_ERR_CUDA, "sel_configure failed");
+  bvio_selprob* pr = new (std::nothrow) bvio_selprob();
+  if (!pr) return fail(ctx, BVIO_ERR_INVALID, "out of host memory");
+  SelProb& sp = pr->sp;
+  memset(&sp, 0, sizeof sp);
+  const int H = in->H, T = 3 * H, TT = T * (T + 1) / 2, D = 9 * (H + 1), N = in->N, U = in->U, C = in->C;
+  sp.H = H; sp.T = T; sp.TT = TT; sp.D = D; sp.Do = D - T;
+  sp.N = N; sp.U = U; sp.C = C; sp.kappa = in->kappa; sp.nr_imu = in->nr_imu;
+  sp.rank = sharded ? ctx->rank : 0;
+  sp.world = sharded ? ctx->world : 1;
+  // contiguous blocks of ceil(N/world) candidates per rank (ascending id => rank-independent tie-breaking)
+  const int per = (N + sp.world - 1) / sp.world;
+  sp.c0 = std::min(N, sp.rank * per);
+  sp.c1 = std::min(N, (sp.rank + 1) * per);
+  const int nloc = sp.c1 - sp.c0;
+  sp.grid_round = std::max(1, std::min((nloc + SEL_WARPS - 1) / SEL_WARPS, 4 * ctx->sm_count));
+  sp.delta_imu = in->delta_imu; sp.acc_var = in->acc_var; sp.acc_bias_var = in->acc_bias_var;
+  for (int i = 0; i < 4; i++) sp.q_ic[i] = in->q_ic[i];
+  for (int i = 0; i < 3; i++) sp.t_ic[i] = in->t_ic[i];
+  sp.cam = in->cam;
+  pr->sharded = sharded;
+  pr->cand_id.assign(in->cand_id, in->cand_id + N);
+
+  Carver cv;
+  const size_t Dd = sizeof(double), I = sizeof(int);
+  size_t o_hpos = cv.take((size_t)(H + 1) * 3 * Dd), o_hquat = cv.take((size_t)(H + 1) * 4 * Dd);
+  size_t o_cxy = cv.take((size_t)N * 2 * Dd), o_cp = cv.take((size_t)N * Dd);
+  size_t o_uxy = cv.take((size_t)U * 2 * Dd);
+  size_t o_clxy = cv.take((size_t)C * 2 * Dd), o_cld = cv.take((size_t)C * Dd);
+  pr->in_bytes = cv.off;
+  pr->out_off = cv.off;
+  pr->o_out_idx = cv.take((size_t)std::max(1, in->kappa) * I);
+  pr->o_out_val = cv.take((size_t)std::max(1, in->kappa) * Dd);
+  pr->o_ctrl = cv.take(sizeof(SelCtrl));
+  pr->out_bytes = cv.off - pr->out_off;
+  const size_t h_bytes = cv.off;
+  size_t o_Cc = cv.take((size_t)N * TT * Dd), o_Cu = cv.take((size_t)U * TT * Dd);
+  size_t o_valid = cv.take((size_t)N * I), o_valid_u = cv.take((size_t)U * I), o_taken = cv.take((size_t)N * I);
+  size_t o_depth = cv.take((size_t)(N + U) * Dd);
+  size_t o_pair = cv.take((size_t)H * 324 * Dd), o_omega = cv.take((size_t)D * D * Dd), o_R = cv.take((size_t)TT * Dd);
+  size_t o_blk = cv.take((size_t)sp.grid_round * 4 * Dd);
+  size_t o_send = cv.take((size_t)(SEL_REC_HDR + TT) * Dd), o_all = cv.take((size_t)sp.world * (SEL_REC_HDR + TT) * Dd);
+  size_t o_counts = cv.take(2 * sizeof(unsigned long long));
+  const size_t d_bytes = cv.off;
+
+  cudaError_t ce;
+  if (use_cache) ce = slab_acquire(ctx->sel_cache, ctx->sel_cache_busy, d_bytes, h_bytes, pr->slab, pr->from_cache);
+  else {
+    bool busy = true;
+    Slab none;
+    ce = slab_acquire(none, busy, d_bytes, h_bytes, pr->slab, pr->from_cache);
+  }
+  if (ce != cudaSuccess) { delete pr; return fail(ctx, BVIO_ERR_CUDA, std::string("slab alloc: ") + cudaGetErrorString(ce)); }
+  char* d = pr->slab.d;
+  char* h = pr->slab.h;
+  memcpy(h + o_hpos, in->horizon_pos, (size_t)(H + 1) * 3 * Dd);
+  memcpy(h + o_hquat, in->horizon_quat, (size_t)(H + 1) * 4 * Dd);
+  if (N) { memcpy(h + o_cxy, in->cand_xy, (size_t)N * 2 * Dd); memcpy(h + o_cp, in->cand_prob, (size_t)N * Dd); }
+  if (U) memcpy(h + o_uxy, in->used_xy, (size_t)U * 2 * Dd);
+  if (C) { memcpy(h + o_clxy, in->cloud_xy, (size_t)C * 2 * Dd); memcpy(h + o_cld, in->cloud_depth, (size_t)C * Dd); }
+  sp.hpos = (const double*)(d + o_hpos); sp.hquat = (const double*)(d + o_hquat);
+  sp.cand_xy = (const double2*)(d + o_cxy); sp.cand_prob = (const double*)(d + o_cp);
+  sp.used_xy = (const double2*)(d + o_uxy);
+  sp.cloud_xy = (const double2*)(d + o_clxy); sp.cloud_depth = (const double*)(d + o_cld);
+  sp.out_idx = (int*)(d + pr->o_out_idx); sp.out_val = (double*)(d + pr->o_out_val); sp.ctrl = (SelCtrl*)(d + pr->o_ctrl);
+  sp.Cc = (double*)(d + o_Cc); sp.Cu = (double*)(d + o_Cu);
+  sp.valid = (int*)(d + o_valid); sp.valid_u = (int*)(d + o_valid_u); sp.taken = (int*)(d + o_taken);
+  sp.depth = (double*)(d + o_depth); sp.pair = (double*)(d + o_pair); sp.omega = (double*)(d + o_omega);
+  sp.R = (double*)(d + o_R); sp.blk_best = (double*)(d + o_blk);
+  sp.rec_send = (double*)(d + o_send); sp.rec_all = (double*)(d + o_all);
+  pr->counts = (unsigned long long*)(d + o_counts);
+  cudaError_t e = cudaMemcpyAsync(d, h, pr->in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    slab_release(pr->slab, ctx->sel_cache_busy, pr->from_cache);
+    delete pr;
+    return fail(ctx, BVIO_ERR_CUDA, std::string("select upload: ") + cudaGetErrorString(e));
+  }
+  *out = pr;
+  return BVIO_OK;
+}
+
+static int sel_enqueue(bvio_ctx* ctx, bvio_selprob* pr, cudaStream_t st, int* nccl_rc) {
+  const SelProb& sp = pr->sp;
+  int n = 0;
+  *nccl_rc = 0;
+  n += sel_launch_reset(sp, st);
+  n += sel_launch_build(sp, st);
+  const size_t RS = SEL_REC_HDR + sp.TT;
+  for (int it = 0; it < sp.kappa; it++) {
+    n += sel_launch_round(sp, st);
+    if (sp.world > 1) {
+      int r = g_nccl.AllGather(sp.rec_send, sp.rec_all, RS, kNcclFloat64, ctx->comm, st);
+      if (r) { *nccl_rc = r; return n; }
+      n += sel_launch_apply(sp, st);
+    }
+  }
+  n += sel_launch_final(sp, st);
+  if (sp.world > 1) {
+    n += sel_launch_counts(sp, pr->counts, 0, st);
+    int r = g_nccl.AllReduce(pr->counts, pr->counts, 2, kNcclUint64, kNcclSum, ctx->comm, st);
+    if (r) { *nccl_rc = r; return n; }
+    n += sel_launch_counts(sp, pr->counts, 1, st);
+  }
+  return n;
+}
+
+extern "C" {
+
+void bvio_sel_ctx_destroy(bvio_ctx* ctx) {
+  if (ctx && ctx->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+}
+
+int bvio_select_upload(bvio_ctx* ctx, const bvio_select_in* in, bvio_selprob** out) {
+  return sel_upload_impl(ctx, in, false, ctx && ctx->comm && ctx->world > 1, out);
+}
+
+int bvio_select_run(bvio_ctx* ctx, bvio_selprob* pr) {
+  if (!ctx || !pr) return fail(ctx, BVIO_ERR_INVALID, "null problem");
+  cudaSetDevice(ctx->device);
+  int nrc = 0;
+  BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (pr->use_graph) {
+    if (!pr->graph) {
+      cudaGraph_t g = nullptr;
+      BVIO_CUDA_OK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      pr->launches_per_run = sel_enqueue(ctx, pr, ctx->stream, &nrc);
+      cudaError_t ee = cudaStreamEndCapture(ctx->stream, &g);
+      if (nrc) return fail(ctx, BVIO_ERR_NCCL, std::string("nccl: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+      BVIO_CUDA_OK(ctx, ee);
+      BVIO_CUDA_OK(ctx, cudaGraphInstantiate(&pr->graph, g, 0));
+      cudaGraphDestroy(g);
+      BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    }
+    BVIO_CUDA_OK(ctx, cudaGraphLaunch(pr->graph, ctx->stream));
+    ctx->launches += pr->launches_per_run;
+  } else {
+    ctx->launches += sel_enqueue(ctx, pr, ctx->stream, &nrc);
+    if (nrc) return fail(ctx, BVIO_ERR_NCCL, std::string("nccl: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+  }
+  BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  BVIO_CUDA_OK(ctx, cudaGetLastError());
+  return BVIO_OK;
+}
+
+int bvio_select_fetch(bvio_ctx* ctx, bvio_selprob* pr, int32_t* out_ids, double* out_values, bvio_select_summary* summary) {
+  if (!ctx || !pr) return fail(ctx, BVIO_ERR_INVALID, "null problem");
+  cudaSetDevice(ctx->device);
+  char* ho = pr->slab.h + pr->out_off;
+  BVIO_CUDA_OK(ctx, cudaMemcpyAsync(ho, pr->slab.d + pr->out_off, pr->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  BVIO_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  const int* idx = (const int*)(pr->slab.h + pr->o_out_idx);
+  const double* val = (const double*)(pr->slab.h + pr->o_out_val);
+  const SelCtrl* c = (const SelCtrl*)(pr->slab.h + pr->o_ctrl);
+  for (int i = 0; i < c->n_selected; i++) {
+    if (out_ids) out_ids[i] = pr->cand_id[idx[i]];
+    if (out_values) out_values[i] = val[i];
+  }
+  if (summary) {
+    summary->n_selected = c->n_selected;
+    summary->n_candidates_valid = c->n_valid;
+    summary->candidates_scored = (int64_t)c->scored;
+    summary->final_logdet = c->final_logdet;
+    summary->min_margin = c->min_margin;
+    summary->device_ms = ms;
+  }
+  return BVIO_OK;
+}
+
+void bvio_select_free(bvio_ctx* ctx, bvio_selprob* pr) {
+  if (!pr) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (pr->graph) cudaGraphExecDestroy(pr->graph);
+  bool dummy = true;
+  slab_release(pr->slab, ctx ? ctx->sel_cache_busy : dummy, pr->from_cache);
+  delete pr;
+}
+
+static int select_impl(bvio_ctx* ctx, const bvio_select_in* in, bool sharded, int32_t* out_ids, double* out_values,
+                       bvio_select_summary* summary) {
+  bvio_selprob* pr = nullptr;
+  int rc = sel_upload_impl(ctx, in, true, sharded, &pr);
+  if (rc) return rc;
+  pr->use_graph = false;
+  rc = bvio_select_run(ctx, pr);
+  if (rc == BVIO_OK) rc = bvio_select_fetch(ctx, pr, out_ids, out_values, summary);
+  bvio_select_free(ctx, pr);
+  return rc;
+}
+
+int bvio_select(bvio_ctx* ctx, const bvio_select_in* in, int32_t* out_ids, double* out_values, bvio_select_summary* summary) {
+  return select_impl(ctx, in, false, out_ids, out_values, summary);
+}
+
+int bvio_select_sharded(bvio_ctx* ctx, const bvio_select_in* in, int32_t* out_ids, double* out_values,
+                        bvio_select_summary* summary) {
+  return select_impl(ctx, in, true, out_ids, out_values, summary);
+}
+
+int bvio_nccl_unique_id(void* uid128) {
+  if (!uid128 || !nccl_load()) return BVIO_ERR_NCCL;
+  nccl_uid_t id;
+  if (g_nccl.GetUniqueId(&id)) return BVIO_ERR_NCCL;
+  memcpy(uid128, &id, sizeof id);
+  return BVIO_OK;
+}
+
+int bvio_comm_init(bvio_ctx* ctx, const void* uid128, int32_t rank, int32_t world) {
+  if (!ctx || !uid128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, BVIO_ERR_INVALID, "bad comm arguments");
+  if (!nccl_load()) return fail(ctx, BVIO_ERR_NCCL, "libnccl.so.2 not found");
+  cudaSetDevice(ctx->device);
+  if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  nccl_uid_t id;
+  memcpy(&id, uid128, sizeof id);
+  int r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+  if (r) return fail(ctx, BVIO_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  ctx->rank = rank; ctx->world = world;
+  return BVIO_OK;
+}
+
+int bvio_debug_build_delta(bvio_ctx* ctx, const bvio_select_in* in, double* Cout, int32_t* valid, double* omega) {
+  bvio_selprob* pr = nullptr;
+  int rc = sel_upload_impl(ctx, in, false, false, &pr);
+  if (rc) return rc;
+  const SelProb& sp = pr->sp;
+  ctx->launches += sel_launch_reset(sp, ctx->stream);
+  ctx->launches += sel_launch_build(sp, ctx->stream);
+  cudaError_t e = cudaGetLastError();
+  double* dfull = nullptr;
+  if (e == cudaSuccess && Cout && sp.N) {
+    e = cudaMalloc((void**)&dfull, sizeof(double) * (size_t)sp.N * sp.T * sp.T);
+    if (e == cudaSuccess) { ctx->launches += sel_launch_expand(sp, dfull, ctx->stream); e = cudaGetLastError(); }
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && dfull) e = cudaMemcpy(Cout, dfull, sizeof(double) * (size_t)sp.N * sp.T * sp.T, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && valid && sp.N) e = cudaMemcpy(valid, sp.valid, sizeof(int) * sp.N, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && omega) e = cudaMemcpy(omega, sp.omega, sizeof(double) * (size_t)sp.D * sp.D, cudaMemcpyDeviceToHost);
+  if (dfull) cudaFree(dfull);
+  bvio_select_free(ctx, pr);
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("debug_build_delta: ") + cudaGetErrorString(e));
+  return BVIO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,526 @@
+// sel_kernels.cu -- anticipated feature selection on sm_100a (FP64).  Replaces the numerical part of
+// FeatureSelector::select (vins_estimator/src/feature_selector.cpp:139-170):
+//
+//   sel_build   calcInfoFromFeatures + findNNDepth + inFOV (feature_selector.cpp:239-376, 437-459) and
+//               PinholeCamera::spaceToPlane (camera_model/src/camera_models/PinholeCamera.cc:520-542):
+//               one warp per candidate, lane = horizon frame; writes the packed T x T position block
+//   sel_omega   calcInfoFromRobotMotion + createLinearImuMatrices + addOmegaPrior
+//               (feature_selector.cpp:463-609), adds the tracked features' blocks (:620-623) and
+//               Schur-complements the non-position variables once (see sel.h)
+//   sel_round   one greedy round of selectInformativeFeatures (feature_selector.cpp:633-682): one warp per
+//               remaining candidate computes logdet(R + p C_ell) by an in-warp Cholesky (the value the
+//               reference gets from Utility::logdet, utility.h:143-167); the last CTA picks the arg-max
+//               and applies Omega_S += p Delta (:674)
+//   sel_apply   multi-GPU: pick among the gathered per-rank winner records, identical on every rank
+#include "sel.h"
+#include <float.h>
+
+namespace bvio {
+
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
+__device__ __forceinline__ d3 normalized3(d3 a) {
+  double n = sqrt(dot3(a, a));
+  return {a.x / n, a.y / n, a.z / n};
+}
+__device__ __forceinline__ void tri_decode(int e, int& i, int& j) {
+  i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+  while (i * (i + 1) / 2 > e) i--;
+  while ((i + 1) * (i + 2) / 2 <= e) i++;
+  j = e - i * (i + 1) / 2;
+}
+
+// =============================================================================================
+__global__ void sel_reset_kernel(SelProb sp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int k = i; k < sp.N; k += stride) { sp.taken[k] = 0; sp.valid[k] = 0; }
+  for (int k = i; k < sp.kappa; k += stride) { sp.out_idx[k] = -1; sp.out_val[k] = 0.0; }
+  if (i == 0) {
+    SelCtrl c;
+    c.scored = 0; c.min_margin = INFINITY; c.logdet_oo = 0; c.final_logdet = 0;
+    c.n_selected = 0; c.round = 0; c.n_valid = 0; c.pad = 0; c.ticket = 0; c.pad2 = 0;
+    *sp.ctrl = c;
+  }
+}
+
+// =============================================================================================
+// build: one warp per feature (local candidates, then the tracked features)
+// =============================================================================================
+__global__ void __launch_bounds__(32 * SEL_WARPS) sel_build_kernel(SelProb sp) {
+  __shared__ double sC[SEL_WARPS][BVIO_HMAX * 9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nloc = sp.c1 - sp.c0, H = sp.H;
+  const int f = blockIdx.x * SEL_WARPS + warp;
+  if (f >= nloc + sp.U) return;
+  const bool is_used = f >= nloc;
+  const int idx = is_used ? f - nloc : sp.c0 + f;
+  const double2 xy = is_used ? sp.used_xy[idx] : sp.cand_xy[idx];
+  // findNNDepth (feature_selector.cpp:437-459): exact 1-NN, first-found minimum
+  double bd = DBL_MAX;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < sp.C; i += 32) {
+    double dx = sp.cloud_xy[i].x - xy.x, dy = sp.cloud_xy[i].y - xy.y;
+    double d = dx * dx + dy * dy;
+    if (d < bd) { bd = d; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double od = __shfl_xor_sync(0xffffffffu, bd, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+  }
+  if (bi == 0x7fffffff) bi = 0;
+  const double depth = sp.C > 0 ? sp.cloud_depth[bi] : 1.0;
+
+  const q4 qic{sp.q_ic[0], sp.q_ic[1], sp.q_ic[2], sp.q_ic[3]};
+  const d3 tic{sp.t_ic[0], sp.t_ic[1], sp.t_ic[2]};
+  const d3 P1{sp.hpos[3], sp.hpos[4], sp.hpos[5]};
+  const q4 Q1{sp.hquat[4], sp.hquat[5], sp.hquat[6], sp.hquat[7]};
+  const d3 t_wc1 = P1 + qrot(Q1, tic);
+  const q4 q_wc1 = qmul(Q1, qic);
+  d3 feat = normalized3(d3{xy.x, xy.y, 1.0});
+  feat = depth * feat;
+  const d3 pell = t_wc1 + qrot(q_wc1, feat);
+
+  const int h = lane + 1;
+  bool vis = false;
+  double Cm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (h <= H) {
+    d3 u;
+    q4 qwc;
+    if (h == 1) {
+      u = normalized3(feat); qwc = q_wc1; vis = true;
+    } else {
+      const q4 Qh{sp.hquat[4 * h], sp.hquat[4 * h + 1], sp.hquat[4 * h + 2], sp.hquat[4 * h + 3]};
+      const d3 t_wch = d3{sp.hpos[3 * h], sp.hpos[3 * h + 1], sp.hpos[3 * h + 2]} + qrot(Qh, tic);
+      qwc = qmul(Qh, qic);
+      u = normalized3(qrot(qinv(qwc), pell - t_wch));
+      // PinholeCamera::spaceToPlane with radtan distortion, then inFOV (round to int pixel)
+      const bvio_camera& c = sp.cam;
+      double mx = u.x / u.z, my = u.y / u.z;
+      double mx2 = mx * mx, my2 = my * my, mxy = mx * my, rho2 = mx2 + my2;
+      double rad = c.k1 * rho2 + c.k2 * rho2 * rho2;
+      double ddx = mx * rad + 2.0 * c.p1 * mxy + c.p2 * (rho2 + 2.0 * mx2);
+      double ddy = my * rad + 2.0 * c.p2 * mxy + c.p1 * (rho2 + 2.0 * my2);
+      double pu = c.fx * (mx + ddx) + c.cx, pv = c.fy * (my + ddy) + c.cy;
+      double ru = round(pu), rv = round(pv);
+      vis = (0.0 <= ru && ru < (double)c.width) && (0.0 <= rv && rv < (double)c.height);
+    }
+    if (vis) {
+      // B_h = [u]x * ((q_WC_h * q_IC)^-1).R  -- q_IC applied twice, as the reference does (:304, :321)
+      double Rm[9], Bm[9];
+      qmat(qinv(qmul(qwc, qic)), Rm);
+      const double sk[9] = {0, -u.z, u.y, u.z, 0, -u.x, -u.y, u.x, 0};
+      mm3(sk, Rm, Bm);
+      mtm3(Bm, Bm, Cm);
+    }
+  }
+  const unsigned vm = __ballot_sync(0xffffffffu, vis && h >= 2);
+  const bool ok = (1 + __popc(vm)) > 1;
+  if (lane == 0) {
+    if (is_used) sp.valid_u[idx] = ok; else { sp.valid[idx] = ok; if (ok) atomicAdd(&sp.ctrl->n_valid, 1); }
+    sp.depth[is_used ? sp.N + idx : idx] = depth;
+  }
+  if (!ok) return;
+  double* myC = sC[warp];
+  if (h <= H) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) myC[(h - 1) * 9 + k] = Cm[k];
+  }
+  __syncwarp();
+  // EtE in the reference's summation order: h = 2..H, then the k+1 block (:307-326)
+  double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int hh = 2; hh <= H; hh++)
+#pragma unroll
+    for (int k = 0; k < 9; k++) E[k] += myC[(hh - 1) * 9 + k];
+#pragma unroll
+  for (int k = 0; k < 9; k++) E[k] += myC[k];
+  // Eigen fixed-size 3x3 inverse: cofactors / determinant
+  double W[9];
+  {
+    double c00 = E[4] * E[8] - E[5] * E[7], c01 = E[2] * E[7] - E[1] * E[8], c02 = E[1] * E[5] - E[2] * E[4];
+    double c10 = E[5] * E[6] - E[3] * E[8], c11 = E[0] * E[8] - E[2] * E[6], c12 = E[2] * E[3] - E[0] * E[5];
+    double c20 = E[3] * E[7] - E[4] * E[6], c21 = E[1] * E[6] - E[0] * E[7], c22 = E[0] * E[4] - E[1] * E[3];
+    double det = E[0] * c00 + E[1] * c10 + E[2] * c20, id = 1.0 / det;
+    W[0] = id * c00; W[1] = id * c01; W[2] = id * c02; W[3] = id * c10; W[4] = id * c11; W[5] = id * c12;
+    W[6] = id * c20; W[7] = id * c21; W[8] = id * c22;
+  }
+  double* out = (is_used ? sp.Cu : sp.Cc) + (size_t)idx * sp.TT;
+  const int npairs = H * (H + 1) / 2;
+  for (int pr = lane; pr < npairs; pr += 32) {
+    int i, j;
+    tri_decode(pr, i, j);   // 0-based frames i >= j  (reference's i,j = 1..H)
+    double CW[9], Dij[9];
+    mm3(myC + i * 9, W, CW);
+    mmt3(CW, myC + j * 9, Dij);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        if (i == j && b > a) continue;
+        double lo = (i == j) ? myC[i * 9 + a * 3 + b] - Dij[a * 3 + b] : -Dij[a * 3 + b];
+        out[tri(3 * i + a, 3 * j + b)] = lo;
+      }
+  }
+}
+
+// =============================================================================================
+// omega: one CTA
+// =============================================================================================
+__global__ void __launch_bounds__(256) sel_omega_kernel(SelProb sp) {
+  extern __shared__ double sm[];
+  const int H = sp.H, D = sp.D, T = sp.T, Do = sp.Do, tid = threadIdx.x, nt = blockDim.x;
+  double* M = sm;
+  int* oi = reinterpret_cast<int*>(M + (size_t)D * D);
+  int* pi = oi + Do;
+  // ---- createLinearImuMatrices per consecutive pair (feature_selector.cpp:531-598)
+  if (tid < H) {
+    const int h = tid + 1;
+    const q4 Qi{sp.hquat[4 * (h - 1)], sp.hquat[4 * (h - 1) + 1], sp.hquat[4 * (h - 1) + 2], sp.hquat[4 * (h - 1) + 3]};
+    const q4 Qj{sp.hquat[4 * h], sp.hquat[4 * h + 1], sp.hquat[4 * h + 2], sp.hquat[4 * h + 3]};
+    const int nr = sp.nr_imu;
+    double Nij[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Mij[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double c11 = 0, c12 = 0;
+    for (int i = 0; i < nr; ++i) {
+      q4 q = qslerp(Qi, i / (double)nr, Qj);
+      double jkh = nr - i - 0.5, Rm[9];
+      qmat(q, Rm);
+#pragma unroll
+      for (int k = 0; k < 9; k++) { Nij[k] += jkh * Rm[k]; Mij[k] += Rm[k]; }
+      c11 += jkh * jkh;
+      c12 += jkh;
+    }
+    const double dI = sp.delta_imu, d2 = dI * dI, d3v = d2 * dI, d4 = d3v * dI;
+    const double a = 1.0 * nr * c11 * d4 * sp.acc_var, b = 1.0 * c12 * d3v * sp.acc_var;
+    const double c = 1.0 * nr * d2 * sp.acc_var, e = 1.0 * nr * sp.acc_bias_var;
+    // covImu = [[aI bI 0],[bI cI 0],[0 0 eI]]: inverse in closed form
+    const double det = a * c - b * b;
+    double* Wm = sp.pair + (size_t)(h - 1) * 324;
+    double* Am = Wm + 81;
+    for (int k = 0; k < 162; k++) Wm[k] = 0.0;
+    for (int k = 0; k < 3; k++) {
+      Wm[k * 9 + k] = c / det; Wm[k * 9 + 3 + k] = -b / det; Wm[(3 + k) * 9 + k] = -b / det;
+      Wm[(3 + k) * 9 + 3 + k] = a / det; Wm[(6 + k) * 9 + 6 + k] = 1.0 / e;
+    }
+    for (int k = 0; k < 9; k++) Am[k * 9 + k] = -1.0;
+    for (int k = 0; k < 3; k++) Am[k * 9 + 3 + k] = -1.0 * nr * dI;
+    for (int r = 0; r < 3; r++)
+      for (int cc = 0; cc < 3; cc++) { Am[r * 9 + 6 + cc] = d2 * Nij[r * 3 + cc]; Am[(3 + r) * 9 + 6 + cc] = dI * Mij[r * 3 + cc]; }
+  }
+  __syncthreads();
+  for (int e = tid; e < H * 81; e += nt) {
+    int hh = e / 81, rc = e - hh * 81, r = rc / 9, c = rc - r * 9;
+    const double* Wm = sp.pair + (size_t)hh * 324;
+    const double* Am = Wm + 81;
+    double s = 0;
+    for (int k = 0; k < 9; k++) s += Am[k * 9 + r] * Wm[k * 9 + c];
+    sp.pair[(size_t)hh * 324 + 162 + rc] = s;   // A^T W
+  }
+  __syncthreads();
+  for (int e = tid; e < H * 81; e += nt) {
+    int hh = e / 81, rc = e - hh * 81, r = rc / 9, c = rc - r * 9;
+    const double* Am = sp.pair + (size_t)hh * 324 + 81;
+    const double* AtW = sp.pair + (size_t)hh * 324 + 162;
+    double s = 0;
+    for (int k = 0; k < 9; k++) s += AtW[r * 9 + k] * Am[k * 9 + c];
+    sp.pair[(size_t)hh * 324 + 243 + rc] = s;   // A^T W A
+  }
+  __syncthreads();
+  // ---- block-tridiagonal Omega_kkH (feature_selector.cpp:507-523) + I9 prior (:605-608)
+  for (int e = tid; e < D * D; e += nt) {
+    int i = e / D, j = e - i * D, bi = i / 9, bj = j / 9, a = i - bi * 9, b = j - bj * 9;
+    double v = 0;
+    if (bi == bj) {
+      if (bi >= 1) v += sp.pair[(size_t)(bi - 1) * 324 + a * 9 + b];
+      if (bi < H) v += sp.pair[(size_t)bi * 324 + 243 + a * 9 + b];
+      if (bi == 0 && a == b) v += 1.0;
+    } else if (bj == bi + 1) {
+      v = sp.pair[(size_t)(bj - 1) * 324 + 162 + a * 9 + b];
+    } else if (bi == bj + 1) {
+      v = sp.pair[(size_t)(bi - 1) * 324 + 162 + b * 9 + a];
+    }
+    M[e] = v;
+    sp.omega[e] = v;
+  }
+  if (tid == 0) {
+    int no = 0, npos = 0;
+    for (int i = 0; i < D; i++) {
+      int blk = i / 9, a = i - blk * 9;
+      if (blk >= 1 && a < 3) pi[npos++] = i; else oi[no++] = i;
+    }
+  }
+  __syncthreads();
+  // ---- Omega += Delta_used (feature_selector.cpp:620-623)
+  for (int e = tid; e < T * T; e += nt) {
+    int t1 = e / T, t2 = e - t1 * T;
+    int lo = t1 >= t2 ? tri(t1, t2) : tri(t2, t1);
+    double v = M[pi[t1] * D + pi[t2]];
+    for (int u = 0; u < sp.U; u++)
+      if (sp.valid_u[u]) v += sp.Cu[(size_t)u * sp.TT + lo];
+    M[pi[t1] * D + pi[t2]] = v;
+  }
+  __syncthreads();
+  // ---- Cholesky of M_oo (in place, through the index map)
+  for (int k = 0; k < Do; k++) {
+    const int ok = oi[k];
+    const double d = sqrt(M[ok * D + ok]);
+    __syncthreads();
+    if (tid == 0) M[ok * D + ok] = d;
+    for (int i = k + 1 + tid; i < Do; i += nt) M[oi[i] * D + ok] /= d;
+    __syncthreads();
+    const int m = Do - 1 - k;
+    for (int e = tid; e < m * m; e += nt) {
+      int ii = e / m, jj = e - ii * m;
+      if (jj > ii) continue;
+      int ri = oi[k + 1 + ii], rj = oi[k + 1 + jj];
+      M[ri * D + rj] -= M[ri * D + ok] * M[rj * D + ok];
+    }
+    __syncthreads();
+  }
+  // ---- Y = L^-1 M_op, stored over M_op
+  if (tid < T) {
+    const int pc = pi[tid];
+    for (int i = 0; i < Do; i++) {
+      const int ri = oi[i];
+      double s = M[ri * D + pc];
+      for (int k = 0; k < i; k++) s -= M[ri * D + oi[k]] * M[oi[k] * D + pc];
+      M[ri * D + pc] = s / M[ri * D + ri];
+    }
+  }
+  __syncthreads();
+  // ---- R = S0 = M_pp - Y^T Y ; logdet(M_oo)
+  for (int e = tid; e < T * T; e += nt) {
+    int t1 = e / T, t2 = e - t1 * T;
+    if (t2 > t1) continue;
+    double s = M[pi[t1] * D + pi[t2]];
+    for (int i = 0; i < Do; i++) s -= M[oi[i] * D + pi[t1]] * M[oi[i] * D + pi[t2]];
+    sp.R[tri(t1, t2)] = s;
+  }
+  if (tid == 0) {
+    double ld = 0;
+    for (int i = 0; i < Do; i++) ld += log(M[oi[i] * D + oi[i]]);
+    sp.ctrl->logdet_oo = 2.0 * ld;
+  }
+}
+
+// =============================================================================================
+// in-warp Cholesky of a packed-lower T x T matrix in shared memory; returns sum(log diag(L)) or NaN
+// =============================================================================================
+__device__ __forceinline__ double warp_chol_logdet(double* A, int T, int lane) {
+  bool bad = false;
+  for (int j = 0; j < T; j++) {
+    double d = A[tri(j, j)];
+    if (!(d > 0.0)) { bad = true; break; }
+    d = sqrt(d);
+    const double inv = 1.0 / d;
+    __syncwarp();
+    if (lane == 0) A[tri(j, j)] = d;
+    for (int i = j + 1 + lane; i < T; i += 32) A[tri(i, j)] *= inv;
+    __syncwarp();
+    for (int i = j + 1 + lane; i < T; i += 32) {
+      const double lij = A[tri(i, j)];
+      double* row = A + tri(i, 0);
+      for (int k = j + 1; k <= i; k++) row[k] -= lij * A[tri(k, j)];
+    }
+    __syncwarp();
+  }
+  if (bad) return NAN;
+  double l = 0;
+  for (int i = lane; i < T; i += 32) l += log(A[tri(i, i)]);
+  return warp_sum(l);
+}
+
+__device__ __forceinline__ void merge_best(double& best, double& second, int& idx, double ob, double os, int oidx) {
+  // (best, idx) ordered by value, ties to the smaller candidate index
+  if (ob > best || (ob == best && oidx >= 0 && (idx < 0 || oidx < idx))) {
+    second = fmax(fmax(best, second), os);
+    best = ob; idx = oidx;
+  } else {
+    second = fmax(second, fmax(ob, os));
+  }
+}
+
+// Omega_S += p Delta (feature_selector.cpp:671-681) on the compact state; all threads of one CTA
+__device__ void apply_winner(const SelProb& sp, double best, double second, int idx, double p, const double* C,
+                             unsigned long long cnt) {
+  SelCtrl* c = sp.ctrl;
+  if (idx >= 0) {
+    for (int e = threadIdx.x; e < sp.TT; e += blockDim.x) sp.R[e] += p * C[e];
+  }
+  if (threadIdx.x == 0) {
+    if (idx >= 0) {
+      sp.taken[idx] = 1;
+      sp.out_idx[c->n_selected] = idx;
+      sp.out_val[c->n_selected] = best;
+      c->n_selected++;
+      if (second > -1.0) c->min_margin = fmin(c->min_margin, best - second);
+    }
+    c->scored += cnt;
+    c->round++;
+    c->ticket = 0;
+  }
+}
+
+__global__ void __launch_bounds__(32 * SEL_WARPS) sel_round_kernel(SelProb sp) {
+  extern __shared__ double sm[];
+  const int T = sp.T, TT = sp.TT, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sR = sm;
+  double* A = sR + TT + (size_t)warp * TT;
+  double* sred = sm + (size_t)(1 + SEL_WARPS) * TT;   // [SEL_WARPS*4] then [4] broadcast
+  __shared__ int s_last;
+  for (int e = threadIdx.x; e < TT; e += blockDim.x) sR[e] = sp.R[e];
+  __syncthreads();
+  const double ld_oo = sp.ctrl->logdet_oo;
+  double best = -1.0, second = -INFINITY;   // fMax starts at -1 (feature_selector.cpp:639)
+  int bidx = -1;
+  double cnt = 0;
+  for (int i = sp.c0 + blockIdx.x * SEL_WARPS + warp; i < sp.c1; i += gridDim.x * SEL_WARPS) {
+    if (!sp.valid[i] || sp.taken[i]) continue;
+    const double p = sp.cand_prob[i];
+    const double* Ci = sp.Cc + (size_t)i * TT;
+    for (int e = lane; e < TT; e += 32) A[e] = sR[e] + p * Ci[e];
+    __syncwarp();
+    const double ld = warp_chol_logdet(A, T, lane);
+    const double val = ld_oo + 2.0 * ld;
+    cnt += 1;
+    if (val > best) { second = best; best = val; bidx = i; }
+    else if (val > second) second = val;
+    __syncwarp();
+  }
+  if (lane == 0) { sred[warp * 4] = best; sred[warp * 4 + 1] = second; sred[warp * 4 + 2] = (double)bidx; sred[warp * 4 + 3] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = -1.0, s = -INFINITY, c = 0;
+    int ix = -1;
+    for (int q = 0; q < SEL_WARPS; q++) { merge_best(b, s, ix, sred[q * 4], sred[q * 4 + 1], (int)sred[q * 4 + 2]); c += sred[q * 4 + 3]; }
+    double* bb = sp.blk_best + (size_t)blockIdx.x * 4;
+    bb[0] = b; bb[1] = s; bb[2] = (double)ix; bb[3] = c;
+    __threadfence();
+    unsigned old = atomicAdd(&sp.ctrl->ticket, 1u);
+    s_last = (old == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double* bc = sred + SEL_WARPS * 4;
+  if (threadIdx.x == 0) {
+    double b = -1.0, s = -INFINITY, c = 0;
+    int ix = -1;
+    const volatile double* bb = sp.blk_best;
+    for (unsigned q = 0; q < gridDim.x; q++) { merge_best(b, s, ix, bb[q * 4], bb[q * 4 + 1], (int)bb[q * 4 + 2]); c += bb[q * 4 + 3]; }
+    bc[0] = b; bc[1] = s; bc[2] = (double)ix; bc[3] = c;
+  }
+  __syncthreads();
+  const double b = bc[0], s = bc[1];
+  const int ix = (int)bc[2];
+  const unsigned long long c = (unsigned long long)bc[3];
+  if (sp.world == 1) {
+    apply_winner(sp, b, s, ix, ix >= 0 ? sp.cand_prob[ix] : 0.0, ix >= 0 ? sp.Cc + (size_t)ix * TT : nullptr, c);
+  } else {
+    // this rank's winner record for the exchange
+    double* r = sp.rec_send;
+    if (threadIdx.x == 0) {
+      r[0] = b; r[1] = s; r[2] = (double)ix; r[3] = ix >= 0 ? sp.cand_prob[ix] : 0.0;
+      sp.ctrl->scored += c;
+      sp.ctrl->ticket = 0;
+    }
+    for (int e = threadIdx.x; e < TT; e += blockDim.x) r[SEL_REC_HDR + e] = ix >= 0 ? sp.Cc[(size_t)ix * TT + e] : 0.0;
+  }
+}
+
+// multi-GPU: every rank holds the same gathered records and applies the same update
+__global__ void __launch_bounds__(256) sel_apply_kernel(SelProb sp) {
+  __shared__ double bc[4];
+  const int RS = SEL_REC_HDR + sp.TT;
+  if (threadIdx.x == 0) {
+    double b = -1.0, s = -INFINITY;
+    int ix = -1, who = -1;
+    for (int r = 0; r < sp.world; r++) {
+      const double* rec = sp.rec_all + (size_t)r * RS;
+      int before = ix;
+      merge_best(b, s, ix, rec[0], rec[1], (int)rec[2]);
+      if (ix != before) who = r;
+    }
+    bc[0] = b; bc[1] = s; bc[2] = (double)ix; bc[3] = (double)who;
+  }
+  __syncthreads();
+  const int ix = (int)bc[2], who = (int)bc[3];
+  const double* rec = sp.rec_all + (size_t)(who < 0 ? 0 : who) * RS;
+  apply_winner(sp, bc[0], bc[1], ix, rec[3], rec + SEL_REC_HDR, 0ull);
+}
+
+__global__ void __launch_bounds__(32) sel_final_kernel(SelProb sp) {
+  extern __shared__ double sm[];
+  for (int e = threadIdx.x; e < sp.TT; e += 32) sm[e] = sp.R[e];
+  __syncwarp();
+  double ld = warp_chol_logdet(sm, sp.T, threadIdx.x);
+  if (threadIdx.x == 0) sp.ctrl->final_logdet = sp.ctrl->logdet_oo + 2.0 * ld;
+}
+
+__global__ void sel_expand_kernel(SelProb sp, double* Cfull) {
+  const int T = sp.T;
+  const size_t total = (size_t)sp.N * T * T;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    int f = (int)(e / (T * T)), rc = (int)(e - (size_t)f * T * T), r = rc / T, c = rc - r * T;
+    double v = 0;
+    if (f >= sp.c0 && f < sp.c1 && sp.valid[f]) v = sp.Cc[(size_t)f * sp.TT + (r >= c ? tri(r, c) : tri(c, r))];
+    Cfull[e] = v;
+  }
+}
+
+// multi-GPU finalize: dir 0 packs (scored, n_valid) for the all-reduce, dir 1 writes the sums back
+__global__ void sel_counts_kernel(SelProb sp, unsigned long long* buf, int dir) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (dir == 0) { buf[0] = sp.ctrl->scored; buf[1] = (unsigned long long)sp.ctrl->n_valid; }
+  else { sp.ctrl->scored = buf[0]; sp.ctrl->n_valid = (int)buf[1]; }
+}
+int sel_launch_counts(const SelProb& sp, unsigned long long* buf, int dir, cudaStream_t st) {
+  sel_counts_kernel<<<1, 32, 0, st>>>(sp, buf, dir);
+  return 1;
+}
+
+// =============================================================================================
+size_t sel_omega_smem_bytes(int H) {
+  int D = 9 * (H + 1);
+  return sizeof(double) * (size_t)D * D + sizeof(int) * (size_t)D + 16;
+}
+static size_t round_smem(int TT) { return sizeof(double) * ((size_t)(1 + SEL_WARPS) * TT + SEL_WARPS * 4 + 4); }
+
+static bool g_sel_configured = false;
+int sel_configure(void) {
+  if (g_sel_configured) return 0;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(sel_omega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sel_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+  g_sel_configured = true;
+  return 0;
+}
+int sel_launch_reset(const SelProb& sp, cudaStream_t st) {
+  int blocks = (sp.N + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  sel_reset_kernel<<<blocks, 256, 0, st>>>(sp);
+  return 1;
+}
+int sel_launch_build(const SelProb& sp, cudaStream_t st) {
+  int nf = (sp.c1 - sp.c0) + sp.U, n = 0;
+  if (nf > 0) { sel_build_kernel<<<(nf + SEL_WARPS - 1) / SEL_WARPS, 32 * SEL_WARPS, 0, st>>>(sp); n++; }
+  sel_omega_kernel<<<1, 256, sel_omega_smem_bytes(sp.H), st>>>(sp);
+  return n + 1;
+}
+int sel_launch_round(const SelProb& sp, cudaStream_t st) {
+  sel_round_kernel<<<sp.grid_round, 32 * SEL_WARPS, round_smem(sp.TT), st>>>(sp);
+  return 1;
+}
+int sel_launch_apply(const SelProb& sp, cudaStream_t st) {
+  sel_apply_kernel<<<1, 256, 0, st>>>(sp);
+  return 1;
+}
+int sel_launch_final(const SelProb& sp, cudaStream_t st) {
+  sel_final_kernel<<<1, 32, sizeof(double) * sp.TT, st>>>(sp);
+  return 1;
+}
+int sel_launch_expand(const SelProb& sp, double* Cfull, cudaStream_t st) {
+  sel_expand_kernel<<<296, 256, 0, st>>>(sp, Cfull);
+  return 1;
+}
+
+}  // namespace bvio
