@@ -95,7 +95,7 @@ struct BaBatch {                  // all pointers are device pointers
 // launchers (ba_kernels.cu); all asynchronous on `st`; return number of kernels launched
 int ba_launch_prepare(const BaBatch& bt, cudaStream_t st);
 int ba_launch_reset(const BaBatch& bt, cudaStream_t st);
-int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step);
+int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cudaEvent_t* ev = nullptr);  // ev[4]: before/after each kernel
 int ba_launch_finish(const BaBatch& bt, cudaStream_t st);
 size_t ba_linearize_smem_bytes(int K, int nwarps);
 int ba_pick_linearize_warps(int K);

@@ -423,6 +423,37 @@ int bvio_debug_linearize(bvio_ctx* ctx, const bvio_window* window, const bvio_op
   return BVIO_OK;
 }
 
+// Per-kernel device time of one solve (bench.py roofline): direct launches with an event between
+// kernels.  out_ms = {linearize, solve, cost, total of the three}, summed over all passes;
+// out_launches = {linearize, solve, cost} launch counts.
+int bvio_batch_solve_timed(bvio_ctx* ctx, bvio_batch* bb, double out_ms[4], int32_t out_launches[3]) {
+  if (!ctx || !bb || !out_ms) return fail(ctx, BVIO_ERR_INVALID, "null argument");
+  cudaSetDevice(ctx->device);
+  const int passes = bb->bt.max_iters + 1;
+  std::vector<cudaEvent_t> ev((size_t)passes * 4);
+  for (auto& e : ev) BVIO_CUDA_OK(ctx, cudaEventCreate(&e));
+  ctx->launches += ba_launch_reset(bb->bt, ctx->stream);
+  for (int it = 0; it < passes; it++)
+    ctx->launches += ba_launch_iteration(bb->bt, ctx->stream, it < bb->bt.max_iters, &ev[(size_t)it * 4]);
+  ctx->launches += ba_launch_finish(bb->bt, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  out_ms[0] = out_ms[1] = out_ms[2] = out_ms[3] = 0;
+  int nl[3] = {0, 0, 0};
+  for (int it = 0; it < passes && e == cudaSuccess; it++) {
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, ev[it * 4], ev[it * 4 + 1]);
+    cudaEventElapsedTime(&b, ev[it * 4 + 1], ev[it * 4 + 2]);
+    cudaEventElapsedTime(&c, ev[it * 4 + 2], ev[it * 4 + 3]);
+    out_ms[0] += a; out_ms[1] += b; nl[0]++; nl[1]++;
+    if (it < bb->bt.max_iters) { out_ms[2] += c; nl[2]++; }
+  }
+  out_ms[3] = out_ms[0] + out_ms[1] + out_ms[2];
+  if (out_launches) { out_launches[0] = nl[0]; out_launches[1] = nl[1]; out_launches[2] = nl[2]; }
+  for (auto& x : ev) cudaEventDestroy(x);
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("solve_timed: ") + cudaGetErrorString(e));
+  return BVIO_OK;
+}
+
 int bvio_marginalize(bvio_ctx* ctx, const bvio_window*, const bvio_opts*, int32_t, bvio_prior_out*) {
   return fail(ctx, BVIO_ERR_UNSUPPORTED, "bvio_marginalize: not implemented yet (SURVEY.md row f1)");
 }

@@ -29,6 +29,7 @@ __constant__ unsigned char c_tri30B[465];
 
 constexpr int FR = 12;            // per-frame staged state: R (9, row-major) + P (3)
 constexpr int STG = 29;           // per-factor staging stride (28 used; odd => conflict-free)
+constexpr int ACS = 37;           // padded stride of one 6x6 accumulator block (odd => lanes hit distinct banks)
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
@@ -395,10 +396,11 @@ __global__ void __launch_bounds__(BA_THREADS) ba_linearize_kernel(BaBatch bt) {
   double* sFr = sm;                       // K * FR
   double* sEx = sFr + K * FR;             // FR
   double* sScal = sEx + FR;               // 2 * NW (cost, gmax per warp)
-  const int per_warp = REC + (BVIO_KMAX - 1) * STG + BVIO_KMAX * 6 + 36 + 6 + BVIO_KMAX /*frames as doubles*/;
+  const int SREC = NPb * ACS + 3 * K6;    // padded in-smem record
+  const int per_warp = SREC + (BVIO_KMAX - 1) * STG + BVIO_KMAX * 6 + 36 + 6 + BVIO_KMAX /*frames as doubles*/;
   double* mine = sScal + 2 * 8 + (size_t)warp * per_warp;
   double* acc = mine;                     // [NPb*36]
-  double* gred = acc + NPb * 36;          // [K6]
+  double* gred = acc + NPb * ACS;         // [K6]
   double* bpv = gred + K6;                // [K6]
   double* dgh = bpv + K6;                 // [K6]
   double* stage = dgh + K6;               // [(KMAX-1)*STG]
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_linearize_kernel(BaBatch bt) {
   int* sfr = reinterpret_cast<int*>(gA + 6);    // [KMAX] ints (fits in KMAX doubles)
 
   stage_frames(bt, w, bt.pose[cur], sFr, sEx);
-  for (int i = lane; i < REC; i += 32) acc[i] = 0.0;
+  for (int i = lane; i < SREC; i += 32) acc[i] = 0.0;
   __syncthreads();
 
   const double radius = ctrl->radius;
@@ -476,22 +478,30 @@ __global__ void __launch_bounds__(BA_THREADS) ba_linearize_kernel(BaBatch bt) {
     double b = warp_sum(cc0 * rr0 + cc1 * rr1);
     cost_w += warp_sum(fcost);
     __syncwarp();
-    // anchor-side reductions over the factors: AtA (36), wA (6), gA (6)
-    for (int e = lane; e < 48; e += 32) {
-      double s = 0;
-      if (e < 36) {
-        int r = e / 6, c = e - r * 6;
-        for (int f = 0; f < nfac; f++) { const double* st = stage + f * STG; s += st[r] * st[c] + st[6 + r] * st[6 + c]; }
-        AtA[e] = s;
-      } else if (e < 42) {
-        int r = e - 36;
-        for (int f = 0; f < nfac; f++) { const double* st = stage + f * STG; s += st[r] * st[24] + st[6 + r] * st[25]; }
-        wv[r] = s;
-      } else {
-        int r = e - 42;
-        for (int f = 0; f < nfac; f++) { const double* st = stage + f * STG; s += st[r] * st[26] + st[6 + r] * st[27]; }
-        gA[r] = s;
+    // anchor-side reductions over the factors: AtA (36), wA (6), gA (6) = 48 outputs of the form
+    // sum_f st[p]*st[q] + st[p+6]*st[q'] ; every lane carries two of them through one loop (ILP 2)
+    {
+      int pp[2], qa[2], qb[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int e = lane + 32 * u;
+        if (e < 36) { pp[u] = e / 6; qa[u] = e - pp[u] * 6; qb[u] = qa[u] + 6; }
+        else if (e < 42) { pp[u] = e - 36; qa[u] = 24; qb[u] = 25; }
+        else if (e < 48) { pp[u] = e - 42; qa[u] = 26; qb[u] = 27; }
+        else { pp[u] = 0; qa[u] = 0; qb[u] = 6; }
       }
+      double s0 = 0, s1 = 0;
+      for (int f = 0; f < nfac; f++) {
+        const double* st = stage + f * STG;
+        s0 += st[pp[0]] * st[qa[0]] + st[pp[0] + 6] * st[qb[0]];
+        s1 += st[pp[1]] * st[qa[1]] + st[pp[1] + 6] * st[qb[1]];
+      }
+      double* blk00 = acc + tri(fi, fi) * ACS;
+      AtA[lane] = s0;            // lane < 32 < 36
+      blk00[lane] += s0;         // visual J^T J of the anchor block goes straight to the accumulator
+      if (lane < 4) { AtA[lane + 32] = s1; blk00[lane + 32] += s1; }
+      else if (lane < 10) wv[lane - 4] = s1;
+      else if (lane < 16) gA[lane - 10] = s1;
     }
     if (lane < nfac) {
 #pragma unroll
@@ -514,20 +524,38 @@ __global__ void __launch_bounds__(BA_THREADS) ba_linearize_kernel(BaBatch bt) {
     }
     for (int e = lane; e < n * 6; e += 32) bt.w[(size_t)o0 * 6 + e] = wv[e];
     // accumulate this landmark's (J^T J - w w^T / (h + d)) into the warp's private S blocks
-    const int E = (n * (n + 1) / 2) * 36;
-    for (int e = lane; e < E; e += 32) {
-      int pr = e / 36, rc = e - pr * 36, r = rc / 6, c = rc - r * 6;
-      int a = c_triA[pr], b2 = c_triB[pr];
-      int fa = sfr[a], fb = sfr[b2];
-      double val = -wv[a * 6 + r] * wv[b2 * 6 + c] * inv_hd;
-      if (b2 == 0) {
-        if (a == 0) val += AtA[rc];
-        else { const double* st = stage + (a - 1) * STG; val += st[12 + r] * st[c] + st[18 + r] * st[6 + c]; }
-      } else if (a == b2) {
-        const double* st = stage + (a - 1) * STG;
-        val += st[12 + r] * st[12 + c] + st[18 + r] * st[18 + c];
+    // One lane per 6x6 block pair (a >= b over the landmark's observations): the 36 products live in
+    // registers, the block is a padded (ACS = 37) private slice, so lanes never collide on a bank.
+    const int nbp = n * (n + 1) / 2;
+    for (int pr = lane; pr < nbp; pr += 32) {
+      int a = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+      if (a * (a + 1) / 2 > pr) a--;
+      if ((a + 1) * (a + 2) / 2 <= pr) a++;
+      const int b2 = pr - a * (a + 1) / 2;
+      const int fa = sfr[a], fb = sfr[b2];
+      double wa[6], wb[6], X0[6], X1[6], Y0[6], Y1[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { wa[k] = -inv_hd * wv[a * 6 + k]; wb[k] = wv[b2 * 6 + k]; }
+      // visual J^T J part: (a,a) -> B_a^T B_a ; (a,0) -> B_a^T A_a ; (0,0) -> sum_f A_f^T A_f (added below)
+      const bool has = (a > 0) && (b2 == 0 || a == b2);
+      const double* sx = stage + (a > 0 ? a - 1 : 0) * STG + 12;
+      const double* sy = (b2 == 0) ? sx - 12 : sx;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        X0[k] = has ? sx[k] : 0.0; X1[k] = has ? sx[6 + k] : 0.0;
+        Y0[k] = has ? sy[k] : 0.0; Y1[k] = has ? sy[6 + k] : 0.0;
       }
-      acc[tri(fa, fb) * 36 + rc] += val;
+      double* blk = acc + tri(fa, fb) * ACS;
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        double v[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) v[c] = blk[r * 6 + c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) v[c] += wa[r] * wb[c] + X0[r] * Y0[c] + X1[r] * Y1[c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) blk[r * 6 + c] = v[c];
+      }
     }
     for (int e = lane; e < n * 6; e += 32) {
       int a = e / 6, r = e - a * 6;
@@ -552,7 +580,8 @@ __global__ void __launch_bounds__(BA_THREADS) ba_linearize_kernel(BaBatch bt) {
   const double* base = sScal + 16;
   for (int i = threadIdx.x; i < REC; i += blockDim.x) {
     double s = 0;
-    for (int q = 0; q < NW; q++) s += base[(size_t)q * per_warp + i];
+    const int si = i < NPb * 36 ? (i / 36) * ACS + (i % 36) : i - NPb * 36 + NPb * ACS;
+    for (int q = 0; q < NW; q++) s += base[(size_t)q * per_warp + si];
     out[i] = s;
   }
   if (threadIdx.x == 0) {
@@ -776,16 +805,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_kernel(BaBatch bt, int
 // =============================================================================================
 // cost at the candidate + accept/reject
 // =============================================================================================
-__device__ void decide(const BaBatch& bt, int w) {
+__device__ void decide(const BaBatch& bt, int w, double cv, double ml, double s2, double x2) {
   BaCtrl* c = bt.ctrl + w;
   c->stepped = 0;
   c->ticket = 0;
   bool valid = c->solve_ok != 0;
-  double cv = 0, ml = 0, s2 = 0, x2 = 0;
-  if (valid) {
-    const volatile double* co = bt.cost_out + (size_t)w * (bt.T + 1) * COST_REC;
-    for (int t = 0; t <= bt.T; t++) { cv += co[t * COST_REC]; ml += co[t * COST_REC + 1]; s2 += co[t * COST_REC + 2]; x2 += co[t * COST_REC + 3]; }
-  }
   double model = c->model_pose + ml;
   if (valid && !(model > 0)) valid = false;
   if (!valid) {
@@ -823,7 +847,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
   BaCtrl* ctrl = bt.ctrl + w;
   if (ctrl->done || !ctrl->stepped) return;
   if (!ctrl->solve_ok) {
-    if (t == 0 && threadIdx.x == 0) decide(bt, w);
+    if (t == 0 && threadIdx.x == 0) decide(bt, w, 0, 0, 0, 0);
     return;
   }
   const int cur = ctrl->cur, nxt = cur ^ 1;
@@ -963,9 +987,18 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
     s_last = (old == (unsigned)bt.T);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last && threadIdx.x < 32) {
+    // warp 0 sums the T+1 partial records with a fixed tree (T <= 32), then lane 0 decides
     __threadfence();
-    decide(bt, w);
+    const double2* co2 = reinterpret_cast<const double2*>(bt.cost_out + (size_t)w * (bt.T + 1) * COST_REC);
+    double v[4] = {0, 0, 0, 0};
+    for (int q = threadIdx.x; q <= bt.T; q += 32) {
+      const double2 a = __ldcg(co2 + 2 * q), b = __ldcg(co2 + 2 * q + 1);
+      v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = warp_sum(v[k]);
+    if (threadIdx.x == 0) decide(bt, w, v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -975,7 +1008,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
 static size_t imu_prior_smem(int K, int nmax) { return sizeof(double) * ((size_t)(K - 1) * (900 + 30) + 2 * nmax); }
 
 size_t ba_linearize_smem_bytes(int K, int nwarps) {
-  int NPb = K * (K + 1) / 2, REC = NPb * 36 + 18 * K;
+  int NPb = K * (K + 1) / 2, REC = NPb * ACS + 18 * K;
   size_t per_warp = REC + (BVIO_KMAX - 1) * STG + BVIO_KMAX * 6 + 36 + 6 + BVIO_KMAX;
   return sizeof(double) * ((size_t)(K + 1) * FR + 16 + per_warp * nwarps);
 }
@@ -1027,13 +1060,17 @@ int ba_launch_reset(const BaBatch& bt, cudaStream_t st) {
   ba_reset_kernel<<<blocks, 256, 0, st>>>(bt);
   return 1;
 }
-int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step) {
+int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cudaEvent_t* ev) {
   size_t s1 = ba_linearize_smem_bytes(bt.K, bt.nwarps_lin), s1b = imu_prior_smem(bt.K, bt.nmax);
   if (s1b > s1) s1 = s1b;
+  if (ev) cudaEventRecord(ev[0], st);
   ba_linearize_kernel<<<dim3(bt.T + 1, bt.B), 32 * bt.nwarps_lin, s1, st>>>(bt);
+  if (ev) cudaEventRecord(ev[1], st);
   ba_solve_kernel<<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.K), st>>>(bt, with_step ? 1 : 0);
-  if (!with_step || bt.undamped) return 2;
+  if (ev) cudaEventRecord(ev[2], st);
+  if (!with_step || bt.undamped) { if (ev) cudaEventRecord(ev[3], st); return 2; }
   ba_cost_kernel<<<dim3(bt.T + 1, bt.B), BA_THREADS, cost_smem(bt.K, bt.nmax), st>>>(bt);
+  if (ev) cudaEventRecord(ev[3], st);
   return 3;
 }
 int ba_launch_finish(const BaBatch& bt, cudaStream_t st) {

@@ -105,6 +105,7 @@ static int sel_upload_impl(bvio_ctx* ctx, const bvio_select_in* in, bool use_cac
   for (int i = 0; i < 3; i++) sp.t_ic[i] = in->t_ic[i];
   sp.cam = in->cam;
   pr->sharded = sharded;
+  pr->use_graph = !sharded;   // NCCL calls stay outside graph capture
   pr->cand_id.assign(in->cand_id, in->cand_id + N);
 
   Carver cv;

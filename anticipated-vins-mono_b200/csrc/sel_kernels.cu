@@ -303,30 +303,47 @@ __global__ void __launch_bounds__(256) sel_omega_kernel(SelProb sp) {
 }
 
 // =============================================================================================
-// in-warp Cholesky of a packed-lower T x T matrix in shared memory; returns sum(log diag(L)) or NaN
+// in-warp Cholesky of a packed-lower T x T matrix: returns sum(log diag(L)) or NaN.
+// Register-resident: lane i holds row i (and i+32 when T > 32); column j is broadcast with warp
+// shuffles, so the whole factorization runs without shared-memory round trips.  T is a compile-time
+// constant so that every register index is static.
 // =============================================================================================
-__device__ __forceinline__ double warp_chol_logdet(double* A, int T, int lane) {
-  bool bad = false;
-  for (int j = 0; j < T; j++) {
-    double d = A[tri(j, j)];
-    if (!(d > 0.0)) { bad = true; break; }
-    d = sqrt(d);
-    const double inv = 1.0 / d;
-    __syncwarp();
-    if (lane == 0) A[tri(j, j)] = d;
-    for (int i = j + 1 + lane; i < T; i += 32) A[tri(i, j)] *= inv;
-    __syncwarp();
-    for (int i = j + 1 + lane; i < T; i += 32) {
-      const double lij = A[tri(i, j)];
-      double* row = A + tri(i, 0);
-      for (int k = j + 1; k <= i; k++) row[k] -= lij * A[tri(k, j)];
-    }
-    __syncwarp();
+template <int T>
+__device__ __forceinline__ double warp_chol_logdet(const double* A, int lane) {
+  constexpr int R = (T + 31) / 32;
+  double a[R][T];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i = lane + 32 * r;
+    const double* row = A + tri(i < T ? i : 0, 0);
+#pragma unroll
+    for (int k = 0; k < T; k++) a[r][k] = (i < T && k <= i) ? row[k] : 0.0;
   }
-  if (bad) return NAN;
+  double mypiv[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) mypiv[r] = 1.0;
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < T; j++) {
+    const double pj = __shfl_sync(0xffffffffu, a[j / 32][j], j % 32);
+    bad |= !(pj > 0.0);
+    if (lane == (j % 32)) mypiv[j / 32] = pj;
+    const double inv = rsqrt(pj);
+#pragma unroll
+    for (int r = 0; r < R; r++) a[r][j] *= inv;
+#pragma unroll
+    for (int k = j + 1; k < T; k++) {
+      const double lkj = __shfl_sync(0xffffffffu, a[k / 32][j], k % 32);
+#pragma unroll
+      for (int r = 0; r < R; r++) a[r][k] = fma(-a[r][j], lkj, a[r][k]);
+    }
+  }
   double l = 0;
-  for (int i = lane; i < T; i += 32) l += log(A[tri(i, i)]);
-  return warp_sum(l);
+#pragma unroll
+  for (int r = 0; r < R; r++)
+    if (lane + 32 * r < T) l += log(mypiv[r]);
+  l = warp_sum(l);
+  return bad ? NAN : 0.5 * l;
 }
 
 __device__ __forceinline__ void merge_best(double& best, double& second, int& idx, double ob, double os, int oidx) {
@@ -360,6 +377,7 @@ __device__ void apply_winner(const SelProb& sp, double best, double second, int 
   }
 }
 
+template <int H>
 __global__ void __launch_bounds__(32 * SEL_WARPS) sel_round_kernel(SelProb sp) {
   extern __shared__ double sm[];
   const int T = sp.T, TT = sp.TT, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,7 +397,7 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) sel_round_kernel(SelProb sp) {
     const double* Ci = sp.Cc + (size_t)i * TT;
     for (int e = lane; e < TT; e += 32) A[e] = sR[e] + p * Ci[e];
     __syncwarp();
-    const double ld = warp_chol_logdet(A, T, lane);
+    const double ld = warp_chol_logdet<3 * H>(A, lane);
     const double val = ld_oo + 2.0 * ld;
     cnt += 1;
     if (val > best) { second = best; best = val; bidx = i; }
@@ -402,12 +420,31 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) sel_round_kernel(SelProb sp) {
   if (!s_last) return;
   __threadfence();
   double* bc = sred + SEL_WARPS * 4;
-  if (threadIdx.x == 0) {
+  {
+    // parallel merge of the per-CTA records: (best, idx) has a total order, so the tree is exact
     double b = -1.0, s = -INFINITY, c = 0;
     int ix = -1;
-    const volatile double* bb = sp.blk_best;
-    for (unsigned q = 0; q < gridDim.x; q++) { merge_best(b, s, ix, bb[q * 4], bb[q * 4 + 1], (int)bb[q * 4 + 2]); c += bb[q * 4 + 3]; }
-    bc[0] = b; bc[1] = s; bc[2] = (double)ix; bc[3] = c;
+    for (unsigned q = threadIdx.x; q < gridDim.x; q += blockDim.x) {
+      const double2 r0 = __ldcg(reinterpret_cast<const double2*>(sp.blk_best) + 2 * q);
+      const double2 r1 = __ldcg(reinterpret_cast<const double2*>(sp.blk_best) + 2 * q + 1);
+      merge_best(b, s, ix, r0.x, r0.y, (int)r1.x);
+      c += r1.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, b, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      merge_best(b, s, ix, ob, os, oi);
+    }
+    __syncthreads();   // sred[0 .. SEL_WARPS*4) is free again
+    if (lane == 0) { sred[warp * 4] = b; sred[warp * 4 + 1] = s; sred[warp * 4 + 2] = (double)ix; sred[warp * 4 + 3] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      b = -1.0; s = -INFINITY; c = 0; ix = -1;
+      for (int q = 0; q < SEL_WARPS; q++) { merge_best(b, s, ix, sred[q * 4], sred[q * 4 + 1], (int)sred[q * 4 + 2]); c += sred[q * 4 + 3]; }
+      bc[0] = b; bc[1] = s; bc[2] = (double)ix; bc[3] = c;
+    }
   }
   __syncthreads();
   const double b = bc[0], s = bc[1];
@@ -448,11 +485,12 @@ __global__ void __launch_bounds__(256) sel_apply_kernel(SelProb sp) {
   apply_winner(sp, bc[0], bc[1], ix, rec[3], rec + SEL_REC_HDR, 0ull);
 }
 
+template <int H>
 __global__ void __launch_bounds__(32) sel_final_kernel(SelProb sp) {
   extern __shared__ double sm[];
   for (int e = threadIdx.x; e < sp.TT; e += 32) sm[e] = sp.R[e];
   __syncwarp();
-  double ld = warp_chol_logdet(sm, sp.T, threadIdx.x);
+  double ld = warp_chol_logdet<3 * H>(sm, threadIdx.x);
   if (threadIdx.x == 0) sp.ctrl->final_logdet = sp.ctrl->logdet_oo + 2.0 * ld;
 }
 
@@ -485,12 +523,16 @@ size_t sel_omega_smem_bytes(int H) {
 }
 static size_t round_smem(int TT) { return sizeof(double) * ((size_t)(1 + SEL_WARPS) * TT + SEL_WARPS * 4 + 4); }
 
+#define BVIO_SEL_FOR_EACH_H(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16)
 static bool g_sel_configured = false;
 int sel_configure(void) {
   if (g_sel_configured) return 0;
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(sel_omega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sel_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+#define BVIO_SEL_ATTR(HH) \
+  if ((e = cudaFuncSetAttribute(sel_round_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+  BVIO_SEL_FOR_EACH_H(BVIO_SEL_ATTR)
+#undef BVIO_SEL_ATTR
   g_sel_configured = true;
   return 0;
 }
@@ -507,7 +549,12 @@ int sel_launch_build(const SelProb& sp, cudaStream_t st) {
   return n + 1;
 }
 int sel_launch_round(const SelProb& sp, cudaStream_t st) {
-  sel_round_kernel<<<sp.grid_round, 32 * SEL_WARPS, round_smem(sp.TT), st>>>(sp);
+  switch (sp.H) {
+#define BVIO_SEL_CASE(HH) case HH: sel_round_kernel<HH><<<sp.grid_round, 32 * SEL_WARPS, round_smem(sp.TT), st>>>(sp); break;
+    BVIO_SEL_FOR_EACH_H(BVIO_SEL_CASE)
+#undef BVIO_SEL_CASE
+    default: break;
+  }
   return 1;
 }
 int sel_launch_apply(const SelProb& sp, cudaStream_t st) {
@@ -515,7 +562,12 @@ int sel_launch_apply(const SelProb& sp, cudaStream_t st) {
   return 1;
 }
 int sel_launch_final(const SelProb& sp, cudaStream_t st) {
-  sel_final_kernel<<<1, 32, sizeof(double) * sp.TT, st>>>(sp);
+  switch (sp.H) {
+#define BVIO_SEL_CASE(HH) case HH: sel_final_kernel<HH><<<1, 32, sizeof(double) * sp.TT, st>>>(sp); break;
+    BVIO_SEL_FOR_EACH_H(BVIO_SEL_CASE)
+#undef BVIO_SEL_CASE
+    default: break;
+  }
   return 1;
 }
 int sel_launch_expand(const SelProb& sp, double* Cfull, cudaStream_t st) {

@@ -15,7 +15,7 @@ _lib = None
 EXPORTS = [
     "bvio_create", "bvio_destroy", "bvio_last_error", "bvio_abi_version", "bvio_default_opts",
     "bvio_optimize", "bvio_optimize_batch", "bvio_batch_upload", "bvio_batch_solve", "bvio_batch_download",
-    "bvio_batch_free", "bvio_stream", "bvio_launch_count", "bvio_marginalize", "bvio_select",
+    "bvio_batch_free", "bvio_batch_solve_timed", "bvio_stream", "bvio_launch_count", "bvio_marginalize", "bvio_select",
     "bvio_nccl_unique_id", "bvio_comm_init", "bvio_select_sharded", "bvio_select_upload", "bvio_select_run",
     "bvio_select_fetch", "bvio_select_free", "bvio_debug_linearize", "bvio_debug_build_delta",
 ]
@@ -42,6 +42,7 @@ def load():
     L.bvio_batch_upload.argtypes = [vp, C.POINTER(abi.WindowS), i32, C.POINTER(abi.Opts), C.POINTER(vp)]
     L.bvio_batch_solve.argtypes = [vp, vp]
     L.bvio_batch_download.argtypes = [vp, vp, C.POINTER(abi.WindowS), C.POINTER(abi.Summary)]
+    L.bvio_batch_solve_timed.argtypes = [vp, vp, dp, ip]
     L.bvio_batch_free.argtypes = [vp, vp]
     L.bvio_batch_free.restype = None
     L.bvio_stream.argtypes = [vp]

@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native BA solver + anticipated feature selector.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (libbvio.so, CUDA)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+
+Metric (BASELINE.json): GN iterations/s on 11-keyframe / 1500-feature windows (+ candidates-scored/s
+of the selector on 2000 candidates, H=10, kappa=150, reported under "selector").  A BA "step" is one
+solve (8 LM iterations, tolerances off so every window runs all 8) of a batch of independent windows
+that is larger than L2; a selector "step" is one full greedy selection.  Multi-GPU: BA = independent
+replicas (no collective, weak scaling); selector = candidates sharded across ranks with one NCCL
+all-gather of winner records per greedy round.
+
+One JSON line on stdout (rank 0).  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as g  # noqa: E402
+
+K_FRAMES, L_FEATS, TRACK_MIN = 11, 1500, 6
+SEL_N, SEL_H, SEL_KAPPA = 2000, 10, 150
+POOL = 4                      # distinct synthetic windows, tiled to the batch size
+BENCH_OPTS = dict(max_iters=8, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
+
+
+def ba_algorithmic_bytes(w, n_prior, np_dim):
+    """bytes one GN iteration of one window must move."""
+    nf, L, K = w.n_factors, w.L, w.K
+    return 20 * nf + 40 * L + 2296 * (K - 1) + 8 * n_prior * n_prior + 16 * n_prior + 128 * K + 8 * np_dim
+
+
+def sel_algorithmic_bytes_round(n_remaining, H):
+    TT = (3 * H) * (3 * H + 1) // 2
+    return n_remaining * (8 * TT + 8) + 8 * (9 * (H + 1)) ** 2
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_pool(synth):
+    return [synth.make_window(seed=100 + i, K=K_FRAMES, L=L_FEATS, track_min=TRACK_MIN) for i in range(POOL)]
+
+
+def window_array(abi, pool, B):
+    hs = [abi.WindowHandle(pool[i % len(pool)]) for i in range(B)]
+    arr = (abi.WindowS * B)(*[h.s for h in hs])
+    return hs, arr
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (oracle = CPU restatement of the reference's Ceres/Eigen path; the reference itself cannot
+# be compiled in this image: no Eigen/Ceres/ROS -- DESIGN.md)
+# --------------------------------------------------------------------------------------------
+def cpu_ba(abi, orc, pool, n_solves, threads):
+    o = abi.default_opts(strategy=1, **BENCH_OPTS)      # DOGLEG: what the reference configures (estimator.cpp:798)
+    hs = [abi.WindowHandle(pool[i % len(pool)]) for i in range(n_solves)]
+    sums = [abi.Summary() for _ in range(n_solves)]
+
+    def run(i):
+        orc.oracle_optimize(C.byref(hs[i].s), C.byref(o), C.byref(sums[i]))
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for i in range(n_solves):
+            run(i)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as ex:       # ctypes releases the GIL during the call
+            list(ex.map(run, range(n_solves)))
+    dt = time.perf_counter() - t0
+    iters = sum(s.iterations for s in sums)
+    return iters, dt
+
+
+def cpu_select(abi, synth, orc, kappa):
+    p = synth.make_select_problem(seed=0, N=SEL_N, H=SEL_H, kappa=kappa)
+    h = abi.SelectHandle(p)
+    ids = np.zeros(max(kappa, 1), np.int32)
+    s = abi.SelectSummary()
+    t0 = time.perf_counter()
+    orc.oracle_select(C.byref(h.s), abi.iptr(ids), None, C.byref(s))
+    return s.candidates_scored, time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle_lib
+    pkg = g.load_package()
+    abi, synth = pkg.abi, pkg.synth
+    orc = oracle_lib.load()
+    threads = os.cpu_count() or 1
+    pool = make_pool(synth)
+    per_step = 2 * threads
+    for _ in range(args.warmup):
+        cpu_ba(abi, orc, pool, threads, threads)
+    iters, dt = 0, 0.0
+    for _ in range(args.steps):
+        i, d = cpu_ba(abi, orc, pool, per_step, threads)
+        iters += i
+        dt += d
+    val = iters / dt
+    sc, sdt = cpu_select(abi, synth, orc, 16)
+    line = {
+        "impl": "reference", "metric": "GN iters/sec (BA, 11-kf/1500-feat windows)", "value": val, "unit": "iters/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BA {K_FRAMES}-kf/{L_FEATS}-feat windows, 8 dogleg iterations each, "
+                               f"{per_step} windows per step on {threads} host threads"},
+        "cpu_baseline": {"value": val, "unit": "iters/s", "cores": threads, "kind": "port",
+                         "sample": f"{per_step} window solves per step x {args.steps} steps; CPU restatement "
+                                   "(oracle/) of the reference's Ceres DENSE_SCHUR+DOGLEG path -- the reference "
+                                   "itself needs Eigen/Ceres/ROS and does not compile here"},
+        "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "selector": {"metric": "candidates-scored/sec", "value": sc / sdt, "unit": "cand/s", "cores": 1,
+                     "sample": f"N={SEL_N}, H={SEL_H}, first 16 greedy rounds, lazy-greedy dense {9*(SEL_H+1)}^2 LLT"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = g.load_package()
+    abi, synth = pkg.abi, pkg.synth
+    ctx = pkg.lib.Context(local_rank)
+    L = ctx.L
+    stream = torch.cuda.ExternalStream(L.bvio_stream(ctx.h), device=torch.device("cuda", local_rank))
+    B = args.batch
+    pool = make_pool(synth)
+    hs, arr = window_array(abi, pool, B)
+    o = abi.default_opts(**BENCH_OPTS)
+    sums = (abi.Summary * B)()
+
+    # ---- multi-GPU plumbing for the sharded selector
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            assert L.bvio_nccl_unique_id(buf) == 0
+            uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        ctx.check(L.bvio_comm_init(ctx.h, raw, rank, world), "bvio_comm_init")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- BA, inputs resident in HBM
+    bh = C.c_void_p()
+    ctx.check(L.bvio_batch_upload(ctx.h, arr, B, C.byref(o), C.byref(bh)), "batch_upload")
+    for _ in range(max(args.warmup, 3)):
+        ctx.check(L.bvio_batch_solve(ctx.h, bh), "batch_solve")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = L.bvio_launch_count(ctx.h)
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.check(L.bvio_batch_solve(ctx.h, bh), "batch_solve")
+    e1.record(stream)
+    barrier()
+    ba_ms = max_over_ranks(e0.elapsed_time(e1))
+    ba_launches = L.bvio_launch_count(ctx.h) - l0
+    ctx.check(L.bvio_batch_download(ctx.h, bh, arr, sums), "batch_download")
+    iters_per_solve = sum(s.iterations for s in sums)
+    total_iters = sum_over_ranks(float(iters_per_solve)) * args.steps
+    ba_value = total_iters / (ba_ms * 1e-3)
+    final_costs = [s.final_cost for s in sums[:POOL]]
+
+    # per-kernel split for the roofline (direct launches + events between kernels; same stream)
+    kms = (C.c_double * 4)()
+    kl = (C.c_int32 * 3)()
+    for _ in range(2):
+        ctx.check(L.bvio_batch_solve_timed(ctx.h, bh, kms, kl), "solve_timed")
+    lin_ms, solve_ms, cost_ms = kms[0] / kl[0], kms[1] / kl[1], kms[2] / max(kl[2], 1)
+    n_prior = pool[0].prior["n"] if pool[0].prior is not None else 0
+    alg_bytes_iter = sum(ba_algorithmic_bytes(pool[i % POOL], n_prior, 15 * K_FRAMES) for i in range(B))
+    lin_bytes = alg_bytes_iter - 8 * 15 * K_FRAMES * B      # everything but the delta-x write is read by linearize
+    L.bvio_batch_free(ctx.h, bh)
+
+    # ---- selector, inputs resident in HBM
+    p = synth.make_select_problem(seed=0, N=SEL_N, H=SEL_H, kappa=SEL_KAPPA)
+    sh = abi.SelectHandle(p)
+    ph = C.c_void_p()
+    ctx.check(L.bvio_select_upload(ctx.h, C.byref(sh.s), C.byref(ph)), "select_upload")
+    for _ in range(max(args.warmup, 3)):
+        ctx.check(L.bvio_select_run(ctx.h, ph), "select_run")
+    barrier()
+    l1 = L.bvio_launch_count(ctx.h)
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.check(L.bvio_select_run(ctx.h, ph), "select_run")
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    sel_ms = max_over_ranks(e0.elapsed_time(e1))
+    sel_launches = L.bvio_launch_count(ctx.h) - l1
+    ids = np.zeros(SEL_KAPPA, np.int32)
+    ss = abi.SelectSummary()
+    ctx.check(L.bvio_select_fetch(ctx.h, ph, abi.iptr(ids), None, C.byref(ss)), "select_fetch")
+    L.bvio_select_free(ctx.h, ph)
+    sel_value = ss.candidates_scored * args.steps / (sel_ms * 1e-3)
+    nv = ss.n_candidates_valid
+    sel_bytes = sum(sel_algorithmic_bytes_round(nv - i, SEL_H) for i in range(ss.n_selected))
+
+    # ---- end to end through the public C-ABI with HOST buffers (H2D + D2H inside the timed region)
+    e2e_steps = max(1, min(args.steps, 5))
+    hs2, arr2 = window_array(abi, pool, B)
+    state0 = [(h.pose.copy(), h.sb.copy(), h.inv.copy()) for h in hs2]
+    for _ in range(2):
+        ctx.check(L.bvio_optimize_batch(ctx.h, arr2, B, C.byref(o), sums), "optimize_batch")
+    barrier()
+    t_e2e, it_e2e = 0.0, 0
+    for _ in range(e2e_steps):
+        for h, (a, b_, c) in zip(hs2, state0):     # restore inputs (not timed)
+            h.pose[...] = a
+            h.sb[...] = b_
+            h.inv[...] = c
+        t0 = time.perf_counter()
+        ctx.check(L.bvio_optimize_batch(ctx.h, arr2, B, C.byref(o), sums), "optimize_batch")
+        t_e2e += time.perf_counter() - t0
+        it_e2e += sum(s.iterations for s in sums)
+    t_e2e = max_over_ranks(t_e2e)
+    e2e_value = sum_over_ranks(float(it_e2e)) / t_e2e
+    h2d = sum(h.pose.nbytes + h.sb.nbytes + h.ex.nbytes + h.inv.nbytes + h.off.nbytes + h.frame.nbytes +
+              h.xy.nbytes + h.pre.nbytes + (h._pj.nbytes + h._pr.nbytes + h._px0.nbytes if h.prior_s else 0) for h in hs2)
+    d2h = sum(h.pose.nbytes + h.sb.nbytes + h.inv.nbytes for h in hs2) + B * 104
+    # selector end to end
+    ids2 = np.zeros(SEL_KAPPA, np.int32)
+    sel = L.bvio_select_sharded if world > 1 else L.bvio_select
+    ctx.check(sel(ctx.h, C.byref(sh.s), abi.iptr(ids2), None, C.byref(ss)), "select")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.check(sel(ctx.h, C.byref(sh.s), abi.iptr(ids2), None, C.byref(ss)), "select")
+    t_sel_e2e = max_over_ranks(time.perf_counter() - t0)
+    sel_e2e = ss.candidates_scored * e2e_steps / t_sel_e2e
+    sel_h2d = sh.pos.nbytes + sh.quat.nbytes + sh.cxy.nbytes + sh.cp.nbytes + sh.clxy.nbytes + sh.cld.nbytes
+    assert (ids2 == ids).all(), "one-shot and resident selector disagree"
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_lib
+        orc = oracle_lib.load()
+        it, dt = cpu_ba(abi, orc, pool, args.cpu_solves, 1)
+        sc, sdt = cpu_select(abi, synth, orc, args.cpu_kappa)
+        cpu = {"value": it / dt, "unit": "iters/s", "cores": 1, "kind": "port",
+               "sample": f"{args.cpu_solves} solves of the same {K_FRAMES}-kf/{L_FEATS}-feat windows, 8 dogleg "
+                         f"iterations each, 1 thread ({dt:.1f} s); selector: first {args.cpu_kappa} rounds of "
+                         f"N={SEL_N} ({sdt:.1f} s)",
+               "selector_value": sc / sdt, "selector_unit": "cand/s"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("ba_linearize_kernel")
+        except Exception:
+            pass
+        achieved = lin_bytes / (lin_ms * 1e-3) / 1e9
+        line = {
+            "metric": "GN iters/sec (BA, 11-kf/1500-feat windows)", "value": ba_value, "unit": "iters/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ba_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[2]: {K_FRAMES}-keyframe/{L_FEATS}-feature windows "
+                                   f"({pool[0].n_factors} projection factors), {B} independent windows per GPU per "
+                                   f"step, 8 LM iterations each (tolerances off), full-rank 15-dim prior on frame 0",
+                       "batch_windows_per_gpu": B, "l2_policy": "BA batch footprint > L2 (inputs larger than L2); "
+                       "selector working set (7 MB) is L2-resident by design and re-read every round",
+                       "parallelism": "replicas (BA) + candidate-sharded selector" if world > 1 else "single GPU",
+                       "final_cost_check": final_costs},
+            "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "api": "bvio_optimize_batch (host buffers, pack + H2D + solve + D2H)"},
+            "gpu_launches": int(ba_launches + sel_launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "ba_linearize_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
+                         "algorithmic_bytes_per_launch": int(lin_bytes), "launch_ms": lin_ms,
+                         "kernel_ms_per_pass": {"ba_linearize_kernel": lin_ms, "ba_solve_kernel": solve_ms,
+                                                "ba_cost_kernel": cost_ms},
+                         "note": "FP64 compute/latency-bound path: ~28 MFLOP per 0.38 MB window-iteration; the HBM "
+                                 "fraction is reported as BASELINE.json asks, not as the binding limit"},
+            "selector": {"metric": "candidates-scored/sec", "value": sel_value, "unit": "cand/s",
+                         "ms_per_step": sel_ms / args.steps, "workload": f"configs[3]: N={SEL_N}, H={SEL_H}, "
+                         f"kappa={SEL_KAPPA}, {nv} valid candidates, every remaining candidate scored each round",
+                         "scaling": "strong" if world > 1 else None,
+                         "achieved_gbs": sel_bytes * args.steps / (sel_ms * 1e-3) / 1e9,
+                         "e2e": {"value": sel_e2e, "unit": "cand/s", "h2d_bytes_per_step": int(sel_h2d),
+                                 "d2h_bytes_per_step": int(SEL_KAPPA * 12 + 64)},
+                         "selected_head": ids[:8].tolist()},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="independent windows per GPU per BA step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-solves", type=int, default=64)
+    ap.add_argument("--cpu-kappa", type=int, default=16)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

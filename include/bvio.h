@@ -177,6 +177,9 @@ int  bvio_batch_solve(bvio_ctx* ctx, bvio_batch* batch);               /* async 
 int  bvio_batch_download(bvio_ctx* ctx, bvio_batch* batch, bvio_window* windows,
                          bvio_summary* summaries);                      /* syncs */
 void bvio_batch_free(bvio_ctx* ctx, bvio_batch* batch);
+/* Per-kernel device time of one solve, for roofline reporting: out_ms = {linearize, solve, cost,
+ * sum} in ms summed over all passes, out_launches = launches of each kernel.  Synchronous. */
+int  bvio_batch_solve_timed(bvio_ctx* ctx, bvio_batch* batch, double out_ms[4], int32_t out_launches[3]);
 /* stream the batch runs on (cudaStream_t as void*), for event timing */
 void* bvio_stream(bvio_ctx* ctx);
 /* kernels launched by this context since creation (for gpu_launches) */
