@@ -50,7 +50,7 @@ constexpr int COST_REC = 4;
 struct BaBatch {                  // all pointers are device pointers
   int B, K, np, T;                // windows, keyframes, reduced dimension, landmark tiles per window
   int total_L, total_obs, nmax;   // nmax = max prior dimension (row stride of the prior arrays)
-  int nwarps_lin;                 // warps per CTA in ba_linearize (bounded by shared memory)
+  int chunk_l;                    // landmarks per chunk in ba_linearize (bounded by shared memory)
   int undamped;                   // debug: linearize without LM damping (bvio_debug_linearize)
   // solver options
   int max_iters, jacobi_scaling;
@@ -97,8 +97,8 @@ int ba_launch_prepare(const BaBatch& bt, cudaStream_t st);
 int ba_launch_reset(const BaBatch& bt, cudaStream_t st);
 int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cudaEvent_t* ev = nullptr);  // ev[4]: before/after each kernel
 int ba_launch_finish(const BaBatch& bt, cudaStream_t st);
-size_t ba_linearize_smem_bytes(int K, int nwarps);
-int ba_pick_linearize_warps(int K);
+size_t ba_linearize_smem_bytes(int K, int chunk_l);
+int ba_pick_chunk(int K);
 size_t ba_solve_smem_bytes(int K);
 int ba_configure(void);   // cudaFuncSetAttribute for the big-smem kernels; returns cudaError_t
 

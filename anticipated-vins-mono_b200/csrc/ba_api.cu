@@ -149,8 +149,8 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   BaBatch& bt = bb->bt;
   memset(&bt, 0, sizeof bt);
   bt.B = B; bt.K = K; bt.np = 15 * K; bt.total_L = total_L; bt.total_obs = total_obs; bt.nmax = nmax;
-  bt.nwarps_lin = ba_pick_linearize_warps(K);
-  int T = (maxL + 4 * bt.nwarps_lin - 1) / (4 * bt.nwarps_lin);
+  bt.chunk_l = ba_pick_chunk(K);
+  int T = (maxL + 2 * bt.chunk_l - 1) / (2 * bt.chunk_l);   // >= 2 chunks per tile when there is a choice
   int Tcap = std::max(1, (2 * ctx->sm_count + B - 1) / B);
   T = std::max(1, std::min(std::min(T, Tcap), 32));
   bt.T = T;

@@ -381,7 +381,14 @@ __device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* s
   }
 }
 
-__global__ void __launch_bounds__(BA_THREADS) ba_linearize_kernel(BaBatch bt) {
+// Visual part, chunked: the CTA walks its landmark tile in chunks of CL landmarks.
+//   A1  thread = (landmark, factor) slot: residual + Jacobians + Cauchy -> 28 doubles per factor in smem
+//   A2  thread = (landmark, output): anchor reductions A^T A, A^T c, A^T r, h, b
+//   A3  thread = landmark: LM damping of the eliminated depth, h/b/w to HBM
+//   B   thread = owner of fixed 1x6 strips of the 6K x 6K block matrix, accumulated in REGISTERS over the
+//       chunk's landmarks (fixed order => deterministic; no shared-memory accumulators, no atomics)
+template <int NS>
+__global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt) {
   extern __shared__ double sm[];
   const int w = blockIdx.y, t = blockIdx.x;
   BaCtrl* ctrl = bt.ctrl + w;
@@ -389,212 +396,260 @@ __global__ void __launch_bounds__(BA_THREADS) ba_linearize_kernel(BaBatch bt) {
   const int cur = ctrl->cur;
   if (t == bt.T) { imu_prior_linearize(bt, w, cur, sm); return; }
 
-  const int K = bt.K, K6 = 6 * K, NPb = K * (K + 1) / 2;
-  const int REC = NPb * 36 + 3 * K6;
-  const int NW = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sFr = sm;                       // K * FR
-  double* sEx = sFr + K * FR;             // FR
-  double* sScal = sEx + FR;               // 2 * NW (cost, gmax per warp)
-  const int SREC = NPb * ACS + 3 * K6;    // padded in-smem record
-  const int per_warp = SREC + (BVIO_KMAX - 1) * STG + BVIO_KMAX * 6 + 36 + 6 + BVIO_KMAX /*frames as doubles*/;
-  double* mine = sScal + 2 * 8 + (size_t)warp * per_warp;
-  double* acc = mine;                     // [NPb*36]
-  double* gred = acc + NPb * ACS;         // [K6]
-  double* bpv = gred + K6;                // [K6]
-  double* dgh = bpv + K6;                 // [K6]
-  double* stage = dgh + K6;               // [(KMAX-1)*STG]
-  double* wv = stage + (BVIO_KMAX - 1) * STG;   // [KMAX*6]
-  double* AtA = wv + BVIO_KMAX * 6;       // [36]
-  double* gA = AtA + 36;                  // [6]
-  int* sfr = reinterpret_cast<int*>(gA + 6);    // [KMAX] ints (fits in KMAX doubles)
+  const int K = bt.K, K6 = 6 * K, NPb = K * (K + 1) / 2, FS = K - 1, CL = bt.chunk_l;
+  const int tid = threadIdx.x;
+  double* sFr = sm;                                  // [K*FR]
+  double* sEx = sFr + K * FR;                        // [FR]
+  double* sRed = sEx + FR;                           // [16]
+  double* sFac = sRed + 16;                          // [CL*FS*STG]
+  double* sW = sFac + (size_t)CL * FS * STG;         // [CL*K6]
+  double* sAtA = sW + (size_t)CL * K6;               // [CL*36]
+  double* sgA = sAtA + (size_t)CL * 36;              // [CL*6]
+  double* sSc = sgA + (size_t)CL * 6;                // [CL*4] inv_hd, b, h, -
+  int* sMeta = reinterpret_cast<int*>(sSc + (size_t)CL * 4);            // [CL*2] o0, n
+  signed char* sOidx = reinterpret_cast<signed char*>(sMeta + CL * 2);  // [CL*K] frame -> observation index
+
+  // Units this thread owns: a unit is half a 6x6 block (3 rows x 6 columns = 18 register accumulators).
+  // Block order: the K diagonal blocks first, then the off-diagonal blocks (p > q) sorted by column q, so
+  // that "q is this landmark's anchor frame" is (nearly) warp-uniform.  The last warp owns the three
+  // gradient vectors instead of units.
+  const int NUNIT = NPb * 2, TS = (NUNIT + NS - 1) / NS;         // TS <= BA_THREADS - 32 by choice of NS
+  int s_p[NS], s_q[NS], s_r[NS];
+  double acc[NS][3][6];
+#pragma unroll
+  for (int u = 0; u < NS; u++) {
+    const int uidx = tid + TS * u;
+    s_p[u] = -1; s_q[u] = -1; s_r[u] = 0;
+    if (tid < TS && uidx < NUNIT) {
+      const int blk = uidx >> 1;
+      s_r[u] = 3 * (uidx & 1);
+      if (blk < K) { s_p[u] = blk; s_q[u] = blk; }
+      else {
+        int rem = blk - K, q = 0;
+        while (rem >= K - 1 - q) { rem -= K - 1 - q; q++; }
+        s_q[u] = q; s_p[u] = q + 1 + rem;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) acc[u][i][c] = 0.0;
+  }
+  const bool gwarp = tid >= BA_THREADS - 32;          // gradient elements lane, lane+32, lane+64 (< 6K <= 90)
+  const int glane = tid - (BA_THREADS - 32);
+  double g_red[3] = {0, 0, 0}, g_bp[3] = {0, 0, 0}, g_dg[3] = {0, 0, 0};
+  double cost_t = 0, gmax_t = 0;
 
   stage_frames(bt, w, bt.pose[cur], sFr, sEx);
-  for (int i = lane; i < SREC; i += 32) acc[i] = 0.0;
-  __syncthreads();
-
   const double radius = ctrl->radius;
   const int first = ctrl->first;
   const double* invd = bt.invd[cur];
   int l0, l1;
   tile_range(bt, w, t, l0, l1);
-  double cost_w = 0.0, gmax_w = 0.0;
 
-  for (int l = l0 + warp; l < l1; l += NW) {
-    const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0, nfac = n - 1;
-    const double lam = invd[l];
-    const double2 pi = bt.obs_xy[o0];
-    int myfr = 0;
-    if (lane < n) { myfr = bt.obs_frame[o0 + lane]; sfr[lane] = myfr; }
-    const int fi = __shfl_sync(0xffffffffu, myfr, 0);
-    const int fj = __shfl_down_sync(0xffffffffu, myfr, 1);   // frame of observation lane+1
-    double cc0 = 0, cc1 = 0, rr0 = 0, rr1 = 0, fcost = 0;
-    double wB[6] = {0, 0, 0, 0, 0, 0};
-    if (lane < nfac) {
-      const double2 pj = bt.obs_xy[o0 + 1 + lane];
-      const double* Fi = sFr + fi * FR;
-      const double* Fj = sFr + fj * FR;
-      ProjGeom g = proj_geom(Fi, Fj, sEx, pi.x, pi.y, lam);
-      const double inv = 1.0 / g.pcj.z, si = bt.sqrt_info;
-      double r0 = si * (g.pcj.x * inv - pj.x), r1 = si * (g.pcj.y * inv - pj.y);
-      // reduce (2x3) * ric^T -> Gm (2x3); Gm * Rj^T -> Q (2x3)
-      double red[2][3] = {{si * inv, 0.0, -si * g.pcj.x * inv * inv}, {0.0, si * inv, -si * g.pcj.y * inv * inv}};
-      double Gm[2][3], Q[2][3];
-#pragma unroll
-      for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-          Gm[a][c] = red[a][0] * sEx[c * 3 + 0] + red[a][1] * sEx[c * 3 + 1] + red[a][2] * sEx[c * 3 + 2];
-#pragma unroll
-      for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) Q[a][c] = Gm[a][0] * Fj[c * 3 + 0] + Gm[a][1] * Fj[c * 3 + 1] + Gm[a][2] * Fj[c * 3 + 2];
-      double s = r0 * r0 + r1 * r1, rho0, rho1;
-      cauchy(bt.cauchy_a, s, rho0, rho1);
-      fcost = 0.5 * rho0;
-      const double sr = sqrt(rho1);
-      double* st = stage + lane * STG;
-      const d3 tic{sEx[9], sEx[10], sEx[11]};
-      const d3 dimu = g.pimu_i - tic;
-      double Jf[2];
-#pragma unroll
-      for (int a = 0; a < 2; a++) {
-        // u = Ri^T Q[a]^T
-        d3 u = mtv3(Fi, d3{Q[a][0], Q[a][1], Q[a][2]});
-        d3 jr = cross3(g.pimu_i, u);                                   // -(Q Ri skew(pts_imu_i)) row
-        d3 jjr = cross3(d3{Gm[a][0], Gm[a][1], Gm[a][2]}, g.pimu_j);   // (Gm skew(pts_imu_j)) row
-        st[a * 6 + 0] = sr * Q[a][0]; st[a * 6 + 1] = sr * Q[a][1]; st[a * 6 + 2] = sr * Q[a][2];
-        st[a * 6 + 3] = sr * jr.x; st[a * 6 + 4] = sr * jr.y; st[a * 6 + 5] = sr * jr.z;
-        st[12 + a * 6 + 0] = -sr * Q[a][0]; st[12 + a * 6 + 1] = -sr * Q[a][1]; st[12 + a * 6 + 2] = -sr * Q[a][2];
-        st[12 + a * 6 + 3] = sr * jjr.x; st[12 + a * 6 + 4] = sr * jjr.y; st[12 + a * 6 + 5] = sr * jjr.z;
-        Jf[a] = -dot3(u, dimu) / lam;
-      }
-      cc0 = sr * Jf[0]; cc1 = sr * Jf[1]; rr0 = sr * r0; rr1 = sr * r1;
-      st[24] = cc0; st[25] = cc1; st[26] = rr0; st[27] = rr1;
-#pragma unroll
-      for (int k = 0; k < 6; k++) wB[k] = st[12 + k] * cc0 + st[18 + k] * cc1;
-    }
-    double h = warp_sum(cc0 * cc0 + cc1 * cc1);
-    double b = warp_sum(cc0 * rr0 + cc1 * rr1);
-    cost_w += warp_sum(fcost);
-    __syncwarp();
-    // anchor-side reductions over the factors: AtA (36), wA (6), gA (6) = 48 outputs of the form
-    // sum_f st[p]*st[q] + st[p+6]*st[q'] ; every lane carries two of them through one loop (ILP 2)
+  for (int lb = l0; lb < l1; lb += CL) {
+    const int nl = min(CL, l1 - lb);
+    __syncthreads();                                 // previous chunk fully consumed (and frames staged)
+    for (int i = tid; i < nl * K; i += BA_THREADS) sOidx[i] = -1;
+    __syncthreads();
+    // ---- A1: factor evaluation
     {
-      int pp[2], qa[2], qb[2];
+      const int lc = tid / FS, f = tid - lc * FS;
+      if (lc < nl) {
+        const int l = lb + lc;
+        const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0;
+        const int fi = bt.obs_frame[o0];
+        if (f == 0) { sMeta[lc * 2] = o0; sMeta[lc * 2 + 1] = n; sOidx[lc * K + fi] = 0; }
+        if (f < n - 1) {
+          const double lam = invd[l];
+          const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + f];
+          const int fj = bt.obs_frame[o0 + 1 + f];
+          sOidx[lc * K + fj] = (signed char)(f + 1);
+          const double* Fi = sFr + fi * FR;
+          const double* Fj = sFr + fj * FR;
+          ProjGeom g = proj_geom(Fi, Fj, sEx, pi.x, pi.y, lam);
+          const double inv = 1.0 / g.pcj.z, si = bt.sqrt_info;
+          const double r0 = si * (g.pcj.x * inv - pj.x), r1 = si * (g.pcj.y * inv - pj.y);
+          const double red[2][3] = {{si * inv, 0.0, -si * g.pcj.x * inv * inv}, {0.0, si * inv, -si * g.pcj.y * inv * inv}};
+          double Gm[2][3], Q[2][3];
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int e = lane + 32 * u;
-        if (e < 36) { pp[u] = e / 6; qa[u] = e - pp[u] * 6; qb[u] = qa[u] + 6; }
-        else if (e < 42) { pp[u] = e - 36; qa[u] = 24; qb[u] = 25; }
-        else if (e < 48) { pp[u] = e - 42; qa[u] = 26; qb[u] = 27; }
-        else { pp[u] = 0; qa[u] = 0; qb[u] = 6; }
+          for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+              Gm[a][c] = red[a][0] * sEx[c * 3 + 0] + red[a][1] * sEx[c * 3 + 1] + red[a][2] * sEx[c * 3 + 2];
+#pragma unroll
+          for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) Q[a][c] = Gm[a][0] * Fj[c * 3 + 0] + Gm[a][1] * Fj[c * 3 + 1] + Gm[a][2] * Fj[c * 3 + 2];
+          double rho0, rho1;
+          cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
+          cost_t += 0.5 * rho0;
+          const double sr = sqrt(rho1);
+          double* st = sFac + (size_t)(lc * FS + f) * STG;
+          const d3 dimu = g.pimu_i - d3{sEx[9], sEx[10], sEx[11]};
+          double cc[2];
+#pragma unroll
+          for (int a = 0; a < 2; a++) {
+            const d3 u = mtv3(Fi, d3{Q[a][0], Q[a][1], Q[a][2]});              // Ri^T Q[a]^T
+            const d3 jr = cross3(g.pimu_i, u);                                 // -(Q Ri [pts_imu_i]x) row
+            const d3 jjr = cross3(d3{Gm[a][0], Gm[a][1], Gm[a][2]}, g.pimu_j); // (Gm [pts_imu_j]x) row
+            st[a * 6 + 0] = sr * Q[a][0]; st[a * 6 + 1] = sr * Q[a][1]; st[a * 6 + 2] = sr * Q[a][2];
+            st[a * 6 + 3] = sr * jr.x; st[a * 6 + 4] = sr * jr.y; st[a * 6 + 5] = sr * jr.z;
+            st[12 + a * 6 + 0] = -sr * Q[a][0]; st[12 + a * 6 + 1] = -sr * Q[a][1]; st[12 + a * 6 + 2] = -sr * Q[a][2];
+            st[12 + a * 6 + 3] = sr * jjr.x; st[12 + a * 6 + 4] = sr * jjr.y; st[12 + a * 6 + 5] = sr * jjr.z;
+            cc[a] = sr * (-dot3(u, dimu) / lam);
+          }
+          st[24] = cc[0]; st[25] = cc[1]; st[26] = sr * r0; st[27] = sr * r1;
+          double* wo = sW + (size_t)lc * K6 + (f + 1) * 6;
+          double* wg = bt.w + (size_t)(o0 + 1 + f) * 6;
+#pragma unroll
+          for (int k = 0; k < 6; k++) { const double v = st[12 + k] * cc[0] + st[18 + k] * cc[1]; wo[k] = v; wg[k] = v; }
+        }
       }
+    }
+    __syncthreads();
+    // ---- A2: anchor reductions, 35 outputs per landmark (A^T A lower triangle 21, A^T c 6, A^T r 6, h, b),
+    //      all of the form sum_f st[p]*st[q] + st[p2]*st[q2]
+    for (int task = tid; task < nl * 35; task += BA_THREADS) {
+      const int lc = task / 35, o = task - lc * 35;
+      int p, q, p2, q2;
+      if (o < 21) { p = c_triA[o]; q = c_triB[o]; p2 = p + 6; q2 = q + 6; }
+      else if (o < 27) { p = o - 21; q = 24; p2 = p + 6; q2 = 25; }
+      else if (o < 33) { p = o - 27; q = 26; p2 = p + 6; q2 = 27; }
+      else if (o == 33) { p = 24; q = 24; p2 = 25; q2 = 25; }
+      else { p = 24; q = 26; p2 = 25; q2 = 27; }
+      const int nf = sMeta[lc * 2 + 1] - 1;
+      const double* st = sFac + (size_t)lc * FS * STG;
       double s0 = 0, s1 = 0;
-      for (int f = 0; f < nfac; f++) {
-        const double* st = stage + f * STG;
-        s0 += st[pp[0]] * st[qa[0]] + st[pp[0] + 6] * st[qb[0]];
-        s1 += st[pp[1]] * st[qa[1]] + st[pp[1] + 6] * st[qb[1]];
+      int f = 0;
+      for (; f + 1 < nf; f += 2, st += 2 * STG) {
+        s0 += st[p] * st[q] + st[p2] * st[q2];
+        s1 += st[STG + p] * st[STG + q] + st[STG + p2] * st[STG + q2];
       }
-      double* blk00 = acc + tri(fi, fi) * ACS;
-      AtA[lane] = s0;            // lane < 32 < 36
-      blk00[lane] += s0;         // visual J^T J of the anchor block goes straight to the accumulator
-      if (lane < 4) { AtA[lane + 32] = s1; blk00[lane + 32] += s1; }
-      else if (lane < 10) wv[lane - 4] = s1;
-      else if (lane < 16) gA[lane - 10] = s1;
+      if (f < nf) s0 += st[p] * st[q] + st[p2] * st[q2];
+      const double sv = s0 + s1;
+      if (o < 21) { sAtA[lc * 36 + p * 6 + q] = sv; sAtA[lc * 36 + q * 6 + p] = sv; }
+      else if (o < 27) { sW[(size_t)lc * K6 + (o - 21)] = sv; bt.w[(size_t)sMeta[lc * 2] * 6 + (o - 21)] = sv; }
+      else if (o < 33) sgA[lc * 6 + (o - 27)] = sv;
+      else if (o == 33) sSc[lc * 4 + 2] = sv;
+      else sSc[lc * 4 + 1] = sv;
     }
-    if (lane < nfac) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) wv[(lane + 1) * 6 + k] = wB[k];
-    }
-    __syncwarp();
-    // LM damping of the eliminated block (Ceres LevenbergMarquardtStrategy with Jacobi scaling)
-    double sl2 = 1.0;
-    if (bt.jacobi_scaling) {
-      if (first) { double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
-      else sl2 = bt.sl2[l];
-    }
-    double ddl = fmin(fmax(sl2 * h, 1e-6), 1e32) / (radius * sl2);
-    double inv_hd = 1.0 / (h + ddl);
-    if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
-    gmax_w = fmax(gmax_w, fabs(b));
-    if (lane == 0) {
+    __syncthreads();
+    // ---- A3: damping of the eliminated block (Ceres LevenbergMarquardtStrategy, Jacobi scaling), outputs
+    if (tid < nl) {
+      const int l = lb + tid;
+      const double h = sSc[tid * 4 + 2], b = sSc[tid * 4 + 1];
+      double sl2 = 1.0;
+      if (bt.jacobi_scaling) {
+        if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
+        else sl2 = bt.sl2[l];
+      }
+      const double ddl = fmin(fmax(sl2 * h, 1e-6), 1e32) / (radius * sl2);
+      double inv_hd = 1.0 / (h + ddl);
+      if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
+      sSc[tid * 4] = inv_hd;
+      gmax_t = fmax(gmax_t, fabs(b));
       bt.h[l] = h; bt.b[l] = b;
       if (first) bt.sl2[l] = sl2;
     }
-    for (int e = lane; e < n * 6; e += 32) bt.w[(size_t)o0 * 6 + e] = wv[e];
-    // accumulate this landmark's (J^T J - w w^T / (h + d)) into the warp's private S blocks
-    // One lane per 6x6 block pair (a >= b over the landmark's observations): the 36 products live in
-    // registers, the block is a padded (ACS = 37) private slice, so lanes never collide on a bank.
-    const int nbp = n * (n + 1) / 2;
-    for (int pr = lane; pr < nbp; pr += 32) {
-      int a = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
-      if (a * (a + 1) / 2 > pr) a--;
-      if ((a + 1) * (a + 2) / 2 <= pr) a++;
-      const int b2 = pr - a * (a + 1) / 2;
-      const int fa = sfr[a], fb = sfr[b2];
-      double wa[6], wb[6], X0[6], X1[6], Y0[6], Y1[6];
+    __syncthreads();
+    // ---- B: register accumulation of sum_l (J^T J - w w^T / (h + d))
+    for (int lc = 0; lc < nl; lc++) {
+      const double inv = sSc[lc * 4], bl = sSc[lc * 4 + 1];
+      const signed char* oi = sOidx + lc * K;
+      const double* W = sW + (size_t)lc * K6;
+      const double* F = sFac + (size_t)lc * FS * STG;
 #pragma unroll
-      for (int k = 0; k < 6; k++) { wa[k] = -inv_hd * wv[a * 6 + k]; wb[k] = wv[b2 * 6 + k]; }
-      // visual J^T J part: (a,a) -> B_a^T B_a ; (a,0) -> B_a^T A_a ; (0,0) -> sum_f A_f^T A_f (added below)
-      const bool has = (a > 0) && (b2 == 0 || a == b2);
-      const double* sx = stage + (a > 0 ? a - 1 : 0) * STG + 12;
-      const double* sy = (b2 == 0) ? sx - 12 : sx;
+      for (int u = 0; u < NS; u++) {
+        if (s_p[u] < 0) continue;
+        const int a = oi[s_p[u]], b = oi[s_q[u]];
+        if (a < 0 || b < 0) continue;
+        const int r0 = s_r[u];
+        const double* wa = W + a * 6 + r0;
+        const double* wb = W + b * 6;
+        double war[3], wbv[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) {
-        X0[k] = has ? sx[k] : 0.0; X1[k] = has ? sx[6 + k] : 0.0;
-        Y0[k] = has ? sy[k] : 0.0; Y1[k] = has ? sy[6 + k] : 0.0;
+        for (int i = 0; i < 3; i++) war[i] = -inv * wa[i];
+#pragma unroll
+        for (int c = 0; c < 6; c++) wbv[c] = wb[c];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int c = 0; c < 6; c++) acc[u][i][c] = fma(war[i], wbv[c], acc[u][i][c]);
+        if (b == 0 && a == 0) {
+          const double* at = sAtA + lc * 36 + r0 * 6;      // sum_f A_f^T A_f
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[u][i][c] += at[i * 6 + c];
+        } else if (b == 0 || a == b) {
+          // (a,0) -> B_a^T A_a ; (a,a) -> B_a^T B_a
+          const double* st = F + (a - 1) * STG;
+          const double* sy = (b == 0) ? st : st + 12;
+          double x0[3], x1[3], y0[6], y1[6];
+#pragma unroll
+          for (int i = 0; i < 3; i++) { x0[i] = st[12 + r0 + i]; x1[i] = st[18 + r0 + i]; }
+#pragma unroll
+          for (int c = 0; c < 6; c++) { y0[c] = sy[c]; y1[c] = sy[6 + c]; }
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[u][i][c] += x0[i] * y0[c] + x1[i] * y1[c];
+        }
       }
-      double* blk = acc + tri(fa, fb) * ACS;
+      if (gwarp) {
 #pragma unroll
-      for (int r = 0; r < 6; r++) {
-        double v[6];
-#pragma unroll
-        for (int c = 0; c < 6; c++) v[c] = blk[r * 6 + c];
-#pragma unroll
-        for (int c = 0; c < 6; c++) v[c] += wa[r] * wb[c] + X0[r] * Y0[c] + X1[r] * Y1[c];
-#pragma unroll
-        for (int c = 0; c < 6; c++) blk[r * 6 + c] = v[c];
+        for (int v = 0; v < 3; v++) {
+          const int gi = glane + 32 * v;
+          if (gi >= K6) continue;
+          const int gp = gi / 6, gr = gi - gp * 6;
+          const int a = oi[gp];
+          if (a < 0) continue;
+          double gv, dv;
+          if (a == 0) { gv = sgA[lc * 6 + gr]; dv = sAtA[lc * 36 + gr * 7]; }
+          else {
+            const double* st = F + (a - 1) * STG;
+            gv = st[12 + gr] * st[26] + st[18 + gr] * st[27];
+            dv = st[12 + gr] * st[12 + gr] + st[18 + gr] * st[18 + gr];
+          }
+          g_bp[v] += gv;
+          g_red[v] += gv - W[a * 6 + gr] * bl * inv;
+          g_dg[v] += dv;
+        }
       }
     }
-    for (int e = lane; e < n * 6; e += 32) {
-      int a = e / 6, r = e - a * 6;
-      int idx = sfr[a] * 6 + r;
-      double gv, dv;
-      if (a == 0) { gv = gA[r]; dv = AtA[r * 7]; }
-      else {
-        const double* st = stage + (a - 1) * STG;
-        gv = st[12 + r] * st[26] + st[18 + r] * st[27];
-        dv = st[12 + r] * st[12 + r] + st[18 + r] * st[18 + r];
-      }
-      bpv[idx] += gv;
-      gred[idx] += gv - wv[e] * b * inv_hd;
-      dgh[idx] += dv;
-    }
-    __syncwarp();
   }
-  if (lane == 0) { sScal[warp] = cost_w; sScal[8 + warp] = gmax_w; }
-  __syncthreads();
-  // fixed-order reduction over the warps, one tile record to HBM
+  // ---- one tile record to HBM
   double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(K);
-  const double* base = sScal + 16;
-  for (int i = threadIdx.x; i < REC; i += blockDim.x) {
-    double s = 0;
-    const int si = i < NPb * 36 ? (i / 36) * ACS + (i % 36) : i - NPb * 36 + NPb * ACS;
-    for (int q = 0; q < NW; q++) s += base[(size_t)q * per_warp + si];
-    out[i] = s;
+#pragma unroll
+  for (int u = 0; u < NS; u++) {
+    if (s_p[u] < 0) continue;
+    double* o = out + (size_t)tri(s_p[u], s_q[u]) * 36 + s_r[u] * 6;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) o[i * 6 + c] = acc[u][i][c];
   }
-  if (threadIdx.x == 0) {
-    double c = 0, g = 0;
-    for (int q = 0; q < NW; q++) { c += sScal[q]; g = fmax(g, sScal[8 + q]); }
-    out[REC] = c; out[REC + 1] = g; out[REC + 2] = 0; out[REC + 3] = 0;
+  if (gwarp) {
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+      const int gi = glane + 32 * v;
+      if (gi < K6) { out[NPb * 36 + gi] = g_red[v]; out[NPb * 36 + K6 + gi] = g_bp[v]; out[NPb * 36 + 2 * K6 + gi] = g_dg[v]; }
+    }
+  }
+  __syncthreads();
+  const double c = block_sum(cost_t, sRed);
+  const double gm = block_max(gmax_t, sRed + 8);
+  if (tid == 0) {
+    const int REC = NPb * 36 + 3 * K6;
+    out[REC] = c; out[REC + 1] = gm; out[REC + 2] = 0; out[REC + 3] = 0;
   }
 }
 
 // =============================================================================================
 // solve: one CTA per window
 // =============================================================================================
-__global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_kernel(BaBatch bt, int with_step) {
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, int with_step) {
   extern __shared__ double sm[];
   const int w = blockIdx.x, K = bt.K, np = bt.np, K6 = 6 * K, NPb = K * (K + 1) / 2;
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -721,22 +776,28 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_kernel(BaBatch bt, int
   for (int kb = 0; kb < K; kb++) {
     const int j0 = 15 * kb;
     if (tid < 32) {
+      // 15 x 15 diagonal block in registers: lane i holds row i, column j broadcast by shuffles
+      double a[15];
+#pragma unroll
+      for (int k = 0; k < 15; k++) a[k] = (tid < 15 && k <= tid) ? S[tri(j0 + tid, j0 + k)] : 0.0;
+      bool bad = false;
+#pragma unroll
       for (int j = 0; j < 15; j++) {
-        double d = S[tri(j0 + j, j0 + j)];
-        if (!(d > 0.0)) { if (tid == 0) s_fail = 1; d = 1.0; }
-        d = sqrt(d);
-        __syncwarp();
-        if (tid == j) S[tri(j0 + j, j0 + j)] = d;
-        if (tid > j && tid < 15) S[tri(j0 + tid, j0 + j)] /= d;
-        __syncwarp();
-        // trailing update inside the diagonal block
-        for (int e = tid; e < 105; e += 32) {
-          int a = c_triA[e], b2 = c_triB[e];   // a >= b2 in 0..13
-          int i = j + 1 + a, k2 = j + 1 + b2;
-          if (i < 15) S[tri(j0 + i, j0 + k2)] -= S[tri(j0 + i, j0 + j)] * S[tri(j0 + k2, j0 + j)];
+        const double pj = __shfl_sync(0xffffffffu, a[j], j);
+        bad |= !(pj > 0.0);
+        const double inv = rsqrt(pj);
+        a[j] *= inv;
+#pragma unroll
+        for (int k = j + 1; k < 15; k++) {
+          const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+          a[k] = fma(-a[j], lkj, a[k]);
         }
-        __syncwarp();
       }
+      if (tid < 15) {
+#pragma unroll
+        for (int k = 0; k < 15; k++) if (k <= tid) S[tri(j0 + tid, j0 + k)] = a[k];
+      }
+      if (bad && tid == 0) s_fail = 1;
     }
     __syncthreads();
     if (s_fail) break;
@@ -780,17 +841,32 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_kernel(BaBatch bt, int
   // back substitution L^T dp = y (warp 0)
   for (int i = tid; i < np; i += nthr) yv[i] = S[tri(np, i)];
   __syncthreads();
-  if (tid < 32) {
-    for (int i = np - 1; i >= 0; i--) {
-      const double* row = S + tri(i, 0);
-      double di = yv[i] / row[i];
-      __syncwarp();
-      for (int k = tid; k < i; k += 32) yv[k] -= row[k] * di;
-      if (tid == 0) yv[i] = di;
-      __syncwarp();
+  // blocked: per 15-block one warp solves L_kk^T x = y_k in registers (lane d holds column d of L_kk),
+  // then all threads eliminate x from the rows above
+  for (int kb = K - 1; kb >= 0; kb--) {
+    const int j0 = 15 * kb;
+    if (tid < 32) {
+      double col[15];
+#pragma unroll
+      for (int k = 0; k < 15; k++) col[k] = (tid < 15 && k >= tid) ? S[tri(j0 + k, j0 + tid)] : 1.0;
+      double y = tid < 15 ? yv[j0 + tid] : 0.0;
+#pragma unroll
+      for (int c = 14; c >= 0; c--) {
+        const double xc = __shfl_sync(0xffffffffu, y / col[c], c);
+        if (tid == c) y = xc;
+        else if (tid < c) y = fma(-col[c], xc, y);
+      }
+      if (tid < 15) yv[j0 + tid] = y;
     }
+    __syncthreads();
+    for (int k = tid; k < j0; k += nthr) {
+      double v = yv[k];
+#pragma unroll
+      for (int c = 0; c < 15; c++) v = fma(-S[tri(j0 + c, k)], yv[j0 + c], v);
+      yv[k] = v;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // step + pose part of the model cost change:  -g^T d - 1/2 d^T H d = -1/2 g^T d + 1/2 d^T D d
   double mp = 0;
   for (int i = tid; i < np; i += nthr) {
@@ -1007,15 +1083,18 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
 // =============================================================================================
 static size_t imu_prior_smem(int K, int nmax) { return sizeof(double) * ((size_t)(K - 1) * (900 + 30) + 2 * nmax); }
 
-size_t ba_linearize_smem_bytes(int K, int nwarps) {
-  int NPb = K * (K + 1) / 2, REC = NPb * ACS + 18 * K;
-  size_t per_warp = REC + (BVIO_KMAX - 1) * STG + BVIO_KMAX * 6 + 36 + 6 + BVIO_KMAX;
-  return sizeof(double) * ((size_t)(K + 1) * FR + 16 + per_warp * nwarps);
+size_t ba_linearize_smem_bytes(int K, int CL) {
+  const int FS = K - 1;
+  size_t d = (size_t)(K + 1) * FR + 16 + (size_t)CL * (FS * STG + 6 * K + 36 + 6 + 4);
+  size_t bytes = d * sizeof(double) + (size_t)CL * 2 * sizeof(int) + (size_t)CL * K;
+  return (bytes + 15) & ~size_t(15);
 }
-int ba_pick_linearize_warps(int K) {
-  int nw = 8;
-  while (nw > 1 && ba_linearize_smem_bytes(K, nw) > 216 * 1024) nw--;
-  return nw;
+// landmarks per chunk: one (landmark, factor) slot per thread, capped so that two CTAs fit an SM
+int ba_pick_chunk(int K) {
+  int CL = BA_THREADS / (K - 1);
+  if (CL > 64) CL = 64;
+  while (CL > 1 && ba_linearize_smem_bytes(K, CL) > 100 * 1024) CL--;
+  return CL;
 }
 size_t ba_solve_smem_bytes(int K) {
   int np = 15 * K, N1 = np + 1;
@@ -1039,7 +1118,10 @@ int ba_configure(void) {
     if ((err = cudaMemcpyToSymbol(c_triB, tb, sizeof tb)) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_tri30A, ua, sizeof ua)) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_tri30B, ub, sizeof ub)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_linearize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
     g_tables_done = true;
@@ -1061,10 +1143,14 @@ int ba_launch_reset(const BaBatch& bt, cudaStream_t st) {
   return 1;
 }
 int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cudaEvent_t* ev) {
-  size_t s1 = ba_linearize_smem_bytes(bt.K, bt.nwarps_lin), s1b = imu_prior_smem(bt.K, bt.nmax);
+  size_t s1 = ba_linearize_smem_bytes(bt.K, bt.chunk_l), s1b = imu_prior_smem(bt.K, bt.nmax);
   if (s1b > s1) s1 = s1b;
   if (ev) cudaEventRecord(ev[0], st);
-  ba_linearize_kernel<<<dim3(bt.T + 1, bt.B), 32 * bt.nwarps_lin, s1, st>>>(bt);
+  const int nstrip = (bt.K * (bt.K + 1) / 2) * 2;   // half-block units
+  if (nstrip <= BA_THREADS - 32) ba_linearize_kernel<1><<<dim3(bt.T + 1, bt.B), BA_THREADS, s1, st>>>(bt);
+  else if (nstrip <= 2 * (BA_THREADS - 32)) ba_linearize_kernel<2><<<dim3(bt.T + 1, bt.B), BA_THREADS, s1, st>>>(bt);
+  else if (nstrip <= 3 * (BA_THREADS - 32)) ba_linearize_kernel<3><<<dim3(bt.T + 1, bt.B), BA_THREADS, s1, st>>>(bt);
+  else ba_linearize_kernel<4><<<dim3(bt.T + 1, bt.B), BA_THREADS, s1, st>>>(bt);
   if (ev) cudaEventRecord(ev[1], st);
   ba_solve_kernel<<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.K), st>>>(bt, with_step ? 1 : 0);
   if (ev) cudaEventRecord(ev[2], st);

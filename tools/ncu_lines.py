@@ -48,7 +48,7 @@ def main():
     ts = sum(v[1] for v in agg.values()) or 1
     lines = open(src).read().split("\n") if src else None
     print(f"total warp-instructions {ti}, samples {ts}")
-    for key, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+    for key, v in sorted(agg.items(), key=lambda kv: -(kv[1][0] if "--by-inst" in sys.argv else kv[1][1]))[:top]:
         text = ""
         if lines and key and key[1] - 1 < len(lines):
             text = lines[key[1] - 1].strip()[:90]
