@@ -906,4 +906,200 @@ void oracle_double2vector(const double pre_pose0[7], int K, double* para_pose, d
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// a9: marginalization.  Literal restatement of the tail of Estimator::optimization()
+// (estimator.cpp:816-991) and MarginalizationInfo::{addResidualBlockInfo, preMarginalize, marginalize,
+// getParameterBlocks} (marginalization_factor.cpp:89-319): every factor that touches a dropped block is
+// evaluated at the current state (Cauchy corrector on visual factors, ResidualBlockInfo::Evaluate :37-68),
+// A = sum J^T J, b = sum J^T r over the local (6/9/6/1) coordinates with the dropped blocks first,
+// Amm pseudo-inverse by eigen-decomposition with eps = 1e-8 (marginalization_factor.h:70), Schur
+// complement, second eigen-decomposition -> linearized_jacobians / linearized_residuals.
+// Deviation: the reference orders blocks by std::unordered_map<long,...> iteration over ADDRESSES
+// (implementation-defined); we use frame order (Pose f, SpeedBias f ascending, then Ex_Pose).  The
+// quadratic form is order-invariant; rows of J are defined up to the eigenvector basis.
+// flag 1 (MARGIN_SECOND_NEW) when the prior does not touch Pose[K-2]: out->n = -1 (prior unchanged).
+int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_prior_out* out) {
+  if (o->estimate_td || o->estimate_extrinsic) return BVIO_ERR_UNSUPPORTED;
+  const int K = w->K, L = w->L;
+  const double eps = 1e-8;
+  // variable ids: pose f -> f, sb f -> K+f, ex -> 2K, landmark l -> 2K+1+l
+  const int NV = 2 * K + 1 + L;
+  auto vloc = [&](int v) { return v < K ? 6 : (v < 2 * K ? 9 : (v == 2 * K ? 6 : 1)); };
+  std::vector<char> present(NV, 0), drop(NV, 0);
+  struct Fac { std::vector<int> vars; std::vector<std::vector<double>> J; std::vector<double> r; };
+  std::vector<Fac> facs;
+  const bvio_prior* pr = w->prior;
+  auto prior_var = [&](int b) {
+    int kind = pr->block_kind[b];
+    return kind == BVIO_BLK_POSE ? pr->block_frame[b] : (kind == BVIO_BLK_SPEEDBIAS ? K + pr->block_frame[b] : 2 * K);
+  };
+  auto add_prior = [&]() {
+    int n = pr->n;
+    Fac f;
+    f.r.resize(n);
+    std::vector<double> dx(n);
+    prior_eval(pr, w, f.r.data(), dx.data());
+    for (int b = 0; b < pr->nblocks; b++) {
+      if (pr->block_kind[b] == BVIO_BLK_TD) continue;
+      int loc = blk_local(pr->block_kind[b]), idx = pr->block_idx[b];
+      std::vector<double> J((size_t)n * loc);
+      for (int i = 0; i < n; i++)
+        for (int c = 0; c < loc; c++) J[(size_t)i * loc + c] = pr->lin_jac[(size_t)(idx + c) * n + i];
+      f.vars.push_back(prior_var(b));
+      f.J.push_back(J);
+    }
+    facs.push_back(f);
+  };
+  if (flag == 0) {
+    if (pr) { add_prior(); }
+    if (w->preint[1].sum_dt < 10.0) {
+      double si[225], r[15], Jpi[105], Jsbi[135], Jpj[105], Jsbj[135];
+      imu_sqrt_info(w->preint[1].covariance, si);
+      imu_eval(&w->preint[1], v3(o->G), w->para_pose, w->para_speed_bias, w->para_pose + 7, w->para_speed_bias + 9, si, r,
+               Jpi, Jsbi, Jpj, Jsbj);
+      Fac f;
+      f.r.assign(r, r + 15);
+      auto take = [&](const double* J, int cols, int loc) {
+        std::vector<double> o2((size_t)15 * loc);
+        for (int i = 0; i < 15; i++) for (int c = 0; c < loc; c++) o2[(size_t)i * loc + c] = J[i * cols + c];
+        return o2;
+      };
+      f.vars = {0, K, 1, K + 1};
+      f.J = {take(Jpi, 7, 6), take(Jsbi, 9, 9), take(Jpj, 7, 6), take(Jsbj, 9, 9)};
+      facs.push_back(f);
+      drop[0] = drop[K] = 1;
+    }
+    if (pr) for (int b = 0; b < pr->nblocks; b++) { int v = prior_var(b); if (v == 0 || v == K) drop[v] = 1; }
+    double sqrt_info = o->focal_length / 1.5;
+    V3 tic = v3(w->para_ex_pose); Q4 qic = q4(w->para_ex_pose + 3);
+    for (int l = 0; l < L; l++) {
+      int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
+      if (w->obs_frame[o0] != 0) continue;
+      V3 pts_i{w->obs_xy[2 * o0], w->obs_xy[2 * o0 + 1], 1.0};
+      for (int k = o0 + 1; k < o1; k++) {
+        int fj = w->obs_frame[k];
+        V3 pts_j{w->obs_xy[2 * k], w->obs_xy[2 * k + 1], 1.0};
+        double r[2], Ji[14], Jj[14], Jex[14], Jf[2];
+        projection_eval(pts_i, pts_j, v3(w->para_pose), q4(w->para_pose + 3), v3(w->para_pose + 7 * fj),
+                        q4(w->para_pose + 7 * fj + 3), tic, qic, w->inv_depth[l], sqrt_info, r, Ji, Jj, Jex, Jf);
+        double rho[3];
+        cauchy(o->cauchy_a, r[0] * r[0] + r[1] * r[1], rho);
+        double sr = std::sqrt(rho[1]);   // rho'' <= 0 for Cauchy: the simple branch of the corrector
+        Fac f;
+        f.r = {sr * r[0], sr * r[1]};
+        auto take = [&](const double* J) {
+          std::vector<double> o2(12);
+          for (int a = 0; a < 2; a++) for (int c = 0; c < 6; c++) o2[a * 6 + c] = sr * J[a * 7 + c];
+          return o2;
+        };
+        f.vars = {0, fj, 2 * K, 2 * K + 1 + l};
+        f.J = {take(Ji), take(Jj), take(Jex), std::vector<double>{sr * Jf[0], sr * Jf[1]}};
+        facs.push_back(f);
+        drop[0] = 1; drop[2 * K + 1 + l] = 1;
+      }
+    }
+  } else {
+    bool touches = false;
+    if (pr) for (int b = 0; b < pr->nblocks; b++) if (pr->block_kind[b] == BVIO_BLK_POSE && pr->block_frame[b] == K - 2) touches = true;
+    if (!touches) { out->n = -1; out->nblocks = 0; return BVIO_OK; }
+    add_prior();
+    drop[K - 2] = 1;
+  }
+  for (auto& f : facs) for (int v : f.vars) present[v] = 1;
+  // ordering: dropped first, kept after (frame order)
+  std::vector<int> idx(NV, -1), order;
+  int pos = 0;
+  auto push = [&](int v) { if (present[v] && idx[v] < 0) { idx[v] = pos; pos += vloc(v); order.push_back(v); } };
+  for (int f = 0; f < K; f++) { if (drop[f]) push(f); if (drop[K + f]) push(K + f); }
+  for (int l = 0; l < L; l++) if (drop[2 * K + 1 + l]) push(2 * K + 1 + l);
+  const int m = pos;
+  std::vector<int> kept;
+  for (int f = 0; f < K; f++) {
+    if (present[f] && !drop[f]) { push(f); kept.push_back(f); }
+    if (present[K + f] && !drop[K + f]) { push(K + f); kept.push_back(K + f); }
+  }
+  if (present[2 * K] && !drop[2 * K]) { push(2 * K); kept.push_back(2 * K); }
+  const int n = pos - m;
+  std::vector<double> A((size_t)pos * pos, 0.0), b(pos, 0.0);
+  for (auto& f : facs) {
+    int rows = (int)f.r.size();
+    for (size_t i = 0; i < f.vars.size(); i++) {
+      int ii = idx[f.vars[i]], si = vloc(f.vars[i]);
+      for (size_t j = 0; j < f.vars.size(); j++) {
+        int jj = idx[f.vars[j]], sj = vloc(f.vars[j]);
+        for (int a = 0; a < si; a++)
+          for (int c = 0; c < sj; c++) {
+            double s = 0;
+            for (int k = 0; k < rows; k++) s += f.J[i][(size_t)k * si + a] * f.J[j][(size_t)k * sj + c];
+            A[(size_t)(ii + a) * pos + jj + c] += s;
+          }
+      }
+      for (int a = 0; a < si; a++) {
+        double s = 0;
+        for (int k = 0; k < rows; k++) s += f.J[i][(size_t)k * si + a] * f.r[k];
+        b[ii + a] += s;
+      }
+    }
+  }
+  // Amm pseudo-inverse
+  std::vector<double> Amm((size_t)m * m), wv(m), Vm((size_t)m * m), Ainv((size_t)m * m, 0.0);
+  for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Amm[(size_t)i * m + j] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]);
+  if (m > 0) jacobi_eigh(Amm.data(), m, wv.data(), Vm.data());
+  for (int k = 0; k < m; k++) {
+    if (!(wv[k] > eps)) continue;
+    double iv = 1.0 / wv[k];
+    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Ainv[(size_t)i * m + j] += Vm[(size_t)i * m + k] * iv * Vm[(size_t)j * m + k];
+  }
+  // Schur complement
+  std::vector<double> T((size_t)n * m, 0.0), Ar((size_t)n * n), br(n);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < m; j++) {
+      double s = 0;
+      for (int k = 0; k < m; k++) s += A[(size_t)(m + i) * pos + k] * Ainv[(size_t)k * m + j];
+      T[(size_t)i * m + j] = s;
+    }
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < n; j++) {
+      double s = A[(size_t)(m + i) * pos + m + j];
+      for (int k = 0; k < m; k++) s -= T[(size_t)i * m + k] * A[(size_t)k * pos + m + j];
+      Ar[(size_t)i * n + j] = s;
+    }
+    double s = b[m + i];
+    for (int k = 0; k < m; k++) s -= T[(size_t)i * m + k] * b[k];
+    br[i] = s;
+  }
+  // second eigen-decomposition (Eigen reads the lower triangle; symmetrise for the Jacobi sweeps)
+  std::vector<double> As((size_t)n * n), S(n), V((size_t)n * n);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) As[(size_t)i * n + j] = 0.5 * (Ar[(size_t)i * n + j] + Ar[(size_t)j * n + i]);
+  if (n > 0) jacobi_eigh(As.data(), n, S.data(), V.data());
+  if (n > out->cap_n || (int)kept.size() > out->cap_blocks) return BVIO_ERR_INVALID;
+  out->n = n;
+  out->nblocks = (int)kept.size();
+  for (int k = 0; k < n; k++) {
+    double sk = S[k] > eps ? S[k] : 0.0, sik = S[k] > eps ? 1.0 / S[k] : 0.0;
+    double sq = std::sqrt(sk), siq = std::sqrt(sik), vb = 0;
+    for (int i = 0; i < n; i++) {
+      out->lin_jac[(size_t)i * n + k] = sq * V[(size_t)i * n + k];   // J(k,i), column-major n x n
+      vb += V[(size_t)i * n + k] * br[i];
+    }
+    out->lin_res[k] = siq * vb;
+  }
+  double* x0 = out->x0;
+  for (size_t bi = 0; bi < kept.size(); bi++) {
+    int v = kept[bi], kind, frame = 0;
+    const double* src;
+    if (v < K) { kind = BVIO_BLK_POSE; frame = v; src = w->para_pose + 7 * v; }
+    else if (v < 2 * K) { kind = BVIO_BLK_SPEEDBIAS; frame = v - K; src = w->para_speed_bias + 9 * (v - K); }
+    else { kind = BVIO_BLK_EXPOSE; src = w->para_ex_pose; }
+    int gs = blk_global(kind);
+    // addr_shift (estimator.cpp:904-916 / 962-984)
+    if (kind != BVIO_BLK_EXPOSE) frame = (flag == 0) ? frame - 1 : (frame == K - 1 ? K - 2 : frame);
+    out->block_kind[bi] = kind; out->block_frame[bi] = frame; out->block_idx[bi] = idx[v] - m;
+    std::memcpy(x0, src, sizeof(double) * gs);
+    x0 += gs;
+  }
+  return BVIO_OK;
+}
+
 }  // extern "C"
