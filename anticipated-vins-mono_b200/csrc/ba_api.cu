@@ -454,8 +454,95 @@ int bvio_batch_solve_timed(bvio_ctx* ctx, bvio_batch* bb, double out_ms[4], int3
   return BVIO_OK;
 }
 
-int bvio_marginalize(bvio_ctx* ctx, const bvio_window*, const bvio_opts*, int32_t, bvio_prior_out*) {
-  return fail(ctx, BVIO_ERR_UNSUPPORTED, "bvio_marginalize: not implemented yet (SURVEY.md row f1)");
+// Marginalization tail of Estimator::optimization() (estimator.cpp:816-991).  The host only decides
+// which parameter blocks are present / dropped / kept (pure bookkeeping over the window structure,
+// what MarginalizationInfo::addResidualBlockInfo does with its address maps); all arithmetic runs in
+// ba_marginalize_kernel.  Kept blocks come out in frame order (Pose f, SpeedBias f ascending, then
+// Ex_Pose) with the reference's addr_shift applied.  flag 1 and a prior that does not touch Pose[K-2]:
+// out->n = -1 (the reference leaves last_marginalization_info untouched, estimator.cpp:926-928).
+int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts, int32_t flag, bvio_prior_out* out) {
+  if (!ctx || !w || !opts || !out || (flag != 0 && flag != 1)) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
+  const int K = w->K;
+  int rc = validate(ctx, w, opts, K);
+  if (rc) return rc;
+  const bvio_prior* pr = w->prior;
+  std::vector<char> has_pose(K, 0), has_sb(K, 0);
+  bool has_ex = false;
+  if (pr) for (int b = 0; b < pr->nblocks; b++) {
+    int kind = pr->block_kind[b], f = pr->block_frame[b];
+    if (kind == BVIO_BLK_POSE) has_pose[f] = 1;
+    else if (kind == BVIO_BLK_SPEEDBIAS) has_sb[f] = 1;
+    else if (kind == BVIO_BLK_EXPOSE) has_ex = true;
+  }
+  std::vector<int> dropidx, keepidx;
+  if (flag == 1) {
+    if (!pr || !has_pose[K - 2]) { out->n = -1; out->nblocks = 0; return BVIO_OK; }
+    for (int i = 0; i < 6; i++) dropidx.push_back(15 * (K - 2) + i);
+    has_pose[K - 2] = 0;
+  } else {
+    if (w->preint[1].sum_dt < 10.0) { has_pose[0] = has_sb[0] = has_pose[1] = has_sb[1] = 1; }
+    for (int l = 0; l < w->L; l++) {
+      int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
+      if (w->obs_frame[o0] != 0) continue;
+      has_ex = true;
+      for (int k = o0; k < o1; k++) has_pose[w->obs_frame[k]] = 1;
+    }
+    for (int i = 0; i < 15; i++) dropidx.push_back(i);
+    has_pose[0] = has_sb[0] = 0;
+  }
+  struct Blk { int kind, frame, idx; };
+  std::vector<Blk> blocks;
+  int n = 0;
+  for (int f = 0; f < K; f++) {
+    if (has_pose[f]) { blocks.push_back({BVIO_BLK_POSE, f, n}); for (int i = 0; i < 6; i++) keepidx.push_back(15 * f + i); n += 6; }
+    if (has_sb[f]) { blocks.push_back({BVIO_BLK_SPEEDBIAS, f, n}); for (int i = 0; i < 9; i++) keepidx.push_back(15 * f + 6 + i); n += 9; }
+  }
+  if (has_ex) { blocks.push_back({BVIO_BLK_EXPOSE, 0, n}); for (int i = 0; i < 6; i++) keepidx.push_back(15 * K + i); n += 6; }
+  const int m = (int)dropidx.size();
+  if (n > out->cap_n || (int)blocks.size() > out->cap_blocks) return fail(ctx, BVIO_ERR_INVALID, "bvio_prior_out capacity too small");
+  out->n = n;
+  out->nblocks = (int)blocks.size();
+  double* x0 = out->x0;
+  for (size_t i = 0; i < blocks.size(); i++) {
+    const Blk& bl = blocks[i];
+    const double* src = bl.kind == BVIO_BLK_POSE ? w->para_pose + 7 * bl.frame
+                        : bl.kind == BVIO_BLK_SPEEDBIAS ? w->para_speed_bias + 9 * bl.frame : w->para_ex_pose;
+    int gs = bl.kind == BVIO_BLK_SPEEDBIAS ? 9 : 7;
+    int frame = bl.frame;
+    if (bl.kind != BVIO_BLK_EXPOSE) frame = (flag == 0) ? frame - 1 : (frame == K - 1 ? K - 2 : frame);   // addr_shift
+    out->block_kind[i] = bl.kind; out->block_frame[i] = frame; out->block_idx[i] = bl.idx;
+    memcpy(x0, src, sizeof(double) * gs);
+    x0 += gs;
+  }
+  if (n == 0) return BVIO_OK;
+  const int M = 15 * K + 6;
+  if (ba_marginalize_smem_bytes(K, pr ? pr->n : 1, n) > 220 * 1024)
+    return fail(ctx, BVIO_ERR_UNSUPPORTED, "kept dimension too large for the single-CTA eigen-decomposition");
+  bvio_batch* bb = nullptr;
+  rc = upload_impl(ctx, w, 1, opts, true, 0, &bb);
+  if (rc) return rc;
+  char* scratch = nullptr;
+  Carver cv;
+  size_t o_A = cv.take(sizeof(double) * M * M), o_b = cv.take(sizeof(double) * M), o_jac = cv.take(sizeof(double) * n * n);
+  size_t o_res = cv.take(sizeof(double) * n), o_drop = cv.take(sizeof(int) * (m + 1)), o_keep = cv.take(sizeof(int) * n);
+  size_t o_st = cv.take(sizeof(int) * 4);
+  cudaError_t e = cudaMalloc((void**)&scratch, cv.off);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_drop, dropidx.data(), sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_keep, keepidx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    ctx->launches += ba_launch_marginalize(bb->bt, flag, m, n, (const int*)(scratch + o_drop), (const int*)(scratch + o_keep),
+                                           (double*)(scratch + o_A), (double*)(scratch + o_b), (double*)(scratch + o_jac),
+                                           (double*)(scratch + o_res), (int*)(scratch + o_st), ctx->stream);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_jac, scratch + o_jac, sizeof(double) * n * n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_res, scratch + o_res, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (scratch) cudaFree(scratch);
+  bvio_batch_free(ctx, bb);
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("marginalize: ") + cudaGetErrorString(e));
+  for (int i = 0; i < n * n; i++) if (!(out->lin_jac[i] == out->lin_jac[i])) return fail(ctx, BVIO_ERR_NUMERIC, "non-finite prior");
+  return BVIO_OK;
 }
 
 }  // extern "C"

@@ -1165,4 +1165,424 @@ int ba_launch_finish(const BaBatch& bt, cudaStream_t st) {
   return 1;
 }
 
+
+// =============================================================================================
+// marginalization (row a9): MarginalizationInfo::{preMarginalize, marginalize}
+// (marginalization_factor.cpp:109-297) for the factor sets Estimator::optimization() builds at
+// estimator.cpp:816-991.  One CTA.  The scalar inverse-depth blocks are eliminated analytically
+// (they are mutually independent), the <= 15 remaining dropped dimensions by the reference's eigen
+// pseudo-inverse (eps = 1e-8), and the kept system is factored back to (J, r) by a parallel
+// cyclic-Jacobi eigen-decomposition in shared memory (stands in for Eigen::SelfAdjointEigenSolver).
+// =============================================================================================
+struct MargArgs {
+  int flag;             // 0 MARGIN_OLD, 1 MARGIN_SECOND_NEW
+  int M;                // 15K + 6: frame-major 15-blocks, then the extrinsic block
+  int m, n, ne;         // dropped / kept dimensions, ne = n rounded up to even
+  const int* dropidx;   // [m] indices into the M layout
+  const int* keepidx;   // [n]
+  double* A;            // [M*M] scratch
+  double* b;            // [M]
+  double* out_jac;      // [n*n] column-major linearized_jacobians
+  double* out_res;      // [n]
+  int* status;          // [1] sweeps used
+};
+
+constexpr int MARG_THREADS = 512;
+constexpr int MF = 40;      // per-factor staging: A(12) B(12) E(12) c(2) r(2)
+
+// column `d` (visual layout: 6 dims per frame, then 6 extrinsic dims) of factor f's 2 x . Jacobian
+__device__ __forceinline__ void marg_col(const double* st, int fj, int K, int d, double& j0, double& j1) {
+  j0 = 0; j1 = 0;
+  if (d < 6) { j0 = st[d]; j1 = st[6 + d]; }
+  else if (d >= 6 * K) { j0 = st[24 + d - 6 * K]; j1 = st[30 + d - 6 * K]; }
+  else if (d >= 6 * fj && d < 6 * fj + 6) { j0 = st[12 + d - 6 * fj]; j1 = st[18 + d - 6 * fj]; }
+}
+
+__global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch bt, MargArgs ma) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, nt = blockDim.x, K = bt.K, M = ma.M, w = 0;
+  const int VD = 6 * K + 6;                 // visual layout dimension
+  double* A = ma.A;
+  double* bv = ma.b;
+  for (int i = tid; i < M * M; i += nt) A[i] = 0.0;
+  for (int i = tid; i < M; i += nt) bv[i] = 0.0;
+  __syncthreads();
+  auto vmap = [&](int d) { return d < 6 * K ? 15 * (d / 6) + d % 6 : 15 * K + (d - 6 * K); };
+
+  if (ma.flag == 0) {
+    // ---- visual factors of the landmarks anchored at frame 0 (estimator.cpp:852-893)
+    double* sFr = sm;                       // [K*FR]
+    double* sEx = sFr + K * FR;             // [FR]
+    double* sF = sEx + FR;                  // [(KMAX-1)*MF]
+    double* sWv = sF + (BVIO_KMAX - 1) * MF;  // [VD] w, then [VD] J^T r
+    double* sG = sWv + VD;
+    double* sS = sG + VD;                   // [2] h, b
+    int* sFj = reinterpret_cast<int*>(sS + 2);   // [KMAX]
+    stage_frames(bt, w, bt.pose0, sFr, sEx);
+    constexpr int NE = 12;                  // owned entries per thread: VD*VD <= 96*96 = 9216 <= 512*18
+    double acc[18];
+#pragma unroll
+    for (int u = 0; u < 18; u++) acc[u] = 0.0;
+    double gacc = 0.0;
+    (void)NE;
+    __syncthreads();
+    const int L0 = bt.lm_base[0], L1 = bt.lm_base[1];
+    for (int l = L0; l < L1; l++) {
+      const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0, nfac = n - 1;
+      if (bt.obs_frame[o0] != 0) continue;
+      __syncthreads();
+      if (tid < nfac) {
+        const int fj = bt.obs_frame[o0 + 1 + tid];
+        const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + tid];
+        const double lam = bt.invd0[l];
+        const double* Fi = sFr;
+        const double* Fj = sFr + fj * FR;
+        ProjGeom g = proj_geom(Fi, Fj, sEx, pi.x, pi.y, lam);
+        const double inv = 1.0 / g.pcj.z, si = bt.sqrt_info;
+        const double r0 = si * (g.pcj.x * inv - pj.x), r1 = si * (g.pcj.y * inv - pj.y);
+        const double red[2][3] = {{si * inv, 0.0, -si * g.pcj.x * inv * inv}, {0.0, si * inv, -si * g.pcj.y * inv * inv}};
+        double rho0, rho1;
+        cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
+        const double sr = sqrt(rho1);
+        double* st = sF + tid * MF;
+        const d3 tic{sEx[9], sEx[10], sEx[11]};
+        const d3 pci = (1.0 / lam) * d3{pi.x, pi.y, 1.0};
+        // tmp_r = ric^T Rj^T Ri ric ; tvec = ric^T (Rj^T (Ri tic + Pi - Pj) - tic)   (projection_factor.cpp:100-105)
+        double RjTRi[9], T1[9], tmp_r[9];
+        mtm3(Fj, Fi, RjTRi);
+        mtm3(sEx, RjTRi, T1);               // ric^T Rj^T Ri
+        mm3(T1, sEx, tmp_r);
+        const d3 inner = mtv3(Fj, mv3(Fi, tic) + d3{Fi[9], Fi[10], Fi[11]} - d3{Fj[9], Fj[10], Fj[11]}) - tic;
+        const d3 tvec = mtv3(sEx, inner);
+        const d3 trp = mv3(tmp_r, pci);
+        for (int a = 0; a < 2; a++) {
+          double Gm[3], Q[3];
+          for (int c = 0; c < 3; c++) Gm[c] = red[a][0] * sEx[c * 3 + 0] + red[a][1] * sEx[c * 3 + 1] + red[a][2] * sEx[c * 3 + 2];
+          for (int c = 0; c < 3; c++) Q[c] = Gm[0] * Fj[c * 3 + 0] + Gm[1] * Fj[c * 3 + 1] + Gm[2] * Fj[c * 3 + 2];
+          const d3 u = mtv3(Fi, d3{Q[0], Q[1], Q[2]});
+          const d3 jr = cross3(g.pimu_i, u);
+          const d3 jjr = cross3(d3{Gm[0], Gm[1], Gm[2]}, g.pimu_j);
+          st[a * 6 + 0] = sr * Q[0]; st[a * 6 + 1] = sr * Q[1]; st[a * 6 + 2] = sr * Q[2];
+          st[a * 6 + 3] = sr * jr.x; st[a * 6 + 4] = sr * jr.y; st[a * 6 + 5] = sr * jr.z;
+          st[12 + a * 6 + 0] = -sr * Q[0]; st[12 + a * 6 + 1] = -sr * Q[1]; st[12 + a * 6 + 2] = -sr * Q[2];
+          st[12 + a * 6 + 3] = sr * jjr.x; st[12 + a * 6 + 4] = sr * jjr.y; st[12 + a * 6 + 5] = sr * jjr.z;
+          // extrinsic block: reduce * [ ric^T (Rj^T Ri - I) | -tmp_r [pci]x + [tmp_r pci]x + [tvec]x ]
+          const double rd[3] = {red[a][0], red[a][1], red[a][2]};
+          double el[3];
+          for (int c = 0; c < 3; c++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += rd[k] * (T1[k * 3 + c] - sEx[c * 3 + k]);   // ric^T Rj^T Ri - ric^T
+            el[c] = s;
+          }
+          // row^T [v]x = (row x v)^T ;  row^T (-tmp_r [pci]x) = -((tmp_r^T row) x pci)^T
+          const d3 rowv{rd[0], rd[1], rd[2]};
+          const d3 t1 = mtv3(tmp_r, rowv);
+          const d3 e1 = cross3(t1, pci);
+          const d3 e2 = cross3(rowv, trp);
+          const d3 e3 = cross3(rowv, tvec);
+          st[24 + a * 6 + 0] = sr * el[0]; st[24 + a * 6 + 1] = sr * el[1]; st[24 + a * 6 + 2] = sr * el[2];
+          st[24 + a * 6 + 3] = sr * (-e1.x + e2.x + e3.x); st[24 + a * 6 + 4] = sr * (-e1.y + e2.y + e3.y);
+          st[24 + a * 6 + 5] = sr * (-e1.z + e2.z + e3.z);
+          st[36 + a] = sr * (-dot3(u, g.pimu_i - tic) / lam);
+        }
+        st[38] = sr * r0; st[39] = sr * r1;
+        sFj[tid] = fj;
+      }
+      __syncthreads();
+      if (tid < VD) {
+        double wsum = 0, gsum = 0;
+        for (int f = 0; f < nfac; f++) {
+          double j0, j1;
+          const double* st = sF + f * MF;
+          marg_col(st, sFj[f], K, tid, j0, j1);
+          wsum += j0 * st[36] + j1 * st[37];
+          gsum += j0 * st[38] + j1 * st[39];
+        }
+        sWv[tid] = wsum; sG[tid] = gsum;
+      } else if (tid == VD) {
+        double h = 0, bb = 0;
+        for (int f = 0; f < nfac; f++) { const double* st = sF + f * MF; h += st[36] * st[36] + st[37] * st[37]; bb += st[36] * st[38] + st[37] * st[39]; }
+        sS[0] = h; sS[1] = bb;
+      }
+      __syncthreads();
+      const double h = sS[0], bb = sS[1];
+      const double ih = h > 1e-8 ? 1.0 / h : 0.0;      // eps of the reference's pseudo-inverse
+#pragma unroll
+      for (int u = 0; u < 18; u++) {
+        const int e = tid + u * nt;
+        if (e >= VD * VD) break;
+        const int d1 = e / VD, d2 = e - d1 * VD;
+        double s = -sWv[d1] * sWv[d2] * ih;
+        for (int f = 0; f < nfac; f++) {
+          double a0, a1, b0, b1;
+          const double* st = sF + f * MF;
+          marg_col(st, sFj[f], K, d1, a0, a1);
+          marg_col(st, sFj[f], K, d2, b0, b1);
+          s += a0 * b0 + a1 * b1;
+        }
+        acc[u] += s;
+      }
+      if (tid < VD) gacc += sG[tid] - sWv[tid] * bb * ih;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 18; u++) {
+      const int e = tid + u * nt;
+      if (e >= VD * VD) break;
+      const int d1 = e / VD, d2 = e - d1 * VD;
+      A[(size_t)vmap(d1) * M + vmap(d2)] = acc[u];
+    }
+    if (tid < VD) bv[vmap(tid)] = gacc;
+    __syncthreads();
+    // ---- IMU factor 0 -> 1 (estimator.cpp:841-850)
+    {
+      double* sJ = sm;            // [450] raw
+      double* sJ2 = sJ + 450;     // [450] whitened
+      double* sR = sJ2 + 450;     // [15] raw, [15] whitened
+      const double* rec = bt.imu + (size_t)(w * K + 1) * IMU_REC;
+      const bool use = rec[IR_DT] < 10.0;
+      for (int i = tid; i < 450; i += nt) sJ[i] = 0.0;
+      __syncthreads();
+      if (use) {
+        if (tid == 0) imu_raw(rec, bt.G, bt.pose0, bt.sb0, bt.pose0 + 7, bt.sb0 + 9, sR, sJ);
+        __syncthreads();
+        const double* SI = rec + IR_SQ;
+        for (int e = tid; e < 465; e += nt) {
+          int i = e / 31, c = e - i * 31;
+          double s = 0;
+          if (c < 30) { for (int k = i; k < 15; k++) s += SI[i * 15 + k] * sJ[k * 30 + c]; sJ2[i * 30 + c] = s; }
+          else { for (int k = i; k < 15; k++) s += SI[i * 15 + k] * sR[k]; sR[15 + i] = s; }
+        }
+        __syncthreads();
+        for (int e = tid; e < 930; e += nt) {
+          double s = 0;
+          if (e < 900) {
+            int a = e / 30, c = e - a * 30;
+            for (int k = 0; k < 15; k++) s += sJ2[k * 30 + a] * sJ2[k * 30 + c];
+            A[(size_t)a * M + c] += s;
+          } else {
+            int a = e - 900;
+            for (int k = 0; k < 15; k++) s += sJ2[k * 30 + a] * sR[15 + k];
+            bv[a] += s;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- prior (estimator.cpp:822-839 / 932-948)
+  {
+    const int np_ = bt.pr_n[w];
+    if (np_ > 0) {
+      double* sdx = sm;
+      double* spr = sdx + bt.nmax;
+      int* pmap = reinterpret_cast<int*>(spr + bt.nmax);   // prior column -> M layout (incl. extrinsics)
+      const int nb = bt.pr_nb[w];
+      for (int i = tid; i < np_; i += nt) pmap[i] = -1;
+      __syncthreads();
+      for (int bidx = tid; bidx < nb; bidx += nt) {
+        int kind = bt.pr_kind[w * PRIOR_MAXB + bidx], fr = bt.pr_frame[w * PRIOR_MAXB + bidx], idx = bt.pr_idx[w * PRIOR_MAXB + bidx];
+        int loc = kind == 1 ? 9 : (kind == 3 ? 1 : 6);
+        int base = kind == 0 ? 15 * fr : (kind == 1 ? 15 * fr + 6 : (kind == 2 ? 15 * K : -1));
+        for (int i = 0; i < loc; i++) pmap[idx + i] = base < 0 ? -1 : base + i;
+      }
+      __syncthreads();
+      prior_residual(bt, w, bt.pose0, bt.sb0, sdx, spr);
+      const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
+      for (int e = tid; e < np_ * np_; e += nt) {
+        int a = e / np_, c = e - a * np_;
+        if (pmap[a] < 0 || pmap[c] < 0) continue;
+        double s = 0;
+        for (int k = 0; k < np_; k++) s += Jc[(size_t)a * np_ + k] * Jc[(size_t)c * np_ + k];
+        A[(size_t)pmap[a] * M + pmap[c]] += s;
+      }
+      for (int a = tid; a < np_; a += nt) {
+        if (pmap[a] < 0) continue;
+        double s = 0;
+        for (int k = 0; k < np_; k++) s += Jc[(size_t)a * np_ + k] * spr[k];
+        bv[pmap[a]] += s;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- eliminate the m dropped dimensions: Amm pseudo-inverse by Jacobi eigen-decomposition (warp 0)
+  const int m = ma.m, n = ma.n, ne = ma.ne;
+  double* Am = sm;                    // [16*16]
+  double* Vm = Am + 256;              // [16*16]
+  double* Ai = Vm + 256;              // [16*16] pseudo-inverse
+  double* Tm = Ai + 256;              // [n*16]
+  for (int e = tid; e < 256; e += nt) {
+    int i = e >> 4, j = e & 15;
+    Am[e] = (i < m && j < m) ? 0.5 * (A[(size_t)ma.dropidx[i] * M + ma.dropidx[j]] + A[(size_t)ma.dropidx[j] * M + ma.dropidx[i]]) : 0.0;
+    Vm[e] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int k = tid;
+    for (int sweep = 0; sweep < 60; sweep++) {
+      double off = 0;
+      for (int i = 0; i < m; i++) for (int j = i + 1; j < m; j++) off += Am[i * 16 + j] * Am[i * 16 + j];
+      if (off == 0.0) break;
+      double dg = 0;
+      for (int i = 0; i < m; i++) dg += Am[i * 16 + i] * Am[i * 16 + i];
+      if (off <= 1e-40 * (dg + 1e-300)) break;
+      for (int p = 0; p < m - 1; p++)
+        for (int q = p + 1; q < m; q++) {
+          const double apq = Am[p * 16 + q];
+          if (apq == 0.0) continue;
+          const double app = Am[p * 16 + p], aqq = Am[q * 16 + q];
+          const double theta = (aqq - app) / (2.0 * apq);
+          const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+          __syncwarp();
+          if (k < m) {
+            double akp = Am[k * 16 + p], akq = Am[k * 16 + q];
+            Am[k * 16 + p] = c * akp - s * akq; Am[k * 16 + q] = s * akp + c * akq;
+          }
+          __syncwarp();
+          if (k < m) {
+            double apk = Am[p * 16 + k], aqk = Am[q * 16 + k];
+            Am[p * 16 + k] = c * apk - s * aqk; Am[q * 16 + k] = s * apk + c * aqk;
+            double vkp = Vm[k * 16 + p], vkq = Vm[k * 16 + q];
+            Vm[k * 16 + p] = c * vkp - s * vkq; Vm[k * 16 + q] = s * vkp + c * vkq;
+          }
+          __syncwarp();
+        }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 256; e += nt) {
+    int i = e >> 4, j = e & 15;
+    double s = 0;
+    if (i < m && j < m)
+      for (int k = 0; k < m; k++) { double lam = Am[k * 16 + k]; if (lam > 1e-8) s += Vm[i * 16 + k] * Vm[j * 16 + k] / lam; }
+    Ai[e] = s;
+  }
+  __syncthreads();
+  for (int e = tid; e < n * 16; e += nt) {
+    int i = e >> 4, j = e & 15;
+    double s = 0;
+    if (j < m) for (int k = 0; k < m; k++) s += A[(size_t)ma.keepidx[i] * M + ma.dropidx[k]] * Ai[k * 16 + j];
+    Tm[e] = s;
+  }
+  __syncthreads();
+  // ---- kept system Ar = Arr - Arm Amm^+ Amr (symmetrised), br; eigen-decomposition by parallel Jacobi
+  double* Ar = Tm + (size_t)n * 16;           // [ne*ne]
+  double* Vr = Ar + (size_t)ne * ne;          // [ne*ne]
+  double* br = Vr + (size_t)ne * ne;          // [ne]
+  double* cs = br + ne;                       // [ne] (c,s) per pair
+  int* pp = reinterpret_cast<int*>(cs + ne);  // [ne] pairs
+  double* red = reinterpret_cast<double*>(pp + ne + (ne & 1));   // [32]
+  for (int e = tid; e < ne * ne; e += nt) {
+    int i = e / ne, j = e - i * ne;
+    double s = 0;
+    if (i < n && j < n) {
+      s = A[(size_t)ma.keepidx[i] * M + ma.keepidx[j]];
+      for (int k = 0; k < m; k++) s -= Tm[i * 16 + k] * A[(size_t)ma.dropidx[k] * M + ma.keepidx[j]];
+    }
+    Ar[e] = s;
+    Vr[e] = (i == j) ? 1.0 : 0.0;
+  }
+  for (int i = tid; i < ne; i += nt) {
+    double s = 0;
+    if (i < n) {
+      s = bv[ma.keepidx[i]];
+      for (int k = 0; k < m; k++) s -= Tm[i * 16 + k] * bv[ma.dropidx[k]];
+    }
+    br[i] = s;
+  }
+  __syncthreads();
+  for (int e = tid; e < ne * ne; e += nt) {       // symmetrise (two passes: read pairs, then write)
+    int i = e / ne, j = e - i * ne;
+    if (i > j) { double v = 0.5 * (Ar[i * ne + j] + Ar[j * ne + i]); Ar[i * ne + j] = v; Ar[j * ne + i] = v; }
+  }
+  __syncthreads();
+  int sweeps = 0;
+  const int half = ne / 2;
+  for (; sweeps < 40 && ne >= 2; sweeps++) {
+    double off = 0, dg = 0;
+    for (int e = tid; e < ne * ne; e += nt) {
+      int i = e / ne, j = e - i * ne;
+      double v = Ar[e] * Ar[e];
+      if (i == j) dg += v; else off += v;
+    }
+    off = block_sum(off, red);
+    dg = block_sum(dg, red);
+    __syncthreads();
+    if (off <= 1e-36 * (dg + 1e-300)) break;
+    for (int step = 0; step < ne - 1; step++) {
+      // round-robin pairing: ne-1 is fixed, the others rotate
+      if (tid < half) {
+        int p, q;
+        if (tid == 0) { p = ne - 1; q = step; }
+        else { p = (step + tid) % (ne - 1); q = (step - tid + (ne - 1)) % (ne - 1); }
+        if (p > q) { int t2 = p; p = q; q = t2; }
+        const double apq = Ar[p * ne + q];
+        double c = 1.0, s = 0.0;
+        if (apq != 0.0) {
+          const double app = Ar[p * ne + p], aqq = Ar[q * ne + q];
+          const double theta = (aqq - app) / (2.0 * apq);
+          const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = 1.0 / sqrt(tt * tt + 1.0); s = tt * c;
+        }
+        pp[2 * tid] = p; pp[2 * tid + 1] = q; cs[2 * tid] = c; cs[2 * tid + 1] = s;
+      }
+      __syncthreads();
+      for (int e = tid; e < half * ne; e += nt) {      // columns of A and V
+        int pr = e / ne, k = e - pr * ne;
+        int p = pp[2 * pr], q = pp[2 * pr + 1];
+        double c = cs[2 * pr], s = cs[2 * pr + 1];
+        double akp = Ar[k * ne + p], akq = Ar[k * ne + q];
+        Ar[k * ne + p] = c * akp - s * akq; Ar[k * ne + q] = s * akp + c * akq;
+        double vkp = Vr[k * ne + p], vkq = Vr[k * ne + q];
+        Vr[k * ne + p] = c * vkp - s * vkq; Vr[k * ne + q] = s * vkp + c * vkq;
+      }
+      __syncthreads();
+      for (int e = tid; e < half * ne; e += nt) {      // rows of A
+        int pr = e / ne, k = e - pr * ne;
+        int p = pp[2 * pr], q = pp[2 * pr + 1];
+        double c = cs[2 * pr], s = cs[2 * pr + 1];
+        double apk = Ar[p * ne + k], aqk = Ar[q * ne + k];
+        Ar[p * ne + k] = c * apk - s * aqk; Ar[q * ne + k] = s * apk + c * aqk;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- linearized_jacobians = sqrt(S) V^T, linearized_residuals = sqrt(S^-1) V^T b  (:283-291)
+  for (int e = tid; e < n * n; e += nt) {
+    int i = e / n, k = e - i * n;       // column-major J(k, i) at [i*n + k]
+    double lam = Ar[k * ne + k];
+    ma.out_jac[e] = (lam > 1e-8 ? sqrt(lam) : 0.0) * Vr[i * ne + k];
+  }
+  for (int k = tid; k < n; k += nt) {
+    double lam = Ar[k * ne + k], s = 0;
+    for (int i = 0; i < n; i++) s += Vr[i * ne + k] * br[i];
+    ma.out_res[k] = (lam > 1e-8 ? sqrt(1.0 / lam) : 0.0) * s;
+  }
+  if (tid == 0) ma.status[0] = sweeps;
+}
+
+size_t ba_marginalize_smem_bytes(int K, int nmax, int n) {
+  int ne = (n + 1) & ~1, VD = 6 * K + 6;
+  size_t a = (size_t)(K + 1) * FR + (BVIO_KMAX - 1) * MF + 2 * VD + 2 + BVIO_KMAX;       // visual phase
+  size_t b = 930 + 32;                                                                    // IMU phase
+  size_t c = 2 * (size_t)nmax + nmax / 2 + 2;                                             // prior phase
+  size_t d = 768 + (size_t)n * 16 + 2 * (size_t)ne * ne + 2 * ne + ne / 2 + 2 + 32 + 8;   // elimination + Jacobi
+  size_t mx = a > b ? a : b;
+  if (c > mx) mx = c;
+  if (d > mx) mx = d;
+  return mx * sizeof(double);
+}
+
+int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, const int* dropidx, const int* keepidx, double* A,
+                          double* b, double* out_jac, double* out_res, int* status, cudaStream_t st) {
+  MargArgs ma;
+  ma.flag = flag; ma.M = 15 * bt.K + 6; ma.m = m; ma.n = n; ma.ne = (n + 1) & ~1;
+  ma.dropidx = dropidx; ma.keepidx = keepidx; ma.A = A; ma.b = b; ma.out_jac = out_jac; ma.out_res = out_res; ma.status = status;
+  size_t smem = ba_marginalize_smem_bytes(bt.K, bt.nmax, n);
+  cudaFuncSetAttribute(ba_marginalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  ba_marginalize_kernel<<<1, MARG_THREADS, smem, st>>>(bt, ma);
+  return 1;
+}
+
 }  // namespace bvio
