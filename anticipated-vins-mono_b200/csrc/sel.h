@@ -33,6 +33,7 @@ struct SelProb {
   int c0, c1;                         // candidates scored by this rank: [c0, c1)
   int rank, world;
   int grid_round;                     // CTAs of the round kernel
+  int grid_persist, cpw;              // persistent single-kernel path: CTAs, candidates per warp (0 = not used)
   double delta_imu, acc_var, acc_bias_var;
   double q_ic[4], t_ic[3];
   bvio_camera cam;
@@ -61,6 +62,8 @@ int sel_configure(void);
 int sel_launch_reset(const SelProb& sp, cudaStream_t st);
 int sel_launch_build(const SelProb& sp, cudaStream_t st);      // build_delta + omega/Schur
 int sel_launch_round(const SelProb& sp, cudaStream_t st);      // score + local winner (+ apply when world == 1)
+int sel_plan_persist(SelProb& sp, int sm_count);             // 1 when the persistent path fits
+int sel_launch_persist(const SelProb& sp, cudaStream_t st);   // all kappa rounds in one kernel (single GPU)
 int sel_launch_apply(const SelProb& sp, cudaStream_t st);      // multi-GPU: pick among gathered records
 int sel_launch_final(const SelProb& sp, cudaStream_t st);
 int sel_launch_expand(const SelProb& sp, double* Cfull, cudaStream_t st);   // debug: packed -> dense [N][T*T]

@@ -100,12 +100,14 @@ static int sel_upload_impl(bvio_ctx* ctx, const bvio_select_in* in, bool use_cac
   sp.c1 = std::min(N, (sp.rank + 1) * per);
   const int nloc = sp.c1 - sp.c0;
   sp.grid_round = std::max(1, std::min((nloc + SEL_WARPS - 1) / SEL_WARPS, 4 * ctx->sm_count));
+  sel_plan_persist(sp, ctx->sm_count);
   sp.delta_imu = in->delta_imu; sp.acc_var = in->acc_var; sp.acc_bias_var = in->acc_bias_var;
   for (int i = 0; i < 4; i++) sp.q_ic[i] = in->q_ic[i];
   for (int i = 0; i < 3; i++) sp.t_ic[i] = in->t_ic[i];
   sp.cam = in->cam;
   pr->sharded = sharded;
-  pr->use_graph = !sharded;   // NCCL calls stay outside graph capture
+  // NCCL calls and the cooperative persistent kernel stay outside graph capture (5 launches anyway)
+  pr->use_graph = !sharded && sp.grid_persist == 0;
   pr->cand_id.assign(in->cand_id, in->cand_id + N);
 
   Carver cv;
@@ -125,7 +127,7 @@ static int sel_upload_impl(bvio_ctx* ctx, const bvio_select_in* in, bool use_cac
   size_t o_valid = cv.take((size_t)N * I), o_valid_u = cv.take((size_t)U * I), o_taken = cv.take((size_t)N * I);
   size_t o_depth = cv.take((size_t)(N + U) * Dd);
   size_t o_pair = cv.take((size_t)H * 324 * Dd), o_omega = cv.take((size_t)D * D * Dd), o_R = cv.take((size_t)TT * Dd);
-  size_t o_blk = cv.take((size_t)sp.grid_round * 4 * Dd);
+  size_t o_blk = cv.take((size_t)std::max(sp.grid_round, 2 * sp.grid_persist) * 4 * Dd);
   size_t o_send = cv.take((size_t)(SEL_REC_HDR + TT) * Dd), o_all = cv.take((size_t)sp.world * (SEL_REC_HDR + TT) * Dd);
   size_t o_counts = cv.take(2 * sizeof(unsigned long long));
   const size_t d_bytes = cv.off;
@@ -173,7 +175,8 @@ static int sel_enqueue(bvio_ctx* ctx, bvio_selprob* pr, cudaStream_t st, int* nc
   n += sel_launch_reset(sp, st);
   n += sel_launch_build(sp, st);
   const size_t RS = SEL_REC_HDR + sp.TT;
-  for (int it = 0; it < sp.kappa; it++) {
+  if (sp.grid_persist > 0) n += sel_launch_persist(sp, st);
+  for (int it = 0; it < sp.kappa && sp.grid_persist == 0; it++) {
     n += sel_launch_round(sp, st);
     if (sp.world > 1) {
       int r = g_nccl.AllGather(sp.rec_send, sp.rec_all, RS, kNcclFloat64, ctx->comm, st);

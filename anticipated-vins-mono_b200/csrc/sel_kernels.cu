@@ -308,16 +308,17 @@ __global__ void __launch_bounds__(256) sel_omega_kernel(SelProb sp) {
 // shuffles, so the whole factorization runs without shared-memory round trips.  T is a compile-time
 // constant so that every register index is static.
 // =============================================================================================
-template <int T>
-__device__ __forceinline__ double warp_chol_logdet(const double* A, int lane) {
+template <int T, bool ADD = false>
+__device__ __forceinline__ double warp_chol_logdet(const double* A, int lane, const double* C = nullptr, double p = 0.0) {
   constexpr int R = (T + 31) / 32;
   double a[R][T];
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int i = lane + 32 * r;
     const double* row = A + tri(i < T ? i : 0, 0);
+    const double* crow = ADD ? C + tri(i < T ? i : 0, 0) : nullptr;
 #pragma unroll
-    for (int k = 0; k < T; k++) a[r][k] = (i < T && k <= i) ? row[k] : 0.0;
+    for (int k = 0; k < T; k++) a[r][k] = (i < T && k <= i) ? (ADD ? fma(p, crow[k], row[k]) : row[k]) : 0.0;
   }
   double mypiv[R];
 #pragma unroll
@@ -464,6 +465,127 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) sel_round_kernel(SelProb sp) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-GPU fast path: ALL kappa greedy rounds in one cooperative kernel.  Each warp keeps its
+// candidates' packed C_ell in shared memory for the whole selection, every CTA keeps its own copy of R;
+// per round: score -> per-CTA record -> ONE grid-wide sync -> every CTA merges the records (same total
+// order => same winner everywhere) and applies R += p C_best to its copy.  Records are double-buffered
+// by round parity, so one barrier per round is enough.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int H>
+__global__ void __launch_bounds__(32 * SEL_WARPS, 2) sel_persist_kernel(SelProb sp) {
+  extern __shared__ double sm[];
+  constexpr int T = 3 * H, TT = T * (T + 1) / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cpw = sp.cpw;
+  double* sR = sm;                                         // [TT]
+  double* sC = sR + TT + (size_t)warp * cpw * TT;          // [cpw][TT] this warp's candidates
+  double* sred = sm + (size_t)(1 + SEL_WARPS * cpw) * TT;  // [SEL_WARPS*4] + [4]
+  const int gw = blockIdx.x * SEL_WARPS + warp, nw = gridDim.x * SEL_WARPS;
+  // candidates of this warp: index, prob, alive (valid and not yet taken), one per slot k
+  for (int k = 0; k < cpw; k++) {
+    const int i = sp.c0 + gw + k * nw;
+    if (i < sp.c1 && sp.valid[i])
+      for (int e = lane; e < TT; e += 32) sC[(size_t)k * TT + e] = sp.Cc[(size_t)i * TT + e];
+  }
+  for (int e = threadIdx.x; e < TT; e += blockDim.x) sR[e] = sp.R[e];
+  unsigned long long alive = 0;                            // bit k: slot k still a candidate (cpw <= 64)
+  for (int k = 0; k < cpw; k++) {
+    const int i = sp.c0 + gw + k * nw;
+    if (i < sp.c1 && sp.valid[i]) alive |= 1ull << k;
+  }
+  __syncthreads();
+  const double ld_oo = sp.ctrl->logdet_oo;
+  int n_selected = 0;
+  double min_margin = INFINITY;
+  unsigned long long scored = 0;
+  for (int round = 0; round < sp.kappa; round++) {
+    double best = -1.0, second = -INFINITY, cnt = 0;
+    int bidx = -1;
+    for (int k = 0; k < cpw; k++) {
+      if (!((alive >> k) & 1ull)) continue;
+      const int i = sp.c0 + gw + k * nw;
+      const double ld = warp_chol_logdet<T, true>(sR, lane, sC + (size_t)k * TT, sp.cand_prob[i]);
+      const double val = ld_oo + 2.0 * ld;
+      cnt += 1;
+      if (val > best) { second = best; best = val; bidx = i; }
+      else if (val > second) second = val;
+    }
+    if (lane == 0) { sred[warp * 4] = best; sred[warp * 4 + 1] = second; sred[warp * 4 + 2] = (double)bidx; sred[warp * 4 + 3] = cnt; }
+    __syncthreads();
+    double* rec = sp.blk_best + (size_t)(round & 1) * gridDim.x * 4;
+    if (threadIdx.x == 0) {
+      double b = -1.0, s = -INFINITY, c = 0;
+      int ix = -1;
+      for (int q = 0; q < SEL_WARPS; q++) { merge_best(b, s, ix, sred[q * 4], sred[q * 4 + 1], (int)sred[q * 4 + 2]); c += sred[q * 4 + 3]; }
+      double* bb = rec + (size_t)blockIdx.x * 4;
+      __stcg(bb, b); __stcg(bb + 1, s); __stcg(bb + 2, (double)ix); __stcg(bb + 3, c);
+    }
+    grid_barrier(&sp.ctrl->ticket, (unsigned)(round + 1) * gridDim.x);
+    // merge all CTA records (identical on every CTA)
+    {
+      double b = -1.0, s = -INFINITY, c = 0;
+      int ix = -1;
+      for (unsigned q = threadIdx.x; q < gridDim.x; q += blockDim.x) {
+        const double2 r0 = __ldcg(reinterpret_cast<const double2*>(rec) + 2 * q);
+        const double2 r1 = __ldcg(reinterpret_cast<const double2*>(rec) + 2 * q + 1);
+        merge_best(b, s, ix, r0.x, r0.y, (int)r1.x);
+        c += r1.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, b, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        merge_best(b, s, ix, ob, os, oi);
+      }
+      if (lane == 0) { sred[warp * 4] = b; sred[warp * 4 + 1] = s; sred[warp * 4 + 2] = (double)ix; sred[warp * 4 + 3] = c; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        b = -1.0; s = -INFINITY; c = 0; ix = -1;
+        for (int q = 0; q < SEL_WARPS; q++) { merge_best(b, s, ix, sred[q * 4], sred[q * 4 + 1], (int)sred[q * 4 + 2]); c += sred[q * 4 + 3]; }
+        double* bc = sred + SEL_WARPS * 4;
+        bc[0] = b; bc[1] = s; bc[2] = (double)ix; bc[3] = c;
+      }
+      __syncthreads();
+    }
+    const double* bc = sred + SEL_WARPS * 4;
+    const double wb = bc[0], ws = bc[1];
+    const int wix = (int)bc[2];
+    scored += (unsigned long long)bc[3];
+    if (wix >= 0) {
+      // Omega_S += p Delta (feature_selector.cpp:674) on this CTA's copy of R
+      const double p = sp.cand_prob[wix];
+      const double* Cw = sp.Cc + (size_t)wix * TT;
+      for (int e = threadIdx.x; e < TT; e += blockDim.x) sR[e] += p * __ldg(Cw + e);
+      // the owner warp retires the candidate
+      const int rel = wix - sp.c0 - gw;
+      if (rel >= 0 && rel % nw == 0 && rel / nw < cpw) alive &= ~(1ull << (rel / nw));
+      if (blockIdx.x == 0 && threadIdx.x == 0) { sp.taken[wix] = 1; sp.out_idx[n_selected] = wix; sp.out_val[n_selected] = wb; }
+      n_selected++;
+      if (ws > -1.0) min_margin = fmin(min_margin, wb - ws);
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {
+    for (int e = threadIdx.x; e < TT; e += blockDim.x) sp.R[e] = sR[e];
+    if (threadIdx.x == 0) {
+      SelCtrl* c = sp.ctrl;
+      c->n_selected = n_selected; c->min_margin = min_margin; c->scored = scored; c->round = sp.kappa;
+    }
+  }
+}
+
 // multi-GPU: every rank holds the same gathered records and applies the same update
 __global__ void __launch_bounds__(256) sel_apply_kernel(SelProb sp) {
   __shared__ double bc[4];
@@ -533,6 +655,10 @@ int sel_configure(void) {
   if ((e = cudaFuncSetAttribute(sel_round_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
   BVIO_SEL_FOR_EACH_H(BVIO_SEL_ATTR)
 #undef BVIO_SEL_ATTR
+#define BVIO_SEL_ATTR(HH) \
+  if ((e = cudaFuncSetAttribute(sel_persist_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+  BVIO_SEL_FOR_EACH_H(BVIO_SEL_ATTR)
+#undef BVIO_SEL_ATTR
   g_sel_configured = true;
   return 0;
 }
@@ -551,6 +677,46 @@ int sel_launch_build(const SelProb& sp, cudaStream_t st) {
 int sel_launch_round(const SelProb& sp, cudaStream_t st) {
   switch (sp.H) {
 #define BVIO_SEL_CASE(HH) case HH: sel_round_kernel<HH><<<sp.grid_round, 32 * SEL_WARPS, round_smem(sp.TT), st>>>(sp); break;
+    BVIO_SEL_FOR_EACH_H(BVIO_SEL_CASE)
+#undef BVIO_SEL_CASE
+    default: break;
+  }
+  return 1;
+}
+static size_t persist_smem(int TT, int cpw) { return sizeof(double) * ((size_t)(1 + SEL_WARPS * cpw) * TT + SEL_WARPS * 4 + 4); }
+
+// Picks the grid of the persistent kernel: every CTA must be co-resident (the kernel spins on a grid
+// barrier).  Returns 0 when the problem does not fit (the caller then runs one kernel per round).
+int sel_plan_persist(SelProb& sp, int sm_count) {
+  const int nloc = sp.c1 - sp.c0;
+  sp.grid_persist = 0; sp.cpw = 0;
+  if (sp.world != 1 || nloc <= 0 || sp.kappa <= 0) return 0;
+  int per_sm = 0;
+  cudaError_t e = cudaSuccess;
+  int want = (nloc + SEL_WARPS - 1) / SEL_WARPS;
+  for (int cpw = 1; cpw <= 8; cpw++) {
+    size_t smem = persist_smem(sp.TT, cpw);
+    if (smem > 100 * 1024) break;
+    switch (sp.H) {
+#define BVIO_SEL_CASE(HH) case HH: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sel_persist_kernel<HH>, 32 * SEL_WARPS, smem); break;
+      BVIO_SEL_FOR_EACH_H(BVIO_SEL_CASE)
+#undef BVIO_SEL_CASE
+      default: return 0;
+    }
+    if (e != cudaSuccess || per_sm < 1) return 0;
+    int cap = per_sm * sm_count;
+    int need = (want + cpw - 1) / cpw;
+    if (need <= cap) { sp.grid_persist = need; sp.cpw = cpw; return 1; }
+  }
+  return 0;
+}
+int sel_launch_persist(const SelProb& sp, cudaStream_t st) {
+  size_t smem = persist_smem(sp.TT, sp.cpw);
+  switch (sp.H) {
+  // cooperative launch: the driver guarantees (or refuses) co-residency of all CTAs, which the grid
+  // barrier inside the kernel relies on
+#define BVIO_SEL_CASE(HH) case HH: { SelProb arg = sp; void* args[] = {&arg}; \
+    cudaLaunchCooperativeKernel((const void*)sel_persist_kernel<HH>, dim3(sp.grid_persist), dim3(32 * SEL_WARPS), args, smem, st); } break;
     BVIO_SEL_FOR_EACH_H(BVIO_SEL_CASE)
 #undef BVIO_SEL_CASE
     default: break;
