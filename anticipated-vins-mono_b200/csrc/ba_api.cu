@@ -5,8 +5,11 @@
 #include "ba.h"
 #include "ctx.h"
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <new>
+#include <thread>
 
 using namespace bvio;
 
@@ -232,10 +235,20 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   double* h_pr_jac = (double*)(h + o_pr_jac);
   double* h_pr_res = (double*)(h + o_pr_res);
   bb->lm_base.resize(B + 1);
-  int lb = 0, ob = 0;
-  for (int b = 0; b < B; b++) {
+  std::vector<int> obs_base(B + 1);
+  {
+    int lb0 = 0, ob0 = 0;
+    for (int b = 0; b < B; b++) {
+      bb->lm_base[b] = lb0; obs_base[b] = ob0;
+      lb0 += ws[b].L; ob0 += ws[b].L ? ws[b].lm_obs_offset[ws[b].L] : 0;
+    }
+    bb->lm_base[B] = lb0; obs_base[B] = ob0;
+  }
+  // windows are packed independently: spread large batches over a few host threads
+  auto pack = [&](int b) {
     const bvio_window& w = ws[b];
-    h_lm_base[b] = lb; bb->lm_base[b] = lb;
+    const int lb = bb->lm_base[b], ob = obs_base[b];
+    h_lm_base[b] = lb;
     int nobs = w.L ? w.lm_obs_offset[w.L] : 0;
     for (int l = 0; l < w.L; l++) h_lm_off[lb + l] = ob + w.lm_obs_offset[l];
     if (nobs) {
@@ -264,10 +277,21 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
       memcpy(h_pr_jac + (size_t)b * nmax * nmax, p->lin_jac, (size_t)p->n * p->n * D);
       memcpy(h_pr_res + (size_t)b * nmax, p->lin_res, (size_t)p->n * D);
     }
-    lb += w.L; ob += nobs;
+  };
+  {
+    int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 8);
+    if (B < 16) nthreads = 1;
+    if (nthreads <= 1) {
+      for (int b = 0; b < B; b++) pack(b);
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthreads; t++)
+        th.emplace_back([&, t]() { for (int b = t; b < B; b += nthreads) pack(b); });
+      for (auto& x : th) x.join();
+    }
   }
-  h_lm_base[B] = lb; bb->lm_base[B] = lb;
-  h_lm_off[total_L] = ob;
+  h_lm_base[B] = bb->lm_base[B];
+  h_lm_off[total_L] = obs_base[B];
 
   bt.lm_base = (const int*)(d + o_lm_base); bt.lm_off = (const int*)(d + o_lm_off);
   bt.obs_frame = (const int*)(d + o_obs_frame); bt.obs_xy = (const double2*)(d + o_obs_xy);
@@ -538,6 +562,7 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts,
   if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_jac, scratch + o_jac, sizeof(double) * n * n, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_res, scratch + o_res, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && getenv("BVIO_DEBUG")) { int stv[4] = {0, 0, 0, 0}; cudaMemcpy(stv, scratch + o_st, sizeof stv, cudaMemcpyDeviceToHost); fprintf(stderr, "[bvio] marginalize: m=%d n=%d jacobi sweeps=%d\n", m, n, stv[0]); }
   if (scratch) cudaFree(scratch);
   bvio_batch_free(ctx, bb);
   if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("marginalize: ") + cudaGetErrorString(e));

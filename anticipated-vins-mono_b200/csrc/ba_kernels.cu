@@ -1218,6 +1218,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
     double* sG = sWv + VD;
     double* sS = sG + VD;                   // [2] h, b
     int* sFj = reinterpret_cast<int*>(sS + 2);   // [KMAX]
+    int* sFof = sFj + BVIO_KMAX;                 // [KMAX+1] frame -> factor index of this landmark
     stage_frames(bt, w, bt.pose0, sFr, sEx);
     constexpr int NE = 12;                  // owned entries per thread: VD*VD <= 96*96 = 9216 <= 512*18
     double acc[18];
@@ -1231,8 +1232,11 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0, nfac = n - 1;
       if (bt.obs_frame[o0] != 0) continue;
       __syncthreads();
+      if (tid <= K) sFof[tid] = -1;
+      __syncthreads();
       if (tid < nfac) {
         const int fj = bt.obs_frame[o0 + 1 + tid];
+        sFof[fj] = tid;
         const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + tid];
         const double lam = bt.invd0[l];
         const double* Fi = sFr;
@@ -1313,7 +1317,16 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         if (e >= VD * VD) break;
         const int d1 = e / VD, d2 = e - d1 * VD;
         double s = -sWv[d1] * sWv[d2] * ih;
-        for (int f = 0; f < nfac; f++) {
+        // a frame-block dimension is touched by exactly one factor; pose-0 / extrinsic dimensions by all
+        const int k1 = d1 / 6, k2 = d2 / 6;
+        int f_lo = 0, f_hi = nfac;
+        if (k1 != 0 && k1 != K) { const int f = sFof[k1]; if (f < 0) f_hi = 0; else { f_lo = f; f_hi = f + 1; } }
+        if (k2 != 0 && k2 != K && f_hi > f_lo) {
+          const int f = sFof[k2];
+          if (f < 0 || (f_hi - f_lo == 1 && k1 != 0 && k1 != K && f != f_lo)) f_hi = f_lo;
+          else { f_lo = f; f_hi = f + 1; }
+        }
+        for (int f = f_lo; f < f_hi; f++) {
           double a0, a1, b0, b1;
           const double* st = sF + f * MF;
           marg_col(st, sFj[f], K, d1, a0, a1);
@@ -1425,7 +1438,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       if (off == 0.0) break;
       double dg = 0;
       for (int i = 0; i < m; i++) dg += Am[i * 16 + i] * Am[i * 16 + i];
-      if (off <= 1e-40 * (dg + 1e-300)) break;
+      if (off <= 1e-30 * (dg + 1e-300)) break;
       for (int p = 0; p < m - 1; p++)
         for (int q = p + 1; q < m; q++) {
           const double apq = Am[p * 16 + q];
@@ -1467,9 +1480,10 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
   }
   __syncthreads();
   // ---- kept system Ar = Arr - Arm Amm^+ Amr (symmetrised), br; eigen-decomposition by parallel Jacobi
-  double* Ar = Tm + (size_t)n * 16;           // [ne*ne]
-  double* Vr = Ar + (size_t)ne * ne;          // [ne*ne]
-  double* br = Vr + (size_t)ne * ne;          // [ne]
+  const int ld = ne | 1;                      // odd row stride: column sweeps hit distinct banks
+  double* Ar = Tm + (size_t)n * 16;           // [ne*ld]
+  double* Vr = Ar + (size_t)ne * ld;          // [ne*ld]
+  double* br = Vr + (size_t)ne * ld;          // [ne]
   double* cs = br + ne;                       // [ne] (c,s) per pair
   int* pp = reinterpret_cast<int*>(cs + ne);  // [ne] pairs
   double* red = reinterpret_cast<double*>(pp + ne + (ne & 1));   // [32]
@@ -1480,8 +1494,8 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       s = A[(size_t)ma.keepidx[i] * M + ma.keepidx[j]];
       for (int k = 0; k < m; k++) s -= Tm[i * 16 + k] * A[(size_t)ma.dropidx[k] * M + ma.keepidx[j]];
     }
-    Ar[e] = s;
-    Vr[e] = (i == j) ? 1.0 : 0.0;
+    Ar[i * ld + j] = s;
+    Vr[i * ld + j] = (i == j) ? 1.0 : 0.0;
   }
   for (int i = tid; i < ne; i += nt) {
     double s = 0;
@@ -1494,7 +1508,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
   __syncthreads();
   for (int e = tid; e < ne * ne; e += nt) {       // symmetrise (two passes: read pairs, then write)
     int i = e / ne, j = e - i * ne;
-    if (i > j) { double v = 0.5 * (Ar[i * ne + j] + Ar[j * ne + i]); Ar[i * ne + j] = v; Ar[j * ne + i] = v; }
+    if (i > j) { double v = 0.5 * (Ar[i * ld + j] + Ar[j * ld + i]); Ar[i * ld + j] = v; Ar[j * ld + i] = v; }
   }
   __syncthreads();
   int sweeps = 0;
@@ -1503,13 +1517,13 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
     double off = 0, dg = 0;
     for (int e = tid; e < ne * ne; e += nt) {
       int i = e / ne, j = e - i * ne;
-      double v = Ar[e] * Ar[e];
+      double v = Ar[i * ld + j] * Ar[i * ld + j];
       if (i == j) dg += v; else off += v;
     }
     off = block_sum(off, red);
     dg = block_sum(dg, red);
     __syncthreads();
-    if (off <= 1e-36 * (dg + 1e-300)) break;
+    if (off <= 1e-30 * (dg + 1e-300)) break;   // off-diagonal Frobenius norm below 1e-15 ||A||: converged in double
     for (int step = 0; step < ne - 1; step++) {
       // round-robin pairing: ne-1 is fixed, the others rotate
       if (tid < half) {
@@ -1517,10 +1531,10 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         if (tid == 0) { p = ne - 1; q = step; }
         else { p = (step + tid) % (ne - 1); q = (step - tid + (ne - 1)) % (ne - 1); }
         if (p > q) { int t2 = p; p = q; q = t2; }
-        const double apq = Ar[p * ne + q];
+        const double apq = Ar[p * ld + q];
         double c = 1.0, s = 0.0;
         if (apq != 0.0) {
-          const double app = Ar[p * ne + p], aqq = Ar[q * ne + q];
+          const double app = Ar[p * ld + p], aqq = Ar[q * ld + q];
           const double theta = (aqq - app) / (2.0 * apq);
           const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
           c = 1.0 / sqrt(tt * tt + 1.0); s = tt * c;
@@ -1532,18 +1546,18 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         int pr = e / ne, k = e - pr * ne;
         int p = pp[2 * pr], q = pp[2 * pr + 1];
         double c = cs[2 * pr], s = cs[2 * pr + 1];
-        double akp = Ar[k * ne + p], akq = Ar[k * ne + q];
-        Ar[k * ne + p] = c * akp - s * akq; Ar[k * ne + q] = s * akp + c * akq;
-        double vkp = Vr[k * ne + p], vkq = Vr[k * ne + q];
-        Vr[k * ne + p] = c * vkp - s * vkq; Vr[k * ne + q] = s * vkp + c * vkq;
+        double akp = Ar[k * ld + p], akq = Ar[k * ld + q];
+        Ar[k * ld + p] = c * akp - s * akq; Ar[k * ld + q] = s * akp + c * akq;
+        double vkp = Vr[k * ld + p], vkq = Vr[k * ld + q];
+        Vr[k * ld + p] = c * vkp - s * vkq; Vr[k * ld + q] = s * vkp + c * vkq;
       }
       __syncthreads();
       for (int e = tid; e < half * ne; e += nt) {      // rows of A
         int pr = e / ne, k = e - pr * ne;
         int p = pp[2 * pr], q = pp[2 * pr + 1];
         double c = cs[2 * pr], s = cs[2 * pr + 1];
-        double apk = Ar[p * ne + k], aqk = Ar[q * ne + k];
-        Ar[p * ne + k] = c * apk - s * aqk; Ar[q * ne + k] = s * apk + c * aqk;
+        double apk = Ar[p * ld + k], aqk = Ar[q * ld + k];
+        Ar[p * ld + k] = c * apk - s * aqk; Ar[q * ld + k] = s * apk + c * aqk;
       }
       __syncthreads();
     }
@@ -1551,12 +1565,12 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
   // ---- linearized_jacobians = sqrt(S) V^T, linearized_residuals = sqrt(S^-1) V^T b  (:283-291)
   for (int e = tid; e < n * n; e += nt) {
     int i = e / n, k = e - i * n;       // column-major J(k, i) at [i*n + k]
-    double lam = Ar[k * ne + k];
-    ma.out_jac[e] = (lam > 1e-8 ? sqrt(lam) : 0.0) * Vr[i * ne + k];
+    double lam = Ar[k * ld + k];
+    ma.out_jac[e] = (lam > 1e-8 ? sqrt(lam) : 0.0) * Vr[i * ld + k];
   }
   for (int k = tid; k < n; k += nt) {
-    double lam = Ar[k * ne + k], s = 0;
-    for (int i = 0; i < n; i++) s += Vr[i * ne + k] * br[i];
+    double lam = Ar[k * ld + k], s = 0;
+    for (int i = 0; i < n; i++) s += Vr[i * ld + k] * br[i];
     ma.out_res[k] = (lam > 1e-8 ? sqrt(1.0 / lam) : 0.0) * s;
   }
   if (tid == 0) ma.status[0] = sweeps;
@@ -1564,10 +1578,10 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
 
 size_t ba_marginalize_smem_bytes(int K, int nmax, int n) {
   int ne = (n + 1) & ~1, VD = 6 * K + 6;
-  size_t a = (size_t)(K + 1) * FR + (BVIO_KMAX - 1) * MF + 2 * VD + 2 + BVIO_KMAX;       // visual phase
+  size_t a = (size_t)(K + 1) * FR + (BVIO_KMAX - 1) * MF + 2 * VD + 2 + 2 * BVIO_KMAX;   // visual phase
   size_t b = 930 + 32;                                                                    // IMU phase
   size_t c = 2 * (size_t)nmax + nmax / 2 + 2;                                             // prior phase
-  size_t d = 768 + (size_t)n * 16 + 2 * (size_t)ne * ne + 2 * ne + ne / 2 + 2 + 32 + 8;   // elimination + Jacobi
+  size_t d = 768 + (size_t)n * 16 + 2 * (size_t)ne * (ne + 1) + 2 * ne + ne / 2 + 2 + 32 + 8;   // elimination + Jacobi
   size_t mx = a > b ? a : b;
   if (c > mx) mx = c;
   if (d > mx) mx = d;

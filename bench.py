@@ -321,6 +321,42 @@ def run_ours(args, rank, world, local_rank):
     sel_h2d = sh.pos.nbytes + sh.quat.nbytes + sh.cxy.nbytes + sh.cp.nbytes + sh.clxy.nbytes + sh.cld.nbytes
     assert (ids2 == ids).all(), "one-shot and resident selector disagree"
 
+    # ---- frame-rate use (BASELINE configs[4] shape): one 11-kf/150-feature window per call through the
+    #      one-shot C-ABI (host buffers in, host buffers out), optimize + marginalize + select per frame
+    stream = None
+    if rank == 0 and args.stream_frames > 0:
+        import test_oracle_marg as tm
+        wpool = [synth.make_window(seed=300 + i, K=K_FRAMES, L=150) for i in range(4)]
+        spool = [abi.SelectHandle(synth.make_select_problem(seed=400 + i, N=300, H=SEL_H, kappa=150)) for i in range(4)]
+        od = abi.default_opts()            # the reference's budget: 8 iterations, Ceres default tolerances
+        lat = {"optimize": [], "marginalize": [], "select": [], "frame": []}
+        for f in range(args.stream_frames + 5):
+            wh = abi.WindowHandle(wpool[f % 4])
+            sh2 = spool[f % 4]
+            s1, ss2 = abi.Summary(), abi.SelectSummary()
+            ids3 = np.zeros(150, np.int32)
+            t0 = time.perf_counter()
+            ctx.check(L.bvio_optimize(ctx.h, C.byref(wh.s), C.byref(od), C.byref(s1)), "optimize")
+            t1 = time.perf_counter()
+            wpost = wpool[f % 4].copy()
+            wpost.para_pose, wpost.para_speed_bias, wpost.inv_depth = wh.pose, wh.sb, wh.inv
+            t1b = time.perf_counter()
+            assert tm.run_marg(abi, L.bvio_marginalize, wpost, 0, ctx=ctx.h) is not None
+            t2 = time.perf_counter()
+            ctx.check(L.bvio_select(ctx.h, C.byref(sh2.s), abi.iptr(ids3), None, C.byref(ss2)), "select")
+            t3 = time.perf_counter()
+            if f >= 5:
+                lat["optimize"].append(t1 - t0)
+                lat["marginalize"].append(t2 - t1b)
+                lat["select"].append(t3 - t2)
+                lat["frame"].append((t1 - t0) + (t2 - t1b) + (t3 - t2))
+        stream = {"frames": args.stream_frames, "workload": "11-kf/150-feature window, 8 LM iterations (Ceres default "
+                  "tolerances) + MARGIN_OLD + select(N=300, H=10, kappa=150) per frame, host buffers, wall clock incl. "
+                  "Python/ctypes packing of the prior output", "budget_ms_30hz": 33.3}
+        for k, v in lat.items():
+            a = np.array(v) * 1e3
+            stream[k + "_ms"] = {"p50": float(np.percentile(a, 50)), "p99": float(np.percentile(a, 99)), "max": float(a.max())}
+
     # ---- CPU baseline on the host cores (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -378,6 +414,7 @@ def run_ours(args, rank, world, local_rank):
                          "e2e": {"value": sel_e2e, "unit": "cand/s", "h2d_bytes_per_step": int(sel_h2d),
                                  "d2h_bytes_per_step": int(SEL_KAPPA * 12 + 64)},
                          "selected_head": ids[:8].tolist()},
+            "stream": stream,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -396,6 +433,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-solves", type=int, default=64)
     ap.add_argument("--cpu-kappa", type=int, default=16)
+    ap.add_argument("--stream-frames", type=int, default=200, help="frames of the per-frame latency leg (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
