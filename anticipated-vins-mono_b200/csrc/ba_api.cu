@@ -82,6 +82,7 @@ void bvio_destroy(bvio_ctx* ctx) {
   bvio_sel_ctx_destroy(ctx);
   ctx->ba_cache.release();
   ctx->sel_cache.release();
+  if (ctx->marg_scratch) cudaFree(ctx->marg_scratch);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -550,7 +551,14 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts,
   size_t o_A = cv.take(sizeof(double) * M * M), o_b = cv.take(sizeof(double) * M), o_jac = cv.take(sizeof(double) * n * n);
   size_t o_res = cv.take(sizeof(double) * n), o_drop = cv.take(sizeof(int) * (m + 1)), o_keep = cv.take(sizeof(int) * n);
   size_t o_st = cv.take(sizeof(int) * 4);
-  cudaError_t e = cudaMalloc((void**)&scratch, cv.off);
+  cudaError_t e = cudaSuccess;
+  if (ctx->marg_bytes < cv.off) {
+    if (ctx->marg_scratch) cudaFree(ctx->marg_scratch);
+    ctx->marg_scratch = nullptr; ctx->marg_bytes = 0;
+    e = cudaMalloc((void**)&ctx->marg_scratch, cv.off + cv.off / 4);
+    if (e == cudaSuccess) ctx->marg_bytes = cv.off + cv.off / 4;
+  }
+  scratch = ctx->marg_scratch;
   if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_drop, dropidx.data(), sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_keep, keepidx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
@@ -563,7 +571,6 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts,
   if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_res, scratch + o_res, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess && getenv("BVIO_DEBUG")) { int stv[4] = {0, 0, 0, 0}; cudaMemcpy(stv, scratch + o_st, sizeof stv, cudaMemcpyDeviceToHost); fprintf(stderr, "[bvio] marginalize: m=%d n=%d jacobi sweeps=%d\n", m, n, stv[0]); }
-  if (scratch) cudaFree(scratch);
   bvio_batch_free(ctx, bb);
   if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("marginalize: ") + cudaGetErrorString(e));
   for (int i = 0; i < n * n; i++) if (!(out->lin_jac[i] == out->lin_jac[i])) return fail(ctx, BVIO_ERR_NUMERIC, "non-finite prior");

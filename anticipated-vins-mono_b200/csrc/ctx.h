@@ -44,6 +44,8 @@ struct bvio_ctx {
   // pay cudaMalloc + cudaMallocHost every call
   bvio::Slab ba_cache, sel_cache;
   bool ba_cache_busy = false, sel_cache_busy = false;
+  char* marg_scratch = nullptr;   // grow-only device scratch of bvio_marginalize
+  size_t marg_bytes = 0;
   // multi-GPU selector
   ncclComm* comm = nullptr;
   int rank = 0, world = 1;
