@@ -27,6 +27,14 @@ KEYS = [
 ]
 
 
+def kname(full):
+    """'void ba_linearize_kernel<1>(BaBatch)' -> 'ba_linearize_kernel'"""
+    n = full.split("(")[0].strip()
+    if n.startswith("void "):
+        n = n[5:]
+    return n.split("<")[0].split("::")[-1]
+
+
 def launches_md(path, out):
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.defaultdict(list)
@@ -35,7 +43,7 @@ def launches_md(path, out):
             v = float(row["Metric Value"].replace(",", ""))
         except (ValueError, KeyError):
             continue
-        agg[row["Kernel Name"].split("(")[0]].append(v)
+        agg[kname(row["Kernel Name"])].append(v)
     tot = sum(sum(v) for v in agg.values())
     with open(out, "w") as f:
         f.write(f"# ncu launch list ({os.path.basename(path)}): gpu__time_duration.sum, --clock-control none\n\n")
@@ -73,7 +81,7 @@ def main():
                 idx = {h: i for i, h in enumerate(hdr)}
                 seen = collections.Counter()
                 for r in rows:
-                    name = r[idx["Kernel Name"]].split("(")[0]
+                    name = kname(r[idx["Kernel Name"]])
                     seen[name] += 1
                     if seen[name] > 1:
                         continue
