@@ -35,8 +35,13 @@ struct BaCtrl {                   // per-window LM state, lives in HBM
   int solve_ok;                   // a step was computed this pass (Cholesky succeeded)
   int invalid_run;
   int stepped;                    // this pass computed a step that the cost kernel must judge
-  unsigned int ticket;            // CTAs of the cost kernel that finished (last one decides)
+  unsigned int ticket;            // CTAs of the cost / dogleg kernel that finished (last one decides)
   int pad;
+  // BVIO_STRATEGY_DOGLEG (Ceres DoglegStrategy, TRADITIONAL_DOGLEG)
+  double mu;                      // Gauss-Newton regularisation (min_mu 1e-8, x10 on failure, /5 on success)
+  double dsum[6];                 // pose parts of the dogleg dot products (ba_solve -> ba_dogleg)
+  double ca, cb;                  // step = ca * (scaled gradient direction t) + cb * (Gauss-Newton step)
+  double step_norm;               // |step| in Ceres' diagonally scaled space (drives the radius update)
 };
 
 // per-(window,tile) output record of ba_linearize, in doubles:
@@ -46,6 +51,8 @@ struct BaCtrl {                   // per-window LM state, lives in HBM
 __host__ __device__ inline int tile_rec_doubles(int K) { return (K * (K + 1) / 2) * 36 + 18 * K + 4; }
 // per-(window,tile) output record of ba_cost: cost, model_lm, step2, x2
 constexpr int COST_REC = 4;
+// per-(window,tile) output record of ba_dogleg: |g_y|^2, t^T H t, |gn_y|^2, g^T n, n^T D n, t^T D n (landmark parts)
+constexpr int DOG_REC = 8;
 
 struct BaBatch {                  // all pointers are device pointers
   int B, K, np, T;                // windows, keyframes, reduced dimension, landmark tiles per window
@@ -54,6 +61,7 @@ struct BaBatch {                  // all pointers are device pointers
   int undamped;                   // debug: linearize without LM damping (bvio_debug_linearize)
   // solver options
   int max_iters, jacobi_scaling;
+  int strategy;                   // BVIO_STRATEGY_LM / BVIO_STRATEGY_DOGLEG
   double sqrt_info, cauchy_a, G[3];
   double function_tolerance, gradient_tolerance, parameter_tolerance, initial_radius, min_relative_decrease;
   // structure
@@ -86,7 +94,10 @@ struct BaBatch {                  // all pointers are device pointers
   double* w;                      // [total_obs][6]
   double* tile_out;               // [B][T][tile_rec_doubles(K)]
   double* cost_out;               // [B][T+1][COST_REC]
-  double* delta_p;                // [B][np]
+  double* delta_p;                // [B][np]  LM step / Gauss-Newton step (dogleg)
+  double* dog_t;                  // [B][np]  dogleg: scaled gradient direction t = scale^2 g / D^2 (pose part)
+  double* dog_l;                  // [total_L][2] dogleg: landmark parts (t_l, Gauss-Newton dlambda_l)
+  double* dog_out;                // [B][T][DOG_REC] per-tile partial dot products
   double* scale_p;                // [B][np] Jacobi scaling of the pose/speed-bias columns
   double* dbg_S; double* dbg_g;   // [B][np*np], [B][np] (debug linearize only, else null)
   BaCtrl* ctrl;                   // [B]

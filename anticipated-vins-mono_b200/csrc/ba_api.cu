@@ -100,8 +100,8 @@ static int validate(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* o, int
   if (!w || !o) return fail(ctx, BVIO_ERR_INVALID, "null window/opts");
   if (o->estimate_extrinsic || o->estimate_td)
     return fail(ctx, BVIO_ERR_UNSUPPORTED, "estimate_extrinsic / estimate_td are not implemented on the device path");
-  if (o->strategy != BVIO_STRATEGY_LM)
-    return fail(ctx, BVIO_ERR_UNSUPPORTED, "device path implements BVIO_STRATEGY_LM only");
+  if (o->strategy != BVIO_STRATEGY_LM && o->strategy != BVIO_STRATEGY_DOGLEG)
+    return fail(ctx, BVIO_ERR_INVALID, "unknown trust-region strategy");
   if (w->K < 2 || w->K > BVIO_KMAX - 1) return fail(ctx, BVIO_ERR_INVALID, "K out of range [2,15] (reduced system must fit one CTA's shared memory)");
   if (w->K != K0) return fail(ctx, BVIO_ERR_INVALID, "all windows of a batch must have the same K");
   if (w->L < 0 || !w->para_pose || !w->para_speed_bias || !w->para_ex_pose || !w->preint)
@@ -160,6 +160,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bt.T = T;
   bt.undamped = debug;
   bt.max_iters = o->max_iters; bt.jacobi_scaling = o->jacobi_scaling;
+  bt.strategy = o->strategy;
   bt.sqrt_info = o->focal_length / 1.5;   // estimator.cpp:17
   bt.cauchy_a = o->cauchy_a;
   for (int i = 0; i < 3; i++) bt.G[i] = o->G[i];
@@ -202,6 +203,11 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   size_t o_tile = cv.take((size_t)B * T * tile_rec_doubles(K) * D);
   size_t o_cost = cv.take((size_t)B * (T + 1) * COST_REC * D);
   size_t o_dp = cv.take((size_t)B * bt.np * D), o_sp = cv.take((size_t)B * bt.np * D);
+  size_t o_dog_t = 0, o_dog_l = 0, o_dog_out = 0;
+  if (bt.strategy == BVIO_STRATEGY_DOGLEG) {
+    o_dog_t = cv.take((size_t)B * bt.np * D); o_dog_l = cv.take((size_t)total_L * 2 * D);
+    o_dog_out = cv.take((size_t)B * T * DOG_REC * D);
+  }
   size_t o_dbgS = 0, o_dbgg = 0;
   if (debug) { o_dbgS = cv.take((size_t)B * bt.np * bt.np * D); o_dbgg = cv.take((size_t)B * bt.np * D); }
   const size_t d_bytes = cv.off;
@@ -311,6 +317,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bt.h = (double*)(d + o_h); bt.b = (double*)(d + o_b); bt.sl2 = (double*)(d + o_sl2); bt.w = (double*)(d + o_w);
   bt.tile_out = (double*)(d + o_tile); bt.cost_out = (double*)(d + o_cost);
   bt.delta_p = (double*)(d + o_dp); bt.scale_p = (double*)(d + o_sp);
+  bt.dog_t = (double*)(d + o_dog_t); bt.dog_l = (double*)(d + o_dog_l); bt.dog_out = (double*)(d + o_dog_out);
   bt.dbg_S = debug ? (double*)(d + o_dbgS) : nullptr;
   bt.dbg_g = debug ? (double*)(d + o_dbgg) : nullptr;
 

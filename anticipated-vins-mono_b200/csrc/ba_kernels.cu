@@ -68,6 +68,13 @@ __device__ __forceinline__ ProjGeom proj_geom(const double* Fi, const double* Fj
   return g;
 }
 
+// Diagonal regularisation of one column with Jacobi scale^2 = s2 and clamped scaled diagonal `cl`:
+//   LM      (LevenbergMarquardtStrategy): D^2 = cl / radius          -> unscaled cl / (radius s2)
+//   dogleg  (DoglegStrategy GN step)    : D^2 = mu * cl              -> unscaled mu cl / s2
+__device__ __forceinline__ double damp_term(double cl, double s2, double radius, double mu, int dogleg) {
+  return dogleg ? mu * cl / s2 : cl / (radius * s2);
+}
+
 __device__ __forceinline__ void cauchy(double a, double s, double& rho0, double& rho1) {
   double bb = a * a, c = 1.0 / bb;
   double sum = 1.0 + s * c, inv = 1.0 / sum;
@@ -288,6 +295,8 @@ __global__ void ba_reset_kernel(BaBatch bt) {
     c.model_pose = 0; c.gmax = 0; c.initial_cost = 0; c.rho = 0;
     c.cur = 0; c.done = 0; c.termination = 0 /*MAX_ITERS*/; c.iterations = 0; c.accepted = 0; c.rejected = 0;
     c.first = 1; c.solve_ok = 0; c.invalid_run = 0; c.stepped = 0; c.ticket = 0; c.pad = 0;
+    c.mu = 1e-8; c.ca = 0; c.cb = 1; c.step_norm = 0;
+    for (int q = 0; q < 6; q++) c.dsum[q] = 0;
     bt.ctrl[k] = c;
   }
 }
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   double cost_t = 0, gmax_t = 0;
 
   stage_frames(bt, w, bt.pose[cur], sFr, sEx);
-  const double radius = ctrl->radius;
+  const double radius = ctrl->radius, mu = ctrl->mu;
   const int first = ctrl->first;
   const double* invd = bt.invd[cur];
   int l0, l1;
@@ -544,7 +553,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
         if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
         else sl2 = bt.sl2[l];
       }
-      const double ddl = fmin(fmax(sl2 * h, 1e-6), 1e32) / (radius * sl2);
+      const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, radius, mu, bt.strategy);
       double inv_hd = 1.0 / (h + ddl);
       if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
       sSc[tid * 4] = inv_hd;
@@ -664,6 +673,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
   double* yv = ddp + np;                          // [np]
   double* red = yv + np;                          // [32]
   double* dinv = red + 32;                        // [np] reciprocal diagonal of L
+  double* tv = dinv + np;                         // [np] dogleg: scaled gradient direction t
   __shared__ int s_fail;
   const int REC = NPb * 36 + 3 * K6;
   const int TREC = tile_rec_doubles(K);
@@ -763,11 +773,38 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
     if (tid == 0) { ctrl->done = 1; if (stop > 0) ctrl->termination = stop; ctrl->stepped = 0; }
     return;
   }
+  const int dogleg = bt.strategy;
+  const double mu = ctrl->mu;
+  auto scale2 = [&](int i) {
+    const double sp = first ? (bt.jacobi_scaling ? 1.0 / (1.0 + sqrt(dH[i])) : 1.0) : bt.scale_p[(size_t)w * np + i];
+    return sp * sp;
+  };
+  // dogleg (Ceres DoglegStrategy::ComputeGradient / ComputeCauchyPoint): t = scale^2 g / D^2 is the
+  // scaled steepest-descent direction in x space; pose parts of |g_y|^2 = g^T t and t^T H t (S still holds
+  // the undamped reduced matrix, the landmark kernel adds the rest of H)
+  double dg_gsq = 0, dg_tSt = 0;
+  if (dogleg) {
+    for (int i = tid; i < np; i += nthr) {
+      const double sp2 = scale2(i);
+      tv[i] = sp2 * bp[i] / fmin(fmax(sp2 * dH[i], 1e-6), 1e32);
+    }
+    __syncthreads();
+    double a = 0, q = 0;
+    for (int i = tid; i < np; i += nthr) {
+      double sacc = 0;
+      const double* row = S + tri(i, 0);
+      for (int j = 0; j < i; j++) sacc += row[j] * tv[j];
+      q += tv[i] * (2.0 * sacc + row[i] * tv[i]);
+      a += bp[i] * tv[i];
+    }
+    dg_gsq = block_sum(a, red);
+    dg_tSt = block_sum(q, red);
+    __syncthreads();
+  }
   // damping + augmented row
   for (int i = tid; i < np; i += nthr) {
-    double sp = first ? (bt.jacobi_scaling ? 1.0 / (1.0 + sqrt(dH[i])) : 1.0) : bt.scale_p[(size_t)w * np + i];
-    double sp2 = sp * sp;
-    double d = fmin(fmax(sp2 * dH[i], 1e-6), 1e32) / (radius * sp2);
+    double sp2 = scale2(i);
+    double d = damp_term(fmin(fmax(sp2 * dH[i], 1e-6), 1e32), sp2, radius, mu, dogleg);
     ddp[i] = d;
     S[tri(i, i)] += d;
     S[tri(np, i)] = -gr[i];
@@ -893,13 +930,26 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
     __syncthreads();
   }
   // step + pose part of the model cost change:  -g^T d - 1/2 d^T H d = -1/2 g^T d + 1/2 d^T D d
-  double mp = 0;
+  double mp = 0, s_bgn = 0, s_gn2 = 0, s_nDn = 0, s_tDn = 0;
   for (int i = tid; i < np; i += nthr) {
     double d = yv[i];
     bt.delta_p[(size_t)w * np + i] = d;
     mp += -0.5 * bp[i] * d + 0.5 * ddp[i] * d * d;
+    if (dogleg) {
+      const double sp2 = scale2(i), cl = fmin(fmax(sp2 * dH[i], 1e-6), 1e32);
+      bt.dog_t[(size_t)w * np + i] = tv[i];
+      s_bgn += bp[i] * d; s_gn2 += cl * d * d / sp2; s_nDn += ddp[i] * d * d; s_tDn += ddp[i] * tv[i] * d;
+    }
   }
   mp = block_sum(mp, red);
+  if (dogleg) {
+    s_bgn = block_sum(s_bgn, red); s_gn2 = block_sum(s_gn2, red);
+    s_nDn = block_sum(s_nDn, red); s_tDn = block_sum(s_tDn, red);
+    if (tid == 0) {
+      ctrl->dsum[0] = dg_gsq; ctrl->dsum[1] = dg_tSt; ctrl->dsum[2] = s_gn2;
+      ctrl->dsum[3] = s_bgn; ctrl->dsum[4] = s_nDn; ctrl->dsum[5] = s_tDn;
+    }
+  }
   if (tid == 0) { ctrl->model_pose = mp; ctrl->solve_ok = 1; ctrl->stepped = 1; ctrl->iterations++; }
 }
 
@@ -913,10 +963,12 @@ __device__ void decide(const BaBatch& bt, int w, double cv, double ml, double s2
   bool valid = c->solve_ok != 0;
   double model = c->model_pose + ml;
   if (valid && !(model > 0)) valid = false;
+  const int dogleg = bt.strategy;
   if (!valid) {
     c->rejected++;
     if (++c->invalid_run >= 5) { c->done = 1; c->termination = 4; return; }
-    c->radius /= c->decrease_factor; c->decrease_factor *= 2;
+    if (dogleg) c->mu *= 10.0;      // DoglegStrategy::StepIsInvalid: mu_ *= mu_increase_factor_
+    else { c->radius /= c->decrease_factor; c->decrease_factor *= 2; }
     if (c->radius < 1e-32) { c->done = 1; c->termination = 4; }
     return;
   }
@@ -932,13 +984,128 @@ __device__ void decide(const BaBatch& bt, int w, double cv, double ml, double s2
     c->accepted++;
     c->cur ^= 1;
     c->cost = cv;
-    double t = 2.0 * rho - 1.0;
-    c->radius = fmin(1e16, c->radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
-    c->decrease_factor = 2.0;
+    if (dogleg) {                   // DoglegStrategy::StepAccepted
+      if (rho < 0.25) c->radius *= 0.5;
+      if (rho > 0.75) c->radius = fmax(c->radius, 3.0 * c->step_norm);
+      c->mu = fmax(1e-8, 2.0 * c->mu / 10.0);
+    } else {
+      double t = 2.0 * rho - 1.0;
+      c->radius = fmin(1e16, c->radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+      c->decrease_factor = 2.0;
+    }
   } else {
     c->rejected++;
-    c->radius /= c->decrease_factor; c->decrease_factor *= 2;
+    if (dogleg) c->radius *= 0.5;   // DoglegStrategy::StepRejected
+    else { c->radius /= c->decrease_factor; c->decrease_factor *= 2; }
     if (c->radius < 1e-32) { c->done = 1; c->termination = 4; }
+  }
+}
+
+// Traditional dogleg (Ceres DoglegStrategy::ComputeStep, TRADITIONAL_DOGLEG), landmark part + combination.
+// ba_solve left the Gauss-Newton step n_p (mu-regularised) and the scaled gradient direction t_p; here 16 lanes
+// per landmark back-substitute n_l = -(b + w.n_p)/(h + d), form t_l = s^2 b / D^2 and the landmark parts of
+//   |g_y|^2 = g.t,  t^T H t,  |n_y|^2,  g.n,  n^T D n,  t^T D n          (D = mu * Jacobi-scaled diagonal)
+// with  t^T H t = t_p^T S t_p + sum_l [(w.t_p)^2/(h+d) + 2 t_l (w.t_p) + h t_l^2]   (S = reduced matrix).
+// The last CTA of the window (ticket) adds the pose parts, picks the dogleg coefficients
+//   step = ca * t + cb * n      (Gauss-Newton / Cauchy / interpolated, in Ceres' scaled y space)
+// and the model decrease, using H n = -g - D n:  n^T H n = -g.n - n^T D n,  t^T H n = -g.t - t^T D n.
+__global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.y, t = blockIdx.x, np = bt.np;
+  BaCtrl* ctrl = bt.ctrl + w;
+  if (ctrl->done || !ctrl->stepped || !ctrl->solve_ok) return;
+  double* sn = sm;             // [np] Gauss-Newton step (pose part)
+  double* st = sn + np;        // [np] t (pose part)
+  double* red = st + np;       // [16 * DOG_REC]
+  __shared__ int s_last;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    sn[i] = bt.delta_p[(size_t)w * np + i];
+    st[i] = bt.dog_t[(size_t)w * np + i];
+  }
+  __syncthreads();
+  const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15, NG = blockDim.x >> 4;
+  const unsigned gmask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+  const double mu = ctrl->mu;
+  const int cur = ctrl->cur;
+  int l0, l1;
+  tile_range(bt, w, t, l0, l1);
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  for (int l = l0 + grp; l < l1; l += NG) {
+    const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0;
+    double wn = 0, wt = 0;
+    if (l16 < n) {
+      const int fr = bt.obs_frame[o0 + l16];
+      const double* wp = bt.w + (size_t)(o0 + l16) * 6;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { wn += wp[k] * sn[15 * fr + k]; wt += wp[k] * st[15 * fr + k]; }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { wn += __shfl_xor_sync(gmask, wn, o, 16); wt += __shfl_xor_sync(gmask, wt, o, 16); }
+    if (l16 == 0) {
+      const double h = bt.h[l], b = bt.b[l];
+      const double sl2 = bt.jacobi_scaling ? bt.sl2[l] : 1.0;
+      const double cl = fmin(fmax(sl2 * h, 1e-6), 1e32);
+      const double ddl = mu * cl / sl2, hd = h + ddl;
+      const double tl = sl2 * b / cl;
+      const double nl = -(b + wn) / hd;
+      bt.dog_l[(size_t)2 * l] = tl; bt.dog_l[(size_t)2 * l + 1] = nl;
+      a[0] += b * tl;
+      a[1] += wt * wt / hd + 2.0 * tl * wt + h * tl * tl;
+      a[2] += cl * nl * nl / sl2;
+      a[3] += b * nl;
+      a[4] += ddl * nl * nl;
+      a[5] += ddl * tl * nl;
+    }
+  }
+  if (l16 == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) red[grp * DOG_REC + k] = a[k];
+  }
+  __syncthreads();
+  double* out = bt.dog_out + (size_t)(w * bt.T + t) * DOG_REC;
+  if (threadIdx.x < 6) {
+    double s = 0;
+    for (int g = 0; g < NG; g++) s += red[g * DOG_REC + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned old = atomicAdd(&ctrl->ticket, 1u);
+    s_last = (old == (unsigned)(bt.T - 1));
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double v[6];
+    for (int k = 0; k < 6; k++) v[k] = ctrl->dsum[k];
+    const double* rec = bt.dog_out + (size_t)w * bt.T * DOG_REC;
+    for (int q = 0; q < bt.T; q++)
+      for (int k = 0; k < 6; k++) v[k] += __ldcg(rec + q * DOG_REC + k);
+    const double gsq = v[0], tHt = v[1], gn2 = v[2], gdn = v[3], nDn = v[4], tDn = v[5];
+    const double radius = ctrl->radius;
+    const double alpha = gsq / tHt;                       // Cauchy step length: |g|^2 / |J g|^2 (y space)
+    const double g_norm = sqrt(gsq), gn_norm = sqrt(gn2);
+    double ca, cb, sn2;
+    if (gn_norm <= radius) { ca = 0; cb = 1; sn2 = gn2; }
+    else if (g_norm * alpha >= radius) { ca = -(radius / g_norm); cb = 0; sn2 = radius * radius; }
+    else {
+      // y-space dot product gradient . gn equals g . n in x space
+      const double b_dot_a = -alpha * gdn;
+      const double a_sq = alpha * alpha * gsq;
+      const double bma_sq = a_sq - 2 * b_dot_a + gn2;
+      const double c = b_dot_a - a_sq;
+      const double d = sqrt(c * c + bma_sq * (radius * radius - a_sq));
+      const double beta = (c <= 0) ? (d - c) / bma_sq : (radius * radius - a_sq) / (d + c);
+      ca = -alpha * (1.0 - beta); cb = beta;
+      sn2 = ca * ca * gsq + 2.0 * ca * cb * gdn + cb * cb * gn2;
+    }
+    const double tHn = -gsq - tDn, nHn = -gdn - nDn;
+    const double quad = ca * ca * tHt + 2.0 * ca * cb * tHn + cb * cb * nHn;
+    ctrl->ca = ca; ctrl->cb = cb;
+    ctrl->step_norm = sqrt(fmax(sn2, 0.0));
+    ctrl->model_pose = -(ca * gsq + cb * gdn) - 0.5 * quad;   // the whole model decrease (cost kernel adds 0)
+    ctrl->ticket = 0;
   }
 }
 
@@ -959,7 +1126,13 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
   double* red = sEx + FR;           // [16*4 + 32]
   double* extra = red + 96;         // IMU/prior CTA scratch
   __shared__ int s_last;
-  for (int i = threadIdx.x; i < np; i += blockDim.x) sdp[i] = bt.delta_p[(size_t)w * np + i];
+  const int dogleg = bt.strategy;
+  const double ca = ctrl->ca, cb = ctrl->cb, mu = ctrl->mu;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    double d = bt.delta_p[(size_t)w * np + i];
+    if (dogleg) d = ca * bt.dog_t[(size_t)w * np + i] + cb * d;
+    sdp[i] = d;
+  }
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += blockDim.x)
     pose_plus(bt.pose[cur] + (size_t)(w * K + k) * 7, sdp + 15 * k, sPose + k * 7);
@@ -986,17 +1159,22 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       double part = 0;
       if (l16 < n) {
         myfr = bt.obs_frame[o0 + l16];
-        const double* wp = bt.w + (size_t)(o0 + l16) * 6;
-        const double* d = sdp + 15 * myfr;
+        if (!dogleg) {
+          const double* wp = bt.w + (size_t)(o0 + l16) * 6;
+          const double* d = sdp + 15 * myfr;
 #pragma unroll
-        for (int k = 0; k < 6; k++) part += wp[k] * d[k];
+          for (int k = 0; k < 6; k++) part += wp[k] * d[k];
+        }
       }
+      if (!dogleg) {
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, 16);
+        for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, 16);
+      }
       const int fi = __shfl_sync(gmask, myfr, 0, 16);
       double sl2 = bt.jacobi_scaling ? bt.sl2[l] : 1.0;
-      double ddl = fmin(fmax(sl2 * h, 1e-6), 1e32) / (radius * sl2);
+      double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, radius, mu, dogleg);
       double dl = -(b + part) / (h + ddl);
+      if (dogleg) dl = ca * bt.dog_l[(size_t)2 * l] + cb * bt.dog_l[(size_t)2 * l + 1];
       double lamc = lam + dl;
       double fc = 0;
       if (l16 >= 1 && l16 < n) {
@@ -1013,7 +1191,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       if (l16 == 0) {
         bt.invd[nxt][l] = lamc;
         a_cost += fc;
-        a_model += -0.5 * b * dl + 0.5 * ddl * dl * dl;
+        if (!dogleg) a_model += -0.5 * b * dl + 0.5 * ddl * dl * dl;
         a_s2 += dl * dl;
         a_x2 += lam * lam;
       }
@@ -1123,7 +1301,7 @@ int ba_pick_chunk(int K) {
 }
 size_t ba_solve_smem_bytes(int K) {
   int np = 15 * K, N1 = np + 1;
-  return sizeof(double) * ((size_t)N1 * (N1 + 1) / 2 + 6 * np + 32);
+  return sizeof(double) * ((size_t)N1 * (N1 + 1) / 2 + 7 * np + 32);
 }
 static size_t cost_smem(int K, int nmax) {
   return sizeof(double) * ((size_t)15 * K + K * 7 + (K + 1) * FR + 96 + K * 9 + (K - 1) * 15 + 2 * nmax);
@@ -1178,11 +1356,16 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
   else ba_linearize_kernel<4><<<dim3(bt.T + 1, bt.B), BA_THREADS, s1, st>>>(bt);
   if (ev) cudaEventRecord(ev[1], st);
   ba_solve_kernel<<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.K), st>>>(bt, with_step ? 1 : 0);
+  if (!with_step || bt.undamped) { if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); } return 2; }
+  int nk = 3;
+  if (bt.strategy) {   // dogleg combination; its time is booked with the reduced solve
+    ba_dogleg_kernel<<<dim3(bt.T, bt.B), BA_THREADS, sizeof(double) * (2 * bt.np + 16 * DOG_REC), st>>>(bt);
+    nk = 4;
+  }
   if (ev) cudaEventRecord(ev[2], st);
-  if (!with_step || bt.undamped) { if (ev) cudaEventRecord(ev[3], st); return 2; }
   ba_cost_kernel<<<dim3(bt.T + 1, bt.B), BA_THREADS, cost_smem(bt.K, bt.nmax), st>>>(bt);
   if (ev) cudaEventRecord(ev[3], st);
-  return 3;
+  return nk;
 }
 int ba_launch_finish(const BaBatch& bt, cudaStream_t st) {
   int blocks = bt.B < 1184 ? bt.B : 1184;

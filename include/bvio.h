@@ -122,7 +122,7 @@ typedef struct {
   double  parameter_tolerance;  /* 1e-8  */
   double  initial_radius;       /* 1e4   */
   double  min_relative_decrease;/* 1e-3  */
-  int32_t strategy;             /* BVIO_STRATEGY_LM on the device path         */
+  int32_t strategy;             /* BVIO_STRATEGY_LM (default) or _DOGLEG       */
   int32_t jacobi_scaling;       /* 1                                            */
 } bvio_opts;
 

@@ -105,6 +105,38 @@ def test_default_opts_trajectory_matches_oracle(env):
         assert np.linalg.norm(xg - xo) <= 1e-8 * np.linalg.norm(xo)
 
 
+@pytest.mark.parametrize("seed,radius,iters", [(10, 1e4, 8), (11, 1e4, 8), (12, 1e4, 8), (13, 1.0, 8), (14, 0.05, 8),
+                                               (15, 1e-3, 8), (16, 1.0, 25), (17, 0.05, 30)])
+def test_dogleg_reference_budget_matches_oracle(env, seed, radius, iters):
+    """The strategy the reference configures (estimator.cpp:800 DOGLEG, 8 iterations, Ceres default
+    tolerances): identical iteration / accept / reject / termination trajectory and the same state.  Small
+    initial radii force the Cauchy-point and interpolated branches of the traditional dogleg."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=seed, K=11, L=150)
+    hg, ho, sg, so = _solve_both(env, w, dict(strategy=1, initial_radius=radius, max_iters=iters))
+    assert (sg.iterations, sg.num_accepted, sg.num_rejected, sg.termination) == \
+           (so.iterations, so.num_accepted, so.num_rejected, so.termination), (sg.as_dict(), so.as_dict())
+    xg, xo = hg.state_vector(), ho.state_vector()
+    assert np.linalg.norm(xg - xo) <= 1e-8 * np.linalg.norm(xo), (sg.as_dict(), so.as_dict())
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    assert abs(sg.final_radius - so.final_radius) <= 1e-6 * so.final_radius
+
+
+@pytest.mark.parametrize("seed,K,L", [(0, 11, 150), (1, 11, 150), (2, 2, 20), (3, 5, 37), (7, 11, 1500)])
+def test_dogleg_converged_state_matches_oracle(env, seed, K, L):
+    abi, synth, orc, ctx = env
+    kw = dict(track_min=2, track_max=2) if K == 2 else (dict(track_min=6) if L == 1500 else {})
+    w = synth.make_window(seed=seed, K=K, L=L, **kw)
+    hg, ho, sg, so = _solve_both(env, w, dict(strategy=1, **TIGHT))
+    xg, xo = hg.state_vector(), ho.state_vector()
+    assert np.linalg.norm(xg - xo) <= 1e-6 * np.linalg.norm(xo), (sg.as_dict(), so.as_dict())
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    # dogleg and LM descend to the same minimum (the state along weakly observable directions is only
+    # determined to ~sqrt of the cost tolerance, so compare costs)
+    hl, _, sl, _ = _solve_both(env, w, TIGHT)
+    assert abs(sg.final_cost - sl.final_cost) <= 1e-6 * sl.final_cost
+
+
 def test_stress_window_1500_features(env):
     """BASELINE config 3: 11-kf / 1500-feature window."""
     abi, synth, orc, ctx = env
@@ -160,6 +192,6 @@ def test_rejects_unsupported_and_invalid(env):
     h = abi.WindowHandle(w)
     s = abi.Summary()
     assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(estimate_td=1)), C.byref(s)) == -4
-    assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(strategy=1)), C.byref(s)) == -4
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(strategy=7)), C.byref(s)) == -1
     h.frame[1] = h.frame[0]   # not strictly ascending
     assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts()), C.byref(s)) == -1
