@@ -62,6 +62,7 @@ struct BaBatch {                  // all pointers are device pointers
   // solver options
   int max_iters, jacobi_scaling;
   int strategy;                   // BVIO_STRATEGY_LM / BVIO_STRATEGY_DOGLEG
+  int est_ex;                     // estimate_extrinsic: np = 15K + 6, extrinsic block = pseudo-frame K
   double sqrt_info, cauchy_a, G[3];
   double function_tolerance, gradient_tolerance, parameter_tolerance, initial_radius, min_relative_decrease;
   // structure
@@ -72,7 +73,9 @@ struct BaBatch {                  // all pointers are device pointers
   // state, double buffered
   double* pose[2];                // [B][K][7]
   double* sb[2];                  // [B][K][9]
-  double* ex;                     // [B][7] (constant: estimate_extrinsic = 0 on the device path)
+  const double* ex;               // [B][7] uploaded extrinsic pose
+  double* exs[2];                 // [B][7] extrinsic state, double buffered (both = ex when it is constant)
+  double* ex_out;                 // [B][7]
   double* invd[2];                // [total_L]
   const double* pose0; const double* sb0; const double* invd0;   // uploaded initial state (for reset)
   double* pose_out; double* sb_out; double* invd_out;            // final state gathered from X[cur]
@@ -92,6 +95,7 @@ struct BaBatch {                  // all pointers are device pointers
   // linearization products
   double* h; double* b; double* sl2;   // [total_L]
   double* w;                      // [total_obs][6]
+  double* wex;                    // [total_L][6] extrinsic part of the landmark's coupling row (est_ex only)
   double* tile_out;               // [B][T][tile_rec_doubles(K)]
   double* cost_out;               // [B][T+1][COST_REC]
   double* delta_p;                // [B][np]  LM step / Gauss-Newton step (dogleg)
@@ -108,9 +112,9 @@ int ba_launch_prepare(const BaBatch& bt, cudaStream_t st);
 int ba_launch_reset(const BaBatch& bt, cudaStream_t st);
 int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cudaEvent_t* ev = nullptr);  // ev[4]: before/after each kernel
 int ba_launch_finish(const BaBatch& bt, cudaStream_t st);
-size_t ba_linearize_smem_bytes(int K, int chunk_l);
-int ba_pick_chunk(int K);
-size_t ba_solve_smem_bytes(int K);
+size_t ba_linearize_smem_bytes(int K, int chunk_l, int est_ex);
+int ba_pick_chunk(int K, int est_ex);
+size_t ba_solve_smem_bytes(int np);
 size_t ba_marginalize_smem_bytes(int K, int nmax, int n);
 int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, const int* dropidx, const int* keepidx, double* A,
                           double* b, double* out_jac, double* out_res, int* status, cudaStream_t st);

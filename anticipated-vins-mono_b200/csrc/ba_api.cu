@@ -19,7 +19,7 @@ struct bvio_batch {
   bool from_cache = false;
   size_t in_bytes = 0;                 // [0, in_bytes): inputs, mirrored on the host
   size_t out_off = 0, out_bytes = 0;   // [out_off, out_off+out_bytes): outputs, mirrored on the host
-  size_t o_pose_out = 0, o_sb_out = 0, o_invd_out = 0, o_ctrl = 0;
+  size_t o_pose_out = 0, o_sb_out = 0, o_invd_out = 0, o_ex_out = 0, o_ctrl = 0;
   std::vector<int> lm_base;
   cudaGraphExec_t graph = nullptr;
   bool use_graph = true;
@@ -98,8 +98,10 @@ int64_t bvio_launch_count(const bvio_ctx* ctx) { return ctx ? ctx->launches : 0;
 // ---------------------------------------------------------------------------------------------
 static int validate(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* o, int K0) {
   if (!w || !o) return fail(ctx, BVIO_ERR_INVALID, "null window/opts");
-  if (o->estimate_extrinsic || o->estimate_td)
-    return fail(ctx, BVIO_ERR_UNSUPPORTED, "estimate_extrinsic / estimate_td are not implemented on the device path");
+  if (o->estimate_td)
+    return fail(ctx, BVIO_ERR_UNSUPPORTED, "estimate_td is not implemented on the device path");
+  if (o->estimate_extrinsic && w->K > BVIO_KMAX - 2)
+    return fail(ctx, BVIO_ERR_INVALID, "K out of range [2,14] with estimate_extrinsic (reduced system must fit one CTA's shared memory)");
   if (o->strategy != BVIO_STRATEGY_LM && o->strategy != BVIO_STRATEGY_DOGLEG)
     return fail(ctx, BVIO_ERR_INVALID, "unknown trust-region strategy");
   if (w->K < 2 || w->K > BVIO_KMAX - 1) return fail(ctx, BVIO_ERR_INVALID, "K out of range [2,15] (reduced system must fit one CTA's shared memory)");
@@ -152,8 +154,10 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   if (!bb) return fail(ctx, BVIO_ERR_INVALID, "out of host memory");
   BaBatch& bt = bb->bt;
   memset(&bt, 0, sizeof bt);
-  bt.B = B; bt.K = K; bt.np = 15 * K; bt.total_L = total_L; bt.total_obs = total_obs; bt.nmax = nmax;
-  bt.chunk_l = ba_pick_chunk(K);
+  const int est_ex = o->estimate_extrinsic != 0, KE = est_ex ? K + 1 : K;
+  bt.B = B; bt.K = K; bt.np = 15 * K + (est_ex ? 6 : 0); bt.total_L = total_L; bt.total_obs = total_obs; bt.nmax = nmax;
+  bt.est_ex = est_ex;
+  bt.chunk_l = ba_pick_chunk(K, est_ex);
   int T = (maxL + 2 * bt.chunk_l - 1) / (2 * bt.chunk_l);   // >= 2 chunks per tile when there is a choice
   int Tcap = std::max(1, (2 * ctx->sm_count + B - 1) / B);
   T = std::max(1, std::min(std::min(T, Tcap), 32));
@@ -187,6 +191,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bb->o_pose_out = cv.take((size_t)B * K * 7 * D);
   bb->o_sb_out = cv.take((size_t)B * K * 9 * D);
   bb->o_invd_out = cv.take((size_t)total_L * D);
+  bb->o_ex_out = cv.take((size_t)B * 7 * D);
   bb->o_ctrl = cv.take((size_t)B * sizeof(BaCtrl));
   bb->out_bytes = cv.off - bb->out_off;
   const size_t h_bytes = cv.off;
@@ -200,7 +205,9 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   size_t o_pr_out = cv.take((size_t)B * (nmax + 1) * D);
   size_t o_h = cv.take((size_t)total_L * D), o_b = cv.take((size_t)total_L * D), o_sl2 = cv.take((size_t)total_L * D);
   size_t o_w = cv.take((size_t)total_obs * 6 * D);
-  size_t o_tile = cv.take((size_t)B * T * tile_rec_doubles(K) * D);
+  size_t o_tile = cv.take((size_t)B * T * tile_rec_doubles(KE) * D);
+  size_t o_exs[2] = {cv.take((size_t)B * 7 * D), cv.take((size_t)B * 7 * D)};
+  size_t o_wex = est_ex ? cv.take((size_t)total_L * 6 * D) : 0;
   size_t o_cost = cv.take((size_t)B * (T + 1) * COST_REC * D);
   size_t o_dp = cv.take((size_t)B * bt.np * D), o_sp = cv.take((size_t)B * bt.np * D);
   size_t o_dog_t = 0, o_dog_l = 0, o_dog_out = 0;
@@ -302,7 +309,9 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
 
   bt.lm_base = (const int*)(d + o_lm_base); bt.lm_off = (const int*)(d + o_lm_off);
   bt.obs_frame = (const int*)(d + o_obs_frame); bt.obs_xy = (const double2*)(d + o_obs_xy);
-  bt.pose0 = (const double*)(d + o_pose0); bt.sb0 = (const double*)(d + o_sb0); bt.ex = (double*)(d + o_ex);
+  bt.pose0 = (const double*)(d + o_pose0); bt.sb0 = (const double*)(d + o_sb0); bt.ex = (const double*)(d + o_ex);
+  bt.exs[0] = (double*)(d + o_exs[0]); bt.exs[1] = (double*)(d + o_exs[1]); bt.ex_out = (double*)(d + bb->o_ex_out);
+  bt.wex = (double*)(d + o_wex);
   bt.invd0 = (const double*)(d + o_invd0); bt.preint_raw = (const double*)(d + o_preint);
   bt.pr_n = (const int*)(d + o_pr_n); bt.pr_nb = (const int*)(d + o_pr_nb);
   bt.pr_kind = (const int*)(d + o_pr_kind); bt.pr_frame = (const int*)(d + o_pr_frame); bt.pr_idx = (const int*)(d + o_pr_idx);
@@ -384,6 +393,7 @@ int bvio_batch_download(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, bvi
   const double* pose = (const double*)(bb->slab.h + bb->o_pose_out);
   const double* sb = (const double*)(bb->slab.h + bb->o_sb_out);
   const double* invd = (const double*)(bb->slab.h + bb->o_invd_out);
+  const double* exo = (const double*)(bb->slab.h + bb->o_ex_out);
   const BaCtrl* ctrl = (const BaCtrl*)(bb->slab.h + bb->o_ctrl);
   int rc = BVIO_OK;
   for (int b = 0; b < bt.B; b++) {
@@ -393,6 +403,7 @@ int bvio_batch_download(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, bvi
       memcpy(w.para_speed_bias, sb + (size_t)b * bt.K * 9, (size_t)bt.K * 9 * sizeof(double));
       int L = bb->lm_base[b + 1] - bb->lm_base[b];
       if (L) memcpy(w.inv_depth, invd + bb->lm_base[b], (size_t)L * sizeof(double));
+      if (bt.est_ex) memcpy(w.para_ex_pose, exo + (size_t)b * 7, 7 * sizeof(double));
     }
     const BaCtrl& c = ctrl[b];
     if (summaries) {

@@ -29,6 +29,7 @@ __constant__ unsigned char c_tri30B[465];
 
 constexpr int FR = 12;            // per-frame staged state: R (9, row-major) + P (3)
 constexpr int STG = 29;           // per-factor staging stride (28 used; odd => conflict-free)
+constexpr int STGX = 41;          // same with the 2x6 extrinsic Jacobian at 28..39 (estimate_extrinsic)
 constexpr int ACS = 37;           // padded stride of one 6x6 accumulator block (odd => lanes hit distinct banks)
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
@@ -41,9 +42,10 @@ __device__ __forceinline__ void tile_range(const BaBatch& bt, int w, int t, int&
 }
 
 // stage R,P of the K frames of window w (state buffer `buf`) and the extrinsics into shared memory
-__device__ __forceinline__ void stage_frames(const BaBatch& bt, int w, const double* pose, double* sFr, double* sEx) {
+__device__ __forceinline__ void stage_frames(const BaBatch& bt, int w, const double* pose, const double* ex,
+                                             double* sFr, double* sEx) {
   for (int k = threadIdx.x; k <= bt.K; k += blockDim.x) {
-    const double* p = (k < bt.K) ? pose + (size_t)(w * bt.K + k) * 7 : bt.ex + (size_t)w * 7;
+    const double* p = (k < bt.K) ? pose + (size_t)(w * bt.K + k) * 7 : ex + (size_t)w * 7;
     double* o = (k < bt.K) ? sFr + k * FR : sEx;
     qmat(q4{p[3], p[4], p[5], p[6]}, o);
     o[9] = p[0]; o[10] = p[1]; o[11] = p[2];
@@ -172,15 +174,15 @@ __device__ void imu_raw(const double* rec, const double* G, const double* pi, co
 
 // MarginalizationFactor::Evaluate residual: dx per kept block, r = r0 + J dx. Block-cooperative.
 // sdx, sr: shared [nmax]. Returns nothing; caller syncs.
-__device__ void prior_residual(const BaBatch& bt, int w, const double* pose, const double* sb, double* sdx,
-                               double* sr) {
+__device__ void prior_residual(const BaBatch& bt, int w, const double* pose, const double* sb, const double* ex,
+                               double* sdx, double* sr) {
   int n = bt.pr_n[w], nb = bt.pr_nb[w];
   for (int bidx = threadIdx.x; bidx < nb; bidx += blockDim.x) {
     int kind = bt.pr_kind[w * PRIOR_MAXB + bidx], fr = bt.pr_frame[w * PRIOR_MAXB + bidx];
     int idx = bt.pr_idx[w * PRIOR_MAXB + bidx];
     const double* x0 = bt.pr_x0 + (size_t)(w * PRIOR_MAXB + bidx) * 9;
     const double* x = kind == 0 ? pose + (size_t)(w * bt.K + fr) * 7
-                      : kind == 1 ? sb + (size_t)(w * bt.K + fr) * 9 : bt.ex + (size_t)w * 7;
+                      : kind == 1 ? sb + (size_t)(w * bt.K + fr) * 9 : ex + (size_t)w * 7;
     if (kind == 1) {
       for (int i = 0; i < 9; i++) sdx[idx + i] = x[i] - x0[i];
     } else if (kind == 3) {
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_prepare_kernel(BaBatch bt) {
     int kind = bt.pr_kind[w * PRIOR_MAXB + bidx], fr = bt.pr_frame[w * PRIOR_MAXB + bidx];
     int idx = bt.pr_idx[w * PRIOR_MAXB + bidx];
     int loc = kind == 1 ? 9 : (kind == 3 ? 1 : 6);
-    int base = kind == 0 ? 15 * fr : (kind == 1 ? 15 * fr + 6 : -1);   // EXPOSE / TD constant here
+    int base = kind == 0 ? 15 * fr : (kind == 1 ? 15 * fr + 6 : ((kind == 2 && bt.est_ex) ? 15 * K : -1));   // TD constant
     for (int i = 0; i < loc; i++) map[idx + i] = base < 0 ? -1 : base + i;
   }
   const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
@@ -289,6 +291,7 @@ __global__ void ba_reset_kernel(BaBatch bt) {
   for (size_t k = i; k < (size_t)bt.B * bt.K * 7; k += stride) bt.pose[0][k] = bt.pose0[k];
   for (size_t k = i; k < (size_t)bt.B * bt.K * 9; k += stride) bt.sb[0][k] = bt.sb0[k];
   for (size_t k = i; k < (size_t)bt.total_L; k += stride) bt.invd[0][k] = bt.invd0[k];
+  for (size_t k = i; k < (size_t)bt.B * 7; k += stride) { bt.exs[0][k] = bt.ex[k]; bt.exs[1][k] = bt.ex[k]; }
   for (size_t k = i; k < (size_t)bt.B; k += stride) {
     BaCtrl c;
     c.cost = 0; c.cand_cost = 0; c.radius = bt.initial_radius; c.decrease_factor = 2.0;
@@ -306,6 +309,7 @@ __global__ void ba_finish_kernel(BaBatch bt) {
   const size_t np7 = (size_t)bt.K * 7, np9 = (size_t)bt.K * 9;
   for (size_t k = i; k < (size_t)bt.B * np7; k += stride) bt.pose_out[k] = bt.pose[bt.ctrl[k / np7].cur][k];
   for (size_t k = i; k < (size_t)bt.B * np9; k += stride) bt.sb_out[k] = bt.sb[bt.ctrl[k / np9].cur][k];
+  for (size_t k = i; k < (size_t)bt.B * 7; k += stride) bt.ex_out[k] = bt.exs[bt.ctrl[k / 7].cur][k];
   for (int w = blockIdx.x; w < bt.B; w += gridDim.x) {
     int cur = bt.ctrl[w].cur;
     for (int l = bt.lm_base[w] + threadIdx.x; l < bt.lm_base[w + 1]; l += blockDim.x) bt.invd_out[l] = bt.invd[cur][l];
@@ -373,7 +377,7 @@ __device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* s
   int n = bt.pr_n[w];
   double* po = bt.pr_out + (size_t)w * (bt.nmax + 1);
   if (n > 0) {
-    prior_residual(bt, w, pose, sb, sdx, spr);
+    prior_residual(bt, w, pose, sb, bt.exs[cur], sdx, spr);
     const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
     for (int a = threadIdx.x; a < n; a += blockDim.x) {
       double s = 0;
@@ -396,7 +400,10 @@ __device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* s
 //   A3  thread = landmark: LM damping of the eliminated depth, h/b/w to HBM
 //   B   thread = owner of fixed 1x6 strips of the 6K x 6K block matrix, accumulated in REGISTERS over the
 //       chunk's landmarks (fixed order => deterministic; no shared-memory accumulators, no atomics)
-template <int NS>
+// With EX (estimate_extrinsic, estimator.cpp:672-683) the extrinsic block is treated as pseudo-frame K of the
+// visual layout: every landmark "observes" it with w_ex = sum_f E_f^T c_f, and its J^T J terms are
+// (K,K) = sum_f E_f^T E_f, (K,anchor) = sum_f E_f^T A_f, (K,frame of f) = E_f^T B_f  (projection_factor.cpp:97-106).
+template <int NS, bool EX>
 __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt) {
   extern __shared__ double sm[];
   const int w = blockIdx.y, t = blockIdx.x;
@@ -405,21 +412,26 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   const int cur = ctrl->cur;
   if (t == bt.T) { imu_prior_linearize(bt, w, cur, sm); return; }
 
-  const int K = bt.K, K6 = 6 * K, NPb = K * (K + 1) / 2, FS = K - 1, CL = bt.chunk_l;
+  constexpr int SG = EX ? STGX : STG;                 // per-factor staging stride
+  constexpr int NRED = EX ? 104 : 35;                 // per-landmark reductions over the factors
+  const int K = bt.K, KE = EX ? K + 1 : K, K6 = 6 * KE, NPb = KE * (KE + 1) / 2, FS = K - 1, CL = bt.chunk_l;
   const int tid = threadIdx.x;
   double* sFr = sm;                                  // [K*FR]
   double* sEx = sFr + K * FR;                        // [FR]
   double* sRed = sEx + FR;                           // [16]
-  double* sFac = sRed + 16;                          // [CL*FS*STG]
-  double* sW = sFac + (size_t)CL * FS * STG;         // [CL*K6]
+  double* sFac = sRed + 16;                          // [CL*FS*SG]
+  double* sW = sFac + (size_t)CL * FS * SG;          // [CL*K6]
   double* sAtA = sW + (size_t)CL * K6;               // [CL*36]
   double* sgA = sAtA + (size_t)CL * 36;              // [CL*6]
   double* sSc = sgA + (size_t)CL * 6;                // [CL*4] inv_hd, b, h, -
-  int* sMeta = reinterpret_cast<int*>(sSc + (size_t)CL * 4);            // [CL*2] o0, n
-  signed char* sOidx = reinterpret_cast<signed char*>(sMeta + CL * 2);  // [CL*K] frame -> observation index
+  double* sEtE = sSc + (size_t)CL * 4;               // EX: [CL*36] sum E^T E, [CL*36] sum E^T A, [CL*6] sum E^T r
+  double* sEtA = sEtE + (EX ? (size_t)CL * 36 : 0);
+  double* sgE = sEtA + (EX ? (size_t)CL * 36 : 0);
+  int* sMeta = reinterpret_cast<int*>(sgE + (EX ? (size_t)CL * 6 : 0));  // [CL*2] o0, n
+  signed char* sOidx = reinterpret_cast<signed char*>(sMeta + CL * 2);  // [CL*KE] frame -> observation index
 
   // Units this thread owns: a unit is half a 6x6 block (3 rows x 6 columns = 18 register accumulators).
-  // Block order: the K diagonal blocks first, then the off-diagonal blocks (p > q) sorted by column q, so
+  // Block order: the KE diagonal blocks first, then the off-diagonal blocks (p > q) sorted by column q, so
   // that "q is this landmark's anchor frame" is (nearly) warp-uniform.  The last warp owns the three
   // gradient vectors instead of units.
   const int NUNIT = NPb * 2, TS = (NUNIT + NS - 1) / NS;         // TS <= BA_THREADS - 32 by choice of NS
@@ -432,10 +444,10 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
     if (tid < TS && uidx < NUNIT) {
       const int blk = uidx >> 1;
       s_r[u] = 3 * (uidx & 1);
-      if (blk < K) { s_p[u] = blk; s_q[u] = blk; }
+      if (blk < KE) { s_p[u] = blk; s_q[u] = blk; }
       else {
-        int rem = blk - K, q = 0;
-        while (rem >= K - 1 - q) { rem -= K - 1 - q; q++; }
+        int rem = blk - KE, q = 0;
+        while (rem >= KE - 1 - q) { rem -= KE - 1 - q; q++; }
         s_q[u] = q; s_p[u] = q + 1 + rem;
       }
     }
@@ -444,12 +456,12 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
 #pragma unroll
       for (int c = 0; c < 6; c++) acc[u][i][c] = 0.0;
   }
-  const bool gwarp = tid >= BA_THREADS - 32;          // gradient elements lane, lane+32, lane+64 (< 6K <= 90)
+  const bool gwarp = tid >= BA_THREADS - 32;          // gradient elements lane, lane+32, lane+64 (< 6KE <= 96)
   const int glane = tid - (BA_THREADS - 32);
   double g_red[3] = {0, 0, 0}, g_bp[3] = {0, 0, 0}, g_dg[3] = {0, 0, 0};
   double cost_t = 0, gmax_t = 0;
 
-  stage_frames(bt, w, bt.pose[cur], sFr, sEx);
+  stage_frames(bt, w, bt.pose[cur], bt.exs[cur], sFr, sEx);
   const double radius = ctrl->radius, mu = ctrl->mu;
   const int first = ctrl->first;
   const double* invd = bt.invd[cur];
@@ -459,7 +471,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   for (int lb = l0; lb < l1; lb += CL) {
     const int nl = min(CL, l1 - lb);
     __syncthreads();                                 // previous chunk fully consumed (and frames staged)
-    for (int i = tid; i < nl * K; i += BA_THREADS) sOidx[i] = -1;
+    for (int i = tid; i < nl * KE; i += BA_THREADS) sOidx[i] = (EX && (i % KE) == K) ? (signed char)K : (signed char)-1;
     __syncthreads();
     // ---- A1: factor evaluation
     {
@@ -468,12 +480,12 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
         const int l = lb + lc;
         const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0;
         const int fi = bt.obs_frame[o0];
-        if (f == 0) { sMeta[lc * 2] = o0; sMeta[lc * 2 + 1] = n; sOidx[lc * K + fi] = 0; }
+        if (f == 0) { sMeta[lc * 2] = o0; sMeta[lc * 2 + 1] = n; sOidx[lc * KE + fi] = 0; }
         if (f < n - 1) {
           const double lam = invd[l];
           const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + f];
           const int fj = bt.obs_frame[o0 + 1 + f];
-          sOidx[lc * K + fj] = (signed char)(f + 1);
+          sOidx[lc * KE + fj] = (signed char)(f + 1);
           const double* Fi = sFr + fi * FR;
           const double* Fj = sFr + fj * FR;
           ProjGeom g = proj_geom(Fi, Fj, sEx, pi.x, pi.y, lam);
@@ -494,7 +506,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
           cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
           cost_t += 0.5 * rho0;
           const double sr = sqrt(rho1);
-          double* st = sFac + (size_t)(lc * FS + f) * STG;
+          double* st = sFac + (size_t)(lc * FS + f) * SG;
           const d3 dimu = g.pimu_i - d3{sEx[9], sEx[10], sEx[11]};
           double cc[2];
 #pragma unroll
@@ -509,6 +521,37 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
             cc[a] = sr * (-dot3(u, dimu) / lam);
           }
           st[24] = cc[0]; st[25] = cc[1]; st[26] = sr * r0; st[27] = sr * r1;
+          if (EX) {
+            // extrinsic Jacobian: reduce * [ ric^T (Rj^T Ri - I) | -tmp_r [pci]x + [tmp_r pci]x + [tvec]x ]
+            // tmp_r = ric^T Rj^T Ri ric ; tvec = ric^T (Rj^T (Ri tic + Pi - Pj) - tic)  (projection_factor.cpp:100-105)
+            const d3 tic{sEx[9], sEx[10], sEx[11]};
+            const d3 pci = (1.0 / lam) * d3{pi.x, pi.y, 1.0};
+            double RjTRi[9], T1[9], tmp_r[9];
+            mtm3(Fj, Fi, RjTRi);
+            mtm3(sEx, RjTRi, T1);
+            mm3(T1, sEx, tmp_r);
+            const d3 inner = mtv3(Fj, mv3(Fi, tic) + d3{Fi[9], Fi[10], Fi[11]} - d3{Fj[9], Fj[10], Fj[11]}) - tic;
+            const d3 tvec = mtv3(sEx, inner);
+            const d3 trp = mv3(tmp_r, pci);
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+              const double rd[3] = {red[a][0], red[a][1], red[a][2]};
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                double sacc = 0;
+#pragma unroll
+                for (int k = 0; k < 3; k++) sacc += rd[k] * (T1[k * 3 + c] - sEx[c * 3 + k]);
+                st[28 + a * 6 + c] = sr * sacc;
+              }
+              const d3 rowv{rd[0], rd[1], rd[2]};
+              const d3 e1 = cross3(mtv3(tmp_r, rowv), pci);
+              const d3 e2 = cross3(rowv, trp);
+              const d3 e3 = cross3(rowv, tvec);
+              st[28 + a * 6 + 3] = sr * (-e1.x + e2.x + e3.x);
+              st[28 + a * 6 + 4] = sr * (-e1.y + e2.y + e3.y);
+              st[28 + a * 6 + 5] = sr * (-e1.z + e2.z + e3.z);
+            }
+          }
           double* wo = sW + (size_t)lc * K6 + (f + 1) * 6;
           double* wg = bt.w + (size_t)(o0 + 1 + f) * 6;
 #pragma unroll
@@ -517,23 +560,27 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
       }
     }
     __syncthreads();
-    // ---- A2: anchor reductions, 35 outputs per landmark (A^T A lower triangle 21, A^T c 6, A^T r 6, h, b),
-    //      all of the form sum_f st[p]*st[q] + st[p2]*st[q2]
-    for (int task = tid; task < nl * 35; task += BA_THREADS) {
-      const int lc = task / 35, o = task - lc * 35;
+    // ---- A2: reductions over the landmark's factors, all of the form sum_f st[p]*st[q] + st[p2]*st[q2]:
+    //      A^T A lower triangle 21, A^T c 6, A^T r 6, h, b;  EX: E^T E lower 21, E^T A 36, E^T c 6, E^T r 6
+    for (int task = tid; task < nl * NRED; task += BA_THREADS) {
+      const int lc = task / NRED, o = task - lc * NRED;
       int p, q, p2, q2;
       if (o < 21) { p = c_triA[o]; q = c_triB[o]; p2 = p + 6; q2 = q + 6; }
       else if (o < 27) { p = o - 21; q = 24; p2 = p + 6; q2 = 25; }
       else if (o < 33) { p = o - 27; q = 26; p2 = p + 6; q2 = 27; }
       else if (o == 33) { p = 24; q = 24; p2 = 25; q2 = 25; }
-      else { p = 24; q = 26; p2 = 25; q2 = 27; }
+      else if (o == 34) { p = 24; q = 26; p2 = 25; q2 = 27; }
+      else if (o < 56) { p = 28 + c_triA[o - 35]; q = 28 + c_triB[o - 35]; p2 = p + 6; q2 = q + 6; }
+      else if (o < 92) { const int i = (o - 56) / 6; p = 28 + i; q = (o - 56) - 6 * i; p2 = p + 6; q2 = q + 6; }
+      else if (o < 98) { p = 28 + (o - 92); q = 24; p2 = p + 6; q2 = 25; }
+      else { p = 28 + (o - 98); q = 26; p2 = p + 6; q2 = 27; }
       const int nf = sMeta[lc * 2 + 1] - 1;
-      const double* st = sFac + (size_t)lc * FS * STG;
+      const double* st = sFac + (size_t)lc * FS * SG;
       double s0 = 0, s1 = 0;
       int f = 0;
-      for (; f + 1 < nf; f += 2, st += 2 * STG) {
+      for (; f + 1 < nf; f += 2, st += 2 * SG) {
         s0 += st[p] * st[q] + st[p2] * st[q2];
-        s1 += st[STG + p] * st[STG + q] + st[STG + p2] * st[STG + q2];
+        s1 += st[SG + p] * st[SG + q] + st[SG + p2] * st[SG + q2];
       }
       if (f < nf) s0 += st[p] * st[q] + st[p2] * st[q2];
       const double sv = s0 + s1;
@@ -541,7 +588,11 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
       else if (o < 27) { sW[(size_t)lc * K6 + (o - 21)] = sv; bt.w[(size_t)sMeta[lc * 2] * 6 + (o - 21)] = sv; }
       else if (o < 33) sgA[lc * 6 + (o - 27)] = sv;
       else if (o == 33) sSc[lc * 4 + 2] = sv;
-      else sSc[lc * 4 + 1] = sv;
+      else if (o == 34) sSc[lc * 4 + 1] = sv;
+      else if (o < 56) { const int a = p - 28, b = q - 28; sEtE[lc * 36 + a * 6 + b] = sv; sEtE[lc * 36 + b * 6 + a] = sv; }
+      else if (o < 92) sEtA[lc * 36 + (o - 56)] = sv;
+      else if (o < 98) { sW[(size_t)lc * K6 + 6 * K + (o - 92)] = sv; bt.wex[(size_t)(lb + lc) * 6 + (o - 92)] = sv; }
+      else sgE[lc * 6 + (o - 98)] = sv;
     }
     __syncthreads();
     // ---- A3: damping of the eliminated block (Ceres LevenbergMarquardtStrategy, Jacobi scaling), outputs
@@ -565,9 +616,9 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
     // ---- B: register accumulation of sum_l (J^T J - w w^T / (h + d))
     for (int lc = 0; lc < nl; lc++) {
       const double inv = sSc[lc * 4], bl = sSc[lc * 4 + 1];
-      const signed char* oi = sOidx + lc * K;
+      const signed char* oi = sOidx + lc * KE;
       const double* W = sW + (size_t)lc * K6;
-      const double* F = sFac + (size_t)lc * FS * STG;
+      const double* F = sFac + (size_t)lc * FS * SG;
 #pragma unroll
       for (int u = 0; u < NS; u++) {
         if (s_p[u] < 0) continue;
@@ -585,7 +636,26 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
         for (int i = 0; i < 3; i++)
 #pragma unroll
           for (int c = 0; c < 6; c++) acc[u][i][c] = fma(war[i], wbv[c], acc[u][i][c]);
-        if (b == 0 && a == 0) {
+        if (EX && a == K) {
+          if (b == K || b == 0) {
+            const double* at = (b == K ? sEtE : sEtA) + lc * 36 + r0 * 6;   // sum_f E^T E / sum_f E^T A
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+              for (int c = 0; c < 6; c++) acc[u][i][c] += at[i * 6 + c];
+          } else {
+            const double* st = F + (b - 1) * SG;                             // E_f^T B_f, f = b - 1
+            double x0[3], x1[3], y0[6], y1[6];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { x0[i] = st[28 + r0 + i]; x1[i] = st[34 + r0 + i]; }
+#pragma unroll
+            for (int c = 0; c < 6; c++) { y0[c] = st[12 + c]; y1[c] = st[18 + c]; }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+              for (int c = 0; c < 6; c++) acc[u][i][c] += x0[i] * y0[c] + x1[i] * y1[c];
+          }
+        } else if (b == 0 && a == 0) {
           const double* at = sAtA + lc * 36 + r0 * 6;      // sum_f A_f^T A_f
 #pragma unroll
           for (int i = 0; i < 3; i++)
@@ -593,7 +663,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
             for (int c = 0; c < 6; c++) acc[u][i][c] += at[i * 6 + c];
         } else if (b == 0 || a == b) {
           // (a,0) -> B_a^T A_a ; (a,a) -> B_a^T B_a
-          const double* st = F + (a - 1) * STG;
+          const double* st = F + (a - 1) * SG;
           const double* sy = (b == 0) ? st : st + 12;
           double x0[3], x1[3], y0[6], y1[6];
 #pragma unroll
@@ -615,9 +685,10 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
           const int a = oi[gp];
           if (a < 0) continue;
           double gv, dv;
-          if (a == 0) { gv = sgA[lc * 6 + gr]; dv = sAtA[lc * 36 + gr * 7]; }
+          if (EX && a == K) { gv = sgE[lc * 6 + gr]; dv = sEtE[lc * 36 + gr * 7]; }
+          else if (a == 0) { gv = sgA[lc * 6 + gr]; dv = sAtA[lc * 36 + gr * 7]; }
           else {
-            const double* st = F + (a - 1) * STG;
+            const double* st = F + (a - 1) * SG;
             gv = st[12 + gr] * st[26] + st[18 + gr] * st[27];
             dv = st[12 + gr] * st[12 + gr] + st[18 + gr] * st[18 + gr];
           }
@@ -629,7 +700,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
     }
   }
   // ---- one tile record to HBM
-  double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(K);
+  double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(KE);
 #pragma unroll
   for (int u = 0; u < NS; u++) {
     if (s_p[u] < 0) continue;
@@ -658,9 +729,13 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
 // =============================================================================================
 // solve: one CTA per window
 // =============================================================================================
+// EX: the reduced system carries the 6 extrinsic dimensions after the K 15-blocks (np = 15K + 6); the last
+// Cholesky panel is then 6 wide (BW = panel width is a compile-time 15 otherwise).
+template <bool EX>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, int with_step) {
   extern __shared__ double sm[];
-  const int w = blockIdx.x, K = bt.K, np = bt.np, K6 = 6 * K, NPb = K * (K + 1) / 2;
+  const int w = blockIdx.x, K = bt.K, np = bt.np, KE = EX ? K + 1 : K, K6 = 6 * KE, NPb = KE * (KE + 1) / 2;
+  const int NB = KE;                               // diagonal panels of the blocked Cholesky
   const int tid = threadIdx.x, nthr = blockDim.x;
   BaCtrl* ctrl = bt.ctrl + w;
   if (ctrl->done) return;
@@ -676,7 +751,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
   double* tv = dinv + np;                         // [np] dogleg: scaled gradient direction t
   __shared__ int s_fail;
   const int REC = NPb * 36 + 3 * K6;
-  const int TREC = tile_rec_doubles(K);
+  const int TREC = tile_rec_doubles(KE);
   const double* tiles = bt.tile_out + (size_t)w * bt.T * TREC;
   const double* imo = bt.imu_out + (size_t)w * K * IMU_OUT;
   const int n = bt.pr_n[w];
@@ -725,7 +800,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
       }
     }
     if (p + 1 < K) { const double* o = imo + (size_t)(p + 1) * IMU_OUT; g1 += o[465 + r]; g2 += o[465 + r]; d += o[tri(r, r)]; }
-    if (p >= 1) { const double* o = imo + (size_t)p * IMU_OUT; g1 += o[465 + 15 + r]; g2 += o[465 + 15 + r]; d += o[tri(15 + r, 15 + r)]; }
+    if (p >= 1 && p < K) { const double* o = imo + (size_t)p * IMU_OUT; g1 += o[465 + 15 + r]; g2 += o[465 + 15 + r]; d += o[tri(15 + r, 15 + r)]; }
     for (int a = 0; a < n; a++)
       if (map[a] == i) { g1 += po[a]; g2 += po[a]; d += pH[(size_t)a * bt.nmax + a]; }
     bp[i] = g1; gr[i] = g2; dH[i] = d;
@@ -811,20 +886,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
   }
   __syncthreads();
   // blocked Cholesky (15-wide panels) of the augmented matrix: the last row becomes y = L^-1 (-g)
-  for (int kb = 0; kb < K; kb++) {
+  for (int kb = 0; kb < NB; kb++) {
     const int j0 = 15 * kb;
+    const int bw = EX ? min(15, np - j0) : 15;
     if (tid < 32) {
-      // 15 x 15 diagonal block in registers: lane i holds row i, column j broadcast by shuffles
+      // bw x bw diagonal block in registers: lane i holds row i, column j broadcast by shuffles
       double a[15];
 #pragma unroll
-      for (int k = 0; k < 15; k++) a[k] = (tid < 15 && k <= tid) ? S[tri(j0 + tid, j0 + k)] : 0.0;
+      for (int k = 0; k < 15; k++) a[k] = (tid < bw && k <= tid) ? S[tri(j0 + tid, j0 + k)] : 0.0;
       bool bad = false;
 #pragma unroll
       for (int j = 0; j < 15; j++) {
-        const double pj = __shfl_sync(0xffffffffu, a[j], j);
+        double pj = __shfl_sync(0xffffffffu, a[j], j);
+        if (EX && j >= bw) pj = 1.0;
         bad |= !(pj > 0.0);
         const double inv = rsqrt(pj);
-        if (tid == j) dinv[j0 + j] = inv;          // 1 / L_jj for the panel and the back substitution
+        if (tid == j && j < bw) dinv[j0 + j] = inv;   // 1 / L_jj for the panel and the back substitution
         a[j] *= inv;
 #pragma unroll
         for (int k = j + 1; k < 15; k++) {
@@ -832,7 +909,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
           a[k] = fma(-a[j], lkj, a[k]);
         }
       }
-      if (tid < 15) {
+      if (tid < bw) {
 #pragma unroll
         for (int k = 0; k < 15; k++) if (k <= tid) S[tri(j0 + tid, j0 + k)] = a[k];
       }
@@ -841,11 +918,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
     __syncthreads();
     if (s_fail) break;
     // panel: rows below the diagonal block (incl. the augmented row)
-    for (int i = j0 + 15 + tid; i <= np; i += nthr) {
+    for (int i = j0 + bw + tid; i <= np; i += nthr) {
       double x[15];
       double* row = S + tri(i, j0);
 #pragma unroll
       for (int c = 0; c < 15; c++) {
+        if (EX && c >= bw) { x[c] = 0.0; continue; }
         double v = row[c];
         const double* lr = S + tri(j0 + c, j0);
 #pragma unroll
@@ -853,11 +931,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
         x[c] = v * dinv[j0 + c];
       }
 #pragma unroll
-      for (int c = 0; c < 15; c++) row[c] = x[c];
+      for (int c = 0; c < 15; c++) if (!EX || c < bw) row[c] = x[c];
     }
     __syncthreads();
     // trailing update
-    const int r0 = j0 + 15, mrows = np + 1 - r0;
+    const int r0 = j0 + bw, mrows = np + 1 - r0;
     // 4 x 4 register tiles of the lower triangle: 120 shared loads feed 240 FMAs
     const int mt = (mrows + 3) >> 2, ntile = mt * (mt + 1) / 2;
     for (int tix = tid; tix < ntile; tix += nthr) {
@@ -877,6 +955,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
         for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
 #pragma unroll
       for (int c = 0; c < 15; c++) {
+        if (EX && c >= bw) break;
         double av[4], bv[4];
 #pragma unroll
         for (int a = 0; a < 4; a++) { av[a] = ri[a][c]; bv[a] = rk[a][c]; }
@@ -902,29 +981,30 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
   // back substitution L^T dp = y (warp 0)
   for (int i = tid; i < np; i += nthr) yv[i] = S[tri(np, i)];
   __syncthreads();
-  // blocked: per 15-block one warp solves L_kk^T x = y_k in registers (lane d holds column d of L_kk),
+  // blocked: per panel one warp solves L_kk^T x = y_k in registers (lane d holds column d of L_kk),
   // then all threads eliminate x from the rows above
-  for (int kb = K - 1; kb >= 0; kb--) {
+  for (int kb = NB - 1; kb >= 0; kb--) {
     const int j0 = 15 * kb;
+    const int bw = EX ? min(15, np - j0) : 15;
     if (tid < 32) {
       double col[15];
 #pragma unroll
-      for (int k = 0; k < 15; k++) col[k] = (tid < 15 && k >= tid) ? S[tri(j0 + k, j0 + tid)] : 1.0;
-      double y = tid < 15 ? yv[j0 + tid] : 0.0;
-      const double di = tid < 15 ? dinv[j0 + tid] : 1.0;
+      for (int k = 0; k < 15; k++) col[k] = (tid < bw && k >= tid && k < bw) ? S[tri(j0 + k, j0 + tid)] : (k == tid ? 1.0 : 0.0);
+      double y = tid < bw ? yv[j0 + tid] : 0.0;
+      const double di = tid < bw ? dinv[j0 + tid] : 1.0;
 #pragma unroll
       for (int c = 14; c >= 0; c--) {
         const double xc = __shfl_sync(0xffffffffu, y * di, c);
         if (tid == c) y = xc;
         else if (tid < c) y = fma(-col[c], xc, y);
       }
-      if (tid < 15) yv[j0 + tid] = y;
+      if (tid < bw) yv[j0 + tid] = y;
     }
     __syncthreads();
     for (int k = tid; k < j0; k += nthr) {
       double v = yv[k];
 #pragma unroll
-      for (int c = 0; c < 15; c++) v = fma(-S[tri(j0 + c, k)], yv[j0 + c], v);
+      for (int c = 0; c < 15; c++) if (!EX || c < bw) v = fma(-S[tri(j0 + c, k)], yv[j0 + c], v);
       yv[k] = v;
     }
     __syncthreads();
@@ -1039,6 +1119,11 @@ __global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
 #pragma unroll
       for (int k = 0; k < 6; k++) { wn += wp[k] * sn[15 * fr + k]; wt += wp[k] * st[15 * fr + k]; }
     }
+    if (bt.est_ex && l16 == 0) {
+      const double* wp = bt.wex + (size_t)l * 6;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { wn += wp[k] * sn[15 * bt.K + k]; wt += wp[k] * st[15 * bt.K + k]; }
+    }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) { wn += __shfl_xor_sync(gmask, wn, o, 16); wt += __shfl_xor_sync(gmask, wt, o, 16); }
     if (l16 == 0) {
@@ -1120,8 +1205,8 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
   }
   const int cur = ctrl->cur, nxt = cur ^ 1;
   double* sdp = sm;                 // [np]
-  double* sPose = sdp + np;         // [K*7] candidate poses
-  double* sFr = sPose + K * 7;      // [K*FR]
+  double* sPose = sdp + np;         // [(K+1)*7] candidate poses, then the (candidate) extrinsic pose
+  double* sFr = sPose + (K + 1) * 7;   // [K*FR]
   double* sEx = sFr + K * FR;       // [FR]
   double* red = sEx + FR;           // [16*4 + 32]
   double* extra = red + 96;         // IMU/prior CTA scratch
@@ -1134,13 +1219,16 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
     sdp[i] = d;
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x)
-    pose_plus(bt.pose[cur] + (size_t)(w * K + k) * 7, sdp + 15 * k, sPose + k * 7);
+  for (int k = threadIdx.x; k <= K; k += blockDim.x) {
+    if (k < K) pose_plus(bt.pose[cur] + (size_t)(w * K + k) * 7, sdp + 15 * k, sPose + k * 7);
+    else if (bt.est_ex) pose_plus(bt.exs[cur] + (size_t)w * 7, sdp + 15 * K, sPose + K * 7);
+    else for (int i = 0; i < 7; i++) sPose[K * 7 + i] = bt.exs[cur][(size_t)w * 7 + i];
+  }
   __syncthreads();
   double* co = bt.cost_out + (size_t)(w * (bt.T + 1) + t) * COST_REC;
   if (t < bt.T) {
     for (int k = threadIdx.x; k <= K; k += blockDim.x) {
-      const double* p = (k < K) ? sPose + k * 7 : bt.ex + (size_t)w * 7;
+      const double* p = sPose + k * 7;
       double* o = (k < K) ? sFr + k * FR : sEx;
       qmat(q4{p[3], p[4], p[5], p[6]}, o);
       o[9] = p[0]; o[10] = p[1]; o[11] = p[2];
@@ -1164,6 +1252,11 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
           const double* d = sdp + 15 * myfr;
 #pragma unroll
           for (int k = 0; k < 6; k++) part += wp[k] * d[k];
+          if (bt.est_ex && l16 == 0) {
+            const double* we = bt.wex + (size_t)l * 6;
+#pragma unroll
+            for (int k = 0; k < 6; k++) part += we[k] * sdp[15 * K + k];
+          }
         }
       }
       if (!dogleg) {
@@ -1218,6 +1311,10 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       double v = sPose[i], o = pc[i];
       pn[i] = v; s2 += (o - v) * (o - v); x2 += o * o;
     }
+    if (bt.est_ex && threadIdx.x < 7) {
+      double v = sPose[K * 7 + threadIdx.x], o = bt.exs[cur][(size_t)w * 7 + threadIdx.x];
+      bt.exs[nxt][(size_t)w * 7 + threadIdx.x] = v; s2 += (o - v) * (o - v); x2 += o * o;
+    }
     for (int i = threadIdx.x; i < K * 9; i += blockDim.x) {
       int k = i / 9, r = i - k * 9;
       double o = sc[i], v = o + sdp[15 * k + 6 + r];
@@ -1252,7 +1349,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       // written to the nxt buffers by this CTA
       __threadfence_block();
       __syncthreads();
-      prior_residual(bt, w, bt.pose[nxt], bt.sb[nxt], sdx, spr);
+      prior_residual(bt, w, bt.pose[nxt], bt.sb[nxt], bt.exs[nxt], sdx, spr);
       for (int i = threadIdx.x; i < n; i += blockDim.x) c += 0.5 * spr[i] * spr[i];
     }
     c = block_sum(c, red);
@@ -1286,25 +1383,25 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
 // =============================================================================================
 static size_t imu_prior_smem(int K, int nmax) { return sizeof(double) * ((size_t)(K - 1) * (900 + 30) + 2 * nmax); }
 
-size_t ba_linearize_smem_bytes(int K, int CL) {
-  const int FS = K - 1;
-  size_t d = (size_t)(K + 1) * FR + 16 + (size_t)CL * (FS * STG + 6 * K + 36 + 6 + 4);
-  size_t bytes = d * sizeof(double) + (size_t)CL * 2 * sizeof(int) + (size_t)CL * K;
+size_t ba_linearize_smem_bytes(int K, int CL, int est_ex) {
+  const int FS = K - 1, KE = est_ex ? K + 1 : K;
+  size_t d = (size_t)(K + 1) * FR + 16 + (size_t)CL * (FS * (est_ex ? STGX : STG) + 6 * KE + 36 + 6 + 4 + (est_ex ? 78 : 0));
+  size_t bytes = d * sizeof(double) + (size_t)CL * 2 * sizeof(int) + (size_t)CL * KE;
   return (bytes + 15) & ~size_t(15);
 }
 // landmarks per chunk: one (landmark, factor) slot per thread, capped so that two CTAs fit an SM
-int ba_pick_chunk(int K) {
+int ba_pick_chunk(int K, int est_ex) {
   int CL = BA_THREADS / (K - 1);
   if (CL > 64) CL = 64;
-  while (CL > 1 && ba_linearize_smem_bytes(K, CL) > 100 * 1024) CL--;
+  while (CL > 1 && ba_linearize_smem_bytes(K, CL, est_ex) > 100 * 1024) CL--;
   return CL;
 }
-size_t ba_solve_smem_bytes(int K) {
-  int np = 15 * K, N1 = np + 1;
+size_t ba_solve_smem_bytes(int np) {
+  int N1 = np + 1;
   return sizeof(double) * ((size_t)N1 * (N1 + 1) / 2 + 7 * np + 32);
 }
 static size_t cost_smem(int K, int nmax) {
-  return sizeof(double) * ((size_t)15 * K + K * 7 + (K + 1) * FR + 96 + K * 9 + (K - 1) * 15 + 2 * nmax);
+  return sizeof(double) * ((size_t)15 * K + 6 + (K + 1) * 7 + (K + 1) * FR + 96 + K * 9 + (K - 1) * 15 + 2 * nmax);
 }
 
 static bool g_tables_done = false;
@@ -1321,11 +1418,13 @@ int ba_configure(void) {
     if ((err = cudaMemcpyToSymbol(c_triB, tb, sizeof tb)) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_tri30A, ua, sizeof ua)) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_tri30B, ub, sizeof ub)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return err;
+#define BVIO_LIN_ATTR(NS, EX) \
+    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<NS, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
+    BVIO_LIN_ATTR(1, false) BVIO_LIN_ATTR(2, false) BVIO_LIN_ATTR(3, false) BVIO_LIN_ATTR(4, false)
+    BVIO_LIN_ATTR(1, true) BVIO_LIN_ATTR(2, true) BVIO_LIN_ATTR(3, true) BVIO_LIN_ATTR(4, true)
+#undef BVIO_LIN_ATTR
+    if ((err = cudaFuncSetAttribute(ba_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
     g_tables_done = true;
   }
@@ -1346,16 +1445,23 @@ int ba_launch_reset(const BaBatch& bt, cudaStream_t st) {
   return 1;
 }
 int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cudaEvent_t* ev) {
-  size_t s1 = ba_linearize_smem_bytes(bt.K, bt.chunk_l), s1b = imu_prior_smem(bt.K, bt.nmax);
+  size_t s1 = ba_linearize_smem_bytes(bt.K, bt.chunk_l, bt.est_ex), s1b = imu_prior_smem(bt.K, bt.nmax);
   if (s1b > s1) s1 = s1b;
   if (ev) cudaEventRecord(ev[0], st);
-  const int nstrip = (bt.K * (bt.K + 1) / 2) * 2;   // half-block units
-  if (nstrip <= BA_THREADS - 32) ba_linearize_kernel<1><<<dim3(bt.T + 1, bt.B), BA_THREADS, s1, st>>>(bt);
-  else if (nstrip <= 2 * (BA_THREADS - 32)) ba_linearize_kernel<2><<<dim3(bt.T + 1, bt.B), BA_THREADS, s1, st>>>(bt);
-  else if (nstrip <= 3 * (BA_THREADS - 32)) ba_linearize_kernel<3><<<dim3(bt.T + 1, bt.B), BA_THREADS, s1, st>>>(bt);
-  else ba_linearize_kernel<4><<<dim3(bt.T + 1, bt.B), BA_THREADS, s1, st>>>(bt);
+  const int KE = bt.est_ex ? bt.K + 1 : bt.K;
+  const int nstrip = (KE * (KE + 1) / 2) * 2;   // half-block units
+  const dim3 grid(bt.T + 1, bt.B);
+#define BVIO_LIN(NS) \
+  { if (bt.est_ex) ba_linearize_kernel<NS, true><<<grid, BA_THREADS, s1, st>>>(bt); \
+    else ba_linearize_kernel<NS, false><<<grid, BA_THREADS, s1, st>>>(bt); }
+  if (nstrip <= BA_THREADS - 32) BVIO_LIN(1)
+  else if (nstrip <= 2 * (BA_THREADS - 32)) BVIO_LIN(2)
+  else if (nstrip <= 3 * (BA_THREADS - 32)) BVIO_LIN(3)
+  else BVIO_LIN(4)
+#undef BVIO_LIN
   if (ev) cudaEventRecord(ev[1], st);
-  ba_solve_kernel<<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.K), st>>>(bt, with_step ? 1 : 0);
+  if (bt.est_ex) ba_solve_kernel<true><<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.np), st>>>(bt, with_step ? 1 : 0);
+  else ba_solve_kernel<false><<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.np), st>>>(bt, with_step ? 1 : 0);
   if (!with_step || bt.undamped) { if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); } return 2; }
   int nk = 3;
   if (bt.strategy) {   // dogleg combination; its time is booked with the reduced solve
@@ -1427,7 +1533,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
     double* sS = sG + VD;                   // [2] h, b
     int* sFj = reinterpret_cast<int*>(sS + 2);   // [KMAX]
     int* sFof = sFj + BVIO_KMAX;                 // [KMAX+1] frame -> factor index of this landmark
-    stage_frames(bt, w, bt.pose0, sFr, sEx);
+    stage_frames(bt, w, bt.pose0, bt.ex, sFr, sEx);
     constexpr int NE = 12;                  // owned entries per thread: VD*VD <= 96*96 = 9216 <= 512*18
     double acc[18];
 #pragma unroll
@@ -1608,7 +1714,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         for (int i = 0; i < loc; i++) pmap[idx + i] = base < 0 ? -1 : base + i;
       }
       __syncthreads();
-      prior_residual(bt, w, bt.pose0, bt.sb0, sdx, spr);
+      prior_residual(bt, w, bt.pose0, bt.sb0, bt.ex, sdx, spr);
       const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
       for (int e = tid; e < np_ * np_; e += nt) {
         int a = e / np_, c = e - a * np_;

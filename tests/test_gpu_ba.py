@@ -18,11 +18,21 @@ def env(pkg, oracle):
     ctx.close()
 
 
-def _linearize_both(env, w):
+def _perturb_extrinsic(synth, w, seed, sigma_t=0.02, sigma_r=0.01):
+    """Window copy whose camera-IMU extrinsics are off by (2 cm, 0.6 deg): something for ESTIMATE_EXTRINSIC to fix."""
+    rng = np.random.default_rng(1000 + seed)
+    w = w.copy()
+    w.para_ex_pose[:3] += rng.normal(0, sigma_t, 3)
+    q = synth.quat_mul(w.para_ex_pose[3:], np.concatenate([0.5 * rng.normal(0, sigma_r, 3), [1.0]]))
+    w.para_ex_pose[3:] = q / np.linalg.norm(q)
+    return w
+
+
+def _linearize_both(env, w, **opts_kw):
     abi, synth, orc, ctx = env
-    o = abi.default_opts()
+    o = abi.default_opts(**opts_kw)
     h1, h2 = abi.WindowHandle(w), abi.WindowHandle(w)
-    np_ = 15 * w.K
+    np_ = 15 * w.K + (6 if opts_kw.get("estimate_extrinsic") else 0)
     L = w.L
     out = {}
     for name, fn, hh in (("gpu", None, h1), ("cpu", orc.oracle_linearize, h2)):
@@ -137,6 +147,50 @@ def test_dogleg_converged_state_matches_oracle(env, seed, K, L):
     assert abs(sg.final_cost - sl.final_cost) <= 1e-6 * sl.final_cost
 
 
+@pytest.mark.parametrize("seed,K,L,prior", [(0, 11, 150, "frame0"), (1, 11, 150, "none"), (2, 2, 20, "none"),
+                                            (3, 5, 37, "frame0"), (4, 11, 1500, "frame0"), (5, 14, 64, "frame0")])
+def test_extrinsic_linearize_matches_oracle(env, seed, K, L, prior):
+    """ESTIMATE_EXTRINSIC (estimator.cpp:672-683): para_Ex_Pose is a free block; the reduced system carries the
+    extrinsic Jacobian of every ProjectionFactor (projection_factor.cpp:97-106) in its last 6 rows / columns."""
+    abi, synth, orc, ctx = env
+    kw = dict(track_min=2, track_max=2) if K == 2 else {}
+    w = _perturb_extrinsic(synth, synth.make_window(seed=seed, K=K, L=L, prior=prior, **kw), seed)
+    r = _linearize_both(env, w, estimate_extrinsic=1)
+    (S1, g1, h1, b1, c1), (S2, g2, h2, b2, c2) = r["gpu"], r["cpu"]
+    assert np.isfinite(S1).all() and S1.shape == (15 * K + 6, 15 * K + 6)
+    assert np.abs(S2[15 * K:, :]).max() > 0
+    assert abs(c1 - c2) <= 1e-11 * abs(c2)
+    assert np.abs(h1 - h2).max() <= 1e-11 * np.abs(h2).max()
+    assert np.abs(S1 - S2).max() <= 1e-9 * np.abs(S2).max()
+    assert np.abs(g1 - g2).max() <= 1e-9 * max(np.abs(g2).max(), 1.0)
+    assert np.abs(S1 - S1.T).max() == 0.0
+
+
+@pytest.mark.parametrize("seed,strategy", [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1), (2, 1)])
+def test_extrinsic_converged_state_matches_oracle(env, seed, strategy):
+    abi, synth, orc, ctx = env
+    w0 = synth.make_window(seed=seed, K=11, L=150)
+    w = _perturb_extrinsic(synth, w0, seed)
+    hg, ho, sg, so = _solve_both(env, w, dict(estimate_extrinsic=1, strategy=strategy, **TIGHT))
+    xg, xo = hg.state_vector(), ho.state_vector()
+    assert np.linalg.norm(xg - xo) <= 1e-6 * np.linalg.norm(xo), (sg.as_dict(), so.as_dict())
+    assert np.linalg.norm(hg.ex - ho.ex) <= 1e-6 * np.linalg.norm(ho.ex)
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    # the extrinsic block is really free (t_ic is only weakly observable over a 1 s window, so no claim on where it goes)
+    assert np.linalg.norm(hg.ex - w.para_ex_pose) > 1e-4
+
+
+@pytest.mark.parametrize("seed,strategy", [(10, 0), (11, 0), (10, 1), (11, 1)])
+def test_extrinsic_reference_budget_trajectory(env, seed, strategy):
+    abi, synth, orc, ctx = env
+    w = _perturb_extrinsic(synth, synth.make_window(seed=seed, K=11, L=150), seed)
+    hg, ho, sg, so = _solve_both(env, w, dict(estimate_extrinsic=1, strategy=strategy))
+    assert (sg.iterations, sg.num_accepted, sg.num_rejected, sg.termination) == \
+           (so.iterations, so.num_accepted, so.num_rejected, so.termination), (sg.as_dict(), so.as_dict())
+    xg, xo = hg.state_vector(), ho.state_vector()
+    assert np.linalg.norm(xg - xo) <= 1e-8 * np.linalg.norm(xo)
+
+
 def test_stress_window_1500_features(env):
     """BASELINE config 3: 11-kf / 1500-feature window."""
     abi, synth, orc, ctx = env
@@ -193,5 +247,8 @@ def test_rejects_unsupported_and_invalid(env):
     s = abi.Summary()
     assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(estimate_td=1)), C.byref(s)) == -4
     assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(strategy=7)), C.byref(s)) == -1
+    w15 = synth.make_window(seed=0, K=15, L=10)
+    h15 = abi.WindowHandle(w15)
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h15.s), C.byref(abi.default_opts(estimate_extrinsic=1)), C.byref(s)) == -1
     h.frame[1] = h.frame[0]   # not strictly ascending
     assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts()), C.byref(s)) == -1
