@@ -62,6 +62,7 @@ struct BaBatch {                  // all pointers are device pointers
   // solver options
   int max_iters, jacobi_scaling;
   int strategy;                   // BVIO_STRATEGY_LM / BVIO_STRATEGY_DOGLEG
+  int use_mma;                    // linearize with the FP64 tensor-core (DMMA) kernel (extrinsics fixed)
   int est_ex;                     // estimate_extrinsic: np = 15K + 6, extrinsic block = pseudo-frame K
   double sqrt_info, cauchy_a, G[3];
   double function_tolerance, gradient_tolerance, parameter_tolerance, initial_radius, min_relative_decrease;
@@ -115,6 +116,7 @@ int ba_launch_finish(const BaBatch& bt, cudaStream_t st);
 size_t ba_linearize_smem_bytes(int K, int chunk_l, int est_ex);
 int ba_pick_chunk(int K, int est_ex);
 size_t ba_solve_smem_bytes(int np);
+size_t ba_linearize_mma_smem_bytes(int K);
 size_t ba_marginalize_smem_bytes(int K, int nmax, int n);
 int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, const int* dropidx, const int* keepidx, double* A,
                           double* b, double* out_jac, double* out_res, int* status, cudaStream_t st);

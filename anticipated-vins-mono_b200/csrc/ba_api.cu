@@ -21,6 +21,7 @@ struct bvio_batch {
   size_t out_off = 0, out_bytes = 0;   // [out_off, out_off+out_bytes): outputs, mirrored on the host
   size_t o_pose_out = 0, o_sb_out = 0, o_invd_out = 0, o_ex_out = 0, o_ctrl = 0;
   std::vector<int> lm_base;
+  std::vector<int> perm;          // [total_L] device landmark -> caller landmark (within its window)
   cudaGraphExec_t graph = nullptr;
   bool use_graph = true;
   int launches_per_solve = 0;
@@ -157,6 +158,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   const int est_ex = o->estimate_extrinsic != 0, KE = est_ex ? K + 1 : K;
   bt.B = B; bt.K = K; bt.np = 15 * K + (est_ex ? 6 : 0); bt.total_L = total_L; bt.total_obs = total_obs; bt.nmax = nmax;
   bt.est_ex = est_ex;
+  bt.use_mma = !est_ex && !getenv("BVIO_LEGACY_LINEARIZE");
   bt.chunk_l = ba_pick_chunk(K, est_ex);
   int T = (maxL + 2 * bt.chunk_l - 1) / (2 * bt.chunk_l);   // >= 2 chunks per tile when there is a choice
   int Tcap = std::max(1, (2 * ctx->sm_count + B - 1) / B);
@@ -249,6 +251,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   double* h_pr_jac = (double*)(h + o_pr_jac);
   double* h_pr_res = (double*)(h + o_pr_res);
   bb->lm_base.resize(B + 1);
+  bb->perm.resize(total_L);
   std::vector<int> obs_base(B + 1);
   {
     int lb0 = 0, ob0 = 0;
@@ -263,16 +266,28 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
     const bvio_window& w = ws[b];
     const int lb = bb->lm_base[b], ob = obs_base[b];
     h_lm_base[b] = lb;
-    int nobs = w.L ? w.lm_obs_offset[w.L] : 0;
-    for (int l = 0; l < w.L; l++) h_lm_off[lb + l] = ob + w.lm_obs_offset[l];
-    if (nobs) {
-      memcpy(h_obs_frame + ob, w.obs_frame, nobs * I);
-      memcpy(h_obs_xy + (size_t)2 * ob, w.obs_xy, (size_t)nobs * 2 * D);
+    // device order: landmarks grouped by anchor frame (stable counting sort).  FeatureManager's list is
+    // already in this order (features are appended as they are first seen); ba_linearize_mma walks the
+    // anchors present in a chunk, so grouped input keeps that loop at 1-2 trips.  perm[device] = caller index.
+    int* perm = bb->perm.data() + lb;
+    {
+      int cnt[BVIO_KMAX + 1] = {0};
+      for (int l = 0; l < w.L; l++) cnt[w.obs_frame[w.lm_obs_offset[l]] + 1]++;
+      for (int f = 0; f < BVIO_KMAX; f++) cnt[f + 1] += cnt[f];
+      for (int l = 0; l < w.L; l++) perm[cnt[w.obs_frame[w.lm_obs_offset[l]]]++] = l;
+    }
+    int run = ob;
+    for (int j = 0; j < w.L; j++) {
+      const int l = perm[j], o0 = w.lm_obs_offset[l], n = w.lm_obs_offset[l + 1] - o0;
+      h_lm_off[lb + j] = run;
+      memcpy(h_obs_frame + run, w.obs_frame + o0, n * I);
+      memcpy(h_obs_xy + (size_t)2 * run, w.obs_xy + (size_t)2 * o0, (size_t)n * 2 * D);
+      run += n;
     }
     memcpy(h_pose0 + (size_t)b * K * 7, w.para_pose, (size_t)K * 7 * D);
     memcpy(h_sb0 + (size_t)b * K * 9, w.para_speed_bias, (size_t)K * 9 * D);
     memcpy(h_ex + (size_t)b * 7, w.para_ex_pose, 7 * D);
-    if (w.L) memcpy(h_invd0 + lb, w.inv_depth, (size_t)w.L * D);
+    for (int j = 0; j < w.L; j++) h_invd0[lb + j] = w.inv_depth[perm[j]];
     memcpy(h_pre + (size_t)b * K * PREINT_DOUBLES, w.preint, (size_t)K * sizeof(bvio_preint));
     h_pr_n[b] = 0; h_pr_nb[b] = 0;
     if (w.prior) {
@@ -402,7 +417,8 @@ int bvio_batch_download(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, bvi
       memcpy(w.para_pose, pose + (size_t)b * bt.K * 7, (size_t)bt.K * 7 * sizeof(double));
       memcpy(w.para_speed_bias, sb + (size_t)b * bt.K * 9, (size_t)bt.K * 9 * sizeof(double));
       int L = bb->lm_base[b + 1] - bb->lm_base[b];
-      if (L) memcpy(w.inv_depth, invd + bb->lm_base[b], (size_t)L * sizeof(double));
+      const int* perm = bb->perm.data() + bb->lm_base[b];
+      for (int j = 0; j < L; j++) w.inv_depth[perm[j]] = invd[bb->lm_base[b] + j];
       if (bt.est_ex) memcpy(w.para_ex_pose, exo + (size_t)b * 7, 7 * sizeof(double));
     }
     const BaCtrl& c = ctrl[b];
@@ -454,8 +470,15 @@ int bvio_debug_linearize(bvio_ctx* ctx, const bvio_window* window, const bvio_op
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess && S) e = cudaMemcpy(S, bt.dbg_S, sizeof(double) * bt.np * bt.np, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && g) e = cudaMemcpy(g, bt.dbg_g, sizeof(double) * bt.np, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && h && bt.total_L) e = cudaMemcpy(h, bt.h, sizeof(double) * bt.total_L, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && b && bt.total_L) e = cudaMemcpy(b, bt.b, sizeof(double) * bt.total_L, cudaMemcpyDeviceToHost);
+  std::vector<double> tmp(bt.total_L);
+  if (e == cudaSuccess && h && bt.total_L) {
+    e = cudaMemcpy(tmp.data(), bt.h, sizeof(double) * bt.total_L, cudaMemcpyDeviceToHost);
+    for (int j = 0; j < bt.total_L; j++) h[bb->perm[j]] = tmp[j];
+  }
+  if (e == cudaSuccess && b && bt.total_L) {
+    e = cudaMemcpy(tmp.data(), bt.b, sizeof(double) * bt.total_L, cudaMemcpyDeviceToHost);
+    for (int j = 0; j < bt.total_L; j++) b[bb->perm[j]] = tmp[j];
+  }
   if (e == cudaSuccess && cost) {
     BaCtrl c;
     e = cudaMemcpy(&c, bt.ctrl, sizeof c, cudaMemcpyDeviceToHost);

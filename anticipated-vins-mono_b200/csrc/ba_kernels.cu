@@ -727,6 +727,329 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
 }
 
 // =============================================================================================
+// linearize, FP64 tensor-core variant (default when the extrinsics are fixed).
+//
+// Same factor evaluation (A1) as above, but (i) a chunk is a run of landmarks holding <= 256 FACTORS, one
+// factor per thread, so no lane idles on a short track, and (ii) every accumulation into the 6K x 6K block
+// matrix is a small dense Gram product issued as mma.sync.m8n8k4.f64 (DMMA: the same IEEE double FMAs as
+// DFMA at 1/8 of the issue slots -- this kernel was issue-bound, not FP64-pipe-bound):
+//   P1   S -= W~^T W~        W~ [landmark][6K+1]: sqrt(1/(h+d)) w_l scattered to frame positions, zero where
+//                            unobserved, last column beta_l = b_l sqrt(1/(h+d)) => row 6K of the product is the
+//                            Schur correction of the gradient.  Lower 8x8 tiles spread over the 8 warps.
+//   P2a  (p,p) += X_p^T X_p  X_p = rows [B_f | r_f] of the factors observed in frame p (column 6 => sum B^T r)
+//   P2b  (p,q) += B^T A      over the landmarks anchored at q that are seen in p
+//   AtA  (q,q) += Y^T Y      Y = rows [A_f | r_f] of all factors anchored at q, split-K over the warps
+// P1/P2a live in registers across chunks, P2b/AtA go to a shared-memory copy of the tile record each chunk
+// (single owner per element, fixed order => bit-reproducible).  Landmarks are expected grouped by anchor
+// frame (FeatureManager's list order); any order is correct, grouped is fast (the q loop has 1-2 trips).
+// =============================================================================================
+constexpr int MM_NF = BA_THREADS;   // factor slots per chunk
+constexpr int MM_CL = 40;           // landmarks per chunk (multiple of 4)
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__host__ __device__ inline int mm_ntile(int K) { return (6 * K + 1 + 7) / 8; }
+__host__ __device__ inline int mm_wstride(int K) { int ws = 8 * mm_ntile(K); return (ws % 16 == 0) ? ws + 8 : ws; }
+
+template <int TM>
+__global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch bt) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.y, t = blockIdx.x;
+  BaCtrl* ctrl = bt.ctrl + w;
+  if (ctrl->done) return;
+  const int cur = ctrl->cur;
+  if (t == bt.T) { imu_prior_linearize(bt, w, cur, sm); return; }
+
+  const int K = bt.K, K6 = 6 * K, NPb = K * (K + 1) / 2, NT = mm_ntile(K), WS = mm_wstride(K);
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, g = lane >> 2, tq = lane & 3;
+  double* sFr = sm;                                  // [K*FR]
+  double* sEx = sFr + K * FR;                        // [FR]
+  double* sRed = sEx + FR;                           // [16]
+  double* sFac = sRed + 16;                          // [MM_NF*STG] A(12) B(12) c(2) r(2) per factor
+  double* sW = sFac + MM_NF * STG;                   // [MM_CL*WS]
+  double* sSc = sW + MM_CL * WS;                     // [MM_CL*4] sqrt(1/(h+d)), b, h, beta
+  double* sAcc = sSc + MM_CL * 4;                    // [NPb*36] the tile record's blocks
+  double* sGb = sAcc + NPb * 36;                     // [K6] sum J^T r (unreduced gradient)
+  double* sGr = sGb + K6;                            // [K6] Schur correction of the gradient
+  double* sDg = sGr + K6;                            // [K6] diag of the unreduced H_pp
+  double* sPart = sDg + K6;                          // [8*64] split-K partial tiles of AtA
+  int* sFirst = reinterpret_cast<int*>(sPart + 8 * 64);   // [MM_CL] first factor slot of the landmark
+  int* sNobs = sFirst + MM_CL;                       // [MM_CL]
+  int* sO0 = sNobs + MM_CL;                          // [MM_CL] first observation (global index)
+  int* sAnc = sO0 + MM_CL;                           // [MM_CL] anchor frame
+  int* sMask = sAnc + MM_CL;                         // [2] bit q set: some landmark of the chunk is anchored at q
+  short* sSlot = reinterpret_cast<short*>(sMask + 2);             // [MM_CL*K] frame -> factor slot, -1 unobserved, -2 anchor
+  unsigned char* sFl = reinterpret_cast<unsigned char*>(sSlot + MM_CL * K + (MM_CL * K & 1));   // [MM_NF] slot -> landmark
+  unsigned char* sFp = sFl + MM_NF;                  // [MM_NF] slot -> frame
+
+  // P1 tiles of this warp: lower-triangular tile index wp + 8 s
+  const int ntile = NT * (NT + 1) / 2;
+  int ti[TM], tj[TM];
+  double accW[TM][2];
+#pragma unroll
+  for (int s = 0; s < TM; s++) {
+    int idx = wp + 8 * s, i = 0;
+    ti[s] = -1; tj[s] = 0;
+    if (idx < ntile) {
+      while ((i + 1) * (i + 2) / 2 <= idx) i++;
+      ti[s] = i; tj[s] = idx - i * (i + 1) / 2;
+    }
+    accW[s][0] = accW[s][1] = 0.0;
+  }
+  // P2a: frames wp and wp + 8
+  double accD[2][2] = {{0, 0}, {0, 0}};
+  double cost_t = 0, gmax_t = 0;
+
+  for (int i = tid; i < NPb * 36 + 3 * K6; i += BA_THREADS) sAcc[i] = 0.0;
+  stage_frames(bt, w, bt.pose[cur], bt.exs[cur], sFr, sEx);
+  const double radius = ctrl->radius, mu = ctrl->mu;
+  const int first = ctrl->first;
+  const double* invd = bt.invd[cur];
+  int l0, l1;
+  tile_range(bt, w, t, l0, l1);
+
+  for (int lb = l0; lb < l1;) {
+    // ---- chunk extent: as many landmarks as fit MM_NF factor slots (and MM_CL rows)
+    const int obase = bt.lm_off[lb];
+    int pred = 0;
+    if (tid >= 1 && tid <= MM_CL && lb + tid <= l1) pred = (bt.lm_off[lb + tid] - obase - tid) <= MM_NF;
+    const int nl = __syncthreads_count(pred);        // also: previous chunk fully consumed, frames staged
+    const int nfac = bt.lm_off[lb + nl] - obase - nl;
+    const int nl4 = (nl + 3) & ~3;
+    for (int i = tid; i < nl4 * WS; i += BA_THREADS) sW[i] = 0.0;
+    for (int i = tid; i < nl * K; i += BA_THREADS) sSlot[i] = -1;
+    if (tid < 2) sMask[tid] = 0;
+    __syncthreads();
+    // ---- A0: slot tables
+    if (tid < nl) {
+      const int l = lb + tid;
+      const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0, fs = (o0 - obase) - tid;
+      const int fi = bt.obs_frame[o0];
+      sFirst[tid] = fs; sNobs[tid] = n; sO0[tid] = o0; sAnc[tid] = fi;
+      sSlot[tid * K + fi] = -2;
+      for (int k = 1; k < n; k++) {
+        const int fj = bt.obs_frame[o0 + k], slot = fs + k - 1;
+        sSlot[tid * K + fj] = (short)slot;
+        sFl[slot] = (unsigned char)tid; sFp[slot] = (unsigned char)fj;
+      }
+      atomicOr(&sMask[0], 1 << fi);
+    }
+    __syncthreads();
+    // ---- A1: factor evaluation, one factor per thread
+    if (tid < nfac) {
+      const int lc = sFl[tid], fj = sFp[tid], l = lb + lc;
+      const int o0 = sO0[lc], fi = sAnc[lc], ko = o0 + 1 + (tid - sFirst[lc]);
+      const double lam = invd[l];
+      const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[ko];
+      const double* Fi = sFr + fi * FR;
+      const double* Fj = sFr + fj * FR;
+      ProjGeom gm = proj_geom(Fi, Fj, sEx, pi.x, pi.y, lam);
+      const double inv = 1.0 / gm.pcj.z, si = bt.sqrt_info;
+      const double r0 = si * (gm.pcj.x * inv - pj.x), r1 = si * (gm.pcj.y * inv - pj.y);
+      const double red[2][3] = {{si * inv, 0.0, -si * gm.pcj.x * inv * inv}, {0.0, si * inv, -si * gm.pcj.y * inv * inv}};
+      double Gm[2][3], Q[2][3];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          Gm[a][c] = red[a][0] * sEx[c * 3 + 0] + red[a][1] * sEx[c * 3 + 1] + red[a][2] * sEx[c * 3 + 2];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) Q[a][c] = Gm[a][0] * Fj[c * 3 + 0] + Gm[a][1] * Fj[c * 3 + 1] + Gm[a][2] * Fj[c * 3 + 2];
+      double rho0, rho1;
+      cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
+      cost_t += 0.5 * rho0;
+      const double sr = sqrt(rho1);
+      double* st = sFac + (size_t)tid * STG;
+      const d3 dimu = gm.pimu_i - d3{sEx[9], sEx[10], sEx[11]};
+      double cc[2];
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+        const d3 u = mtv3(Fi, d3{Q[a][0], Q[a][1], Q[a][2]});              // Ri^T Q[a]^T
+        const d3 jr = cross3(gm.pimu_i, u);                                // -(Q Ri [pts_imu_i]x) row
+        const d3 jjr = cross3(d3{Gm[a][0], Gm[a][1], Gm[a][2]}, gm.pimu_j); // (Gm [pts_imu_j]x) row
+        st[a * 6 + 0] = sr * Q[a][0]; st[a * 6 + 1] = sr * Q[a][1]; st[a * 6 + 2] = sr * Q[a][2];
+        st[a * 6 + 3] = sr * jr.x; st[a * 6 + 4] = sr * jr.y; st[a * 6 + 5] = sr * jr.z;
+        st[12 + a * 6 + 0] = -sr * Q[a][0]; st[12 + a * 6 + 1] = -sr * Q[a][1]; st[12 + a * 6 + 2] = -sr * Q[a][2];
+        st[12 + a * 6 + 3] = sr * jjr.x; st[12 + a * 6 + 4] = sr * jjr.y; st[12 + a * 6 + 5] = sr * jjr.z;
+        cc[a] = sr * (-dot3(u, dimu) / lam);
+      }
+      st[24] = cc[0]; st[25] = cc[1]; st[26] = sr * r0; st[27] = sr * r1;
+      double* wo = sW + lc * WS + 6 * fj;
+      double* wg = bt.w + (size_t)ko * 6;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { const double v = st[12 + k] * cc[0] + st[18 + k] * cc[1]; wo[k] = v; wg[k] = v; }
+    }
+    __syncthreads();
+    // ---- A2: per landmark  A^T c (6: the anchor's w), h = sum c^T c, b = sum c^T r
+    for (int task = tid; task < nl * 8; task += BA_THREADS) {
+      const int lc = task >> 3, o = task & 7;
+      const int p = o < 6 ? o : 24, q = o < 7 ? 24 : 26;
+      const int nf = sNobs[lc] - 1;
+      const double* st = sFac + (size_t)sFirst[lc] * STG;
+      double s0 = 0, s1 = 0;
+      int f = 0;
+      for (; f + 1 < nf; f += 2, st += 2 * STG) {
+        s0 += st[p] * st[q] + st[p + (o < 6 ? 6 : 1)] * st[q + 1];
+        s1 += st[STG + p] * st[STG + q] + st[STG + p + (o < 6 ? 6 : 1)] * st[STG + q + 1];
+      }
+      if (f < nf) s0 += st[p] * st[q] + st[p + (o < 6 ? 6 : 1)] * st[q + 1];
+      const double sv = s0 + s1;
+      if (o < 6) { sW[lc * WS + 6 * sAnc[lc] + o] = sv; bt.w[(size_t)sO0[lc] * 6 + o] = sv; }
+      else if (o == 6) sSc[lc * 4 + 2] = sv;
+      else sSc[lc * 4 + 1] = sv;
+    }
+    __syncthreads();
+    // ---- A3: damping of the eliminated depth (Ceres LevenbergMarquardtStrategy / dogleg mu, Jacobi scaling)
+    if (tid < nl) {
+      const int l = lb + tid;
+      const double h = sSc[tid * 4 + 2], b = sSc[tid * 4 + 1];
+      double sl2 = 1.0;
+      if (bt.jacobi_scaling) {
+        if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
+        else sl2 = bt.sl2[l];
+      }
+      const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, radius, mu, bt.strategy);
+      double inv_hd = 1.0 / (h + ddl);
+      if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
+      const double sq = sqrt(inv_hd);
+      sSc[tid * 4] = sq; sSc[tid * 4 + 3] = b * sq;
+      gmax_t = fmax(gmax_t, fabs(b));
+      bt.h[l] = h; bt.b[l] = b;
+      if (first) bt.sl2[l] = sl2;
+    }
+    __syncthreads();
+    for (int e = tid; e < nl * (K6 + 1); e += BA_THREADS) {
+      const int lc = e / (K6 + 1), d = e - lc * (K6 + 1);
+      if (d < K6) sW[lc * WS + d] *= sSc[lc * 4];
+      else sW[lc * WS + K6] = sSc[lc * 4 + 3];
+    }
+    __syncthreads();
+    // ---- AtA(q) partials first (their reduction overlaps the other products)
+    const unsigned amask = (unsigned)sMask[0];
+    int nq = 0;
+    for (int q = 0; q < K; q++) {
+      if (!((amask >> q) & 1u)) continue;
+      if (nq++ > 0) __syncthreads();                 // sPart reused
+      double c0 = 0, c1 = 0;
+      for (int ks = wp; 2 * ks < nfac; ks += 8) {
+        const int slot = 2 * ks + (tq >> 1), row = tq & 1;
+        double x = 0.0;
+        if (slot < nfac && g < 7 && sAnc[sFl[slot]] == q) x = sFac[(size_t)slot * STG + (g < 6 ? 6 * row + g : 26 + row)];
+        dmma884(c0, c1, x, x);
+      }
+      sPart[wp * 64 + g * 8 + 2 * tq] = c0; sPart[wp * 64 + g * 8 + 2 * tq + 1] = c1;
+      __syncthreads();
+      if (tid < 64) {
+        const int m = tid >> 3, n = tid & 7;
+        double sacc = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sacc += sPart[k * 64 + tid];
+        if (m < 6 && n < 6) {
+          sAcc[tri(q, q) * 36 + m * 6 + n] += sacc;
+          if (m == n) sDg[6 * q + m] += sacc;
+        } else if (m == 6 && n < 6) sGb[6 * q + n] += sacc;
+      }
+      // ---- P2b: blocks (p, q), p > q, one warp per p
+      for (int p = q + 1 + wp; p < K; p += 8) {
+        double d0 = 0, d1 = 0;
+        for (int ks = 0; 2 * ks < nl; ks++) {
+          const int lc = 2 * ks + (tq >> 1), row = tq & 1;
+          double xa = 0.0, xb = 0.0;
+          if (lc < nl && g < 6 && sAnc[lc] == q) {
+            const int slot = sSlot[lc * K + p];
+            if (slot >= 0) { const double* st = sFac + (size_t)slot * STG + 6 * row + g; xa = st[12]; xb = st[0]; }
+          }
+          dmma884(d0, d1, xa, xb);
+        }
+        if (g < 6 && tq < 3) {
+          double* o = sAcc + tri(p, q) * 36 + g * 6 + 2 * tq;
+          o[0] += d0; o[1] += d1;
+        }
+      }
+    }
+    // ---- P1: S -= W~^T W~ (register tiles)
+    for (int ks = 0; ks < nl4; ks += 4) {
+      const double* wr = sW + (ks + tq) * WS + g;
+#pragma unroll
+      for (int s = 0; s < TM; s++) {
+        if (ti[s] < 0) continue;
+        dmma884(accW[s][0], accW[s][1], wr[8 * ti[s]], wr[8 * tj[s]]);
+      }
+    }
+    // ---- P2a: diagonal blocks (p, p) from the factors seen in frame p (non-anchor side)
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int p = wp + 8 * u;
+      if (p >= K) continue;
+      for (int ks = 0; 2 * ks < nl; ks++) {
+        const int lc = 2 * ks + (tq >> 1), row = tq & 1;
+        double x = 0.0;
+        if (lc < nl && g < 7) {
+          const int slot = sSlot[lc * K + p];
+          if (slot >= 0) x = sFac[(size_t)slot * STG + (g < 6 ? 12 + 6 * row + g : 26 + row)];
+        }
+        dmma884(accD[u][0], accD[u][1], x, x);
+      }
+    }
+    lb += nl;
+  }
+  // ---- fold the register tiles into the shared record (single owner per element in each phase)
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    const int p = wp + 8 * u;
+    if (p >= K) continue;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int m = g, n = 2 * tq + e;
+      const double v = accD[u][e];
+      if (m < 6 && n < 6) {
+        sAcc[tri(p, p) * 36 + m * 6 + n] += v;
+        if (m == n) sDg[6 * p + m] += v;
+      } else if (m == 6 && n < 6) sGb[6 * p + n] += v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < TM; s++) {
+    if (ti[s] < 0) continue;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int r = 8 * ti[s] + g, c = 8 * tj[s] + 2 * tq + e;
+      if (c >= K6 || c > r) continue;
+      if (r < K6) sAcc[tri(r / 6, c / 6) * 36 + (r % 6) * 6 + (c % 6)] -= accW[s][e];
+      else if (r == K6) sGr[c] = accW[s][e];
+    }
+  }
+  __syncthreads();
+  // ---- one tile record to HBM
+  double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(K);
+  for (int i = tid; i < NPb * 36; i += BA_THREADS) out[i] = sAcc[i];
+  for (int i = tid; i < K6; i += BA_THREADS) {
+    out[NPb * 36 + i] = sGb[i] - sGr[i];
+    out[NPb * 36 + K6 + i] = sGb[i];
+    out[NPb * 36 + 2 * K6 + i] = sDg[i];
+  }
+  const double c = block_sum(cost_t, sRed);
+  const double gmx = block_max(gmax_t, sRed + 8);
+  if (tid == 0) {
+    const int REC = NPb * 36 + 3 * K6;
+    out[REC] = c; out[REC + 1] = gmx; out[REC + 2] = 0; out[REC + 3] = 0;
+  }
+}
+
+size_t ba_linearize_mma_smem_bytes(int K) {
+  const int NPb = K * (K + 1) / 2, WS = mm_wstride(K);
+  size_t d = (size_t)(K + 1) * FR + 16 + (size_t)MM_NF * STG + (size_t)MM_CL * WS + MM_CL * 4 + (size_t)NPb * 36 + 18 * K + 8 * 64;
+  size_t bytes = d * sizeof(double) + (size_t)(4 * MM_CL + 2) * sizeof(int) + (size_t)(MM_CL * K + 1) * sizeof(short) + 2 * MM_NF;
+  return (bytes + 15) & ~size_t(15);
+}
+
+// =============================================================================================
 // solve: one CTA per window
 // =============================================================================================
 // EX: the reduced system carries the 6 extrinsic dimensions after the K 15-blocks (np = 15K + 6); the last
@@ -1423,6 +1746,8 @@ int ba_configure(void) {
     BVIO_LIN_ATTR(1, false) BVIO_LIN_ATTR(2, false) BVIO_LIN_ATTR(3, false) BVIO_LIN_ATTR(4, false)
     BVIO_LIN_ATTR(1, true) BVIO_LIN_ATTR(2, true) BVIO_LIN_ATTR(3, true) BVIO_LIN_ATTR(4, true)
 #undef BVIO_LIN_ATTR
+    if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
@@ -1454,7 +1779,14 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
 #define BVIO_LIN(NS) \
   { if (bt.est_ex) ba_linearize_kernel<NS, true><<<grid, BA_THREADS, s1, st>>>(bt); \
     else ba_linearize_kernel<NS, false><<<grid, BA_THREADS, s1, st>>>(bt); }
-  if (nstrip <= BA_THREADS - 32) BVIO_LIN(1)
+  if (bt.use_mma) {
+    size_t sm1 = ba_linearize_mma_smem_bytes(bt.K);
+    if (s1b > sm1) sm1 = s1b;
+    const int NT = mm_ntile(bt.K);
+    if (NT * (NT + 1) / 2 <= 48) ba_linearize_mma_kernel<6><<<grid, BA_THREADS, sm1, st>>>(bt);
+    else ba_linearize_mma_kernel<10><<<grid, BA_THREADS, sm1, st>>>(bt);
+  }
+  else if (nstrip <= BA_THREADS - 32) BVIO_LIN(1)
   else if (nstrip <= 2 * (BA_THREADS - 32)) BVIO_LIN(2)
   else if (nstrip <= 3 * (BA_THREADS - 32)) BVIO_LIN(3)
   else BVIO_LIN(4)
