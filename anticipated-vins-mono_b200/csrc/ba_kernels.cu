@@ -779,9 +779,10 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
   int* sNobs = sFirst + MM_CL;                       // [MM_CL]
   int* sO0 = sNobs + MM_CL;                          // [MM_CL] first observation (global index)
   int* sAnc = sO0 + MM_CL;                           // [MM_CL] anchor frame
-  int* sMask = sAnc + MM_CL;                         // [2] bit q set: some landmark of the chunk is anchored at q
-  short* sSlot = reinterpret_cast<short*>(sMask + 2);             // [MM_CL*K] frame -> factor slot, -1 unobserved, -2 anchor
-  unsigned char* sFl = reinterpret_cast<unsigned char*>(sSlot + MM_CL * K + (MM_CL * K & 1));   // [MM_NF] slot -> landmark
+  int* sQlo = sAnc + MM_CL;                          // [BVIO_KMAX] first / one-past-last landmark of the chunk anchored
+  int* sQhi = sQlo + BVIO_KMAX;                      // [BVIO_KMAX] at frame q (landmarks arrive grouped by anchor)
+  short* sSlot = reinterpret_cast<short*>(sQhi + BVIO_KMAX);      // [(MM_CL+2)*K] frame -> factor slot, -1 unobserved, -2 anchor
+  unsigned char* sFl = reinterpret_cast<unsigned char*>(sSlot + (MM_CL + 2) * K + ((MM_CL + 2) * K & 1));   // [MM_NF] slot -> landmark
   unsigned char* sFp = sFl + MM_NF;                  // [MM_NF] slot -> frame
 
   // P1 tiles of this warp: lower-triangular tile index wp + 8 s
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
     ti[s] = -1; tj[s] = 0;
     if (idx < ntile) {
       while ((i + 1) * (i + 2) / 2 <= idx) i++;
-      ti[s] = i; tj[s] = idx - i * (i + 1) / 2;
+      ti[s] = 8 * i; tj[s] = 8 * (idx - i * (i + 1) / 2);   // column offsets of the tile's row / column fragment
     }
     accW[s][0] = accW[s][1] = 0.0;
   }
@@ -819,8 +820,8 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
     const int nfac = bt.lm_off[lb + nl] - obase - nl;
     const int nl4 = (nl + 3) & ~3;
     for (int i = tid; i < nl4 * WS; i += BA_THREADS) sW[i] = 0.0;
-    for (int i = tid; i < nl * K; i += BA_THREADS) sSlot[i] = -1;
-    if (tid < 2) sMask[tid] = 0;
+    for (int i = tid; i < (nl + 2) * K; i += BA_THREADS) sSlot[i] = -1;   // two pad rows: pair loops need no bound check
+    if (tid < BVIO_KMAX) { sQlo[tid] = MM_CL; sQhi[tid] = 0; }
     __syncthreads();
     // ---- A0: slot tables
     if (tid < nl) {
@@ -834,7 +835,8 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
         sSlot[tid * K + fj] = (short)slot;
         sFl[slot] = (unsigned char)tid; sFp[slot] = (unsigned char)fj;
       }
-      atomicOr(&sMask[0], 1 << fi);
+      atomicMin(&sQlo[fi], tid);
+      atomicMax(&sQhi[fi], tid + 1);
     }
     __syncthreads();
     // ---- A1: factor evaluation, one factor per thread
@@ -884,64 +886,73 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
       for (int k = 0; k < 6; k++) { const double v = st[12 + k] * cc[0] + st[18 + k] * cc[1]; wo[k] = v; wg[k] = v; }
     }
     __syncthreads();
-    // ---- A2: per landmark  A^T c (6: the anchor's w), h = sum c^T c, b = sum c^T r
+    // ---- A2: per landmark  A^T c (6 tasks: the anchor's w) and one task for h = sum c^T c, b = sum c^T r with the
+    //      damping of the eliminated depth (Ceres LevenbergMarquardtStrategy / dogleg mu, Jacobi scaling)
     for (int task = tid; task < nl * 8; task += BA_THREADS) {
       const int lc = task >> 3, o = task & 7;
-      const int p = o < 6 ? o : 24, q = o < 7 ? 24 : 26;
+      if (o == 7) continue;
       const int nf = sNobs[lc] - 1;
       const double* st = sFac + (size_t)sFirst[lc] * STG;
-      double s0 = 0, s1 = 0;
-      int f = 0;
-      for (; f + 1 < nf; f += 2, st += 2 * STG) {
-        s0 += st[p] * st[q] + st[p + (o < 6 ? 6 : 1)] * st[q + 1];
-        s1 += st[STG + p] * st[STG + q] + st[STG + p + (o < 6 ? 6 : 1)] * st[STG + q + 1];
+      if (o < 6) {
+        double s0 = 0, s1 = 0;
+        int f = 0;
+        for (; f + 1 < nf; f += 2, st += 2 * STG) {
+          s0 += st[o] * st[24] + st[o + 6] * st[25];
+          s1 += st[STG + o] * st[STG + 24] + st[STG + o + 6] * st[STG + 25];
+        }
+        if (f < nf) s0 += st[o] * st[24] + st[o + 6] * st[25];
+        const double sv = s0 + s1;
+        sW[lc * WS + 6 * sAnc[lc] + o] = sv; bt.w[(size_t)sO0[lc] * 6 + o] = sv;
+      } else {
+        double h = 0, b = 0;
+        for (int f = 0; f < nf; f++, st += STG) {
+          h += st[24] * st[24] + st[25] * st[25];
+          b += st[24] * st[26] + st[25] * st[27];
+        }
+        const int l = lb + lc;
+        double sl2 = 1.0;
+        if (bt.jacobi_scaling) {
+          if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
+          else sl2 = bt.sl2[l];
+        }
+        const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, radius, mu, bt.strategy);
+        double inv_hd = 1.0 / (h + ddl);
+        if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
+        const double sq = sqrt(inv_hd);
+        sSc[lc * 4] = sq; sSc[lc * 4 + 3] = b * sq;
+        gmax_t = fmax(gmax_t, fabs(b));
+        bt.h[l] = h; bt.b[l] = b;
+        if (first) bt.sl2[l] = sl2;
       }
-      if (f < nf) s0 += st[p] * st[q] + st[p + (o < 6 ? 6 : 1)] * st[q + 1];
-      const double sv = s0 + s1;
-      if (o < 6) { sW[lc * WS + 6 * sAnc[lc] + o] = sv; bt.w[(size_t)sO0[lc] * 6 + o] = sv; }
-      else if (o == 6) sSc[lc * 4 + 2] = sv;
-      else sSc[lc * 4 + 1] = sv;
     }
     __syncthreads();
-    // ---- A3: damping of the eliminated depth (Ceres LevenbergMarquardtStrategy / dogleg mu, Jacobi scaling)
-    if (tid < nl) {
-      const int l = lb + tid;
-      const double h = sSc[tid * 4 + 2], b = sSc[tid * 4 + 1];
-      double sl2 = 1.0;
-      if (bt.jacobi_scaling) {
-        if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
-        else sl2 = bt.sl2[l];
-      }
-      const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, radius, mu, bt.strategy);
-      double inv_hd = 1.0 / (h + ddl);
-      if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
-      const double sq = sqrt(inv_hd);
-      sSc[tid * 4] = sq; sSc[tid * 4 + 3] = b * sq;
-      gmax_t = fmax(gmax_t, fabs(b));
-      bt.h[l] = h; bt.b[l] = b;
-      if (first) bt.sl2[l] = sl2;
-    }
-    __syncthreads();
-    for (int e = tid; e < nl * (K6 + 1); e += BA_THREADS) {
-      const int lc = e / (K6 + 1), d = e - lc * (K6 + 1);
-      if (d < K6) sW[lc * WS + d] *= sSc[lc * 4];
-      else sW[lc * WS + K6] = sSc[lc * 4 + 3];
+    // ---- scale: W~ = sqrt(1/(h+d)) w, beta in column 6K
+    for (int lc = wp; lc < nl; lc += 8) {
+      const double sq = sSc[lc * 4];
+      double* wr = sW + lc * WS;
+      for (int d = lane; d < K6; d += 32) wr[d] *= sq;
+      if (lane == 0) wr[K6] = sSc[lc * 4 + 3];
     }
     __syncthreads();
     // ---- AtA(q) partials first (their reduction overlaps the other products)
-    const unsigned amask = (unsigned)sMask[0];
     int nq = 0;
     for (int q = 0; q < K; q++) {
-      if (!((amask >> q) & 1u)) continue;
+      const int lq0 = sQlo[q], lq1 = sQhi[q];
+      if (lq1 <= lq0) continue;
       if (nq++ > 0) __syncthreads();                 // sPart reused
-      double c0 = 0, c1 = 0;
-      for (int ks = wp; 2 * ks < nfac; ks += 8) {
-        const int slot = 2 * ks + (tq >> 1), row = tq & 1;
-        double x = 0.0;
-        if (slot < nfac && g < 7 && sAnc[sFl[slot]] == q) x = sFac[(size_t)slot * STG + (g < 6 ? 6 * row + g : 26 + row)];
-        dmma884(c0, c1, x, x);
+      {
+        // factor slots of the landmarks anchored at q are contiguous: [f0, f1)
+        const int f0 = sFirst[lq0], f1 = sFirst[lq1 - 1] + sNobs[lq1 - 1] - 1;
+        const int goff = (g < 6 ? 6 * (tq & 1) + g : 26 + (tq & 1));
+        double c0 = 0, c1 = 0;
+        for (int sb = (f0 & ~1) + 2 * wp; sb < f1; sb += 16) {   // warp-uniform trip count (mma.sync)
+          const int slot = sb + (tq >> 1);
+          double x = 0.0;
+          if (slot >= f0 && slot < f1 && g < 7) x = sFac[(size_t)slot * STG + goff];
+          dmma884(c0, c1, x, x);
+        }
+        sPart[wp * 64 + g * 8 + 2 * tq] = c0; sPart[wp * 64 + g * 8 + 2 * tq + 1] = c1;
       }
-      sPart[wp * 64 + g * 8 + 2 * tq] = c0; sPart[wp * 64 + g * 8 + 2 * tq + 1] = c1;
       __syncthreads();
       if (tid < 64) {
         const int m = tid >> 3, n = tid & 7;
@@ -953,16 +964,15 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
           if (m == n) sDg[6 * q + m] += sacc;
         } else if (m == 6 && n < 6) sGb[6 * q + n] += sacc;
       }
-      // ---- P2b: blocks (p, q), p > q, one warp per p
-      for (int p = q + 1 + wp; p < K; p += 8) {
+      // ---- P2b: blocks (p, q), p > q, one warp per p (warps taken from the top: P2a loads the low warps)
+      for (int p = q + 1 + (7 - wp); p < K; p += 8) {
         double d0 = 0, d1 = 0;
-        for (int ks = 0; 2 * ks < nl; ks++) {
-          const int lc = 2 * ks + (tq >> 1), row = tq & 1;
+        const short* sl = sSlot + (lq0 + (tq >> 1)) * K + p;
+        const int roff = 6 * (tq & 1) + g;
+        for (int lc = lq0; lc < lq1; lc += 2, sl += 2 * K) {
           double xa = 0.0, xb = 0.0;
-          if (lc < nl && g < 6 && sAnc[lc] == q) {
-            const int slot = sSlot[lc * K + p];
-            if (slot >= 0) { const double* st = sFac + (size_t)slot * STG + 6 * row + g; xa = st[12]; xb = st[0]; }
-          }
+          const int slot = *sl;
+          if (slot >= 0 && g < 6 && lc + (tq >> 1) < lq1) { const double* st = sFac + (size_t)slot * STG + roff; xa = st[12]; xb = st[0]; }
           dmma884(d0, d1, xa, xb);
         }
         if (g < 6 && tq < 3) {
@@ -977,7 +987,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
 #pragma unroll
       for (int s = 0; s < TM; s++) {
         if (ti[s] < 0) continue;
-        dmma884(accW[s][0], accW[s][1], wr[8 * ti[s]], wr[8 * tj[s]]);
+        dmma884(accW[s][0], accW[s][1], wr[ti[s]], wr[tj[s]]);
       }
     }
     // ---- P2a: diagonal blocks (p, p) from the factors seen in frame p (non-anchor side)
@@ -985,13 +995,12 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
     for (int u = 0; u < 2; u++) {
       const int p = wp + 8 * u;
       if (p >= K) continue;
-      for (int ks = 0; 2 * ks < nl; ks++) {
-        const int lc = 2 * ks + (tq >> 1), row = tq & 1;
+      const short* sl = sSlot + (tq >> 1) * K + p;
+      const int goff = (g < 6 ? 12 + 6 * (tq & 1) + g : 26 + (tq & 1));
+      for (int lc = 0; lc < nl; lc += 2, sl += 2 * K) {
         double x = 0.0;
-        if (lc < nl && g < 7) {
-          const int slot = sSlot[lc * K + p];
-          if (slot >= 0) x = sFac[(size_t)slot * STG + (g < 6 ? 12 + 6 * row + g : 26 + row)];
-        }
+        const int slot = *sl;                         // rows nl, nl+1 are padding (-1)
+        if (slot >= 0 && g < 7) x = sFac[(size_t)slot * STG + goff];
         dmma884(accD[u][0], accD[u][1], x, x);
       }
     }
@@ -1019,7 +1028,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
     if (ti[s] < 0) continue;
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const int r = 8 * ti[s] + g, c = 8 * tj[s] + 2 * tq + e;
+      const int r = ti[s] + g, c = tj[s] + 2 * tq + e;
       if (c >= K6 || c > r) continue;
       if (r < K6) sAcc[tri(r / 6, c / 6) * 36 + (r % 6) * 6 + (c % 6)] -= accW[s][e];
       else if (r == K6) sGr[c] = accW[s][e];
@@ -1045,7 +1054,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
 size_t ba_linearize_mma_smem_bytes(int K) {
   const int NPb = K * (K + 1) / 2, WS = mm_wstride(K);
   size_t d = (size_t)(K + 1) * FR + 16 + (size_t)MM_NF * STG + (size_t)MM_CL * WS + MM_CL * 4 + (size_t)NPb * 36 + 18 * K + 8 * 64;
-  size_t bytes = d * sizeof(double) + (size_t)(4 * MM_CL + 2) * sizeof(int) + (size_t)(MM_CL * K + 1) * sizeof(short) + 2 * MM_NF;
+  size_t bytes = d * sizeof(double) + (size_t)(4 * MM_CL + 2 * BVIO_KMAX) * sizeof(int) + (size_t)((MM_CL + 2) * K + 1) * sizeof(short) + 2 * MM_NF;
   return (bytes + 15) & ~size_t(15);
 }
 
@@ -1427,13 +1436,14 @@ __global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
   }
   __syncthreads();
   const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15, NG = blockDim.x >> 4;
-  const unsigned gmask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+  const unsigned gmask = 0xffffffffu;   // both half-warps always iterate together (warp-uniform trip count)
   const double mu = ctrl->mu;
-  const int cur = ctrl->cur;
   int l0, l1;
   tile_range(bt, w, t, l0, l1);
   double a[6] = {0, 0, 0, 0, 0, 0};
-  for (int l = l0 + grp; l < l1; l += NG) {
+  for (int lw = l0 + (grp & ~1); lw < l1; lw += NG) {
+    const bool act = lw + (grp & 1) < l1;
+    const int l = act ? lw + (grp & 1) : l1 - 1;      // the idle half-warp shadows a valid landmark, results dropped
     const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0;
     double wn = 0, wt = 0;
     if (l16 < n) {
@@ -1449,7 +1459,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) { wn += __shfl_xor_sync(gmask, wn, o, 16); wt += __shfl_xor_sync(gmask, wt, o, 16); }
-    if (l16 == 0) {
+    if (l16 == 0 && act) {
       const double h = bt.h[l], b = bt.b[l];
       const double sl2 = bt.jacobi_scaling ? bt.sl2[l] : 1.0;
       const double cl = fmin(fmax(sl2 * h, 1e-6), 1e32);
@@ -1558,12 +1568,14 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
     }
     __syncthreads();
     const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15, NG = blockDim.x >> 4;
-    const unsigned gmask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+    const unsigned gmask = 0xffffffffu;   // both half-warps always iterate together (warp-uniform trip count)
     const double radius = ctrl->radius;
     int l0, l1;
     tile_range(bt, w, t, l0, l1);
     double a_cost = 0, a_model = 0, a_s2 = 0, a_x2 = 0;
-    for (int l = l0 + grp; l < l1; l += NG) {
+    for (int lw = l0 + (grp & ~1); lw < l1; lw += NG) {
+      const bool act = lw + (grp & 1) < l1;
+      const int l = act ? lw + (grp & 1) : l1 - 1;    // the idle half-warp shadows a valid landmark, results dropped
       const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0;
       const double lam = bt.invd[cur][l], h = bt.h[l], b = bt.b[l];
       int myfr = 0;
@@ -1604,7 +1616,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       }
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) fc += __shfl_xor_sync(gmask, fc, o, 16);
-      if (l16 == 0) {
+      if (l16 == 0 && act) {
         bt.invd[nxt][l] = lamc;
         a_cost += fc;
         if (!dogleg) a_model += -0.5 * b * dl + 0.5 * ddl * dl * dl;
