@@ -73,9 +73,9 @@ __device__ __forceinline__ ProjGeom proj_geom(const double* Fi, const double* Fj
 // Diagonal regularisation of one column with Jacobi scale^2 = s2 and clamped scaled diagonal `cl`:
 //   LM      (LevenbergMarquardtStrategy): D^2 = cl / radius          -> unscaled cl / (radius s2)
 //   dogleg  (DoglegStrategy GN step)    : D^2 = mu * cl              -> unscaled mu cl / s2
-__device__ __forceinline__ double damp_term(double cl, double s2, double radius, double mu, int dogleg) {
-  return dogleg ? mu * cl / s2 : cl / (radius * s2);
-}
+// One division per call: the strategy-dependent factor (mu or 1/radius) is formed once per thread.
+__device__ __forceinline__ double damp_factor(double radius, double mu, int dogleg) { return dogleg ? mu : 1.0 / radius; }
+__device__ __forceinline__ double damp_term(double cl, double s2, double dfac) { return dfac * cl / s2; }
 
 __device__ __forceinline__ void cauchy(double a, double s, double& rho0, double& rho1) {
   double bb = a * a, c = 1.0 / bb;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   double cost_t = 0, gmax_t = 0;
 
   stage_frames(bt, w, bt.pose[cur], bt.exs[cur], sFr, sEx);
-  const double radius = ctrl->radius, mu = ctrl->mu;
+  const double dfac = damp_factor(ctrl->radius, ctrl->mu, bt.strategy);
   const int first = ctrl->first;
   const double* invd = bt.invd[cur];
   int l0, l1;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
         if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
         else sl2 = bt.sl2[l];
       }
-      const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, radius, mu, bt.strategy);
+      const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, dfac);
       double inv_hd = 1.0 / (h + ddl);
       if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
       sSc[tid * 4] = inv_hd;
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
 
   for (int i = tid; i < NPb * 36 + 3 * K6; i += BA_THREADS) sAcc[i] = 0.0;
   stage_frames(bt, w, bt.pose[cur], bt.exs[cur], sFr, sEx);
-  const double radius = ctrl->radius, mu = ctrl->mu;
+  const double dfac = damp_factor(ctrl->radius, ctrl->mu, bt.strategy);
   const int first = ctrl->first;
   const double* invd = bt.invd[cur];
   int l0, l1;
@@ -915,7 +915,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
           if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
           else sl2 = bt.sl2[l];
         }
-        const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, radius, mu, bt.strategy);
+        const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, dfac);
         double inv_hd = 1.0 / (h + ddl);
         if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
         const double sq = sqrt(inv_hd);
@@ -1181,7 +1181,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
     return;
   }
   const int dogleg = bt.strategy;
-  const double mu = ctrl->mu;
+  const double dfac = damp_factor(radius, ctrl->mu, dogleg);
   auto scale2 = [&](int i) {
     const double sp = first ? (bt.jacobi_scaling ? 1.0 / (1.0 + sqrt(dH[i])) : 1.0) : bt.scale_p[(size_t)w * np + i];
     return sp * sp;
@@ -1211,7 +1211,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
   // damping + augmented row
   for (int i = tid; i < np; i += nthr) {
     double sp2 = scale2(i);
-    double d = damp_term(fmin(fmax(sp2 * dH[i], 1e-6), 1e32), sp2, radius, mu, dogleg);
+    double d = damp_term(fmin(fmax(sp2 * dH[i], 1e-6), 1e32), sp2, dfac);
     ddp[i] = d;
     S[tri(i, i)] += d;
     S[tri(np, i)] = -gr[i];
@@ -1569,7 +1569,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
     __syncthreads();
     const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15, NG = blockDim.x >> 4;
     const unsigned gmask = 0xffffffffu;   // both half-warps always iterate together (warp-uniform trip count)
-    const double radius = ctrl->radius;
+    const double dfac = damp_factor(ctrl->radius, mu, dogleg);
     int l0, l1;
     tile_range(bt, w, t, l0, l1);
     double a_cost = 0, a_model = 0, a_s2 = 0, a_x2 = 0;
@@ -1600,7 +1600,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       }
       const int fi = __shfl_sync(gmask, myfr, 0, 16);
       double sl2 = bt.jacobi_scaling ? bt.sl2[l] : 1.0;
-      double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, radius, mu, dogleg);
+      double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, dfac);
       double dl = -(b + part) / (h + ddl);
       if (dogleg) dl = ca * bt.dog_l[(size_t)2 * l] + cb * bt.dog_l[(size_t)2 * l + 1];
       double lamc = lam + dl;
