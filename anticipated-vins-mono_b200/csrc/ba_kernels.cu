@@ -753,7 +753,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 __host__ __device__ inline int mm_ntile(int K) { return (6 * K + 1 + 7) / 8; }
 __host__ __device__ inline int mm_wstride(int K) { int ws = 8 * mm_ntile(K); return (ws % 16 == 0) ? ws + 8 : ws; }
 
-template <int TM>
+template <int TM, int WSC>   // WSC: compile-time row stride of W~ (0 = runtime) so that P1's loads take immediates
 __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch bt) {
   extern __shared__ double sm[];
   const int w = blockIdx.y, t = blockIdx.x;
@@ -762,14 +762,14 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
   const int cur = ctrl->cur;
   if (t == bt.T) { imu_prior_linearize(bt, w, cur, sm); return; }
 
-  const int K = bt.K, K6 = 6 * K, NPb = K * (K + 1) / 2, NT = mm_ntile(K), WS = mm_wstride(K);
+  const int K = bt.K, K6 = 6 * K, NPb = K * (K + 1) / 2, NT = mm_ntile(K), WS = WSC ? WSC : mm_wstride(K);
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, g = lane >> 2, tq = lane & 3;
   double* sFr = sm;                                  // [K*FR]
   double* sEx = sFr + K * FR;                        // [FR]
   double* sRed = sEx + FR;                           // [16]
   double* sFac = sRed + 16;                          // [MM_NF*STG] A(12) B(12) c(2) r(2) per factor
   double* sW = sFac + MM_NF * STG;                   // [MM_CL*WS]
-  double* sSc = sW + MM_CL * WS;                     // [MM_CL*4] sqrt(1/(h+d)), b, h, beta
+  double* sSc = sW + MM_CL * WS;                     // [MM_CL*4] 1/(h+d), b, -, -
   double* sAcc = sSc + MM_CL * 4;                    // [NPb*36] the tile record's blocks
   double* sGb = sAcc + NPb * 36;                     // [K6] sum J^T r (unreduced gradient)
   double* sGr = sGb + K6;                            // [K6] Schur correction of the gradient
@@ -781,8 +781,8 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
   int* sAnc = sO0 + MM_CL;                           // [MM_CL] anchor frame
   int* sQlo = sAnc + MM_CL;                          // [BVIO_KMAX] first / one-past-last landmark of the chunk anchored
   int* sQhi = sQlo + BVIO_KMAX;                      // [BVIO_KMAX] at frame q (landmarks arrive grouped by anchor)
-  short* sSlot = reinterpret_cast<short*>(sQhi + BVIO_KMAX);      // [(MM_CL+2)*K] frame -> factor slot, -1 unobserved, -2 anchor
-  unsigned char* sFl = reinterpret_cast<unsigned char*>(sSlot + (MM_CL + 2) * K + ((MM_CL + 2) * K & 1));   // [MM_NF] slot -> landmark
+  short* sSlot = reinterpret_cast<short*>(sQhi + BVIO_KMAX);      // [(MM_CL+4)*K] frame -> factor slot, -1 unobserved, -2 anchor
+  unsigned char* sFl = reinterpret_cast<unsigned char*>(sSlot + (MM_CL + 4) * K);   // [MM_NF] slot -> landmark
   unsigned char* sFp = sFl + MM_NF;                  // [MM_NF] slot -> frame
 
   // P1 tiles of this warp: lower-triangular tile index wp + 8 s
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
     accW[s][0] = accW[s][1] = 0.0;
   }
   // P2a: frames wp and wp + 8
-  double accD[2][2] = {{0, 0}, {0, 0}};
+  double accD[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // two independent chains per tile
   double cost_t = 0, gmax_t = 0;
 
   for (int i = tid; i < NPb * 36 + 3 * K6; i += BA_THREADS) sAcc[i] = 0.0;
@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
     const int nfac = bt.lm_off[lb + nl] - obase - nl;
     const int nl4 = (nl + 3) & ~3;
     for (int i = tid; i < nl4 * WS; i += BA_THREADS) sW[i] = 0.0;
-    for (int i = tid; i < (nl + 2) * K; i += BA_THREADS) sSlot[i] = -1;   // two pad rows: pair loops need no bound check
+    for (int i = tid; i < (nl + 4) * K; i += BA_THREADS) sSlot[i] = -1;   // four pad rows: the pair loops need no bound check
     if (tid < BVIO_KMAX) { sQlo[tid] = MM_CL; sQhi[tid] = 0; }
     __syncthreads();
     // ---- A0: slot tables
@@ -886,30 +886,30 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
       for (int k = 0; k < 6; k++) { const double v = st[12 + k] * cc[0] + st[18 + k] * cc[1]; wo[k] = v; wg[k] = v; }
     }
     __syncthreads();
-    // ---- A2: per landmark  A^T c (6 tasks: the anchor's w) and one task for h = sum c^T c, b = sum c^T r with the
-    //      damping of the eliminated depth (Ceres LevenbergMarquardtStrategy / dogleg mu, Jacobi scaling)
-    for (int task = tid; task < nl * 8; task += BA_THREADS) {
-      const int lc = task >> 3, o = task & 7;
-      if (o == 7) continue;
+    // ---- A2: two threads per landmark sum over its factors: A^T c (the anchor's w, 3 components each), and
+    //      h = sum c^T c with the damping of the eliminated depth (Ceres LevenbergMarquardtStrategy / dogleg mu,
+    //      Jacobi scaling) on one, b = sum c^T r on the other
+    if (tid < 2 * nl) {
+      const int lc = tid >> 1, half = tid & 1, o3 = 3 * half, l = lb + lc;
       const int nf = sNobs[lc] - 1;
       const double* st = sFac + (size_t)sFirst[lc] * STG;
-      if (o < 6) {
-        double s0 = 0, s1 = 0;
-        int f = 0;
-        for (; f + 1 < nf; f += 2, st += 2 * STG) {
-          s0 += st[o] * st[24] + st[o + 6] * st[25];
-          s1 += st[STG + o] * st[STG + 24] + st[STG + o + 6] * st[STG + 25];
-        }
-        if (f < nf) s0 += st[o] * st[24] + st[o + 6] * st[25];
-        const double sv = s0 + s1;
-        sW[lc * WS + 6 * sAnc[lc] + o] = sv; bt.w[(size_t)sO0[lc] * 6 + o] = sv;
+      double a0 = 0, a1 = 0, a2 = 0, hb = 0;
+      for (int f = 0; f < nf; f++, st += STG) {
+        const double c0 = st[24], c1 = st[25];
+        a0 += st[o3] * c0 + st[o3 + 6] * c1;
+        a1 += st[o3 + 1] * c0 + st[o3 + 7] * c1;
+        a2 += st[o3 + 2] * c0 + st[o3 + 8] * c1;
+        hb += half ? c0 * st[26] + c1 * st[27] : c0 * c0 + c1 * c1;
+      }
+      double* wo = sW + lc * WS + 6 * sAnc[lc] + o3;
+      double* wg = bt.w + (size_t)sO0[lc] * 6 + o3;
+      wo[0] = a0; wo[1] = a1; wo[2] = a2; wg[0] = a0; wg[1] = a1; wg[2] = a2;
+      if (half) {
+        sW[lc * WS + K6] = hb;                       // column 6K of W: b_l => row 6K of P1 = Schur gradient term
+        gmax_t = fmax(gmax_t, fabs(hb));
+        bt.b[l] = hb;
       } else {
-        double h = 0, b = 0;
-        for (int f = 0; f < nf; f++, st += STG) {
-          h += st[24] * st[24] + st[25] * st[25];
-          b += st[24] * st[26] + st[25] * st[27];
-        }
-        const int l = lb + lc;
+        const double h = hb;
         double sl2 = 1.0;
         if (bt.jacobi_scaling) {
           if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
@@ -918,20 +918,10 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
         const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, dfac);
         double inv_hd = 1.0 / (h + ddl);
         if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
-        const double sq = sqrt(inv_hd);
-        sSc[lc * 4] = sq; sSc[lc * 4 + 3] = b * sq;
-        gmax_t = fmax(gmax_t, fabs(b));
-        bt.h[l] = h; bt.b[l] = b;
+        sSc[lc * 4] = inv_hd;
+        bt.h[l] = h;
         if (first) bt.sl2[l] = sl2;
       }
-    }
-    __syncthreads();
-    // ---- scale: W~ = sqrt(1/(h+d)) w, beta in column 6K
-    for (int lc = wp; lc < nl; lc += 8) {
-      const double sq = sSc[lc * 4];
-      double* wr = sW + lc * WS;
-      for (int d = lane; d < K6; d += 32) wr[d] *= sq;
-      if (lane == 0) wr[K6] = sSc[lc * 4 + 3];
     }
     __syncthreads();
     // ---- AtA(q) partials first (their reduction overlaps the other products)
@@ -944,14 +934,18 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
         // factor slots of the landmarks anchored at q are contiguous: [f0, f1)
         const int f0 = sFirst[lq0], f1 = sFirst[lq1 - 1] + sNobs[lq1 - 1] - 1;
         const int goff = (g < 6 ? 6 * (tq & 1) + g : 26 + (tq & 1));
-        double c0 = 0, c1 = 0;
-        for (int sb = (f0 & ~1) + 2 * wp; sb < f1; sb += 16) {   // warp-uniform trip count (mma.sync)
-          const int slot = sb + (tq >> 1);
-          double x = 0.0;
-          if (slot >= f0 && slot < f1 && g < 7) x = sFac[(size_t)slot * STG + goff];
+        const unsigned span = (unsigned)(f1 - f0);
+        double c0 = 0, c1 = 0, e0 = 0, e1 = 0;
+        const double* px = sFac + goff;
+        for (int sb = (f0 & ~1) + 2 * wp; sb < f1; sb += 32) {   // warp-uniform trip count (mma.sync); 2 chains
+          const int s0 = sb + (tq >> 1), s1 = s0 + 16;
+          double x = 0.0, y = 0.0;
+          if ((unsigned)(s0 - f0) < span && g < 7) x = px[(size_t)s0 * STG];
+          if ((unsigned)(s1 - f0) < span && g < 7) y = px[(size_t)s1 * STG];
           dmma884(c0, c1, x, x);
+          dmma884(e0, e1, y, y);
         }
-        sPart[wp * 64 + g * 8 + 2 * tq] = c0; sPart[wp * 64 + g * 8 + 2 * tq + 1] = c1;
+        sPart[wp * 64 + g * 8 + 2 * tq] = c0 + e0; sPart[wp * 64 + g * 8 + 2 * tq + 1] = c1 + e1;
       }
       __syncthreads();
       if (tid < 64) {
@@ -966,28 +960,37 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
       }
       // ---- P2b: blocks (p, q), p > q, one warp per p (warps taken from the top: P2a loads the low warps)
       for (int p = q + 1 + (7 - wp); p < K; p += 8) {
-        double d0 = 0, d1 = 0;
+        double d0 = 0, d1 = 0, e0 = 0, e1 = 0;
         const short* sl = sSlot + (lq0 + (tq >> 1)) * K + p;
-        const int roff = 6 * (tq & 1) + g;
-        for (int lc = lq0; lc < lq1; lc += 2, sl += 2 * K) {
-          double xa = 0.0, xb = 0.0;
-          const int slot = *sl;
-          if (slot >= 0 && g < 6 && lc + (tq >> 1) < lq1) { const double* st = sFac + (size_t)slot * STG + roff; xa = st[12]; xb = st[0]; }
+        const double* pf = sFac + 6 * (tq & 1) + g;
+        for (int lc = lq0 + (tq >> 1); lc - (tq >> 1) < lq1; lc += 4, sl += 4 * K) {
+          double xa = 0.0, xb = 0.0, ya = 0.0, yb = 0.0;
+          const int s0 = sl[0], s1 = sl[2 * K];
+          if (s0 >= 0 && g < 6 && lc < lq1) { const double* st = pf + (size_t)s0 * STG; xa = st[12]; xb = st[0]; }
+          if (s1 >= 0 && g < 6 && lc + 2 < lq1) { const double* st = pf + (size_t)s1 * STG; ya = st[12]; yb = st[0]; }
           dmma884(d0, d1, xa, xb);
+          dmma884(e0, e1, ya, yb);
         }
         if (g < 6 && tq < 3) {
           double* o = sAcc + tri(p, q) * 36 + g * 6 + 2 * tq;
-          o[0] += d0; o[1] += d1;
+          o[0] += d0 + e0; o[1] += d1 + e1;
         }
       }
     }
-    // ---- P1: S -= W~^T W~ (register tiles)
-    for (int ks = 0; ks < nl4; ks += 4) {
-      const double* wr = sW + (ks + tq) * WS + g;
+    // ---- P1: S -= W^T diag(1/(h+d)) W (register tiles; the row scaling rides on the A fragment)
+    {
+      const double* wb = sW + tq * WS + g;
 #pragma unroll
-      for (int s = 0; s < TM; s++) {
-        if (ti[s] < 0) continue;
-        dmma884(accW[s][0], accW[s][1], wr[ti[s]], wr[tj[s]]);
+      for (int kk = 0; kk < MM_CL / 4; kk++) {
+        if (4 * kk < nl4) {
+          const double inv = (4 * kk + tq < nl) ? sSc[(4 * kk + tq) * 4] : 0.0;
+          const double* wr = wb + kk * 4 * WS;
+#pragma unroll
+          for (int s = 0; s < TM; s++) {
+            if (ti[s] < 0) continue;
+            dmma884(accW[s][0], accW[s][1], wr[ti[s]] * inv, wr[tj[s]]);
+          }
+        }
       }
     }
     // ---- P2a: diagonal blocks (p, p) from the factors seen in frame p (non-anchor side)
@@ -996,12 +999,14 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
       const int p = wp + 8 * u;
       if (p >= K) continue;
       const short* sl = sSlot + (tq >> 1) * K + p;
-      const int goff = (g < 6 ? 12 + 6 * (tq & 1) + g : 26 + (tq & 1));
-      for (int lc = 0; lc < nl; lc += 2, sl += 2 * K) {
-        double x = 0.0;
-        const int slot = *sl;                         // rows nl, nl+1 are padding (-1)
-        if (slot >= 0 && g < 7) x = sFac[(size_t)slot * STG + goff];
+      const double* px = sFac + (g < 6 ? 12 + 6 * (tq & 1) + g : 26 + (tq & 1));
+      for (int lc = 0; lc < nl; lc += 4, sl += 4 * K) {
+        double x = 0.0, y = 0.0;
+        const int s0 = sl[0], s1 = sl[2 * K];           // rows nl .. nl+3 are padding (-1)
+        if (s0 >= 0 && g < 7) x = px[(size_t)s0 * STG];
+        if (s1 >= 0 && g < 7) y = px[(size_t)s1 * STG];
         dmma884(accD[u][0], accD[u][1], x, x);
+        dmma884(accD[u][2], accD[u][3], y, y);
       }
     }
     lb += nl;
@@ -1015,7 +1020,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const int m = g, n = 2 * tq + e;
-      const double v = accD[u][e];
+      const double v = accD[u][e] + accD[u][2 + e];
       if (m < 6 && n < 6) {
         sAcc[tri(p, p) * 36 + m * 6 + n] += v;
         if (m == n) sDg[6 * p + m] += v;
@@ -1054,7 +1059,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
 size_t ba_linearize_mma_smem_bytes(int K) {
   const int NPb = K * (K + 1) / 2, WS = mm_wstride(K);
   size_t d = (size_t)(K + 1) * FR + 16 + (size_t)MM_NF * STG + (size_t)MM_CL * WS + MM_CL * 4 + (size_t)NPb * 36 + 18 * K + 8 * 64;
-  size_t bytes = d * sizeof(double) + (size_t)(4 * MM_CL + 2 * BVIO_KMAX) * sizeof(int) + (size_t)((MM_CL + 2) * K + 1) * sizeof(short) + 2 * MM_NF;
+  size_t bytes = d * sizeof(double) + (size_t)(4 * MM_CL + 2 * BVIO_KMAX) * sizeof(int) + (size_t)((MM_CL + 4) * K) * sizeof(short) + 2 * MM_NF;
   return (bytes + 15) & ~size_t(15);
 }
 
@@ -1758,8 +1763,9 @@ int ba_configure(void) {
     BVIO_LIN_ATTR(1, false) BVIO_LIN_ATTR(2, false) BVIO_LIN_ATTR(3, false) BVIO_LIN_ATTR(4, false)
     BVIO_LIN_ATTR(1, true) BVIO_LIN_ATTR(2, true) BVIO_LIN_ATTR(3, true) BVIO_LIN_ATTR(4, true)
 #undef BVIO_LIN_ATTR
-    if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
@@ -1795,8 +1801,9 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
     size_t sm1 = ba_linearize_mma_smem_bytes(bt.K);
     if (s1b > sm1) sm1 = s1b;
     const int NT = mm_ntile(bt.K);
-    if (NT * (NT + 1) / 2 <= 48) ba_linearize_mma_kernel<6><<<grid, BA_THREADS, sm1, st>>>(bt);
-    else ba_linearize_mma_kernel<10><<<grid, BA_THREADS, sm1, st>>>(bt);
+    if (NT * (NT + 1) / 2 <= 48 && mm_wstride(bt.K) == 72) ba_linearize_mma_kernel<6, 72><<<grid, BA_THREADS, sm1, st>>>(bt);
+    else if (NT * (NT + 1) / 2 <= 48) ba_linearize_mma_kernel<6, 0><<<grid, BA_THREADS, sm1, st>>>(bt);
+    else ba_linearize_mma_kernel<10, 0><<<grid, BA_THREADS, sm1, st>>>(bt);
   }
   else if (nstrip <= BA_THREADS - 32) BVIO_LIN(1)
   else if (nstrip <= 2 * (BA_THREADS - 32)) BVIO_LIN(2)
