@@ -16,7 +16,9 @@ using namespace bvio;
 struct bvio_batch {
   BaBatch bt;
   Slab slab;
-  bool from_cache = false;
+ bool from_cache = false;
+  int cache_slot = -1;                 // -1: own allocation, 0: ctx->ba_cache, 1 + i: ctx->ba_pipe[i]
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of the last solve of this batch
   size_t in_bytes = 0;                 // [0, in_bytes): inputs, mirrored on the host
   size_t out_off = 0, out_bytes = 0;   // [out_off, out_off+out_bytes): outputs, mirrored on the host
   size_t o_pose_out = 0, o_sb_out = 0, o_invd_out = 0, o_ex_out = 0, o_ctrl = 0;
@@ -65,6 +67,7 @@ int bvio_create(int device, bvio_ctx** out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return BVIO_ERR_CUDA; }
   c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
       ba_configure() != 0) {
     delete c;
@@ -82,11 +85,13 @@ void bvio_destroy(bvio_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   bvio_sel_ctx_destroy(ctx);
   ctx->ba_cache.release();
+  for (int i = 0; i < bvio_ctx::PIPE; i++) ctx->ba_pipe[i].release();
   ctx->sel_cache.release();
   if (ctx->marg_scratch) cudaFree(ctx->marg_scratch);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
@@ -136,7 +141,16 @@ static int validate(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* o, int
   return BVIO_OK;
 }
 
-static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_opts* o, bool use_cache, int debug,
+static Slab& cache_of(bvio_ctx* ctx, int slot) { return slot == 0 ? ctx->ba_cache : ctx->ba_pipe[slot - 1]; }
+static bool& busy_of(bvio_ctx* ctx, int slot) { return slot == 0 ? ctx->ba_cache_busy : ctx->ba_pipe_busy[slot - 1]; }
+static void release_slab(bvio_ctx* ctx, bvio_batch* bb) {
+  bool dummy = true;
+  if (bb->cache_slot >= 0 && ctx) slab_release(bb->slab, busy_of(ctx, bb->cache_slot), bb->from_cache);
+  else slab_release(bb->slab, dummy, false);
+}
+
+// cache_slot: -1 = private allocation, 0 = the one-shot cache, 1.. = pipeline slots
+static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_opts* o, int cache_slot, int debug,
                        bvio_batch** out) {
   if (!ctx || !ws || B < 1 || !o || !out) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
   *out = nullptr;
@@ -161,8 +175,9 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bt.use_mma = !est_ex && !getenv("BVIO_LEGACY_LINEARIZE");
   bt.chunk_l = ba_pick_chunk(K, est_ex);
   int T = (maxL + 2 * bt.chunk_l - 1) / (2 * bt.chunk_l);   // >= 2 chunks per tile when there is a choice
-  int Tcap = std::max(1, (2 * ctx->sm_count + B - 1) / B);
+  int Tcap = std::max(1, (10 * ctx->sm_count + B - 1) / B);   // ~5 waves of 2 CTAs/SM: measured optimum (tile record traffic vs tail)
   T = std::max(1, std::min(std::min(T, Tcap), 32));
+  if (const char* ev = getenv("BVIO_TILES")) T = std::max(1, std::min(atoi(ev), 32));   // tuning knob
   bt.T = T;
   bt.undamped = debug;
   bt.max_iters = o->max_iters; bt.jacobi_scaling = o->jacobi_scaling;
@@ -222,12 +237,15 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   const size_t d_bytes = cv.off;
 
   cudaError_t ce;
-  if (use_cache) ce = slab_acquire(ctx->ba_cache, ctx->ba_cache_busy, d_bytes, h_bytes, bb->slab, bb->from_cache);
+  bb->cache_slot = cache_slot;
+  if (cache_slot >= 0) ce = slab_acquire(cache_of(ctx, cache_slot), busy_of(ctx, cache_slot), d_bytes, h_bytes, bb->slab, bb->from_cache);
   else {
     bool dummy_busy = true;
     Slab none;
     ce = slab_acquire(none, dummy_busy, d_bytes, h_bytes, bb->slab, bb->from_cache);
   }
+  if (ce == cudaSuccess) ce = cudaEventCreate(&bb->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&bb->ev1);
   if (ce != cudaSuccess) { delete bb; return fail(ctx, BVIO_ERR_CUDA, std::string("slab alloc: ") + cudaGetErrorString(ce)); }
   char* d = bb->slab.d;
   char* h = bb->slab.h;
@@ -345,10 +363,16 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bt.dbg_S = debug ? (double*)(d + o_dbgS) : nullptr;
   bt.dbg_g = debug ? (double*)(d + o_dbgg) : nullptr;
 
-  cudaError_t e = cudaMemcpyAsync(d, h, bb->in_bytes, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) { ctx->launches += ba_launch_prepare(bt, ctx->stream); e = cudaGetLastError(); }
+  // pipeline slots upload on the copy stream so that the H2D overlaps the previous sub-batch's kernels
+  cudaStream_t up = cache_slot >= 1 ? ctx->copy_stream : ctx->stream;
+  cudaError_t e = cudaMemcpyAsync(d, h, bb->in_bytes, cudaMemcpyHostToDevice, up);
+  if (e == cudaSuccess) { ctx->launches += ba_launch_prepare(bt, up); e = cudaGetLastError(); }
+  if (e == cudaSuccess && up != ctx->stream) {
+    e = cudaEventRecord(bb->ev1, up);                      // ev1 is re-recorded by the solve afterwards
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, bb->ev1, 0);
+  }
   if (e != cudaSuccess) {
-    slab_release(bb->slab, ctx->ba_cache_busy, bb->from_cache);
+    release_slab(ctx, bb);
     delete bb;
     return fail(ctx, BVIO_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e));
   }
@@ -368,13 +392,13 @@ static int enqueue_solve(bvio_ctx* ctx, bvio_batch* bb, cudaStream_t st) {
 extern "C" {
 
 int bvio_batch_upload(bvio_ctx* ctx, const bvio_window* windows, int32_t B, const bvio_opts* opts, bvio_batch** out) {
-  return upload_impl(ctx, windows, B, opts, false, 0, out);
+  return upload_impl(ctx, windows, B, opts, -1, 0, out);
 }
 
 int bvio_batch_solve(bvio_ctx* ctx, bvio_batch* bb) {
   if (!ctx || !bb) return fail(ctx, BVIO_ERR_INVALID, "null batch");
   cudaSetDevice(ctx->device);
-  BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  BVIO_CUDA_OK(ctx, cudaEventRecord(bb->ev0, ctx->stream));
   if (bb->use_graph) {
     if (!bb->graph) {
       cudaGraph_t g = nullptr;
@@ -384,26 +408,31 @@ int bvio_batch_solve(bvio_ctx* ctx, bvio_batch* bb) {
       BVIO_CUDA_OK(ctx, cudaGraphInstantiate(&bb->graph, g, 0));
       cudaGraphDestroy(g);
       // the event recorded before the capture is still valid; re-record so ev0 directly precedes the launch
-      BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+      BVIO_CUDA_OK(ctx, cudaEventRecord(bb->ev0, ctx->stream));
     }
     BVIO_CUDA_OK(ctx, cudaGraphLaunch(bb->graph, ctx->stream));
     ctx->launches += bb->launches_per_solve;
   } else {
     ctx->launches += enqueue_solve(ctx, bb, ctx->stream);
   }
-  BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  BVIO_CUDA_OK(ctx, cudaEventRecord(bb->ev1, ctx->stream));
   BVIO_CUDA_OK(ctx, cudaGetLastError());
   return BVIO_OK;
 }
 
-int bvio_batch_download(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, bvio_summary* summaries) {
-  if (!ctx || !bb) return fail(ctx, BVIO_ERR_INVALID, "null batch");
-  cudaSetDevice(ctx->device);
+}  // extern "C"
+
+// D2H of the outputs, asynchronous on the context stream
+static int enqueue_d2h(bvio_ctx* ctx, bvio_batch* bb) {
   char* ho = bb->slab.h + bb->out_off;
   BVIO_CUDA_OK(ctx, cudaMemcpyAsync(ho, bb->slab.d + bb->out_off, bb->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  BVIO_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return BVIO_OK;
+}
+
+// after the stream has been synchronised: scatter the pinned output mirror into the caller's arrays
+static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, bvio_summary* summaries) {
   float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  cudaEventElapsedTime(&ms, bb->ev0, bb->ev1);
   const BaBatch& bt = bb->bt;
   const double* pose = (const double*)(bb->slab.h + bb->o_pose_out);
   const double* sb = (const double*)(bb->slab.h + bb->o_sb_out);
@@ -434,23 +463,62 @@ int bvio_batch_download(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, bvi
   return BVIO_OK;
 }
 
+extern "C" {
+
+int bvio_batch_download(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, bvio_summary* summaries) {
+  if (!ctx || !bb) return fail(ctx, BVIO_ERR_INVALID, "null batch");
+  cudaSetDevice(ctx->device);
+  int rc = enqueue_d2h(ctx, bb);
+  if (rc) return rc;
+  BVIO_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return unpack_outputs(ctx, bb, windows, summaries);
+}
+
 void bvio_batch_free(bvio_ctx* ctx, bvio_batch* bb) {
   if (!bb) return;
   if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
   if (bb->graph) cudaGraphExecDestroy(bb->graph);
-  bool dummy = true;
-  slab_release(bb->slab, ctx ? ctx->ba_cache_busy : dummy, bb->from_cache);
+  if (bb->ev0) cudaEventDestroy(bb->ev0);
+  if (bb->ev1) cudaEventDestroy(bb->ev1);
+  release_slab(ctx, bb);
   delete bb;
 }
 
+// One-shot solve of B independent windows with host buffers.  Large batches are cut into sub-batches of about
+// one window per SM and software-pipelined on the context stream: while the GPU solves sub-batch i the host
+// packs sub-batch i+1 into its own pinned slab, and the D2H of i trails its solve -- so the wall time tends to
+// max(host packing, device solve) instead of their sum.
 int bvio_optimize_batch(bvio_ctx* ctx, bvio_window* windows, int32_t B, const bvio_opts* opts, bvio_summary* summaries) {
-  bvio_batch* bb = nullptr;
-  int rc = upload_impl(ctx, windows, B, opts, true, 0, &bb);
-  if (rc) return rc;
-  bb->use_graph = false;   // one-shot: direct launches beat capture + instantiate
-  rc = bvio_batch_solve(ctx, bb);
-  if (rc == BVIO_OK) rc = bvio_batch_download(ctx, bb, windows, summaries);
-  bvio_batch_free(ctx, bb);
+  if (!ctx || !windows || B < 1 || !opts) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
+  int S = std::min(bvio_ctx::PIPE, std::max(1, B / std::max(1, ctx->sm_count)));
+  if (S == 1) {
+    bvio_batch* bb = nullptr;
+    int rc = upload_impl(ctx, windows, B, opts, 0, 0, &bb);
+    if (rc) return rc;
+    bb->use_graph = false;   // one-shot: direct launches beat capture + instantiate
+    rc = bvio_batch_solve(ctx, bb);
+    if (rc == BVIO_OK) rc = bvio_batch_download(ctx, bb, windows, summaries);
+    bvio_batch_free(ctx, bb);
+    return rc;
+  }
+  bvio_batch* sub[bvio_ctx::PIPE] = {nullptr};
+  int b0[bvio_ctx::PIPE + 1];
+  for (int i = 0; i <= S; i++) b0[i] = (int)((long long)B * i / S);
+  int rc = BVIO_OK;
+  for (int i = 0; i < S && rc == BVIO_OK; i++) {
+    rc = upload_impl(ctx, windows + b0[i], b0[i + 1] - b0[i], opts, 1 + i, 0, &sub[i]);
+    if (rc) break;
+    sub[i]->use_graph = false;
+    rc = bvio_batch_solve(ctx, sub[i]);
+    if (rc == BVIO_OK) rc = enqueue_d2h(ctx, sub[i]);
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (rc == BVIO_OK && e != cudaSuccess) rc = fail(ctx, BVIO_ERR_CUDA, std::string("optimize_batch: ") + cudaGetErrorString(e));
+  for (int i = 0; i < S; i++) {
+    if (!sub[i]) continue;
+    if (rc == BVIO_OK) rc = unpack_outputs(ctx, sub[i], windows + b0[i], summaries ? summaries + b0[i] : nullptr);
+    bvio_batch_free(ctx, sub[i]);
+  }
   return rc;
 }
 
@@ -461,7 +529,7 @@ int bvio_optimize(bvio_ctx* ctx, bvio_window* window, const bvio_opts* opts, bvi
 int bvio_debug_linearize(bvio_ctx* ctx, const bvio_window* window, const bvio_opts* opts, double* S, double* g,
                          double* h, double* b, double* cost) {
   bvio_batch* bb = nullptr;
-  int rc = upload_impl(ctx, window, 1, opts, false, 1, &bb);
+  int rc = upload_impl(ctx, window, 1, opts, -1, 1, &bb);
   if (rc) return rc;
   const BaBatch& bt = bb->bt;
   ctx->launches += ba_launch_reset(bt, ctx->stream);
@@ -585,7 +653,7 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts,
   if (ba_marginalize_smem_bytes(K, pr ? pr->n : 1, n) > 220 * 1024)
     return fail(ctx, BVIO_ERR_UNSUPPORTED, "kept dimension too large for the single-CTA eigen-decomposition");
   bvio_batch* bb = nullptr;
-  rc = upload_impl(ctx, w, 1, opts, true, 0, &bb);
+  rc = upload_impl(ctx, w, 1, opts, 0, 0, &bb);
   if (rc) return rc;
   char* scratch = nullptr;
   Carver cv;

@@ -36,6 +36,7 @@ struct Carver {
 struct bvio_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D of the next sub-batch while the previous one computes (pipelined batches)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int64_t launches = 0;
@@ -44,6 +45,10 @@ struct bvio_ctx {
   // pay cudaMalloc + cudaMallocHost every call
   bvio::Slab ba_cache, sel_cache;
   bool ba_cache_busy = false, sel_cache_busy = false;
+  // sub-batch slabs of the pipelined bvio_optimize_batch (host packing of sub-batch i+1 overlaps the solve of i)
+  static constexpr int PIPE = 8;
+  bvio::Slab ba_pipe[PIPE];
+  bool ba_pipe_busy[PIPE] = {false, false, false, false, false, false, false, false};
   char* marg_scratch = nullptr;   // grow-only device scratch of bvio_marginalize
   size_t marg_bytes = 0;
   // multi-GPU selector

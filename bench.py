@@ -34,6 +34,7 @@ import __graft_entry__ as g  # noqa: E402
 K_FRAMES, L_FEATS, TRACK_MIN = 11, 1500, 6
 SEL_N, SEL_H, SEL_KAPPA = 2000, 10, 150
 POOL = 4                      # distinct synthetic windows, tiled to the batch size
+FP64_PEAK_TFLOPS = 36.4       # measured DFMA ceiling of this pool's B200 (tools/fp64_peak.cu; DMMA: 37.2)
 BENCH_OPTS = dict(max_iters=8, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
 
 
@@ -41,6 +42,14 @@ def ba_algorithmic_bytes(w, n_prior, np_dim):
     """bytes one GN iteration of one window must move."""
     nf, L, K = w.n_factors, w.L, w.K
     return 20 * nf + 40 * L + 2296 * (K - 1) + 8 * n_prior * n_prior + 16 * n_prior + 128 * K + 8 * np_dim
+
+
+def ba_linearize_flops(w):
+    """Algorithmic FP64 flops of one linearization of one window: per projection factor
+    ~600 (residual + Jacobians + Cauchy) + ~700 (its J^T J / J^T r blocks), per landmark the Schur outer product
+    2 (6 n_l)^2.  The reduced solve (n_p^3 / 3) belongs to ba_solve and is not counted here."""
+    nobs = np.diff(np.asarray(w.lm_obs_offset))
+    return 1300.0 * w.n_factors + float((2.0 * (6.0 * nobs) ** 2).sum())
 
 
 def sel_algorithmic_bytes_round(n_remaining, H):
@@ -191,7 +200,8 @@ def run_ours(args, rank, world, local_rank):
     ctx = pkg.lib.Context(local_rank)
     L = ctx.L
     stream = torch.cuda.ExternalStream(L.bvio_stream(ctx.h), device=torch.device("cuda", local_rank))
-    B = args.batch
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    B = args.batch if args.batch > 0 else 4 * n_sm    # whole waves of windows: 4 per SM (592 on a B200)
     pool = make_pool(synth)
     hs, arr = window_array(abi, pool, B)
     o = abi.default_opts(**BENCH_OPTS)
@@ -259,6 +269,7 @@ def run_ours(args, rank, world, local_rank):
     n_prior = pool[0].prior["n"] if pool[0].prior is not None else 0
     alg_bytes_iter = sum(ba_algorithmic_bytes(pool[i % POOL], n_prior, 15 * K_FRAMES) for i in range(B))
     lin_bytes = alg_bytes_iter - 8 * 15 * K_FRAMES * B      # everything but the delta-x write is read by linearize
+    lin_flops = sum(ba_linearize_flops(pool[i % POOL]) for i in range(B))
     L.bvio_batch_free(ctx.h, bh)
 
     # ---- selector, inputs resident in HBM
@@ -398,14 +409,19 @@ def run_ours(args, rank, world, local_rank):
                     "steps": e2e_steps, "api": "bvio_optimize_batch (host buffers, pack + H2D + solve + D2H)"},
             "gpu_launches": int(ba_launches + sel_launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "ba_linearize_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "ba_linearize_mma_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": int(lin_bytes), "launch_ms": lin_ms,
                          "kernel_ms_per_pass": {"ba_linearize_kernel": lin_ms, "ba_solve_kernel": solve_ms,
                                                 "ba_cost_kernel": cost_ms},
-                         "note": "FP64 compute/latency-bound path: ~28 MFLOP per 0.38 MB window-iteration; the HBM "
-                                 "fraction is reported as BASELINE.json asks, not as the binding limit"},
+                         "fp64": {"achieved": lin_flops / (lin_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS,
+                                  "unit": "TFLOP/s", "frac": lin_flops / (lin_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                                  "peak_source": "tools/fp64_peak.cu on this pool's B200: DFMA 36.4 / DMMA 37.2 TFLOP/s "
+                                                 "(profiles/r01_fp64_peak.json)",
+                                  "algorithmic_flops_per_launch": lin_flops},
+                         "note": "FP64 compute/latency-bound path (~95 flop/byte): the HBM fraction is reported as "
+                                 "BASELINE.json asks; the binding ceiling is the FP64 pipe, reported under fp64"},
             "selector": {"metric": "candidates-scored/sec", "value": sel_value, "unit": "cand/s",
                          "ms_per_step": sel_ms / args.steps, "workload": f"configs[3]: N={SEL_N}, H={SEL_H}, "
                          f"kappa={SEL_KAPPA}, {nv} valid candidates, every remaining candidate scored each round",
@@ -429,7 +445,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="independent windows per GPU per BA step")
+    ap.add_argument("--batch", type=int, default=0, help="independent windows per GPU per BA step (0 = 4 per SM)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-solves", type=int, default=64)
     ap.add_argument("--cpu-kappa", type=int, default=16)
