@@ -190,3 +190,33 @@ class SelectHandle:
         s.cloud_depth = dptr(self.cld) if s.C else None
         s.kappa = p.kappa
         self.s = s
+
+
+def call_marginalize(lib_fn, w, flag, ctx=None, opts=None):
+    """bvio_marginalize / oracle_marginalize on a synth.Window; returns the next prior as the dict synth.Window.prior
+    expects (plus J, the n x n linearized_jacobians), or None when the reference would keep the old prior."""
+    import time
+    h = WindowHandle(w)
+    cap_n, cap_b = 15 * w.K + 16, 2 * w.K + 2
+    bk, bf, bi = (np.zeros(cap_b, np.int32) for _ in range(3))
+    x0, jac, res = np.zeros(9 * cap_b), np.zeros(cap_n * cap_n), np.zeros(cap_n)
+    out = PriorOut()
+    out.block_kind, out.block_frame, out.block_idx = iptr(bk), iptr(bf), iptr(bi)
+    out.x0, out.lin_jac, out.lin_res = dptr(x0), dptr(jac), dptr(res)
+    out.cap_n, out.cap_blocks = cap_n, cap_b
+    o = opts if opts is not None else default_opts()
+    t0 = time.perf_counter()
+    rc = lib_fn(C.byref(h.s), C.byref(o), flag, C.byref(out)) if ctx is None else \
+        lib_fn(ctx, C.byref(h.s), C.byref(o), flag, C.byref(out))
+    call_marginalize.t_call = time.perf_counter() - t0
+    if rc != 0:
+        raise RuntimeError(f"marginalize failed: {rc}")
+    n, nb = out.n, out.nblocks
+    if n < 0:
+        return None
+    J = jac[:n * n].reshape(n, n, order="F").copy()
+    return dict(n=n, block_kind=bk[:nb].copy(), block_frame=bf[:nb].copy(), block_idx=bi[:nb].copy(),
+                x0=x0.copy(), lin_jac=jac[:n * n].copy(), lin_res=res[:n].copy(), J=J)
+
+
+call_marginalize.t_call = 0.0

@@ -332,38 +332,38 @@ def run_ours(args, rank, world, local_rank):
     sel_h2d = sh.pos.nbytes + sh.quat.nbytes + sh.cxy.nbytes + sh.cp.nbytes + sh.clxy.nbytes + sh.cld.nbytes
     assert (ids2 == ids).all(), "one-shot and resident selector disagree"
 
-    # ---- frame-rate use (BASELINE configs[4] shape): one 11-kf/150-feature window per call through the
-    #      one-shot C-ABI (host buffers in, host buffers out), optimize + marginalize + select per frame
+    # ---- frame-rate use (BASELINE configs[4]): a closed-loop sequence of CONSECUTIVE sliding windows (slider.py: IMU
+    #      prediction, tracking, triangulation, optimize -> marginalize -> select -> slideWindow; each window's prior is
+    #      the previous window's marginalization output), one window per call through the one-shot C-ABI with host
+    #      buffers.  *_call = the FFI call alone; the others include the Python/ctypes packing around it.
     stream = None
     if rank == 0 and args.stream_frames > 0:
-        import test_oracle_marg as tm
-        wpool = [synth.make_window(seed=300 + i, K=K_FRAMES, L=150) for i in range(4)]
-        spool = [abi.SelectHandle(synth.make_select_problem(seed=400 + i, N=300, H=SEL_H, kappa=150)) for i in range(4)]
-        od = abi.default_opts()            # the reference's budget: 8 iterations, Ceres default tolerances
-        lat = {"optimize": [], "marginalize": [], "select": [], "frame": []}
-        for f in range(args.stream_frames + 5):
-            wh = abi.WindowHandle(wpool[f % 4])
-            sh2 = spool[f % 4]
-            s1, ss2 = abi.Summary(), abi.SelectSummary()
-            ids3 = np.zeros(150, np.int32)
-            t0 = time.perf_counter()
-            ctx.check(L.bvio_optimize(ctx.h, C.byref(wh.s), C.byref(od), C.byref(s1)), "optimize")
-            t1 = time.perf_counter()
-            wpost = wpool[f % 4].copy()
-            wpost.para_pose, wpost.para_speed_bias, wpost.inv_depth = wh.pose, wh.sb, wh.inv
-            t1b = time.perf_counter()
-            assert tm.run_marg(abi, L.bvio_marginalize, wpost, 0, ctx=ctx.h) is not None
-            t2 = time.perf_counter()
-            ctx.check(L.bvio_select(ctx.h, C.byref(sh2.s), abi.iptr(ids3), None, C.byref(ss2)), "select")
-            t3 = time.perf_counter()
-            if f >= 5:
-                lat["optimize"].append(t1 - t0)
-                lat["marginalize"].append(t2 - t1b)
-                lat["select"].append(t3 - t2)
-                lat["frame"].append((t1 - t0) + (t2 - t1b) + (t3 - t2))
-        stream = {"frames": args.stream_frames, "workload": "11-kf/150-feature window, 8 LM iterations (Ceres default "
-                  "tolerances) + MARGIN_OLD + select(N=300, H=10, kappa=150) per frame, host buffers, wall clock incl. "
-                  "Python/ctypes packing of the prior output", "budget_ms_30hz": 33.3}
+        sim = pkg.slider.SlidingWindowSim(seed=7, max_feats=150, max_cand=300, H=SEL_H, frame_dt=1.0 / 30.0)
+        gb = pkg.slider.GpuBackend(ctx, abi)          # the reference's budget: 8 iterations, Ceres default tolerances
+        keys = ("optimize", "marginalize", "select", "optimize_call", "marginalize_call", "select_call")
+        lat = {k: [] for k in keys + ("frame", "frame_call")}
+        cnt = {"L": [], "n_factors": [], "N": [], "kappa": [], "iterations": []}
+        warm = sim.K + 4
+        for f in range(args.stream_frames + warm):
+            r = sim.step(gb)
+            if r is None or f < warm:
+                continue
+            for k in keys:
+                lat[k].append(r[k])
+            lat["frame"].append(r["optimize"] + r["marginalize"] + r["select"])
+            lat["frame_call"].append(r["optimize_call"] + r["marginalize_call"] + r["select_call"])
+            for k in cnt:
+                cnt[k].append(r.get(k, 0))
+        errs = np.array([h[1] for h in sim.history])
+        stream = {"frames": args.stream_frames,
+                  "workload": "closed-loop 30 Hz sequence of consecutive 11-keyframe windows: per frame bvio_optimize (8 LM "
+                              "iterations, Ceres default tolerances, prior = previous marginalization) + bvio_marginalize "
+                              "(MARGIN_OLD) + bvio_select (H=10, budget 150 features), host buffers, wall clock",
+                  "budget_ms_30hz": 33.3,
+                  "mean_landmarks": float(np.mean(cnt["L"])), "mean_factors": float(np.mean(cnt["n_factors"])),
+                  "mean_candidates": float(np.mean(cnt["N"])), "mean_kappa": float(np.mean(cnt["kappa"])),
+                  "mean_iterations": float(np.mean(cnt["iterations"])),
+                  "position_error_m": {"mean": float(errs.mean()), "last": float(errs[-1])}}
         for k, v in lat.items():
             a = np.array(v) * 1e3
             stream[k + "_ms"] = {"p50": float(np.percentile(a, 50)), "p99": float(np.percentile(a, 99)), "max": float(a.max())}
@@ -449,7 +449,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-solves", type=int, default=64)
     ap.add_argument("--cpu-kappa", type=int, default=16)
-    ap.add_argument("--stream-frames", type=int, default=200, help="frames of the per-frame latency leg (0 = skip)")
+    ap.add_argument("--stream-frames", type=int, default=300,
+                    help="frames of the closed-loop latency leg (0 = skip; BASELINE configs[4] asks for 10000)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,0 +1,27 @@
+"""Oracle backend for the closed-loop slider (tests only: the product backend is slider.GpuBackend)."""
+import ctypes as C
+import dataclasses
+
+import numpy as np
+
+
+class OracleBackend:
+    def __init__(self, orc, abi):
+        self.orc, self.abi = orc, abi
+        self.t_call = 0.0
+
+    def optimize(self, w, opts):
+        abi = self.abi
+        h, o, s = abi.WindowHandle(w), abi.default_opts(**opts), abi.Summary()
+        assert self.orc.oracle_optimize(C.byref(h.s), C.byref(o), C.byref(s)) == 0
+        return dataclasses.replace(w, para_pose=h.pose, para_speed_bias=h.sb, inv_depth=h.inv), s.as_dict()
+
+    def marginalize(self, w, flag):
+        return self.abi.call_marginalize(self.orc.oracle_marginalize, w, flag)
+
+    def select(self, prob):
+        abi = self.abi
+        h, ss = abi.SelectHandle(prob), abi.SelectSummary()
+        ids = np.zeros(max(prob.kappa, 1), np.int32)
+        assert self.orc.oracle_select(C.byref(h.s), abi.iptr(ids), None, C.byref(ss)) == 0
+        return ids[:ss.n_selected].copy()

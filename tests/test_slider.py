@@ -1,0 +1,130 @@
+"""Closed-loop sliding-window driver: host logic on the CPU oracle backend, and -- on a GPU --
+the same session through libbvio.so, frame by frame against the oracle."""
+import numpy as np
+import pytest
+
+from slider_backends import OracleBackend
+
+
+def _run(sim, backend, frames):
+    lats = []
+    for _ in range(frames):
+        lat = sim.step(backend)
+        if lat is not None:
+            lats.append(lat)
+    return lats
+
+
+def test_slider_bookkeeping_on_oracle(pkg, oracle):
+    """30 frames: the window fills, every later frame optimises, marginalises (prior feeds the next window),
+    selects new features up to the budget and slides; the estimate stays on the ground-truth trajectory."""
+    sl = pkg.slider
+    sim = sl.SlidingWindowSim(seed=3, max_feats=60, max_cand=80, opts=dict(max_iters=8))
+    lats = _run(sim, OracleBackend(oracle, pkg.abi), 30)
+    assert len(lats) == 30 - (sim.K - 1)
+    assert len(sim.pose) == sim.K - 1 and len(sim.preint) == sim.K - 1        # slid, waiting for the next frame
+    assert sim.prior is not None and sim.prior["n"] >= 15
+    # prior blocks refer to frames of the slid window (addr_shift applied), frame-major
+    assert sim.prior["block_frame"].max() <= sim.K - 2
+    for lat in lats[2:]:
+        assert lat["L"] >= 20 and lat["iterations"] >= 1
+    # features that are parameters obey the reference's filter; observations are consecutive frames
+    for tr in sim.tracks.values():
+        assert 0 <= tr.start <= sim.K - 1 and tr.start + len(tr.xy) <= sim.K - 1 + 1
+    errs = np.array([h[1] for h in sim.history])
+    assert errs[-5:].max() < 0.25, errs
+    # the per-frame budget: tracked + newly selected never exceeds max_feats
+    newest = len(sim.pose)          # index the newest frame had before the slide
+    n_new = sum(1 for tr in sim.tracks.values() if tr.alive)
+    assert n_new <= 60
+
+
+def test_regauge_keeps_frame0_yaw_and_position(pkg):
+    sl, S = pkg.slider, pkg.synth
+    rng = np.random.default_rng(0)
+    w = S.make_window(seed=1, K=5, L=10)
+    pose, sb = w.para_pose.copy(), w.para_speed_bias.copy()
+    before = pose[0].copy()
+    # apply a global yaw + translation (the gauge freedom of VIO) to the "solution"
+    Rz = sl._yaw_R(17.0)
+    sol = pose.copy()
+    for i in range(len(sol)):
+        sol[i, :3] = Rz @ pose[i, :3] + np.array([0.3, -0.2, 0.1])
+        sol[i, 3:] = S.rot_to_quat(Rz @ S.quat_to_rot(pose[i, 3:]))
+    sbs = sb.copy()
+    sbs[:, :3] = sb[:, :3] @ Rz.T
+    sl.regauge(before, sol, sbs)
+    assert np.allclose(sol[:, :3], pose[:, :3], atol=1e-9)
+    assert np.allclose(sbs[:, :3], sb[:, :3], atol=1e-9)
+    for i in range(len(sol)):
+        assert np.allclose(S.quat_to_rot(sol[i, 3:]), S.quat_to_rot(pose[i, 3:]), atol=1e-9)
+
+
+def test_triangulate_recovers_depth(pkg):
+    sl, S = pkg.slider, pkg.synth
+    w = S.make_window(seed=2, K=8, L=30, noise=False, perturb=False)
+    U_, _, Vt_ = np.linalg.svd(S.EUROC_RIC)
+    ric = U_ @ Vt_
+    for l in range(w.L):
+        o0, o1 = w.lm_obs_offset[l], w.lm_obs_offset[l + 1]
+        tr = sl.Track(lid=l, start=int(w.obs_frame[o0]), xy=[w.obs_xy[k] for k in range(o0, o1)])
+        d = sl.triangulate(tr, w.gt_pose, ric, S.EUROC_TIC)
+        assert abs(d - 1.0 / w.gt_inv_depth[l]) < 1e-6 * d
+
+
+class DualBackend(OracleBackend):
+    """Runs the CUDA library and the oracle on the SAME inputs at every call of a closed-loop session, checks parity,
+    and hands the oracle's result back to the driver (so the session itself is deterministic)."""
+
+    def __init__(self, orc, abi, gpu):
+        super().__init__(orc, abi)
+        self.gpu, self.n = gpu, {"optimize": 0, "marginalize": 0, "select": 0}
+
+    def optimize(self, w, opts):
+        wg, sg = self.gpu.optimize(w.copy(), opts)
+        wo, so = super().optimize(w.copy(), opts)
+        assert (sg["iterations"], sg["num_accepted"], sg["num_rejected"], sg["termination"]) == \
+               (so["iterations"], so["num_accepted"], so["num_rejected"], so["termination"]), (sg, so)
+        for a, b in ((wg.para_pose, wo.para_pose), (wg.para_speed_bias, wo.para_speed_bias), (wg.inv_depth, wo.inv_depth)):
+            assert np.linalg.norm(a - b) <= 1e-6 * np.linalg.norm(b), (self.n, sg, so)
+        assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-8 * so["final_cost"]
+        self.n["optimize"] += 1
+        return wo, so
+
+    def marginalize(self, w, flag):
+        pg, po = self.gpu.marginalize(w, flag), super().marginalize(w, flag)
+        assert (pg is None) == (po is None)
+        if po is not None:
+            assert pg["n"] == po["n"] and (pg["block_kind"] == po["block_kind"]).all()
+            assert (pg["block_frame"] == po["block_frame"]).all() and (pg["block_idx"] == po["block_idx"]).all()
+            assert np.allclose(pg["x0"], po["x0"], rtol=0, atol=1e-12)
+            Hg, Ho = pg["J"].T @ pg["J"], po["J"].T @ po["J"]          # marginalization_factor.cpp:295-296
+            gg, go = pg["J"].T @ pg["lin_res"], po["J"].T @ po["lin_res"]
+            # same tolerances as tests/test_gpu_marg.py: cond(A_mm) ~ 1e8 (1e11 without any prior on frame 0) and
+            # different elimination orders (analytic depth elimination vs one big pseudo-inverse)
+            htol = 1e-7 if w.prior is not None else 2e-5
+            assert np.abs(Hg - Ho).max() <= htol * np.abs(Ho).max(), self.n
+            assert np.abs(gg - go).max() <= 5e-5 * max(np.abs(go).max(), 1.0), self.n
+        self.n["marginalize"] += 1
+        return po
+
+    def select(self, prob):
+        ig, io = self.gpu.select(prob), super().select(prob)
+        assert len(ig) == len(io) and (ig == io).all(), (ig, io)
+        self.n["select"] += 1
+        return io
+
+
+@pytest.mark.gpu
+def test_closed_loop_session_gpu_vs_oracle_on_identical_inputs(pkg, oracle):
+    """BASELINE configs[4] in miniature: 40 consecutive frames; every optimize (reference budget, prior = previous
+    marginalization), marginalize and select call is issued to libbvio.so AND to the oracle on the same host buffers."""
+    sl = pkg.slider
+    ctx = pkg.lib.Context(0)
+    sim = sl.SlidingWindowSim(seed=5, max_feats=100, max_cand=150, opts=dict(max_iters=8))
+    dual = DualBackend(oracle, pkg.abi, sl.GpuBackend(ctx, pkg.abi))
+    for f in range(40):
+        sim.step(dual)
+    assert dual.n["optimize"] == 30 and dual.n["marginalize"] == 30 and dual.n["select"] >= 10, dual.n
+    assert sim.prior["n"] == 75
+    ctx.close()
