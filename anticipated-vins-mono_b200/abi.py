@@ -138,6 +138,11 @@ class WindowHandle:
         s.inv_depth = dptr(self.inv)
         s.lm_obs_offset, s.obs_frame, s.obs_xy = iptr(self.off), iptr(self.frame), dptr(self.xy)
         s.obs_vel = s.obs_td = s.obs_row = None
+        if getattr(w, "obs_vel", None) is not None:
+            self.vel = np.ascontiguousarray(w.obs_vel, np.float64)
+            self.otd = np.ascontiguousarray(w.obs_td, np.float64)
+            self.row = np.ascontiguousarray(w.obs_row, np.float64)
+            s.obs_vel, s.obs_td, s.obs_row = dptr(self.vel), dptr(self.otd), dptr(self.row)
         s.preint = C.cast(self.pre.ctypes.data, C.POINTER(Preint))
         self.prior_s = None
         if w.prior is not None:

@@ -270,6 +270,12 @@ class Window:
     gt_pose: np.ndarray | None = None
     gt_speed_bias: np.ndarray | None = None
     gt_inv_depth: np.ndarray | None = None
+    # ProjectionTdFactor inputs (estimate_td): per observation feature velocity on the normalized plane, the td in
+    # force when the observation was taken (cur_td) and its pixel row (feature_manager.h FeaturePerFrame)
+    obs_vel: np.ndarray | None = None    # [n_obs,2]
+    obs_td: np.ndarray | None = None     # [n_obs]
+    obs_row: np.ndarray | None = None    # [n_obs]
+    gt_td: float = 0.0
 
     @property
     def L(self):
@@ -295,7 +301,7 @@ def pack_preint(p: Preintegration) -> np.ndarray:
 
 
 def make_window(seed=0, K=11, L=150, track_min=3, track_max=11, frame_dt=0.1, imu_rate=200,
-                prior="frame0", noise=True, perturb=True, depth_range=(2.0, 10.0)) -> Window:
+                prior="frame0", noise=True, perturb=True, depth_range=(2.0, 10.0), td_true=None) -> Window:
     """Configs 1-3 of SURVEY.md section 8d.  prior: 'frame0' (15-dim full-rank prior on
     frame 0, Lambda = 1e4 I), 'none'."""
     rng = np.random.default_rng(seed)
@@ -348,6 +354,7 @@ def make_window(seed=0, K=11, L=150, track_min=3, track_max=11, frame_dt=0.1, im
     # landmarks
     offs = [0]
     obs_frame, obs_xy, inv_depth_gt = [], [], []
+    obs_vel, obs_row = [], []
     sig_px = 1.5 / FOCAL_LENGTH
     tries = 0
     while len(inv_depth_gt) < L and tries < 100 * L + 1000:
@@ -364,7 +371,7 @@ def make_window(seed=0, K=11, L=150, track_min=3, track_max=11, frame_dt=0.1, im
         pc = ray * depth
         Ri, Pi = traj.rot(tk[start]), traj.pos(tk[start])
         pw = Ri @ (ric @ pc + tic) + Pi
-        frames, pts = [], []
+        frames, pts, vels, rows = [], [], [], []
         ok = True
         for j in range(start, start + nl):
             Rj, Pj = traj.rot(tk[j]), traj.pos(tk[j])
@@ -373,6 +380,16 @@ def make_window(seed=0, K=11, L=150, track_min=3, track_max=11, frame_dt=0.1, im
                 ok = False
                 break
             xy = pcj[:2] / pcj[2]
+            if td_true is not None:
+                # feature velocity on the normalized plane (feature_tracker publishes it, estimator_node.cpp:318-320);
+                # the image is taken td_true late: observed = xy(t_k) + td_true * velocity
+                hh = 1e-4
+                pa = ric.T @ (traj.rot(tk[j] + hh).T @ (pw - traj.pos(tk[j] + hh)) - tic)
+                pb = ric.T @ (traj.rot(tk[j] - hh).T @ (pw - traj.pos(tk[j] - hh)) - tic)
+                vel = (pa[:2] / pa[2] - pb[:2] / pb[2]) / (2 * hh)
+                vels.append(vel)
+                rows.append(space_to_plane(cam, pcj)[1])
+                xy = xy + td_true * vel
             if noise:
                 xy = xy + rng.normal(0, sig_px, 2)
             frames.append(j)
@@ -382,6 +399,8 @@ def make_window(seed=0, K=11, L=150, track_min=3, track_max=11, frame_dt=0.1, im
         # keep the visible prefix (contiguous track, like FeatureManager)
         obs_frame += frames
         obs_xy += pts
+        obs_vel += vels[:len(frames)]
+        obs_row += rows[:len(frames)]
         offs.append(len(obs_frame))
         inv_depth_gt.append(1.0 / depth)
     assert len(inv_depth_gt) == L, "could not place enough landmarks"
@@ -416,7 +435,11 @@ def make_window(seed=0, K=11, L=150, track_min=3, track_max=11, frame_dt=0.1, im
                   para_ex_pose=np.concatenate([tic, qic]), para_td=np.zeros(1),
                   inv_depth=inv0, lm_obs_offset=np.array(offs, np.int32),
                   obs_frame=np.array(obs_frame, np.int32), obs_xy=np.array(obs_xy, float).reshape(-1, 2),
-                  preint=preint, prior=pr, gt_pose=gt_pose, gt_speed_bias=gt_sb, gt_inv_depth=inv_depth_gt)
+                  preint=preint, prior=pr, gt_pose=gt_pose, gt_speed_bias=gt_sb, gt_inv_depth=inv_depth_gt,
+                  obs_vel=np.array(obs_vel, float).reshape(-1, 2) if td_true is not None else None,
+                  obs_td=np.zeros(len(obs_frame)) if td_true is not None else None,
+                  obs_row=np.array(obs_row, float) if td_true is not None else None,
+                  gt_td=td_true or 0.0)
 
 
 # ----------------------------------------------------------------------------

@@ -92,6 +92,36 @@ void projection_eval(V3 pts_i, V3 pts_j, V3 Pi, Q4 Qi, V3 Pj, Q4 Qj, V3 tic, Q4 
 }
 
 // ---------------------------------------------------------------------------
+// a2': ProjectionTdFactor::Evaluate (projection_td_factor.cpp:34-141).  Same chain as ProjectionFactor on the
+// time-shifted points pts_td = pts - (td - td_obs + TR/ROW * (row - ROW/2)) * velocity (:51-52, rows centred in
+// the constructor :18-19), plus the 2x1 Jacobian w.r.t. td (:131-136):
+//   reduce * ric^T Rj^T Ri ric * velocity_i / inv_dep_i * -1  +  sqrt_info * velocity_j.head(2)
+// ---------------------------------------------------------------------------
+struct TdObs { V3 vel; double td, row; };
+void projection_td_eval(V3 pts_i, V3 pts_j, TdObs oi, TdObs oj, double td, double TR, double ROW, V3 Pi, Q4 Qi, V3 Pj,
+                        Q4 Qj, V3 tic, Q4 qic, double inv_dep_i, double sqrt_info, double res[2], double* Ji, double* Jj,
+                        double* Jex, double* Jf, double* Jtd) {
+  double row_i = oi.row - ROW / 2, row_j = oj.row - ROW / 2;
+  V3 pts_i_td = pts_i - (td - oi.td + TR / ROW * row_i) * oi.vel;
+  V3 pts_j_td = pts_j - (td - oj.td + TR / ROW * row_j) * oj.vel;
+  projection_eval(pts_i_td, pts_j_td, Pi, Qi, Pj, Qj, tic, qic, inv_dep_i, sqrt_info, res, Ji, Jj, Jex, Jf);
+  if (!Jtd) return;
+  M3 Ri = qmat(Qi), Rj = qmat(Qj), ric = qmat(qic);
+  V3 pts_camera_i = pts_i_td / inv_dep_i;
+  V3 pts_camera_j = qrot(qinv(qic), qrot(qinv(Qj), qrot(Qi, qrot(qic, pts_camera_i) + tic) + Pi - Pj) - tic);
+  double dep_j = pts_camera_j.z;
+  double reduce[2][3] = {{sqrt_info / dep_j, 0, -sqrt_info * pts_camera_j.x / (dep_j * dep_j)},
+                         {0, sqrt_info / dep_j, -sqrt_info * pts_camera_j.y / (dep_j * dep_j)}};
+  V3 v = (transpose(ric) * transpose(Rj) * Ri * ric) * oi.vel;
+  for (int a = 0; a < 2; a++)
+    Jtd[a] = (reduce[a][0] * v.x + reduce[a][1] * v.y + reduce[a][2] * v.z) / inv_dep_i * -1.0 +
+             sqrt_info * (a == 0 ? oj.vel.x : oj.vel.y);
+}
+inline TdObs td_obs(const bvio_window* w, int k) {
+  return TdObs{V3{w->obs_vel[2 * k], w->obs_vel[2 * k + 1], 0.0}, w->obs_td[k], w->obs_row[k]};
+}
+
+// ---------------------------------------------------------------------------
 // a3: IMUFactor::Evaluate
 // ---------------------------------------------------------------------------
 void imu_sqrt_info(const double cov[225], double si[225]) {
@@ -255,18 +285,20 @@ void prior_eval(const bvio_prior* p, const bvio_window* w, double* res, double* 
 // problem, normal equations, Schur
 // ---------------------------------------------------------------------------
 struct Layout {
-  int K, L, np, ex_off, est_ex;
+  int K, L, np, ex_off, est_ex, td_off, est_td;
 };
 Layout layout(const bvio_window* w, const bvio_opts* o) {
   Layout l;
   l.K = w->K; l.L = w->L; l.est_ex = o->estimate_extrinsic != 0;
   l.ex_off = 15 * w->K;
-  l.np = 15 * w->K + (l.est_ex ? 6 : 0);
+  l.est_td = o->estimate_td != 0;
+  l.td_off = 15 * w->K + (l.est_ex ? 6 : 0);
+  l.np = l.td_off + (l.est_td ? 1 : 0);
   return l;
 }
 
 struct Normal {
-  std::vector<double> Hpp, bp, h, b, w, wex;  // w: 6 per observation (obs 0 = anchor frame)
+  std::vector<double> Hpp, bp, h, b, w, wex, wtd;  // w: 6 per observation (obs 0 = anchor frame)
   double cost;
 };
 
@@ -290,6 +322,12 @@ double visual_cost(const bvio_window* w, const bvio_opts* o) {
       int fj = w->obs_frame[k];
       V3 pts_j{w->obs_xy[2 * k], w->obs_xy[2 * k + 1], 1.0};
       double r[2];
+      if (o->estimate_td)
+        projection_td_eval(pts_i, pts_j, td_obs(w, o0), td_obs(w, k), w->para_td[0], o->TR, o->ROW,
+                           v3(w->para_pose + 7 * fi), q4(w->para_pose + 7 * fi + 3), v3(w->para_pose + 7 * fj),
+                           q4(w->para_pose + 7 * fj + 3), tic, qic, w->inv_depth[l], sqrt_info, r, nullptr, nullptr,
+                           nullptr, nullptr, nullptr);
+      else
       projection_eval(pts_i, pts_j, v3(w->para_pose + 7 * fi), q4(w->para_pose + 7 * fi + 3),
                       v3(w->para_pose + 7 * fj), q4(w->para_pose + 7 * fj + 3), tic, qic, w->inv_depth[l],
                       sqrt_info, r, nullptr, nullptr, nullptr, nullptr);
@@ -335,6 +373,7 @@ void linearize(const bvio_window* w, const bvio_opts* o, const ImuCache& ic, con
   N.b.assign(L, 0.0);
   N.w.assign((size_t)6 * nobs, 0.0);
   N.wex.assign((size_t)6 * L, 0.0);
+  N.wtd.assign((size_t)L, 0.0);
   N.cost = 0;
   double sqrt_info = o->focal_length / 1.5;
   V3 tic = v3(w->para_ex_pose); Q4 qic = q4(w->para_ex_pose + 3);
@@ -351,7 +390,13 @@ void linearize(const bvio_window* w, const bvio_opts* o, const ImuCache& ic, con
     for (int k = o0 + 1; k < o1; k++) {
       int fj = w->obs_frame[k];
       V3 pts_j{w->obs_xy[2 * k], w->obs_xy[2 * k + 1], 1.0};
-      double r[2], Ji[14], Jj[14], Jex[14], Jf[2];
+      double r[2], Ji[14], Jj[14], Jex[14], Jf[2], Jtd[2] = {0, 0};
+      if (ly.est_td)
+        projection_td_eval(pts_i, pts_j, td_obs(w, o0), td_obs(w, k), w->para_td[0], o->TR, o->ROW,
+                           v3(w->para_pose + 7 * fi), q4(w->para_pose + 7 * fi + 3), v3(w->para_pose + 7 * fj),
+                           q4(w->para_pose + 7 * fj + 3), tic, qic, w->inv_depth[l], sqrt_info, r, Ji, Jj,
+                           ly.est_ex ? Jex : nullptr, Jf, Jtd);
+      else
       projection_eval(pts_i, pts_j, v3(w->para_pose + 7 * fi), q4(w->para_pose + 7 * fi + 3),
                       v3(w->para_pose + 7 * fj), q4(w->para_pose + 7 * fj + 3), tic, qic, w->inv_depth[l],
                       sqrt_info, r, Ji, Jj, ly.est_ex ? Jex : nullptr, Jf);
@@ -385,6 +430,23 @@ void linearize(const bvio_window* w, const bvio_opts* o, const ImuCache& ic, con
           N.bp[re + a] += E[a] * r[0] + E[6 + a] * r[1];
           N.wex[(size_t)6 * l + a] += E[a] * c[0] + E[6 + a] * c[1];
         }
+      }
+      if (ly.est_td) {
+        // the td column (one per factor row pair) against every other block this factor touches
+        int rt = ly.td_off;
+        double t0 = sr * Jtd[0], t1 = sr * Jtd[1];
+        H[(size_t)rt * np + rt] += t0 * t0 + t1 * t1;
+        for (int a = 0; a < 6; a++) {
+          double va = A[a] * t0 + A[6 + a] * t1, vb = B[a] * t0 + B[6 + a] * t1;
+          H[(size_t)(ri + a) * np + rt] += va; H[(size_t)rt * np + ri + a] += va;
+          H[(size_t)(rj + a) * np + rt] += vb; H[(size_t)rt * np + rj + a] += vb;
+          if (ly.est_ex) {
+            double ve = E[a] * t0 + E[6 + a] * t1;
+            H[(size_t)(ly.ex_off + a) * np + rt] += ve; H[(size_t)rt * np + ly.ex_off + a] += ve;
+          }
+        }
+        N.bp[rt] += t0 * r[0] + t1 * r[1];
+        N.wtd[l] += t0 * c[0] + t1 * c[1];
       }
       N.h[l] += c[0] * c[0] + c[1] * c[1];
       N.b[l] += c[0] * r[0] + c[1] * r[1];
@@ -430,6 +492,7 @@ void linearize(const bvio_window* w, const bvio_opts* o, const ImuCache& ic, con
       if (kind == BVIO_BLK_POSE) base = 15 * p->block_frame[b];
       else if (kind == BVIO_BLK_SPEEDBIAS) base = 15 * p->block_frame[b] + 6;
       else if (kind == BVIO_BLK_EXPOSE) base = ly.est_ex ? ly.ex_off : -1;
+      else if (kind == BVIO_BLK_TD) base = ly.est_td ? ly.td_off : -1;
       for (int i = 0; i < loc; i++) map[p->block_idx[b] + i] = base < 0 ? -1 : base + i;
     }
     for (int a = 0; a < n; a++) {
@@ -466,6 +529,7 @@ bool schur_solve(const bvio_window* w, const Layout& ly, const Normal& N, const 
       for (int a = 0; a < 6; a++) { idx.push_back(15 * w->obs_frame[k] + a); wv.push_back(N.w[(size_t)6 * k + a]); }
     if (ly.est_ex)
       for (int a = 0; a < 6; a++) { idx.push_back(ly.ex_off + a); wv.push_back(N.wex[(size_t)6 * l + a]); }
+    if (ly.est_td) { idx.push_back(ly.td_off); wv.push_back(N.wtd[l]); }
     double inv = 1.0 / hl;
     int m = (int)idx.size();
     for (int a = 0; a < m; a++) {
@@ -490,6 +554,7 @@ bool schur_solve(const bvio_window* w, const Layout& ly, const Normal& N, const 
       for (int a = 0; a < 6; a++) s += N.w[(size_t)6 * k + a] * dp[15 * w->obs_frame[k] + a];
     if (ly.est_ex)
       for (int a = 0; a < 6; a++) s += N.wex[(size_t)6 * l + a] * dp[ly.ex_off + a];
+    if (ly.est_td) s += N.wtd[l] * dp[ly.td_off];
     dl[l] = -s / hl;
   }
   return true;
@@ -511,6 +576,7 @@ double quad_form(const bvio_window* w, const Layout& ly, const Normal& N, const 
       for (int a = 0; a < 6; a++) s += N.w[(size_t)6 * k + a] * xp[15 * w->obs_frame[k] + a];
     if (ly.est_ex)
       for (int a = 0; a < 6; a++) s += N.wex[(size_t)6 * l + a] * xp[ly.ex_off + a];
+    if (ly.est_td) s += N.wtd[l] * xp[ly.td_off];
     q += 2.0 * xl[l] * s + N.h[l] * xl[l] * xl[l];
   }
   return q;
@@ -529,6 +595,7 @@ void apply_plus(const bvio_window* src, bvio_window* dst, const Layout& ly, cons
   }
   if (ly.est_ex) pose_plus(src->para_ex_pose, dp + ly.ex_off, dst->para_ex_pose);
   else std::memcpy(dst->para_ex_pose, src->para_ex_pose, 7 * sizeof(double));
+  if (dst->para_td && src->para_td) dst->para_td[0] = src->para_td[0] + (ly.est_td ? dp[ly.td_off] : 0.0);
   for (int l = 0; l < ly.L; l++) dst->inv_depth[l] = src->inv_depth[l] + dl[l];
 }
 
@@ -555,6 +622,7 @@ void state_norms(const bvio_window* x, const bvio_window* c, const Layout& ly, d
   acc(x->para_pose, c->para_pose, 7 * ly.K);
   acc(x->para_speed_bias, c->para_speed_bias, 9 * ly.K);
   if (ly.est_ex) acc(x->para_ex_pose, c->para_ex_pose, 7);
+  if (ly.est_td) acc(x->para_td, c->para_td, 1);
   acc(x->inv_depth, c->inv_depth, ly.L);
   *x_norm = std::sqrt(xn);
   *step_norm = std::sqrt(sn);
@@ -564,6 +632,7 @@ void copy_state(const bvio_window* src, bvio_window* dst, const Layout& ly) {
   std::memcpy(dst->para_pose, src->para_pose, sizeof(double) * 7 * ly.K);
   std::memcpy(dst->para_speed_bias, src->para_speed_bias, sizeof(double) * 9 * ly.K);
   std::memcpy(dst->para_ex_pose, src->para_ex_pose, sizeof(double) * 7);
+  if (dst->para_td && src->para_td) dst->para_td[0] = src->para_td[0];
   std::memcpy(dst->inv_depth, src->inv_depth, sizeof(double) * ly.L);
 }
 
@@ -579,6 +648,17 @@ void oracle_projection_factor(const double pts_i[3], const double pts_j[3], cons
                               double res[2], double* jac_i, double* jac_j, double* jac_ex, double* jac_f) {
   projection_eval(v3(pts_i), v3(pts_j), v3(pose_i), q4(pose_i + 3), v3(pose_j), q4(pose_j + 3), v3(ex_pose),
                   q4(ex_pose + 3), inv_dep, sqrt_info, res, jac_i, jac_j, jac_ex, jac_f);
+}
+
+void oracle_projection_td_factor(const double pts_i[3], const double pts_j[3], const double vel_i[2],
+                                 const double vel_j[2], double td_i, double td_j, double row_i, double row_j, double TR,
+                                 double ROW, const double pose_i[7], const double pose_j[7], const double ex_pose[7],
+                                 double inv_dep, double td, double sqrt_info, double res[2], double* jac_i, double* jac_j,
+                                 double* jac_ex, double* jac_f, double* jac_td) {
+  projection_td_eval(v3(pts_i), v3(pts_j), TdObs{V3{vel_i[0], vel_i[1], 0.0}, td_i, row_i},
+                     TdObs{V3{vel_j[0], vel_j[1], 0.0}, td_j, row_j}, td, TR, ROW, v3(pose_i), q4(pose_i + 3), v3(pose_j),
+                     q4(pose_j + 3), v3(ex_pose), q4(ex_pose + 3), inv_dep, sqrt_info, res, jac_i, jac_j, jac_ex, jac_f,
+                     jac_td);
 }
 
 void oracle_imu_sqrt_info(const double cov[225], double sqrt_info[225]) { imu_sqrt_info(cov, sqrt_info); }
@@ -678,7 +758,7 @@ double oracle_cost(const bvio_window* w, const bvio_opts* opts) {
 
 int oracle_linearize(const bvio_window* w, const bvio_opts* opts, double* S, double* g, double* h, double* b,
                      double* cost) {
-  if (opts->estimate_td) return BVIO_ERR_UNSUPPORTED;
+  if (opts->estimate_td && (!w->obs_vel || !w->obs_td || !w->obs_row || !w->para_td)) return BVIO_ERR_INVALID;
   Layout ly = layout(w, opts);
   ImuCache ic;
   build_imu_cache(w, ic);
@@ -695,7 +775,7 @@ int oracle_linearize(const bvio_window* w, const bvio_opts* opts, double* S, dou
 }
 
 int oracle_optimize(bvio_window* w, const bvio_opts* o, bvio_summary* sum) {
-  if (o->estimate_td) return BVIO_ERR_UNSUPPORTED;
+  if (o->estimate_td && (!w->obs_vel || !w->obs_td || !w->obs_row || !w->para_td)) return BVIO_ERR_INVALID;
   auto t_start = std::chrono::steady_clock::now();
   Layout ly = layout(w, o);
   int np = ly.np, L = ly.L;

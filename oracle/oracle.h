@@ -34,6 +34,13 @@ void oracle_projection_factor(const double pts_i[3], const double pts_j[3], cons
                               const double pose_j[7], const double ex_pose[7], double inv_dep,
                               double sqrt_info, double res[2], double* jac_i, double* jac_j,
                               double* jac_ex, double* jac_f);
+/* a2': ProjectionTdFactor::Evaluate (projection_td_factor.cpp:34-141); jacobians 2x7 row-major, jac_f / jac_td 2x1 */
+void oracle_projection_td_factor(const double pts_i[3], const double pts_j[3], const double vel_i[2],
+                                 const double vel_j[2], double td_i, double td_j, double row_i, double row_j, double TR,
+                                 double ROW, const double pose_i[7], const double pose_j[7], const double ex_pose[7],
+                                 double inv_dep, double td, double sqrt_info, double res[2], double* jac_i, double* jac_j,
+                                 double* jac_ex, double* jac_f, double* jac_td);
+
 /* IMUFactor::Evaluate, imu_factor.h:19-179.  jac row-major 15x7,15x9,15x7,15x9. */
 void oracle_imu_factor(const bvio_preint* pre, const double G[3], const double pose_i[7],
                        const double sb_i[9], const double pose_j[7], const double sb_j[9],

@@ -22,6 +22,8 @@ def load():
     dp, ip, i32, d = abi.c_double_p, abi.c_int32_p, C.c_int32, C.c_double
     L.oracle_projection_factor.argtypes = [dp, dp, dp, dp, dp, d, d, dp, dp, dp, dp, dp]
     L.oracle_projection_factor.restype = None
+    L.oracle_projection_td_factor.argtypes = [dp, dp, dp, dp, d, d, d, d, d, d, dp, dp, dp, d, d, d, dp, dp, dp, dp, dp, dp]
+    L.oracle_projection_td_factor.restype = None
     L.oracle_imu_factor.argtypes = [C.POINTER(abi.Preint), dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     L.oracle_imu_factor.restype = None
     L.oracle_imu_sqrt_info.argtypes = [dp, dp]

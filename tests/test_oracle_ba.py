@@ -253,3 +253,91 @@ def test_double2vector_restores_gauge(mods):
         q = pose[i, 3:] * np.sign(pose[i, 6]) * np.sign(w.para_pose[i, 6])
         assert np.allclose(q, w.para_pose[i, 3:], atol=1e-12)
         assert np.allclose(sb[i, :3], w.para_speed_bias[i, :3], atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# a2': ProjectionTdFactor (projection_td_factor.cpp:34-141)
+# ---------------------------------------------------------------------------------------------
+def _td_factor(orc, abi, x, pts_i, pts_j, vel_i, vel_j, tdi, tdj, rowi, rowj, TR, ROW, jac=True):
+    pose_i, pose_j, ex, lam, td = x[:7].copy(), x[7:14].copy(), x[14:21].copy(), float(x[21]), float(x[22])
+    res = np.zeros(2)
+    Ji, Jj, Je, Jf, Jt = np.zeros(14), np.zeros(14), np.zeros(14), np.zeros(2), np.zeros(2)
+    orc.oracle_projection_td_factor(abi.dptr(pts_i), abi.dptr(pts_j), abi.dptr(vel_i), abi.dptr(vel_j), tdi, tdj, rowi,
+                                    rowj, TR, ROW, abi.dptr(pose_i), abi.dptr(pose_j), abi.dptr(ex), lam, td, 460 / 1.5,
+                                    abi.dptr(res), *(abi.dptr(a) if jac else None for a in (Ji, Jj, Je, Jf, Jt)))
+    return res, Ji.reshape(2, 7), Jj.reshape(2, 7), Je.reshape(2, 7), Jf, Jt
+
+
+def test_td_factor_jacobians_match_finite_differences(pkg, oracle):
+    """The check() convention of the reference (projection_td_factor.cpp:143-233): perturb each local coordinate
+    (pose blocks through PoseLocalParameterization::Plus) and compare with the analytic Jacobians."""
+    abi, S = pkg.abi, pkg.synth
+    rng = np.random.default_rng(0)
+    w = S.make_window(seed=4, K=6, L=8, td_true=0.004)
+    k_i, k_j = int(w.lm_obs_offset[2]), int(w.lm_obs_offset[2]) + 2
+    fi, fj = int(w.obs_frame[k_i]), int(w.obs_frame[k_j])
+    pts_i, pts_j = np.array([*w.obs_xy[k_i], 1.0]), np.array([*w.obs_xy[k_j], 1.0])
+    args = (pts_i, pts_j, w.obs_vel[k_i].copy(), w.obs_vel[k_j].copy(), 0.001, -0.002, float(w.obs_row[k_i]),
+            float(w.obs_row[k_j]), 0.03, 480.0)
+    x = np.concatenate([w.gt_pose[fi], w.gt_pose[fj], w.para_ex_pose, [w.gt_inv_depth[2]], [0.003]])
+    r0, Ji, Jj, Je, Jf, Jt = _td_factor(oracle, abi, x, *args)
+    assert np.abs(Ji[:, 6]).max() == 0 and np.abs(Jj[:, 6]).max() == 0 and np.abs(Je[:, 6]).max() == 0
+    ana = np.hstack([Ji[:, :6], Jj[:, :6], Je[:, :6], Jf[:, None], Jt[:, None]])
+    num = np.zeros_like(ana)
+    eps = 1e-6
+
+    def plus(pose, d):
+        q = S.quat_mul(pose[3:], np.array([d[3] / 2, d[4] / 2, d[5] / 2, 1.0]))
+        return np.concatenate([pose[:3] + d[:3], q / np.linalg.norm(q)])
+
+    for c in range(20):
+        xp = x.copy()
+        d = np.zeros(6)
+        if c < 18:
+            b = c // 6
+            d[c % 6] = eps
+            xp[7 * b:7 * b + 7] = plus(x[7 * b:7 * b + 7], d)
+        else:
+            xp[21 + (c - 18)] += eps
+        num[:, c] = (_td_factor(oracle, abi, xp, *args, jac=False)[0] - r0) / eps
+    assert np.abs(ana - num).max() <= 2e-5 * max(np.abs(ana).max(), 1.0), np.abs(ana - num).max()
+    assert np.abs(Jt).max() > 1.0        # the td column is really exercised
+
+
+def test_td_factor_reduces_to_projection_factor(pkg, oracle):
+    """td == td_i == td_j and TR == 0 (global shutter) leave the points unshifted: same residual and pose / depth
+    Jacobians as ProjectionFactor."""
+    abi, S = pkg.abi, pkg.synth
+    w = S.make_window(seed=5, K=6, L=8, td_true=0.0)
+    k_i, k_j = int(w.lm_obs_offset[1]), int(w.lm_obs_offset[1]) + 1
+    fi, fj = int(w.obs_frame[k_i]), int(w.obs_frame[k_j])
+    pts_i, pts_j = np.array([*w.obs_xy[k_i], 1.0]), np.array([*w.obs_xy[k_j], 1.0])
+    x = np.concatenate([w.para_pose[fi], w.para_pose[fj], w.para_ex_pose, [w.inv_depth[1]], [0.01]])
+    r, Ji, Jj, Je, Jf, Jt = _td_factor(oracle, abi, x, pts_i, pts_j, w.obs_vel[k_i].copy(), w.obs_vel[k_j].copy(),
+                                        0.01, 0.01, 100.0, 300.0, 0.0, 480.0)
+    res = np.zeros(2)
+    ji, jj, je, jf = np.zeros(14), np.zeros(14), np.zeros(14), np.zeros(2)
+    oracle.oracle_projection_factor(abi.dptr(pts_i), abi.dptr(pts_j), abi.dptr(x[:7].copy()), abi.dptr(x[7:14].copy()),
+                                    abi.dptr(x[14:21].copy()), float(x[21]), 460 / 1.5, abi.dptr(res), abi.dptr(ji),
+                                    abi.dptr(jj), abi.dptr(je), abi.dptr(jf))
+    assert np.array_equal(r, res) and np.array_equal(Ji.ravel(), ji) and np.array_equal(Jj.ravel(), jj)
+    assert np.array_equal(Je.ravel(), je) and np.array_equal(Jf, jf)
+
+
+@pytest.mark.parametrize("strategy", [0, 1])
+def test_estimate_td_recovers_time_offset(pkg, oracle, strategy):
+    """Noise-free observations generated 5 ms late, state started at the truth with td = 0: with ESTIMATE_TD the
+    solver pulls para_Td to the true offset (from a perturbed start td is only weakly observable over 1 s)."""
+    abi, S = pkg.abi, pkg.synth
+    w = S.make_window(seed=6, K=11, L=120, td_true=0.005, noise=False, perturb=False)
+    o = abi.default_opts(estimate_td=1, strategy=strategy, max_iters=40, function_tolerance=1e-14,
+                         gradient_tolerance=1e-12, parameter_tolerance=1e-14)
+    h, s = abi.WindowHandle(w), abi.Summary()
+    assert oracle.oracle_optimize(C.byref(h.s), C.byref(o), C.byref(s)) == 0
+    assert s.final_cost < 1e-5 * s.initial_cost
+    assert abs(h.td[0] - 0.005) < 1e-5, h.td
+    # without the td parameter the same data cannot be explained as well
+    o0 = abi.default_opts(max_iters=40, function_tolerance=1e-14, gradient_tolerance=1e-12, parameter_tolerance=1e-14)
+    h0, s0 = abi.WindowHandle(w), abi.Summary()
+    assert oracle.oracle_optimize(C.byref(h0.s), C.byref(o0), C.byref(s0)) == 0
+    assert s0.final_cost > 5 * s.final_cost
