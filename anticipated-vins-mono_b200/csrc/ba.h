@@ -63,7 +63,8 @@ struct BaBatch {                  // all pointers are device pointers
   int max_iters, jacobi_scaling;
   int strategy;                   // BVIO_STRATEGY_LM / BVIO_STRATEGY_DOGLEG
   int use_mma;                    // linearize with the FP64 tensor-core (DMMA) kernel (extrinsics fixed)
-  int est_ex;                     // estimate_extrinsic: np = 15K + 6, extrinsic block = pseudo-frame K
+  int est_ex;                     // estimate_extrinsic: +6 dims, extrinsic block = pseudo-frame K of the visual layout
+  int est_td;                     // estimate_td: +1 dim (after the extrinsic block), pseudo-frame K + est_ex
   double sqrt_info, cauchy_a, G[3];
   double function_tolerance, gradient_tolerance, parameter_tolerance, initial_radius, min_relative_decrease;
   // structure
@@ -77,6 +78,11 @@ struct BaBatch {                  // all pointers are device pointers
   const double* ex;               // [B][7] uploaded extrinsic pose
   double* exs[2];                 // [B][7] extrinsic state, double buffered (both = ex when it is constant)
   double* ex_out;                 // [B][7]
+  const double* td0;              // [B] uploaded camera-IMU time offset
+  double* tds[2];                 // [B] td state, double buffered
+  double* td_out;                 // [B]
+  const double2* obs_vel;         // [total_obs] feature velocity on the normalized plane (estimate_td only)
+  const double* obs_shift;        // [total_obs] -td_obs + TR/ROW (row - ROW/2) (estimate_td only)
   double* invd[2];                // [total_L]
   const double* pose0; const double* sb0; const double* invd0;   // uploaded initial state (for reset)
   double* pose_out; double* sb_out; double* invd_out;            // final state gathered from X[cur]
@@ -96,7 +102,7 @@ struct BaBatch {                  // all pointers are device pointers
   // linearization products
   double* h; double* b; double* sl2;   // [total_L]
   double* w;                      // [total_obs][6]
-  double* wex;                    // [total_L][6] extrinsic part of the landmark's coupling row (est_ex only)
+  double* wex;                    // [total_L][est_ex + est_td][6] extra-block parts of the landmark's coupling row
   double* tile_out;               // [B][T][tile_rec_doubles(K)]
   double* cost_out;               // [B][T+1][COST_REC]
   double* delta_p;                // [B][np]  LM step / Gauss-Newton step (dogleg)
@@ -113,8 +119,8 @@ int ba_launch_prepare(const BaBatch& bt, cudaStream_t st);
 int ba_launch_reset(const BaBatch& bt, cudaStream_t st);
 int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cudaEvent_t* ev = nullptr);  // ev[4]: before/after each kernel
 int ba_launch_finish(const BaBatch& bt, cudaStream_t st);
-size_t ba_linearize_smem_bytes(int K, int chunk_l, int est_ex);
-int ba_pick_chunk(int K, int est_ex);
+size_t ba_linearize_smem_bytes(int K, int chunk_l, int n_extra_blocks);
+int ba_pick_chunk(int K, int n_extra_blocks);
 size_t ba_solve_smem_bytes(int np);
 size_t ba_linearize_mma_smem_bytes(int K);
 size_t ba_marginalize_smem_bytes(int K, int nmax, int n);

@@ -21,7 +21,7 @@ struct bvio_batch {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of the last solve of this batch
   size_t in_bytes = 0;                 // [0, in_bytes): inputs, mirrored on the host
   size_t out_off = 0, out_bytes = 0;   // [out_off, out_off+out_bytes): outputs, mirrored on the host
-  size_t o_pose_out = 0, o_sb_out = 0, o_invd_out = 0, o_ex_out = 0, o_ctrl = 0;
+  size_t o_pose_out = 0, o_sb_out = 0, o_invd_out = 0, o_ex_out = 0, o_td_out = 0, o_ctrl = 0;
   std::vector<int> lm_base;
   std::vector<int> perm;          // [total_L] device landmark -> caller landmark (within its window)
   cudaGraphExec_t graph = nullptr;
@@ -104,10 +104,12 @@ int64_t bvio_launch_count(const bvio_ctx* ctx) { return ctx ? ctx->launches : 0;
 // ---------------------------------------------------------------------------------------------
 static int validate(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* o, int K0) {
   if (!w || !o) return fail(ctx, BVIO_ERR_INVALID, "null window/opts");
-  if (o->estimate_td)
-    return fail(ctx, BVIO_ERR_UNSUPPORTED, "estimate_td is not implemented on the device path");
-  if (o->estimate_extrinsic && w->K > BVIO_KMAX - 2)
-    return fail(ctx, BVIO_ERR_INVALID, "K out of range [2,14] with estimate_extrinsic (reduced system must fit one CTA's shared memory)");
+  if (o->estimate_td && (!w->obs_vel || !w->obs_td || !w->obs_row || !w->para_td))
+    return fail(ctx, BVIO_ERR_INVALID, "estimate_td needs obs_vel / obs_td / obs_row / para_td");
+  if (o->estimate_td && !(o->ROW > 0)) return fail(ctx, BVIO_ERR_INVALID, "estimate_td needs ROW > 0");
+  if (15 * w->K + (o->estimate_extrinsic ? 6 : 0) + (o->estimate_td ? 1 : 0) > 226 ||
+      w->K + (o->estimate_extrinsic ? 1 : 0) + (o->estimate_td ? 1 : 0) > BVIO_KMAX)
+    return fail(ctx, BVIO_ERR_INVALID, "K too large with estimate_extrinsic / estimate_td (reduced system must fit one CTA's shared memory)");
   if (o->strategy != BVIO_STRATEGY_LM && o->strategy != BVIO_STRATEGY_DOGLEG)
     return fail(ctx, BVIO_ERR_INVALID, "unknown trust-region strategy");
   if (w->K < 2 || w->K > BVIO_KMAX - 1) return fail(ctx, BVIO_ERR_INVALID, "K out of range [2,15] (reduced system must fit one CTA's shared memory)");
@@ -169,11 +171,11 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   if (!bb) return fail(ctx, BVIO_ERR_INVALID, "out of host memory");
   BaBatch& bt = bb->bt;
   memset(&bt, 0, sizeof bt);
-  const int est_ex = o->estimate_extrinsic != 0, KE = est_ex ? K + 1 : K;
-  bt.B = B; bt.K = K; bt.np = 15 * K + (est_ex ? 6 : 0); bt.total_L = total_L; bt.total_obs = total_obs; bt.nmax = nmax;
-  bt.est_ex = est_ex;
-  bt.use_mma = !est_ex && !getenv("BVIO_LEGACY_LINEARIZE");
-  bt.chunk_l = ba_pick_chunk(K, est_ex);
+  const int est_ex = o->estimate_extrinsic != 0, est_td = o->estimate_td != 0, XB = est_ex + est_td, KE = K + XB;
+  bt.B = B; bt.K = K; bt.np = 15 * K + (est_ex ? 6 : 0) + est_td; bt.total_L = total_L; bt.total_obs = total_obs; bt.nmax = nmax;
+  bt.est_ex = est_ex; bt.est_td = est_td;
+  bt.use_mma = XB == 0 && !getenv("BVIO_LEGACY_LINEARIZE");
+  bt.chunk_l = ba_pick_chunk(K, XB);
   int T = (maxL + 2 * bt.chunk_l - 1) / (2 * bt.chunk_l);   // >= 2 chunks per tile when there is a choice
   int Tcap = std::max(1, (10 * ctx->sm_count + B - 1) / B);   // ~5 waves of 2 CTAs/SM: measured optimum (tile record traffic vs tail)
   T = std::max(1, std::min(std::min(T, Tcap), 32));
@@ -197,6 +199,8 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   size_t o_obs_xy = cv.take((size_t)total_obs * 2 * D);
   size_t o_pose0 = cv.take((size_t)B * K * 7 * D), o_sb0 = cv.take((size_t)B * K * 9 * D), o_ex = cv.take((size_t)B * 7 * D);
   size_t o_invd0 = cv.take((size_t)total_L * D);
+  size_t o_td0 = cv.take((size_t)B * D);
+  size_t o_obs_vel = est_td ? cv.take((size_t)total_obs * 2 * D) : 0, o_obs_shift = est_td ? cv.take((size_t)total_obs * D) : 0;
   size_t o_preint = cv.take((size_t)B * K * PREINT_DOUBLES * D);
   size_t o_pr_n = cv.take(B * I), o_pr_nb = cv.take(B * I);
   size_t o_pr_kind = cv.take((size_t)B * PRIOR_MAXB * I), o_pr_frame = cv.take((size_t)B * PRIOR_MAXB * I);
@@ -209,6 +213,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bb->o_sb_out = cv.take((size_t)B * K * 9 * D);
   bb->o_invd_out = cv.take((size_t)total_L * D);
   bb->o_ex_out = cv.take((size_t)B * 7 * D);
+  bb->o_td_out = cv.take((size_t)B * D);
   bb->o_ctrl = cv.take((size_t)B * sizeof(BaCtrl));
   bb->out_bytes = cv.off - bb->out_off;
   const size_t h_bytes = cv.off;
@@ -224,7 +229,8 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   size_t o_w = cv.take((size_t)total_obs * 6 * D);
   size_t o_tile = cv.take((size_t)B * T * tile_rec_doubles(KE) * D);
   size_t o_exs[2] = {cv.take((size_t)B * 7 * D), cv.take((size_t)B * 7 * D)};
-  size_t o_wex = est_ex ? cv.take((size_t)total_L * 6 * D) : 0;
+  size_t o_wex = XB ? cv.take((size_t)total_L * XB * 6 * D) : 0;
+  size_t o_tds[2] = {cv.take((size_t)B * D), cv.take((size_t)B * D)};
   size_t o_cost = cv.take((size_t)B * (T + 1) * COST_REC * D);
   size_t o_dp = cv.take((size_t)B * bt.np * D), o_sp = cv.take((size_t)B * bt.np * D);
   size_t o_dog_t = 0, o_dog_l = 0, o_dog_out = 0;
@@ -259,6 +265,9 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   double* h_sb0 = (double*)(h + o_sb0);
   double* h_ex = (double*)(h + o_ex);
   double* h_invd0 = (double*)(h + o_invd0);
+  double* h_td0 = (double*)(h + o_td0);
+  double* h_obs_vel = (double*)(h + o_obs_vel);
+  double* h_obs_shift = (double*)(h + o_obs_shift);
   double* h_pre = (double*)(h + o_preint);
   int* h_pr_n = (int*)(h + o_pr_n);
   int* h_pr_nb = (int*)(h + o_pr_nb);
@@ -300,11 +309,17 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
       h_lm_off[lb + j] = run;
       memcpy(h_obs_frame + run, w.obs_frame + o0, n * I);
       memcpy(h_obs_xy + (size_t)2 * run, w.obs_xy + (size_t)2 * o0, (size_t)n * 2 * D);
+      if (est_td) {
+        memcpy(h_obs_vel + (size_t)2 * run, w.obs_vel + (size_t)2 * o0, (size_t)n * 2 * D);
+        // row centred like the factor's constructor (projection_td_factor.cpp:18-19)
+        for (int k = 0; k < n; k++) h_obs_shift[run + k] = -w.obs_td[o0 + k] + o->TR / o->ROW * (w.obs_row[o0 + k] - o->ROW / 2);
+      }
       run += n;
     }
     memcpy(h_pose0 + (size_t)b * K * 7, w.para_pose, (size_t)K * 7 * D);
     memcpy(h_sb0 + (size_t)b * K * 9, w.para_speed_bias, (size_t)K * 9 * D);
     memcpy(h_ex + (size_t)b * 7, w.para_ex_pose, 7 * D);
+    h_td0[b] = w.para_td ? w.para_td[0] : 0.0;
     for (int j = 0; j < w.L; j++) h_invd0[lb + j] = w.inv_depth[perm[j]];
     memcpy(h_pre + (size_t)b * K * PREINT_DOUBLES, w.preint, (size_t)K * sizeof(bvio_preint));
     h_pr_n[b] = 0; h_pr_nb[b] = 0;
@@ -345,6 +360,9 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bt.pose0 = (const double*)(d + o_pose0); bt.sb0 = (const double*)(d + o_sb0); bt.ex = (const double*)(d + o_ex);
   bt.exs[0] = (double*)(d + o_exs[0]); bt.exs[1] = (double*)(d + o_exs[1]); bt.ex_out = (double*)(d + bb->o_ex_out);
   bt.wex = (double*)(d + o_wex);
+  bt.td0 = (const double*)(d + o_td0); bt.tds[0] = (double*)(d + o_tds[0]); bt.tds[1] = (double*)(d + o_tds[1]);
+  bt.td_out = (double*)(d + bb->o_td_out);
+  bt.obs_vel = (const double2*)(d + o_obs_vel); bt.obs_shift = (const double*)(d + o_obs_shift);
   bt.invd0 = (const double*)(d + o_invd0); bt.preint_raw = (const double*)(d + o_preint);
   bt.pr_n = (const int*)(d + o_pr_n); bt.pr_nb = (const int*)(d + o_pr_nb);
   bt.pr_kind = (const int*)(d + o_pr_kind); bt.pr_frame = (const int*)(d + o_pr_frame); bt.pr_idx = (const int*)(d + o_pr_idx);
@@ -438,6 +456,7 @@ static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, b
   const double* sb = (const double*)(bb->slab.h + bb->o_sb_out);
   const double* invd = (const double*)(bb->slab.h + bb->o_invd_out);
   const double* exo = (const double*)(bb->slab.h + bb->o_ex_out);
+  const double* tdo = (const double*)(bb->slab.h + bb->o_td_out);
   const BaCtrl* ctrl = (const BaCtrl*)(bb->slab.h + bb->o_ctrl);
   int rc = BVIO_OK;
   for (int b = 0; b < bt.B; b++) {
@@ -449,6 +468,7 @@ static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, b
       const int* perm = bb->perm.data() + bb->lm_base[b];
       for (int j = 0; j < L; j++) w.inv_depth[perm[j]] = invd[bb->lm_base[b] + j];
       if (bt.est_ex) memcpy(w.para_ex_pose, exo + (size_t)b * 7, 7 * sizeof(double));
+      if (bt.est_td) w.para_td[0] = tdo[b];
     }
     const BaCtrl& c = ctrl[b];
     if (summaries) {
@@ -597,6 +617,8 @@ int bvio_batch_solve_timed(bvio_ctx* ctx, bvio_batch* bb, double out_ms[4], int3
 int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts, int32_t flag, bvio_prior_out* out) {
   if (!ctx || !w || !opts || !out || (flag != 0 && flag != 1)) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
   const int K = w->K;
+  if (opts->estimate_td)
+    return fail(ctx, BVIO_ERR_UNSUPPORTED, "bvio_marginalize: ProjectionTdFactor (estimate_td) is not implemented");
   int rc = validate(ctx, w, opts, K);
   if (rc) return rc;
   const bvio_prior* pr = w->prior;

@@ -52,6 +52,20 @@ __device__ __forceinline__ void stage_frames(const BaBatch& bt, int w, const dou
   }
 }
 
+// visual layout (6 dims per frame, then one 6-slot per extra block) <-> reduced layout (15 per frame, then the
+// extrinsic 6, then td 1)
+__device__ __forceinline__ int vis2red(const BaBatch& bt, int p, int r) {
+  if (p < bt.K) return 15 * p + r;
+  if (bt.est_ex && p == bt.K) return 15 * bt.K + r;
+  return r == 0 ? 15 * bt.K + 6 * bt.est_ex : -1;           // td lives in column 0 of its slot
+}
+__device__ __forceinline__ int red2vis(const BaBatch& bt, int i) {
+  if (i < 15 * bt.K) { const int p = i / 15, r = i - 15 * p; return r < 6 ? 6 * p + r : -1; }
+  const int j = i - 15 * bt.K;
+  if (bt.est_ex && j < 6) return 6 * bt.K + j;
+  return 6 * (bt.K + bt.est_ex);
+}
+
 struct ProjGeom {   // what both the residual-only and the full evaluation need
   d3 pimu_i, pimu_j, pcj;
 };
@@ -175,7 +189,7 @@ __device__ void imu_raw(const double* rec, const double* G, const double* pi, co
 // MarginalizationFactor::Evaluate residual: dx per kept block, r = r0 + J dx. Block-cooperative.
 // sdx, sr: shared [nmax]. Returns nothing; caller syncs.
 __device__ void prior_residual(const BaBatch& bt, int w, const double* pose, const double* sb, const double* ex,
-                               double* sdx, double* sr) {
+                               const double* td, double* sdx, double* sr) {
   int n = bt.pr_n[w], nb = bt.pr_nb[w];
   for (int bidx = threadIdx.x; bidx < nb; bidx += blockDim.x) {
     int kind = bt.pr_kind[w * PRIOR_MAXB + bidx], fr = bt.pr_frame[w * PRIOR_MAXB + bidx];
@@ -186,7 +200,7 @@ __device__ void prior_residual(const BaBatch& bt, int w, const double* pose, con
     if (kind == 1) {
       for (int i = 0; i < 9; i++) sdx[idx + i] = x[i] - x0[i];
     } else if (kind == 3) {
-      sdx[idx] = 0.0;   // td is constant on the device path
+      sdx[idx] = td[w] - x0[0];
     } else {
       for (int i = 0; i < 3; i++) sdx[idx + i] = x[i] - x0[i];
       q4 dq = qmul(qinv(q4{x0[3], x0[4], x0[5], x0[6]}), q4{x[3], x[4], x[5], x[6]});
@@ -273,7 +287,8 @@ __global__ void __launch_bounds__(BA_THREADS) ba_prepare_kernel(BaBatch bt) {
     int kind = bt.pr_kind[w * PRIOR_MAXB + bidx], fr = bt.pr_frame[w * PRIOR_MAXB + bidx];
     int idx = bt.pr_idx[w * PRIOR_MAXB + bidx];
     int loc = kind == 1 ? 9 : (kind == 3 ? 1 : 6);
-    int base = kind == 0 ? 15 * fr : (kind == 1 ? 15 * fr + 6 : ((kind == 2 && bt.est_ex) ? 15 * K : -1));   // TD constant
+    int base = kind == 0 ? 15 * fr : (kind == 1 ? 15 * fr + 6 : ((kind == 2 && bt.est_ex) ? 15 * K
+               : ((kind == 3 && bt.est_td) ? 15 * K + 6 * bt.est_ex : -1)));   // constant blocks drop out
     for (int i = 0; i < loc; i++) map[idx + i] = base < 0 ? -1 : base + i;
   }
   const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
@@ -292,6 +307,7 @@ __global__ void ba_reset_kernel(BaBatch bt) {
   for (size_t k = i; k < (size_t)bt.B * bt.K * 9; k += stride) bt.sb[0][k] = bt.sb0[k];
   for (size_t k = i; k < (size_t)bt.total_L; k += stride) bt.invd[0][k] = bt.invd0[k];
   for (size_t k = i; k < (size_t)bt.B * 7; k += stride) { bt.exs[0][k] = bt.ex[k]; bt.exs[1][k] = bt.ex[k]; }
+  for (size_t k = i; k < (size_t)bt.B; k += stride) { bt.tds[0][k] = bt.td0[k]; bt.tds[1][k] = bt.td0[k]; }
   for (size_t k = i; k < (size_t)bt.B; k += stride) {
     BaCtrl c;
     c.cost = 0; c.cand_cost = 0; c.radius = bt.initial_radius; c.decrease_factor = 2.0;
@@ -310,6 +326,7 @@ __global__ void ba_finish_kernel(BaBatch bt) {
   for (size_t k = i; k < (size_t)bt.B * np7; k += stride) bt.pose_out[k] = bt.pose[bt.ctrl[k / np7].cur][k];
   for (size_t k = i; k < (size_t)bt.B * np9; k += stride) bt.sb_out[k] = bt.sb[bt.ctrl[k / np9].cur][k];
   for (size_t k = i; k < (size_t)bt.B * 7; k += stride) bt.ex_out[k] = bt.exs[bt.ctrl[k / 7].cur][k];
+  for (size_t k = i; k < (size_t)bt.B; k += stride) bt.td_out[k] = bt.tds[bt.ctrl[k].cur][k];
   for (int w = blockIdx.x; w < bt.B; w += gridDim.x) {
     int cur = bt.ctrl[w].cur;
     for (int l = bt.lm_base[w] + threadIdx.x; l < bt.lm_base[w + 1]; l += blockDim.x) bt.invd_out[l] = bt.invd[cur][l];
@@ -377,7 +394,7 @@ __device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* s
   int n = bt.pr_n[w];
   double* po = bt.pr_out + (size_t)w * (bt.nmax + 1);
   if (n > 0) {
-    prior_residual(bt, w, pose, sb, bt.exs[cur], sdx, spr);
+    prior_residual(bt, w, pose, sb, bt.exs[cur], bt.tds[cur], sdx, spr);
     const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
     for (int a = threadIdx.x; a < n; a += blockDim.x) {
       double s = 0;
@@ -400,10 +417,12 @@ __device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* s
 //   A3  thread = landmark: LM damping of the eliminated depth, h/b/w to HBM
 //   B   thread = owner of fixed 1x6 strips of the 6K x 6K block matrix, accumulated in REGISTERS over the
 //       chunk's landmarks (fixed order => deterministic; no shared-memory accumulators, no atomics)
-// With EX (estimate_extrinsic, estimator.cpp:672-683) the extrinsic block is treated as pseudo-frame K of the
-// visual layout: every landmark "observes" it with w_ex = sum_f E_f^T c_f, and its J^T J terms are
-// (K,K) = sum_f E_f^T E_f, (K,anchor) = sum_f E_f^T A_f, (K,frame of f) = E_f^T B_f  (projection_factor.cpp:97-106).
-template <int NS, bool EX>
+// XB extra parameter blocks ride as pseudo-frames K .. K+XB-1 of the visual layout: the extrinsic pose (estimate_extrinsic,
+// estimator.cpp:672-683; Jacobian projection_factor.cpp:97-106) and/or the camera-IMU time offset td (estimate_td,
+// estimator.cpp:732-740; ProjectionTdFactor, projection_td_factor.cpp:34-141; a 2x1 Jacobian carried in column 0 of
+// a 2x6 slot).  Every landmark "observes" pseudo-frame x with w_x = sum_f X_f^T c_f, and its J^T J terms are
+// (x,x) = sum_f X_f^T X_f, (x,anchor) = sum_f X_f^T A_f, (x,frame of f) = X_f^T B_f, (td,ex) = sum_f T_f^T E_f.
+template <int NS, int XB>
 __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt) {
   extern __shared__ double sm[];
   const int w = blockIdx.y, t = blockIdx.x;
@@ -412,9 +431,11 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   const int cur = ctrl->cur;
   if (t == bt.T) { imu_prior_linearize(bt, w, cur, sm); return; }
 
-  constexpr int SG = EX ? STGX : STG;                 // per-factor staging stride
-  constexpr int NRED = EX ? 104 : 35;                 // per-landmark reductions over the factors
-  const int K = bt.K, KE = EX ? K + 1 : K, K6 = 6 * KE, NPb = KE * (KE + 1) / 2, FS = K - 1, CL = bt.chunk_l;
+  constexpr int SG = STG + 12 * XB;                   // per-factor staging stride (29 / 41 / 53: odd)
+  constexpr int NRED = 35 + 69 * XB + (XB == 2 ? 36 : 0);   // per-landmark reductions over the factors
+  constexpr bool EX = XB > 0;
+  const int K = bt.K, KE = K + XB, K6 = 6 * KE, NPb = KE * (KE + 1) / 2, FS = K - 1, CL = bt.chunk_l;
+  const int x_ex = bt.est_ex ? 0 : -1, x_td = bt.est_td ? bt.est_ex : -1;   // pseudo-frame index of each extra block
   const int tid = threadIdx.x;
   double* sFr = sm;                                  // [K*FR]
   double* sEx = sFr + K * FR;                        // [FR]
@@ -424,10 +445,11 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   double* sAtA = sW + (size_t)CL * K6;               // [CL*36]
   double* sgA = sAtA + (size_t)CL * 36;              // [CL*6]
   double* sSc = sgA + (size_t)CL * 6;                // [CL*4] inv_hd, b, h, -
-  double* sEtE = sSc + (size_t)CL * 4;               // EX: [CL*36] sum E^T E, [CL*36] sum E^T A, [CL*6] sum E^T r
-  double* sEtA = sEtE + (EX ? (size_t)CL * 36 : 0);
-  double* sgE = sEtA + (EX ? (size_t)CL * 36 : 0);
-  int* sMeta = reinterpret_cast<int*>(sgE + (EX ? (size_t)CL * 6 : 0));  // [CL*2] o0, n
+  double* sEtE = sSc + (size_t)CL * 4;               // [XB][CL*36] sum X^T X, then [XB][CL*36] sum X^T A,
+  double* sEtA = sEtE + (size_t)XB * CL * 36;        // [XB][CL*6] sum X^T r, and (XB == 2) [CL*36] sum X_1^T X_0
+  double* sgE = sEtA + (size_t)XB * CL * 36;
+  double* sXX = sgE + (size_t)XB * CL * 6;
+  int* sMeta = reinterpret_cast<int*>(sXX + (XB == 2 ? (size_t)CL * 36 : 0));  // [CL*2] o0, n
   signed char* sOidx = reinterpret_cast<signed char*>(sMeta + CL * 2);  // [CL*KE] frame -> observation index
 
   // Units this thread owns: a unit is half a 6x6 block (3 rows x 6 columns = 18 register accumulators).
@@ -471,7 +493,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   for (int lb = l0; lb < l1; lb += CL) {
     const int nl = min(CL, l1 - lb);
     __syncthreads();                                 // previous chunk fully consumed (and frames staged)
-    for (int i = tid; i < nl * KE; i += BA_THREADS) sOidx[i] = (EX && (i % KE) == K) ? (signed char)K : (signed char)-1;
+    for (int i = tid; i < nl * KE; i += BA_THREADS) sOidx[i] = (EX && (i % KE) >= K) ? (signed char)(i % KE) : (signed char)-1;
     __syncthreads();
     // ---- A1: factor evaluation
     {
@@ -483,7 +505,13 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
         if (f == 0) { sMeta[lc * 2] = o0; sMeta[lc * 2 + 1] = n; sOidx[lc * KE + fi] = 0; }
         if (f < n - 1) {
           const double lam = invd[l];
-          const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + f];
+          double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + f];
+          double2 vi = {0, 0}, vj = {0, 0};
+          if (XB > 0 && x_td >= 0) {   // pts_td = pts - (td - td_obs + TR/ROW row) velocity (projection_td_factor.cpp:51-52)
+            vi = bt.obs_vel[o0]; vj = bt.obs_vel[o0 + 1 + f];
+            const double td = bt.tds[cur][w], si_ = td + bt.obs_shift[o0], sj_ = td + bt.obs_shift[o0 + 1 + f];
+            pi.x -= si_ * vi.x; pi.y -= si_ * vi.y; pj.x -= sj_ * vj.x; pj.y -= sj_ * vj.y;
+          }
           const int fj = bt.obs_frame[o0 + 1 + f];
           sOidx[lc * KE + fj] = (signed char)(f + 1);
           const double* Fi = sFr + fi * FR;
@@ -521,7 +549,20 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
             cc[a] = sr * (-dot3(u, dimu) / lam);
           }
           st[24] = cc[0]; st[25] = cc[1]; st[26] = sr * r0; st[27] = sr * r1;
-          if (EX) {
+          if (XB > 0) {
+#pragma unroll
+            for (int k = 28; k < SG - 1; k++) st[k] = 0.0;
+          }
+          if (XB > 0 && x_td >= 0) {
+            // td Jacobian (projection_td_factor.cpp:131-136): -Q Ri ric velocity_i / lambda + sqrt_info velocity_j
+            const d3 rv = mv3(sEx, d3{vi.x, vi.y, 0.0});
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+              const d3 u = mtv3(Fi, d3{Q[a][0], Q[a][1], Q[a][2]});
+              st[28 + 12 * x_td + 6 * a] = sr * (-dot3(u, rv) / lam + si * (a == 0 ? vj.x : vj.y));
+            }
+          }
+          if (XB > 0 && x_ex >= 0) {
             // extrinsic Jacobian: reduce * [ ric^T (Rj^T Ri - I) | -tmp_r [pci]x + [tmp_r pci]x + [tvec]x ]
             // tmp_r = ric^T Rj^T Ri ric ; tvec = ric^T (Rj^T (Ri tic + Pi - Pj) - tic)  (projection_factor.cpp:100-105)
             const d3 tic{sEx[9], sEx[10], sEx[11]};
@@ -570,10 +611,13 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
       else if (o < 33) { p = o - 27; q = 26; p2 = p + 6; q2 = 27; }
       else if (o == 33) { p = 24; q = 24; p2 = 25; q2 = 25; }
       else if (o == 34) { p = 24; q = 26; p2 = 25; q2 = 27; }
-      else if (o < 56) { p = 28 + c_triA[o - 35]; q = 28 + c_triB[o - 35]; p2 = p + 6; q2 = q + 6; }
-      else if (o < 92) { const int i = (o - 56) / 6; p = 28 + i; q = (o - 56) - 6 * i; p2 = p + 6; q2 = q + 6; }
-      else if (o < 98) { p = 28 + (o - 92); q = 24; p2 = p + 6; q2 = 25; }
-      else { p = 28 + (o - 98); q = 26; p2 = p + 6; q2 = 27; }
+      else if (o < 35 + 69 * XB) {
+        const int x = (o - 35) / 69, r = (o - 35) - 69 * x, bx = 28 + 12 * x;
+        if (r < 21) { p = bx + c_triA[r]; q = bx + c_triB[r]; p2 = p + 6; q2 = q + 6; }                 // X^T X
+        else if (r < 57) { const int i = (r - 21) / 6; p = bx + i; q = (r - 21) - 6 * i; p2 = p + 6; q2 = q + 6; }   // X^T A
+        else if (r < 63) { p = bx + (r - 57); q = 24; p2 = p + 6; q2 = 25; }                             // X^T c
+        else { p = bx + (r - 63); q = 26; p2 = p + 6; q2 = 27; }                                         // X^T r
+      } else { const int i = (o - 35 - 138) / 6; p = 40 + i; q = 28 + (o - 35 - 138) - 6 * i; p2 = p + 6; q2 = q + 6; }   // X_1^T X_0
       const int nf = sMeta[lc * 2 + 1] - 1;
       const double* st = sFac + (size_t)lc * FS * SG;
       double s0 = 0, s1 = 0;
@@ -589,10 +633,13 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
       else if (o < 33) sgA[lc * 6 + (o - 27)] = sv;
       else if (o == 33) sSc[lc * 4 + 2] = sv;
       else if (o == 34) sSc[lc * 4 + 1] = sv;
-      else if (o < 56) { const int a = p - 28, b = q - 28; sEtE[lc * 36 + a * 6 + b] = sv; sEtE[lc * 36 + b * 6 + a] = sv; }
-      else if (o < 92) sEtA[lc * 36 + (o - 56)] = sv;
-      else if (o < 98) { sW[(size_t)lc * K6 + 6 * K + (o - 92)] = sv; bt.wex[(size_t)(lb + lc) * 6 + (o - 92)] = sv; }
-      else sgE[lc * 6 + (o - 98)] = sv;
+      else if (o < 35 + 69 * XB) {
+        const int x = (o - 35) / 69, r = (o - 35) - 69 * x, bx = 28 + 12 * x;
+        if (r < 21) { const int a = p - bx, b = q - bx; sEtE[(x * CL + lc) * 36 + a * 6 + b] = sv; sEtE[(x * CL + lc) * 36 + b * 6 + a] = sv; }
+        else if (r < 57) sEtA[(x * CL + lc) * 36 + (r - 21)] = sv;
+        else if (r < 63) { sW[(size_t)lc * K6 + 6 * (K + x) + (r - 57)] = sv; bt.wex[((size_t)(lb + lc) * XB + x) * 6 + (r - 57)] = sv; }
+        else sgE[(x * CL + lc) * 6 + (r - 63)] = sv;
+      } else sXX[lc * 36 + (o - 35 - 138)] = sv;
     }
     __syncthreads();
     // ---- A3: damping of the eliminated block (Ceres LevenbergMarquardtStrategy, Jacobi scaling), outputs
@@ -636,18 +683,21 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
         for (int i = 0; i < 3; i++)
 #pragma unroll
           for (int c = 0; c < 6; c++) acc[u][i][c] = fma(war[i], wbv[c], acc[u][i][c]);
-        if (EX && a == K) {
-          if (b == K || b == 0) {
-            const double* at = (b == K ? sEtE : sEtA) + lc * 36 + r0 * 6;   // sum_f E^T E / sum_f E^T A
+        if (EX && a >= K) {
+          const int x = a - K;
+          if (b >= K || b == 0) {
+            // sum_f X^T X (diagonal), sum_f X_1^T X_0 (td against extrinsics), sum_f X^T A (against the anchor)
+            const double* at = (b == a ? sEtE + (x * CL + lc) * 36 : (b >= K ? sXX + lc * 36 : sEtA + (x * CL + lc) * 36)) + r0 * 6;
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
               for (int c = 0; c < 6; c++) acc[u][i][c] += at[i * 6 + c];
           } else {
-            const double* st = F + (b - 1) * SG;                             // E_f^T B_f, f = b - 1
+            const double* st = F + (b - 1) * SG;                             // X_f^T B_f, f = b - 1
+            const int bx = 28 + 12 * x;
             double x0[3], x1[3], y0[6], y1[6];
 #pragma unroll
-            for (int i = 0; i < 3; i++) { x0[i] = st[28 + r0 + i]; x1[i] = st[34 + r0 + i]; }
+            for (int i = 0; i < 3; i++) { x0[i] = st[bx + r0 + i]; x1[i] = st[bx + 6 + r0 + i]; }
 #pragma unroll
             for (int c = 0; c < 6; c++) { y0[c] = st[12 + c]; y1[c] = st[18 + c]; }
 #pragma unroll
@@ -685,7 +735,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
           const int a = oi[gp];
           if (a < 0) continue;
           double gv, dv;
-          if (EX && a == K) { gv = sgE[lc * 6 + gr]; dv = sEtE[lc * 36 + gr * 7]; }
+          if (EX && a >= K) { gv = sgE[((a - K) * CL + lc) * 6 + gr]; dv = sEtE[((a - K) * CL + lc) * 36 + gr * 7]; }
           else if (a == 0) { gv = sgA[lc * 6 + gr]; dv = sAtA[lc * 36 + gr * 7]; }
           else {
             const double* st = F + (a - 1) * SG;
@@ -1066,13 +1116,13 @@ size_t ba_linearize_mma_smem_bytes(int K) {
 // =============================================================================================
 // solve: one CTA per window
 // =============================================================================================
-// EX: the reduced system carries the 6 extrinsic dimensions after the K 15-blocks (np = 15K + 6); the last
-// Cholesky panel is then 6 wide (BW = panel width is a compile-time 15 otherwise).
+// EX: the reduced system carries extra dimensions after the K 15-blocks (6 extrinsic and/or 1 td: np = 15K + 6 / + 1 /
+// + 7); the last Cholesky panel is then partial (the panel width is a compile-time 15 otherwise).
 template <bool EX>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, int with_step) {
   extern __shared__ double sm[];
-  const int w = blockIdx.x, K = bt.K, np = bt.np, KE = EX ? K + 1 : K, K6 = 6 * KE, NPb = KE * (KE + 1) / 2;
-  const int NB = KE;                               // diagonal panels of the blocked Cholesky
+  const int w = blockIdx.x, K = bt.K, np = bt.np, KE = K + bt.est_ex + bt.est_td, K6 = 6 * KE, NPb = KE * (KE + 1) / 2;
+  const int NB = (np + 14) / 15;                   // diagonal panels of the blocked Cholesky
   const int tid = threadIdx.x, nthr = blockDim.x;
   BaCtrl* ctrl = bt.ctrl + w;
   if (ctrl->done) return;
@@ -1106,7 +1156,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
     int blk = idx / 36, rc = idx - blk * 36, r = rc / 6, c = rc - r * 6;
     int p = c_triA[blk], q = c_triB[blk];
     if (p == q && c > r) continue;
-    S[tri(15 * p + r, 15 * q + c)] = s;
+    const int ri = vis2red(bt, p, r), ci = vis2red(bt, q, c);
+    if (ri < 0 || ci < 0) continue;
+    S[tri(ri, ci)] = s;
   }
   __syncthreads();
   // IMU blocks: odd then even factors (consecutive factors overlap on one frame block)
@@ -1130,10 +1182,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
   for (int i = tid; i < np; i += nthr) {
     int p = i / 15, r = i - p * 15;
     double g1 = 0, g2 = 0, d = 0;
-    if (r < 6) {
+    const int v = red2vis(bt, i);
+    if (v >= 0) {
       for (int t = 0; t < bt.T; t++) {
         const double* rec = tiles + (size_t)t * TREC + NPb * 36;
-        g2 += rec[6 * p + r]; g1 += rec[K6 + 6 * p + r]; d += rec[2 * K6 + 6 * p + r];
+        g2 += rec[v]; g1 += rec[K6 + v]; d += rec[2 * K6 + v];
       }
     }
     if (p + 1 < K) { const double* o = imo + (size_t)(p + 1) * IMU_OUT; g1 += o[465 + r]; g2 += o[465 + r]; d += o[tri(r, r)]; }
@@ -1457,10 +1510,14 @@ __global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
 #pragma unroll
       for (int k = 0; k < 6; k++) { wn += wp[k] * sn[15 * fr + k]; wt += wp[k] * st[15 * fr + k]; }
     }
-    if (bt.est_ex && l16 == 0) {
-      const double* wp = bt.wex + (size_t)l * 6;
+    if (l16 == 0 && (bt.est_ex | bt.est_td)) {      // extra blocks: extrinsic (6) and / or td (column 0 of its slot)
+      const int XB = bt.est_ex + bt.est_td;
+      const double* wp = bt.wex + (size_t)l * XB * 6;
+      if (bt.est_ex) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) { wn += wp[k] * sn[15 * bt.K + k]; wt += wp[k] * st[15 * bt.K + k]; }
+        for (int k = 0; k < 6; k++) { wn += wp[k] * sn[15 * bt.K + k]; wt += wp[k] * st[15 * bt.K + k]; }
+      }
+      if (bt.est_td) { const int o = 15 * bt.K + 6 * bt.est_ex; wn += wp[6 * bt.est_ex] * sn[o]; wt += wp[6 * bt.est_ex] * st[o]; }
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) { wn += __shfl_xor_sync(gmask, wn, o, 16); wt += __shfl_xor_sync(gmask, wt, o, 16); }
@@ -1544,7 +1601,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
   const int cur = ctrl->cur, nxt = cur ^ 1;
   double* sdp = sm;                 // [np]
   double* sPose = sdp + np;         // [(K+1)*7] candidate poses, then the (candidate) extrinsic pose
-  double* sFr = sPose + (K + 1) * 7;   // [K*FR]
+  double* sFr = sPose + (K + 1) * 7 + 1;   // [K*FR]; sPose[(K+1)*7] = candidate td
   double* sEx = sFr + K * FR;       // [FR]
   double* red = sEx + FR;           // [16*4 + 32]
   double* extra = red + 96;         // IMU/prior CTA scratch
@@ -1561,6 +1618,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
     if (k < K) pose_plus(bt.pose[cur] + (size_t)(w * K + k) * 7, sdp + 15 * k, sPose + k * 7);
     else if (bt.est_ex) pose_plus(bt.exs[cur] + (size_t)w * 7, sdp + 15 * K, sPose + K * 7);
     else for (int i = 0; i < 7; i++) sPose[K * 7 + i] = bt.exs[cur][(size_t)w * 7 + i];
+    if (k == K) sPose[(K + 1) * 7] = bt.tds[cur][w] + (bt.est_td ? sdp[15 * K + 6 * bt.est_ex] : 0.0);
   }
   __syncthreads();
   double* co = bt.cost_out + (size_t)(w * (bt.T + 1) + t) * COST_REC;
@@ -1592,10 +1650,13 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
           const double* d = sdp + 15 * myfr;
 #pragma unroll
           for (int k = 0; k < 6; k++) part += wp[k] * d[k];
-          if (bt.est_ex && l16 == 0) {
-            const double* we = bt.wex + (size_t)l * 6;
+          if (l16 == 0 && (bt.est_ex | bt.est_td)) {
+            const double* we = bt.wex + (size_t)l * (bt.est_ex + bt.est_td) * 6;
+            if (bt.est_ex) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) part += we[k] * sdp[15 * K + k];
+              for (int k = 0; k < 6; k++) part += we[k] * sdp[15 * K + k];
+            }
+            if (bt.est_td) part += we[6 * bt.est_ex] * sdp[15 * K + 6 * bt.est_ex];
           }
         }
       }
@@ -1611,7 +1672,12 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       double lamc = lam + dl;
       double fc = 0;
       if (l16 >= 1 && l16 < n) {
-        const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + l16];
+        double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + l16];
+        if (bt.est_td) {
+          const double tdc = sPose[(K + 1) * 7], si_ = tdc + bt.obs_shift[o0], sj_ = tdc + bt.obs_shift[o0 + l16];
+          const double2 vi = bt.obs_vel[o0], vj = bt.obs_vel[o0 + l16];
+          pi.x -= si_ * vi.x; pi.y -= si_ * vi.y; pj.x -= sj_ * vj.x; pj.y -= sj_ * vj.y;
+        }
         ProjGeom g = proj_geom(sFr + fi * FR, sFr + myfr * FR, sEx, pi.x, pi.y, lamc);
         double inv = 1.0 / g.pcj.z;
         double r0 = bt.sqrt_info * (g.pcj.x * inv - pj.x), r1 = bt.sqrt_info * (g.pcj.y * inv - pj.y);
@@ -1655,6 +1721,10 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       double v = sPose[K * 7 + threadIdx.x], o = bt.exs[cur][(size_t)w * 7 + threadIdx.x];
       bt.exs[nxt][(size_t)w * 7 + threadIdx.x] = v; s2 += (o - v) * (o - v); x2 += o * o;
     }
+    if (bt.est_td && threadIdx.x == 32) {
+      const double v = sPose[(K + 1) * 7], o = bt.tds[cur][w];
+      bt.tds[nxt][w] = v; s2 += (o - v) * (o - v); x2 += o * o;
+    }
     for (int i = threadIdx.x; i < K * 9; i += blockDim.x) {
       int k = i / 9, r = i - k * 9;
       double o = sc[i], v = o + sdp[15 * k + 6 + r];
@@ -1689,7 +1759,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       // written to the nxt buffers by this CTA
       __threadfence_block();
       __syncthreads();
-      prior_residual(bt, w, bt.pose[nxt], bt.sb[nxt], bt.exs[nxt], sdx, spr);
+      prior_residual(bt, w, bt.pose[nxt], bt.sb[nxt], bt.exs[nxt], bt.tds[nxt], sdx, spr);
       for (int i = threadIdx.x; i < n; i += blockDim.x) c += 0.5 * spr[i] * spr[i];
     }
     c = block_sum(c, red);
@@ -1723,17 +1793,17 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
 // =============================================================================================
 static size_t imu_prior_smem(int K, int nmax) { return sizeof(double) * ((size_t)(K - 1) * (900 + 30) + 2 * nmax); }
 
-size_t ba_linearize_smem_bytes(int K, int CL, int est_ex) {
-  const int FS = K - 1, KE = est_ex ? K + 1 : K;
-  size_t d = (size_t)(K + 1) * FR + 16 + (size_t)CL * (FS * (est_ex ? STGX : STG) + 6 * KE + 36 + 6 + 4 + (est_ex ? 78 : 0));
+size_t ba_linearize_smem_bytes(int K, int CL, int XB) {
+  const int FS = K - 1, KE = K + XB;
+  size_t d = (size_t)(K + 1) * FR + 16 + (size_t)CL * (FS * (STG + 12 * XB) + 6 * KE + 36 + 6 + 4 + 78 * XB + (XB == 2 ? 36 : 0));
   size_t bytes = d * sizeof(double) + (size_t)CL * 2 * sizeof(int) + (size_t)CL * KE;
   return (bytes + 15) & ~size_t(15);
 }
 // landmarks per chunk: one (landmark, factor) slot per thread, capped so that two CTAs fit an SM
-int ba_pick_chunk(int K, int est_ex) {
+int ba_pick_chunk(int K, int XB) {
   int CL = BA_THREADS / (K - 1);
   if (CL > 64) CL = 64;
-  while (CL > 1 && ba_linearize_smem_bytes(K, CL, est_ex) > 100 * 1024) CL--;
+  while (CL > 1 && ba_linearize_smem_bytes(K, CL, XB) > 100 * 1024) CL--;
   return CL;
 }
 size_t ba_solve_smem_bytes(int np) {
@@ -1741,7 +1811,7 @@ size_t ba_solve_smem_bytes(int np) {
   return sizeof(double) * ((size_t)N1 * (N1 + 1) / 2 + 7 * np + 32);
 }
 static size_t cost_smem(int K, int nmax) {
-  return sizeof(double) * ((size_t)15 * K + 6 + (K + 1) * 7 + (K + 1) * FR + 96 + K * 9 + (K - 1) * 15 + 2 * nmax);
+  return sizeof(double) * ((size_t)15 * K + 8 + (K + 1) * 7 + (K + 1) * FR + 96 + K * 9 + (K - 1) * 15 + 2 * nmax);
 }
 
 static bool g_tables_done = false;
@@ -1758,10 +1828,11 @@ int ba_configure(void) {
     if ((err = cudaMemcpyToSymbol(c_triB, tb, sizeof tb)) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_tri30A, ua, sizeof ua)) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_tri30B, ub, sizeof ub)) != cudaSuccess) return err;
-#define BVIO_LIN_ATTR(NS, EX) \
-    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<NS, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
-    BVIO_LIN_ATTR(1, false) BVIO_LIN_ATTR(2, false) BVIO_LIN_ATTR(3, false) BVIO_LIN_ATTR(4, false)
-    BVIO_LIN_ATTR(1, true) BVIO_LIN_ATTR(2, true) BVIO_LIN_ATTR(3, true) BVIO_LIN_ATTR(4, true)
+#define BVIO_LIN_ATTR(NS, XB) \
+    if ((err = cudaFuncSetAttribute(ba_linearize_kernel<NS, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)) != cudaSuccess) return err;
+    BVIO_LIN_ATTR(1, 0) BVIO_LIN_ATTR(2, 0) BVIO_LIN_ATTR(3, 0) BVIO_LIN_ATTR(4, 0)
+    BVIO_LIN_ATTR(1, 1) BVIO_LIN_ATTR(2, 1) BVIO_LIN_ATTR(3, 1) BVIO_LIN_ATTR(4, 1)
+    BVIO_LIN_ATTR(1, 2) BVIO_LIN_ATTR(2, 2) BVIO_LIN_ATTR(3, 2) BVIO_LIN_ATTR(4, 2)
 #undef BVIO_LIN_ATTR
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
@@ -1788,15 +1859,17 @@ int ba_launch_reset(const BaBatch& bt, cudaStream_t st) {
   return 1;
 }
 int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cudaEvent_t* ev) {
-  size_t s1 = ba_linearize_smem_bytes(bt.K, bt.chunk_l, bt.est_ex), s1b = imu_prior_smem(bt.K, bt.nmax);
+  const int XB = bt.est_ex + bt.est_td;
+  size_t s1 = ba_linearize_smem_bytes(bt.K, bt.chunk_l, XB), s1b = imu_prior_smem(bt.K, bt.nmax);
   if (s1b > s1) s1 = s1b;
   if (ev) cudaEventRecord(ev[0], st);
-  const int KE = bt.est_ex ? bt.K + 1 : bt.K;
+  const int KE = bt.K + XB;
   const int nstrip = (KE * (KE + 1) / 2) * 2;   // half-block units
   const dim3 grid(bt.T + 1, bt.B);
 #define BVIO_LIN(NS) \
-  { if (bt.est_ex) ba_linearize_kernel<NS, true><<<grid, BA_THREADS, s1, st>>>(bt); \
-    else ba_linearize_kernel<NS, false><<<grid, BA_THREADS, s1, st>>>(bt); }
+  { if (XB == 2) ba_linearize_kernel<NS, 2><<<grid, BA_THREADS, s1, st>>>(bt); \
+    else if (XB == 1) ba_linearize_kernel<NS, 1><<<grid, BA_THREADS, s1, st>>>(bt); \
+    else ba_linearize_kernel<NS, 0><<<grid, BA_THREADS, s1, st>>>(bt); }
   if (bt.use_mma) {
     size_t sm1 = ba_linearize_mma_smem_bytes(bt.K);
     if (s1b > sm1) sm1 = s1b;
@@ -1811,7 +1884,7 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
   else BVIO_LIN(4)
 #undef BVIO_LIN
   if (ev) cudaEventRecord(ev[1], st);
-  if (bt.est_ex) ba_solve_kernel<true><<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.np), st>>>(bt, with_step ? 1 : 0);
+  if (XB) ba_solve_kernel<true><<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.np), st>>>(bt, with_step ? 1 : 0);
   else ba_solve_kernel<false><<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.np), st>>>(bt, with_step ? 1 : 0);
   if (!with_step || bt.undamped) { if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); } return 2; }
   int nk = 3;
@@ -2065,7 +2138,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         for (int i = 0; i < loc; i++) pmap[idx + i] = base < 0 ? -1 : base + i;
       }
       __syncthreads();
-      prior_residual(bt, w, bt.pose0, bt.sb0, bt.ex, sdx, spr);
+      prior_residual(bt, w, bt.pose0, bt.sb0, bt.ex, bt.td0, sdx, spr);
       const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
       for (int e = tid; e < np_ * np_; e += nt) {
         int a = e / np_, c = e - a * np_;

@@ -32,7 +32,7 @@ def _linearize_both(env, w, **opts_kw):
     abi, synth, orc, ctx = env
     o = abi.default_opts(**opts_kw)
     h1, h2 = abi.WindowHandle(w), abi.WindowHandle(w)
-    np_ = 15 * w.K + (6 if opts_kw.get("estimate_extrinsic") else 0)
+    np_ = 15 * w.K + (6 if opts_kw.get("estimate_extrinsic") else 0) + (1 if opts_kw.get("estimate_td") else 0)
     L = w.L
     out = {}
     for name, fn, hh in (("gpu", None, h1), ("cpu", orc.oracle_linearize, h2)):
@@ -191,6 +191,63 @@ def test_extrinsic_reference_budget_trajectory(env, seed, strategy):
     assert np.linalg.norm(xg - xo) <= 1e-8 * np.linalg.norm(xo)
 
 
+@pytest.mark.parametrize("seed,K,L,ex,TR", [(0, 11, 150, 0, 0.0), (1, 11, 150, 1, 0.0), (2, 2, 20, 0, 0.0),
+                                            (3, 5, 37, 1, 0.02), (4, 11, 1500, 0, 0.03), (5, 14, 64, 1, 0.0)])
+def test_td_linearize_matches_oracle(env, seed, K, L, ex, TR):
+    """ESTIMATE_TD (estimator.cpp:732-740): ProjectionTdFactor on time-shifted points, para_Td free: the reduced
+    system carries the td row / column after the frames (and after the extrinsic block when that is free too)."""
+    abi, synth, orc, ctx = env
+    kw = dict(track_min=2, track_max=2) if K == 2 else {}
+    w = synth.make_window(seed=seed, K=K, L=L, td_true=0.004, **kw)
+    w.para_td[0] = 0.001
+    if ex:
+        w = _perturb_extrinsic(synth, w, seed)
+    n = 15 * K + 6 * ex + 1
+    r = _linearize_both(env, w, estimate_td=1, estimate_extrinsic=ex, TR=TR)
+    (S1, g1, h1, b1, c1), (S2, g2, h2, b2, c2) = r["gpu"], r["cpu"]
+    assert np.isfinite(S1).all() and S1.shape == (n, n)
+    assert np.abs(S2[n - 1, :]).max() > 0
+    assert abs(c1 - c2) <= 1e-11 * abs(c2)
+    assert np.abs(h1 - h2).max() <= 1e-11 * np.abs(h2).max()
+    assert np.abs(S1 - S2).max() <= 1e-9 * np.abs(S2).max()
+    assert np.abs(g1 - g2).max() <= 1e-9 * max(np.abs(g2).max(), 1.0)
+    assert np.abs(S1 - S1.T).max() == 0.0
+
+
+@pytest.mark.parametrize("seed,strategy,ex", [(0, 0, 0), (1, 0, 1), (2, 1, 0), (3, 1, 1)])
+def test_td_converged_state_matches_oracle(env, seed, strategy, ex):
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=seed, K=11, L=150, td_true=0.006)
+    if ex:
+        w = _perturb_extrinsic(synth, w, seed)
+    hg, ho, sg, so = _solve_both(env, w, dict(estimate_td=1, estimate_extrinsic=ex, strategy=strategy, TR=0.01, **TIGHT))
+    xg, xo = hg.state_vector(), ho.state_vector()
+    assert np.linalg.norm(xg - xo) <= 1e-6 * np.linalg.norm(xo), (sg.as_dict(), so.as_dict())
+    assert abs(hg.td[0] - ho.td[0]) <= 1e-6 * max(abs(ho.td[0]), 1e-3), (hg.td, ho.td)
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    assert abs(hg.td[0]) > 1e-5                      # the offset really moved away from 0
+
+
+@pytest.mark.parametrize("seed,strategy", [(10, 0), (11, 1)])
+def test_td_reference_budget_trajectory(env, seed, strategy):
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=seed, K=11, L=150, td_true=0.006)
+    hg, ho, sg, so = _solve_both(env, w, dict(estimate_td=1, strategy=strategy))
+    assert (sg.iterations, sg.num_accepted, sg.num_rejected, sg.termination) == \
+           (so.iterations, so.num_accepted, so.num_rejected, so.termination), (sg.as_dict(), so.as_dict())
+    assert np.linalg.norm(hg.state_vector() - ho.state_vector()) <= 1e-8 * np.linalg.norm(ho.state_vector())
+    assert abs(hg.td[0] - ho.td[0]) <= 1e-8
+
+
+def test_td_recovers_time_offset_on_device(env):
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=6, K=11, L=120, td_true=0.005, noise=False, perturb=False)
+    o = abi.default_opts(estimate_td=1, **TIGHT)
+    h, s = abi.WindowHandle(w), abi.Summary()
+    ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(o), C.byref(s)), "bvio_optimize")
+    assert abs(h.td[0] - 0.005) < 1e-5, h.td
+
+
 def test_stress_window_1500_features(env):
     """BASELINE config 3: 11-kf / 1500-feature window."""
     abi, synth, orc, ctx = env
@@ -245,7 +302,7 @@ def test_rejects_unsupported_and_invalid(env):
     w = synth.make_window(seed=0, K=4, L=10)
     h = abi.WindowHandle(w)
     s = abi.Summary()
-    assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(estimate_td=1)), C.byref(s)) == -4
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(estimate_td=1)), C.byref(s)) == -1   # no obs_vel
     assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(strategy=7)), C.byref(s)) == -1
     w15 = synth.make_window(seed=0, K=15, L=10)
     h15 = abi.WindowHandle(w15)
