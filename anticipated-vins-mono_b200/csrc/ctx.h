@@ -54,6 +54,11 @@ struct bvio_ctx {
   // multi-GPU selector
   ncclComm* comm = nullptr;
   int rank = 0, world = 1;
+  // fused selector exchange: this rank's mailbox and every rank's mailbox mapped through CUDA IPC
+  void* mbox_local = nullptr;
+  void* mbox_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool p2p_ready = false;
+  unsigned long long sel_epoch = 0;
 };
 
 namespace bvio {

@@ -17,6 +17,9 @@ namespace bvio {
 
 constexpr int SEL_WARPS = 8;          // warps per CTA in the build / round kernels
 constexpr int SEL_REC_HDR = 4;        // winner record header: value, second, candidate index, prob
+constexpr int SEL_MAX_WORLD = 8;      // ranks of the fused (peer-memory) exchange: one NVSwitch domain
+constexpr size_t SEL_MBOX_BYTES = 4096;   // per-rank mailbox: [2 parities][world][4] doubles, then [2][world] u64 epoch flags
+constexpr size_t SEL_MBOX_FLAG_OFF = 2048;
 
 struct SelCtrl {
   unsigned long long scored;          // (candidate, round) log-dets evaluated (all ranks after finalize)
@@ -25,12 +28,20 @@ struct SelCtrl {
   double final_logdet;
   int n_selected, round, n_valid, pad;
   unsigned int ticket, pad2;
+  int peer_timeout, pad3;             // fused exchange: a peer's record did not arrive within the time limit
 };
 
 struct SelProb {
   int H, T, TT, D, Do;                // T = 3H, TT = T(T+1)/2, D = 9(H+1), Do = D - T
   int N, U, C, kappa, nr_imu;
   int c0, c1;                         // candidates scored by this rank: [c0, c1)
+  int b0, b1;                         // candidates whose information blocks this rank builds: [c0, c1), or all of
+                                      // them in fused mode (the build is 1 % of a select; replicating it means a
+                                      // round's exchange is a 32-byte record instead of a 3.7 KB block)
+  int fused;                          // multi-GPU rounds inside the persistent kernel, exchange over peer memory
+  unsigned long long epoch_base;      // flags carry epoch_base + round + 1: never reset, never ambiguous
+  double* mbox; unsigned long long* mflag;                     // this rank's mailbox (peers write into it)
+  double* peer_mbox[SEL_MAX_WORLD]; unsigned long long* peer_flag[SEL_MAX_WORLD];   // every rank's mailbox, peer-mapped
   int rank, world;
   int grid_round;                     // CTAs of the round kernel
   int grid_persist, cpw;              // persistent single-kernel path: CTAs, candidates per warp (0 = not used)

@@ -9,6 +9,7 @@
 #include "ctx.h"
 #include <dlfcn.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <new>
 
@@ -26,7 +27,7 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
-static const int kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0;
+static const int kNcclInt8 = 0, kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0;
 
 static bool nccl_load() {
   if (g_nccl.lib) return true;
@@ -100,7 +101,28 @@ static int sel_upload_impl(bvio_ctx* ctx, const bvio_select_in* in, bool use_cac
   sp.c1 = std::min(N, (sp.rank + 1) * per);
   const int nloc = sp.c1 - sp.c0;
   sp.grid_round = std::max(1, std::min((nloc + SEL_WARPS - 1) / SEL_WARPS, 4 * ctx->sm_count));
+  sp.b0 = sp.c0; sp.b1 = sp.c1;
+  // multi-GPU: all greedy rounds in the persistent kernel with the exchange over peer memory when the mailboxes
+  // are mapped and the shard fits the co-resident grid on EVERY rank (the plan depends only on N / world sizes);
+  // otherwise one kernel per round with an ncclAllGather in between
+  sp.fused = (sharded && sp.world > 1 && ctx->p2p_ready && !getenv("BVIO_SEL_NCCL") && (sp.world - 1) * per < N) ? 1 : 0;
+  if (sp.fused) {
+    SelProb probe = sp;                       // the largest shard (rank 0's) decides for all ranks
+    probe.c0 = 0; probe.c1 = std::min(N, per);
+    if (!sel_plan_persist(probe, ctx->sm_count)) sp.fused = 0;
+  }
+  if (sp.fused) {
+    sp.b0 = 0; sp.b1 = N;
+    sp.epoch_base = ctx->sel_epoch;
+    sp.mbox = (double*)ctx->mbox_local;
+    sp.mflag = (unsigned long long*)((char*)ctx->mbox_local + SEL_MBOX_FLAG_OFF);
+    for (int r = 0; r < sp.world; r++) {
+      sp.peer_mbox[r] = (double*)ctx->mbox_peer[r];
+      sp.peer_flag[r] = (unsigned long long*)((char*)ctx->mbox_peer[r] + SEL_MBOX_FLAG_OFF);
+    }
+  }
   sel_plan_persist(sp, ctx->sm_count);
+  if (sp.fused && sp.grid_persist == 0) return (delete pr, fail(ctx, BVIO_ERR_INVALID, "fused selector plan mismatch"));
   sp.delta_imu = in->delta_imu; sp.acc_var = in->acc_var; sp.acc_bias_var = in->acc_bias_var;
   for (int i = 0; i < 4; i++) sp.q_ic[i] = in->q_ic[i];
   for (int i = 0; i < 3; i++) sp.t_ic[i] = in->t_ic[i];
@@ -185,7 +207,7 @@ static int sel_enqueue(bvio_ctx* ctx, bvio_selprob* pr, cudaStream_t st, int* nc
     }
   }
   n += sel_launch_final(sp, st);
-  if (sp.world > 1) {
+  if (sp.world > 1 && !sp.fused) {
     n += sel_launch_counts(sp, pr->counts, 0, st);
     int r = g_nccl.AllReduce(pr->counts, pr->counts, 2, kNcclUint64, kNcclSum, ctx->comm, st);
     if (r) { *nccl_rc = r; return n; }
@@ -196,8 +218,67 @@ static int sel_enqueue(bvio_ctx* ctx, bvio_selprob* pr, cudaStream_t st, int* nc
 
 extern "C" {
 
+static void mbox_release(bvio_ctx* ctx) {
+  for (int r = 0; r < 8; r++) {
+    if (ctx->mbox_peer[r] && ctx->mbox_peer[r] != ctx->mbox_local) cudaIpcCloseMemHandle(ctx->mbox_peer[r]);
+    ctx->mbox_peer[r] = nullptr;
+  }
+  if (ctx->mbox_local) cudaFree(ctx->mbox_local);
+  ctx->mbox_local = nullptr;
+  ctx->p2p_ready = false;
+}
+
 void bvio_sel_ctx_destroy(bvio_ctx* ctx) {
-  if (ctx && ctx->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  if (!ctx) return;
+  mbox_release(ctx);
+  if (ctx->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+}
+
+// Mailboxes of the fused exchange: every rank allocates 4 KB, publishes its CUDA IPC handle through one ncclAllGather
+// and maps the others'.  Any failure (no peer access between the processes' devices, IPC disabled in the container)
+// just leaves p2p_ready false: bvio_select_sharded then runs one kernel per round with an ncclAllGather in between.
+static void mbox_setup(bvio_ctx* ctx) {
+  mbox_release(ctx);
+  if (ctx->world < 2 || ctx->world > SEL_MAX_WORLD) return;
+  cudaIpcMemHandle_t mine, all[SEL_MAX_WORLD];
+  char* dbuf = nullptr;
+  bool ok = cudaMalloc(&ctx->mbox_local, SEL_MBOX_BYTES) == cudaSuccess &&
+            cudaMemset(ctx->mbox_local, 0, SEL_MBOX_BYTES) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine, ctx->mbox_local) == cudaSuccess &&
+            cudaMalloc((void**)&dbuf, sizeof(mine) * (ctx->world + 1)) == cudaSuccess;
+  // the collective must be entered by every rank, whatever happened locally: a failed rank publishes zeros
+  if (!ok) memset(&mine, 0, sizeof mine);
+  int all_ok = 0;
+  if (dbuf) {
+    cudaMemcpyAsync(dbuf, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream);
+    int r = g_nccl.AllGather(dbuf, dbuf + sizeof mine, sizeof mine, kNcclInt8, ctx->comm, ctx->stream);
+    if (r == 0 && cudaMemcpyAsync(all, dbuf + sizeof mine, sizeof(mine) * ctx->world, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+        cudaStreamSynchronize(ctx->stream) == cudaSuccess) all_ok = 1;
+  }
+  if (all_ok && ok) {
+    cudaIpcMemHandle_t zero;
+    memset(&zero, 0, sizeof zero);
+    for (int r = 0; r < ctx->world && ok; r++) {
+      if (r == ctx->rank) { ctx->mbox_peer[r] = ctx->mbox_local; continue; }
+      if (!memcmp(&all[r], &zero, sizeof zero)) { ok = false; break; }
+      ok = cudaIpcOpenMemHandle(&ctx->mbox_peer[r], all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    }
+  } else ok = false;
+  cudaGetLastError();
+  if (dbuf) cudaFree(dbuf);
+  // every rank must agree (a rank that could not map a peer would otherwise wait for records nobody sends)
+  unsigned long long* flag = nullptr;
+  unsigned long long hv = ok ? 1ull : 0ull, res = 0;
+  if (cudaMalloc((void**)&flag, 2 * sizeof(unsigned long long)) == cudaSuccess) {
+    cudaMemcpyAsync(flag, &hv, sizeof hv, cudaMemcpyHostToDevice, ctx->stream);
+    // sum of the ok flags == world  <=>  everybody is ready
+    if (g_nccl.AllReduce(flag, flag + 1, 1, kNcclUint64, kNcclSum, ctx->comm, ctx->stream) == 0 &&
+        cudaMemcpyAsync(&res, flag + 1, sizeof res, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+        cudaStreamSynchronize(ctx->stream) == cudaSuccess && res == (unsigned long long)ctx->world) ctx->p2p_ready = true;
+    cudaFree(flag);
+  }
+  if (!ctx->p2p_ready) mbox_release(ctx);
+  ctx->sel_epoch = 0;
 }
 
 int bvio_select_upload(bvio_ctx* ctx, const bvio_select_in* in, bvio_selprob** out) {
@@ -227,6 +308,10 @@ int bvio_select_run(bvio_ctx* ctx, bvio_selprob* pr) {
     ctx->launches += sel_enqueue(ctx, pr, ctx->stream, &nrc);
     if (nrc) return fail(ctx, BVIO_ERR_NCCL, std::string("nccl: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
   }
+  if (pr->sp.fused) {            // every rank runs the same sequence of selections: epochs stay in lock step
+    ctx->sel_epoch += (unsigned long long)pr->sp.kappa;
+    pr->sp.epoch_base = ctx->sel_epoch;
+  }
   BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   BVIO_CUDA_OK(ctx, cudaGetLastError());
   return BVIO_OK;
@@ -247,6 +332,7 @@ int bvio_select_fetch(bvio_ctx* ctx, bvio_selprob* pr, int32_t* out_ids, double*
     if (out_ids) out_ids[i] = pr->cand_id[idx[i]];
     if (out_values) out_values[i] = val[i];
   }
+  if (c->peer_timeout) return fail(ctx, BVIO_ERR_NCCL, "fused selector: a peer's round record did not arrive within 3 s");
   if (summary) {
     summary->n_selected = c->n_selected;
     summary->n_candidates_valid = c->n_valid;
@@ -306,6 +392,7 @@ int bvio_comm_init(bvio_ctx* ctx, const void* uid128, int32_t rank, int32_t worl
   int r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
   if (r) return fail(ctx, BVIO_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   ctx->rank = rank; ctx->world = world;
+  mbox_setup(ctx);
   return BVIO_OK;
 }
 

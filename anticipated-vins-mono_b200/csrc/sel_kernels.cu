@@ -37,7 +37,7 @@ __global__ void sel_reset_kernel(SelProb sp) {
   if (i == 0) {
     SelCtrl c;
     c.scored = 0; c.min_margin = INFINITY; c.logdet_oo = 0; c.final_logdet = 0;
-    c.n_selected = 0; c.round = 0; c.n_valid = 0; c.pad = 0; c.ticket = 0; c.pad2 = 0;
+    c.n_selected = 0; c.round = 0; c.n_valid = 0; c.pad = 0; c.ticket = 0; c.pad2 = 0; c.peer_timeout = 0; c.pad3 = 0;
     *sp.ctrl = c;
   }
 }
@@ -48,11 +48,11 @@ __global__ void sel_reset_kernel(SelProb sp) {
 __global__ void __launch_bounds__(32 * SEL_WARPS) sel_build_kernel(SelProb sp) {
   __shared__ double sC[SEL_WARPS][BVIO_HMAX * 9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nloc = sp.c1 - sp.c0, H = sp.H;
+  const int nloc = sp.b1 - sp.b0, H = sp.H;
   const int f = blockIdx.x * SEL_WARPS + warp;
   if (f >= nloc + sp.U) return;
   const bool is_used = f >= nloc;
-  const int idx = is_used ? f - nloc : sp.c0 + f;
+  const int idx = is_used ? f - nloc : sp.b0 + f;
   const double2 xy = is_used ? sp.used_xy[idx] : sp.cand_xy[idx];
   // findNNDepth (feature_selector.cpp:437-459): exact 1-NN, first-found minimum
   double bd = DBL_MAX;
@@ -483,6 +483,30 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
+// system-scope accesses for the peer-memory exchange (the mailbox of rank r is ordinary device memory of GPU r that
+// the other ranks have mapped through CUDA IPC; stores travel over NVLink / NVSwitch)
+__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int H>
 __global__ void __launch_bounds__(32 * SEL_WARPS, 2) sel_persist_kernel(SelProb sp) {
   extern __shared__ double sm[];
@@ -559,6 +583,45 @@ __global__ void __launch_bounds__(32 * SEL_WARPS, 2) sel_persist_kernel(SelProb 
       }
       __syncthreads();
     }
+    if (sp.world > 1) {
+      // ---- fused exchange: CTA 0 stores this rank's 32-byte winner record into every rank's mailbox
+      //      (peer stores over NVLink), then every CTA of every rank waits for the world's records of this round in
+      //      its OWN mailbox and merges them in rank order -> the same winner everywhere, no host, no NCCL call
+      double* bcw = sred + SEL_WARPS * 4;
+      // epochs run on across selections (epoch_base += kappa per run) so that consecutive exchanges always
+      // alternate parity: a rank can be at most one exchange ahead of a peer's reads, two slots are enough
+      const unsigned long long ep = sp.epoch_base + (unsigned long long)round + 1ull;
+      const int par = (int)(ep & 1ull), world = sp.world;
+      if (blockIdx.x == 0 && threadIdx.x < world) {
+        const int r = threadIdx.x;
+        double* dst = sp.peer_mbox[r] + ((size_t)par * world + sp.rank) * 4;
+        st_relaxed_sys(dst, bcw[0]); st_relaxed_sys(dst + 1, bcw[1]); st_relaxed_sys(dst + 2, bcw[2]); st_relaxed_sys(dst + 3, bcw[3]);
+        st_release_sys(sp.peer_flag[r] + (size_t)par * world + sp.rank, ep);
+      }
+      __syncthreads();                                     // bcw consumed before it is overwritten below
+      double* sx = sred;                                   // [world][4] (world <= 8 = SEL_WARPS)
+      if (threadIdx.x < world) {
+        const int r = threadIdx.x;
+        const unsigned long long* fl = sp.mflag + (size_t)par * world + r;
+        const unsigned long long t0 = global_ns();
+        bool ok = true;
+        while (ld_acquire_sys(fl) < ep) {
+          if (global_ns() - t0 > 3000000000ull) { ok = false; break; }     // 3 s: a peer died; give up, do not hang
+        }
+        const double* src = sp.mbox + ((size_t)par * world + r) * 4;
+        sx[r * 4] = ok ? ld_relaxed_sys(src) : -1.0; sx[r * 4 + 1] = ok ? ld_relaxed_sys(src + 1) : -INFINITY;
+        sx[r * 4 + 2] = ok ? ld_relaxed_sys(src + 2) : -1.0; sx[r * 4 + 3] = ok ? ld_relaxed_sys(src + 3) : 0.0;
+        if (!ok) sp.ctrl->peer_timeout = 1;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double b = -1.0, s = -INFINITY, c = 0;
+        int ix = -1;
+        for (int r = 0; r < world; r++) { merge_best(b, s, ix, sx[r * 4], sx[r * 4 + 1], (int)sx[r * 4 + 2]); c += sx[r * 4 + 3]; }
+        bcw[0] = b; bcw[1] = s; bcw[2] = (double)ix; bcw[3] = c;
+      }
+      __syncthreads();
+    }
     const double* bc = sred + SEL_WARPS * 4;
     const double wb = bc[0], ws = bc[1];
     const int wix = (int)bc[2];
@@ -622,7 +685,7 @@ __global__ void sel_expand_kernel(SelProb sp, double* Cfull) {
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     int f = (int)(e / (T * T)), rc = (int)(e - (size_t)f * T * T), r = rc / T, c = rc - r * T;
     double v = 0;
-    if (f >= sp.c0 && f < sp.c1 && sp.valid[f]) v = sp.Cc[(size_t)f * sp.TT + (r >= c ? tri(r, c) : tri(c, r))];
+    if (f >= sp.b0 && f < sp.b1 && sp.valid[f]) v = sp.Cc[(size_t)f * sp.TT + (r >= c ? tri(r, c) : tri(c, r))];
     Cfull[e] = v;
   }
 }
@@ -669,7 +732,7 @@ int sel_launch_reset(const SelProb& sp, cudaStream_t st) {
   return 1;
 }
 int sel_launch_build(const SelProb& sp, cudaStream_t st) {
-  int nf = (sp.c1 - sp.c0) + sp.U, n = 0;
+  int nf = (sp.b1 - sp.b0) + sp.U, n = 0;
   if (nf > 0) { sel_build_kernel<<<(nf + SEL_WARPS - 1) / SEL_WARPS, 32 * SEL_WARPS, 0, st>>>(sp); n++; }
   sel_omega_kernel<<<1, 256, sel_omega_smem_bytes(sp.H), st>>>(sp);
   return n + 1;
@@ -690,7 +753,7 @@ static size_t persist_smem(int TT, int cpw) { return sizeof(double) * ((size_t)(
 int sel_plan_persist(SelProb& sp, int sm_count) {
   const int nloc = sp.c1 - sp.c0;
   sp.grid_persist = 0; sp.cpw = 0;
-  if (sp.world != 1 || nloc <= 0 || sp.kappa <= 0) return 0;
+  if ((sp.world != 1 && !sp.fused) || nloc <= 0 || sp.kappa <= 0) return 0;
   int per_sm = 0;
   cudaError_t e = cudaSuccess;
   int want = (nloc + SEL_WARPS - 1) / SEL_WARPS;
