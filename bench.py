@@ -390,7 +390,7 @@ def run_ours(args, rank, world, local_rank):
         peak = peaks.get("hbm_gbs", 6650.0)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("ba_linearize_kernel")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("ba_linearize_mma_kernel")
         except Exception:
             pass
         achieved = lin_bytes / (lin_ms * 1e-3) / 1e9

@@ -66,8 +66,10 @@ def main():
     ap.add_argument("--launches")
     ap.add_argument("--rep", action="append", default=[])
     ap.add_argument("--note", default="")
+    ap.add_argument("--outdir", default=os.path.join(ROOT, "profiles"),
+                    help="where to write (on the GPU box: a directory under gpurun_out/, the only one that travels back)")
     a = ap.parse_args()
-    pd = os.path.join(ROOT, "profiles")
+    pd = a.outdir
     os.makedirs(pd, exist_ok=True)
     if a.launches:
         launches_md(a.launches, os.path.join(pd, f"{a.tag}_launches.md"))
