@@ -45,6 +45,26 @@ def main():
         d.update(outc_state=hc.state_vector(), outc_cost=np.array([sc.final_cost]))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "cost", c[0], "->", s8.final_cost, "->", sc.final_cost)
+    # option variants at the reference budget: {LM, DOGLEG} x estimate_extrinsic x estimate_td on one window whose
+    # extrinsics are slightly off and whose observations are taken 4 ms late
+    w = synth.make_window(seed=44, K=11, L=80, td_true=0.004)
+    rng = np.random.default_rng(44)
+    w.para_ex_pose[:3] += rng.normal(0, 0.02, 3)
+    q = synth.quat_mul(w.para_ex_pose[3:], np.concatenate([0.5 * rng.normal(0, 0.01, 3), [1.0]]))
+    w.para_ex_pose[3:] = q / np.linalg.norm(q)
+    d = window_to_dict(w)
+    for strategy in (0, 1):
+        for ex in (0, 1):
+            for td in (0, 1):
+                o = abi.default_opts(strategy=strategy, estimate_extrinsic=ex, estimate_td=td, TR=0.01)
+                h, s = abi.WindowHandle(w), abi.Summary()
+                assert orc.oracle_optimize(C.byref(h.s), C.byref(o), C.byref(s)) == 0
+                key = f"out_s{strategy}_e{ex}_t{td}"
+                d[key + "_state"] = np.concatenate([h.state_vector(), h.td])
+                d[key + "_summary"] = np.array([s.iterations, s.num_accepted, s.num_rejected, s.termination], np.int32)
+                d[key + "_cost"] = np.array([s.initial_cost, s.final_cost, s.final_radius])
+                print("variants", key, s.as_dict())
+    np.savez_compressed(os.path.join(HERE, "opt_variants_k11_l80.npz"), **d)
     for name, kw in (("sel_n40_h10", dict(seed=51, N=40, H=10, kappa=8)), ("sel_n60_h13_u5", dict(seed=52, N=60, H=13, U=5, kappa=10)),
                      ("sel_n150_h10", dict(seed=53, N=150, H=10, kappa=30))):
         p = synth.make_select_problem(**kw)

@@ -12,6 +12,9 @@ _CAM = ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "width", "height")
 def window_to_dict(w):
     d = {"in_" + k: np.asarray(getattr(w, k)) for k in _W}
     d["in_K"] = np.array([w.K], np.int32)
+    if getattr(w, "obs_vel", None) is not None:
+        for k in ("obs_vel", "obs_td", "obs_row"):
+            d["in_" + k] = np.asarray(getattr(w, k))
     d["in_has_prior"] = np.array([w.prior is not None], np.int32)
     if w.prior is not None:
         d["in_prior_n"] = np.array([w.prior["n"]], np.int32)
@@ -27,6 +30,9 @@ def window_from_dict(d):
         prior = {k: d["in_prior_" + k] for k in _P}
         prior["n"] = int(d["in_prior_n"][0])
     kw = {k: d["in_" + k] for k in _W}
+    for k in ("obs_vel", "obs_td", "obs_row"):
+        if "in_" + k in d:
+            kw[k] = d["in_" + k]
     return synth.Window(K=int(d["in_K"][0]), prior=prior, **kw)
 
 

@@ -39,6 +39,45 @@ def test_oracle_reproduces_ba_golden(pkg, oracle, path):
     assert np.linalg.norm(h8.state_vector() - d["out8_state"]) <= 1e-10 * np.linalg.norm(d["out8_state"])
 
 
+VARIANTS = [(s, e, t) for s in (0, 1) for e in (0, 1) for t in (0, 1)]
+
+
+def _variant(pkg, solve, strategy, ex, td):
+    abi = pkg.abi
+    d = np.load(os.path.join(GOLD, "opt_variants_k11_l80.npz"))
+    w = golden_io.window_from_dict(d)
+    o = abi.default_opts(strategy=strategy, estimate_extrinsic=ex, estimate_td=td, TR=0.01)
+    h, s = abi.WindowHandle(w), abi.Summary()
+    solve(h, o, s)
+    key = f"out_s{strategy}_e{ex}_t{td}"
+    return d, key, np.concatenate([h.state_vector(), h.td]), s
+
+
+@pytest.mark.parametrize("strategy,ex,td", VARIANTS)
+def test_oracle_reproduces_variant_golden(pkg, oracle, strategy, ex, td):
+    """{LM, DOGLEG} x estimate_extrinsic x estimate_td at the reference budget (8 iterations)."""
+    def solve(h, o, s):
+        assert oracle.oracle_optimize(C.byref(h.s), C.byref(o), C.byref(s)) == 0
+    d, key, x, s = _variant(pkg, solve, strategy, ex, td)
+    assert [s.iterations, s.num_accepted, s.num_rejected, s.termination] == d[key + "_summary"].tolist()
+    assert np.linalg.norm(x - d[key + "_state"]) <= 1e-10 * np.linalg.norm(d[key + "_state"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy,ex,td", VARIANTS)
+def test_cuda_matches_variant_golden(pkg, strategy, ex, td):
+    ctx = pkg.lib.Context(0)
+
+    def solve(h, o, s):
+        ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(o), C.byref(s)), "optimize")
+    d, key, x, s = _variant(pkg, solve, strategy, ex, td)
+    assert [s.iterations, s.num_accepted, s.num_rejected, s.termination] == d[key + "_summary"].tolist()
+    assert np.linalg.norm(x - d[key + "_state"]) <= 1e-8 * np.linalg.norm(d[key + "_state"])
+    assert abs(s.final_cost - d[key + "_cost"][1]) <= 1e-9 * d[key + "_cost"][1]
+    assert abs(s.final_radius - d[key + "_cost"][2]) <= 1e-6 * d[key + "_cost"][2]
+    ctx.close()
+
+
 @pytest.mark.parametrize("path", SEL, ids=os.path.basename)
 def test_oracle_reproduces_select_golden(pkg, oracle, path):
     abi = pkg.abi
