@@ -125,7 +125,7 @@ size_t ba_solve_smem_bytes(int np);
 size_t ba_linearize_mma_smem_bytes(int K);
 size_t ba_marginalize_smem_bytes(int K, int nmax, int n);
 int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, const int* dropidx, const int* keepidx, double* A,
-                          double* b, double* out_jac, double* out_res, int* status, cudaStream_t st);
+                          double* b, double* out_jac, double* out_res, int* status, int method, cudaStream_t st);
 int ba_configure(void);   // cudaFuncSetAttribute for the big-smem kernels; returns cudaError_t
 
 }  // namespace bvio

@@ -695,13 +695,14 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts,
   if (e == cudaSuccess) {
     ctx->launches += ba_launch_marginalize(bb->bt, flag, m, n, (const int*)(scratch + o_drop), (const int*)(scratch + o_keep),
                                            (double*)(scratch + o_A), (double*)(scratch + o_b), (double*)(scratch + o_jac),
-                                           (double*)(scratch + o_res), (int*)(scratch + o_st), ctx->stream);
+                                           (double*)(scratch + o_res), (int*)(scratch + o_st),
+                                           getenv("BVIO_MARG_CHOLESKY") ? 1 : 0, ctx->stream);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_jac, scratch + o_jac, sizeof(double) * n * n, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_res, scratch + o_res, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e == cudaSuccess && getenv("BVIO_DEBUG")) { int stv[4] = {0, 0, 0, 0}; cudaMemcpy(stv, scratch + o_st, sizeof stv, cudaMemcpyDeviceToHost); fprintf(stderr, "[bvio] marginalize: m=%d n=%d jacobi sweeps=%d\n", m, n, stv[0]); }
+  if (e == cudaSuccess && getenv("BVIO_DEBUG")) { int stv[4] = {0, 0, 0, 0}; cudaMemcpy(stv, scratch + o_st, sizeof stv, cudaMemcpyDeviceToHost); fprintf(stderr, "[bvio] marginalize: m=%d n=%d sweeps/rank=%d log10 pivots min %.2f max %.2f\n", m, n, stv[0], stv[1] / 100.0, stv[2] / 100.0); }
   bvio_batch_free(ctx, bb);
   if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("marginalize: ") + cudaGetErrorString(e));
   for (int i = 0; i < n * n; i++) if (!(out->lin_jac[i] == out->lin_jac[i])) return fail(ctx, BVIO_ERR_NUMERIC, "non-finite prior");

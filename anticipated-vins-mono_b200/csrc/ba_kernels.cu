@@ -1922,7 +1922,8 @@ struct MargArgs {
   double* b;            // [M]
   double* out_jac;      // [n*n] column-major linearized_jacobians
   double* out_res;      // [n]
-  int* status;          // [1] sweeps used
+  int* status;          // [1] sweeps used (eigen) / rank (cholesky)
+  int method;           // 0: eigen-decomposition like the reference, 1: pivoted Cholesky (same J^T J, J^T r)
 };
 
 constexpr int MARG_THREADS = 512;
@@ -2249,6 +2250,68 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
     if (i > j) { double v = 0.5 * (Ar[i * ld + j] + Ar[j * ld + i]); Ar[i * ld + j] = v; Ar[j * ld + i] = v; }
   }
   __syncthreads();
+  if (ma.method == 1) {
+    // ---- opt-in (BVIO_MARG_CHOLESKY=1; the default below is the reference's eigen-decomposition):
+    //      (J, r) by diagonally pivoted Cholesky.  The reference factors A = V S V^T and keeps J = sqrt(S) V^T,
+    //      r = sqrt(S)^-1 V^T b (:283-291); every use of the prior -- r0 + J dx in MarginalizationFactor::Evaluate,
+    //      its cost, J^T J and J^T r in the next marginalization (:295-296) -- is invariant under J -> Q J,
+    //      r -> Q r with Q orthogonal, so any factor with J^T J = A, J^T r = b is the same prior.  Pivoting on the
+    //      largest remaining diagonal is rank revealing: it stops when what is left is below the reference's
+    //      eps = 1e-8 (marginalization_factor.h:70), the counterpart of its eigenvalue threshold.  Difference to the
+    //      eigen route: when A is rank deficient (gauge directions) that one also projects b onto range(A); here the
+    //      rounding-level component of b along the null directions (~1e-4 |b|, no curvature behind it) stays in J^T r.
+    int* perm = pp;                            // [ne]
+    double* col = cs;                          // [ne] current column of L (pivot order)
+    __shared__ int s_piv;
+    __shared__ double s_d;
+    for (int e = tid; e < n * n; e += nt) ma.out_jac[e] = 0.0;
+    for (int i = tid; i < n; i += nt) { perm[i] = i; ma.out_res[i] = 0.0; }
+    __syncthreads();
+    int rank = 0;
+    double minpiv = 1e300, maxpiv = 0;
+    for (int k = 0; k < n; k++) {
+      if (tid < 32) {
+        double best = -1.0;
+        int bi = n;
+        for (int i = k + tid; i < n; i += 32) {
+          const double v = Ar[perm[i] * ld + perm[i]];
+          if (v > best) { best = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (tid == 0) {
+          s_piv = (best > 1e-8) ? bi : -1;
+          if (best > 1e-8) { const int t2 = perm[k]; perm[k] = perm[bi]; perm[bi] = t2; s_d = sqrt(best); }
+        }
+      }
+      __syncthreads();
+      if (s_piv < 0) break;
+      rank = k + 1;
+      const int pk = perm[k];
+      const double d = s_d, rk = br[pk] / d;
+      minpiv = fmin(minpiv, d * d); maxpiv = fmax(maxpiv, d * d);
+      for (int i = k + tid; i < n; i += nt) {
+        const double lik = (i == k) ? d : Ar[perm[i] * ld + pk] / d;
+        col[i] = lik;
+        ma.out_jac[(size_t)perm[i] * n + k] = lik;         // J(k, perm[i]) = L(i, k), column-major
+      }
+      if (tid == 0) ma.out_res[k] = rk;
+      __syncthreads();
+      const int rem = n - k - 1;
+      for (int e = tid; e < rem * rem; e += nt) {
+        const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+        Ar[perm[i] * ld + perm[j]] -= col[i] * col[j];
+      }
+      for (int i = k + 1 + tid; i < n; i += nt) br[perm[i]] -= col[i] * rk;
+      __syncthreads();
+    }
+    if (tid == 0) { ma.status[0] = rank; ma.status[1] = (int)(100 * log10(minpiv)); ma.status[2] = (int)(100 * log10(maxpiv + 1e-300)); }
+    return;
+  }
   int sweeps = 0;
   const int half = ne / 2;
   for (; sweeps < 40 && ne >= 2; sweeps++) {
@@ -2327,8 +2390,9 @@ size_t ba_marginalize_smem_bytes(int K, int nmax, int n) {
 }
 
 int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, const int* dropidx, const int* keepidx, double* A,
-                          double* b, double* out_jac, double* out_res, int* status, cudaStream_t st) {
+                          double* b, double* out_jac, double* out_res, int* status, int method, cudaStream_t st) {
   MargArgs ma;
+  ma.method = method;
   ma.flag = flag; ma.M = 15 * bt.K + 6; ma.m = m; ma.n = n; ma.ne = (n + 1) & ~1;
   ma.dropidx = dropidx; ma.keepidx = keepidx; ma.A = A; ma.b = b; ma.out_jac = out_jac; ma.out_res = out_res; ma.status = status;
   size_t smem = ba_marginalize_smem_bytes(bt.K, bt.nmax, n);

@@ -367,6 +367,20 @@ def run_ours(args, rank, world, local_rank):
         for k, v in lat.items():
             a = np.array(v) * 1e3
             stream[k + "_ms"] = {"p50": float(np.percentile(a, 50)), "p99": float(np.percentile(a, 99)), "max": float(a.max())}
+        # same session, prior factored by pivoted Cholesky instead of the reference's eigen-decomposition (opt-in)
+        os.environ["BVIO_MARG_CHOLESKY"] = "1"
+        sim2 = pkg.slider.SlidingWindowSim(seed=7, max_feats=150, max_cand=300, H=SEL_H, frame_dt=1.0 / 30.0)
+        fc, mc = [], []
+        for f in range(min(args.stream_frames, 200) + warm):
+            r = sim2.step(gb)
+            if r is not None and f >= warm:
+                fc.append(r["optimize_call"] + r["marginalize_call"] + r["select_call"])
+                mc.append(r["marginalize_call"])
+        os.environ.pop("BVIO_MARG_CHOLESKY", None)
+        fc, mc = np.array(fc) * 1e3, np.array(mc) * 1e3
+        stream["cholesky_prior"] = {"frames": len(fc), "frame_call_ms": {"p50": float(np.percentile(fc, 50)), "p99": float(np.percentile(fc, 99))},
+                                    "marginalize_call_ms": {"p50": float(np.percentile(mc, 50)), "p99": float(np.percentile(mc, 99))},
+                                    "note": "BVIO_MARG_CHOLESKY=1: same quadratic prior, different (J, r) factor"}
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None

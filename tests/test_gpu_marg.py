@@ -4,6 +4,7 @@ parity is on the reference's own invariants J^T J (= A) and J^T r (= b)
 (marginalization_factor.cpp:295-296), in state coordinates, plus block bookkeeping and x0."""
 import ctypes as C
 import dataclasses
+import os
 
 import numpy as np
 import pytest
@@ -14,11 +15,16 @@ pytestmark = pytest.mark.gpu
 KEYS = ("n", "block_kind", "block_frame", "block_idx", "x0", "lin_jac", "lin_res")
 
 
-@pytest.fixture(scope="module")
-def env(pkg, oracle):
+@pytest.fixture(scope="module", params=["eigen", "cholesky"])
+def env(pkg, oracle, request):
+    """Both factorizations of the kept information into (J, r): the reference's eigen-decomposition (default) and the
+    opt-in pivoted Cholesky (BVIO_MARG_CHOLESKY=1, 2x faster); the prior they define is the same quadratic form."""
+    if request.param == "cholesky":
+        os.environ["BVIO_MARG_CHOLESKY"] = "1"
     ctx = pkg.lib.Context(0)
     yield pkg.abi, pkg.synth, oracle, ctx
     ctx.close()
+    os.environ.pop("BVIO_MARG_CHOLESKY", None)
 
 
 def _both(env, w, flag):
