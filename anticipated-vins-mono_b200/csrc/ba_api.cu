@@ -617,18 +617,19 @@ int bvio_batch_solve_timed(bvio_ctx* ctx, bvio_batch* bb, double out_ms[4], int3
 int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts, int32_t flag, bvio_prior_out* out) {
   if (!ctx || !w || !opts || !out || (flag != 0 && flag != 1)) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
   const int K = w->K;
-  if (opts->estimate_td)
-    return fail(ctx, BVIO_ERR_UNSUPPORTED, "bvio_marginalize: ProjectionTdFactor (estimate_td) is not implemented");
+  if (opts->estimate_td && K > 14)
+    return fail(ctx, BVIO_ERR_INVALID, "bvio_marginalize: K <= 14 with estimate_td");
   int rc = validate(ctx, w, opts, K);
   if (rc) return rc;
   const bvio_prior* pr = w->prior;
   std::vector<char> has_pose(K, 0), has_sb(K, 0);
-  bool has_ex = false;
+  bool has_ex = false, has_td = false;
   if (pr) for (int b = 0; b < pr->nblocks; b++) {
     int kind = pr->block_kind[b], f = pr->block_frame[b];
     if (kind == BVIO_BLK_POSE) has_pose[f] = 1;
     else if (kind == BVIO_BLK_SPEEDBIAS) has_sb[f] = 1;
     else if (kind == BVIO_BLK_EXPOSE) has_ex = true;
+    else if (kind == BVIO_BLK_TD) has_td = true;
   }
   std::vector<int> dropidx, keepidx;
   if (flag == 1) {
@@ -641,6 +642,7 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts,
       int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
       if (w->obs_frame[o0] != 0) continue;
       has_ex = true;
+      if (opts->estimate_td) has_td = true;        // para_Td is a block of every ProjectionTdFactor (estimator.cpp:863-871)
       for (int k = o0; k < o1; k++) has_pose[w->obs_frame[k]] = 1;
     }
     for (int i = 0; i < 15; i++) dropidx.push_back(i);
@@ -654,6 +656,7 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts,
     if (has_sb[f]) { blocks.push_back({BVIO_BLK_SPEEDBIAS, f, n}); for (int i = 0; i < 9; i++) keepidx.push_back(15 * f + 6 + i); n += 9; }
   }
   if (has_ex) { blocks.push_back({BVIO_BLK_EXPOSE, 0, n}); for (int i = 0; i < 6; i++) keepidx.push_back(15 * K + i); n += 6; }
+  if (has_td) { blocks.push_back({BVIO_BLK_TD, 0, n}); keepidx.push_back(15 * K + 6); n += 1; }
   const int m = (int)dropidx.size();
   if (n > out->cap_n || (int)blocks.size() > out->cap_blocks) return fail(ctx, BVIO_ERR_INVALID, "bvio_prior_out capacity too small");
   out->n = n;
@@ -662,16 +665,17 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts,
   for (size_t i = 0; i < blocks.size(); i++) {
     const Blk& bl = blocks[i];
     const double* src = bl.kind == BVIO_BLK_POSE ? w->para_pose + 7 * bl.frame
-                        : bl.kind == BVIO_BLK_SPEEDBIAS ? w->para_speed_bias + 9 * bl.frame : w->para_ex_pose;
-    int gs = bl.kind == BVIO_BLK_SPEEDBIAS ? 9 : 7;
+                        : bl.kind == BVIO_BLK_SPEEDBIAS ? w->para_speed_bias + 9 * bl.frame
+                        : bl.kind == BVIO_BLK_TD ? w->para_td : w->para_ex_pose;
+    int gs = bl.kind == BVIO_BLK_SPEEDBIAS ? 9 : (bl.kind == BVIO_BLK_TD ? 1 : 7);
     int frame = bl.frame;
-    if (bl.kind != BVIO_BLK_EXPOSE) frame = (flag == 0) ? frame - 1 : (frame == K - 1 ? K - 2 : frame);   // addr_shift
+    if (bl.kind != BVIO_BLK_EXPOSE && bl.kind != BVIO_BLK_TD) frame = (flag == 0) ? frame - 1 : (frame == K - 1 ? K - 2 : frame);   // addr_shift
     out->block_kind[i] = bl.kind; out->block_frame[i] = frame; out->block_idx[i] = bl.idx;
     memcpy(x0, src, sizeof(double) * gs);
     x0 += gs;
   }
   if (n == 0) return BVIO_OK;
-  const int M = 15 * K + 6;
+  const int M = 15 * K + 7;
   if (ba_marginalize_smem_bytes(K, pr ? pr->n : 1, n) > 220 * 1024)
     return fail(ctx, BVIO_ERR_UNSUPPORTED, "kept dimension too large for the single-CTA eigen-decomposition");
   bvio_batch* bb = nullptr;

@@ -1914,7 +1914,7 @@ int ba_launch_finish(const BaBatch& bt, cudaStream_t st) {
 // =============================================================================================
 struct MargArgs {
   int flag;             // 0 MARGIN_OLD, 1 MARGIN_SECOND_NEW
-  int M;                // 15K + 6: frame-major 15-blocks, then the extrinsic block
+  int M;                // 15K + 7: frame-major 15-blocks, then the extrinsic block, then td
   int m, n, ne;         // dropped / kept dimensions, ne = n rounded up to even
   const int* dropidx;   // [m] indices into the M layout
   const int* keepidx;   // [n]
@@ -1927,12 +1927,13 @@ struct MargArgs {
 };
 
 constexpr int MARG_THREADS = 512;
-constexpr int MF = 40;      // per-factor staging: A(12) B(12) E(12) c(2) r(2)
+constexpr int MF = 42;      // per-factor staging: A(12) B(12) E(12) c(2) r(2) td(2)
 
-// column `d` (visual layout: 6 dims per frame, then 6 extrinsic dims) of factor f's 2 x . Jacobian
+// column `d` (visual layout: 6 dims per frame, then 6 extrinsic dims, then td) of factor f's 2 x . Jacobian
 __device__ __forceinline__ void marg_col(const double* st, int fj, int K, int d, double& j0, double& j1) {
   j0 = 0; j1 = 0;
   if (d < 6) { j0 = st[d]; j1 = st[6 + d]; }
+  else if (d == 6 * K + 6) { j0 = st[40]; j1 = st[41]; }
   else if (d >= 6 * K) { j0 = st[24 + d - 6 * K]; j1 = st[30 + d - 6 * K]; }
   else if (d >= 6 * fj && d < 6 * fj + 6) { j0 = st[12 + d - 6 * fj]; j1 = st[18 + d - 6 * fj]; }
 }
@@ -1940,13 +1941,13 @@ __device__ __forceinline__ void marg_col(const double* st, int fj, int K, int d,
 __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch bt, MargArgs ma) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x, nt = blockDim.x, K = bt.K, M = ma.M, w = 0;
-  const int VD = 6 * K + 6;                 // visual layout dimension
+  const int VD = 6 * K + 7;                 // visual layout dimension (frames, extrinsics, td)
   double* A = ma.A;
   double* bv = ma.b;
   for (int i = tid; i < M * M; i += nt) A[i] = 0.0;
   for (int i = tid; i < M; i += nt) bv[i] = 0.0;
   __syncthreads();
-  auto vmap = [&](int d) { return d < 6 * K ? 15 * (d / 6) + d % 6 : 15 * K + (d - 6 * K); };
+  auto vmap = [&](int d) { return d < 6 * K ? 15 * (d / 6) + d % 6 : 15 * K + (d - 6 * K); };   // td: 15K + 6
 
   if (ma.flag == 0) {
     // ---- visual factors of the landmarks anchored at frame 0 (estimator.cpp:852-893)
@@ -1976,7 +1977,13 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       if (tid < nfac) {
         const int fj = bt.obs_frame[o0 + 1 + tid];
         sFof[fj] = tid;
-        const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + tid];
+        double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + tid];
+        double2 vi = {0, 0}, vj = {0, 0};
+        if (bt.est_td) {   // ProjectionTdFactor: time-shifted points (projection_td_factor.cpp:51-52)
+          vi = bt.obs_vel[o0]; vj = bt.obs_vel[o0 + 1 + tid];
+          const double td = bt.td0[w], si_ = td + bt.obs_shift[o0], sj_ = td + bt.obs_shift[o0 + 1 + tid];
+          pi.x -= si_ * vi.x; pi.y -= si_ * vi.y; pj.x -= sj_ * vj.x; pj.y -= sj_ * vj.y;
+        }
         const double lam = bt.invd0[l];
         const double* Fi = sFr;
         const double* Fj = sFr + fj * FR;
@@ -2027,6 +2034,8 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
           st[24 + a * 6 + 3] = sr * (-e1.x + e2.x + e3.x); st[24 + a * 6 + 4] = sr * (-e1.y + e2.y + e3.y);
           st[24 + a * 6 + 5] = sr * (-e1.z + e2.z + e3.z);
           st[36 + a] = sr * (-dot3(u, g.pimu_i - tic) / lam);
+          // td Jacobian (projection_td_factor.cpp:131-136); zero when td is not estimated
+          st[40 + a] = bt.est_td ? sr * (-dot3(u, mv3(sEx, d3{vi.x, vi.y, 0.0})) / lam + si * (a == 0 ? vj.x : vj.y)) : 0.0;
         }
         st[38] = sr * r0; st[39] = sr * r1;
         sFj[tid] = fj;
@@ -2059,10 +2068,10 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         // a frame-block dimension is touched by exactly one factor; pose-0 / extrinsic dimensions by all
         const int k1 = d1 / 6, k2 = d2 / 6;
         int f_lo = 0, f_hi = nfac;
-        if (k1 != 0 && k1 != K) { const int f = sFof[k1]; if (f < 0) f_hi = 0; else { f_lo = f; f_hi = f + 1; } }
-        if (k2 != 0 && k2 != K && f_hi > f_lo) {
+        if (k1 != 0 && k1 < K) { const int f = sFof[k1]; if (f < 0) f_hi = 0; else { f_lo = f; f_hi = f + 1; } }
+        if (k2 != 0 && k2 < K && f_hi > f_lo) {
           const int f = sFof[k2];
-          if (f < 0 || (f_hi - f_lo == 1 && k1 != 0 && k1 != K && f != f_lo)) f_hi = f_lo;
+          if (f < 0 || (f_hi - f_lo == 1 && k1 != 0 && k1 < K && f != f_lo)) f_hi = f_lo;
           else { f_lo = f; f_hi = f + 1; }
         }
         for (int f = f_lo; f < f_hi; f++) {
@@ -2135,8 +2144,8 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       for (int bidx = tid; bidx < nb; bidx += nt) {
         int kind = bt.pr_kind[w * PRIOR_MAXB + bidx], fr = bt.pr_frame[w * PRIOR_MAXB + bidx], idx = bt.pr_idx[w * PRIOR_MAXB + bidx];
         int loc = kind == 1 ? 9 : (kind == 3 ? 1 : 6);
-        int base = kind == 0 ? 15 * fr : (kind == 1 ? 15 * fr + 6 : (kind == 2 ? 15 * K : -1));
-        for (int i = 0; i < loc; i++) pmap[idx + i] = base < 0 ? -1 : base + i;
+        int base = kind == 0 ? 15 * fr : (kind == 1 ? 15 * fr + 6 : (kind == 2 ? 15 * K : 15 * K + 6));
+        for (int i = 0; i < loc; i++) pmap[idx + i] = base + i;
       }
       __syncthreads();
       prior_residual(bt, w, bt.pose0, bt.sb0, bt.ex, bt.td0, sdx, spr);
@@ -2378,7 +2387,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
 }
 
 size_t ba_marginalize_smem_bytes(int K, int nmax, int n) {
-  int ne = (n + 1) & ~1, VD = 6 * K + 6;
+  int ne = (n + 1) & ~1, VD = 6 * K + 7;
   size_t a = (size_t)(K + 1) * FR + (BVIO_KMAX - 1) * MF + 2 * VD + 2 + 2 * BVIO_KMAX;   // visual phase
   size_t b = 930 + 32;                                                                    // IMU phase
   size_t c = 2 * (size_t)nmax + nmax / 2 + 2;                                             // prior phase
@@ -2393,7 +2402,7 @@ int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, const int* 
                           double* b, double* out_jac, double* out_res, int* status, int method, cudaStream_t st) {
   MargArgs ma;
   ma.method = method;
-  ma.flag = flag; ma.M = 15 * bt.K + 6; ma.m = m; ma.n = n; ma.ne = (n + 1) & ~1;
+  ma.flag = flag; ma.M = 15 * bt.K + 7; ma.m = m; ma.n = n; ma.ne = (n + 1) & ~1;
   ma.dropidx = dropidx; ma.keepidx = keepidx; ma.A = A; ma.b = b; ma.out_jac = out_jac; ma.out_res = out_res; ma.status = status;
   size_t smem = ba_marginalize_smem_bytes(bt.K, bt.nmax, n);
   cudaFuncSetAttribute(ba_marginalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);

@@ -1000,11 +1000,14 @@ void oracle_double2vector(const double pre_pose0[7], int K, double* para_pose, d
 // quadratic form is order-invariant; rows of J are defined up to the eigenvector basis.
 // flag 1 (MARGIN_SECOND_NEW) when the prior does not touch Pose[K-2]: out->n = -1 (prior unchanged).
 int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_prior_out* out) {
-  if (o->estimate_td || o->estimate_extrinsic) return BVIO_ERR_UNSUPPORTED;
+  // ESTIMATE_EXTRINSIC does not change the marginalization: para_Ex_Pose is a parameter block of every visual factor
+  // either way (estimator.cpp:872-890).  ESTIMATE_TD swaps in ProjectionTdFactor with para_Td as a fifth, kept block
+  // (estimator.cpp:863-871).
+  if (o->estimate_td && (!w->obs_vel || !w->obs_td || !w->obs_row || !w->para_td)) return BVIO_ERR_INVALID;
   const int K = w->K, L = w->L;
   const double eps = 1e-8;
-  // variable ids: pose f -> f, sb f -> K+f, ex -> 2K, landmark l -> 2K+1+l
-  const int NV = 2 * K + 1 + L;
+  // variable ids: pose f -> f, sb f -> K+f, ex -> 2K, landmark l -> 2K+1+l, td -> 2K+1+L
+  const int NV = 2 * K + 2 + L, VTD = 2 * K + 1 + L;
   auto vloc = [&](int v) { return v < K ? 6 : (v < 2 * K ? 9 : (v == 2 * K ? 6 : 1)); };
   std::vector<char> present(NV, 0), drop(NV, 0);
   struct Fac { std::vector<int> vars; std::vector<std::vector<double>> J; std::vector<double> r; };
@@ -1012,7 +1015,8 @@ int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_
   const bvio_prior* pr = w->prior;
   auto prior_var = [&](int b) {
     int kind = pr->block_kind[b];
-    return kind == BVIO_BLK_POSE ? pr->block_frame[b] : (kind == BVIO_BLK_SPEEDBIAS ? K + pr->block_frame[b] : 2 * K);
+    return kind == BVIO_BLK_POSE ? pr->block_frame[b] : (kind == BVIO_BLK_SPEEDBIAS ? K + pr->block_frame[b]
+           : (kind == BVIO_BLK_TD ? VTD : 2 * K));
   };
   auto add_prior = [&]() {
     int n = pr->n;
@@ -1021,7 +1025,6 @@ int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_
     std::vector<double> dx(n);
     prior_eval(pr, w, f.r.data(), dx.data());
     for (int b = 0; b < pr->nblocks; b++) {
-      if (pr->block_kind[b] == BVIO_BLK_TD) continue;
       int loc = blk_local(pr->block_kind[b]), idx = pr->block_idx[b];
       std::vector<double> J((size_t)n * loc);
       for (int i = 0; i < n; i++)
@@ -1060,7 +1063,12 @@ int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_
       for (int k = o0 + 1; k < o1; k++) {
         int fj = w->obs_frame[k];
         V3 pts_j{w->obs_xy[2 * k], w->obs_xy[2 * k + 1], 1.0};
-        double r[2], Ji[14], Jj[14], Jex[14], Jf[2];
+        double r[2], Ji[14], Jj[14], Jex[14], Jf[2], Jtd[2] = {0, 0};
+        if (o->estimate_td)
+          projection_td_eval(pts_i, pts_j, td_obs(w, o0), td_obs(w, k), w->para_td[0], o->TR, o->ROW, v3(w->para_pose),
+                             q4(w->para_pose + 3), v3(w->para_pose + 7 * fj), q4(w->para_pose + 7 * fj + 3), tic, qic,
+                             w->inv_depth[l], sqrt_info, r, Ji, Jj, Jex, Jf, Jtd);
+        else
         projection_eval(pts_i, pts_j, v3(w->para_pose), q4(w->para_pose + 3), v3(w->para_pose + 7 * fj),
                         q4(w->para_pose + 7 * fj + 3), tic, qic, w->inv_depth[l], sqrt_info, r, Ji, Jj, Jex, Jf);
         double rho[3];
@@ -1075,6 +1083,7 @@ int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_
         };
         f.vars = {0, fj, 2 * K, 2 * K + 1 + l};
         f.J = {take(Ji), take(Jj), take(Jex), std::vector<double>{sr * Jf[0], sr * Jf[1]}};
+        if (o->estimate_td) { f.vars.push_back(VTD); f.J.push_back(std::vector<double>{sr * Jtd[0], sr * Jtd[1]}); }
         facs.push_back(f);
         drop[0] = 1; drop[2 * K + 1 + l] = 1;
       }
@@ -1100,6 +1109,7 @@ int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_
     if (present[K + f] && !drop[K + f]) { push(K + f); kept.push_back(K + f); }
   }
   if (present[2 * K] && !drop[2 * K]) { push(2 * K); kept.push_back(2 * K); }
+  if (present[VTD]) { push(VTD); kept.push_back(VTD); }
   const int n = pos - m;
   std::vector<double> A((size_t)pos * pos, 0.0), b(pos, 0.0);
   for (auto& f : facs) {
@@ -1171,10 +1181,11 @@ int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_
     const double* src;
     if (v < K) { kind = BVIO_BLK_POSE; frame = v; src = w->para_pose + 7 * v; }
     else if (v < 2 * K) { kind = BVIO_BLK_SPEEDBIAS; frame = v - K; src = w->para_speed_bias + 9 * (v - K); }
+    else if (v == VTD) { kind = BVIO_BLK_TD; src = w->para_td; }
     else { kind = BVIO_BLK_EXPOSE; src = w->para_ex_pose; }
     int gs = blk_global(kind);
     // addr_shift (estimator.cpp:904-916 / 962-984)
-    if (kind != BVIO_BLK_EXPOSE) frame = (flag == 0) ? frame - 1 : (frame == K - 1 ? K - 2 : frame);
+    if (kind != BVIO_BLK_EXPOSE && kind != BVIO_BLK_TD) frame = (flag == 0) ? frame - 1 : (frame == K - 1 ? K - 2 : frame);
     out->block_kind[bi] = kind; out->block_frame[bi] = frame; out->block_idx[bi] = idx[v] - m;
     std::memcpy(x0, src, sizeof(double) * gs);
     x0 += gs;

@@ -27,10 +27,10 @@ def env(pkg, oracle, request):
     os.environ.pop("BVIO_MARG_CHOLESKY", None)
 
 
-def _both(env, w, flag):
+def _both(env, w, flag, **opts_kw):
     abi, synth, orc, ctx = env
-    pg = run_marg(abi, ctx.L.bvio_marginalize, w, flag, ctx=ctx.h)
-    po = run_marg(abi, orc.oracle_marginalize, w, flag)
+    pg = run_marg(abi, ctx.L.bvio_marginalize, w, flag, ctx=ctx.h, opts=abi.default_opts(**opts_kw))
+    po = run_marg(abi, orc.oracle_marginalize, w, flag, opts=abi.default_opts(**opts_kw))
     return pg, po
 
 
@@ -88,3 +88,57 @@ def test_marginalized_prior_drives_the_next_solve(env):
         ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(tight), C.byref(s)), "optimize")
         xs.append(h.state_vector())
     assert np.linalg.norm(xs[0] - xs[1]) <= 1e-6 * np.linalg.norm(xs[1])
+
+
+def _info_td(p, K, unshift):
+    """like info_in_state_coords, with the td column after the extrinsic block"""
+    M = 15 * K + 7
+    cols = np.full(p["n"], -1)
+    for kind, frame, idx in zip(p["block_kind"], p["block_frame"], p["block_idx"]):
+        f = unshift(int(frame)) if kind in (0, 1) else 0
+        if kind == 0:
+            cols[idx:idx + 6] = 15 * f + np.arange(6)
+        elif kind == 1:
+            cols[idx:idx + 9] = 15 * f + 6 + np.arange(9)
+        elif kind == 2:
+            cols[idx:idx + 6] = 15 * K + np.arange(6)
+        else:
+            cols[idx] = 15 * K + 6
+    assert (cols >= 0).all()
+    H, g = np.zeros((M, M)), np.zeros(M)
+    H[np.ix_(cols, cols)] = p["J"].T @ p["J"]
+    g[cols] = p["J"].T @ p["lin_res"]
+    return H, g
+
+
+@pytest.mark.parametrize("seed,K,L,TR", [(0, 11, 150, 0.0), (1, 6, 40, 0.02), (2, 11, 300, 0.01)])
+def test_margin_old_with_td_matches_oracle(env, seed, K, L, TR):
+    """ESTIMATE_TD: ProjectionTdFactor in the marginalization (estimator.cpp:863-871), para_Td kept."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=seed, K=K, L=L, td_true=0.004)
+    w.para_td[0] = 0.002
+    pg, po = _both(env, w, 0, estimate_td=1, TR=TR)
+    assert pg["n"] == po["n"] and pg["block_kind"][-1] == 3
+    for k in ("block_kind", "block_frame", "block_idx"):
+        assert np.array_equal(pg[k], po[k]), k
+    assert np.array_equal(pg["x0"], po["x0"])
+    Hg, gg = _info_td(pg, K, lambda f: f + 1)
+    Ho, go = _info_td(po, K, lambda f: f + 1)
+    assert Ho[-1, -1] > 0
+    assert np.abs(Hg - Ho).max() <= 1e-7 * np.abs(Ho).max()
+    assert np.abs(gg - go).max() <= 5e-5 * max(np.abs(go).max(), 1.0)
+
+
+def test_td_prior_drives_the_next_solve(env):
+    """A prior that carries the td block feeds an ESTIMATE_TD solve: device and oracle reach the same state."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=8, K=11, L=120, td_true=0.004)
+    pg, po = _both(env, w, 0, estimate_td=1)
+    w2 = dataclasses.replace(synth.make_window(seed=9, K=11, L=120, prior="none", td_true=0.004), prior={k: pg[k] for k in KEYS})
+    o = abi.default_opts(estimate_td=1)
+    hg, ho, sg, so = abi.WindowHandle(w2), abi.WindowHandle(w2), abi.Summary(), abi.Summary()
+    ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(hg.s), C.byref(o), C.byref(sg)), "optimize")
+    assert orc.oracle_optimize(C.byref(ho.s), C.byref(o), C.byref(so)) == 0
+    assert (sg.iterations, sg.num_accepted, sg.termination) == (so.iterations, so.num_accepted, so.termination)
+    assert np.linalg.norm(hg.state_vector() - ho.state_vector()) <= 1e-8 * np.linalg.norm(ho.state_vector())
+    assert abs(hg.td[0] - ho.td[0]) <= 1e-9

@@ -10,7 +10,7 @@ import pytest
 import np_ref
 
 
-def run_marg(abi, lib_fn, w, flag, ctx=None):
+def run_marg(abi, lib_fn, w, flag, ctx=None, opts=None):
     h = abi.WindowHandle(w)
     cap_n, cap_b = 15 * w.K + 16, 2 * w.K + 2
     bk, bf, bi = (np.zeros(cap_b, np.int32) for _ in range(3))
@@ -19,7 +19,7 @@ def run_marg(abi, lib_fn, w, flag, ctx=None):
     out.block_kind, out.block_frame, out.block_idx = abi.iptr(bk), abi.iptr(bf), abi.iptr(bi)
     out.x0, out.lin_jac, out.lin_res = abi.dptr(x0), abi.dptr(jac), abi.dptr(res)
     out.cap_n, out.cap_blocks = cap_n, cap_b
-    o = abi.default_opts()
+    o = opts if opts is not None else abi.default_opts()
     rc = lib_fn(C.byref(h.s), C.byref(o), flag, C.byref(out)) if ctx is None else \
         lib_fn(ctx, C.byref(h.s), C.byref(o), flag, C.byref(out))
     assert rc == 0, rc
@@ -124,3 +124,25 @@ def test_prior_chain_and_second_new(pkg, oracle):
     assert ev.min() >= -1e-8 * ev.max()
     # no prior on Pose[K-2] => unchanged
     assert run_marg(abi, oracle.oracle_marginalize, w, 1) is None
+
+
+def test_td_marginalization_plumbing(pkg, oracle):
+    """ESTIMATE_TD (estimator.cpp:863-871): para_Td is a kept block of the new prior.  With zero feature velocities the
+    td factor is the plain projection factor and carries no information on td: same prior on every other block, one
+    extra all-zero td column."""
+    import dataclasses
+    abi, synth = pkg.abi, pkg.synth
+    w = synth.make_window(seed=3, K=8, L=40, td_true=0.0)
+    w0 = dataclasses.replace(w, obs_vel=np.zeros_like(w.obs_vel))
+    p_td = run_marg(abi, oracle.oracle_marginalize, w0, 0, opts=abi.default_opts(estimate_td=1))
+    p = run_marg(abi, oracle.oracle_marginalize, w0, 0)
+    assert p_td["n"] == p["n"] + 1 and p_td["block_kind"][-1] == 3 and p_td["block_idx"][-1] == p["n"]
+    H, Htd = p["J"].T @ p["J"], p_td["J"].T @ p_td["J"]
+    assert np.abs(Htd[-1]).max() == 0 and np.abs(Htd[:, -1]).max() == 0
+    assert np.abs(Htd[:-1, :-1] - H).max() <= 1e-9 * np.abs(H).max()
+    # real velocities: td couples with the poses
+    p_real = run_marg(abi, oracle.oracle_marginalize, w, 0, opts=abi.default_opts(estimate_td=1, TR=0.01))
+    Hr = p_real["J"].T @ p_real["J"]
+    assert Hr[-1, -1] > 0 and np.abs(Hr[-1, :-1]).max() > 0
+    ev = np.linalg.eigvalsh(Hr)
+    assert ev.min() >= -1e-9 * ev.max()
