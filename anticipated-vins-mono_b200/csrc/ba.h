@@ -18,7 +18,11 @@ constexpr int IMU_OUT = 496;          // per IMU factor: J^T J lower packed (465
 
 constexpr int PRIOR_MAXB = 32;    // max kept parameter blocks in a prior
 constexpr int BA_THREADS = 256;   // linearize / cost kernels
-constexpr int SOLVE_THREADS = 512;
+#ifndef BVIO_SOLVE_THREADS
+#define BVIO_SOLVE_THREADS 256
+#endif
+constexpr int SOLVE_THREADS = BVIO_SOLVE_THREADS;          // ba_solve: 256 x 2 CTAs/SM measured faster than 512 x 1
+constexpr int SOLVE_CTAS_PER_SM = SOLVE_THREADS <= 256 ? 2 : 1;
 
 struct BaCtrl {                   // per-window LM state, lives in HBM
   double cost;                    // cost at X[cur]
@@ -110,6 +114,7 @@ struct BaBatch {                  // all pointers are device pointers
   double* dog_l;                  // [total_L][2] dogleg: landmark parts (t_l, Gauss-Newton dlambda_l)
   double* dog_out;                // [B][T][DOG_REC] per-tile partial dot products
   double* scale_p;                // [B][np] Jacobi scaling of the pose/speed-bias columns
+  double* solve_vec;              // [B][5][np] ba_solve's gradient / diagonal / damping vectors
   double* dbg_S; double* dbg_g;   // [B][np*np], [B][np] (debug linearize only, else null)
   BaCtrl* ctrl;                   // [B]
 };

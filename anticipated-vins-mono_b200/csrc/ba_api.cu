@@ -233,6 +233,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   size_t o_tds[2] = {cv.take((size_t)B * D), cv.take((size_t)B * D)};
   size_t o_cost = cv.take((size_t)B * (T + 1) * COST_REC * D);
   size_t o_dp = cv.take((size_t)B * bt.np * D), o_sp = cv.take((size_t)B * bt.np * D);
+  size_t o_svec = cv.take((size_t)B * 5 * bt.np * D);
   size_t o_dog_t = 0, o_dog_l = 0, o_dog_out = 0;
   if (bt.strategy == BVIO_STRATEGY_DOGLEG) {
     o_dog_t = cv.take((size_t)B * bt.np * D); o_dog_l = cv.take((size_t)total_L * 2 * D);
@@ -376,7 +377,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bt.pr_H = (double*)(d + o_pr_H); bt.pr_map = (int*)(d + o_pr_map); bt.pr_out = (double*)(d + o_pr_out);
   bt.h = (double*)(d + o_h); bt.b = (double*)(d + o_b); bt.sl2 = (double*)(d + o_sl2); bt.w = (double*)(d + o_w);
   bt.tile_out = (double*)(d + o_tile); bt.cost_out = (double*)(d + o_cost);
-  bt.delta_p = (double*)(d + o_dp); bt.scale_p = (double*)(d + o_sp);
+  bt.delta_p = (double*)(d + o_dp); bt.scale_p = (double*)(d + o_sp); bt.solve_vec = (double*)(d + o_svec);
   bt.dog_t = (double*)(d + o_dog_t); bt.dog_l = (double*)(d + o_dog_l); bt.dog_out = (double*)(d + o_dog_out);
   bt.dbg_S = debug ? (double*)(d + o_dbgS) : nullptr;
   bt.dbg_g = debug ? (double*)(d + o_dbgg) : nullptr;

@@ -1119,7 +1119,7 @@ size_t ba_linearize_mma_smem_bytes(int K) {
 // EX: the reduced system carries extra dimensions after the K 15-blocks (6 extrinsic and/or 1 td: np = 15K + 6 / + 1 /
 // + 7); the last Cholesky panel is then partial (the panel width is a compile-time 15 otherwise).
 template <bool EX>
-__global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, int with_step) {
+__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_CTAS_PER_SM) ba_solve_kernel(BaBatch bt, int with_step) {
   extern __shared__ double sm[];
   const int w = blockIdx.x, K = bt.K, np = bt.np, KE = K + bt.est_ex + bt.est_td, K6 = 6 * KE, NPb = KE * (KE + 1) / 2;
   const int NB = (np + 14) / 15;                   // diagonal panels of the blocked Cholesky
@@ -1128,14 +1128,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_kernel(BaBatch bt, 
   if (ctrl->done) return;
   const int N1 = np + 1;                          // augmented dimension
   double* S = sm;                                 // packed lower (N1)(N1+1)/2
-  double* bp = S + (size_t)N1 * (N1 + 1) / 2;     // [np] unreduced gradient
+  // O(np)-touched vectors live in HBM/L2 so that the packed matrix alone decides the shared-memory footprint
+  // (two CTAs per SM for np = 165: one window's barrier waits hide behind the other's work)
+  double* bp = bt.solve_vec + (size_t)w * 5 * np;  // [np] unreduced gradient
   double* gr = bp + np;                           // [np] reduced gradient
   double* dH = gr + np;                           // [np] diag of the undamped, unreduced H_pp
   double* ddp = dH + np;                          // [np]
-  double* yv = ddp + np;                          // [np]
+  double* tv = ddp + np;                          // [np] dogleg: scaled gradient direction t
+  double* yv = S + (size_t)N1 * (N1 + 1) / 2;     // [np]
   double* red = yv + np;                          // [32]
   double* dinv = red + 32;                        // [np] reciprocal diagonal of L
-  double* tv = dinv + np;                         // [np] dogleg: scaled gradient direction t
   __shared__ int s_fail;
   const int REC = NPb * 36 + 3 * K6;
   const int TREC = tile_rec_doubles(KE);
@@ -1808,7 +1810,7 @@ int ba_pick_chunk(int K, int XB) {
 }
 size_t ba_solve_smem_bytes(int np) {
   int N1 = np + 1;
-  return sizeof(double) * ((size_t)N1 * (N1 + 1) / 2 + 7 * np + 32);
+  return sizeof(double) * ((size_t)N1 * (N1 + 1) / 2 + 2 * np + 32);
 }
 static size_t cost_smem(int K, int nmax) {
   return sizeof(double) * ((size_t)15 * K + 8 + (K + 1) * 7 + (K + 1) * FR + 96 + K * 9 + (K - 1) * 15 + 2 * nmax);
