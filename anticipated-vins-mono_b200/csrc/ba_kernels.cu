@@ -1605,8 +1605,8 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
   double* sPose = sdp + np;         // [(K+1)*7] candidate poses, then the (candidate) extrinsic pose
   double* sFr = sPose + (K + 1) * 7 + 1;   // [K*FR]; sPose[(K+1)*7] = candidate td
   double* sEx = sFr + K * FR;       // [FR]
-  double* red = sEx + FR;           // [16*4 + 32]
-  double* extra = red + 96;         // IMU/prior CTA scratch
+  double* red = sEx + FR;           // [32*4 + 32]
+  double* extra = red + 160;        // IMU/prior CTA scratch
   __shared__ int s_last;
   const int dogleg = bt.strategy;
   const double ca = ctrl->ca, cb = ctrl->cb, mu = ctrl->mu;
@@ -1632,63 +1632,73 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
       o[9] = p[0]; o[10] = p[1]; o[11] = p[2];
     }
     __syncthreads();
-    const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15, NG = blockDim.x >> 4;
-    const unsigned gmask = 0xffffffffu;   // both half-warps always iterate together (warp-uniform trip count)
+    // 8 lanes per landmark, lane = observation (a second trip for tracks longer than 8): 4 landmarks per warp
+    const int grp = threadIdx.x >> 3, l16 = threadIdx.x & 7, NG = blockDim.x >> 3;
+    const unsigned gmask = 0xffffffffu;   // the four groups of a warp always iterate together (warp-uniform trip count)
     const double dfac = damp_factor(ctrl->radius, mu, dogleg);
     int l0, l1;
     tile_range(bt, w, t, l0, l1);
     double a_cost = 0, a_model = 0, a_s2 = 0, a_x2 = 0;
-    for (int lw = l0 + (grp & ~1); lw < l1; lw += NG) {
-      const bool act = lw + (grp & 1) < l1;
-      const int l = act ? lw + (grp & 1) : l1 - 1;    // the idle half-warp shadows a valid landmark, results dropped
+    for (int lw = l0 + (grp & ~3); lw < l1; lw += NG) {
+      const bool act = lw + (grp & 3) < l1;
+      const int l = act ? lw + (grp & 3) : l1 - 1;    // idle groups shadow a valid landmark, results dropped
       const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0;
       const double lam = bt.invd[cur][l], h = bt.h[l], b = bt.b[l];
-      int myfr = 0;
+      const int fi = bt.obs_frame[o0];
+      int fr0 = 0, fr1 = 0;
       double part = 0;
-      if (l16 < n) {
-        myfr = bt.obs_frame[o0 + l16];
-        if (!dogleg) {
+      if (l16 < n) fr0 = bt.obs_frame[o0 + l16];
+      if (l16 + 8 < n) fr1 = bt.obs_frame[o0 + l16 + 8];
+      if (!dogleg) {
+        if (l16 < n) {
           const double* wp = bt.w + (size_t)(o0 + l16) * 6;
-          const double* d = sdp + 15 * myfr;
+          const double* d = sdp + 15 * fr0;
 #pragma unroll
           for (int k = 0; k < 6; k++) part += wp[k] * d[k];
-          if (l16 == 0 && (bt.est_ex | bt.est_td)) {
-            const double* we = bt.wex + (size_t)l * (bt.est_ex + bt.est_td) * 6;
-            if (bt.est_ex) {
-#pragma unroll
-              for (int k = 0; k < 6; k++) part += we[k] * sdp[15 * K + k];
-            }
-            if (bt.est_td) part += we[6 * bt.est_ex] * sdp[15 * K + 6 * bt.est_ex];
-          }
         }
-      }
-      if (!dogleg) {
+        if (l16 + 8 < n) {
+          const double* wp = bt.w + (size_t)(o0 + l16 + 8) * 6;
+          const double* d = sdp + 15 * fr1;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, 16);
+          for (int k = 0; k < 6; k++) part += wp[k] * d[k];
+        }
+        if (l16 == 0 && (bt.est_ex | bt.est_td)) {
+          const double* we = bt.wex + (size_t)l * (bt.est_ex + bt.est_td) * 6;
+          if (bt.est_ex) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) part += we[k] * sdp[15 * K + k];
+          }
+          if (bt.est_td) part += we[6 * bt.est_ex] * sdp[15 * K + 6 * bt.est_ex];
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, 8);
       }
-      const int fi = __shfl_sync(gmask, myfr, 0, 16);
       double sl2 = bt.jacobi_scaling ? bt.sl2[l] : 1.0;
       double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, dfac);
       double dl = -(b + part) / (h + ddl);
       if (dogleg) dl = ca * bt.dog_l[(size_t)2 * l] + cb * bt.dog_l[(size_t)2 * l + 1];
       double lamc = lam + dl;
       double fc = 0;
-      if (l16 >= 1 && l16 < n) {
-        double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + l16];
-        if (bt.est_td) {
-          const double tdc = sPose[(K + 1) * 7], si_ = tdc + bt.obs_shift[o0], sj_ = tdc + bt.obs_shift[o0 + l16];
-          const double2 vi = bt.obs_vel[o0], vj = bt.obs_vel[o0 + l16];
-          pi.x -= si_ * vi.x; pi.y -= si_ * vi.y; pj.x -= sj_ * vj.x; pj.y -= sj_ * vj.y;
+#pragma unroll
+      for (int trip = 0; trip < 2; trip++) {
+        const int ko = l16 + 8 * trip, myfr = trip ? fr1 : fr0;
+        if (ko >= 1 && ko < n) {
+          double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + ko];
+          if (bt.est_td) {
+            const double tdc = sPose[(K + 1) * 7], si_ = tdc + bt.obs_shift[o0], sj_ = tdc + bt.obs_shift[o0 + ko];
+            const double2 vi = bt.obs_vel[o0], vj = bt.obs_vel[o0 + ko];
+            pi.x -= si_ * vi.x; pi.y -= si_ * vi.y; pj.x -= sj_ * vj.x; pj.y -= sj_ * vj.y;
+          }
+          ProjGeom g = proj_geom(sFr + fi * FR, sFr + myfr * FR, sEx, pi.x, pi.y, lamc);
+          double inv = 1.0 / g.pcj.z;
+          double r0 = bt.sqrt_info * (g.pcj.x * inv - pj.x), r1 = bt.sqrt_info * (g.pcj.y * inv - pj.y);
+          double rho0, rho1;
+          cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
+          fc += 0.5 * rho0;
         }
-        ProjGeom g = proj_geom(sFr + fi * FR, sFr + myfr * FR, sEx, pi.x, pi.y, lamc);
-        double inv = 1.0 / g.pcj.z;
-        double r0 = bt.sqrt_info * (g.pcj.x * inv - pj.x), r1 = bt.sqrt_info * (g.pcj.y * inv - pj.y);
-        double rho0, rho1;
-        cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
-        fc = 0.5 * rho0;
       }
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) fc += __shfl_xor_sync(gmask, fc, o, 16);
+      for (int o = 4; o > 0; o >>= 1) fc += __shfl_xor_sync(gmask, fc, o, 8);
       if (l16 == 0 && act) {
         bt.invd[nxt][l] = lamc;
         a_cost += fc;
@@ -1813,7 +1823,7 @@ size_t ba_solve_smem_bytes(int np) {
   return sizeof(double) * ((size_t)N1 * (N1 + 1) / 2 + 2 * np + 32);
 }
 static size_t cost_smem(int K, int nmax) {
-  return sizeof(double) * ((size_t)15 * K + 8 + (K + 1) * 7 + (K + 1) * FR + 96 + K * 9 + (K - 1) * 15 + 2 * nmax);
+  return sizeof(double) * ((size_t)15 * K + 8 + (K + 1) * 7 + (K + 1) * FR + 160 + K * 9 + (K - 1) * 15 + 2 * nmax);
 }
 
 static bool g_tables_done = false;
