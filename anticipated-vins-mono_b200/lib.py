@@ -17,7 +17,7 @@ EXPORTS = [
     "bvio_optimize", "bvio_optimize_batch", "bvio_batch_upload", "bvio_batch_solve", "bvio_batch_download",
     "bvio_batch_free", "bvio_batch_solve_timed", "bvio_stream", "bvio_launch_count", "bvio_marginalize", "bvio_select",
     "bvio_nccl_unique_id", "bvio_comm_init", "bvio_select_sharded", "bvio_select_upload", "bvio_select_run",
-    "bvio_select_fetch", "bvio_select_free", "bvio_debug_linearize", "bvio_debug_build_delta",
+    "bvio_select_fetch", "bvio_select_free", "bvio_debug_linearize", "bvio_debug_build_delta", "bvio_triangulate",
 ]
 
 
@@ -61,6 +61,7 @@ def load():
     L.bvio_select_free.restype = None
     L.bvio_debug_linearize.argtypes = [vp, C.POINTER(abi.WindowS), C.POINTER(abi.Opts), dp, dp, dp, dp, dp]
     L.bvio_debug_build_delta.argtypes = [vp, C.POINTER(abi.SelectIn), dp, ip, dp]
+    L.bvio_triangulate.argtypes = [vp, C.POINTER(abi.WindowS), C.c_double, dp]
     _lib = L
     return L
 

@@ -234,18 +234,29 @@ class SlidingWindowSim:
         """features that become parameter blocks (estimator.cpp:712-718)"""
         return [tr for tr in self.tracks.values() if len(tr.xy) >= 2 and tr.start < WINDOW_SIZE - 2]
 
-    def build_window(self):
+    def build_window(self, backend=None):
         K = self.K
         feats = self._optimised()
-        for tr in feats:
-            if tr.depth <= 0:
-                tr.depth = triangulate(tr, self.pose, self.ric, self.tic)
         offs, fr, xy = [0], [], []
         for tr in feats:
             n = min(len(tr.xy), K - tr.start)
             fr += list(range(tr.start, tr.start + n))
             xy += tr.xy[:n]
             offs.append(len(fr))
+        need = [i for i, tr in enumerate(feats) if tr.depth <= 0]
+        if need:                                   # FeatureManager::triangulate for the features without a depth yet
+            if backend is not None and hasattr(backend, "triangulate"):
+                wt = S.Window(K=K, para_pose=self.pose.copy(), para_speed_bias=self.sb.copy(),
+                              para_ex_pose=np.concatenate([self.tic, self.qic]), para_td=np.zeros(1),
+                              inv_depth=np.ones(len(feats)), lm_obs_offset=np.array(offs, np.int32),
+                              obs_frame=np.array(fr, np.int32), obs_xy=np.array(xy, float).reshape(-1, 2),
+                              preint=np.array(self.preint), prior=None)
+                d = backend.triangulate(wt, INIT_DEPTH)
+                for i in need:
+                    feats[i].depth = float(d[i])
+            else:
+                for i in need:
+                    feats[i].depth = triangulate(feats[i], self.pose, self.ric, self.tic)
         w = S.Window(K=K, para_pose=self.pose.copy(), para_speed_bias=self.sb.copy(),
                      para_ex_pose=np.concatenate([self.tic, self.qic]), para_td=np.zeros(1),
                      inv_depth=np.array([1.0 / tr.depth for tr in feats]), lm_obs_offset=np.array(offs, np.int32),
@@ -310,7 +321,7 @@ class SlidingWindowSim:
         new_idx, n_tracked, cand, cxy = self._ingest()
         lat = None
         if len(self.pose) == self.K:
-            w, feats = self.build_window()
+            w, feats = self.build_window(backend)
             pose0 = w.para_pose[0].copy()
             t0 = time.perf_counter()
             wsol, summ = backend.optimize(w, self.opts)
@@ -372,6 +383,12 @@ class GpuBackend:
         self.ctx.check(self.L.bvio_optimize(self.ctx.h, C.byref(h.s), C.byref(o), C.byref(s)), "bvio_optimize")
         self.t_call = time.perf_counter() - t0
         return dataclasses.replace(w, para_pose=h.pose, para_speed_bias=h.sb, inv_depth=h.inv), s.as_dict()
+
+    def triangulate(self, w, init_depth):
+        h = self.abi.WindowHandle(w)
+        d = np.zeros(w.L)
+        self.ctx.check(self.L.bvio_triangulate(self.ctx.h, self.C.byref(h.s), init_depth, self.abi.dptr(d)), "bvio_triangulate")
+        return d
 
     def marginalize(self, w, flag):
         out = self.abi.call_marginalize(self.L.bvio_marginalize, w, flag, ctx=self.ctx.h)

@@ -200,6 +200,13 @@ typedef struct {
 int bvio_marginalize(bvio_ctx* ctx, const bvio_window* window, const bvio_opts* opts,
                      int32_t flag, bvio_prior_out* out);
 
+/* The step right before optimization() in Estimator::solveOdometry (estimator.cpp:471):
+ * FeatureManager::triangulate (feature_manager.cpp:202-257).  For every landmark of the window, the DLT depth in its
+ * anchor camera frame from all its observations (right singular vector of the (2 n_obs) x 4 system, svd_V[2]/svd_V[3]);
+ * values below 0.1 are replaced by init_depth (INIT_DEPTH = 5.0, parameters.cpp:3).  Uses para_pose, para_ex_pose and
+ * the observation CSR only; depth_out[L].  The caller keeps deciding which landmarks need it (estimated_depth <= 0). */
+int bvio_triangulate(bvio_ctx* ctx, const bvio_window* window, double init_depth, double* depth_out);
+
 /* ------------------------------------------------------------------------ */
 /*  Anticipated feature selection (FeatureSelector::select)                  */
 /* ------------------------------------------------------------------------ */

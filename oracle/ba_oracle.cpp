@@ -1193,4 +1193,70 @@ int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_
   return BVIO_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// f2: FeatureManager::triangulate (feature_manager.cpp:202-257).  svd_A rows as in :237-238; the right singular vector
+// of the smallest singular value (Eigen::JacobiSVD, :243) by a one-sided Jacobi SVD of the (2n x 4) matrix.
+// ---------------------------------------------------------------------------------------------
+int oracle_triangulate(const bvio_window* w, double init_depth, double* depth_out) {
+  M3 ric = qmat(q4(w->para_ex_pose + 3));
+  V3 tic = v3(w->para_ex_pose);
+  for (int l = 0; l < w->L; l++) {
+    int o0 = w->lm_obs_offset[l], n = w->lm_obs_offset[l + 1] - o0;
+    int imu_i = w->obs_frame[o0];
+    M3 Ri = qmat(q4(w->para_pose + 7 * imu_i + 3));
+    V3 t0 = v3(w->para_pose + 7 * imu_i) + Ri * tic;
+    M3 R0 = Ri * ric;
+    std::vector<double> A((size_t)2 * n * 4);
+    for (int k = 0; k < n; k++) {
+      int imu_j = w->obs_frame[o0 + k];
+      M3 Rj = qmat(q4(w->para_pose + 7 * imu_j + 3));
+      V3 t1 = v3(w->para_pose + 7 * imu_j) + Rj * tic;
+      M3 R1 = Rj * ric;
+      V3 t = transpose(R0) * (t1 - t0);
+      M3 R = transpose(R0) * R1;
+      M3 Rt = transpose(R);
+      V3 mt = -1.0 * (Rt * t);
+      double P[3][4];
+      for (int r = 0; r < 3; r++) { P[r][0] = Rt[r][0]; P[r][1] = Rt[r][1]; P[r][2] = Rt[r][2]; P[r][3] = mt[r]; }
+      V3 f{w->obs_xy[2 * (o0 + k)], w->obs_xy[2 * (o0 + k) + 1], 1.0};
+      double nf = std::sqrt(f.x * f.x + f.y * f.y + 1.0);
+      f = f / nf;
+      for (int c = 0; c < 4; c++) {
+        A[(size_t)(2 * k) * 4 + c] = f.x * P[2][c] - f.z * P[0][c];
+        A[(size_t)(2 * k + 1) * 4 + c] = f.y * P[2][c] - f.z * P[1][c];
+      }
+    }
+    double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    const int rows = 2 * n;
+    for (int sweep = 0; sweep < 60; sweep++) {
+      double off = 0;
+      for (int p = 0; p < 3; p++)
+        for (int q = p + 1; q < 4; q++) {
+          double al = 0, be = 0, ga = 0;
+          for (int r = 0; r < rows; r++) { al += A[r * 4 + p] * A[r * 4 + p]; be += A[r * 4 + q] * A[r * 4 + q]; ga += A[r * 4 + p] * A[r * 4 + q]; }
+          if (ga == 0.0) continue;
+          off = std::max(off, std::fabs(ga) / std::sqrt(al * be + 1e-300));
+          double zeta = (be - al) / (2.0 * ga);
+          double tt = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+          double c = 1.0 / std::sqrt(1.0 + tt * tt), s2 = c * tt;
+          for (int r = 0; r < rows; r++) { double ap = A[r * 4 + p], aq = A[r * 4 + q]; A[r * 4 + p] = c * ap - s2 * aq; A[r * 4 + q] = s2 * ap + c * aq; }
+          for (int r = 0; r < 4; r++) { double vp = V[r][p], vq = V[r][q]; V[r][p] = c * vp - s2 * vq; V[r][q] = s2 * vp + c * vq; }
+        }
+      if (off <= 1e-15) break;
+    }
+    int bc = 0;
+    double best = 1e300;
+    for (int c = 0; c < 4; c++) {
+      double nn = 0;
+      for (int r = 0; r < rows; r++) nn += A[r * 4 + c] * A[r * 4 + c];
+      if (nn < best) { best = nn; bc = c; }
+    }
+    double d = V[2][bc] / V[3][bc];
+    if (!(d >= 0.1)) d = init_depth;
+    depth_out[l] = d;
+  }
+  return BVIO_OK;
+}
+
 }  // extern "C"

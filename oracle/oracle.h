@@ -89,6 +89,9 @@ int oracle_select(const bvio_select_in* in, int32_t* out_ids, double* out_values
 /* Utility::logdet(M, true), utility.h:143-167 */
 double oracle_logdet(const double* M, int n);
 
+/* f2: FeatureManager::triangulate (feature_manager.cpp:202-257): DLT depth of every landmark, depth_out[L] */
+int oracle_triangulate(const bvio_window* w, double init_depth, double* depth_out);
+
 #ifdef __cplusplus
 }
 #endif

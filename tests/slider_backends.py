@@ -16,6 +16,12 @@ class OracleBackend:
         assert self.orc.oracle_optimize(C.byref(h.s), C.byref(o), C.byref(s)) == 0
         return dataclasses.replace(w, para_pose=h.pose, para_speed_bias=h.sb, inv_depth=h.inv), s.as_dict()
 
+    def triangulate(self, w, init_depth):
+        h = self.abi.WindowHandle(w)
+        d = np.zeros(w.L)
+        assert self.orc.oracle_triangulate(C.byref(h.s), init_depth, self.abi.dptr(d)) == 0
+        return d
+
     def marginalize(self, w, flag):
         return self.abi.call_marginalize(self.orc.oracle_marginalize, w, flag)
 

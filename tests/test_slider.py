@@ -78,7 +78,15 @@ class DualBackend(OracleBackend):
 
     def __init__(self, orc, abi, gpu):
         super().__init__(orc, abi)
-        self.gpu, self.n = gpu, {"optimize": 0, "marginalize": 0, "select": 0}
+        self.gpu, self.n = gpu, {"optimize": 0, "marginalize": 0, "select": 0, "triangulate": 0}
+
+    def triangulate(self, w, init_depth):
+        dg, do = self.gpu.triangulate(w, init_depth), super().triangulate(w, init_depth)
+        fb = do == init_depth
+        assert ((dg == init_depth) == fb).all()
+        assert np.abs(dg - do)[~fb].max(initial=0.0) <= 1e-9 * np.abs(do).max()
+        self.n["triangulate"] += 1
+        return do
 
     def optimize(self, w, opts):
         wg, sg = self.gpu.optimize(w.copy(), opts)
@@ -126,5 +134,6 @@ def test_closed_loop_session_gpu_vs_oracle_on_identical_inputs(pkg, oracle):
     for f in range(40):
         sim.step(dual)
     assert dual.n["optimize"] == 30 and dual.n["marginalize"] == 30 and dual.n["select"] >= 10, dual.n
+    assert dual.n["triangulate"] >= 10, dual.n
     assert sim.prior["n"] == 75
     ctx.close()
