@@ -21,6 +21,11 @@ class Preint(C.Structure):
 assert C.sizeof(Preint) == 467 * 8
 
 
+class ImuSegment(C.Structure):
+    _fields_ = [("n_samples", C.c_int32), ("dt", c_double_p), ("acc", c_double_p), ("gyr", c_double_p),
+                ("lin_ba", C.c_double * 3), ("lin_bg", C.c_double * 3)]
+
+
 class Prior(C.Structure):
     _fields_ = [("n", C.c_int32), ("nblocks", C.c_int32), ("block_kind", c_int32_p), ("block_frame", c_int32_p),
                 ("block_idx", c_int32_p), ("x0", c_double_p), ("lin_jac", c_double_p), ("lin_res", c_double_p)]

@@ -2,6 +2,8 @@
 //   bvio_triangulate   FeatureManager::triangulate (vins_estimator/src/feature_manager.cpp:202-257): DLT depth of
 //                      every landmark from all its observations, the step right before optimization() in
 //                      Estimator::solveOdometry (estimator.cpp:471)
+//   bvio_preintegrate  IntegrationBase::{push_back, propagate, midPointIntegration, repropagate}
+//                      (vins_estimator/src/factor/integration_base.h:30-158): the IMU factors' inputs
 // One warp per landmark: lane = row of the (2 n_obs) x 4 DLT matrix (n_obs <= 16 -> 32 rows, exactly one warp); the
 // right singular vector of the smallest singular value comes from a one-sided (Hestenes) Jacobi SVD whose column dot
 // products are warp reductions -- the same accuracy class as the Eigen::JacobiSVD the reference calls (:243), no
@@ -93,7 +95,166 @@ __global__ void __launch_bounds__(256) tri_kernel(int L, int K, const double* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// IntegrationBase::{push_back, propagate, midPointIntegration} (integration_base.h:30-158): one CTA per frame
+// interval.  The state (delta_p/q/v) is advanced by thread 0; the 15x15 products jacobian = F jacobian and
+// covariance = F cov F^T + V noise V^T (:142-143) are spread over the CTA, one output entry per thread.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put33(double* M, int ld, int r0, int c0, const double* m, double s) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) M[(r0 + i) * ld + c0 + j] = s * m[i * 3 + j];
+}
+
+__global__ void __launch_bounds__(256) preint_kernel(int nseg, const int* __restrict__ seg_off, const double* __restrict__ dts,
+                                                     const double* __restrict__ acc, const double* __restrict__ gyr,
+                                                     const double* __restrict__ lin_b /*[nseg][6]*/, double acc_n, double gyr_n,
+                                                     double acc_w, double gyr_w, double* __restrict__ out /*[nseg][467]*/) {
+  __shared__ double F[15 * 15], V[15 * 18], J[225], Cv[225], T[225], st[16], noise[18];
+  const int sg = blockIdx.x, tid = threadIdx.x;
+  if (sg >= nseg) return;
+  const int s0 = seg_off[sg], ns = seg_off[sg + 1] - s0 - 1;     // ns propagation steps from ns + 1 samples
+  const double* ba = lin_b + sg * 6;
+  const double* bg = ba + 3;
+  for (int i = tid; i < 225; i += blockDim.x) { J[i] = (i / 15 == i % 15) ? 1.0 : 0.0; Cv[i] = 0.0; }
+  if (tid < 18) noise[tid] = (tid < 3 || (tid >= 6 && tid < 9)) ? acc_n * acc_n : (tid < 12 ? gyr_n * gyr_n : (tid < 15 ? acc_w * acc_w : gyr_w * gyr_w));
+  if (tid == 0) { for (int i = 0; i < 16; i++) st[i] = 0.0; st[6] = 1.0; }   // dp(0..2) dq xyzw(3..6) dv(7..9) sum_dt(10)
+  __syncthreads();
+  for (int k = 0; k < ns; k++) {
+    for (int i = tid; i < 225; i += blockDim.x) F[i] = 0.0;
+    for (int i = tid; i < 270; i += blockDim.x) V[i] = 0.0;
+    __syncthreads();
+    if (tid == 0) {
+      const double dt = dts[s0 + k + 1];
+      const d3 a0{acc[3 * (s0 + k)] - ba[0], acc[3 * (s0 + k) + 1] - ba[1], acc[3 * (s0 + k) + 2] - ba[2]};
+      const d3 a1{acc[3 * (s0 + k + 1)] - ba[0], acc[3 * (s0 + k + 1) + 1] - ba[1], acc[3 * (s0 + k + 1) + 2] - ba[2]};
+      const d3 wx{0.5 * (gyr[3 * (s0 + k)] + gyr[3 * (s0 + k + 1)]) - bg[0], 0.5 * (gyr[3 * (s0 + k) + 1] + gyr[3 * (s0 + k + 1) + 1]) - bg[1],
+                  0.5 * (gyr[3 * (s0 + k) + 2] + gyr[3 * (s0 + k + 1) + 2]) - bg[2]};
+      const q4 dq{st[3], st[4], st[5], st[6]};
+      const d3 dp{st[0], st[1], st[2]}, dv{st[7], st[8], st[9]};
+      // midPointIntegration (:64-88)
+      const d3 un_acc_0 = qrot(dq, a0);
+      const q4 rq = qmul(dq, q4{wx.x * dt / 2, wx.y * dt / 2, wx.z * dt / 2, 1.0});
+      const d3 un_acc_1 = qrot(rq, a1);
+      const d3 un_acc = 0.5 * (un_acc_0 + un_acc_1);
+      const d3 rp = dp + dt * dv + (0.5 * dt * dt) * un_acc;
+      const d3 rv = dv + dt * un_acc;
+      double Rq[9], Rr[9], Rw[9], Ra0[9], Ra1[9], I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, m1[9], m2[9], ImW[9];
+      qmat(dq, Rq); qmat(rq, Rr);
+      const double sk[3][9] = {{0, -wx.z, wx.y, wx.z, 0, -wx.x, -wx.y, wx.x, 0}, {0, -a0.z, a0.y, a0.z, 0, -a0.x, -a0.y, a0.x, 0},
+                               {0, -a1.z, a1.y, a1.z, 0, -a1.x, -a1.y, a1.x, 0}};
+      for (int i = 0; i < 9; i++) { Rw[i] = sk[0][i]; Ra0[i] = sk[1][i]; Ra1[i] = sk[2][i]; ImW[i] = I3[i] - dt * Rw[i]; }
+      // F (:93-112)
+      double RqA0[9], RrA1[9], RrA1ImW[9], sum[9];
+      mm3(Rq, Ra0, RqA0); mm3(Rr, Ra1, RrA1); mm3(RrA1, ImW, RrA1ImW);
+      put33(F, 15, 0, 0, I3, 1.0);
+      for (int i = 0; i < 9; i++) sum[i] = (-0.25 * dt * dt) * RqA0[i] + (-0.25 * dt * dt) * RrA1ImW[i];
+      put33(F, 15, 0, 3, sum, 1.0);
+      put33(F, 15, 0, 6, I3, dt);
+      for (int i = 0; i < 9; i++) m1[i] = Rq[i] + Rr[i];
+      put33(F, 15, 0, 9, m1, -0.25 * dt * dt);
+      put33(F, 15, 0, 12, RrA1, -0.25 * dt * dt * -dt);
+      put33(F, 15, 3, 3, ImW, 1.0);
+      put33(F, 15, 3, 12, I3, -dt);
+      for (int i = 0; i < 9; i++) sum[i] = (-0.5 * dt) * RqA0[i] + (-0.5 * dt) * RrA1ImW[i];
+      put33(F, 15, 6, 3, sum, 1.0);
+      put33(F, 15, 6, 6, I3, 1.0);
+      put33(F, 15, 6, 9, m1, -0.5 * dt);
+      put33(F, 15, 6, 12, RrA1, -0.5 * dt * -dt);
+      put33(F, 15, 9, 9, I3, 1.0);
+      put33(F, 15, 12, 12, I3, 1.0);
+      // V (:115-127)
+      for (int i = 0; i < 9; i++) m2[i] = -RrA1[i];
+      put33(V, 18, 0, 0, Rq, 0.25 * dt * dt);
+      put33(V, 18, 0, 3, m2, 0.25 * dt * dt * 0.5 * dt);
+      put33(V, 18, 0, 6, Rr, 0.25 * dt * dt);
+      put33(V, 18, 0, 9, m2, 0.25 * dt * dt * 0.5 * dt);
+      put33(V, 18, 3, 3, I3, 0.5 * dt);
+      put33(V, 18, 3, 9, I3, 0.5 * dt);
+      put33(V, 18, 6, 0, Rq, 0.5 * dt);
+      put33(V, 18, 6, 3, m2, 0.5 * dt * 0.5 * dt);
+      put33(V, 18, 6, 6, Rr, 0.5 * dt);
+      put33(V, 18, 6, 9, m2, 0.5 * dt * 0.5 * dt);
+      put33(V, 18, 9, 12, I3, dt);
+      put33(V, 18, 12, 15, I3, dt);
+      const q4 qn = qnormalized(rq);
+      st[0] = rp.x; st[1] = rp.y; st[2] = rp.z; st[3] = qn.x; st[4] = qn.y; st[5] = qn.z; st[6] = qn.w;
+      st[7] = rv.x; st[8] = rv.y; st[9] = rv.z; st[10] += dt;
+    }
+    __syncthreads();
+    double jn = 0, tn = 0;
+    const int i = tid / 15, j = tid - 15 * i;
+    if (tid < 225) {
+      for (int q = 0; q < 15; q++) { jn += F[i * 15 + q] * J[q * 15 + j]; tn += F[i * 15 + q] * Cv[q * 15 + j]; }
+    }
+    __syncthreads();
+    if (tid < 225) { J[tid] = jn; T[tid] = tn; }
+    __syncthreads();
+    if (tid < 225) {
+      double cn = 0;
+      for (int q = 0; q < 15; q++) cn += T[i * 15 + q] * F[j * 15 + q];
+      for (int q = 0; q < 18; q++) cn += V[i * 18 + q] * noise[q] * V[j * 18 + q];
+      Cv[tid] = cn;
+    }
+    __syncthreads();
+  }
+  double* o = out + (size_t)sg * PREINT_DOUBLES;
+  if (tid < 3) { o[tid] = st[tid]; o[7 + tid] = st[7 + tid]; o[10 + tid] = ba[tid]; o[13 + tid] = bg[tid]; }
+  if (tid < 4) o[3 + tid] = st[3 + tid];
+  if (tid == 0) o[16] = st[10];
+  for (int e = tid; e < 225; e += blockDim.x) { o[17 + e] = J[e]; o[17 + 225 + e] = Cv[e]; }
+}
+
 }  // namespace
+
+extern "C" int bvio_preintegrate(bvio_ctx* ctx, const bvio_imu_segment* segs, int32_t n_segs, double acc_n, double gyr_n,
+                                 double acc_w, double gyr_w, bvio_preint* out) {
+  if (!ctx || !segs || n_segs < 1 || !out) return fail(ctx, BVIO_ERR_INVALID, "null argument");
+  static_assert(sizeof(bvio_preint) == PREINT_DOUBLES * sizeof(double), "bvio_preint layout");
+  int total = 0;
+  for (int s = 0; s < n_segs; s++) {
+    if (segs[s].n_samples < 1 || !segs[s].dt || !segs[s].acc || !segs[s].gyr) return fail(ctx, BVIO_ERR_INVALID, "bad IMU segment");
+    total += segs[s].n_samples;
+  }
+  cudaSetDevice(ctx->device);
+  Carver cv;
+  const size_t D = sizeof(double), I = sizeof(int);
+  size_t o_off = cv.take((size_t)(n_segs + 1) * I), o_dt = cv.take((size_t)total * D), o_acc = cv.take((size_t)total * 3 * D);
+  size_t o_gyr = cv.take((size_t)total * 3 * D), o_b = cv.take((size_t)n_segs * 6 * D);
+  const size_t in_bytes = cv.off;
+  size_t o_out = cv.take((size_t)n_segs * PREINT_DOUBLES * D);
+  Slab slab;
+  bool from_cache = false;
+  cudaError_t e = slab_acquire(ctx->sel_cache, ctx->sel_cache_busy, cv.off, cv.off, slab, from_cache);
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("preintegrate alloc: ") + cudaGetErrorString(e));
+  int* h_off = (int*)(slab.h + o_off);
+  int run = 0;
+  for (int s = 0; s < n_segs; s++) {
+    h_off[s] = run;
+    memcpy(slab.h + o_dt + (size_t)run * D, segs[s].dt, (size_t)segs[s].n_samples * D);
+    memcpy(slab.h + o_acc + (size_t)run * 3 * D, segs[s].acc, (size_t)segs[s].n_samples * 3 * D);
+    memcpy(slab.h + o_gyr + (size_t)run * 3 * D, segs[s].gyr, (size_t)segs[s].n_samples * 3 * D);
+    memcpy(slab.h + o_b + (size_t)s * 6 * D, segs[s].lin_ba, 3 * D);
+    memcpy(slab.h + o_b + (size_t)s * 6 * D + 3 * D, segs[s].lin_bg, 3 * D);
+    run += segs[s].n_samples;
+  }
+  h_off[n_segs] = run;
+  e = cudaMemcpyAsync(slab.d, slab.h, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    preint_kernel<<<n_segs, 256, 0, ctx->stream>>>(n_segs, (const int*)(slab.d + o_off), (const double*)(slab.d + o_dt),
+                                                   (const double*)(slab.d + o_acc), (const double*)(slab.d + o_gyr),
+                                                   (const double*)(slab.d + o_b), acc_n, gyr_n, acc_w, gyr_w, (double*)(slab.d + o_out));
+    ctx->launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(slab.h + o_out, slab.d + o_out, (size_t)n_segs * PREINT_DOUBLES * D, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) memcpy(out, slab.h + o_out, (size_t)n_segs * PREINT_DOUBLES * D);
+  slab_release(slab, ctx->sel_cache_busy, from_cache);
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("preintegrate: ") + cudaGetErrorString(e));
+  return BVIO_OK;
+}
 
 extern "C" int bvio_triangulate(bvio_ctx* ctx, const bvio_window* w, double init_depth, double* depth_out) {
   if (!ctx || !w || !depth_out) return fail(ctx, BVIO_ERR_INVALID, "null argument");

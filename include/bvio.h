@@ -207,6 +207,21 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* window, const bvio_opts* 
  * the observation CSR only; depth_out[L].  The caller keeps deciding which landmarks need it (estimated_depth <= 0). */
 int bvio_triangulate(bvio_ctx* ctx, const bvio_window* window, double init_depth, double* depth_out);
 
+/* IMU preintegration between two frames: IntegrationBase::{push_back, propagate, midPointIntegration} and -- called
+ * again with new linearization biases -- repropagate (factor/integration_base.h:30-158), which in the reference runs in
+ * Estimator::processIMU (estimator.cpp:86-117).  Sample 0 of a segment is (acc_0, gyr_0) of the constructor (its dt is
+ * ignored); samples 1..n_samples-1 are the push_back() calls.  Noise densities ACC_N, GYR_N, ACC_W, GYR_W
+ * (parameters.cpp:69-72) fill the 18x18 noise matrix (:21-27). */
+typedef struct {
+  int32_t n_samples;
+  const double* dt;             /* [n_samples]                                   */
+  const double* acc;            /* [n_samples][3]                                */
+  const double* gyr;            /* [n_samples][3]                                */
+  double lin_ba[3], lin_bg[3];  /* linearized_ba / linearized_bg                 */
+} bvio_imu_segment;
+int bvio_preintegrate(bvio_ctx* ctx, const bvio_imu_segment* segments, int32_t n_segments, double acc_n, double gyr_n,
+                      double acc_w, double gyr_w, bvio_preint* out /* [n_segments] */);
+
 /* ------------------------------------------------------------------------ */
 /*  Anticipated feature selection (FeatureSelector::select)                  */
 /* ------------------------------------------------------------------------ */
