@@ -102,45 +102,52 @@ int64_t bvio_launch_count(const bvio_ctx* ctx) { return ctx ? ctx->launches : 0;
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
-static int validate(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* o, int K0) {
-  if (!w || !o) return fail(ctx, BVIO_ERR_INVALID, "null window/opts");
+// pure (thread-safe) structural validation of one window; *msg names the first problem
+static int validate_msg(const bvio_window* w, const bvio_opts* o, int K0, const char** msg) {
+  if (!w || !o) { *msg = "null window/opts"; return BVIO_ERR_INVALID; }
   if (o->estimate_td && (!w->obs_vel || !w->obs_td || !w->obs_row || !w->para_td))
-    return fail(ctx, BVIO_ERR_INVALID, "estimate_td needs obs_vel / obs_td / obs_row / para_td");
-  if (o->estimate_td && !(o->ROW > 0)) return fail(ctx, BVIO_ERR_INVALID, "estimate_td needs ROW > 0");
+    { *msg = "estimate_td needs obs_vel / obs_td / obs_row / para_td"; return BVIO_ERR_INVALID; }
+  if (o->estimate_td && !(o->ROW > 0)) { *msg = "estimate_td needs ROW > 0"; return BVIO_ERR_INVALID; }
   if (15 * w->K + (o->estimate_extrinsic ? 6 : 0) + (o->estimate_td ? 1 : 0) > 226 ||
       w->K + (o->estimate_extrinsic ? 1 : 0) + (o->estimate_td ? 1 : 0) > BVIO_KMAX)
-    return fail(ctx, BVIO_ERR_INVALID, "K too large with estimate_extrinsic / estimate_td (reduced system must fit one CTA's shared memory)");
+    { *msg = "K too large with estimate_extrinsic / estimate_td (reduced system must fit one CTA's shared memory)"; return BVIO_ERR_INVALID; }
   if (o->strategy != BVIO_STRATEGY_LM && o->strategy != BVIO_STRATEGY_DOGLEG)
-    return fail(ctx, BVIO_ERR_INVALID, "unknown trust-region strategy");
-  if (w->K < 2 || w->K > BVIO_KMAX - 1) return fail(ctx, BVIO_ERR_INVALID, "K out of range [2,15] (reduced system must fit one CTA's shared memory)");
-  if (w->K != K0) return fail(ctx, BVIO_ERR_INVALID, "all windows of a batch must have the same K");
+    { *msg = "unknown trust-region strategy"; return BVIO_ERR_INVALID; }
+  if (w->K < 2 || w->K > BVIO_KMAX - 1) { *msg = "K out of range [2,15] (reduced system must fit one CTA's shared memory)"; return BVIO_ERR_INVALID; }
+  if (w->K != K0) { *msg = "all windows of a batch must have the same K"; return BVIO_ERR_INVALID; }
   if (w->L < 0 || !w->para_pose || !w->para_speed_bias || !w->para_ex_pose || !w->preint)
-    return fail(ctx, BVIO_ERR_INVALID, "null state / preint arrays");
+    { *msg = "null state / preint arrays"; return BVIO_ERR_INVALID; }
   if (w->L > 0 && (!w->inv_depth || !w->lm_obs_offset || !w->obs_frame || !w->obs_xy))
-    return fail(ctx, BVIO_ERR_INVALID, "null landmark arrays");
-  if (w->L > 0 && w->lm_obs_offset[0] != 0) return fail(ctx, BVIO_ERR_INVALID, "lm_obs_offset[0] != 0");
+    { *msg = "null landmark arrays"; return BVIO_ERR_INVALID; }
+  if (w->L > 0 && w->lm_obs_offset[0] != 0) { *msg = "lm_obs_offset[0] != 0"; return BVIO_ERR_INVALID; }
   for (int l = 0; l < w->L; l++) {
     int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1], n = o1 - o0;
-    if (n < 2 || n > BVIO_KMAX) return fail(ctx, BVIO_ERR_INVALID, "landmark needs 2..16 observations");
+    if (n < 2 || n > BVIO_KMAX) { *msg = "landmark needs 2..16 observations"; return BVIO_ERR_INVALID; }
     for (int k = o0; k < o1; k++) {
       int f = w->obs_frame[k];
       if (f < 0 || f >= w->K || (k > o0 && f <= w->obs_frame[k - 1]))
-        return fail(ctx, BVIO_ERR_INVALID, "obs_frame must be strictly ascending within [0,K)");
+        { *msg = "obs_frame must be strictly ascending within [0,K)"; return BVIO_ERR_INVALID; }
     }
   }
   if (w->prior) {
     const bvio_prior* p = w->prior;
     if (p->n < 0 || p->n > 256 || p->nblocks < 0 || p->nblocks > PRIOR_MAXB)
-      return fail(ctx, BVIO_ERR_INVALID, "prior dimension out of range");
+      { *msg = "prior dimension out of range"; return BVIO_ERR_INVALID; }
     for (int b = 0; b < p->nblocks; b++) {
       int kind = p->block_kind[b], loc = kind == BVIO_BLK_SPEEDBIAS ? 9 : (kind == BVIO_BLK_TD ? 1 : 6);
       if (kind < 0 || kind > 3 || p->block_idx[b] < 0 || p->block_idx[b] + loc > p->n)
-        return fail(ctx, BVIO_ERR_INVALID, "prior block out of range");
+        { *msg = "prior block out of range"; return BVIO_ERR_INVALID; }
       if ((kind == BVIO_BLK_POSE || kind == BVIO_BLK_SPEEDBIAS) && (p->block_frame[b] < 0 || p->block_frame[b] >= w->K))
-        return fail(ctx, BVIO_ERR_INVALID, "prior block frame out of range");
+        { *msg = "prior block frame out of range"; return BVIO_ERR_INVALID; }
     }
   }
   return BVIO_OK;
+}
+
+static int validate(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* o, int K0) {
+  const char* msg = "";
+  int rc = validate_msg(w, o, K0, &msg);
+  return rc ? fail(ctx, rc, msg) : BVIO_OK;
 }
 
 static Slab& cache_of(bvio_ctx* ctx, int slot) { return slot == 0 ? ctx->ba_cache : ctx->ba_pipe[slot - 1]; }
@@ -159,9 +166,23 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   cudaSetDevice(ctx->device);
   const int K = ws[0].K;
   int total_L = 0, total_obs = 0, nmax = 1, maxL = 0;
+  {
+    // structural validation walks every observation: spread large batches over host threads
+    const int nthreads = B < 16 ? 1 : (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 8);
+    std::vector<int> rcs(nthreads, BVIO_OK);
+    std::vector<const char*> msgs(nthreads, "");
+    auto work = [&](int t) {
+      for (int b = t; b < B && rcs[t] == BVIO_OK; b += nthreads) rcs[t] = validate_msg(ws + b, o, K, &msgs[t]);
+    };
+    if (nthreads == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
+      for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < nthreads; t++) if (rcs[t]) return fail(ctx, rcs[t], msgs[t]);
+  }
   for (int b = 0; b < B; b++) {
-    int rc = validate(ctx, ws + b, o, K);
-    if (rc) return rc;
     total_L += ws[b].L;
     total_obs += ws[b].L ? ws[b].lm_obs_offset[ws[b].L] : 0;
     maxL = std::max(maxL, ws[b].L);
@@ -460,8 +481,24 @@ static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, b
   const double* tdo = (const double*)(bb->slab.h + bb->o_td_out);
   const BaCtrl* ctrl = (const BaCtrl*)(bb->slab.h + bb->o_ctrl);
   int rc = BVIO_OK;
+  auto scatter = [&](int b) {
+      bvio_window& w = windows[b];
+      memcpy(w.para_pose, pose + (size_t)b * bt.K * 7, (size_t)bt.K * 7 * sizeof(double));
+      memcpy(w.para_speed_bias, sb + (size_t)b * bt.K * 9, (size_t)bt.K * 9 * sizeof(double));
+      int L = bb->lm_base[b + 1] - bb->lm_base[b];
+      const int* perm = bb->perm.data() + bb->lm_base[b];
+      for (int j = 0; j < L; j++) w.inv_depth[perm[j]] = invd[bb->lm_base[b] + j];
+      if (bt.est_ex) memcpy(w.para_ex_pose, exo + (size_t)b * 7, 7 * sizeof(double));
+      if (bt.est_td) w.para_td[0] = tdo[b];
+  };
+  if (windows && bt.B >= 64) {
+    const int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 8);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back([&, t]() { for (int b = t; b < bt.B; b += nthreads) scatter(b); });
+    for (auto& x : th) x.join();
+  }
   for (int b = 0; b < bt.B; b++) {
-    if (windows) {
+    if (windows && bt.B < 64) {
       bvio_window& w = windows[b];
       memcpy(w.para_pose, pose + (size_t)b * bt.K * 7, (size_t)bt.K * 7 * sizeof(double));
       memcpy(w.para_speed_bias, sb + (size_t)b * bt.K * 9, (size_t)bt.K * 9 * sizeof(double));

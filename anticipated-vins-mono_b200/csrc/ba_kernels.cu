@@ -1488,29 +1488,34 @@ __global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
   if (ctrl->done || !ctrl->stepped || !ctrl->solve_ok) return;
   double* sn = sm;             // [np] Gauss-Newton step (pose part)
   double* st = sn + np;        // [np] t (pose part)
-  double* red = st + np;       // [16 * DOG_REC]
+  double* red = st + np;       // [32 * DOG_REC]
   __shared__ int s_last;
   for (int i = threadIdx.x; i < np; i += blockDim.x) {
     sn[i] = bt.delta_p[(size_t)w * np + i];
     st[i] = bt.dog_t[(size_t)w * np + i];
   }
   __syncthreads();
-  const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15, NG = blockDim.x >> 4;
-  const unsigned gmask = 0xffffffffu;   // both half-warps always iterate together (warp-uniform trip count)
+  // 8 lanes per landmark, lane = observation (a second trip for tracks longer than 8): 4 landmarks per warp
+  const int grp = threadIdx.x >> 3, l16 = threadIdx.x & 7, NG = blockDim.x >> 3;
+  const unsigned gmask = 0xffffffffu;   // the four groups of a warp always iterate together (warp-uniform trip count)
   const double mu = ctrl->mu;
   int l0, l1;
   tile_range(bt, w, t, l0, l1);
   double a[6] = {0, 0, 0, 0, 0, 0};
-  for (int lw = l0 + (grp & ~1); lw < l1; lw += NG) {
-    const bool act = lw + (grp & 1) < l1;
-    const int l = act ? lw + (grp & 1) : l1 - 1;      // the idle half-warp shadows a valid landmark, results dropped
+  for (int lw = l0 + (grp & ~3); lw < l1; lw += NG) {
+    const bool act = lw + (grp & 3) < l1;
+    const int l = act ? lw + (grp & 3) : l1 - 1;      // idle groups shadow a valid landmark, results dropped
     const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0;
     double wn = 0, wt = 0;
-    if (l16 < n) {
-      const int fr = bt.obs_frame[o0 + l16];
-      const double* wp = bt.w + (size_t)(o0 + l16) * 6;
 #pragma unroll
-      for (int k = 0; k < 6; k++) { wn += wp[k] * sn[15 * fr + k]; wt += wp[k] * st[15 * fr + k]; }
+    for (int trip = 0; trip < 2; trip++) {
+      const int ko = l16 + 8 * trip;
+      if (ko < n) {
+        const int fr = bt.obs_frame[o0 + ko];
+        const double* wp = bt.w + (size_t)(o0 + ko) * 6;
+#pragma unroll
+        for (int k = 0; k < 6; k++) { wn += wp[k] * sn[15 * fr + k]; wt += wp[k] * st[15 * fr + k]; }
+      }
     }
     if (l16 == 0 && (bt.est_ex | bt.est_td)) {      // extra blocks: extrinsic (6) and / or td (column 0 of its slot)
       const int XB = bt.est_ex + bt.est_td;
@@ -1522,7 +1527,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
       if (bt.est_td) { const int o = 15 * bt.K + 6 * bt.est_ex; wn += wp[6 * bt.est_ex] * sn[o]; wt += wp[6 * bt.est_ex] * st[o]; }
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) { wn += __shfl_xor_sync(gmask, wn, o, 16); wt += __shfl_xor_sync(gmask, wt, o, 16); }
+    for (int o = 4; o > 0; o >>= 1) { wn += __shfl_xor_sync(gmask, wn, o, 8); wt += __shfl_xor_sync(gmask, wt, o, 8); }
     if (l16 == 0 && act) {
       const double h = bt.h[l], b = bt.b[l];
       const double sl2 = bt.jacobi_scaling ? bt.sl2[l] : 1.0;
@@ -1901,7 +1906,7 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
   if (!with_step || bt.undamped) { if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); } return 2; }
   int nk = 3;
   if (bt.strategy) {   // dogleg combination; its time is booked with the reduced solve
-    ba_dogleg_kernel<<<dim3(bt.T, bt.B), BA_THREADS, sizeof(double) * (2 * bt.np + 16 * DOG_REC), st>>>(bt);
+    ba_dogleg_kernel<<<dim3(bt.T, bt.B), BA_THREADS, sizeof(double) * (2 * bt.np + 32 * DOG_REC), st>>>(bt);
     nk = 4;
   }
   if (ev) cudaEventRecord(ev[2], st);
