@@ -543,12 +543,14 @@ void bvio_batch_free(bvio_ctx* ctx, bvio_batch* bb) {
 }
 
 // One-shot solve of B independent windows with host buffers.  Large batches are cut into sub-batches of about
-// one window per SM and software-pipelined on the context stream: while the GPU solves sub-batch i the host
+// two windows per SM and software-pipelined on the context stream: while the GPU solves sub-batch i the host
 // packs sub-batch i+1 into its own pinned slab, and the D2H of i trails its solve -- so the wall time tends to
 // max(host packing, device solve) instead of their sum.
 int bvio_optimize_batch(bvio_ctx* ctx, bvio_window* windows, int32_t B, const bvio_opts* opts, bvio_summary* summaries) {
   if (!ctx || !windows || B < 1 || !opts) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
-  int S = std::min(bvio_ctx::PIPE, std::max(1, B / std::max(1, ctx->sm_count)));
+  int per = std::max(1, 2 * ctx->sm_count);   // two windows per SM per sub-batch: measured optimum (74 ... 592 swept)
+  if (const char* ev = getenv("BVIO_PIPE_WINDOWS")) per = std::max(1, atoi(ev));   // tuning knob: windows per sub-batch
+  int S = std::min(bvio_ctx::PIPE, std::max(1, B / per));
   if (S == 1) {
     bvio_batch* bb = nullptr;
     int rc = upload_impl(ctx, windows, B, opts, 0, 0, &bb);
