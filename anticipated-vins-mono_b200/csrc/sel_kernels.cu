@@ -308,8 +308,73 @@ __global__ void __launch_bounds__(256) sel_omega_kernel(SelProb sp) {
 // shuffles, so the whole factorization runs without shared-memory round trips.  T is a compile-time
 // constant so that every register index is static.
 // =============================================================================================
+// T > 32 (HORIZON 11..16; the reference compiles HORIZON = 13, T = 39): lane i keeps row i of the leading 32 x 32 block
+// as above, and lane k additionally keeps column k of the E = T - 32 trailing rows.  While column j of L11 is being
+// finalised the trailing rows ride along (L21 = A21 L11^-T: E extra broadcasts per column), the E x E Schur complement
+// A22 - L21 L21^T is E(E+1)/2 warp reductions, and its small Cholesky runs replicated in every lane.  ~50 live doubles
+// per lane instead of the 2 x T of the row-per-lane scheme (which spilled).
+template <int T, bool ADD>
+__device__ __forceinline__ double warp_chol_logdet_wide(const double* A, int lane, const double* C, double p) {
+  constexpr int E = T - 32;
+  double a[32], b[E];
+  {
+    const double* row = A + tri(lane, 0);
+    const double* crow = ADD ? C + tri(lane, 0) : nullptr;
+#pragma unroll
+    for (int k = 0; k < 32; k++) a[k] = (k <= lane) ? (ADD ? fma(p, crow[k], row[k]) : row[k]) : 0.0;
+#pragma unroll
+    for (int r = 0; r < E; r++) b[r] = ADD ? fma(p, C[tri(32 + r, lane)], A[tri(32 + r, lane)]) : A[tri(32 + r, lane)];
+  }
+  double mypiv = 1.0;
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const double pj = __shfl_sync(0xffffffffu, a[j], j);
+    bad |= !(pj > 0.0);
+    if (lane == j) mypiv = pj;
+    const double inv = rsqrt(pj);
+    a[j] *= inv;                                   // lane i: L11[i][j]
+#pragma unroll
+    for (int k = j + 1; k < 32; k++) {
+      const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+      a[k] = fma(-a[j], lkj, a[k]);
+    }
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      const double l21 = __shfl_sync(0xffffffffu, b[r] * inv, j);      // L21[r][j], final
+      if (lane == j) b[r] = l21;
+      else if (lane > j) b[r] = fma(-l21, a[j], b[r]);                   // A21[r][lane] -= L21[r][j] L11[lane][j]
+    }
+  }
+  // Schur complement of the trailing block, replicated in every lane, then its Cholesky
+  double s22[E][E];
+#pragma unroll
+  for (int r = 0; r < E; r++)
+#pragma unroll
+    for (int c = 0; c <= r; c++) {
+      const double a22 = ADD ? fma(p, C[tri(32 + r, 32 + c)], A[tri(32 + r, 32 + c)]) : A[tri(32 + r, 32 + c)];
+      s22[r][c] = a22 - warp_sum(b[r] * b[c]);
+    }
+  double l = warp_sum(log(mypiv));
+#pragma unroll
+  for (int j = 0; j < E; j++) {
+    const double pj = s22[j][j];
+    bad |= !(pj > 0.0);
+    l += log(pj);
+    const double inv = rsqrt(pj);
+#pragma unroll
+    for (int r = j + 1; r < E; r++) s22[r][j] *= inv;
+#pragma unroll
+    for (int r = j + 1; r < E; r++)
+#pragma unroll
+      for (int c = j + 1; c <= r; c++) s22[r][c] = fma(-s22[r][j], s22[c][j], s22[r][c]);
+  }
+  return bad ? NAN : 0.5 * l;
+}
+
 template <int T, bool ADD = false>
 __device__ __forceinline__ double warp_chol_logdet(const double* A, int lane, const double* C = nullptr, double p = 0.0) {
+  if constexpr (T > 32) return warp_chol_logdet_wide<T, ADD>(A, lane, C, p);
   constexpr int R = (T + 31) / 32;
   double a[R][T];
 #pragma unroll
