@@ -256,6 +256,70 @@ extern "C" int bvio_preintegrate(bvio_ctx* ctx, const bvio_imu_segment* segs, in
   return BVIO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// HorizonGenerator::imu (utility/horizon_generator.cpp:25-70): constant-acceleration, constant-rate propagation of
+// x_{k+1} over the horizon.  A recurrence of (H-1) * nr_imu dependent steps: one thread.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void horizon_imu_kernel(int H, const double* __restrict__ in /*pos0 quat0 ba0 pos1 quat1 vel1 a w: 3 4 3 3 4 3 3 3*/,
+                                   int nr_imu, double delta, double* __restrict__ hpos, double* __restrict__ hquat) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const d3 grav{0.0, 0.0, -9.80665};                                     // state_defs.h:37-41
+  const d3 ba{in[7], in[8], in[9]};
+  d3 p{in[10], in[11], in[12]}, v{in[17], in[18], in[19]};
+  q4 q{in[13], in[14], in[15], in[16]};
+  const d3 a{in[20] - ba.x, in[21] - ba.y, in[22] - ba.z};
+  const q4 qimu{in[23] * delta / 2, in[24] * delta / 2, in[25] * delta / 2, 1.0};   // Utility::deltaQ(w * deltaImu), not normalised
+  for (int i = 0; i < 3; i++) { hpos[i] = in[i]; hpos[3 + i] = in[10 + i]; }
+  for (int i = 0; i < 4; i++) { hquat[i] = in[3 + i]; hquat[4 + i] = in[13 + i]; }
+  for (int h = 2; h <= H; h++) {
+    for (int i = 0; i < nr_imu; i++) {
+      q = qmul(q, qimu);                                                 // :52
+      const d3 qa = qrot(q, a);                                          // Eigen quaternion * vector
+      v = v + delta * (grav + qa);                                       // :58
+      p = p + delta * v + (0.5 * delta * delta) * grav + (0.5 * delta * delta) * qa;   // :61
+    }
+    hpos[3 * h] = p.x; hpos[3 * h + 1] = p.y; hpos[3 * h + 2] = p.z;
+    hquat[4 * h] = q.x; hquat[4 * h + 1] = q.y; hquat[4 * h + 2] = q.z; hquat[4 * h + 3] = q.w;
+  }
+}
+}  // namespace
+
+extern "C" int bvio_horizon_imu(bvio_ctx* ctx, int32_t H, const double* pos0, const double* quat0, const double* ba0,
+                                const double* pos1, const double* quat1, const double* vel1, const double* acc,
+                                const double* gyr, int32_t nr_imu, double delta_imu, double* horizon_pos,
+                                double* horizon_quat) {
+  if (!ctx || !pos0 || !quat0 || !ba0 || !pos1 || !quat1 || !vel1 || !acc || !gyr || !horizon_pos || !horizon_quat)
+    return fail(ctx, BVIO_ERR_INVALID, "null argument");
+  if (H < 1 || H > BVIO_HMAX || nr_imu < 0) return fail(ctx, BVIO_ERR_INVALID, "H out of range [1,16] / nr_imu < 0");
+  cudaSetDevice(ctx->device);
+  Carver cv;
+  const size_t D = sizeof(double);
+  size_t o_in = cv.take(26 * D);
+  const size_t in_bytes = cv.off;
+  size_t o_pos = cv.take((size_t)(H + 1) * 3 * D), o_quat = cv.take((size_t)(H + 1) * 4 * D);
+  Slab slab;
+  bool from_cache = false;
+  cudaError_t e = slab_acquire(ctx->sel_cache, ctx->sel_cache_busy, cv.off, cv.off, slab, from_cache);
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("horizon alloc: ") + cudaGetErrorString(e));
+  double* h = (double*)(slab.h + o_in);
+  memcpy(h, pos0, 3 * D); memcpy(h + 3, quat0, 4 * D); memcpy(h + 7, ba0, 3 * D); memcpy(h + 10, pos1, 3 * D);
+  memcpy(h + 13, quat1, 4 * D); memcpy(h + 17, vel1, 3 * D); memcpy(h + 20, acc, 3 * D); memcpy(h + 23, gyr, 3 * D);
+  e = cudaMemcpyAsync(slab.d, slab.h, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    horizon_imu_kernel<<<1, 32, 0, ctx->stream>>>(H, (const double*)(slab.d + o_in), nr_imu, delta_imu, (double*)(slab.d + o_pos),
+                                                 (double*)(slab.d + o_quat));
+    ctx->launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(slab.h + o_pos, slab.d + o_pos, cv.off - o_pos, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) { memcpy(horizon_pos, slab.h + o_pos, (size_t)(H + 1) * 3 * D); memcpy(horizon_quat, slab.h + o_quat, (size_t)(H + 1) * 4 * D); }
+  slab_release(slab, ctx->sel_cache_busy, from_cache);
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("horizon_imu: ") + cudaGetErrorString(e));
+  return BVIO_OK;
+}
+
 extern "C" int bvio_triangulate(bvio_ctx* ctx, const bvio_window* w, double init_depth, double* depth_out) {
   if (!ctx || !w || !depth_out) return fail(ctx, BVIO_ERR_INVALID, "null argument");
   if (w->K < 1 || w->L < 0 || !w->para_pose || !w->para_ex_pose) return fail(ctx, BVIO_ERR_INVALID, "null state arrays");

@@ -18,7 +18,7 @@ EXPORTS = [
     "bvio_batch_free", "bvio_batch_solve_timed", "bvio_stream", "bvio_launch_count", "bvio_marginalize", "bvio_select",
     "bvio_nccl_unique_id", "bvio_comm_init", "bvio_select_sharded", "bvio_select_upload", "bvio_select_run",
     "bvio_select_fetch", "bvio_select_free", "bvio_debug_linearize", "bvio_debug_build_delta", "bvio_triangulate",
-    "bvio_preintegrate",
+    "bvio_preintegrate", "bvio_horizon_imu",
 ]
 
 
@@ -63,6 +63,7 @@ def load():
     L.bvio_debug_linearize.argtypes = [vp, C.POINTER(abi.WindowS), C.POINTER(abi.Opts), dp, dp, dp, dp, dp]
     L.bvio_debug_build_delta.argtypes = [vp, C.POINTER(abi.SelectIn), dp, ip, dp]
     L.bvio_triangulate.argtypes = [vp, C.POINTER(abi.WindowS), C.c_double, dp]
+    L.bvio_horizon_imu.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, dp, i32, C.c_double, dp, dp]
     L.bvio_preintegrate.argtypes = [vp, C.POINTER(abi.ImuSegment), i32, C.c_double, C.c_double, C.c_double, C.c_double,
                                     C.POINTER(abi.Preint)]
     _lib = L

@@ -233,6 +233,15 @@ typedef struct {
   int32_t width, height;
 } bvio_camera;
 
+/* HorizonGenerator::imu (utility/horizon_generator.cpp:25-70), the step before select() in IMU-horizon mode: x_k and the
+ * IMU-propagated x_{k+1} open the horizon, then x_{k+1} is propagated nr_imu steps of delta_imu per future frame with the
+ * latest accelerometer / gyro sample held constant (bias ba0 of x_k, gravity (0,0,-9.80665), state_defs.h:37-41).
+ * Quaternions x y z w, not re-normalised (the reference multiplies by Utility::deltaQ's unnormalised increment).
+ * Fills horizon_pos[H+1][3] / horizon_quat[H+1][4] in the layout bvio_select_in takes. */
+int bvio_horizon_imu(bvio_ctx* ctx, int32_t H, const double pos0[3], const double quat0[4], const double ba0[3],
+                     const double pos1[3], const double quat1[4], const double vel1[3], const double acc[3],
+                     const double gyr[3], int32_t nr_imu, double delta_imu, double* horizon_pos, double* horizon_quat);
+
 /* Inputs of the numerical part of select(): everything
  * calcInfoFromRobotMotion / calcInfoFromFeatures / selectInformativeFeatures
  * read (feature_selector.cpp:239-728).  Horizon states are

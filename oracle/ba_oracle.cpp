@@ -1259,4 +1259,27 @@ int oracle_triangulate(const bvio_window* w, double init_depth, double* depth_ou
   return BVIO_OK;
 }
 
+
+// f3: HorizonGenerator::imu (utility/horizon_generator.cpp:25-70): constant-acceleration IMU propagation of x_{k+1}
+void oracle_horizon_imu(int H, const double pos0[3], const double quat0[4], const double ba0[3], const double pos1[3],
+                        const double quat1[4], const double vel1[3], const double acc[3], const double gyr[3], int nr_imu,
+                        double delta_imu, double* horizon_pos, double* horizon_quat) {
+  const V3 grav{0.0, 0.0, -9.80665};                         // state_defs.h:37-41
+  V3 Ba = v3(ba0), p = v3(pos1), v = v3(vel1), a = v3(acc), w = v3(gyr);
+  Q4 q = q4(quat1);
+  Q4 Qimu = deltaQ(delta_imu * w);                           // :43, not normalised
+  for (int i = 0; i < 3; i++) { horizon_pos[i] = pos0[i]; horizon_pos[3 + i] = pos1[i]; }
+  for (int i = 0; i < 4; i++) { horizon_quat[i] = quat0[i]; horizon_quat[4 + i] = quat1[i]; }
+  for (int h = 2; h <= H; h++) {
+    for (int i = 0; i < nr_imu; i++) {
+      q = qmul(q, Qimu);                                     // :52
+      V3 qa = qrot(q, a - Ba);
+      v = v + (grav + qa) * delta_imu;                       // :58
+      p = p + v * delta_imu + 0.5 * grav * delta_imu * delta_imu + 0.5 * qa * delta_imu * delta_imu;   // :61
+    }
+    horizon_pos[3 * h] = p.x; horizon_pos[3 * h + 1] = p.y; horizon_pos[3 * h + 2] = p.z;
+    horizon_quat[4 * h] = q.x; horizon_quat[4 * h + 1] = q.y; horizon_quat[4 * h + 2] = q.z; horizon_quat[4 * h + 3] = q.w;
+  }
+}
+
 }  // extern "C"

@@ -92,6 +92,11 @@ double oracle_logdet(const double* M, int n);
 /* f2: FeatureManager::triangulate (feature_manager.cpp:202-257): DLT depth of every landmark, depth_out[L] */
 int oracle_triangulate(const bvio_window* w, double init_depth, double* depth_out);
 
+/* f3: HorizonGenerator::imu (utility/horizon_generator.cpp:25-70) */
+void oracle_horizon_imu(int H, const double pos0[3], const double quat0[4], const double ba0[3], const double pos1[3],
+                        const double quat1[4], const double vel1[3], const double acc[3], const double gyr[3], int nr_imu,
+                        double delta_imu, double* horizon_pos, double* horizon_quat);
+
 #ifdef __cplusplus
 }
 #endif

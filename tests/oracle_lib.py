@@ -38,6 +38,8 @@ def load():
     L.oracle_optimize.argtypes = [C.POINTER(abi.WindowS), C.POINTER(abi.Opts), C.POINTER(abi.Summary)]
     L.oracle_double2vector.argtypes = [dp, i32, dp, dp]
     L.oracle_double2vector.restype = None
+    L.oracle_horizon_imu.argtypes = [i32, dp, dp, dp, dp, dp, dp, dp, dp, i32, d, dp, dp]
+    L.oracle_horizon_imu.restype = None
     L.oracle_triangulate.argtypes = [C.POINTER(abi.WindowS), d, dp]
     L.oracle_marginalize.argtypes = [C.POINTER(abi.WindowS), C.POINTER(abi.Opts), i32, C.POINTER(abi.PriorOut)]
     L.oracle_omega_imu.argtypes = [C.POINTER(abi.SelectIn), dp]
