@@ -278,6 +278,31 @@ def test_batch_equals_single(env):
         assert abs(s.final_cost - c) <= 1e-9 * c
 
 
+def test_pipelined_batch_equals_single(env):
+    """bvio_optimize_batch cuts batches of >= 4 windows per SM ... into pipelined sub-batches (own pinned slab, H2D on the
+    copy stream, trailing D2H): every window must come back in its own slot with the result of a single call."""
+    import torch
+    abi, synth, orc, ctx = env
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 4 * n_sm + 7                                   # two sub-batches of unequal size
+    pool = [synth.make_window(seed=40 + i, K=5, L=10 + (i % 5)) for i in range(9)]
+    o = abi.default_opts(max_iters=4)
+    singles = []
+    for w in pool:
+        h, s = abi.WindowHandle(w), abi.Summary()
+        ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(o), C.byref(s)), "optimize")
+        singles.append((h.state_vector().copy(), s.final_cost, s.iterations))
+    hs = [abi.WindowHandle(pool[(7 * i) % 9]) for i in range(B)]
+    arr = (abi.WindowS * B)(*[h.s for h in hs])
+    sums = (abi.Summary * B)()
+    ctx.check(ctx.L.bvio_optimize_batch(ctx.h, arr, B, C.byref(o), sums), "optimize_batch")
+    for i, (h, s) in enumerate(zip(hs, sums)):
+        x, c, it = singles[(7 * i) % 9]
+        assert s.iterations == it
+        assert np.linalg.norm(h.state_vector() - x) <= 1e-9 * np.linalg.norm(x), i
+        assert abs(s.final_cost - c) <= 1e-9 * c
+
+
 def test_resident_batch_is_deterministic(env):
     abi, synth, orc, ctx = env
     ws = [synth.make_window(seed=30 + i, K=11, L=150) for i in range(4)]
