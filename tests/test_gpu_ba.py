@@ -278,6 +278,45 @@ def test_batch_equals_single(env):
         assert abs(s.final_cost - c) <= 1e-9 * c
 
 
+def test_window_without_landmarks(env):
+    """L = 0: only IMU factors and the prior (the reference's problem right after a feature drought)."""
+    abi, synth, orc, ctx = env
+    for strategy in (0, 1):
+        w = synth.make_window(seed=1, K=6, L=0)
+        hg, ho, sg, so = _solve_both(env, w, dict(strategy=strategy))
+        assert (sg.iterations, sg.num_accepted, sg.termination) == (so.iterations, so.num_accepted, so.termination)
+        assert np.linalg.norm(hg.state_vector() - ho.state_vector()) <= 1e-8 * np.linalg.norm(ho.state_vector())
+
+
+def test_maximum_sizes(env):
+    """K = 15 keyframes with every landmark tracked through all of them (15 observations; the ABI allows 16)."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=2, K=15, L=40, track_min=15, track_max=15)
+    assert np.diff(w.lm_obs_offset).max() == 15
+    r = _linearize_both(env, w)
+    (S1, g1, h1, b1, c1), (S2, g2, h2, b2, c2) = r["gpu"], r["cpu"]
+    assert np.abs(S1 - S2).max() <= 1e-9 * np.abs(S2).max() and np.abs(g1 - g2).max() <= 1e-9 * np.abs(g2).max()
+    hg, ho, sg, so = _solve_both(env, w, {})
+    assert (sg.iterations, sg.num_accepted, sg.termination) == (so.iterations, so.num_accepted, so.termination)
+    assert np.linalg.norm(hg.state_vector() - ho.state_vector()) <= 1e-8 * np.linalg.norm(ho.state_vector())
+
+
+def test_ragged_batch(env):
+    """windows of one batch with very different landmark counts, including none"""
+    abi, synth, orc, ctx = env
+    ws = [synth.make_window(seed=60 + i, K=7, L=L) for i, L in enumerate((0, 3, 250, 1, 40, 0, 97))]
+    o = abi.default_opts(max_iters=5)
+    hs = [abi.WindowHandle(w) for w in ws]
+    arr = (abi.WindowS * len(ws))(*[h.s for h in hs])
+    sums = (abi.Summary * len(ws))()
+    ctx.check(ctx.L.bvio_optimize_batch(ctx.h, arr, len(ws), C.byref(o), sums), "optimize_batch")
+    for w, h, s in zip(ws, hs, sums):
+        ho, so = abi.WindowHandle(w), abi.Summary()
+        assert orc.oracle_optimize(C.byref(ho.s), C.byref(o), C.byref(so)) == 0
+        assert (s.iterations, s.num_accepted, s.termination) == (so.iterations, so.num_accepted, so.termination)
+        assert np.linalg.norm(h.state_vector() - ho.state_vector()) <= 1e-8 * np.linalg.norm(ho.state_vector())
+
+
 def test_pipelined_batch_equals_single(env):
     """bvio_optimize_batch cuts batches of >= 4 windows per SM ... into pipelined sub-batches (own pinned slab, H2D on the
     copy stream, trailing D2H): every window must come back in its own slot with the result of a single call."""
