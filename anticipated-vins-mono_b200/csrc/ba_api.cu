@@ -168,7 +168,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   int total_L = 0, total_obs = 0, nmax = 1, maxL = 0;
   {
     // structural validation walks every observation: spread large batches over host threads
-    const int nthreads = B < 16 ? 1 : (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 8);
+    const int nthreads = B < 16 ? 1 : (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
     std::vector<int> rcs(nthreads, BVIO_OK);
     std::vector<const char*> msgs(nthreads, "");
     auto work = [&](int t) {
@@ -363,7 +363,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
     }
   };
   {
-    int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 8);
+    int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
     if (B < 16) nthreads = 1;
     if (nthreads <= 1) {
       for (int b = 0; b < B; b++) pack(b);
@@ -492,7 +492,7 @@ static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, b
       if (bt.est_td) w.para_td[0] = tdo[b];
   };
   if (windows && bt.B >= 64) {
-    const int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 8);
+    const int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; t++) th.emplace_back([&, t]() { for (int b = t; b < bt.B; b += nthreads) scatter(b); });
     for (auto& x : th) x.join();

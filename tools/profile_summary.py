@@ -29,7 +29,7 @@ KEYS = [
 
 def kname(full):
     """'void ba_linearize_kernel<1>(BaBatch)' -> 'ba_linearize_kernel'"""
-    n = full.split("(")[0].strip()
+    n = full.replace("(anonymous namespace)::", "").split("(")[0].strip()
     if n.startswith("void "):
         n = n[5:]
     return n.split("<")[0].split("::")[-1]
