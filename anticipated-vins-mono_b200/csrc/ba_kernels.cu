@@ -1950,15 +1950,15 @@ constexpr int MF = 42;      // per-factor staging: A(12) B(12) E(12) c(2) r(2) t
 __device__ __forceinline__ void marg_col(const double* st, int fj, int K, int d, double& j0, double& j1) {
   j0 = 0; j1 = 0;
   if (d < 6) { j0 = st[d]; j1 = st[6 + d]; }
-  else if (d == 6 * K + 6) { j0 = st[40]; j1 = st[41]; }
-  else if (d >= 6 * K) { j0 = st[24 + d - 6 * K]; j1 = st[30 + d - 6 * K]; }
-  else if (d >= 6 * fj && d < 6 * fj + 6) { j0 = st[12 + d - 6 * fj]; j1 = st[18 + d - 6 * fj]; }
+  else if (d < 6 * K) { if (d >= 6 * fj && d < 6 * fj + 6) { j0 = st[12 + d - 6 * fj]; j1 = st[18 + d - 6 * fj]; } }
+  else if (d < 6 * K + 6) { j0 = st[24 + d - 6 * K]; j1 = st[30 + d - 6 * K]; }
+  else { j0 = st[40]; j1 = st[41]; }
 }
 
 __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch bt, MargArgs ma) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x, nt = blockDim.x, K = bt.K, M = ma.M, w = 0;
-  const int VD = 6 * K + 7;                 // visual layout dimension (frames, extrinsics, td)
+  const int VD = 6 * K + 6 + bt.est_td;     // visual layout dimension (frames, extrinsics, td when it is estimated)
   double* A = ma.A;
   double* bv = ma.b;
   for (int i = tid; i < M * M; i += nt) A[i] = 0.0;
