@@ -1,18 +1,23 @@
-// ba_kernels.cu -- sliding-window bundle adjustment on sm_100a (FP64, no tensor cores: the
-// blocks are 2x6 / 6x6 / 15x15 and irregular).  Replaces what ceres::Solve does for the problem
+// ba_kernels.cu -- sliding-window bundle adjustment on sm_100a, IEEE double throughout (the blocks are 2x6 / 6x6 /
+// 15x15 and irregular: no tcgen05 / TMEM; the one dense sub-problem, Gram products over a chunk's landmarks, runs on the
+// FP64 tensor-core path mma.sync.m8n8k4.f64).  Replaces what ceres::Solve does for the problem
 // Estimator::optimization() builds (vins_estimator/src/estimator.cpp:661-809):
 //
-//   ba_prepare    once per upload: IMU sqrt-information (imu_factor.h:64), prior J^T J
-//   ba_linearize  ProjectionFactor::Evaluate (projection_factor.cpp:21-121) + Cauchy corrector
-//                 (marginalization_factor.cpp:37-68) one warp per landmark (lane = factor), per-landmark
-//                 J^T J / J^T r reduction and Schur elimination of the inverse depth; one extra CTA per
-//                 window evaluates the IMU factors (imu_factor.h:19-179) and the marginalization prior
-//                 (marginalization_factor.cpp:333-381)
-//   ba_solve      one CTA per window: assemble the 15K x 15K reduced system in shared memory, LM damping
-//                 (Ceres LevenbergMarquardtStrategy), blocked Cholesky, back substitution
-//   ba_cost       back-substitute the inverse depths, PoseLocalParameterization::Plus
-//                 (pose_local_parameterization.cpp:3-18), residual-only cost at the candidate, and the
-//                 trust-region accept/reject decision (last CTA of the window)
+//   ba_prepare        once per upload: IMU sqrt-information (imu_factor.h:64), prior J^T J
+//   ba_linearize_mma  ProjectionFactor::Evaluate (projection_factor.cpp:21-121) + Cauchy corrector
+//                     (marginalization_factor.cpp:37-68), one factor per thread; per-landmark J^T J / J^T r and Schur
+//                     elimination of the inverse depth as DMMA Gram products; one extra CTA per window evaluates the IMU
+//                     factors (imu_factor.h:19-179) and the marginalization prior (marginalization_factor.cpp:333-381)
+//   ba_linearize<XB>  the same with free extrinsics and / or td (ProjectionTdFactor, projection_td_factor.cpp:34-141)
+//                     as pseudo-frames of the visual layout
+//   ba_solve          one CTA per window: assemble the reduced system in shared memory, LM damping (Ceres
+//                     LevenbergMarquardtStrategy) or the mu-regularised Gauss-Newton step of DoglegStrategy, blocked
+//                     Cholesky, back substitution
+//   ba_dogleg         traditional dogleg: landmark parts of the dot products, Gauss-Newton / Cauchy / interpolated step
+//   ba_cost           back-substitute the inverse depths, PoseLocalParameterization::Plus
+//                     (pose_local_parameterization.cpp:3-18), residual-only cost at the candidate, and the
+//                     trust-region accept / reject decision (last CTA of the window)
+//   ba_marginalize    MarginalizationInfo::{preMarginalize, marginalize} (marginalization_factor.cpp:109-297)
 //
 // All reductions run in a fixed order: results are bit-reproducible run to run.
 #include "ba.h"

@@ -1,7 +1,10 @@
 """Host-side restatement of the multi-GPU selector protocol (csrc/sel_api.cu, csrc/sel_kernels.cu):
 candidate partition, winner-record layout and the total order every rank applies to the gathered
 records.  Used by the world_size > 1 CPU tests (gloo) and by bench.py's bookkeeping; the product
-path itself runs these steps in CUDA + NCCL."""
+path itself runs these steps in CUDA.  Both device transports implement this same protocol: the fused
+one (records stored straight into every rank's mailbox over peer memory inside the persistent
+kernel; 32-byte header only, every rank holds all information blocks) and the NCCL one
+(ncclAllGather of header + packed block between sel_round_kernel and sel_apply_kernel)."""
 from __future__ import annotations
 
 import numpy as np
