@@ -190,7 +190,11 @@ int64_t bvio_launch_count(const bvio_ctx* ctx);
  * frame 0), flag 1 = MARGIN_SECOND_NEW (drop Pose[K-2]).  The window holds the
  * post-solve state.  Output blocks already carry the shifted frame indices
  * (addr_shift, estimator.cpp:904-916 / 962-984).  out->* point into
- * caller-provided storage sized by bvio_prior_capacity(). */
+ * caller-provided storage: cap_n >= 15*K + 7 and cap_blocks >= 2*K + 2 always suffice.
+ * With opts->estimate_td the dropped frame's factors are ProjectionTdFactors and para_Td is a kept block
+ * (estimator.cpp:863-871).  (J, r) come from the eigen-decomposition the reference uses
+ * (marginalization_factor.cpp:268-291); the environment variable BVIO_MARG_CHOLESKY=1 selects a pivoted Cholesky
+ * factor of the same quadratic form instead (about half the latency). */
 typedef struct {
   int32_t n, nblocks;
   int32_t* block_kind; int32_t* block_frame; int32_t* block_idx;
