@@ -137,3 +137,55 @@ def test_closed_loop_session_gpu_vs_oracle_on_identical_inputs(pkg, oracle):
     assert dual.n["triangulate"] >= 10, dual.n
     assert sim.prior["n"] == 75
     ctx.close()
+
+
+def test_slide_transfers_depth_to_the_new_anchor(pkg):
+    """FeatureManager::removeBackShiftDepth (feature_manager.cpp:275-311): when frame 0 is dropped, a landmark anchored
+    there keeps its 3-D position -- its depth is re-expressed in the camera of its next observation."""
+    sl, S = pkg.slider, pkg.synth
+    sim = sl.SlidingWindowSim(seed=1)
+    w = S.make_window(seed=3, K=sim.K, L=30, noise=False, perturb=False)
+    sim.pose, sim.sb = w.gt_pose.copy(), w.gt_speed_bias.copy()
+    sim.preint = [np.zeros(S.PREINT_DOUBLES) for _ in range(sim.K)]
+    world = {}
+    for l in range(w.L):
+        o0, o1 = int(w.lm_obs_offset[l]), int(w.lm_obs_offset[l + 1])
+        tr = sl.Track(lid=l, start=int(w.obs_frame[o0]), xy=[w.obs_xy[k].copy() for k in range(o0, o1)],
+                      depth=1.0 / w.gt_inv_depth[l])
+        sim.tracks[l] = tr
+        Rc, tc = sim._cam_pose(sim.pose[tr.start])
+        world[l] = Rc @ (np.array([tr.xy[0][0], tr.xy[0][1], 1.0]) * tr.depth) + tc
+    starts = {l: tr.start for l, tr in sim.tracks.items()}
+    nobs = {l: len(tr.xy) for l, tr in sim.tracks.items()}
+    pose_before = sim.pose.copy()
+    sim._slide()
+    assert len(sim.pose) == sim.K - 1 and np.array_equal(sim.pose, pose_before[1:])
+    moved = 0
+    for l, tr in sim.tracks.items():
+        if starts[l] == 0:
+            assert tr.start == 0 and len(tr.xy) == nobs[l] - 1
+            Rc, tc = sim._cam_pose(sim.pose[0])                      # the old frame 1
+            pw = Rc @ (np.array([tr.xy[0][0], tr.xy[0][1], 1.0]) * tr.depth) + tc
+            assert np.linalg.norm(pw - world[l]) < 1e-9 * max(1.0, np.linalg.norm(world[l]))
+            moved += 1
+        else:
+            assert tr.start == starts[l] - 1 and len(tr.xy) == nobs[l]
+    assert moved > 0
+    # landmarks seen only in frame 0 and one more frame lose their track (fewer than 2 observations left)
+    assert all(len(tr.xy) >= 2 for tr in sim.tracks.values())
+
+
+def test_regauge_uses_full_rotation_near_pitch_singularity(pkg):
+    """estimator.cpp:541-546: within 1 degree of +-90 deg pitch the yaw difference is meaningless; the reference
+    falls back to rot_diff = Rs[0] * R00^T."""
+    sl, S = pkg.slider, pkg.synth
+    R0 = S.euler_zyx(0.4, np.deg2rad(89.7), 0.1)
+    before = np.concatenate([[1.0, 2.0, 3.0], S.rot_to_quat(R0)])
+    Rg = S.euler_zyx(0.3, 0.02, -0.01)                 # an arbitrary rotation the solver drifted by
+    pose = np.zeros((2, 7))
+    pose[0, :3], pose[0, 3:] = [0.5, 0.5, 0.5], S.rot_to_quat(Rg @ R0)
+    pose[1, :3], pose[1, 3:] = [1.5, 0.5, 0.5], S.rot_to_quat(Rg @ R0 @ S.euler_zyx(0.1, 0, 0))
+    sb = np.zeros((2, 9))
+    sl.regauge(before, pose, sb)
+    assert np.allclose(S.quat_to_rot(pose[0, 3:]), R0, atol=1e-9) and np.allclose(pose[0, :3], [1, 2, 3])
+    assert np.allclose(pose[1, :3], np.array([1, 2, 3]) + Rg.T @ np.array([1.0, 0, 0]), atol=1e-9)
