@@ -18,11 +18,7 @@ constexpr int IMU_OUT = 496;          // per IMU factor: J^T J lower packed (465
 
 constexpr int PRIOR_MAXB = 32;    // max kept parameter blocks in a prior
 constexpr int BA_THREADS = 256;   // linearize / cost kernels
-#ifndef BVIO_SOLVE_THREADS
-#define BVIO_SOLVE_THREADS 256
-#endif
-constexpr int SOLVE_THREADS = BVIO_SOLVE_THREADS;          // ba_solve: 256 x 2 CTAs/SM measured faster than 512 x 1
-constexpr int SOLVE_CTAS_PER_SM = SOLVE_THREADS <= 256 ? 2 : 1;
+// ba_solve runs 256 threads x 2 CTAs per SM (throughput) or 512 x 1 (latency, BaBatch::solve_wide)
 
 struct BaCtrl {                   // per-window LM state, lives in HBM
   double cost;                    // cost at X[cur]
@@ -66,6 +62,7 @@ struct BaBatch {                  // all pointers are device pointers
   // solver options
   int max_iters, jacobi_scaling;
   int strategy;                   // BVIO_STRATEGY_LM / BVIO_STRATEGY_DOGLEG
+  int solve_wide;                 // fewer windows than SMs: ba_solve with 512 threads per window
   int use_mma;                    // linearize with the FP64 tensor-core (DMMA) kernel (extrinsics fixed)
   int est_ex;                     // estimate_extrinsic: +6 dims, extrinsic block = pseudo-frame K of the visual layout
   int est_td;                     // estimate_td: +1 dim (after the extrinsic block), pseudo-frame K + est_ex

@@ -195,6 +195,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   const int est_ex = o->estimate_extrinsic != 0, est_td = o->estimate_td != 0, XB = est_ex + est_td, KE = K + XB;
   bt.B = B; bt.K = K; bt.np = 15 * K + (est_ex ? 6 : 0) + est_td; bt.total_L = total_L; bt.total_obs = total_obs; bt.nmax = nmax;
   bt.est_ex = est_ex; bt.est_td = est_td;
+  bt.solve_wide = B < ctx->sm_count && !getenv("BVIO_SOLVE_NARROW");
   bt.use_mma = XB == 0 && !getenv("BVIO_LEGACY_LINEARIZE");
   bt.chunk_l = ba_pick_chunk(K, XB);
   int T = (maxL + 2 * bt.chunk_l - 1) / (2 * bt.chunk_l);   // >= 2 chunks per tile when there is a choice

@@ -1123,8 +1123,9 @@ size_t ba_linearize_mma_smem_bytes(int K) {
 // =============================================================================================
 // EX: the reduced system carries extra dimensions after the K 15-blocks (6 extrinsic and/or 1 td: np = 15K + 6 / + 1 /
 // + 7); the last Cholesky panel is then partial (the panel width is a compile-time 15 otherwise).
-template <bool EX>
-__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_CTAS_PER_SM) ba_solve_kernel(BaBatch bt, int with_step) {
+// NTHR: 256 threads x 2 CTAs per SM for throughput (large batches), 512 x 1 for latency (fewer windows than SMs).
+template <bool EX, int NTHR>
+__global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaBatch bt, int with_step) {
   extern __shared__ double sm[];
   const int w = blockIdx.x, K = bt.K, np = bt.np, KE = K + bt.est_ex + bt.est_td, K6 = 6 * KE, NPb = KE * (KE + 1) / 2;
   const int NB = (np + 14) / 15;                   // diagonal panels of the blocked Cholesky
@@ -1859,8 +1860,10 @@ int ba_configure(void) {
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_solve_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_solve_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_solve_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_solve_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
     g_tables_done = true;
   }
@@ -1906,8 +1909,14 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
   else BVIO_LIN(4)
 #undef BVIO_LIN
   if (ev) cudaEventRecord(ev[1], st);
-  if (XB) ba_solve_kernel<true><<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.np), st>>>(bt, with_step ? 1 : 0);
-  else ba_solve_kernel<false><<<bt.B, SOLVE_THREADS, ba_solve_smem_bytes(bt.np), st>>>(bt, with_step ? 1 : 0);
+  const size_t ssm = ba_solve_smem_bytes(bt.np);
+  if (bt.solve_wide) {
+    if (XB) ba_solve_kernel<true, 512><<<bt.B, 512, ssm, st>>>(bt, with_step ? 1 : 0);
+    else ba_solve_kernel<false, 512><<<bt.B, 512, ssm, st>>>(bt, with_step ? 1 : 0);
+  } else {
+    if (XB) ba_solve_kernel<true, 256><<<bt.B, 256, ssm, st>>>(bt, with_step ? 1 : 0);
+    else ba_solve_kernel<false, 256><<<bt.B, 256, ssm, st>>>(bt, with_step ? 1 : 0);
+  }
   if (!with_step || bt.undamped) { if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); } return 2; }
   int nk = 3;
   if (bt.strategy) {   // dogleg combination; its time is booked with the reduced solve
