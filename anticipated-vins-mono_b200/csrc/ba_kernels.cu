@@ -2383,22 +2383,26 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         pp[2 * tid] = p; pp[2 * tid + 1] = q; cs[2 * tid] = c; cs[2 * tid + 1] = s;
       }
       __syncthreads();
-      for (int e = tid; e < half * ne; e += nt) {      // columns of A and V
-        int pr = e / ne, k = e - pr * ne;
-        int p = pp[2 * pr], q = pp[2 * pr + 1];
-        double c = cs[2 * pr], s = cs[2 * pr + 1];
-        double akp = Ar[k * ld + p], akq = Ar[k * ld + q];
-        Ar[k * ld + p] = c * akp - s * akq; Ar[k * ld + q] = s * akp + c * akq;
-        double vkp = Vr[k * ld + p], vkq = Vr[k * ld + q];
-        Vr[k * ld + p] = c * vkp - s * vkq; Vr[k * ld + q] = s * vkp + c * vkq;
+      // A <- J^T A J in one phase: the 2x2 block of A at (pair I, pair J) only needs the two rotations, so every block has
+      // a single owner and is updated in place; V <- V J alongside (columns of V, one (pair, row) per thread)
+      for (int e = tid; e < half * half; e += nt) {
+        const int I = e / half, Jp = e - I * half;
+        const int p = pp[2 * I], q = pp[2 * I + 1], r = pp[2 * Jp], t2 = pp[2 * Jp + 1];
+        const double ci = cs[2 * I], si = cs[2 * I + 1], cj = cs[2 * Jp], sj = cs[2 * Jp + 1];
+        const double apr = Ar[p * ld + r], apt = Ar[p * ld + t2], aqr = Ar[q * ld + r], aqt = Ar[q * ld + t2];
+        // rows: [p'; q'] = [c -s; s c] [p; q]   (same convention as the two-pass version)
+        const double bpr = ci * apr - si * aqr, bpt = ci * apt - si * aqt;
+        const double bqr = si * apr + ci * aqr, bqt = si * apt + ci * aqt;
+        // columns: [r' t'] = [r t] [c s; -s c]
+        Ar[p * ld + r] = cj * bpr - sj * bpt; Ar[p * ld + t2] = sj * bpr + cj * bpt;
+        Ar[q * ld + r] = cj * bqr - sj * bqt; Ar[q * ld + t2] = sj * bqr + cj * bqt;
       }
-      __syncthreads();
-      for (int e = tid; e < half * ne; e += nt) {      // rows of A
+      for (int e = tid; e < half * ne; e += nt) {
         int pr = e / ne, k = e - pr * ne;
         int p = pp[2 * pr], q = pp[2 * pr + 1];
-        double c = cs[2 * pr], s = cs[2 * pr + 1];
-        double apk = Ar[p * ld + k], aqk = Ar[q * ld + k];
-        Ar[p * ld + k] = c * apk - s * aqk; Ar[q * ld + k] = s * apk + c * aqk;
+        double c = cs[2 * pr], s2 = cs[2 * pr + 1];
+        double vkp = Vr[k * ld + p], vkq = Vr[k * ld + q];
+        Vr[k * ld + p] = c * vkp - s2 * vkq; Vr[k * ld + q] = s2 * vkp + c * vkq;
       }
       __syncthreads();
     }
