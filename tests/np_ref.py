@@ -264,6 +264,128 @@ def solve_gn(w, iters=60, tol=1e-13, **kw):
     return w, cost, np.max(np.abs(J.T @ r))
 
 
+def solve_trust_region(w, strategy=0, max_iters=8, initial_radius=1e4, function_tolerance=1e-6,
+                       gradient_tolerance=1e-10, parameter_tolerance=1e-8, min_relative_decrease=1e-3, **kw):
+    """Ceres' trust-region loop on the DENSE, unreduced normal equations [poses | depths] -- no Schur elimination,
+    numpy's solver -- with Jacobi scaling fixed at the first linearization: LevenbergMarquardtStrategy (strategy 0)
+    or DoglegStrategy / TRADITIONAL_DOGLEG (strategy 1).  Second opinion on the oracle's Schur-based loop: the two
+    must take the same accept / reject path and produce the same iterates.  Returns (window, trace, termination)
+    with trace = [(cost, candidate cost, accepted, radius after)] per iteration."""
+    J, r, cost = full_system(w, **kw)
+    H, g = J.T @ J, J.T @ r
+    scale = 1.0 / (1.0 + np.sqrt(np.diag(H)))
+    radius, decrease, mu, invalid_run = initial_radius, 2.0, 1e-8, 0
+    trace, term, reuse = [], 0, False
+    gn = gr = Dd = None
+    alpha = step_norm = 0.0
+    if np.abs(g).max() <= gradient_tolerance:
+        return w, trace, 2
+    it = 0
+    while it < max_iters:
+        it += 1
+        cl = np.clip(scale * scale * np.diag(H), 1e-6, 1e32)
+        valid = True
+        if strategy == 0:
+            dd = cl / (radius * scale * scale)
+            try:
+                np.linalg.cholesky(H + np.diag(dd))
+                d = -np.linalg.solve(H + np.diag(dd), g)
+            except np.linalg.LinAlgError:
+                valid = False
+        else:
+            if not reuse:
+                Dd = np.sqrt(cl)
+                gr = scale * g / Dd                                  # gradient in the scaled y space
+                t = scale * gr / Dd
+                alpha = (gr @ gr) / (t @ H @ t)
+                while True:
+                    dd = mu * Dd * Dd / (scale * scale)
+                    try:
+                        np.linalg.cholesky(H + np.diag(dd))
+                        dgn = -np.linalg.solve(H + np.diag(dd), g)
+                        break
+                    except np.linalg.LinAlgError:
+                        mu *= 10.0
+                        if mu > 1.0:
+                            valid = False
+                            break
+                if valid:
+                    gn = Dd * dgn / scale
+                reuse = True
+            if valid:
+                gn_norm, g_norm = np.linalg.norm(gn), np.linalg.norm(gr)
+                if gn_norm <= radius:
+                    ca, cb, step_norm = 0.0, 1.0, gn_norm
+                elif g_norm * alpha >= radius:
+                    ca, cb, step_norm = -(radius / g_norm), 0.0, radius
+                else:
+                    b_dot_a = -alpha * (gr @ gn)
+                    a_sq = alpha * alpha * g_norm * g_norm
+                    bma_sq = a_sq - 2 * b_dot_a + gn_norm * gn_norm
+                    c = b_dot_a - a_sq
+                    dq = np.sqrt(c * c + bma_sq * (radius * radius - a_sq))
+                    beta = (dq - c) / bma_sq if c <= 0 else (radius * radius - a_sq) / (dq + c)
+                    ca, cb = -alpha * (1.0 - beta), beta
+                    step_norm = np.linalg.norm(ca * gr + cb * gn)
+                d = scale * (ca * gr + cb * gn) / Dd
+        model = 0.0
+        if valid:
+            model = -(g @ d) - 0.5 * (d @ H @ d)
+            valid = model > 0
+        if not valid:
+            invalid_run += 1
+            trace.append((cost, None, False, radius))
+            if invalid_run >= 5:
+                term = 4
+                break
+            if strategy == 0:
+                radius /= decrease
+                decrease *= 2
+            else:
+                mu *= 10.0
+                reuse = False
+            continue
+        invalid_run = 0
+        cand = apply_delta(w, d)
+        Jc, rc, cc = full_system(cand, **kw)
+        x = np.concatenate([w.para_pose.ravel(), w.para_speed_bias.ravel(), w.inv_depth])
+        xc = np.concatenate([cand.para_pose.ravel(), cand.para_speed_bias.ravel(), cand.inv_depth])
+        if np.linalg.norm(x - xc) <= parameter_tolerance * (np.linalg.norm(x) + parameter_tolerance):
+            term = 3
+            break
+        if abs(cost - cc) <= function_tolerance * cost:
+            term = 1
+            break
+        rho = (cost - cc) / model
+        if np.isfinite(cc) and rho > min_relative_decrease:
+            w, J, r, cost_prev, cost = cand, Jc, rc, cost, cc
+            H, g = J.T @ J, J.T @ r
+            if strategy == 0:
+                tt = 2.0 * rho - 1.0
+                radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - tt ** 3))
+                decrease = 2.0
+            else:
+                if rho < 0.25:
+                    radius *= 0.5
+                if rho > 0.75:
+                    radius = max(radius, 3.0 * step_norm)
+                mu = max(1e-8, 2.0 * mu / 10.0)
+                reuse = False
+            trace.append((cost_prev, cc, True, radius))
+            if np.abs(g).max() <= gradient_tolerance:
+                term = 2
+                break
+        else:
+            if strategy == 0:
+                radius /= decrease
+                decrease *= 2
+            else:
+                radius *= 0.5
+                reuse = True
+            trace.append((cost, cc, False, radius))
+    return w, trace, term
+
+
 # ---------------------------------------------------------------------------
 # selector
 # ---------------------------------------------------------------------------

@@ -224,6 +224,26 @@ def test_lm_dogleg_and_dense_gn_reach_same_fixed_point(mods, seed, K, L):
     assert abs(s_lm.final_cost - cost_gn) <= 1e-6 * cost_gn
 
 
+@pytest.mark.parametrize("seed,K,L,strategy,radius,iters", [(7, 6, 30, 0, 1e4, 8), (8, 6, 30, 1, 1e4, 8), (9, 5, 25, 1, 1.0, 20),
+                                                            (10, 5, 25, 1, 0.05, 25), (11, 11, 40, 0, 1e4, 8), (12, 5, 25, 0, 1e-2, 15)])
+def test_trust_region_trajectory_matches_dense_numpy(mods, seed, K, L, strategy, radius, iters):
+    """The oracle's Schur-eliminated LM / dogleg loop against the same Ceres logic run on the DENSE unreduced system in
+    numpy (tests/np_ref.solve_trust_region): same number of iterations, same accept / reject path, same final radius,
+    cost and state.  Small radii force the Cauchy-point and interpolated dogleg branches."""
+    abi, synth, orc = mods
+    w = synth.make_window(seed=seed, K=K, L=L)
+    h, s = _solve(orc, abi, w, strategy=strategy, initial_radius=radius, max_iters=iters)
+    wn, trace, term = np_ref.solve_trust_region(w, strategy=strategy, initial_radius=radius, max_iters=iters)
+    assert len(trace) == s.iterations or (term in (1, 3) and len(trace) + 1 == s.iterations), (len(trace), s.as_dict())
+    assert sum(t[2] for t in trace) == s.num_accepted and term == s.termination
+    assert abs(trace[-1][3] - s.final_radius) <= 1e-6 * s.final_radius
+    final_cost = trace[-1][1] if trace[-1][2] else trace[-1][0]
+    assert abs(final_cost - s.final_cost) <= 1e-8 * s.final_cost
+    xo = h.state_vector()
+    xn = np.concatenate([wn.para_pose.ravel(), wn.para_speed_bias.ravel(), wn.para_ex_pose, wn.inv_depth])
+    assert np.linalg.norm(xo - xn) <= 1e-7 * np.linalg.norm(xn)
+
+
 def test_reference_defaults_terminate_like_ceres(mods):
     """8 iterations / default tolerances (config/euroc/euroc_config.yaml:54-55)."""
     abi, synth, orc = mods
