@@ -166,6 +166,85 @@ def prior_residual(prior, w):
     return prior["lin_res"] + Jm @ dx, dx, Jm
 
 
+def projection_td(pts_i, pts_j, vel_i, vel_j, td_i, td_j, row_i, row_j, TR, ROW, pose_i, pose_j, ex, inv_dep, td,
+                  sqrt_info=460.0 / 1.5):
+    """ProjectionTdFactor::Evaluate (projection_td_factor.cpp:34-141): the projection chain on the time-shifted
+    points, plus the 2x1 Jacobian w.r.t. td."""
+    si = td - td_i + TR / ROW * (row_i - ROW / 2)
+    sj = td - td_j + TR / ROW * (row_j - ROW / 2)
+    pi_td = np.asarray(pts_i[:2]) - si * np.asarray(vel_i)
+    pj_td = np.asarray(pts_j[:2]) - sj * np.asarray(vel_j)
+    r, Ji, Jj, Jex, Jf = projection(pi_td, pj_td, pose_i, pose_j, ex, inv_dep, sqrt_info)
+    Ri, Rj, ric = R_of(pose_i[3:]), R_of(pose_j[3:]), R_of(ex[3:])
+    pcj = ric.T @ (Rj.T @ (Ri @ (ric @ (np.array([pi_td[0], pi_td[1], 1.0]) / inv_dep) + ex[:3]) + pose_i[:3] - pose_j[:3]) - ex[:3])
+    dep = pcj[2]
+    red = sqrt_info * np.array([[1 / dep, 0, -pcj[0] / dep ** 2], [0, 1 / dep, -pcj[1] / dep ** 2]])
+    Jtd = red @ (ric.T @ Rj.T @ Ri @ ric @ np.array([vel_i[0], vel_i[1], 0.0])) / inv_dep * -1.0 + sqrt_info * np.asarray(vel_j)
+    return r, Ji, Jj, Jex, Jf, Jtd
+
+
+def full_system_ext(w, est_ex=False, est_td=False, TR=0.0, ROW=480.0, G=(0, 0, 9.81007), sqrt_info=460.0 / 1.5, cauchy_a=1.0):
+    """full_system with the extrinsic pose and / or td as free parameters: columns [15K | 6 ex | 1 td | L]."""
+    K, L = w.K, len(w.inv_depth)
+    n_ex, n_td = (6 if est_ex else 0), (1 if est_td else 0)
+    o_ex, o_td = 15 * K, 15 * K + n_ex
+    npar = o_td + n_td
+    J0, r0, cost = full_system(w, G=G, sqrt_info=sqrt_info, cauchy_a=cauchy_a) if not est_td else (None, None, None)
+    rows, res = [], []
+    cost_v = 0.0
+    for l in range(L):
+        o0, o1 = w.lm_obs_offset[l], w.lm_obs_offset[l + 1]
+        fi = w.obs_frame[o0]
+        for k in range(o0 + 1, o1):
+            fj = w.obs_frame[k]
+            if est_td:
+                r, Ji, Jj, Jex, Jf, Jtd = projection_td(w.obs_xy[o0], w.obs_xy[k], w.obs_vel[o0], w.obs_vel[k], w.obs_td[o0],
+                                                        w.obs_td[k], w.obs_row[o0], w.obs_row[k], TR, ROW, w.para_pose[fi],
+                                                        w.para_pose[fj], w.para_ex_pose, w.inv_depth[l], w.para_td[0], sqrt_info)
+            else:
+                r, Ji, Jj, Jex, Jf = projection(w.obs_xy[o0], w.obs_xy[k], w.para_pose[fi], w.para_pose[fj], w.para_ex_pose,
+                                                w.inv_depth[l], sqrt_info)
+            sq = r @ r
+            cost_v += 0.5 * cauchy_a ** 2 * np.log1p(sq / cauchy_a ** 2)
+            sr = np.sqrt(1.0 / (1.0 + sq / cauchy_a ** 2))
+            blk = np.zeros((2, npar + L))
+            blk[:, 15 * fi:15 * fi + 6] += sr * Ji
+            blk[:, 15 * fj:15 * fj + 6] += sr * Jj
+            if est_ex:
+                blk[:, o_ex:o_ex + 6] = sr * Jex
+            if est_td:
+                blk[:, o_td] = sr * Jtd
+            blk[:, npar + l] = sr * Jf
+            rows.append(blk)
+            res.append(sr * r)
+    # IMU and prior rows: reuse the fixed-extrinsic builder on a window without landmarks, widened to the new layout
+    import dataclasses
+    bare = dataclasses.replace(w, inv_depth=np.zeros(0), lm_obs_offset=np.zeros(1, np.int32), obs_frame=np.zeros(0, np.int32),
+                               obs_xy=np.zeros((0, 2)))
+    Jb, rb, cb = full_system(bare, G=G, sqrt_info=sqrt_info, cauchy_a=cauchy_a)
+    wide = np.zeros((Jb.shape[0], npar + L))
+    wide[:, :15 * K] = Jb
+    if w.prior is not None:      # prior columns on the extrinsic / td blocks
+        rp, dx, Jm = prior_residual(w.prior, w)
+        n = w.prior["n"]
+        for kind, frame, idx in zip(w.prior["block_kind"], w.prior["block_frame"], w.prior["block_idx"]):
+            if kind == 2 and est_ex:
+                wide[-n:, o_ex:o_ex + 6] = Jm[:, idx:idx + 6]
+            if kind == 3 and est_td:
+                wide[-n:, o_td] = Jm[:, idx]
+    rows.append(wide)
+    res.append(rb)
+    return np.vstack(rows), np.concatenate(res), cost_v + cb
+
+
+def reduced_system_ext(w, **kw):
+    J, r, cost = full_system_ext(w, **kw)
+    npar = J.shape[1] - len(w.inv_depth)
+    Hf, gf = J.T @ J, J.T @ r
+    Hpp, Hpl, hl = Hf[:npar, :npar], Hf[:npar, npar:], np.diag(Hf[npar:, npar:])
+    return Hpp - (Hpl / hl) @ Hpl.T, gf[:npar] - (Hpl / hl) @ gf[npar:], hl, gf[npar:], cost
+
+
 def full_system(w, G=(0, 0, 9.81007), sqrt_info=460.0 / 1.5, cauchy_a=1.0):
     """Dense weighted Jacobian/residual of the whole window in local coordinates
     [15*K pose/speed-bias | L inverse depths]; extrinsics fixed.  Returns J, r, cost."""

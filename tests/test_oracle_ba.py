@@ -191,6 +191,32 @@ def test_linearize_vs_numpy(mods, seed, K, L):
     assert abs(orc.oracle_cost(C.byref(h.s), C.byref(o)) - cost.value) <= 1e-12 * cost.value
 
 
+@pytest.mark.parametrize("seed,K,L,ex,td", [(0, 5, 30, 1, 0), (1, 5, 30, 0, 1), (2, 11, 40, 1, 1), (3, 2, 20, 1, 1)])
+def test_linearize_with_free_extrinsics_and_td_vs_numpy(mods, seed, K, L, ex, td):
+    """Reduced system with para_Ex_Pose and / or para_Td free (estimator.cpp:672-683, 732-740): the oracle's block
+    assembly + Schur elimination against the dense numpy system with the extra columns."""
+    abi, synth, orc = mods
+    kw = dict(track_min=2, track_max=2) if K == 2 else {}
+    w = synth.make_window(seed=seed, K=K, L=L, td_true=0.004, **kw)
+    w.para_td[0] = 0.001
+    rng = np.random.default_rng(seed)
+    w.para_ex_pose[:3] += rng.normal(0, 0.02, 3)
+    h = abi.WindowHandle(w)
+    o = abi.default_opts(estimate_extrinsic=ex, estimate_td=td, TR=0.02)
+    npar = 15 * K + 6 * ex + td
+    S, g, hh, bb = np.zeros(npar * npar), np.zeros(npar), np.zeros(L), np.zeros(L)
+    cost = C.c_double()
+    assert orc.oracle_linearize(C.byref(h.s), C.byref(o), abi.dptr(S), abi.dptr(g), abi.dptr(hh), abi.dptr(bb),
+                                C.cast(C.byref(cost), abi.c_double_p)) == 0
+    S2, g2, h2, b2, cost2 = np_ref.reduced_system_ext(w, est_ex=bool(ex), est_td=bool(td), TR=0.02)
+    S = S.reshape(npar, npar)
+    assert abs(cost.value - cost2) <= 1e-7 * cost2
+    assert np.allclose(hh, h2, rtol=1e-10) and np.allclose(bb, b2, rtol=1e-9, atol=1e-9 * np.abs(b2).max())
+    assert np.allclose(S, S2, rtol=1e-6, atol=1e-6 * np.abs(S2).max())
+    assert np.allclose(g, g2, rtol=1e-6, atol=1e-6 * np.abs(g2).max())
+    assert np.abs(S2[15 * K:, :]).max() > 0
+
+
 def _solve(orc, abi, w, **kw):
     h = abi.WindowHandle(w)
     o = abi.default_opts(**kw)
