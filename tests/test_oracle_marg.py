@@ -126,6 +126,59 @@ def test_prior_chain_and_second_new(pkg, oracle):
     assert run_marg(abi, oracle.oracle_marginalize, w, 1) is None
 
 
+@pytest.mark.parametrize("seed,K,L", [(0, 8, 60), (4, 11, 120)])
+def test_margin_old_with_td_matches_numpy_schur(pkg, oracle, seed, K, L):
+    """MARGIN_OLD with ESTIMATE_TD (estimator.cpp:863-871): ProjectionTdFactor blocks in the marginalized set; the kept
+    prior spans poses, speed/bias, the extrinsic AND para_Td.  Checked against the Schur complement of the dense numpy
+    system with the extrinsic and td columns."""
+    abi, synth = pkg.abi, pkg.synth
+    w = synth.make_window(seed=seed, K=K, L=L, td_true=0.003)
+    w.para_td[0] = 0.001
+    TR = 0.015
+    p = run_marg(abi, oracle.oracle_marginalize, w, 0, opts=abi.default_opts(estimate_td=1, TR=TR))
+    assert p["block_kind"][-1] == 3
+    itd = int(p["block_idx"][-1])
+    # scatter to [15K | 6 | 1]
+    M = 15 * K + 7
+    cols = np.full(p["n"], -1)
+    for kind, frame, idx in zip(p["block_kind"], p["block_frame"], p["block_idx"]):
+        if kind == 0:
+            cols[idx:idx + 6] = 15 * (frame + 1) + np.arange(6)
+        elif kind == 1:
+            cols[idx:idx + 9] = 15 * (frame + 1) + 6 + np.arange(9)
+        elif kind == 2:
+            cols[idx:idx + 6] = 15 * K + np.arange(6)
+        else:
+            cols[idx] = 15 * K + 6
+    H, g = np.zeros((M, M)), np.zeros(M)
+    H[np.ix_(cols, cols)] = p["J"].T @ p["J"]
+    g[cols] = p["J"].T @ p["lin_res"]
+    # numpy: the MARGIN_OLD factor subset with free extrinsic and td
+    keep = [l for l in range(w.L) if w.obs_frame[w.lm_obs_offset[l]] == 0]
+    sel = np.concatenate([np.arange(w.lm_obs_offset[l], w.lm_obs_offset[l + 1]) for l in keep])
+    offs = np.concatenate([[0], np.cumsum([w.lm_obs_offset[l + 1] - w.lm_obs_offset[l] for l in keep])]).astype(np.int32)
+    pre = w.preint.copy()
+    pre[2:, 16] = 11.0
+    sub = dataclasses.replace(w, inv_depth=w.inv_depth[keep], lm_obs_offset=offs, obs_frame=w.obs_frame[sel],
+                              obs_xy=w.obs_xy[sel], obs_vel=w.obs_vel[sel], obs_td=w.obs_td[sel], obs_row=w.obs_row[sel],
+                              preint=pre)
+    Jd, rd, _ = np_ref.full_system_ext(sub, est_ex=True, est_td=True, TR=TR)
+    Hd, gd = Jd.T @ Jd, Jd.T @ rd
+    dropped = np.r_[np.arange(15), M + np.arange(len(keep))]
+    rest = np.setdiff1d(np.arange(M), np.arange(15))
+    Hmm = 0.5 * (Hd[np.ix_(dropped, dropped)] + Hd[np.ix_(dropped, dropped)].T)
+    wv, V = np.linalg.eigh(Hmm)
+    inv = V @ np.diag(np.where(wv > 1e-8, 1.0 / np.where(wv > 1e-8, wv, 1.0), 0.0)) @ V.T
+    Hs = Hd[np.ix_(rest, rest)] - Hd[np.ix_(rest, dropped)] @ inv @ Hd[np.ix_(dropped, rest)]
+    gs = gd[rest] - Hd[np.ix_(rest, dropped)] @ inv @ gd[dropped]
+    sc = np.abs(Hs).max()
+    assert np.abs(H[np.ix_(rest, rest)] - Hs).max() <= 1e-7 * sc
+    assert np.abs(g[rest] - gs).max() <= 5e-5 * max(np.abs(gs).max(), 1.0)
+    assert Hs[-1, -1] > 0 and abs(H[M - 1, M - 1] - Hs[-1, -1]) <= 1e-7 * sc       # information on td itself
+    assert p["x0"][sum(7 if k == 0 else 9 if k == 1 else 7 for k in p["block_kind"][:-1])] == w.para_td[0]
+    assert itd == p["n"] - 1
+
+
 def test_td_marginalization_plumbing(pkg, oracle):
     """ESTIMATE_TD (estimator.cpp:863-871): para_Td is a kept block of the new prior.  With zero feature velocities the
     td factor is the plain projection factor and carries no information on td: same prior on every other block, one
