@@ -11,11 +11,14 @@ C-ABI without ROS:
   * the filter that decides which features become parameter blocks (used_num >= 2 && start_frame < WINDOW_SIZE - 2,
     estimator.cpp:712-718, feature_manager.cpp:28-43);
   * Estimator::double2vector's yaw / position gauge re-anchoring (estimator.cpp:521-555);
-  * Estimator::slideWindow, MARGIN_OLD branch (estimator.cpp:996-1060);
+  * Estimator::slideWindow, both branches (estimator.cpp:996-1078): MARGIN_OLD with removeBackShiftDepth, and
+    MARGIN_SECOND_NEW (the second-newest frame is not a keyframe: its IMU samples are appended to the previous
+    preintegration, the newest frame takes its slot, FeatureManager::removeFront, feature_manager.cpp:330-351);
   * the new-feature budget of FeatureSelector::select (feature_selector.cpp:157-170): kappa = maxFeatures - tracked.
 
 The arithmetic of optimize / marginalize / select is NOT here: it is delegated to a backend (the CUDA library in the
-product; the CPU oracle only in tests).  Every frame is treated as a keyframe (MARGIN_OLD).  Pure numpy.
+product; the CPU oracle only in tests).  `keyframes="always"` treats every frame as a keyframe (MARGIN_OLD, the
+stream benchmark's setting); `keyframes="parallax"` applies the reference's addFeatureCheckParallax rule.  Pure numpy.
 """
 from __future__ import annotations
 
@@ -28,6 +31,8 @@ from . import synth as S
 
 WINDOW_SIZE = 10           # parameters.h:15 ; K = WINDOW_SIZE + 1 frames in the window
 INIT_DEPTH = 5.0           # parameters.cpp:3
+MIN_PARALLAX = 10.0 / S.FOCAL_LENGTH   # keyframe_parallax 10 px (config/euroc/euroc_config.yaml) / FOCAL_LENGTH, parameters.cpp:88
+MARGIN_OLD, MARGIN_SECOND_NEW = 0, 1
 
 
 @dataclasses.dataclass
@@ -125,14 +130,18 @@ class SlidingWindowSim:
     wall time of each backend call."""
 
     def __init__(self, seed=0, max_feats=150, max_cand=300, H=10, frame_dt=0.1, imu_rate=200, px_sigma=0.5,
-                 opts=None):
+                 opts=None, keyframes="always", speed=1.0):
         self.rng = np.random.default_rng(seed)
         self.K = WINDOW_SIZE + 1
         self.cam = S.EUROC_CAM
         U_, _, Vt_ = np.linalg.svd(S.EUROC_RIC)
         self.ric, self.tic = U_ @ Vt_, S.EUROC_TIC.copy()
         self.qic = S.rot_to_quat(self.ric)
-        self.traj = S.Trajectory(phase=self.rng.uniform(0, 10.0), scale=1.0)
+        self.traj = S.Trajectory(phase=self.rng.uniform(0, 10.0), scale=speed)
+        assert keyframes in ("always", "parallax")
+        self.keyframes = keyframes
+        self.margin_flag = MARGIN_OLD
+        self.sum_of_back = self.sum_of_front = 0       # estimator.h:89 counters
         self.world = World(self.rng)
         self.max_feats, self.max_cand, self.H = max_feats, max_cand, H
         self.frame_dt, self.n_imu = frame_dt, int(round(frame_dt * imu_rate))
@@ -147,6 +156,8 @@ class SlidingWindowSim:
         self.pose = np.zeros((0, 7))
         self.sb = np.zeros((0, 9))
         self.preint = [np.zeros(S.PREINT_DOUBLES)]
+        self.pre_obj = [None]                          # the live IntegrationBase of every interval ...
+        self.imu_buf = [[]]                            # ... and its samples (dt_buf / *_buf, estimator.h:79-81)
         self.tracks: dict[int, Track] = {}
         self.prior = None
         self.last_selected = np.zeros(0, np.int32)
@@ -182,9 +193,11 @@ class SlidingWindowSim:
             ba, bg = self.sb[-1, 3:6].copy(), self.sb[-1, 6:9].copy()
             a0, g0 = self._imu(t0)
             pre = S.Preintegration(a0, g0, ba, bg)
+            buf = []
             for i in range(1, self.n_imu + 1):
                 a1, g1 = self._imu(t0 + i * dt)
                 pre.push_back(dt, a1, g1)
+                buf.append((dt, a1, g1))
             self.t = t0 + self.frame_dt
             Ri, Pi, Vi, T = _R(self.pose[-1, 3:]), self.pose[-1, :3], self.sb[-1, :3], pre.sum_dt
             Pj = Pi + Vi * T - 0.5 * self.g * T * T + Ri @ pre.delta_p
@@ -201,6 +214,8 @@ class SlidingWindowSim:
             self.pose = np.vstack([self.pose, np.concatenate([Pj, qj])])
             self.sb = np.vstack([self.sb, np.concatenate([Vj, ba, bg])])
             self.preint.append(S.pack_preint(pre))
+            self.pre_obj.append(pre)
+            self.imu_buf.append(buf)
         self.frame += 1
         # tracking against the true camera pose of the new frame
         gp, _ = self._gt(self.t)
@@ -218,11 +233,27 @@ class SlidingWindowSim:
             else:
                 tr.xy.append(xy[k] + self.rng.normal(0, self.sig, 2))
                 n_tracked += 1
+        self.margin_flag = self._keyframe_decision(new_idx, n_tracked)
         cand = [i for i in ids.tolist() if i not in self.tracks]
         if len(cand) > self.max_cand:
             cand = sorted(self.rng.choice(cand, self.max_cand, replace=False).tolist())
         cxy = np.array([xy[vis[i]] for i in cand]).reshape(-1, 2)
         return new_idx, n_tracked, np.array(cand, np.int32), cxy
+
+    def _keyframe_decision(self, frame_count, last_track_num):
+        """FeatureManager::addFeatureCheckParallax (feature_manager.cpp:46-97): the second-newest frame is a keyframe
+        (MARGIN_OLD) when tracking is weak or when the mean parallax between the third-newest and second-newest
+        frames (compensatedParallax2, :353-385: no rotation compensation) reaches MIN_PARALLAX."""
+        if self.keyframes == "always" or frame_count < 2 or last_track_num < 20:
+            return MARGIN_OLD
+        par = []
+        for tr in self.tracks.values():
+            if tr.start <= frame_count - 2 and tr.start + len(tr.xy) - 1 >= frame_count - 1:
+                a, b = tr.xy[frame_count - 2 - tr.start], tr.xy[frame_count - 1 - tr.start]
+                par.append(np.hypot(a[0] - b[0], a[1] - b[1]))
+        if not par:
+            return MARGIN_OLD
+        return MARGIN_OLD if sum(par) / len(par) >= MIN_PARALLAX else MARGIN_SECOND_NEW
 
     def _start_tracks(self, new_idx, ids, cand, cxy):
         pos = {int(c): k for k, c in enumerate(cand)}
@@ -300,6 +331,9 @@ class SlidingWindowSim:
         R1c, P1c = self._cam_pose(self.pose[1])
         self.pose, self.sb = self.pose[1:].copy(), self.sb[1:].copy()
         self.preint = [np.zeros(S.PREINT_DOUBLES)] + self.preint[2:]
+        self.pre_obj = [None] + self.pre_obj[2:]
+        self.imu_buf = [[]] + self.imu_buf[2:]
+        self.sum_of_back += 1
         dead = []
         for lid, tr in self.tracks.items():
             if tr.start != 0:
@@ -313,6 +347,31 @@ class SlidingWindowSim:
                 pw = R0c @ (np.array([uv[0], uv[1], 1.0]) * tr.depth) + P0c
                 dj = (R1c.T @ (pw - P1c))[2]
                 tr.depth = dj if dj > 0 else INIT_DEPTH
+        for lid in dead:
+            del self.tracks[lid]
+
+    def _slide_new(self):
+        """Estimator::slideWindow MARGIN_SECOND_NEW (estimator.cpp:1042-1076) + FeatureManager::removeFront."""
+        fc = self.K - 1
+        pre = self.pre_obj[fc - 1]
+        for dt, a, g in self.imu_buf[fc]:
+            pre.push_back(dt, a, g)
+        self.imu_buf[fc - 1] = self.imu_buf[fc - 1] + self.imu_buf[fc]
+        self.preint[fc - 1] = S.pack_preint(pre)
+        self.preint, self.pre_obj, self.imu_buf = self.preint[:fc], self.pre_obj[:fc], self.imu_buf[:fc]
+        self.pose[fc - 1], self.sb[fc - 1] = self.pose[fc], self.sb[fc]
+        self.pose, self.sb = self.pose[:fc].copy(), self.sb[:fc].copy()
+        self.sum_of_front += 1
+        dead = []
+        for lid, tr in self.tracks.items():
+            if tr.start == fc:
+                tr.start -= 1
+                continue
+            if tr.start + len(tr.xy) - 1 < fc - 1:
+                continue
+            del tr.xy[WINDOW_SIZE - 1 - tr.start]
+            if not tr.xy:
+                dead.append(lid)
         for lid in dead:
             del self.tracks[lid]
 
@@ -336,10 +395,18 @@ class SlidingWindowSim:
             wpost = dataclasses.replace(w, para_pose=self.pose.copy(), para_speed_bias=self.sb.copy(),
                                         inv_depth=wsol.inv_depth.copy())
             t2 = time.perf_counter()
-            self.prior = backend.marginalize(wpost, 0)
+            c_marg = 0.0
+            if self.margin_flag == MARGIN_OLD:
+                self.prior = backend.marginalize(wpost, MARGIN_OLD)
+                c_marg = getattr(backend, "t_call", 0.0)
+            elif self.prior is not None:                        # estimator.cpp:926: only if there is a prior; it is
+                p = backend.marginalize(wpost, MARGIN_SECOND_NEW)   # replaced only if it involves Pose[WINDOW_SIZE-1]
+                c_marg = getattr(backend, "t_call", 0.0)
+                if p is not None:
+                    self.prior = p
             t3 = time.perf_counter()
-            lat = {"optimize": t1 - t0, "marginalize": t3 - t2, "optimize_call": c_opt,
-                   "marginalize_call": getattr(backend, "t_call", 0.0), "L": w.L, "n_factors": w.n_factors,
+            lat = {"optimize": t1 - t0, "marginalize": t3 - t2, "optimize_call": c_opt, "flag": self.margin_flag,
+                   "marginalize_call": c_marg, "L": w.L, "n_factors": w.n_factors,
                    "iterations": summ["iterations"], "final_cost": summ["final_cost"]}
             gp, _ = self._gt(self.t)
             self.history.append((self.frame, float(np.linalg.norm(self.pose[-1, :3] - gp[:3])), summ["final_cost"]))
@@ -363,7 +430,7 @@ class SlidingWindowSim:
         if lat is not None and "select" not in lat:
             lat["select"] = lat["select_call"] = 0.0
         if len(self.pose) == self.K:
-            self._slide()
+            self._slide() if self.margin_flag == MARGIN_OLD else self._slide_new()
         return lat
 
 

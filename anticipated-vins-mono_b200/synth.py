@@ -172,6 +172,7 @@ class Preintegration:
     def __init__(self, acc_0, gyr_0, lin_ba, lin_bg,
                  acc_n=ACC_N, gyr_n=GYR_N, acc_w=ACC_W, gyr_w=GYR_W):
         self.acc_0, self.gyr_0 = np.array(acc_0, float), np.array(gyr_0, float)
+        self.linearized_acc, self.linearized_gyr = self.acc_0.copy(), self.gyr_0.copy()   # integration_base.h:16-17
         self.lin_ba, self.lin_bg = np.array(lin_ba, float), np.array(lin_bg, float)
         self.jacobian = np.eye(15)
         self.covariance = np.zeros((15, 15))

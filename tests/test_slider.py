@@ -39,6 +39,73 @@ def test_slider_bookkeeping_on_oracle(pkg, oracle):
     assert n_new <= 60
 
 
+def test_slider_second_new_branch_on_oracle(pkg, oracle):
+    """keyframes="parallax" at 25 Hz: the reference's addFeatureCheckParallax rule alternates MARGIN_OLD and
+    MARGIN_SECOND_NEW (estimator.cpp:134-137), so slideWindowNew / removeFront and the flag-1 marginalization run in the
+    loop, each prior feeding the next window."""
+    sl = pkg.slider
+    sim = sl.SlidingWindowSim(seed=5, max_feats=100, max_cand=150, opts=dict(max_iters=8), keyframes="parallax",
+                              frame_dt=0.04)
+    be = OracleBackend(oracle, pkg.abi)
+    flags, prior_n, sum_dt = [], [], []
+    for _ in range(44):
+        lat = sim.step(be)
+        if lat is not None:
+            flags.append(lat["flag"])
+            prior_n.append(sim.prior["n"] if sim.prior is not None else 0)
+            sum_dt.append(sim.preint[-1][16])
+            assert len(sim.pose) == sim.K - 1 == len(sim.preint) == len(sim.pre_obj) == len(sim.imu_buf)
+            for tr in sim.tracks.values():
+                assert 0 <= tr.start and tr.start + len(tr.xy) <= sim.K - 1 and len(tr.xy) >= 1
+    flags = np.array(flags)
+    assert (flags == 0).sum() >= 10 and (flags == 1).sum() >= 10
+    assert sim.sum_of_back == (flags == 0).sum() and sim.sum_of_front == (flags == 1).sum()
+    # MARGIN_SECOND_NEW drops Pose[WINDOW_SIZE - 1] from the prior (75 -> 69); the next MARGIN_OLD restores 75
+    assert set(prior_n[2:]) == {69, 75}
+    assert all(n == 69 for n, f in zip(prior_n[2:], flags[2:]) if f == 1)
+    # after a SECOND_NEW slide the newest interval spans two camera periods (IMU samples appended, estimator.cpp:1046-1057)
+    for f, sd in zip(flags, sum_dt):
+        assert abs(sd - (0.08 if f == 1 else 0.04)) < 1e-9
+    errs = np.array([h[1] for h in sim.history])
+    assert errs.max() < 0.15, errs
+
+
+def test_slide_new_remove_front_and_imu_merge(pkg):
+    """FeatureManager::removeFront (feature_manager.cpp:330-351) and the preintegration merge of slideWindow's
+    MARGIN_SECOND_NEW branch, on a hand-built window."""
+    sl, S = pkg.slider, pkg.synth
+    sim = sl.SlidingWindowSim(seed=1, keyframes="parallax")
+    while len(sim.pose) < sim.K:                          # fill the window without solving
+        sim._ingest()
+    K, WS = sim.K, sl.WINDOW_SIZE
+    xy = lambda n: [np.array([0.01 * k, 0.0]) for k in range(n)]
+    sim.tracks = {
+        1: sl.Track(lid=1, start=WS, xy=xy(1)),            # born in the newest frame: start moves to WS-1
+        2: sl.Track(lid=2, start=WS - 1, xy=xy(2)),        # seen in WS-1 and WS: loses the WS-1 observation
+        3: sl.Track(lid=3, start=WS - 1, xy=xy(1)),        # seen only in WS-1: erased
+        4: sl.Track(lid=4, start=3, xy=xy(WS - 3 + 1)),    # long track through both frames: one observation fewer
+        5: sl.Track(lid=5, start=2, xy=xy(4)),             # ended before WS-1: untouched
+        6: sl.Track(lid=6, start=4, xy=xy(WS - 1 - 4 + 1)),  # ends exactly at WS-1: loses its last observation
+    }
+    newest_pose, newest_sb = sim.pose[WS].copy(), sim.sb[WS].copy()
+    both = sim.imu_buf[WS - 1] + sim.imu_buf[WS]
+    old = sim.pre_obj[WS - 1]
+    ref = S.Preintegration(old.linearized_acc, old.linearized_gyr, old.lin_ba, old.lin_bg)
+    for dt, a, g in both:                                  # one integration over the concatenated samples
+        ref.push_back(dt, a, g)
+    sim._slide_new()
+    assert np.array_equal(sim.preint[-1], S.pack_preint(ref))
+    assert len(sim.pose) == K - 1 and (sim.pose[-1] == newest_pose).all() and (sim.sb[-1] == newest_sb).all()
+    assert len(sim.imu_buf[-1]) == len(both) and abs(sim.preint[-1][16] - sum(b[0] for b in both)) < 1e-12
+    t = sim.tracks
+    assert t[1].start == WS - 1 and len(t[1].xy) == 1
+    assert t[2].start == WS - 1 and len(t[2].xy) == 1 and t[2].xy[0][0] == 0.01
+    assert 3 not in t
+    assert t[4].start == 3 and len(t[4].xy) == WS - 3 and t[4].xy[-1][0] == 0.01 * (WS - 3) and t[4].xy[-2][0] == 0.01 * (WS - 5)
+    assert len(t[5].xy) == 4 and len(t[6].xy) == WS - 1 - 4
+    assert sim.sum_of_front == 1
+
+
 def test_regauge_keeps_frame0_yaw_and_position(pkg):
     sl, S = pkg.slider, pkg.synth
     rng = np.random.default_rng(0)
@@ -136,6 +203,22 @@ def test_closed_loop_session_gpu_vs_oracle_on_identical_inputs(pkg, oracle):
     assert dual.n["optimize"] == 30 and dual.n["marginalize"] == 30 and dual.n["select"] >= 10, dual.n
     assert dual.n["triangulate"] >= 10, dual.n
     assert sim.prior["n"] == 75
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_closed_loop_session_with_non_keyframes_gpu_vs_oracle(pkg, oracle):
+    """As above at 25 Hz with the reference's keyframe rule: MARGIN_OLD and MARGIN_SECOND_NEW alternate, so the device
+    marginalization runs flag 1 on chained priors and optimize sees merged (two-period) preintegrations."""
+    sl = pkg.slider
+    ctx = pkg.lib.Context(0)
+    sim = sl.SlidingWindowSim(seed=5, max_feats=100, max_cand=150, opts=dict(max_iters=8), keyframes="parallax",
+                              frame_dt=0.04)
+    dual = DualBackend(oracle, pkg.abi, sl.GpuBackend(ctx, pkg.abi))
+    for f in range(36):
+        sim.step(dual)
+    assert dual.n["optimize"] == 26 and sim.sum_of_front >= 8 and sim.sum_of_back >= 8, (dual.n, sim.sum_of_front)
+    assert sim.prior["n"] in (69, 75)
     ctx.close()
 
 
