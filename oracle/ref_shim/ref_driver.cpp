@@ -1,0 +1,303 @@
+// ref_driver.cpp -- C entry points around the REFERENCE's own factor sources, compiled from where they lie under
+// /root/reference (see oracle/Makefile target `ref`; output oracle/_ref/libvins_ref.so).  TEST INFRASTRUCTURE ONLY:
+// it pins the oracle's restatement (oracle/ba_oracle.cpp) to the arithmetic of the reference's code.
+//
+// What runs reference code here:  ProjectionFactor::Evaluate, ProjectionTdFactor::Evaluate, IMUFactor::Evaluate,
+// IntegrationBase::{push_back, propagate, midPointIntegration, repropagate, evaluate}, PoseLocalParameterization::Plus,
+// ResidualBlockInfo::Evaluate (loss corrector), MarginalizationInfo::{addResidualBlockInfo, preMarginalize, marginalize,
+// getParameterBlocks}, MarginalizationFactor::Evaluate, Utility::{deltaQ, Qleft, Qright, skewSymmetric, logdet}.
+// What is ours: the Eigen / Ceres / ROS stand-in headers next to this file (the libraries are not installed here), and
+// the glue below that feeds the factors -- for marginalization it restates which residual blocks
+// Estimator::optimization() hands to MarginalizationInfo and with which drop sets (estimator.cpp:816-991), because
+// estimator.cpp itself needs the whole ROS / OpenCV / Ceres stack.
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <vector>
+using namespace std;   // integration_base.h prints with unqualified cout / endl
+
+#include "factor/imu_factor.h"
+#include "factor/marginalization_factor.h"
+#include "factor/pose_local_parameterization.h"
+#include "factor/projection_factor.h"
+#include "factor/projection_td_factor.h"
+
+#include "../../include/bvio.h"
+
+// globals of parameters.cpp that the factor code reads
+double ACC_N, ACC_W, GYR_N, GYR_W;
+Eigen::Vector3d G;
+double TR, ROW, COL, TD;
+
+namespace {
+Eigen::Vector3d v3(const double* p) { return Eigen::Vector3d(p[0], p[1], p[2]); }
+
+void load(IntegrationBase& ib, const bvio_preint* pre) {
+  ib.delta_p = v3(pre->delta_p);
+  ib.delta_q = Eigen::Quaterniond(pre->delta_q[3], pre->delta_q[0], pre->delta_q[1], pre->delta_q[2]);
+  ib.delta_v = v3(pre->delta_v);
+  ib.sum_dt = pre->sum_dt;
+  for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) {
+    ib.jacobian(i, j) = pre->jacobian[i * 15 + j];
+    ib.covariance(i, j) = pre->covariance[i * 15 + j];
+  }
+}
+void store(const IntegrationBase& ib, bvio_preint* pre) {
+  for (int i = 0; i < 3; ++i) { pre->delta_p[i] = ib.delta_p(i); pre->delta_v[i] = ib.delta_v(i); pre->lin_ba[i] = ib.linearized_ba(i); pre->lin_bg[i] = ib.linearized_bg(i); }
+  pre->delta_q[0] = ib.delta_q.x(); pre->delta_q[1] = ib.delta_q.y(); pre->delta_q[2] = ib.delta_q.z(); pre->delta_q[3] = ib.delta_q.w();
+  pre->sum_dt = ib.sum_dt;
+  for (int i = 0; i < 15; ++i) for (int j = 0; j < 15; ++j) {
+    pre->jacobian[i * 15 + j] = ib.jacobian(i, j);
+    pre->covariance[i * 15 + j] = ib.covariance(i, j);
+  }
+}
+
+// The window copied into Estimator-like parameter arrays (estimator.h:109-115) with stable addresses.
+struct Params {
+  int K, L;
+  std::vector<double> pose, sb, feat;
+  double ex[7], td[1];
+  explicit Params(const bvio_window* w) : K(w->K), L(w->L), pose(w->para_pose, w->para_pose + 7 * w->K),
+      sb(w->para_speed_bias, w->para_speed_bias + 9 * w->K), feat(w->inv_depth, w->inv_depth + w->L) {
+    memcpy(ex, w->para_ex_pose, sizeof ex); td[0] = w->para_td ? w->para_td[0] : 0.0;
+  }
+  double* Pose(int i) { return &pose[7 * i]; }
+  double* SpeedBias(int i) { return &sb[9 * i]; }
+  double* Feature(int l) { return &feat[l]; }
+  double* block(int kind, int frame) {
+    return kind == BVIO_BLK_POSE ? Pose(frame) : kind == BVIO_BLK_SPEEDBIAS ? SpeedBias(frame) : kind == BVIO_BLK_EXPOSE ? ex : td;
+  }
+  bool identify(const double* p, int* kind, int* frame) {
+    for (int i = 0; i < K; ++i) {
+      if (p == Pose(i)) { *kind = BVIO_BLK_POSE; *frame = i; return true; }
+      if (p == SpeedBias(i)) { *kind = BVIO_BLK_SPEEDBIAS; *frame = i; return true; }
+    }
+    if (p == ex) { *kind = BVIO_BLK_EXPOSE; *frame = 0; return true; }
+    if (p == td) { *kind = BVIO_BLK_TD; *frame = 0; return true; }
+    return false;
+  }
+};
+
+int global_size(int kind) { return kind == BVIO_BLK_POSE || kind == BVIO_BLK_EXPOSE ? 7 : kind == BVIO_BLK_SPEEDBIAS ? 9 : 1; }
+
+// last_marginalization_info + last_marginalization_parameter_blocks rebuilt from the C-ABI's prior
+MarginalizationInfo* info_from_prior(const bvio_prior* pr, Params& P, std::vector<double*>* blocks, std::vector<double>* x0_store) {
+  MarginalizationInfo* info = new MarginalizationInfo();
+  info->n = pr->n; info->m = 0;
+  int tot = 0; for (int b = 0; b < pr->nblocks; ++b) tot += global_size(pr->block_kind[b]);
+  x0_store->assign(pr->x0, pr->x0 + tot);
+  int off = 0;
+  for (int b = 0; b < pr->nblocks; ++b) {
+    int gs = global_size(pr->block_kind[b]);
+    info->keep_block_size.push_back(gs);
+    info->keep_block_idx.push_back(pr->block_idx[b]);
+    info->keep_block_data.push_back(x0_store->data() + off);
+    blocks->push_back(P.block(pr->block_kind[b], pr->block_frame[b]));
+    off += gs;
+  }
+  info->linearized_jacobians.resize(pr->n, pr->n);
+  info->linearized_residuals.resize(pr->n);
+  for (int i = 0; i < pr->n; ++i) { info->linearized_residuals(i) = pr->lin_res[i]; for (int j = 0; j < pr->n; ++j) info->linearized_jacobians(i, j) = pr->lin_jac[(size_t)j * pr->n + i]; }
+  return info;
+}
+}  // namespace
+
+extern "C" {
+
+void ref_projection_factor(const double pts_i[3], const double pts_j[3], const double pose_i[7], const double pose_j[7],
+                           const double ex_pose[7], double inv_dep, double sqrt_info, double res[2], double* jac_i,
+                           double* jac_j, double* jac_ex, double* jac_f) {
+  ProjectionFactor::sqrt_info = sqrt_info * Eigen::Matrix2d::Identity();
+  ProjectionFactor f(v3(pts_i), v3(pts_j));
+  const double* params[4] = {pose_i, pose_j, ex_pose, &inv_dep};
+  double* jac[4] = {jac_i, jac_j, jac_ex, jac_f};
+  f.Evaluate(params, res, jac);
+}
+
+void ref_projection_td_factor(const double pts_i[3], const double pts_j[3], const double vel_i[2], const double vel_j[2],
+                              double td_i, double td_j, double row_i, double row_j, double TR_, double ROW_,
+                              const double pose_i[7], const double pose_j[7], const double ex_pose[7], double inv_dep,
+                              double td, double sqrt_info, double res[2], double* jac_i, double* jac_j, double* jac_ex,
+                              double* jac_f, double* jac_td) {
+  TR = TR_; ROW = ROW_;
+  ProjectionTdFactor::sqrt_info = sqrt_info * Eigen::Matrix2d::Identity();
+  ProjectionTdFactor f(v3(pts_i), v3(pts_j), Eigen::Vector2d(vel_i[0], vel_i[1]), Eigen::Vector2d(vel_j[0], vel_j[1]), td_i, td_j, row_i, row_j);
+  const double* params[5] = {pose_i, pose_j, ex_pose, &inv_dep, &td};
+  double* jac[5] = {jac_i, jac_j, jac_ex, jac_f, jac_td};
+  f.Evaluate(params, res, jac);
+}
+
+void ref_imu_factor(const bvio_preint* pre, const double G_[3], const double pose_i[7], const double sb_i[9],
+                    const double pose_j[7], const double sb_j[9], double res[15], double* jac_pi, double* jac_sbi,
+                    double* jac_pj, double* jac_sbj) {
+  G = v3(G_);
+  IntegrationBase ib(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), v3(pre->lin_ba), v3(pre->lin_bg));
+  load(ib, pre);
+  IMUFactor f(&ib);
+  const double* params[4] = {pose_i, sb_i, pose_j, sb_j};
+  double* jac[4] = {jac_pi, jac_sbi, jac_pj, jac_sbj};
+  f.Evaluate(params, res, jac);
+}
+
+void ref_preint_propagate(bvio_preint* pre, double dt, const double acc_0[3], const double gyr_0[3], const double acc_1[3],
+                          const double gyr_1[3], double acc_n, double gyr_n, double acc_w, double gyr_w) {
+  ACC_N = acc_n; GYR_N = gyr_n; ACC_W = acc_w; GYR_W = gyr_w;
+  IntegrationBase ib(v3(acc_0), v3(gyr_0), v3(pre->lin_ba), v3(pre->lin_bg));
+  load(ib, pre);
+  ib.propagate(dt, v3(acc_1), v3(gyr_1));
+  store(ib, pre);
+}
+
+// n push_backs from scratch: acc / gyr hold n + 1 samples (sample 0 starts the interval); then, when new_ba != NULL,
+// IntegrationBase::repropagate(new_ba, new_bg)
+void ref_preintegrate(int n, const double* dt, const double* acc, const double* gyr, const double ba[3], const double bg[3],
+                      double acc_n, double gyr_n, double acc_w, double gyr_w, const double* new_ba, const double* new_bg,
+                      bvio_preint* out) {
+  ACC_N = acc_n; GYR_N = gyr_n; ACC_W = acc_w; GYR_W = gyr_w;
+  IntegrationBase ib(v3(acc), v3(gyr), v3(ba), v3(bg));
+  for (int i = 0; i < n; ++i) ib.push_back(dt[i], v3(acc + 3 * (i + 1)), v3(gyr + 3 * (i + 1)));
+  if (new_ba) ib.repropagate(v3(new_ba), v3(new_bg));
+  store(ib, out);
+}
+
+void ref_pose_plus(const double x[7], const double delta[6], double out[7]) {
+  ceres::LocalParameterization* p = new PoseLocalParameterization();
+  p->Plus(x, delta, out);
+  delete p;
+}
+
+double ref_logdet(const double* M, int n) {
+  Eigen::MatrixXd A(n, n);
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) A(i, j) = M[(size_t)i * n + j];
+  return Utility::logdet(A, true);
+}
+
+// ResidualBlockInfo::Evaluate on one ProjectionFactor with CauchyLoss(a): loss-corrected residual and Jacobians
+void ref_projection_block_corrected(const double pts_i[3], const double pts_j[3], const double pose_i[7], const double pose_j[7],
+                                    const double ex_pose[7], double inv_dep, double sqrt_info, double cauchy_a, double res[2],
+                                    double jac_i[14], double jac_j[14], double jac_ex[14], double jac_f[2]) {
+  ProjectionFactor::sqrt_info = sqrt_info * Eigen::Matrix2d::Identity();
+  double pi[7], pj[7], ex[7], f[1] = {inv_dep};
+  memcpy(pi, pose_i, sizeof pi); memcpy(pj, pose_j, sizeof pj); memcpy(ex, ex_pose, sizeof ex);
+  ceres::CauchyLoss loss(cauchy_a);
+  ResidualBlockInfo rb(new ProjectionFactor(v3(pts_i), v3(pts_j)), &loss, std::vector<double*>{pi, pj, ex, f}, std::vector<int>{0, 3});
+  rb.Evaluate();
+  for (int i = 0; i < 2; ++i) res[i] = rb.residuals(i);
+  double* outs[4] = {jac_i, jac_j, jac_ex, jac_f};
+  for (int b = 0; b < 4; ++b) for (int i = 0; i < rb.jacobians[b].rows(); ++i) for (int j = 0; j < rb.jacobians[b].cols(); ++j)
+    outs[b][i * rb.jacobians[b].cols() + j] = rb.jacobians[b](i, j);
+  delete rb.cost_function; delete[] rb.raw_jacobians;
+}
+
+// MarginalizationFactor::Evaluate of the window's prior at the window's state: residual [n] and the Jacobian in local
+// coordinates, dense row-major [n][n] (columns = the prior's own block_idx layout)
+int ref_prior_eval(const bvio_prior* pr, const bvio_window* w, double* res, double* jac) {
+  Params P(w);
+  std::vector<double*> blocks; std::vector<double> x0;
+  MarginalizationInfo* info = info_from_prior(pr, P, &blocks, &x0);
+  MarginalizationFactor f(info);
+  int n = pr->n;
+  std::vector<std::vector<double>> J(blocks.size());
+  std::vector<double*> jp;
+  for (size_t b = 0; b < blocks.size(); ++b) { J[b].assign((size_t)n * info->keep_block_size[b], 0.0); jp.push_back(J[b].data()); }
+  f.Evaluate(blocks.data(), res, jp.data());
+  if (jac) {
+    std::fill(jac, jac + (size_t)n * n, 0.0);
+    for (size_t b = 0; b < blocks.size(); ++b) {
+      int gs = info->keep_block_size[b], ls = info->localSize(gs), idx = info->keep_block_idx[b];
+      for (int i = 0; i < n; ++i) for (int j = 0; j < ls; ++j) jac[(size_t)i * n + idx + j] = J[b][(size_t)i * gs + j];
+      for (int i = 0; i < n; ++i) for (int j = ls; j < gs; ++j) if (J[b][(size_t)i * gs + j] != 0.0) return -2;   // 7th column must be zero
+    }
+  }
+  info->keep_block_data.clear();
+  return 0;
+}
+
+// Estimator::optimization()'s marginalization step (estimator.cpp:816-991) with the reference's MarginalizationInfo.
+int ref_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_prior_out* out) {
+  Params P(w);
+  const int K = P.K, WS = K - 1;
+  G = v3(o->G); TR = o->TR; ROW = o->ROW;
+  ProjectionFactor::sqrt_info = o->focal_length / 1.5 * Eigen::Matrix2d::Identity();
+  ProjectionTdFactor::sqrt_info = o->focal_length / 1.5 * Eigen::Matrix2d::Identity();
+  ceres::LossFunction* loss_function = new ceres::CauchyLoss(o->cauchy_a);
+  std::vector<double*> last_blocks; std::vector<double> x0;
+  MarginalizationInfo* last = w->prior ? info_from_prior(w->prior, P, &last_blocks, &x0) : nullptr;
+  std::vector<IntegrationBase*> keep_alive;
+  MarginalizationInfo* info = new MarginalizationInfo();
+  std::unordered_map<long, double*> addr_shift;
+  if (flag == 0) {
+    if (last) {
+      std::vector<int> drop_set;
+      for (int i = 0; i < (int)last_blocks.size(); ++i) if (last_blocks[i] == P.Pose(0) || last_blocks[i] == P.SpeedBias(0)) drop_set.push_back(i);
+      info->addResidualBlockInfo(new ResidualBlockInfo(new MarginalizationFactor(last), NULL, last_blocks, drop_set));
+    }
+    if (w->preint[1].sum_dt < 10.0) {
+      IntegrationBase* ib = new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), v3(w->preint[1].lin_ba), v3(w->preint[1].lin_bg));
+      load(*ib, &w->preint[1]); keep_alive.push_back(ib);
+      info->addResidualBlockInfo(new ResidualBlockInfo(new IMUFactor(ib), NULL,
+          std::vector<double*>{P.Pose(0), P.SpeedBias(0), P.Pose(1), P.SpeedBias(1)}, std::vector<int>{0, 1}));
+    }
+    for (int l = 0; l < P.L; ++l) {
+      int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
+      int imu_i = w->obs_frame[o0];
+      if (imu_i != 0) continue;
+      Eigen::Vector3d pts_i(w->obs_xy[2 * o0], w->obs_xy[2 * o0 + 1], 1.0);
+      for (int k = o0 + 1; k < o1; ++k) {
+        int imu_j = w->obs_frame[k];
+        Eigen::Vector3d pts_j(w->obs_xy[2 * k], w->obs_xy[2 * k + 1], 1.0);
+        if (o->estimate_td) {
+          ProjectionTdFactor* f_td = new ProjectionTdFactor(pts_i, pts_j, Eigen::Vector2d(w->obs_vel[2 * o0], w->obs_vel[2 * o0 + 1]),
+              Eigen::Vector2d(w->obs_vel[2 * k], w->obs_vel[2 * k + 1]), w->obs_td[o0], w->obs_td[k], w->obs_row[o0], w->obs_row[k]);
+          info->addResidualBlockInfo(new ResidualBlockInfo(f_td, loss_function,
+              std::vector<double*>{P.Pose(imu_i), P.Pose(imu_j), P.ex, P.Feature(l), P.td}, std::vector<int>{0, 3}));
+        } else {
+          info->addResidualBlockInfo(new ResidualBlockInfo(new ProjectionFactor(pts_i, pts_j), loss_function,
+              std::vector<double*>{P.Pose(imu_i), P.Pose(imu_j), P.ex, P.Feature(l)}, std::vector<int>{0, 3}));
+        }
+      }
+    }
+    for (int i = 1; i <= WS; ++i) {
+      addr_shift[reinterpret_cast<long>(P.Pose(i))] = P.Pose(i - 1);
+      addr_shift[reinterpret_cast<long>(P.SpeedBias(i))] = P.SpeedBias(i - 1);
+    }
+  } else {
+    bool has = false;
+    for (double* b : last_blocks) has |= (b == P.Pose(WS - 1));
+    if (!last || !has) { out->n = -1; out->nblocks = 0; return 0; }
+    std::vector<int> drop_set;
+    for (int i = 0; i < (int)last_blocks.size(); ++i) {
+      if (last_blocks[i] == P.SpeedBias(WS - 1)) return -3;                 // ROS_ASSERT, estimator.cpp:937
+      if (last_blocks[i] == P.Pose(WS - 1)) drop_set.push_back(i);
+    }
+    info->addResidualBlockInfo(new ResidualBlockInfo(new MarginalizationFactor(last), NULL, last_blocks, drop_set));
+    for (int i = 0; i <= WS; ++i) {
+      if (i == WS - 1) continue;
+      int to = i == WS ? i - 1 : i;
+      addr_shift[reinterpret_cast<long>(P.Pose(i))] = P.Pose(to);
+      addr_shift[reinterpret_cast<long>(P.SpeedBias(i))] = P.SpeedBias(to);
+    }
+  }
+  addr_shift[reinterpret_cast<long>(P.ex)] = P.ex;
+  if (o->estimate_td) addr_shift[reinterpret_cast<long>(P.td)] = P.td;
+  info->preMarginalize();
+  info->marginalize();
+  std::vector<double*> parameter_blocks = info->getParameterBlocks(addr_shift);
+
+  int n = info->n, nb = (int)parameter_blocks.size();
+  if (n > out->cap_n || nb > out->cap_blocks) return -4;
+  out->n = n; out->nblocks = nb;
+  int off = 0;
+  for (int b = 0; b < nb; ++b) {
+    int kind, frame;
+    if (!P.identify(parameter_blocks[b], &kind, &frame)) return -5;
+    out->block_kind[b] = kind; out->block_frame[b] = frame; out->block_idx[b] = info->keep_block_idx[b] - info->m;
+    int gs = info->keep_block_size[b];
+    for (int i = 0; i < gs; ++i) out->x0[off + i] = info->keep_block_data[b][i];
+    off += gs;
+  }
+  for (int i = 0; i < n; ++i) { out->lin_res[i] = info->linearized_residuals(i); for (int j = 0; j < n; ++j) out->lin_jac[(size_t)j * n + i] = info->linearized_jacobians(i, j); }
+  return 0;   // the MarginalizationInfo objects are leaked on purpose (their destructor frees with mismatched delete)
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+"""ctypes loader for oracle/_ref/libvins_ref.so -- the REFERENCE's own factor sources (compiled from /root/reference by
+`make -C oracle ref`) behind the C entry points of oracle/ref_shim/ref_driver.cpp.  Tests only."""
+import ctypes as C
+import os
+import subprocess
+
+import __graft_entry__ as g
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(ROOT, "oracle", "_ref", "libvins_ref.so")
+_lib = None
+
+
+def load():
+    """None when the library is neither prebuilt nor buildable (no /root/reference)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(PATH) and os.path.isdir("/root/reference/vins_estimator/src/factor"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    if not os.path.exists(PATH):
+        return None
+    abi = g.load_package().abi
+    L = C.CDLL(PATH)
+    dp, i32, d = abi.c_double_p, C.c_int32, C.c_double
+    L.ref_projection_factor.argtypes = [dp, dp, dp, dp, dp, d, d, dp, dp, dp, dp, dp]
+    L.ref_projection_factor.restype = None
+    L.ref_projection_td_factor.argtypes = [dp, dp, dp, dp, d, d, d, d, d, d, dp, dp, dp, d, d, d, dp, dp, dp, dp, dp, dp]
+    L.ref_projection_td_factor.restype = None
+    L.ref_imu_factor.argtypes = [C.POINTER(abi.Preint), dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
+    L.ref_imu_factor.restype = None
+    L.ref_preint_propagate.argtypes = [C.POINTER(abi.Preint), d, dp, dp, dp, dp, d, d, d, d]
+    L.ref_preint_propagate.restype = None
+    L.ref_preintegrate.argtypes = [i32, dp, dp, dp, dp, dp, d, d, d, d, dp, dp, C.POINTER(abi.Preint)]
+    L.ref_preintegrate.restype = None
+    L.ref_pose_plus.argtypes = [dp, dp, dp]
+    L.ref_pose_plus.restype = None
+    L.ref_logdet.argtypes = [dp, i32]
+    L.ref_logdet.restype = d
+    L.ref_projection_block_corrected.argtypes = [dp, dp, dp, dp, dp, d, d, d, dp, dp, dp, dp, dp]
+    L.ref_projection_block_corrected.restype = None
+    L.ref_prior_eval.argtypes = [C.POINTER(abi.Prior), C.POINTER(abi.WindowS), dp, dp]
+    L.ref_marginalize.argtypes = [C.POINTER(abi.WindowS), C.POINTER(abi.Opts), i32, C.POINTER(abi.PriorOut)]
+    _lib = L
+    return L

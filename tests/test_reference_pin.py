@@ -1,0 +1,304 @@
+"""CPU suite: the oracle against the REFERENCE's own code.
+
+oracle/_ref/libvins_ref.so holds the reference's factor sources (projection_factor.cpp, projection_td_factor.cpp,
+imu_factor.h + integration_base.h, pose_local_parameterization.cpp, marginalization_factor.cpp, utility.h) compiled
+unmodified from /root/reference against the stand-in Eigen / Ceres / ROS headers of oracle/ref_shim/ (the real libraries
+are absent from this image).  Every test feeds identical inputs to a reference entry point and to the oracle
+restatement of the same SURVEY section-8 row."""
+import ctypes as C
+import dataclasses
+
+import numpy as np
+import pytest
+
+import np_ref
+import ref_lib
+from test_oracle_marg import info_in_state_coords, run_marg
+
+
+@pytest.fixture(scope="module")
+def ref():
+    L = ref_lib.load()
+    if L is None:
+        pytest.skip("oracle/_ref/libvins_ref.so not built and /root/reference not present")
+    return L
+
+
+def _rand_pose(rng, scale=1.0):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    return np.concatenate([rng.normal(size=3) * scale, q])
+
+
+def _ex(synth):
+    U, _, Vt = np.linalg.svd(synth.EUROC_RIC)
+    return np.concatenate([synth.EUROC_TIC, synth.rot_to_quat(U @ Vt)])
+
+
+def test_projection_factor_row_a2(pkg, oracle, ref):
+    """ProjectionFactor::Evaluate (projection_factor.cpp:21-121): residual and all four Jacobian blocks."""
+    abi, synth = pkg.abi, pkg.synth
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        pose_i, pose_j, ex = _rand_pose(rng, 0.3), _rand_pose(rng, 0.3), _ex(synth)
+        pose_j[3:] = np_ref.pose_plus(pose_i, np.concatenate([np.zeros(3), rng.normal(size=3) * 0.2]))[3:]
+        pts_i = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4), 1.0])
+        pts_j = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4), 1.0])
+        lam = rng.uniform(0.1, 0.5)
+        out = []
+        for fn in (ref.ref_projection_factor, oracle.oracle_projection_factor):
+            res, Ji, Jj, Jex, Jf = np.zeros(2), np.full(14, np.nan), np.full(14, np.nan), np.full(14, np.nan), np.zeros(2)
+            fn(abi.dptr(pts_i), abi.dptr(pts_j), abi.dptr(pose_i), abi.dptr(pose_j), abi.dptr(ex), lam, 460 / 1.5,
+               abi.dptr(res), abi.dptr(Ji), abi.dptr(Jj), abi.dptr(Jex), abi.dptr(Jf))
+            out.append(np.concatenate([res, Ji, Jj, Jex, Jf]))
+        sc = np.abs(out[0]).max()
+        assert np.abs(out[0] - out[1]).max() <= 1e-12 * sc
+
+
+def test_projection_td_factor_row_a2td(pkg, oracle, ref):
+    """ProjectionTdFactor::Evaluate (projection_td_factor.cpp:34-141) incl. the rolling-shutter row term."""
+    abi, synth = pkg.abi, pkg.synth
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        pose_i, pose_j, ex = _rand_pose(rng, 0.3), _rand_pose(rng, 0.3), _ex(synth)
+        pose_j[3:] = np_ref.pose_plus(pose_i, np.concatenate([np.zeros(3), rng.normal(size=3) * 0.2]))[3:]
+        pts_i = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4), 1.0])
+        pts_j = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4), 1.0])
+        vi, vj = rng.normal(0, 0.3, 2), rng.normal(0, 0.3, 2)
+        tdi, tdj, td = rng.normal(0, 0.01), rng.normal(0, 0.01), rng.normal(0, 0.01)
+        ri, rj = rng.uniform(0, 480), rng.uniform(0, 480)
+        TR = rng.choice([0.0, 0.02])
+        lam = rng.uniform(0.1, 0.5)
+        out = []
+        for fn in (ref.ref_projection_td_factor, oracle.oracle_projection_td_factor):
+            res, Ji, Jj, Jex, Jf, Jtd = np.zeros(2), np.zeros(14), np.zeros(14), np.zeros(14), np.zeros(2), np.zeros(2)
+            fn(abi.dptr(pts_i), abi.dptr(pts_j), abi.dptr(vi), abi.dptr(vj), tdi, tdj, ri, rj, TR, 480.0, abi.dptr(pose_i),
+               abi.dptr(pose_j), abi.dptr(ex), lam, td, 460 / 1.5, abi.dptr(res), abi.dptr(Ji), abi.dptr(Jj), abi.dptr(Jex),
+               abi.dptr(Jf), abi.dptr(Jtd))
+            out.append(np.concatenate([res, Ji, Jj, Jex, Jf, Jtd]))
+        assert np.abs(out[0] - out[1]).max() <= 1e-12 * np.abs(out[0]).max()
+
+
+def test_preintegration_row_a3in(pkg, oracle, ref):
+    """IntegrationBase::push_back / propagate / midPointIntegration (integration_base.h:30-158): 20 samples, both the
+    one-step entry point the oracle exposes and a full interval, then repropagate with new linearization biases."""
+    abi, synth = pkg.abi, pkg.synth
+    rng = np.random.default_rng(2)
+    n = 20
+    ba, bg = rng.normal(0, 0.02, 3), rng.normal(0, 0.002, 3)
+    acc = rng.normal(0, 1, (n + 1, 3)) + [0, 0, 9.8]
+    gyr = rng.normal(0, 0.3, (n + 1, 3))
+    dt = np.full(n, 0.005)
+    noise = (synth.ACC_N, synth.GYR_N, synth.ACC_W, synth.GYR_W)
+
+    def fresh():
+        c = abi.Preint()
+        c.delta_q[3] = 1.0
+        for i in range(3):
+            c.lin_ba[i], c.lin_bg[i] = ba[i], bg[i]
+        for i in range(15):
+            c.jacobian[i * 15 + i] = 1.0
+        return c
+    a, b = fresh(), fresh()
+    for k in range(n):
+        for fn, c in ((ref.ref_preint_propagate, a), (oracle.oracle_preint_propagate, b)):
+            fn(C.byref(c), float(dt[k]), abi.dptr(acc[k].copy()), abi.dptr(gyr[k].copy()), abi.dptr(acc[k + 1].copy()),
+               abi.dptr(gyr[k + 1].copy()), *noise)
+    ga, gb = (np.frombuffer(bytes(c), dtype=np.float64) for c in (a, b))
+    assert np.abs(ga[:17] - gb[:17]).max() <= 1e-14
+    assert np.abs(ga[17:242] - gb[17:242]).max() <= 1e-13 * np.abs(ga[17:242]).max()
+    assert np.abs(ga[242:] - gb[242:]).max() <= 1e-13 * np.abs(ga[242:]).max()
+    # the whole interval through push_back, and against the numpy class that generates every synthetic window
+    full = abi.Preint()
+    ref.ref_preintegrate(n, abi.dptr(dt), abi.dptr(acc.reshape(-1).copy()), abi.dptr(gyr.reshape(-1).copy()), abi.dptr(ba),
+                         abi.dptr(bg), *noise, None, None, C.byref(full))
+    assert np.array_equal(np.frombuffer(bytes(full), dtype=np.float64), ga)
+    pre = synth.Preintegration(acc[0], gyr[0], ba, bg)
+    for k in range(n):
+        pre.push_back(dt[k], acc[k + 1], gyr[k + 1])
+    pk = synth.pack_preint(pre)
+    assert np.abs(pk[:17] - ga[:17]).max() <= 1e-13
+    assert np.abs(pk[17:] - ga[17:]).max() <= 1e-11 * np.abs(ga[17:]).max()
+    # repropagate == integrating from scratch with the new biases
+    nba, nbg = ba + 0.01, bg - 0.001
+    rep, scratch = abi.Preint(), abi.Preint()
+    ref.ref_preintegrate(n, abi.dptr(dt), abi.dptr(acc.reshape(-1).copy()), abi.dptr(gyr.reshape(-1).copy()), abi.dptr(ba),
+                         abi.dptr(bg), *noise, abi.dptr(nba), abi.dptr(nbg), C.byref(rep))
+    ref.ref_preintegrate(n, abi.dptr(dt), abi.dptr(acc.reshape(-1).copy()), abi.dptr(gyr.reshape(-1).copy()), abi.dptr(nba),
+                         abi.dptr(nbg), *noise, None, None, C.byref(scratch))
+    assert bytes(rep) == bytes(scratch)
+
+
+def test_imu_factor_row_a3(pkg, oracle, ref):
+    """IMUFactor::Evaluate (imu_factor.h:19-179) + IntegrationBase::evaluate: whitened residual and four Jacobians.
+    The sqrt-information comes from inverse() + LLT of a covariance with cond ~1e9, so two correct implementations
+    agree to ~1e-7 relative, not to rounding."""
+    abi, synth = pkg.abi, pkg.synth
+    G = np.array([0, 0, synth.G_NORM])
+    for seed in range(4):
+        w = synth.make_window(seed=seed, K=5, L=10)
+        h = abi.WindowHandle(w)
+        for j in range(1, 5):
+            pre_c = C.cast(h.pre.ctypes.data + j * 467 * 8, C.POINTER(abi.Preint))
+            args = [w.para_pose[j - 1].copy(), w.para_speed_bias[j - 1].copy(), w.para_pose[j].copy(), w.para_speed_bias[j].copy()]
+            out = []
+            for fn in (ref.ref_imu_factor, oracle.oracle_imu_factor):
+                res, J = np.zeros(15), [np.zeros(105), np.zeros(135), np.zeros(105), np.zeros(135)]
+                fn(pre_c, abi.dptr(G), *(abi.dptr(a) for a in args), abi.dptr(res), *(abi.dptr(x) for x in J))
+                out.append((res, J))
+            (r0, J0), (r1, J1) = out
+            assert np.abs(r0 - r1).max() <= 2e-7 * np.abs(r0).max()
+            for a, b in zip(J0, J1):
+                assert np.abs(a - b).max() <= 2e-7 * np.abs(a).max()
+            # quantities that do not depend on how the inverse was rounded: the squared Mahalanobis norm and J^T r
+            assert abs(r0 @ r0 - r1 @ r1) <= 1e-9 * (r0 @ r0)
+            for a, b, c in zip(J0, J1, (7, 9, 7, 9)):
+                ga, gb = a.reshape(15, c).T @ r0, b.reshape(15, c).T @ r1
+                assert np.abs(ga - gb).max() <= 1e-8 * np.abs(ga).max()
+
+
+def test_pose_plus_row_a5(pkg, oracle, ref):
+    """PoseLocalParameterization::Plus (pose_local_parameterization.cpp:3-19) vs the restatement every test uses."""
+    abi = pkg.abi
+    rng = np.random.default_rng(3)
+    for _ in range(100):
+        x, d, out = _rand_pose(rng), rng.normal(0, 0.2, 6), np.zeros(7)
+        ref.ref_pose_plus(abi.dptr(x), abi.dptr(d), abi.dptr(out))
+        assert np.abs(out - np_ref.pose_plus(x, d)).max() <= 1e-15
+
+
+def test_loss_corrector_row_a6(pkg, oracle, ref):
+    """ResidualBlockInfo::Evaluate with CauchyLoss(1) (marginalization_factor.cpp:37-68): rho'' < 0 => the simple
+    branch: residual and Jacobians scaled by sqrt(rho')."""
+    abi, synth = pkg.abi, pkg.synth
+    rng = np.random.default_rng(4)
+    for _ in range(50):
+        pose_i, pose_j, ex = _rand_pose(rng, 0.3), _rand_pose(rng, 0.3), _ex(synth)
+        pose_j[3:] = np_ref.pose_plus(pose_i, np.concatenate([np.zeros(3), rng.normal(size=3) * 0.05]))[3:]
+        pts_i = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4), 1.0])
+        pts_j = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4), 1.0])
+        lam = rng.uniform(0.1, 0.5)
+        res, Ji, Jj, Jex, Jf = np.zeros(2), np.zeros(14), np.zeros(14), np.zeros(14), np.zeros(2)
+        ref.ref_projection_block_corrected(abi.dptr(pts_i), abi.dptr(pts_j), abi.dptr(pose_i), abi.dptr(pose_j), abi.dptr(ex),
+                                           lam, 460 / 1.5, 1.0, abi.dptr(res), abi.dptr(Ji), abi.dptr(Jj), abi.dptr(Jex), abi.dptr(Jf))
+        r, oJi, oJj, oJex, oJf = np.zeros(2), np.zeros(14), np.zeros(14), np.zeros(14), np.zeros(2)
+        oracle.oracle_projection_factor(abi.dptr(pts_i), abi.dptr(pts_j), abi.dptr(pose_i), abi.dptr(pose_j), abi.dptr(ex), lam,
+                                        460 / 1.5, abi.dptr(r), abi.dptr(oJi), abi.dptr(oJj), abi.dptr(oJex), abi.dptr(oJf))
+        sr = np.sqrt(1.0 / (1.0 + r @ r))
+        for a, b in ((res, r), (Ji, oJi), (Jj, oJj), (Jex, oJex), (Jf, oJf)):
+            assert np.abs(a - sr * b).max() <= 1e-12 * max(np.abs(a).max(), 1e-30)
+
+
+def test_prior_factor_row_a4(pkg, oracle, ref):
+    """MarginalizationFactor::Evaluate (marginalization_factor.cpp:333-381): residual r0 + J dx with the quaternion
+    sign flip, Jacobian = column slices with a zero 7th column."""
+    abi, synth = pkg.abi, pkg.synth
+    rng = np.random.default_rng(5)
+    w = synth.make_window(seed=5, K=5, L=12)
+    n = 6 + 9 + 6 + 6
+    J = rng.normal(size=(n, n))
+    w.prior = dict(n=n, block_kind=np.array([0, 1, 2, 0], np.int32), block_frame=np.array([0, 0, 0, 2], np.int32),
+                   block_idx=np.array([0, 6, 15, 21], np.int32),
+                   x0=np.concatenate([w.gt_pose[0], w.gt_speed_bias[0], w.para_ex_pose, -w.gt_pose[2]]),
+                   lin_jac=J.reshape(-1, order="F").copy(), lin_res=rng.normal(size=n))
+    h = abi.WindowHandle(w)
+    res_o, dx = np.zeros(n), np.zeros(n)
+    oracle.oracle_prior_residual(C.byref(h.prior_s), C.byref(h.s), abi.dptr(res_o), abi.dptr(dx))
+    res_r, jac = np.zeros(n), np.zeros(n * n)
+    assert ref.ref_prior_eval(C.byref(h.prior_s), C.byref(h.s), abi.dptr(res_r), abi.dptr(jac)) == 0
+    assert np.abs(res_r - res_o).max() <= 1e-12 * np.abs(res_o).max()
+    assert np.array_equal(jac.reshape(n, n), J)
+
+
+def test_logdet_row_a13(pkg, oracle, ref):
+    """Utility::logdet(M, use_cholesky = true), utility.h:143-167."""
+    abi = pkg.abi
+    rng = np.random.default_rng(6)
+    for n in (9, 99, 126):
+        A = rng.normal(size=(n, n))
+        M = A @ A.T + n * np.eye(n)
+        a, b = ref.ref_logdet(abi.dptr(M.reshape(-1).copy()), n), oracle.oracle_logdet(abi.dptr(M.reshape(-1).copy()), n)
+        assert abs(a - b) <= 1e-12 * abs(a) and abs(a - np.linalg.slogdet(M)[1]) <= 1e-12 * abs(a)
+
+
+def _quad(p, K, unshift):
+    return info_in_state_coords(p, K, unshift)
+
+
+@pytest.mark.parametrize("seed,K,L", [(0, 11, 150), (1, 6, 40), (2, 11, 30)])
+def test_margin_old_row_a9(pkg, oracle, ref, seed, K, L):
+    """MarginalizationInfo::{addResidualBlockInfo, preMarginalize, marginalize} on the residual blocks of
+    estimator.cpp:816-925: the new prior's quadratic form (J^T J, J^T r; the factor (J, r) itself and the block order
+    are not unique) and linearization points."""
+    abi, synth = pkg.abi, pkg.synth
+    w = synth.make_window(seed=seed, K=K, L=L)
+    pr = run_marg(abi, ref.ref_marginalize, w, 0)
+    po = run_marg(abi, oracle.oracle_marginalize, w, 0)
+    assert pr["n"] == po["n"] and sorted(zip(pr["block_kind"], pr["block_frame"])) == sorted(zip(po["block_kind"], po["block_frame"]))
+    Hr, gr = _quad(pr, K, lambda f: f + 1)
+    Ho, go = _quad(po, K, lambda f: f + 1)
+    assert np.abs(Hr - Ho).max() <= 1e-7 * np.abs(Hr).max()
+    assert np.abs(gr - go).max() <= 5e-5 * max(np.abs(gr).max(), 1.0)
+    # same linearization points, whatever the block order
+    def x0_map(p):
+        out, off = {}, 0
+        for k, f in zip(p["block_kind"], p["block_frame"]):
+            size = 7 if k in (0, 2) else 9 if k == 1 else 1
+            out[(int(k), int(f))] = p["x0"][off:off + size]
+            off += size
+        return out
+    xr, xo = x0_map(pr), x0_map(po)
+    assert all(np.array_equal(xr[k], xo[k]) for k in xr)
+
+
+def test_margin_chain_and_second_new_row_a9(pkg, oracle, ref):
+    """The reference's marginalization fed with a prior (its own previous output): MARGIN_OLD again, and
+    MARGIN_SECOND_NEW (estimator.cpp:926-990) incl. the 'prior does not involve Pose[WINDOW_SIZE-1]' early-out."""
+    abi, synth = pkg.abi, pkg.synth
+    K = 11
+    w = synth.make_window(seed=5, K=K, L=80)
+    keys = ("n", "block_kind", "block_frame", "block_idx", "x0", "lin_jac", "lin_res")
+    p1 = run_marg(abi, ref.ref_marginalize, w, 0)
+    w2 = dataclasses.replace(w, prior={k: p1[k] for k in keys})
+    for flag, unshift in ((0, lambda f: f + 1), (1, lambda f: f if f < K - 2 else f + 1)):
+        pr = run_marg(abi, ref.ref_marginalize, w2, flag)
+        po = run_marg(abi, oracle.oracle_marginalize, w2, flag)
+        assert pr["n"] == po["n"]
+        Hr, gr = _quad(pr, K, unshift)
+        Ho, go = _quad(po, K, unshift)
+        assert np.abs(Hr - Ho).max() <= 1e-7 * np.abs(Hr).max(), flag
+        assert np.abs(gr - go).max() <= 5e-5 * max(np.abs(gr).max(), 1.0), flag
+    assert run_marg(abi, ref.ref_marginalize, w, 1) is None and run_marg(abi, oracle.oracle_marginalize, w, 1) is None
+
+
+def test_margin_old_with_td_row_a9(pkg, oracle, ref):
+    """ESTIMATE_TD: ProjectionTdFactor blocks with para_Td kept (estimator.cpp:863-871)."""
+    abi, synth = pkg.abi, pkg.synth
+    K = 8
+    w = synth.make_window(seed=3, K=K, L=50, td_true=0.003)
+    w.para_td[0] = 0.001
+    o = dict(estimate_td=1, TR=0.015)
+    pr = run_marg(abi, ref.ref_marginalize, w, 0, opts=abi.default_opts(**o))
+    po = run_marg(abi, oracle.oracle_marginalize, w, 0, opts=abi.default_opts(**o))
+    assert pr["n"] == po["n"] and 3 in pr["block_kind"]
+
+    def quad(p):
+        M = 15 * K + 7
+        cols = np.full(p["n"], -1)
+        for kind, frame, idx in zip(p["block_kind"], p["block_frame"], p["block_idx"]):
+            if kind == 0:
+                cols[idx:idx + 6] = 15 * (frame + 1) + np.arange(6)
+            elif kind == 1:
+                cols[idx:idx + 9] = 15 * (frame + 1) + 6 + np.arange(9)
+            elif kind == 2:
+                cols[idx:idx + 6] = 15 * K + np.arange(6)
+            else:
+                cols[idx] = 15 * K + 6
+        H, g = np.zeros((M, M)), np.zeros(M)
+        H[np.ix_(cols, cols)] = p["J"].T @ p["J"]
+        g[cols] = p["J"].T @ p["lin_res"]
+        return H, g
+    (Hr, gr), (Ho, go) = quad(pr), quad(po)
+    assert np.abs(Hr - Ho).max() <= 1e-7 * np.abs(Hr).max()
+    assert np.abs(gr - go).max() <= 5e-5 * max(np.abs(gr).max(), 1.0)
+    assert Hr[-1, -1] > 0
