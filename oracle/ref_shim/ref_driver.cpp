@@ -22,6 +22,8 @@ using namespace std;   // integration_base.h prints with unqualified cout / endl
 #include "factor/projection_factor.h"
 #include "factor/projection_td_factor.h"
 
+#include "utility/horizon_generator.h"
+
 #include "../../include/bvio.h"
 
 // globals of parameters.cpp that the factor code reads
@@ -299,5 +301,52 @@ int ref_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_pri
   for (int i = 0; i < n; ++i) { out->lin_res[i] = info->linearized_residuals(i); for (int j = 0; j < n; ++j) out->lin_jac[(size_t)j * n + i] = info->linearized_jacobians(i, j); }
   return 0;   // the MarginalizationInfo objects are leaked on purpose (their destructor frees with mismatched delete)
 }
+
+// HorizonGenerator::imu (utility/horizon_generator.cpp:25-70).  The reference's horizon length is the compile-time
+// constant HORIZON (state_defs.h:8).
+int ref_horizon_length(void) { return HORIZON; }
+
+void ref_horizon_imu(int H, const double pos0[3], const double quat0[4], const double ba0[3], const double pos1[3],
+                     const double quat1[4], const double vel1[3], const double acc[3], const double gyr[3], int nr_imu,
+                     double delta_imu, double* horizon_pos, double* horizon_quat) {
+  if (H != HORIZON) std::abort();
+  HorizonGenerator hg{ros::NodeHandle()};
+  state_t s0, s1;
+  s0.first.setZero(); s1.first.setZero();
+  s0.first.segment<3>(xPOS) = v3(pos0); s0.first.segment<3>(xB_A) = v3(ba0);
+  s0.second = Eigen::Quaterniond(quat0[3], quat0[0], quat0[1], quat0[2]);
+  s1.first.segment<3>(xPOS) = v3(pos1); s1.first.segment<3>(xVEL) = v3(vel1); s1.first.segment<3>(xB_A) = v3(ba0);
+  s1.second = Eigen::Quaterniond(quat1[3], quat1[0], quat1[1], quat1[2]);
+  state_horizon_t hz = hg.imu(s0, s1, v3(acc), v3(gyr), nr_imu, delta_imu);
+  for (int h = 0; h <= HORIZON; ++h) {
+    for (int i = 0; i < 3; ++i) horizon_pos[3 * h + i] = hz[h].first(xPOS + i);
+    horizon_quat[4 * h + 0] = hz[h].second.x(); horizon_quat[4 * h + 1] = hz[h].second.y();
+    horizon_quat[4 * h + 2] = hz[h].second.z(); horizon_quat[4 * h + 3] = hz[h].second.w();
+  }
+}
+
+// HorizonGenerator ground-truth mode (horizon_generator.cpp:74-123, 169-210): the constructor loads the EuRoC-style
+// csv named by the "gt_data_csv" parameter; every call advances the generator's private seek cursor.
+void* ref_horizon_gt_open(const char* csv_path) {
+  ros::NodeHandle nh;
+  nh.setParam("gt_data_csv", csv_path);
+  return new HorizonGenerator(nh);
+}
+void ref_horizon_gt(void* handle, double timestamp0, const double pos0[3], const double quat0[4], double delta_frame,
+                    double* horizon_pos, double* horizon_quat) {
+  HorizonGenerator* hg = static_cast<HorizonGenerator*>(handle);
+  state_t s0;
+  s0.first.setZero();
+  s0.first(xTIMESTAMP) = timestamp0;
+  s0.first.segment<3>(xPOS) = v3(pos0);
+  s0.second = Eigen::Quaterniond(quat0[3], quat0[0], quat0[1], quat0[2]);
+  state_horizon_t hz = hg->groundTruth(s0, s0, delta_frame);
+  for (int h = 0; h <= HORIZON; ++h) {
+    for (int i = 0; i < 3; ++i) horizon_pos[3 * h + i] = hz[h].first(xPOS + i);
+    horizon_quat[4 * h + 0] = hz[h].second.x(); horizon_quat[4 * h + 1] = hz[h].second.y();
+    horizon_quat[4 * h + 2] = hz[h].second.z(); horizon_quat[4 * h + 3] = hz[h].second.w();
+  }
+}
+void ref_horizon_gt_close(void* handle) { delete static_cast<HorizonGenerator*>(handle); }
 
 }  // extern "C"

@@ -41,5 +41,14 @@ def load():
     L.ref_projection_block_corrected.restype = None
     L.ref_prior_eval.argtypes = [C.POINTER(abi.Prior), C.POINTER(abi.WindowS), dp, dp]
     L.ref_marginalize.argtypes = [C.POINTER(abi.WindowS), C.POINTER(abi.Opts), i32, C.POINTER(abi.PriorOut)]
+    L.ref_horizon_length.restype = i32
+    L.ref_horizon_imu.argtypes = [i32, dp, dp, dp, dp, dp, dp, dp, dp, i32, d, dp, dp]
+    L.ref_horizon_imu.restype = None
+    L.ref_horizon_gt_open.argtypes = [C.c_char_p]
+    L.ref_horizon_gt_open.restype = C.c_void_p
+    L.ref_horizon_gt.argtypes = [C.c_void_p, d, dp, dp, d, dp, dp]
+    L.ref_horizon_gt.restype = None
+    L.ref_horizon_gt_close.argtypes = [C.c_void_p]
+    L.ref_horizon_gt_close.restype = None
     _lib = L
     return L

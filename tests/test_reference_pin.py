@@ -302,3 +302,61 @@ def test_margin_old_with_td_row_a9(pkg, oracle, ref):
     assert np.abs(Hr - Ho).max() <= 1e-7 * np.abs(Hr).max()
     assert np.abs(gr - go).max() <= 5e-5 * max(np.abs(gr).max(), 1.0)
     assert Hr[-1, -1] > 0
+
+
+def test_horizon_imu_row_f3(pkg, oracle, ref):
+    """HorizonGenerator::imu (utility/horizon_generator.cpp:25-70) at the reference's compile-time HORIZON."""
+    from test_horizon import _call, _inputs
+    H = ref.ref_horizon_length()
+    assert H == 13
+    for seed, nr in ((0, 20), (1, 10), (2, 33)):
+        x = _inputs(pkg, seed)
+        pr, qr = _call(pkg.abi, ref.ref_horizon_imu, H, x, nr, 0.005)
+        po, qo = _call(pkg.abi, oracle.oracle_horizon_imu, H, x, nr, 0.005)
+        assert np.abs(pr - po).max() <= 1e-13 * max(np.abs(pr).max(), 1.0) and np.abs(qr - qo).max() <= 1e-13
+
+
+def _write_euroc_csv(path, synth, seed, rate=200.0, seconds=8.0):
+    """A EuRoC-format ground-truth file (benchmark_publisher/config/*/data.csv layout) from the analytic trajectory."""
+    rng = np.random.default_rng(seed)
+    traj = synth.Trajectory(phase=rng.uniform(0, 5))
+    t0_ns = 1403636580838555648
+    with open(path, "w") as f:
+        f.write("#timestamp, p_RS_R_x [m], p_RS_R_y [m], p_RS_R_z [m], q_RS_w [], q_RS_x [], q_RS_y [], q_RS_z [], "
+                "v_RS_R_x [m s^-1], v_RS_R_y [m s^-1], v_RS_R_z [m s^-1], b_w_RS_S_x [rad s^-1], b_w_RS_S_y [rad s^-1], "
+                "b_w_RS_S_z [rad s^-1], b_a_RS_S_x [m s^-2], b_a_RS_S_y [m s^-2], b_a_RS_S_z [m s^-2]\n")
+        for k in range(int(rate * seconds)):
+            t = k / rate
+            p, q, v = traj.pos(t), synth.rot_to_quat(traj.rot(t)), traj.vel(t)
+            cells = [str(t0_ns + int(round(t * 1e9)))] + [repr(float(x)) for x in (*p, q[3], q[0], q[1], q[2], *v, -0.002, 0.02, 0.07, -0.01, 0.1, 0.05)]
+            f.write(",".join(cells) + "\n")
+    return t0_ns * 1e-9, traj
+
+
+def test_horizon_groundtruth_rows_f3_f4(pkg, ref, tmp_path):
+    """HorizonGenerator::{loadGroundTruth, groundTruth, getNextFrameTruth} (horizon_generator.cpp:74-123, 169-210) on
+    a EuRoC-format csv: the reference's class and horizon.GroundTruthHorizon walk the same frames, call after call
+    (the seek cursor persists), including the off-by-one row selection."""
+    abi, synth, hz = pkg.abi, pkg.synth, pkg.horizon
+    path = str(tmp_path / "data.csv")
+    t0, traj = _write_euroc_csv(path, synth, 7)
+    truth = hz.load_groundtruth_csv(path)
+    assert len(truth["t"]) == 1600 and abs(truth["t"][0] - t0) < 1e-6
+    assert np.allclose(truth["p"][100], traj.pos(0.5), atol=1e-12) and np.allclose(truth["v"][100], traj.vel(0.5), atol=1e-12)
+    assert np.allclose(truth["q"][100], synth.rot_to_quat(traj.rot(0.5)), atol=1e-12)
+    H = ref.ref_horizon_length()
+    mine = hz.GroundTruthHorizon(truth, H)
+    h = ref.ref_horizon_gt_open(path.encode())
+    rng = np.random.default_rng(0)
+    for frame in range(12):
+        ts = t0 + 0.5 + 0.1 * frame + rng.uniform(-0.002, 0.002)
+        pos0 = traj.pos(0.5 + 0.1 * frame) + rng.normal(0, 0.05, 3)           # the estimator's own (drifting) frame
+        quat0 = synth.rot_to_quat(traj.rot(0.5 + 0.1 * frame))
+        pr, qr = np.zeros((H + 1, 3)), np.zeros((H + 1, 4))
+        ref.ref_horizon_gt(h, ts, abi.dptr(pos0.copy()), abi.dptr(quat0.copy()), 0.1, abi.dptr(pr), abi.dptr(qr))
+        pm, qm = mine.generate(ts, pos0, quat0, 0.1)
+        assert np.abs(pr - pm).max() <= 1e-12 * max(np.abs(pr).max(), 1.0), frame
+        assert np.abs(qr - qm).max() <= 1e-12, frame
+        # relative ground-truth motion applied to the estimate: one frame ahead is about 0.1 s of travel
+        assert 0.02 < np.linalg.norm(pm[1] - pm[0]) < 0.3
+    ref.ref_horizon_gt_close(h)
