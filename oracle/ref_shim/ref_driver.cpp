@@ -23,6 +23,7 @@ using namespace std;   // integration_base.h prints with unqualified cout / endl
 #include "factor/projection_td_factor.h"
 
 #include "utility/horizon_generator.h"
+#include "feature_manager.h"
 
 #include "../../include/bvio.h"
 
@@ -30,6 +31,7 @@ using namespace std;   // integration_base.h prints with unqualified cout / endl
 double ACC_N, ACC_W, GYR_N, GYR_W;
 Eigen::Vector3d G;
 double TR, ROW, COL, TD;
+double INIT_DEPTH = 5.0, MIN_PARALLAX = 10.0 / 460.0;
 
 namespace {
 Eigen::Vector3d v3(const double* p) { return Eigen::Vector3d(p[0], p[1], p[2]); }
@@ -348,5 +350,71 @@ void ref_horizon_gt(void* handle, double timestamp0, const double pos0[3], const
   }
 }
 void ref_horizon_gt_close(void* handle) { delete static_cast<HorizonGenerator*>(handle); }
+
+// ---- FeatureManager (feature_manager.cpp) -----------------------------------------------------------------------------------
+struct RefFM {
+  Eigen::Matrix3d Rs[WINDOW_SIZE + 1];
+  Eigen::Vector3d Ps[WINDOW_SIZE + 1];
+  Eigen::Matrix3d ric[NUM_OF_CAM];
+  Eigen::Vector3d tic[NUM_OF_CAM];
+  FeatureManager fm;
+  RefFM() : fm(Rs) {}
+};
+int ref_window_size(void) { return WINDOW_SIZE; }
+void* ref_fm_create(double init_depth, double min_parallax) { INIT_DEPTH = init_depth; MIN_PARALLAX = min_parallax; return new RefFM(); }
+void ref_fm_destroy(void* h) { delete static_cast<RefFM*>(h); }
+// addFeatureCheckParallax: pts [n][7] = x y z u v vx vy; returns 1 when the second-newest frame is a keyframe (MARGIN_OLD)
+int ref_fm_add_frame(void* h, int frame_count, int n, const int32_t* ids, const double* pts, double td) {
+  map<int, vector<pair<int, Eigen::Matrix<double, 7, 1>>>> image;
+  for (int i = 0; i < n; ++i) {
+    Eigen::Matrix<double, 7, 1> v;
+    for (int k = 0; k < 7; ++k) v(k) = pts[7 * i + k];
+    image[ids[i]].emplace_back(0, v);
+  }
+  return static_cast<RefFM*>(h)->fm.addFeatureCheckParallax(frame_count, image, td) ? 1 : 0;
+}
+int ref_fm_last_track_num(void* h) { return static_cast<RefFM*>(h)->fm.last_track_num; }
+// poses [n_frames][7] (p, q xyzw) of the window's frames, extrinsic [7]
+void ref_fm_set_poses(void* h, int n_frames, const double* poses, const double* ex) {
+  RefFM* r = static_cast<RefFM*>(h);
+  for (int i = 0; i < n_frames && i <= WINDOW_SIZE; ++i) {
+    r->Ps[i] = v3(poses + 7 * i);
+    r->Rs[i] = Eigen::Quaterniond(poses[7 * i + 6], poses[7 * i + 3], poses[7 * i + 4], poses[7 * i + 5]).toRotationMatrix();
+  }
+  r->tic[0] = v3(ex);
+  r->ric[0] = Eigen::Quaterniond(ex[6], ex[3], ex[4], ex[5]).toRotationMatrix();
+  r->fm.setRic(r->ric);
+}
+void ref_fm_triangulate(void* h) { RefFM* r = static_cast<RefFM*>(h); r->fm.triangulate(r->Ps, r->tic, r->ric); }
+int ref_fm_feature_count(void* h) { return static_cast<RefFM*>(h)->fm.getFeatureCount(); }
+void ref_fm_get_depth_vector(void* h, double* out) {
+  Eigen::VectorXd d = static_cast<RefFM*>(h)->fm.getDepthVector();
+  for (int i = 0; i < d.size(); ++i) out[i] = d(i);
+}
+void ref_fm_set_depth(void* h, int n, const double* x) {
+  Eigen::VectorXd v(n);
+  for (int i = 0; i < n; ++i) v(i) = x[i];
+  static_cast<RefFM*>(h)->fm.setDepth(v);
+}
+void ref_fm_remove_failures(void* h) { static_cast<RefFM*>(h)->fm.removeFailures(); }
+// slideWindowOld with shift_depth (estimator.cpp:1089-1106): camera poses from the IMU poses of the dropped and the new frame 0
+void ref_fm_remove_back_shift_depth(void* h, const double* pose_marg, const double* pose_new) {
+  RefFM* r = static_cast<RefFM*>(h);
+  Eigen::Matrix3d back_R0 = Eigen::Quaterniond(pose_marg[6], pose_marg[3], pose_marg[4], pose_marg[5]).toRotationMatrix();
+  Eigen::Matrix3d Rs0 = Eigen::Quaterniond(pose_new[6], pose_new[3], pose_new[4], pose_new[5]).toRotationMatrix();
+  Eigen::Matrix3d R0 = back_R0 * r->ric[0], R1 = Rs0 * r->ric[0];
+  Eigen::Vector3d P0 = v3(pose_marg) + back_R0 * r->tic[0], P1 = v3(pose_new) + Rs0 * r->tic[0];
+  r->fm.removeBackShiftDepth(R0, P0, R1, P1);
+}
+void ref_fm_remove_front(void* h, int frame_count) { static_cast<RefFM*>(h)->fm.removeFront(frame_count); }
+// dump: per feature id, start_frame, number of observations, estimated_depth, solve_flag; returns the count
+int ref_fm_dump(void* h, int cap, int32_t* ids, int32_t* start, int32_t* nobs, double* depth) {
+  int k = 0;
+  for (auto& f : static_cast<RefFM*>(h)->fm.feature) {
+    if (k < cap) { ids[k] = f.feature_id; start[k] = f.start_frame; nobs[k] = (int)f.feature_per_frame.size(); depth[k] = f.estimated_depth; }
+    ++k;
+  }
+  return k;
+}
 
 }  // extern "C"

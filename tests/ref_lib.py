@@ -50,5 +50,29 @@ def load():
     L.ref_horizon_gt.restype = None
     L.ref_horizon_gt_close.argtypes = [C.c_void_p]
     L.ref_horizon_gt_close.restype = None
+    ip, vp = abi.c_int32_p, C.c_void_p
+    L.ref_window_size.restype = i32
+    L.ref_fm_create.argtypes = [d, d]
+    L.ref_fm_create.restype = vp
+    L.ref_fm_destroy.argtypes = [vp]
+    L.ref_fm_destroy.restype = None
+    L.ref_fm_add_frame.argtypes = [vp, i32, i32, ip, dp, d]
+    L.ref_fm_last_track_num.argtypes = [vp]
+    L.ref_fm_set_poses.argtypes = [vp, i32, dp, dp]
+    L.ref_fm_set_poses.restype = None
+    L.ref_fm_triangulate.argtypes = [vp]
+    L.ref_fm_triangulate.restype = None
+    L.ref_fm_feature_count.argtypes = [vp]
+    L.ref_fm_get_depth_vector.argtypes = [vp, dp]
+    L.ref_fm_get_depth_vector.restype = None
+    L.ref_fm_set_depth.argtypes = [vp, i32, dp]
+    L.ref_fm_set_depth.restype = None
+    L.ref_fm_remove_failures.argtypes = [vp]
+    L.ref_fm_remove_failures.restype = None
+    L.ref_fm_remove_back_shift_depth.argtypes = [vp, dp, dp]
+    L.ref_fm_remove_back_shift_depth.restype = None
+    L.ref_fm_remove_front.argtypes = [vp, i32]
+    L.ref_fm_remove_front.restype = None
+    L.ref_fm_dump.argtypes = [vp, i32, ip, ip, ip, dp]
     _lib = L
     return L

@@ -360,3 +360,130 @@ def test_horizon_groundtruth_rows_f3_f4(pkg, ref, tmp_path):
         # relative ground-truth motion applied to the estimate: one frame ahead is about 0.1 s of travel
         assert 0.02 < np.linalg.norm(pm[1] - pm[0]) < 0.3
     ref.ref_horizon_gt_close(h)
+
+
+def _fm_dump(ref, h, abi, cap=4096):
+    ids, st, nobs, dep = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+    n = ref.ref_fm_dump(h, cap, abi.iptr(ids), abi.iptr(st), abi.iptr(nobs), abi.dptr(dep))
+    assert n <= cap
+    return {int(i): (int(s), int(k), float(x)) for i, s, k, x in zip(ids[:n], st[:n], nobs[:n], dep[:n])}
+
+
+def test_triangulate_row_f2(pkg, oracle, ref):
+    """FeatureManager::triangulate (feature_manager.cpp:202-257) on the observations of synthetic windows, against the
+    oracle's restatement (which the CUDA tri_kernel is tested against)."""
+    abi, synth = pkg.abi, pkg.synth
+    assert ref.ref_window_size() == 10
+    for seed in range(3):
+        w = synth.make_window(seed=seed, K=11, L=120)
+        h = ref.ref_fm_create(5.0, 10.0 / 460.0)
+        per_frame = {f: [] for f in range(11)}
+        for l in range(w.L):
+            for k in range(w.lm_obs_offset[l], w.lm_obs_offset[l + 1]):
+                per_frame[int(w.obs_frame[k])].append((l, w.obs_xy[k]))
+        for f in range(11):
+            ids = np.array([l for l, _ in per_frame[f]], np.int32)
+            pts = np.zeros((len(ids), 7))
+            pts[:, :2] = [xy for _, xy in per_frame[f]]
+            pts[:, 2] = 1.0
+            ref.ref_fm_add_frame(h, f, len(ids), abi.iptr(ids), abi.dptr(pts.reshape(-1).copy()), 0.0)
+        ref.ref_fm_set_poses(h, 11, abi.dptr(w.para_pose.reshape(-1).copy()), abi.dptr(w.para_ex_pose.copy()))
+        ref.ref_fm_triangulate(h)
+        dump = _fm_dump(ref, h, abi)
+        d_or = np.zeros(w.L)
+        assert oracle.oracle_triangulate(C.byref(abi.WindowHandle(w).s), 5.0, abi.dptr(d_or)) == 0
+        d_ref = np.array([dump[l][2] for l in range(w.L)])
+        fb = d_or == 5.0
+        assert ((d_ref == 5.0) == fb).all()
+        assert np.abs(d_ref - d_or)[~fb].max() <= 1e-9 * np.abs(d_or).max()
+        assert (d_ref > 0).all() and ref.ref_fm_feature_count(h) == w.L
+        ref.ref_fm_destroy(h)
+
+
+def test_slider_bookkeeping_matches_reference_feature_manager_row_f1(pkg, oracle, ref):
+    """The closed-loop slider's host bookkeeping against the reference's FeatureManager driven with the same
+    observations, frame by frame: the keyframe decision (addFeatureCheckParallax), triangulated depths, setDepth /
+    removeFailures, and both slides (removeBackShiftDepth, removeFront) -- ids, start frames, track lengths, depths."""
+    from slider_backends import OracleBackend
+    abi, sl = pkg.abi, pkg.slider
+    h = ref.ref_fm_create(sl.INIT_DEPTH, sl.MIN_PARALLAX)
+
+    class Rec(OracleBackend):
+        def optimize(self, w, opts):
+            self.pre = w.para_pose.copy()
+            out = super().optimize(w, opts)
+            self.post_inv = out[0].inv_depth.copy()
+            return out
+
+    class Mirror(sl.SlidingWindowSim):
+        checked = {"flags": [], "tri": 0, "dumps": 0}
+
+        def _ingest(self):
+            out = super()._ingest()
+            fc = out[0]
+            self.obs_now = {lid: np.array(tr.xy[-1]) for lid, tr in self.tracks.items()
+                            if tr.alive and tr.start + len(tr.xy) - 1 == fc and len(tr.xy) >= 2}
+            return out
+
+        def build_window(self, backend=None):
+            w, feats = super().build_window(backend)
+            self.rec_feats = [(tr.lid, tr.depth) for tr in feats]
+            return w, feats
+
+        def sync_add(self, fc):
+            obs = dict(self.obs_now)
+            for lid, tr in self.tracks.items():
+                if tr.start == fc and len(tr.xy) == 1:
+                    obs[lid] = np.array(tr.xy[0])
+            ids = np.array(sorted(obs), np.int32)
+            pts = np.zeros((len(ids), 7))
+            pts[:, :2] = [obs[int(i)] for i in ids]
+            pts[:, 2] = 1.0
+            return ref.ref_fm_add_frame(h, fc, len(ids), abi.iptr(ids), abi.dptr(pts.reshape(-1).copy()), 0.0)
+
+        def hook(self, flag, be):
+            K = self.K
+            keyframe = self.sync_add(K - 1)
+            assert keyframe == (1 if flag == sl.MARGIN_OLD else 0)
+            self.checked["flags"].append(flag)
+            ex = np.concatenate([self.tic, self.qic])
+            ref.ref_fm_set_poses(h, K, abi.dptr(be.pre.reshape(-1).copy()), abi.dptr(ex))
+            ref.ref_fm_triangulate(h)
+            dump = _fm_dump(ref, h, abi)
+            order = [lid for lid, (st, k, _) in dump.items() if k >= 2 and st < sl.WINDOW_SIZE - 2]
+            assert sorted(order) == sorted(lid for lid, _ in self.rec_feats)
+            for lid, depth in self.rec_feats:                       # depths going into the solve
+                assert abs(dump[lid][2] - depth) <= 1e-8 * abs(depth), (lid, dump[lid], depth)
+                self.checked["tri"] += 1
+            inv = {lid: x for (lid, _), x in zip(self.rec_feats, be.post_inv)}
+            x = np.array([inv[lid] for lid in order])
+            ref.ref_fm_set_depth(h, len(x), abi.dptr(x))
+            ref.ref_fm_remove_failures(h)
+            if flag == sl.MARGIN_OLD:
+                ref.ref_fm_remove_back_shift_depth(h, abi.dptr(self.pose[0].copy()), abi.dptr(self.pose[1].copy()))
+            else:
+                ref.ref_fm_remove_front(h, K - 1)
+
+        def compare(self):
+            dump = _fm_dump(ref, h, abi)
+            assert set(dump) == set(self.tracks)
+            for lid, tr in self.tracks.items():
+                st, k, depth = dump[lid]
+                assert (st, k) == (tr.start, len(tr.xy)), (lid, st, k, tr.start, len(tr.xy))
+                assert abs(depth - tr.depth) <= 1e-9 * max(abs(depth), 1.0), (lid, depth, tr.depth)
+            self.checked["dumps"] += 1
+
+    be = Rec(oracle, abi)
+    sim = Mirror(seed=11, max_feats=90, max_cand=120, opts=dict(max_iters=8), keyframes="parallax", frame_dt=0.04)
+    orig_old, orig_new = sim._slide, sim._slide_new
+    sim._slide = lambda: (sim.hook(sl.MARGIN_OLD, be), orig_old())
+    sim._slide_new = lambda: (sim.hook(sl.MARGIN_SECOND_NEW, be), orig_new())
+    for _ in range(40):
+        full = len(sim.pose) == sim.K - 1 and sim.frame > 0           # this step fills the window and slides
+        sim.step(be)
+        if not full:
+            sim.sync_add(len(sim.pose) - 1)
+        sim.compare()
+    flags = np.array(sim.checked["flags"])
+    assert (flags == 0).sum() >= 8 and (flags == 1).sum() >= 8 and sim.checked["tri"] > 1000 and sim.checked["dumps"] == 40
+    ref.ref_fm_destroy(h)
