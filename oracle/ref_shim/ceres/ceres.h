@@ -37,6 +37,12 @@ class CauchyLoss : public LossFunction {
  private:
   const double b_, c_;
 };
+// named by initial/initial_sfm.h (ReprojectionError3D::Create); never instantiated here
+template <class F, int... Ns> class AutoDiffCostFunction : public CostFunction {
+ public:
+  explicit AutoDiffCostFunction(F*) {}
+  bool Evaluate(double const* const*, double*, double**) const override { return false; }
+};
 class LocalParameterization {
  public:
   virtual ~LocalParameterization() {}

@@ -24,6 +24,7 @@ using namespace std;   // integration_base.h prints with unqualified cout / endl
 
 #include "utility/horizon_generator.h"
 #include "feature_manager.h"
+#include "feature_selector.h"
 
 #include "../../include/bvio.h"
 
@@ -415,6 +416,96 @@ int ref_fm_dump(void* h, int cap, int32_t* ids, int32_t* start, int32_t* nobs, d
     ++k;
   }
   return k;
+}
+
+}  // extern "C"
+
+// ---- FeatureSelector (feature_selector.cpp) -----------------------------------------------------------------------------------
+// estimator.cpp / initial_ex_rotation.cpp are not compiled (they need the full ROS / OpenCV / Ceres stack); the selector
+// only reads data members of Estimator, so the two constructors its type needs are defined here, empty.
+Estimator::Estimator() : f_manager{Rs} {}
+InitialEXRotation::InitialEXRotation() {}
+
+namespace {
+struct RefSel {
+  Estimator est;
+  std::unique_ptr<FeatureSelector> sel;
+};
+image_t make_image(int n, const int32_t* ids, const double* xy, const double* prob) {
+  image_t image;
+  for (int i = 0; i < n; ++i) {
+    Eigen::Matrix<double, fSIZE, 1> v;
+    v.setZero();
+    v(0) = xy[2 * i]; v(1) = xy[2 * i + 1]; v(2) = 1.0; v(fPROB) = prob ? prob[i] : 1.0;
+    image[ids[i]].emplace_back(0, v);
+  }
+  return image;
+}
+}  // namespace
+
+extern "C" {
+
+void* ref_sel_create(const bvio_camera* cam, const double q_ic[4], const double t_ic[3], double acc_var, double acc_bias_var,
+                     int max_features, int init_thresh) {
+  camodocal::PinholeParams& c = camodocal::CameraFactory::registered();
+  c.fx = cam->fx; c.fy = cam->fy; c.cx = cam->cx; c.cy = cam->cy; c.k1 = cam->k1; c.k2 = cam->k2; c.p1 = cam->p1; c.p2 = cam->p2;
+  c.width = cam->width; c.height = cam->height;
+  RefSel* r = new RefSel();
+  r->est.ric[0] = Eigen::Quaterniond(q_ic[3], q_ic[0], q_ic[1], q_ic[2]).toRotationMatrix();
+  r->est.tic[0] = v3(t_ic);
+  r->est.solver_flag = Estimator::INITIAL;
+  r->sel.reset(new FeatureSelector(ros::NodeHandle(), r->est, "unused.yaml"));
+  r->sel->setParameters(acc_var, acc_bias_var, true, max_features, init_thresh, false);
+  return r;
+}
+void ref_sel_destroy(void* h) { delete static_cast<RefSel*>(h); }
+
+// back-end state the selector reads: window poses [WINDOW_SIZE+1][7] (p, q xyzw), velocity and accelerometer bias of the
+// newest frame, and the landmarks of FeatureManager (anchor observation, depth, solve_flag) for initKDTree
+void ref_sel_set_backend(void* h, const double* poses, const double* vel_last, const double* ba_last, int n_lm,
+                         const int32_t* lm_id, const int32_t* lm_start, const int32_t* lm_nobs, const double* lm_xy,
+                         const double* lm_depth, const int32_t* lm_solve_flag) {
+  RefSel* r = static_cast<RefSel*>(h);
+  for (int i = 0; i <= WINDOW_SIZE; ++i) {
+    r->est.Ps[i] = v3(poses + 7 * i);
+    r->est.Rs[i] = Eigen::Quaterniond(poses[7 * i + 6], poses[7 * i + 3], poses[7 * i + 4], poses[7 * i + 5]).toRotationMatrix();
+  }
+  r->est.Vs[WINDOW_SIZE] = v3(vel_last);
+  r->est.Bas[WINDOW_SIZE] = v3(ba_last);
+  r->est.f_manager.feature.clear();
+  for (int l = 0; l < n_lm; ++l) {
+    FeaturePerId f(lm_id[l], lm_start[l]);
+    Eigen::Matrix<double, 7, 1> pt;
+    pt.setZero(); pt(0) = lm_xy[2 * l]; pt(1) = lm_xy[2 * l + 1]; pt(2) = 1.0;
+    for (int k = 0; k < lm_nobs[l]; ++k) f.feature_per_frame.push_back(FeaturePerFrame(pt, 0.0));
+    f.estimated_depth = lm_depth[l];
+    f.solve_flag = lm_solve_flag[l];
+    r->est.f_manager.feature.push_back(f);
+  }
+}
+
+// One FeatureSelector::select().  stamp = (sec, nsec) of the image header; the state of frame k+1 as handed to
+// setNextStateFromImuPropagation.  image = n features (id, x, y, prob).  Returns the number of newly selected ids
+// (written to out_selected in selection order); *n_tracked = size of the tracked list after the call; the ids left in
+// `image` (what the back end receives) are written to out_image (capacity n), their count to *n_image.
+int ref_sel_select(void* h, int initialized, unsigned stamp_sec, unsigned stamp_nsec, const double P1[3], const double Q1[4],
+                   const double V1[3], const double a1[3], const double w1[3], const double Ba1[3], int nr_imu, int n,
+                   const int32_t* ids, const double* xy, const double* prob, int32_t* out_selected, int32_t* n_tracked,
+                   int32_t* out_image, int32_t* n_image) {
+  RefSel* r = static_cast<RefSel*>(h);
+  r->est.solver_flag = initialized ? Estimator::NON_LINEAR : Estimator::INITIAL;
+  std_msgs::Header header;
+  header.stamp.sec = stamp_sec; header.stamp.nsec = stamp_nsec;
+  r->sel->setNextStateFromImuPropagation(header.stamp.toSec(), v3(P1), Eigen::Quaterniond(Q1[3], Q1[0], Q1[1], Q1[2]), v3(V1),
+                                         v3(a1), v3(w1), v3(Ba1));
+  image_t image = make_image(n, ids, xy, prob);
+  auto res = r->sel->select(image, header, nr_imu);
+  for (size_t i = 0; i < res.second.size(); ++i) out_selected[i] = res.second[i];
+  *n_tracked = (int)res.first.size();
+  int k = 0;
+  for (const auto& f : image) out_image[k++] = f.first;
+  *n_image = k;
+  return (int)res.second.size();
 }
 
 }  // extern "C"

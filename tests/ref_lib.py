@@ -74,5 +74,12 @@ def load():
     L.ref_fm_remove_front.argtypes = [vp, i32]
     L.ref_fm_remove_front.restype = None
     L.ref_fm_dump.argtypes = [vp, i32, ip, ip, ip, dp]
+    L.ref_sel_create.argtypes = [C.POINTER(abi.Camera), dp, dp, d, d, i32, i32]
+    L.ref_sel_create.restype = vp
+    L.ref_sel_destroy.argtypes = [vp]
+    L.ref_sel_destroy.restype = None
+    L.ref_sel_set_backend.argtypes = [vp, dp, dp, dp, i32, ip, ip, ip, dp, dp, ip]
+    L.ref_sel_set_backend.restype = None
+    L.ref_sel_select.argtypes = [vp, i32, C.c_uint, C.c_uint, dp, dp, dp, dp, dp, dp, i32, i32, ip, dp, dp, ip, ip, ip, ip]
     _lib = L
     return L

@@ -487,3 +487,110 @@ def test_slider_bookkeeping_matches_reference_feature_manager_row_f1(pkg, oracle
     flags = np.array(sim.checked["flags"])
     assert (flags == 0).sum() >= 8 and (flags == 1).sum() >= 8 and sim.checked["tri"] > 1000 and sim.checked["dumps"] == 40
     ref.ref_fm_destroy(h)
+
+
+def _selector_scene(pkg, seed, N, U, C):
+    """A back-end state + one incoming image for FeatureSelector::select, in the reference's own terms."""
+    S = pkg.synth
+    rng = np.random.default_rng(seed)
+    traj = S.Trajectory(phase=rng.uniform(0, 5))
+    cam = dict(S.EUROC_CAM)
+    U_, _, Vt_ = np.linalg.svd(S.EUROC_RIC)
+    ric, tic = U_ @ Vt_, S.EUROC_TIC.copy()
+    tk = 3.0
+    times = tk - 0.1 * np.arange(10, -1, -1)
+    poses = np.array([np.concatenate([traj.pos(t), S.rot_to_quat(traj.rot(t))]) for t in times])
+    vel_k, ba_k = traj.vel(tk), rng.normal(0, 0.02, 3)
+    t1 = tk + 0.1
+    P1 = traj.pos(t1) + rng.normal(0, 0.01, 3)
+    Q1 = S.rot_to_quat(traj.rot(t1))
+    V1 = traj.vel(t1) + rng.normal(0, 0.02, 3)
+    a1 = traj.rot(t1).T @ (traj.acc(t1) + np.array([0, 0, 9.80665])) + ba_k
+    w1 = traj.omega_body(t1)
+
+    def sample_xy(n):
+        return np.array([S.lift_projective(cam, rng.uniform(0, cam["width"] - 1), rng.uniform(0, cam["height"] - 1))[:2]
+                         for _ in range(n)]).reshape(-1, 2)
+    lm = dict(id=np.arange(5000, 5000 + C, dtype=np.int32), start=rng.integers(0, 10, C).astype(np.int32),
+              nobs=rng.integers(1, 6, C).astype(np.int32), xy=sample_xy(C), depth=rng.uniform(2.0, 10.0, C),
+              flag=rng.choice([1, 1, 1, 1, 0, 2], C).astype(np.int32))
+    used_id = np.arange(1, U + 1, dtype=np.int32)
+    cand_id = (1000 + np.sort(rng.choice(4 * N, size=N, replace=False))).astype(np.int32)
+    return dict(cam=cam, ric=ric, tic=tic, qic=S.rot_to_quat(ric), poses=poses, vel_k=vel_k, ba_k=ba_k, P1=P1, Q1=Q1, V1=V1,
+                a1=a1, w1=w1, lm=lm, used_id=used_id, used_xy=sample_xy(U), cand_id=cand_id, cand_xy=sample_xy(N),
+                cand_prob=rng.uniform(0.05, 1.0, N))
+
+
+def _cloud_numpy(pkg, sc):
+    """initKDTree's dataset (feature_selector.cpp:396-421), as the host adapter builds `cloud_xy / cloud_depth`."""
+    S = pkg.synth
+    lm, xy, dep = sc["lm"], [], []
+    R1 = S.quat_to_rot(sc["Q1"])
+    for l in range(len(lm["id"])):
+        if not (lm["nobs"][l] >= 2 and lm["start"][l] < 10 - 2):
+            continue
+        if lm["start"][l] > 10 * 3.0 / 4.0 or lm["flag"][l] != 1:
+            continue
+        i = lm["start"][l]
+        Ri = S.quat_to_rot(sc["poses"][i, 3:])
+        w = Ri @ (sc["ric"] @ (np.array([lm["xy"][l, 0], lm["xy"][l, 1], 1.0]) * lm["depth"][l]) + sc["tic"]) + sc["poses"][i, :3]
+        pc = sc["ric"].T @ (R1.T @ (w - sc["P1"]) - sc["tic"])
+        xy.append(pc[:2] / pc[2])
+        dep.append(lm["depth"][l])
+    return np.array(xy).reshape(-1, 2), np.array(dep)
+
+
+@pytest.mark.parametrize("seed,N,U,n_lm,kappa", [(0, 120, 0, 60, 25), (1, 150, 12, 80, 30), (2, 60, 5, 0, 10), (3, 200, 20, 120, 40)])
+def test_select_rows_a10_to_a15(pkg, oracle, ref, seed, N, U, n_lm, kappa):
+    """FeatureSelector::select end to end (feature_selector.cpp:74-202 and everything it calls: the IMU horizon,
+    calcInfoFromRobotMotion, addOmegaPrior, initKDTree / findNNDepth through nanoflann, calcInfoFromFeatures,
+    sortedlogDetUB, the lazy greedy loop) against oracle_select on the inputs the C-ABI takes.  The selected ids must be
+    identical, in selection order."""
+    abi, S = pkg.abi, pkg.synth
+    H = ref.ref_horizon_length()
+    sc = _selector_scene(pkg, seed, N, U, n_lm)
+    cam_c = abi.Camera()
+    for k, v in sc["cam"].items():
+        if hasattr(cam_c, k):
+            setattr(cam_c, k, v)
+    f = lambda a: np.ascontiguousarray(a, np.float64)
+    h = ref.ref_sel_create(C.byref(cam_c), abi.dptr(f(sc["qic"])), abi.dptr(f(sc["tic"])), S.ACC_N, S.ACC_W, U + kappa, 0)
+    lm = sc["lm"]
+    ref.ref_sel_set_backend(h, abi.dptr(f(sc["poses"].reshape(-1))), abi.dptr(f(sc["vel_k"])), abi.dptr(f(sc["ba_k"])),
+                            len(lm["id"]), abi.iptr(lm["id"]), abi.iptr(lm["start"]), abi.iptr(lm["nobs"]),
+                            abi.dptr(f(lm["xy"].reshape(-1))), abi.dptr(f(lm["depth"])), abi.iptr(lm["flag"]))
+    state1 = [abi.dptr(f(sc[k])) for k in ("P1", "Q1", "V1", "a1", "w1", "ba_k")]
+    nr = 20
+    sel, img = np.zeros(N + U + 1, np.int32), np.zeros(N + U + 1, np.int32)
+    ntr, nimg = C.c_int32(), C.c_int32()
+    # previous frame, back end not initialised: the first image's features all become tracked (:172-181)
+    n0 = ref.ref_sel_select(h, 0, 100, 0, *state1, nr, U, abi.iptr(sc["used_id"]), abi.dptr(f(sc["used_xy"].reshape(-1))), None,
+                            abi.iptr(sel), C.byref(ntr), abi.iptr(img), C.byref(nimg))
+    assert n0 == 0 and ntr.value == U and nimg.value == U
+    # this frame: tracked + new features
+    ids = np.concatenate([sc["used_id"], sc["cand_id"]]).astype(np.int32)
+    xy = np.vstack([sc["used_xy"], sc["cand_xy"]])
+    prob = np.concatenate([np.ones(U), sc["cand_prob"]])
+    n1 = ref.ref_sel_select(h, 1, 100, 100000000, *state1, nr, len(ids), abi.iptr(ids), abi.dptr(f(xy.reshape(-1))), abi.dptr(f(prob)),
+                            abi.iptr(sel), C.byref(ntr), abi.iptr(img), C.byref(nimg))
+    ref_ids = sel[:n1].copy()
+    ref.ref_sel_destroy(h)
+    # the same problem through the C-ABI's inputs
+    delta_imu = ((100 + 1e-9 * 100000000) - (100 + 1e-9 * 0)) / nr          # header.stamp.toSec() arithmetic (:85-91)
+    hp, hq = np.zeros((H + 1, 3)), np.zeros((H + 1, 4))
+    pk, qk = f(sc["poses"][10, :3]), f(S.rot_to_quat(S.quat_to_rot(sc["poses"][10, 3:])))   # Rs[] -> Quaterniond
+    oracle.oracle_horizon_imu(H, abi.dptr(pk), abi.dptr(qk), abi.dptr(f(sc["ba_k"])), abi.dptr(f(sc["P1"])), abi.dptr(f(sc["Q1"])),
+                              abi.dptr(f(sc["V1"])), abi.dptr(f(sc["a1"])), abi.dptr(f(sc["w1"])), nr, delta_imu, abi.dptr(hp), abi.dptr(hq))
+    cl_xy, cl_d = _cloud_numpy(pkg, sc)
+    prob_o = S.SelectProblem(H=H, horizon_pos=hp, horizon_quat=hq, q_ic=sc["qic"], t_ic=sc["tic"], cam=sc["cam"], nr_imu=nr,
+                             delta_imu=delta_imu, acc_var=S.ACC_N, acc_bias_var=S.ACC_W, cand_id=sc["cand_id"], cand_xy=sc["cand_xy"],
+                             cand_prob=sc["cand_prob"], used_id=sc["used_id"], used_xy=sc["used_xy"], cloud_xy=cl_xy,
+                             cloud_depth=cl_d, kappa=kappa)
+    hs, ss = abi.SelectHandle(prob_o), abi.SelectSummary()
+    out = np.zeros(kappa, np.int32)
+    assert oracle.oracle_select(C.byref(hs.s), abi.iptr(out), None, C.byref(ss)) == 0
+    ora_ids = out[:ss.n_selected]
+    assert n1 == ss.n_selected and n1 > 0, (n1, ss.n_selected)
+    assert (ref_ids == ora_ids).all(), (ref_ids, ora_ids)
+    # bookkeeping of select(): the image handed to the back end = tracked + selected; the tracked list grew
+    assert ntr.value == U + n1 and sorted(img[:nimg.value]) == sorted(np.concatenate([sc["used_id"], ref_ids]))
