@@ -540,12 +540,10 @@ def _cloud_numpy(pkg, sc):
     return np.array(xy).reshape(-1, 2), np.array(dep)
 
 
-@pytest.mark.parametrize("seed,N,U,n_lm,kappa", [(0, 120, 0, 60, 25), (1, 150, 12, 80, 30), (2, 60, 5, 0, 10), (3, 200, 20, 120, 40)])
-def test_select_rows_a10_to_a15(pkg, oracle, ref, seed, N, U, n_lm, kappa):
-    """FeatureSelector::select end to end (feature_selector.cpp:74-202 and everything it calls: the IMU horizon,
-    calcInfoFromRobotMotion, addOmegaPrior, initKDTree / findNNDepth through nanoflann, calcInfoFromFeatures,
-    sortedlogDetUB, the lazy greedy loop) against oracle_select on the inputs the C-ABI takes.  The selected ids must be
-    identical, in selection order."""
+def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None):
+    """Runs the reference's FeatureSelector::select on a synthetic scene; returns (ids it selected, the same problem as
+    the C-ABI's bvio_select_in inputs).  The horizon for the latter comes from the numpy restatement in
+    tests/test_horizon.py unless an oracle is given."""
     abi, S = pkg.abi, pkg.synth
     H = ref.ref_horizon_length()
     sc = _selector_scene(pkg, seed, N, U, n_lm)
@@ -579,18 +577,37 @@ def test_select_rows_a10_to_a15(pkg, oracle, ref, seed, N, U, n_lm, kappa):
     delta_imu = ((100 + 1e-9 * 100000000) - (100 + 1e-9 * 0)) / nr          # header.stamp.toSec() arithmetic (:85-91)
     hp, hq = np.zeros((H + 1, 3)), np.zeros((H + 1, 4))
     pk, qk = f(sc["poses"][10, :3]), f(S.rot_to_quat(S.quat_to_rot(sc["poses"][10, 3:])))   # Rs[] -> Quaterniond
-    oracle.oracle_horizon_imu(H, abi.dptr(pk), abi.dptr(qk), abi.dptr(f(sc["ba_k"])), abi.dptr(f(sc["P1"])), abi.dptr(f(sc["Q1"])),
-                              abi.dptr(f(sc["V1"])), abi.dptr(f(sc["a1"])), abi.dptr(f(sc["w1"])), nr, delta_imu, abi.dptr(hp), abi.dptr(hq))
+    if oracle is not None:
+        oracle.oracle_horizon_imu(H, abi.dptr(pk), abi.dptr(qk), abi.dptr(f(sc["ba_k"])), abi.dptr(f(sc["P1"])), abi.dptr(f(sc["Q1"])),
+                                  abi.dptr(f(sc["V1"])), abi.dptr(f(sc["a1"])), abi.dptr(f(sc["w1"])), nr, delta_imu, abi.dptr(hp), abi.dptr(hq))
+    else:
+        from test_horizon import _numpy
+        hp, hq = _numpy(pkg, H, dict(pos0=pk, quat0=qk, ba0=f(sc["ba_k"]), pos1=f(sc["P1"]), quat1=f(sc["Q1"]), vel1=f(sc["V1"]),
+                                     acc=f(sc["a1"]), gyr=f(sc["w1"])), nr, delta_imu)
     cl_xy, cl_d = _cloud_numpy(pkg, sc)
     prob_o = S.SelectProblem(H=H, horizon_pos=hp, horizon_quat=hq, q_ic=sc["qic"], t_ic=sc["tic"], cam=sc["cam"], nr_imu=nr,
                              delta_imu=delta_imu, acc_var=S.ACC_N, acc_bias_var=S.ACC_W, cand_id=sc["cand_id"], cand_xy=sc["cand_xy"],
                              cand_prob=sc["cand_prob"], used_id=sc["used_id"], used_xy=sc["used_xy"], cloud_xy=cl_xy,
                              cloud_depth=cl_d, kappa=kappa)
+    # bookkeeping of select(): the image handed to the back end = tracked + selected; the tracked list grew
+    assert ntr.value == U + n1 and sorted(img[:nimg.value]) == sorted(np.concatenate([sc["used_id"], ref_ids]))
+    return ref_ids, prob_o
+
+
+@pytest.mark.parametrize("seed,N,U,n_lm,kappa", [(0, 120, 0, 60, 25), (1, 150, 12, 80, 30), (2, 60, 5, 0, 10), (3, 200, 20, 120, 40)])
+def test_select_rows_a10_to_a15(pkg, oracle, ref, seed, N, U, n_lm, kappa):
+    """FeatureSelector::select end to end (feature_selector.cpp:74-202 and everything it calls: the IMU horizon,
+    calcInfoFromRobotMotion, addOmegaPrior, initKDTree / findNNDepth through nanoflann, calcInfoFromFeatures,
+    sortedlogDetUB, the lazy greedy loop) against oracle_select on the inputs the C-ABI takes.  The selected ids must be
+    identical, in selection order."""
+    abi = pkg.abi
+    ref_ids, prob_o = reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=oracle)
     hs, ss = abi.SelectHandle(prob_o), abi.SelectSummary()
     out = np.zeros(kappa, np.int32)
     assert oracle.oracle_select(C.byref(hs.s), abi.iptr(out), None, C.byref(ss)) == 0
     ora_ids = out[:ss.n_selected]
-    assert n1 == ss.n_selected and n1 > 0, (n1, ss.n_selected)
+    assert len(ref_ids) == ss.n_selected and len(ref_ids) > 0, (len(ref_ids), ss.n_selected)
     assert (ref_ids == ora_ids).all(), (ref_ids, ora_ids)
-    # bookkeeping of select(): the image handed to the back end = tracked + selected; the tracked list grew
-    assert ntr.value == U + n1 and sorted(img[:nimg.value]) == sorted(np.concatenate([sc["used_id"], ref_ids]))
+    # the numpy horizon (what the GPU-vs-reference test feeds) leads to the same selection
+    ref_ids2, prob_np = reference_select_case(pkg, ref, seed, N, U, n_lm, kappa)
+    assert (ref_ids2 == ref_ids).all() and np.abs(prob_np.horizon_pos - prob_o.horizon_pos).max() < 1e-12
