@@ -1,5 +1,6 @@
 // oracle/ba_oracle.cpp -- CPU restatement of Estimator::optimization()'s numerical path.
-// TEST INFRASTRUCTURE ONLY; parity unpinned (see oracle/oracle.h).
+// TEST INFRASTRUCTURE ONLY.  Pinned against the reference's own compiled sources (oracle/_ref, tests/test_reference_pin.py)
+// except the Ceres trust-region loop, which is unpinned by reference code (see oracle/oracle.h).
 //
 // Follows, line by line where the arithmetic is observable:
 //   ProjectionFactor::Evaluate          vins_estimator/src/factor/projection_factor.cpp:21-121

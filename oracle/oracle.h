@@ -5,16 +5,31 @@
  * bench.py's cpu_baseline / --impl reference legs may load liboracle.so.  The
  * product library (libbvio.so) never includes, links or calls anything here.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- * for this path and cannot be compiled in this image (no Eigen, Ceres, ROS,
- * OpenCV).  The pins are therefore our own: (1) this C++
- * restatement and an independent numpy restatement (tests/np_ref.py) must
- * agree, (2) analytic Jacobians vs finite differences with the convention of
- * ProjectionFactor::check (projection_factor.cpp:123-225), (3) the known-answer
- * case of support_files/scripts/createMatricesLinearImuFactor.m, (4) algebraic
- * identities listed in SURVEY.md section 8c.  Ceres (trust-region loop, dogleg,
- * Schur eliminator; "tested with 1.14.0", feature_tracker/README.md:7) and
- * Eigen are un-vendored dependencies whose published algorithms are restated.
+ * PARITY: the reference ships no tests, golden vectors or fixtures for this
+ * path, and Eigen / Ceres / ROS / OpenCV are not installed in this image.
+ * The reference's own sources for the path are nevertheless compiled here,
+ * unmodified and from where they lie under /root/reference, against stand-in
+ * Eigen / Ceres / ROS headers (oracle/ref_shim/, `make -C oracle ref` ->
+ * oracle/_ref/libvins_ref.so), and tests/test_reference_pin.py checks this
+ * restatement against them row by row: projection_factor.cpp,
+ * projection_td_factor.cpp, imu_factor.h + integration_base.h,
+ * pose_local_parameterization.cpp, marginalization_factor.cpp (loss corrector,
+ * marginalize, prior factor), utility.h, feature_manager.cpp,
+ * utility/horizon_generator.cpp and feature_selector.cpp (select() end to end,
+ * with the vendored nanoflann).
+ * STILL UNPINNED BY REFERENCE CODE: row a7 -- the trust-region loop, dogleg,
+ * Schur elimination and Jacobi scaling live in Ceres ("tested with 1.14.0",
+ * feature_tracker/README.md:7), an un-vendored dependency; its published
+ * algorithm is restated and pinned by our own means only (an independent
+ * dense numpy trust-region loop, tests/np_ref.py).  The stand-in headers
+ * replace Eigen's LLT / inverse / SelfAdjointEigenSolver / JacobiSVD with plain
+ * textbook versions, and camodocal's PinholeCamera (needs OpenCV) with a
+ * restatement of its spaceToPlane: agreement there is to rounding error or by
+ * invariant (J^T J, selected ids), not bit for bit.
+ * Further pins: analytic Jacobians vs finite differences with the convention of
+ * ProjectionFactor::check (projection_factor.cpp:123-225), the known-answer
+ * case of support_files/scripts/createMatricesLinearImuFactor.m, the algebraic
+ * identities listed in SURVEY.md section 8c.
  *
  * Same structs as include/bvio.h so that the parity tests feed identical
  * inputs to both sides.

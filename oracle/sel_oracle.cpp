@@ -1,5 +1,6 @@
 // oracle/sel_oracle.cpp -- CPU restatement of FeatureSelector's numerical path.
-// TEST INFRASTRUCTURE ONLY; parity unpinned (see oracle/oracle.h).
+// TEST INFRASTRUCTURE ONLY.  Pinned against the reference's own compiled sources (oracle/_ref, tests/test_reference_pin.py)
+// except the Ceres trust-region loop, which is unpinned by reference code (see oracle/oracle.h).
 //
 // Literal restatement (dense 9(H+1) x 9(H+1) matrices, Hadamard upper bounds in a
 // std::map<double,int,greater>, lazy greedy with Cholesky log-det) of
