@@ -540,13 +540,15 @@ def _cloud_numpy(pkg, sc):
     return np.array(xy).reshape(-1, 2), np.array(dep)
 
 
-def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None):
+def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None, twins=0):
     """Runs the reference's FeatureSelector::select on a synthetic scene; returns (ids it selected, the same problem as
     the C-ABI's bvio_select_in inputs).  The horizon for the latter comes from the numpy restatement in
     tests/test_horizon.py unless an oracle is given."""
     abi, S = pkg.abi, pkg.synth
     H = ref.ref_horizon_length()
     sc = _selector_scene(pkg, seed, N, U, n_lm)
+    for k in range(0, 2 * twins, 2):                     # exact duplicates: bit-identical information and upper bound
+        sc["cand_xy"][k + 1], sc["cand_prob"][k + 1] = sc["cand_xy"][k], sc["cand_prob"][k]
     cam_c = abi.Camera()
     for k, v in sc["cam"].items():
         if hasattr(cam_c, k):
@@ -611,3 +613,21 @@ def test_select_rows_a10_to_a15(pkg, oracle, ref, seed, N, U, n_lm, kappa):
     # the numpy horizon (what the GPU-vs-reference test feeds) leads to the same selection
     ref_ids2, prob_np = reference_select_case(pkg, ref, seed, N, U, n_lm, kappa)
     assert (ref_ids2 == ref_ids).all() and np.abs(prob_np.horizon_pos - prob_o.horizon_pos).max() < 1e-12
+
+
+def test_select_duplicate_candidates_ub_collision_quirk(pkg, oracle, ref):
+    """`UBs[ub] = feature_id` (feature_selector.cpp:697-724): two candidates with bit-identical upper bounds share one
+    map slot and only the later-iterated (larger id) is considered in that round, so of two exact duplicates the larger
+    id is selected first.  The oracle reproduces this; the device resolves equal log-dets to the smaller index
+    (selector tie semantics) -- the two differ only in which of two indistinguishable twins is named."""
+    abi = pkg.abi
+    ref_ids, prob = reference_select_case(pkg, ref, 0, 60, 0, 60, 25, oracle=oracle, twins=10)
+    hs, ss = abi.SelectHandle(prob), abi.SelectSummary()
+    out = np.zeros(25, np.int32)
+    assert oracle.oracle_select(C.byref(hs.s), abi.iptr(out), None, C.byref(ss)) == 0
+    assert (out[:ss.n_selected] == ref_ids).all()
+    order = {int(i): k for k, i in enumerate(ref_ids)}
+    pairs = [(int(prob.cand_id[k]), int(prob.cand_id[k + 1])) for k in range(0, 20, 2)]
+    both = [(a, b) for a, b in pairs if a in order and b in order]
+    assert both and all(order[b] < order[a] for a, b in both)            # larger id first
+    assert all(not (a in order and b not in order) for a, b in pairs)    # never the smaller twin alone
