@@ -6,4 +6,4 @@ This package is the thin Python host used by tests and bench.py: ctypes bindings
 is not a valid identifier; import it through `__graft_entry__.load_package()`.
 There is no CPU fallback: `lib.load()` raises if libbvio.so is missing.
 """
-from . import abi, synth, lib, shard, slider, horizon  # noqa: F401
+from . import abi, synth, lib, shard, slider, horizon, replay  # noqa: F401
