@@ -299,9 +299,7 @@ class SlidingWindowSim:
         """Inputs of FeatureSelector::select for the newest frame k: ground-truth horizon (HorizonGenerator GT mode,
         horizon_generator.cpp:95-123), depth cloud = optimised landmarks seen from frame k (initKDTree,
         feature_selector.cpp:380-432), tracked set = features observed in frame k."""
-        th = self.t + self.frame_dt * np.arange(self.H + 1)
-        pos = np.stack([self.traj.pos(t) for t in th])
-        quat = np.stack([S.rot_to_quat(self.traj.rot(t)) for t in th])
+        pos, quat = self._horizon()
         new_idx = len(self.pose) - 1
         Rc, tc = self._cam_pose(self.pose[new_idx])
         cl_xy, cl_d, used_id, used_xy = [], [], [], []
@@ -324,6 +322,11 @@ class SlidingWindowSim:
                                used_id=np.array(used_id, np.int32), used_xy=np.array(used_xy, float).reshape(-1, 2),
                                cloud_xy=np.array(cl_xy, float).reshape(-1, 2), cloud_depth=np.array(cl_d, float),
                                kappa=int(kappa))
+
+    def _horizon(self):
+        """Ground-truth horizon of the simulated trajectory (HorizonGenerator GT mode)."""
+        th = self.t + self.frame_dt * np.arange(self.H + 1)
+        return np.stack([self.traj.pos(t) for t in th]), np.stack([S.rot_to_quat(self.traj.rot(t)) for t in th])
 
     def _slide(self):
         """Estimator::slideWindow MARGIN_OLD (estimator.cpp:1000-1040) + removeBackShiftDepth."""
@@ -377,6 +380,7 @@ class SlidingWindowSim:
 
     def step(self, backend):
         """Returns None while the window fills, else a dict of per-call wall times (s) and counters."""
+        self._backend = backend
         new_idx, n_tracked, cand, cxy = self._ingest()
         lat = None
         if len(self.pose) == self.K:
@@ -434,6 +438,126 @@ class SlidingWindowSim:
         return lat
 
 
+class _Scores:
+    """feature id -> detector score of the current image, indexable like World.score"""
+
+    def __init__(self):
+        self.d = {}
+
+    def __getitem__(self, idx):
+        return np.array([self.d[int(i)] for i in np.atleast_1d(idx)], dtype=float)
+
+
+class ReplaySession(SlidingWindowSim):
+    """The same window bookkeeping driven by recorded front-end traffic instead of the
+    simulator: feed it the decoded `sensor_msgs/Imu` and feature `sensor_msgs/PointCloud` messages in arrival order
+    (replay.read_dump); every feature message that `replay.get_measurements` can pair with its IMU samples becomes one
+    frame.  `init` supplies the states of the first K frames (the stand-in for the reference's visual-inertial
+    initializer, which is out of scope).  New features follow FeatureSelector's rule: only ids above the largest id seen
+    so far are candidates (feature_selector.cpp:208-219); the horizon is the IMU-mode one (backend.horizon_imu)."""
+
+    def __init__(self, cam, ric, tic, init, max_feats=150, H=10, opts=None, keyframes="parallax", td=0.0, gt=None):
+        from . import replay as RP
+        self.RP = RP
+        self.K = WINDOW_SIZE + 1
+        self.cam, self.ric, self.tic = dict(cam), np.array(ric, float), np.array(tic, float)
+        self.qic = S.rot_to_quat(self.ric)
+        self.max_feats, self.H, self.opts, self.td = max_feats, H, opts or {}, td
+        assert keyframes in ("always", "parallax")
+        self.keyframes, self.margin_flag = keyframes, MARGIN_OLD
+        self.sum_of_back = self.sum_of_front = 0
+        self.g = np.array([0, 0, S.G_NORM])
+        self.init, self.gt = init, gt
+        self.world = type("W", (), {})()
+        self.world.score = _Scores()
+        self.t, self.frame, self.frame_dt, self.n_imu = 0.0, 0, 0.1, 20
+        self.pose, self.sb = np.zeros((0, 7)), np.zeros((0, 9))
+        self.preint, self.pre_obj, self.imu_buf = [np.zeros(S.PREINT_DOUBLES)], [None], [[]]
+        self.tracks, self.prior = {}, None
+        self.last_selected, self.history = np.zeros(0, np.int32), []
+        self.last_feature_id = 0
+        self.acc_0 = self.gyr_0 = None
+        self.imu_q, self.feat_q, self.clock = [], [], RP.ImuClock()
+        self._pending = None
+
+    def feed(self, topic, msg, backend):
+        """-> list of per-frame latency dicts (see step) for the frames this message completed."""
+        (self.imu_q if topic == "imu" else self.feat_q).append(msg)
+        out = []
+        for ms, img in self.RP.get_measurements(self.imu_q, self.feat_q, self.td):
+            self._pending = (ms, img)
+            out.append(self.step(backend))
+        return out
+
+    def _gt(self, t):
+        if self.gt is not None:
+            return self.gt(t)
+        return self.pose[-1].copy(), self.sb[-1].copy()
+
+    def _ingest(self):
+        ms, img = self._pending
+        dt, acc, gyr = self.RP.imu_segment(self.clock, ms, img.stamp, self.td)
+        image = self.RP.image_from_pointcloud(img)
+        K = self.K
+        if len(self.pose) == 0:
+            p, sbv = self.init[0]
+            self.pose, self.sb = np.array(p, float)[None, :].copy(), np.array(sbv, float)[None, :].copy()
+        else:
+            ba, bg = self.sb[-1, 3:6].copy(), self.sb[-1, 6:9].copy()
+            pre = S.Preintegration(self.acc_0, self.gyr_0, ba, bg)
+            buf = []
+            for k in range(len(dt)):
+                pre.push_back(dt[k], acc[k], gyr[k])
+                buf.append((dt[k], acc[k].copy(), gyr[k].copy()))
+            Ri, Pi, Vi, T = _R(self.pose[-1, 3:]), self.pose[-1, :3], self.sb[-1, :3], pre.sum_dt
+            Pj = Pi + Vi * T - 0.5 * self.g * T * T + Ri @ pre.delta_p
+            Vj = Vi - self.g * T + Ri @ pre.delta_v
+            qj = S.quat_mul(self.pose[-1, 3:], pre.delta_q)
+            qj /= np.linalg.norm(qj)
+            pj, sj = np.concatenate([Pj, qj]), np.concatenate([Vj, ba, bg])
+            if len(self.pose) < K and self.frame in self.init:
+                pj, sj = (np.array(x, float) for x in self.init[self.frame])
+            self.pose, self.sb = np.vstack([self.pose, pj]), np.vstack([self.sb, sj])
+            self.preint.append(S.pack_preint(pre))
+            self.pre_obj.append(pre)
+            self.imu_buf.append(buf)
+            self.frame_dt, self.n_imu = img.stamp - self.t, len(ms)
+        self.acc_0, self.gyr_0 = acc[-1].copy(), gyr[-1].copy()
+        self.t = img.stamp
+        self.frame += 1
+        new_idx = len(self.pose) - 1
+        n_tracked = 0
+        for tr in self.tracks.values():
+            if not tr.alive:
+                continue
+            obs = image.get(tr.lid)
+            if obs is None:
+                tr.alive = False
+            else:
+                tr.xy.append(obs[0][1][:2].copy())
+                n_tracked += 1
+        self.margin_flag = self._keyframe_decision(new_idx, n_tracked)
+        cand = np.array(sorted(i for i in image if i > self.last_feature_id), np.int32)
+        if len(cand):
+            self.last_feature_id = int(cand[-1])
+        self.world.score.d = {int(i): float(image[int(i)][0][1][7]) for i in cand}
+        cxy = np.array([image[int(i)][0][1][:2] for i in cand]).reshape(-1, 2)
+        return new_idx, n_tracked, cand, cxy
+
+    def _start_tracks(self, new_idx, ids, cand, cxy):
+        pos = {int(c): k for k, c in enumerate(cand)}
+        for i in ids:
+            self.tracks[int(i)] = Track(lid=int(i), start=new_idx, xy=[cxy[pos[int(i)]].copy()])
+
+    def _horizon(self):
+        """IMU-mode horizon (HorizonGenerator::imu): x_k = the previous frame, x_k+1 = the newest frame, latest IMU
+        sample held constant (estimator_node.cpp:326-331)."""
+        nr = max(int(self.n_imu), 1)
+        return self._backend.horizon_imu(self.H, self.pose[-2, :3], self.pose[-2, 3:], self.sb[-2, 3:6], self.pose[-1, :3],
+                                         self.pose[-1, 3:], self.sb[-1, :3], self.acc_0, self.gyr_0 - self.sb[-1, 6:9], nr,
+                                         self.frame_dt / nr)
+
+
 class GpuBackend:
     """optimize / marginalize / select through the C-ABI of libbvio.so (host buffers in, host buffers out).
     `t_call` holds the wall time of the last FFI call alone (without the ctypes packing around it)."""
@@ -456,6 +580,14 @@ class GpuBackend:
         d = np.zeros(w.L)
         self.ctx.check(self.L.bvio_triangulate(self.ctx.h, self.C.byref(h.s), init_depth, self.abi.dptr(d)), "bvio_triangulate")
         return d
+
+    def horizon_imu(self, H, pos0, quat0, ba0, pos1, quat1, vel1, acc, gyr, nr_imu, delta_imu):
+        f = lambda a: np.ascontiguousarray(a, np.float64)
+        pos, quat = np.zeros((H + 1, 3)), np.zeros((H + 1, 4))
+        args = [self.abi.dptr(f(a)) for a in (pos0, quat0, ba0, pos1, quat1, vel1, acc, gyr)]
+        self.ctx.check(self.L.bvio_horizon_imu(self.ctx.h, H, *args, nr_imu, delta_imu, self.abi.dptr(pos), self.abi.dptr(quat)),
+                       "bvio_horizon_imu")
+        return pos, quat
 
     def marginalize(self, w, flag):
         out = self.abi.call_marginalize(self.L.bvio_marginalize, w, flag, ctx=self.ctx.h)

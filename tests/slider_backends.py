@@ -22,6 +22,13 @@ class OracleBackend:
         assert self.orc.oracle_triangulate(C.byref(h.s), init_depth, self.abi.dptr(d)) == 0
         return d
 
+    def horizon_imu(self, H, pos0, quat0, ba0, pos1, quat1, vel1, acc, gyr, nr_imu, delta_imu):
+        f = lambda a: np.ascontiguousarray(a, np.float64)
+        pos, quat = np.zeros((H + 1, 3)), np.zeros((H + 1, 4))
+        args = [self.abi.dptr(f(a)) for a in (pos0, quat0, ba0, pos1, quat1, vel1, acc, gyr)]
+        self.orc.oracle_horizon_imu(H, *args, nr_imu, delta_imu, self.abi.dptr(pos), self.abi.dptr(quat))
+        return pos, quat
+
     def marginalize(self, w, flag):
         return self.abi.call_marginalize(self.orc.oracle_marginalize, w, flag)
 

@@ -119,3 +119,84 @@ def test_replayed_segments_feed_the_preintegration_oracle(pkg, oracle):
         pa, pg = acc[k].copy(), gyr[k].copy()
     got = np.frombuffer(bytes(c), dtype=np.float64)
     assert abs(got[16] - 0.1) < 1e-9 and np.allclose(got[:17], S.pack_preint(pre)[:17], rtol=1e-12, atol=1e-14)
+
+
+def _record_session(pkg, path, seed, frames=26, imu_rate=200, frame_dt=0.1):
+    """An independent front-end stand-in: 200 Hz IMU messages and, per camera frame, one feature message with every
+    visible landmark (tracker-style ids: consecutive integers in order of first detection).  Written as a dump file."""
+    S, sl, rp = pkg.synth, pkg.slider, pkg.replay
+    rng = np.random.default_rng(seed)
+    traj = S.Trajectory(phase=rng.uniform(0, 5))
+    world = sl.World(rng, n=9000)
+    U_, _, Vt_ = np.linalg.svd(S.EUROC_RIC)
+    ric, tic = U_ @ Vt_, S.EUROC_TIC.copy()
+    ba, bg, g = rng.normal(0, 0.02, 3), rng.normal(0, 0.002, 3), np.array([0, 0, S.G_NORM])
+    t_ros = 1000.0                                              # ROS time of trajectory time 1.0
+    n_per = int(round(frame_dt * imu_rate))
+    recs, tracker_id, next_id, init = [], {}, 1, {}
+    prev_xy = {}
+
+    def stamp(t):
+        sec = int(t)
+        return sec, int(round((t - sec) * 1e9))
+    k_imu = 0
+    for f in range(frames):
+        tf = 1.0 + f * frame_dt + 0.0013                        # camera 1.3 ms off the IMU grid
+        while 1.0 + k_imu / imu_rate <= tf + 1.5 / imu_rate:   # IMU messages up to just past the image
+            t = 1.0 + k_imu / imu_rate
+            R = traj.rot(t)
+            acc = R.T @ (traj.acc(t) + g) + ba + rng.normal(0, S.ACC_N, 3)
+            gyr = traj.omega_body(t) + bg + rng.normal(0, S.GYR_N, 3)
+            recs.append(("imu", rp.encode_imu(rp.ImuMsg(k_imu, *stamp(t_ros + t - 1.0), "imu", np.array([0, 0, 0, 1.0]), gyr, acc))))
+            k_imu += 1
+        R, p = traj.rot(tf), traj.pos(tf)
+        ids, xy, _ = world.observe(S.EUROC_CAM, R @ ric, p + R @ tic)
+        fid = []
+        for i in ids.tolist():
+            if i not in tracker_id:
+                tracker_id[i] = next_id
+                next_id += 1
+            fid.append(tracker_id[i])
+        order = np.argsort(fid)
+        fid, xy, lid = np.array(fid)[order], xy[order] + rng.normal(0, 0.5 / 460.0, (len(order), 2)), ids[order]
+        vel = np.array([(xy[j] - prev_xy[l]) / frame_dt if l in prev_xy else (0.0, 0.0) for j, l in enumerate(lid.tolist())]).reshape(-1, 2)
+        prev_xy = {l: xy[j] for j, l in enumerate(lid.tolist())}
+        recs.append(("feature", rp.encode_pointcloud(rp.pointcloud_from_features(f, *stamp(t_ros + tf - 1.0), fid, xy, np.zeros((len(fid), 2)),
+                                                                                 vel, world.score[lid]))))
+        if f < 11:                                              # what the initializer would deliver
+            init[f] = (np.concatenate([p + rng.normal(0, 0.02, 3), S.rot_to_quat(R)]),
+                       np.concatenate([traj.vel(tf) + rng.normal(0, 0.05, 3), ba + rng.normal(0, 0.01, 3), bg + rng.normal(0, 0.001, 3)]))
+    rp.write_dump(path, recs)
+    gt = lambda t: (np.concatenate([traj.pos(t - t_ros + 1.0), S.rot_to_quat(traj.rot(t - t_ros + 1.0))]), np.zeros(9))
+    return dict(ric=ric, tic=tic, init=init, gt=gt, n_frames=frames, n_ids=next_id - 1)
+
+
+def test_recorded_session_replays_through_the_backend(pkg, oracle, tmp_path):
+    """Dump -> decode -> measurement pairing -> window bookkeeping -> optimize / marginalize / select (oracle backend
+    here; slider.GpuBackend in the product): the estimate follows the recorded trajectory, the budget holds, only ids
+    newer than everything seen before are ever selected."""
+    from slider_backends import OracleBackend
+    sl, rp, S = pkg.slider, pkg.replay, pkg.synth
+    path = str(tmp_path / "session.bvio")
+    rec = _record_session(pkg, path, seed=4)
+    ses = sl.ReplaySession(S.EUROC_CAM, rec["ric"], rec["tic"], rec["init"], max_feats=70, H=10, opts=dict(max_iters=8),
+                           keyframes="parallax", gt=rec["gt"])
+    be = OracleBackend(oracle, pkg.abi)
+    lats, n_new = [], 0
+    for topic, msg in rp.read_dump(path):
+        before, known = ses.last_feature_id, set(ses.tracks)
+        for lat in ses.feed(topic, msg, be):
+            if lat is not None:
+                lats.append(lat)
+            started = set(ses.tracks) - known
+            assert all(i > before for i in started), (before, started)       # only never-seen-before ids are selectable
+            n_new += len(started)
+            before, known = ses.last_feature_id, set(ses.tracks)
+    assert n_new > 70
+    assert ses.frame == rec["n_frames"] - 1 or ses.frame == rec["n_frames"]      # the last image may still wait for IMU
+    assert len(lats) >= ses.frame - 10 - 1 and all(l["iterations"] >= 1 and l["L"] >= 15 for l in lats[2:])
+    errs = np.array([h[1] for h in ses.history])
+    assert errs[-5:].max() < 0.3, errs
+    assert ses.prior is not None and ses.prior["n"] in (69, 75)
+    assert sum(1 for tr in ses.tracks.values() if tr.alive) <= 70
+    assert abs(ses.frame_dt - 0.1) < 1e-6 and ses.n_imu in (20, 21, 22)
