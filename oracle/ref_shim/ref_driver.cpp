@@ -33,6 +33,10 @@ double ACC_N, ACC_W, GYR_N, GYR_W;
 Eigen::Vector3d G;
 double TR, ROW, COL, TD;
 double INIT_DEPTH = 5.0, MIN_PARALLAX = 10.0 / 460.0;
+int ESTIMATE_EXTRINSIC = 0, ESTIMATE_TD = 0, NUM_ITERATIONS = 8;
+double SOLVER_TIME = 0.04;
+std::vector<Eigen::Matrix3d> RIC;
+std::vector<Eigen::Vector3d> TIC;
 
 namespace {
 Eigen::Vector3d v3(const double* p) { return Eigen::Vector3d(p[0], p[1], p[2]); }
@@ -423,8 +427,13 @@ int ref_fm_dump(void* h, int cap, int32_t* ids, int32_t* start, int32_t* nobs, d
 // ---- FeatureSelector (feature_selector.cpp) -----------------------------------------------------------------------------------
 // estimator.cpp / initial_ex_rotation.cpp are not compiled (they need the full ROS / OpenCV / Ceres stack); the selector
 // only reads data members of Estimator, so the two constructors its type needs are defined here, empty.
-Estimator::Estimator() : f_manager{Rs} {}
 InitialEXRotation::InitialEXRotation() {}
+// the initializer (initial/*.cpp: OpenCV-based SfM and alignment) is out of scope and never reached by the driver
+GlobalSFM::GlobalSFM() {}
+bool GlobalSFM::construct(int, Quaterniond*, Vector3d*, int, const Matrix3d, const Vector3d, vector<SFMFeature>&, map<int, Vector3d>&) { std::abort(); }
+bool InitialEXRotation::CalibrationExRotation(vector<pair<Vector3d, Vector3d>>, Quaterniond, Matrix3d&) { std::abort(); }
+bool VisualIMUAlignment(map<double, ImageFrame>&, Vector3d*, Vector3d&, VectorXd&) { std::abort(); }
+bool MotionEstimator::solveRelativeRT(const vector<pair<Vector3d, Vector3d>>&, Matrix3d&, Vector3d&) { std::abort(); }
 
 namespace {
 struct RefSel {
@@ -506,6 +515,211 @@ int ref_sel_select(void* h, int initialized, unsigned stamp_sec, unsigned stamp_
   for (const auto& f : image) out_image[k++] = f.first;
   *n_image = k;
   return (int)res.second.size();
+}
+
+}  // extern "C"
+
+
+// ---- Estimator::optimization() around an injected solve (estimator.cpp:477-610, 661-994) -----------------------------------------
+namespace {
+struct EstHook {
+  Estimator* est = nullptr;
+  const double *inj_pose = nullptr, *inj_sb = nullptr, *inj_ex = nullptr, *inj_feat = nullptr, *inj_td = nullptr;
+  double *entry_pose = nullptr, *entry_sb = nullptr, *entry_ex = nullptr, *entry_feat = nullptr;
+  double entry_cost = 0;
+  int counts[8] = {0};    // prior, imu, projection, projection_td, other, ex constant, parameter blocks, residual blocks
+  int options[4] = {0};   // max_num_iterations, DOGLEG?, DENSE_SCHUR?, _
+  double max_time = 0;
+  int L = 0;
+  std::vector<double> H, g;   // normal equations of the whole problem at entry, local coordinates
+  int dim = 0;
+} g_hook;
+
+void est_solve_hook(const ceres::Solver::Options& o, ceres::Problem* pb, ceres::Solver::Summary*) {
+  EstHook& h = g_hook;
+  Estimator& e = *h.est;
+  memcpy(h.entry_pose, e.para_Pose, sizeof(double) * 7 * (WINDOW_SIZE + 1));
+  memcpy(h.entry_sb, e.para_SpeedBias, sizeof(double) * 9 * (WINDOW_SIZE + 1));
+  memcpy(h.entry_ex, e.para_Ex_Pose, sizeof(double) * 7);
+  for (int l = 0; l < h.L; ++l) h.entry_feat[l] = e.para_Feature[l][0];
+  // the objective Ceres would minimise, through the reference's own cost functions: 1/2 sum rho(|r|^2)
+  double cost = 0;
+  for (auto& rb : pb->residual_blocks) {
+    std::vector<double> r(rb.cost->num_residuals());
+    rb.cost->Evaluate(rb.blocks.data(), r.data(), nullptr);
+    double s = 0; for (double x : r) s += x * x;
+    if (rb.loss) { double rho[3]; rb.loss->Evaluate(s, rho); cost += 0.5 * rho[0]; } else cost += 0.5 * s;
+    if (dynamic_cast<MarginalizationFactor*>(rb.cost)) h.counts[0]++;
+    else if (dynamic_cast<IMUFactor*>(rb.cost)) h.counts[1]++;
+    else if (dynamic_cast<ProjectionFactor*>(rb.cost)) h.counts[2]++;
+    else if (dynamic_cast<ProjectionTdFactor*>(rb.cost)) h.counts[3]++;
+    else h.counts[4]++;
+  }
+  h.entry_cost = cost;
+  // Gauss-Newton normal equations J^T J, J^T r of the whole problem at entry, every block evaluated and loss-corrected
+  // by the reference's own ResidualBlockInfo::Evaluate.  Local column layout: frame-major [pose 6 | speed-bias 9] x K,
+  // extrinsic 6, td 1, then one column per feature.
+  {
+    const int K1 = WINDOW_SIZE + 1, npar = 15 * K1 + 7, dim = npar + h.L;
+    auto col_of = [&](double* p, int* size) {
+      for (int i = 0; i < K1; ++i) { if (p == e.para_Pose[i]) { *size = 6; return 15 * i; } if (p == e.para_SpeedBias[i]) { *size = 9; return 15 * i + 6; } }
+      if (p == e.para_Ex_Pose[0]) { *size = 6; return 15 * K1; }
+      if (p == e.para_Td[0]) { *size = 1; return 15 * K1 + 6; }
+      for (int l = 0; l < h.L; ++l) if (p == e.para_Feature[l]) { *size = 1; return npar + l; }
+      *size = 0; return -1;
+    };
+    h.dim = dim; h.H.assign((size_t)dim * dim, 0.0); h.g.assign(dim, 0.0);
+    for (auto& rb : pb->residual_blocks) {
+      ResidualBlockInfo info(rb.cost, rb.loss, rb.blocks, std::vector<int>{});
+      info.Evaluate();
+      const int nr = rb.cost->num_residuals(), nb = (int)rb.blocks.size();
+      std::vector<int> c0(nb), sz(nb);
+      for (int b = 0; b < nb; ++b) c0[b] = col_of(rb.blocks[b], &sz[b]);
+      for (int a = 0; a < nb; ++a) {
+        if (c0[a] < 0) continue;
+        for (int i = 0; i < sz[a]; ++i) {
+          double gi = 0; for (int r = 0; r < nr; ++r) gi += info.jacobians[a](r, i) * info.residuals(r);
+          h.g[c0[a] + i] += gi;
+          for (int b = 0; b < nb; ++b) {
+            if (c0[b] < 0) continue;
+            for (int j = 0; j < sz[b]; ++j) {
+              double v = 0; for (int r = 0; r < nr; ++r) v += info.jacobians[a](r, i) * info.jacobians[b](r, j);
+              h.H[(size_t)(c0[a] + i) * dim + c0[b] + j] += v;
+            }
+          }
+        }
+      }
+      delete[] info.raw_jacobians;
+    }
+  }
+  for (auto& b : pb->parameter_blocks) if (b.ptr == e.para_Ex_Pose[0] && b.constant) h.counts[5] = 1;
+  h.counts[6] = (int)pb->parameter_blocks.size(); h.counts[7] = (int)pb->residual_blocks.size();
+  h.options[0] = o.max_num_iterations; h.options[1] = o.trust_region_strategy_type == ceres::DOGLEG;
+  h.options[2] = o.linear_solver_type == ceres::DENSE_SCHUR; h.max_time = o.max_solver_time_in_seconds;
+  // "the solve": overwrite the parameter blocks with the solution computed elsewhere
+  memcpy(e.para_Pose, h.inj_pose, sizeof(double) * 7 * (WINDOW_SIZE + 1));
+  memcpy(e.para_SpeedBias, h.inj_sb, sizeof(double) * 9 * (WINDOW_SIZE + 1));
+  memcpy(e.para_Ex_Pose, h.inj_ex, sizeof(double) * 7);
+  for (int l = 0; l < h.L; ++l) e.para_Feature[l][0] = h.inj_feat[l];
+  if (h.inj_td) e.para_Td[0][0] = h.inj_td[0];
+}
+}  // namespace
+
+extern "C" {
+
+// Normal equations of the problem the last ref_estimator_optimization() call handed to Ceres (see est_solve_hook)
+int ref_estimator_last_normal(double* H, double* g, int cap_dim) {
+  if (g_hook.dim > cap_dim) return -g_hook.dim;
+  std::copy(g_hook.H.begin(), g_hook.H.end(), H);
+  std::copy(g_hook.g.begin(), g_hook.g.end(), g);
+  return g_hook.dim;
+}
+
+// Runs the reference's Estimator::optimization() on a window (K must be WINDOW_SIZE + 1) with ceres::Solve replaced by
+// "write `solved` into the parameter blocks".  entry_* = what vector2double() produced; scal = {objective at entry,
+// max_solver_time}; counts / options as filled by the hook; post_* = Ps / Rs (row-major 3x3) / Vs / Bas / Bgs, extrinsic
+// (tic, ric row-major), td, per-landmark estimated_depth after double2vector(); prior = the new
+// last_marginalization_info (n = -1 when the reference kept the old one).
+int ref_estimator_optimization(const bvio_window* w, const bvio_opts* o, int flag, const bvio_window* solved, double* entry_pose,
+                               double* entry_sb, double* entry_ex, double* entry_feat, double* scal, int32_t* counts, int32_t* options,
+                               double* post_P, double* post_R, double* post_V, double* post_Ba, double* post_Bg, double* post_ex,
+                               double* post_td, double* post_depth, bvio_prior_out* prior) {
+  if (w->K != WINDOW_SIZE + 1 || w->L > NUM_OF_F) return -1;
+  const int K = w->K, L = w->L;
+  ESTIMATE_EXTRINSIC = o->estimate_extrinsic; ESTIMATE_TD = o->estimate_td; NUM_ITERATIONS = o->max_iters;
+  SOLVER_TIME = o->max_time_s; TD = w->para_td ? w->para_td[0] : 0.0; TR = o->TR; ROW = o->ROW; G = v3(o->G);
+  void* mem = calloc(1, sizeof(Estimator));            // the reference's Estimator lives in zero-initialised static storage
+  Estimator* e = new (mem) Estimator();
+  ProjectionFactor::sqrt_info = o->focal_length / 1.5 * Eigen::Matrix2d::Identity();
+  ProjectionTdFactor::sqrt_info = o->focal_length / 1.5 * Eigen::Matrix2d::Identity();
+  for (int i = 0; i < K; ++i) {
+    const double* p = w->para_pose + 7 * i; const double* s = w->para_speed_bias + 9 * i;
+    e->Ps[i] = v3(p); e->Rs[i] = Eigen::Quaterniond(p[6], p[3], p[4], p[5]).toRotationMatrix();
+    e->Vs[i] = v3(s); e->Bas[i] = v3(s + 3); e->Bgs[i] = v3(s + 6);
+    if (i >= 1) {
+      e->pre_integrations[i] = new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), v3(w->preint[i].lin_ba), v3(w->preint[i].lin_bg));
+      load(*e->pre_integrations[i], &w->preint[i]);
+    }
+  }
+  e->tic[0] = v3(w->para_ex_pose);
+  e->ric[0] = Eigen::Quaterniond(w->para_ex_pose[6], w->para_ex_pose[3], w->para_ex_pose[4], w->para_ex_pose[5]).toRotationMatrix();
+  e->f_manager.setRic(e->ric);
+  e->td = TD;
+  e->frame_count = WINDOW_SIZE; e->solver_flag = Estimator::NON_LINEAR;
+  e->marginalization_flag = flag == 0 ? Estimator::MARGIN_OLD : Estimator::MARGIN_SECOND_NEW;
+  for (int l = 0; l < L; ++l) {
+    int o0 = w->lm_obs_offset[l], o1 = w->lm_obs_offset[l + 1];
+    FeaturePerId f(l, w->obs_frame[o0]);
+    for (int k = o0; k < o1; ++k) {
+      Eigen::Matrix<double, 7, 1> pt;
+      pt.setZero(); pt(0) = w->obs_xy[2 * k]; pt(1) = w->obs_xy[2 * k + 1]; pt(2) = 1.0;
+      if (w->obs_vel) { pt(4) = w->obs_row[k]; pt(5) = w->obs_vel[2 * k]; pt(6) = w->obs_vel[2 * k + 1]; }
+      f.feature_per_frame.push_back(FeaturePerFrame(pt, w->obs_td ? w->obs_td[k] : 0.0));
+    }
+    f.estimated_depth = 1.0 / w->inv_depth[l];
+    f.solve_flag = 1;
+    e->f_manager.feature.push_back(f);
+  }
+  std::vector<double> x0;
+  if (w->prior) {
+    const bvio_prior* pr = w->prior;
+    MarginalizationInfo* info = new MarginalizationInfo();
+    info->n = pr->n; info->m = 0;
+    int tot = 0; for (int b = 0; b < pr->nblocks; ++b) tot += global_size(pr->block_kind[b]);
+    x0.assign(pr->x0, pr->x0 + tot);
+    int off = 0;
+    for (int b = 0; b < pr->nblocks; ++b) {
+      int kind = pr->block_kind[b], fr = pr->block_frame[b], gs = global_size(kind);
+      info->keep_block_size.push_back(gs); info->keep_block_idx.push_back(pr->block_idx[b]); info->keep_block_data.push_back(x0.data() + off);
+      e->last_marginalization_parameter_blocks.push_back(kind == BVIO_BLK_POSE ? e->para_Pose[fr] : kind == BVIO_BLK_SPEEDBIAS ? e->para_SpeedBias[fr]
+                                                         : kind == BVIO_BLK_EXPOSE ? e->para_Ex_Pose[0] : e->para_Td[0]);
+      off += gs;
+    }
+    info->linearized_jacobians.resize(pr->n, pr->n); info->linearized_residuals.resize(pr->n);
+    for (int i = 0; i < pr->n; ++i) { info->linearized_residuals(i) = pr->lin_res[i]; for (int j = 0; j < pr->n; ++j) info->linearized_jacobians(i, j) = pr->lin_jac[(size_t)j * pr->n + i]; }
+    e->last_marginalization_info = info;
+  }
+  MarginalizationInfo* before = e->last_marginalization_info;
+  g_hook = EstHook();
+  g_hook.est = e; g_hook.L = L;
+  g_hook.inj_pose = solved->para_pose; g_hook.inj_sb = solved->para_speed_bias; g_hook.inj_ex = solved->para_ex_pose;
+  g_hook.inj_feat = solved->inv_depth; g_hook.inj_td = o->estimate_td ? solved->para_td : nullptr;
+  g_hook.entry_pose = entry_pose; g_hook.entry_sb = entry_sb; g_hook.entry_ex = entry_ex; g_hook.entry_feat = entry_feat;
+  ceres::solve_hook() = est_solve_hook;
+  e->optimization();
+  ceres::solve_hook() = nullptr;
+  scal[0] = g_hook.entry_cost; scal[1] = g_hook.max_time;
+  for (int i = 0; i < 8; ++i) counts[i] = g_hook.counts[i];
+  for (int i = 0; i < 4; ++i) options[i] = g_hook.options[i];
+  for (int i = 0; i < K; ++i) {
+    for (int a = 0; a < 3; ++a) { post_P[3 * i + a] = e->Ps[i](a); post_V[3 * i + a] = e->Vs[i](a); post_Ba[3 * i + a] = e->Bas[i](a); post_Bg[3 * i + a] = e->Bgs[i](a); }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) post_R[9 * i + 3 * a + b] = e->Rs[i](a, b);
+  }
+  for (int a = 0; a < 3; ++a) post_ex[a] = e->tic[0](a);
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) post_ex[3 + 3 * a + b] = e->ric[0](a, b);
+  post_td[0] = e->td;
+  { int l = 0; for (auto& f : e->f_manager.feature) post_depth[l++] = f.estimated_depth; }
+  // the new prior
+  MarginalizationInfo* info = e->last_marginalization_info;
+  if (info == before || info == nullptr) { prior->n = -1; prior->nblocks = 0; return 0; }
+  int n = info->n, nb = (int)e->last_marginalization_parameter_blocks.size();
+  if (n > prior->cap_n || nb > prior->cap_blocks) return -4;
+  prior->n = n; prior->nblocks = nb;
+  int off = 0;
+  for (int b = 0; b < nb; ++b) {
+    double* p = e->last_marginalization_parameter_blocks[b];
+    int kind = -1, frame = 0;
+    for (int i = 0; i < K; ++i) { if (p == e->para_Pose[i]) { kind = BVIO_BLK_POSE; frame = i; } if (p == e->para_SpeedBias[i]) { kind = BVIO_BLK_SPEEDBIAS; frame = i; } }
+    if (p == e->para_Ex_Pose[0]) kind = BVIO_BLK_EXPOSE;
+    if (p == e->para_Td[0]) kind = BVIO_BLK_TD;
+    if (kind < 0) return -5;
+    prior->block_kind[b] = kind; prior->block_frame[b] = frame; prior->block_idx[b] = info->keep_block_idx[b] - info->m;
+    int gs = info->keep_block_size[b];
+    for (int i = 0; i < gs; ++i) prior->x0[off + i] = info->keep_block_data[b][i];
+    off += gs;
+  }
+  for (int i = 0; i < n; ++i) { prior->lin_res[i] = info->linearized_residuals(i); for (int j = 0; j < n; ++j) prior->lin_jac[(size_t)j * n + i] = info->linearized_jacobians(i, j); }
+  return 0;    // the Estimator and its MarginalizationInfo objects are leaked on purpose (see ref_marginalize)
 }
 
 }  // extern "C"

@@ -81,5 +81,8 @@ def load():
     L.ref_sel_set_backend.argtypes = [vp, dp, dp, dp, i32, ip, ip, ip, dp, dp, ip]
     L.ref_sel_set_backend.restype = None
     L.ref_sel_select.argtypes = [vp, i32, C.c_uint, C.c_uint, dp, dp, dp, dp, dp, dp, i32, i32, ip, dp, dp, ip, ip, ip, ip]
+    W, O = C.POINTER(abi.WindowS), C.POINTER(abi.Opts)
+    L.ref_estimator_optimization.argtypes = [W, O, i32, W, dp, dp, dp, dp, dp, ip, ip, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(abi.PriorOut)]
+    L.ref_estimator_last_normal.argtypes = [dp, dp, i32]
     _lib = L
     return L

@@ -631,3 +631,126 @@ def test_select_duplicate_candidates_ub_collision_quirk(pkg, oracle, ref):
     both = [(a, b) for a, b in pairs if a in order and b in order]
     assert both and all(order[b] < order[a] for a, b in both)            # larger id first
     assert all(not (a in order and b not in order) for a, b in pairs)    # never the smaller twin alone
+
+
+def _run_reference_optimization(pkg, ref, w, solved, flag, **opts_kw):
+    abi = pkg.abi
+    K, L = w.K, w.L
+    hw, hs = abi.WindowHandle(w), abi.WindowHandle(solved)
+    o = abi.default_opts(**opts_kw)
+    e_pose, e_sb, e_ex, e_feat, scal = np.zeros((K, 7)), np.zeros((K, 9)), np.zeros(7), np.zeros(L), np.zeros(2)
+    counts, options = np.zeros(8, np.int32), np.zeros(4, np.int32)
+    P, R, V, Ba, Bg = np.zeros((K, 3)), np.zeros((K, 3, 3)), np.zeros((K, 3)), np.zeros((K, 3)), np.zeros((K, 3))
+    ex, td, depth = np.zeros(12), np.zeros(1), np.zeros(L)
+    cap_n, cap_b = 15 * K + 16, 2 * K + 2
+    bk, bf, bi = (np.zeros(cap_b, np.int32) for _ in range(3))
+    x0, jac, res = np.zeros(9 * cap_b), np.zeros(cap_n * cap_n), np.zeros(cap_n)
+    out = abi.PriorOut()
+    out.block_kind, out.block_frame, out.block_idx = abi.iptr(bk), abi.iptr(bf), abi.iptr(bi)
+    out.x0, out.lin_jac, out.lin_res = abi.dptr(x0), abi.dptr(jac), abi.dptr(res)
+    out.cap_n, out.cap_blocks = cap_n, cap_b
+    rc = ref.ref_estimator_optimization(C.byref(hw.s), C.byref(o), flag, C.byref(hs.s), abi.dptr(e_pose), abi.dptr(e_sb), abi.dptr(e_ex),
+                                        abi.dptr(e_feat), abi.dptr(scal), abi.iptr(counts), abi.iptr(options), abi.dptr(P), abi.dptr(R),
+                                        abi.dptr(V), abi.dptr(Ba), abi.dptr(Bg), abi.dptr(ex), abi.dptr(td), abi.dptr(depth), C.byref(out))
+    assert rc == 0, rc
+    prior = None
+    if out.n >= 0:
+        n, nb = out.n, out.nblocks
+        prior = dict(n=n, block_kind=bk[:nb].copy(), block_frame=bf[:nb].copy(), block_idx=bi[:nb].copy(), x0=x0.copy(),
+                     lin_jac=jac[:n * n].copy(), lin_res=res[:n].copy(), J=jac[:n * n].reshape(n, n, order="F").copy())
+    return dict(entry_pose=e_pose, entry_sb=e_sb, entry_ex=e_ex, entry_feat=e_feat, entry_cost=scal[0], max_time=scal[1],
+                counts=counts, options=options, P=P, R=R, V=V, Ba=Ba, Bg=Bg, ex=ex, td=td[0], depth=depth, prior=prior)
+
+
+@pytest.mark.parametrize("seed,L,strategy,ex,td,flag", [(0, 80, 1, 0, 0, 0), (1, 150, 0, 0, 0, 0), (2, 60, 1, 1, 0, 0),
+                                                        (3, 60, 1, 0, 1, 0), (4, 80, 1, 1, 1, 1)])
+def test_estimator_optimization_around_the_solve_rows_a1_a8_a9(pkg, oracle, ref, seed, L, strategy, ex, td, flag):
+    """The reference's Estimator::optimization() (estimator.cpp:661-994) with ceres::Solve replaced by 'write the
+    oracle's solution into the parameter blocks': vector2double (a1), the problem the reference hands to Ceres (which
+    residual blocks, which loss, the constant extrinsic, the solver options) and its objective at entry, double2vector
+    (a8: yaw / position gauge, setDepth), and the marginalization that follows (a9, the reference's own glue)."""
+    abi, synth = pkg.abi, pkg.synth
+    K = 11
+    tdkw = dict(td_true=0.003) if td else {}
+    o_kw = dict(strategy=strategy, max_iters=8, max_time_s=0.04, estimate_extrinsic=ex, estimate_td=td, TR=0.01 if td else 0.0)
+    w0 = synth.make_window(seed=seed, K=K, L=L, **tdkw)
+    keys = ("n", "block_kind", "block_frame", "block_idx", "x0", "lin_jac", "lin_res")
+    p0 = run_marg(abi, oracle.oracle_marginalize, w0, 0, opts=abi.default_opts(**o_kw))   # a full-size prior (poses 0..9, td)
+    w = dataclasses.replace(synth.make_window(seed=seed + 100, K=K, L=L, **tdkw), prior={k: p0[k] for k in keys})
+    if td:
+        w.para_td[0] = 0.001
+    hs, summ = abi.WindowHandle(w.copy()), abi.Summary()
+    assert oracle.oracle_optimize(C.byref(hs.s), C.byref(abi.default_opts(**o_kw)), C.byref(summ)) == 0
+    solved = dataclasses.replace(w, para_pose=hs.pose.copy(), para_speed_bias=hs.sb.copy(), inv_depth=hs.inv.copy(),
+                                 para_ex_pose=hs.ex.copy(), para_td=hs.td.copy())
+    if ex:
+        assert np.abs(solved.para_ex_pose - w.para_ex_pose).max() > 0
+    r = _run_reference_optimization(pkg, ref, w, solved, flag, **o_kw)
+    # a1: vector2double reproduces the window's parameter arrays (Rs -> quaternion: same rotation, either sign)
+    assert np.array_equal(r["entry_pose"][:, :3], w.para_pose[:, :3]) and np.array_equal(r["entry_sb"], w.para_speed_bias)
+    sgn = np.sign(np.sum(r["entry_pose"][:, 3:] * w.para_pose[:, 3:], axis=1))[:, None]
+    assert np.abs(r["entry_pose"][:, 3:] * sgn - w.para_pose[:, 3:]).max() <= 1e-15
+    assert np.abs(r["entry_feat"] - w.inv_depth).max() <= 1e-15 * np.abs(w.inv_depth).max()
+    # the problem handed to Ceres
+    c = r["counts"]
+    nf = w.n_factors
+    assert (c[0], c[1], c[2], c[3], c[4], c[5]) == (1, K - 1, 0 if td else nf, nf if td else 0, 0, 0 if ex else 1)
+    assert c[6] == 2 * K + 1 + td and c[7] == 1 + K - 1 + nf
+    assert r["options"].tolist()[:3] == [8, 1, 1] and abs(r["max_time"] - 0.04 * (4.0 / 5.0 if flag == 0 else 1.0)) < 1e-15
+    hw, ow = abi.WindowHandle(w), abi.default_opts(**o_kw)
+    cost_o = oracle.oracle_cost(C.byref(hw.s), C.byref(ow))
+    assert abs(r["entry_cost"] - cost_o) <= 1e-9 * cost_o, (r["entry_cost"], cost_o)
+    # a2-a6 at system level: the Gauss-Newton normal equations assembled from the reference's own cost functions and
+    # loss corrector on the reference's own problem, Schur-reduced here, against oracle_linearize
+    dim = 15 * K + 7 + w.L
+    Hn, gn = np.zeros(dim * dim), np.zeros(dim)
+    assert ref.ref_estimator_last_normal(abi.dptr(Hn), abi.dptr(gn), dim) == dim
+    Hn = Hn.reshape(dim, dim)
+    keep = np.r_[np.arange(15 * K), 15 * K + np.arange(6) if ex else np.zeros(0, int), [15 * K + 6] if td else np.zeros(0, int)].astype(int)
+    lm = 15 * K + 7 + np.arange(w.L)
+    if not ex:
+        assert np.abs(Hn[15 * K:15 * K + 6]).max() > 0          # the constant block still gets Jacobians: it is dropped here
+    hl = np.diag(Hn[np.ix_(lm, lm)])
+    assert np.abs(Hn[np.ix_(lm, lm)] - np.diag(hl)).max() == 0
+    Hpl = Hn[np.ix_(keep, lm)]
+    S_ref = Hn[np.ix_(keep, keep)] - (Hpl / hl) @ Hpl.T
+    g_ref = gn[keep] - (Hpl / hl) @ gn[lm]
+    npar = len(keep)
+    S_o, g_o, h_o, b_o, c_o = np.zeros(npar * npar), np.zeros(npar), np.zeros(w.L), np.zeros(w.L), np.zeros(1)
+    assert oracle.oracle_linearize(C.byref(hw.s), C.byref(ow), abi.dptr(S_o), abi.dptr(g_o), abi.dptr(h_o), abi.dptr(b_o), abi.dptr(c_o)) == 0
+    S_o = S_o.reshape(npar, npar)
+    assert np.abs(h_o - hl).max() <= 1e-10 * np.abs(hl).max() and np.abs(b_o - gn[lm]).max() <= 1e-9 * np.abs(gn[lm]).max()
+    assert np.abs(S_o - S_ref).max() <= 1e-6 * np.abs(S_ref).max()
+    assert np.abs(g_o - g_ref).max() <= 1e-6 * np.abs(g_ref).max()
+    # a8: double2vector
+    pose, sb = solved.para_pose.copy(), solved.para_speed_bias.copy()
+    oracle.oracle_double2vector(abi.dptr(w.para_pose[0].copy()), K, abi.dptr(pose), abi.dptr(sb))
+    R_o = np.array([synth.quat_to_rot(q / np.linalg.norm(q)) for q in pose[:, 3:]])
+    assert np.abs(r["P"] - pose[:, :3]).max() <= 1e-12 and np.abs(r["R"] - R_o).max() <= 1e-12
+    assert np.abs(r["V"] - sb[:, :3]).max() <= 1e-12 and np.array_equal(r["Ba"], sb[:, 3:6]) and np.array_equal(r["Bg"], sb[:, 6:9])
+    assert np.abs(r["depth"] - 1.0 / solved.inv_depth).max() <= 1e-15 * np.abs(1.0 / solved.inv_depth).max()
+    assert np.abs(r["P"][0] - w.para_pose[0, :3]).max() <= 1e-12                       # frame 0 keeps its position
+    assert np.abs(r["ex"][:3] - solved.para_ex_pose[:3]).max() == 0 and abs(r["td"] - solved.para_td[0]) == 0
+    assert np.abs(r["ex"][3:].reshape(3, 3) - synth.quat_to_rot(solved.para_ex_pose[3:])).max() <= 1e-14
+    # a9: the marginalization that follows, at the re-gauged state
+    wpost = dataclasses.replace(w, para_pose=pose, para_speed_bias=sb, inv_depth=solved.inv_depth.copy(),
+                                para_ex_pose=solved.para_ex_pose.copy(), para_td=solved.para_td.copy())
+    po = run_marg(abi, oracle.oracle_marginalize, wpost, flag, opts=abi.default_opts(**o_kw))
+    pr = r["prior"]
+    assert pr is not None and pr["n"] == po["n"] == (75 if flag == 0 else 69) + td
+
+    def quad(p):
+        M = 15 * K + 7
+        unshift = (lambda f: f + 1) if flag == 0 else (lambda f: f if f < K - 2 else f + 1)
+        cols = np.full(p["n"], -1)
+        for kind, frame, idx in zip(p["block_kind"], p["block_frame"], p["block_idx"]):
+            base, size = ((15 * unshift(int(frame)), 6) if kind == 0 else (15 * unshift(int(frame)) + 6, 9) if kind == 1
+                          else (15 * K, 6) if kind == 2 else (15 * K + 6, 1))
+            cols[idx:idx + size] = base + np.arange(size)
+        H, g = np.zeros((M, M)), np.zeros(M)
+        H[np.ix_(cols, cols)] = p["J"].T @ p["J"]
+        g[cols] = p["J"].T @ p["lin_res"]
+        return H, g
+    (Hr, gr), (Ho, go) = quad(pr), quad(po)
+    assert np.abs(Hr - Ho).max() <= 1e-7 * np.abs(Hr).max()
+    assert np.abs(gr - go).max() <= 5e-5 * max(np.abs(gr).max(), 1.0)
