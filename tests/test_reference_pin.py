@@ -540,7 +540,7 @@ def _cloud_numpy(pkg, sc):
     return np.array(xy).reshape(-1, 2), np.array(dep)
 
 
-def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None, twins=0):
+def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None, twins=0, acc_var=None, acc_bias_var=None):
     """Runs the reference's FeatureSelector::select on a synthetic scene; returns (ids it selected, the same problem as
     the C-ABI's bvio_select_in inputs).  The horizon for the latter comes from the numpy restatement in
     tests/test_horizon.py unless an oracle is given."""
@@ -554,7 +554,9 @@ def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None, twins=
         if hasattr(cam_c, k):
             setattr(cam_c, k, v)
     f = lambda a: np.ascontiguousarray(a, np.float64)
-    h = ref.ref_sel_create(C.byref(cam_c), abi.dptr(f(sc["qic"])), abi.dptr(f(sc["tic"])), S.ACC_N, S.ACC_W, U + kappa, 0)
+    acc_var = S.ACC_N if acc_var is None else acc_var
+    acc_bias_var = S.ACC_W if acc_bias_var is None else acc_bias_var
+    h = ref.ref_sel_create(C.byref(cam_c), abi.dptr(f(sc["qic"])), abi.dptr(f(sc["tic"])), acc_var, acc_bias_var, U + kappa, 0)
     lm = sc["lm"]
     ref.ref_sel_set_backend(h, abi.dptr(f(sc["poses"].reshape(-1))), abi.dptr(f(sc["vel_k"])), abi.dptr(f(sc["ba_k"])),
                             len(lm["id"]), abi.iptr(lm["id"]), abi.iptr(lm["start"]), abi.iptr(lm["nobs"]),
@@ -588,7 +590,7 @@ def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None, twins=
                                      acc=f(sc["a1"]), gyr=f(sc["w1"])), nr, delta_imu)
     cl_xy, cl_d = _cloud_numpy(pkg, sc)
     prob_o = S.SelectProblem(H=H, horizon_pos=hp, horizon_quat=hq, q_ic=sc["qic"], t_ic=sc["tic"], cam=sc["cam"], nr_imu=nr,
-                             delta_imu=delta_imu, acc_var=S.ACC_N, acc_bias_var=S.ACC_W, cand_id=sc["cand_id"], cand_xy=sc["cand_xy"],
+                             delta_imu=delta_imu, acc_var=acc_var, acc_bias_var=acc_bias_var, cand_id=sc["cand_id"], cand_xy=sc["cand_xy"],
                              cand_prob=sc["cand_prob"], used_id=sc["used_id"], used_xy=sc["used_xy"], cloud_xy=cl_xy,
                              cloud_depth=cl_d, kappa=kappa)
     # bookkeeping of select(): the image handed to the back end = tracked + selected; the tracked list grew
@@ -754,3 +756,15 @@ def test_estimator_optimization_around_the_solve_rows_a1_a8_a9(pkg, oracle, ref,
     (Hr, gr), (Ho, go) = quad(pr), quad(po)
     assert np.abs(Hr - Ho).max() <= 1e-7 * np.abs(Hr).max()
     assert np.abs(gr - go).max() <= 5e-5 * max(np.abs(gr).max(), 1.0)
+
+
+def test_select_nothing_when_every_logdet_is_below_minus_one(pkg, oracle, ref):
+    """`fMax` starts at -1.0 (feature_selector.cpp:639): with a very uninformative IMU model every log-det is far below
+    -1, no candidate ever beats fMax, and select() returns no new feature although kappa > 0."""
+    abi = pkg.abi
+    ref_ids, prob = reference_select_case(pkg, ref, 0, 40, 0, 30, 10, oracle=oracle, acc_var=1e9, acc_bias_var=1e9)
+    assert len(ref_ids) == 0
+    hs, ss = abi.SelectHandle(prob), abi.SelectSummary()
+    out = np.zeros(10, np.int32)
+    assert oracle.oracle_select(C.byref(hs.s), abi.iptr(out), None, C.byref(ss)) == 0
+    assert ss.n_selected == 0
