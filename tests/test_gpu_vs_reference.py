@@ -49,3 +49,25 @@ def test_cuda_marginalize_matches_reference_marginalize(pkg, ref, seed, K, L):
     Hr, gr = info_in_state_coords(pr, K, lambda f: f + 1)
     assert np.abs(Hg - Hr).max() <= 1e-7 * np.abs(Hr).max()
     assert np.abs(gg - gr).max() <= 5e-5 * max(np.abs(gr).max(), 1.0)
+
+
+@pytest.mark.parametrize("seed,L,ex,td", [(0, 150, 0, 0), (1, 80, 1, 1)])
+def test_cuda_linearization_matches_reference_cost_functions(pkg, ref, seed, L, ex, td):
+    """bvio_debug_linearize (the device's reduced system S, g, h, b and cost) vs the Schur-reduced normal equations that
+    the reference's own Estimator::optimization() problem -- its cost functions, its loss corrector -- yields."""
+    from test_reference_pin import reference_reduced_system
+    abi, synth = pkg.abi, pkg.synth
+    K = 11
+    w = synth.make_window(seed=seed, K=K, L=L, **(dict(td_true=0.003) if td else {}))
+    o_kw = dict(estimate_extrinsic=ex, estimate_td=td, TR=0.01 if td else 0.0)
+    S_r, g_r, h_r, b_r, cost_r = reference_reduced_system(pkg, ref, w, **o_kw)
+    npar = 15 * K + 6 * ex + td
+    S, g, h, b, c = np.zeros((npar, npar)), np.zeros(npar), np.zeros(w.L), np.zeros(w.L), np.zeros(1)
+    ctx = pkg.lib.Context(0)
+    hw, o = abi.WindowHandle(w), abi.default_opts(**o_kw)
+    ctx.check(ctx.L.bvio_debug_linearize(ctx.h, C.byref(hw.s), C.byref(o), abi.dptr(S), abi.dptr(g), abi.dptr(h), abi.dptr(b), abi.dptr(c)),
+              "debug_linearize")
+    ctx.close()
+    assert abs(c[0] - cost_r) <= 1e-9 * cost_r
+    assert np.abs(h - h_r).max() <= 1e-9 * np.abs(h_r).max() and np.abs(b - b_r).max() <= 1e-8 * np.abs(b_r).max()
+    assert np.abs(S - S_r).max() <= 1e-6 * np.abs(S_r).max() and np.abs(g - g_r).max() <= 1e-6 * np.abs(g_r).max()

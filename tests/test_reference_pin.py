@@ -635,6 +635,23 @@ def test_select_duplicate_candidates_ub_collision_quirk(pkg, oracle, ref):
     assert all(not (a in order and b not in order) for a, b in pairs)    # never the smaller twin alone
 
 
+def reference_reduced_system(pkg, ref, w, **opts_kw):
+    """(S, g, h, b, cost) of the problem the reference's Estimator::optimization() hands to Ceres for window `w`: normal
+    equations assembled by the reference's cost functions and loss corrector, landmark columns Schur-eliminated here."""
+    abi = pkg.abi
+    K, ex, td = w.K, int(opts_kw.get("estimate_extrinsic", 0)), int(opts_kw.get("estimate_td", 0))
+    r = _run_reference_optimization(pkg, ref, w, w, 0, **opts_kw)
+    dim = 15 * K + 7 + w.L
+    Hn, gn = np.zeros(dim * dim), np.zeros(dim)
+    assert ref.ref_estimator_last_normal(abi.dptr(Hn), abi.dptr(gn), dim) == dim
+    Hn = Hn.reshape(dim, dim)
+    keep = np.r_[np.arange(15 * K), 15 * K + np.arange(6) if ex else np.zeros(0, int), [15 * K + 6] if td else np.zeros(0, int)].astype(int)
+    lm = 15 * K + 7 + np.arange(w.L)
+    hl = np.diag(Hn[np.ix_(lm, lm)]).copy()
+    Hpl = Hn[np.ix_(keep, lm)]
+    return Hn[np.ix_(keep, keep)] - (Hpl / hl) @ Hpl.T, gn[keep] - (Hpl / hl) @ gn[lm], hl, gn[lm].copy(), r["entry_cost"]
+
+
 def _run_reference_optimization(pkg, ref, w, solved, flag, **opts_kw):
     abi = pkg.abi
     K, L = w.K, w.L
