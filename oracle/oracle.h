@@ -17,11 +17,17 @@
  * marginalize, prior factor), utility.h, feature_manager.cpp,
  * utility/horizon_generator.cpp and feature_selector.cpp (select() end to end,
  * with the vendored nanoflann).
- * STILL UNPINNED BY REFERENCE CODE: row a7 -- the trust-region loop, dogleg,
- * Schur elimination and Jacobi scaling live in Ceres ("tested with 1.14.0",
- * feature_tracker/README.md:7), an un-vendored dependency; its published
- * algorithm is restated and pinned by our own means only (an independent
- * dense numpy trust-region loop, tests/np_ref.py).  The stand-in headers
+ * estimator.cpp is compiled too: Estimator::optimization() runs with a
+ * recording ceres::Problem and with ceres::Solve handing control to the test
+ * (vector2double, the problem census / objective / normal equations,
+ * double2vector and the marginalization glue are the reference's own).
+ * STILL UNPINNED BY REFERENCE CODE: Ceres itself ("tested with 1.14.0",
+ * feature_tracker/README.md:7), an un-vendored dependency.  The control logic
+ * of its trust-region loop (LM / traditional dogleg, Jacobi scaling, step
+ * acceptance, radius update, termination) is restated from its published
+ * algorithm twice -- here with Schur elimination, and densely in numpy
+ * (tests/np_ref.py), where it drives the reference's live problem -- and the
+ * two agree; neither has been checked against a real Ceres build.  The stand-in headers
  * replace Eigen's LLT / inverse / SelfAdjointEigenSolver / JacobiSVD with plain
  * textbook versions, and camodocal's PinholeCamera (needs OpenCV) with a
  * restatement of its spaceToPlane: agreement there is to rounding error or by

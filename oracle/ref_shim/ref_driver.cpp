@@ -533,7 +533,10 @@ struct EstHook {
   int L = 0;
   std::vector<double> H, g;   // normal equations of the whole problem at entry, local coordinates
   int dim = 0;
+  ceres::Problem* live = nullptr;      // valid only while the solve callback runs
+  void (*callback)(void) = nullptr;    // external trust-region driver (tests): called instead of injecting a solution
 } g_hook;
+void (*g_solve_callback)(void) = nullptr;
 
 void est_solve_hook(const ceres::Solver::Options& o, ceres::Problem* pb, ceres::Solver::Summary*) {
   EstHook& h = g_hook;
@@ -596,6 +599,12 @@ void est_solve_hook(const ceres::Solver::Options& o, ceres::Problem* pb, ceres::
   h.counts[6] = (int)pb->parameter_blocks.size(); h.counts[7] = (int)pb->residual_blocks.size();
   h.options[0] = o.max_num_iterations; h.options[1] = o.trust_region_strategy_type == ceres::DOGLEG;
   h.options[2] = o.linear_solver_type == ceres::DENSE_SCHUR; h.max_time = o.max_solver_time_in_seconds;
+  if (g_solve_callback) {              // an external driver iterates on the live problem through ref_live_*
+    h.live = pb;
+    g_solve_callback();
+    h.live = nullptr;
+    return;
+  }
   // "the solve": overwrite the parameter blocks with the solution computed elsewhere
   memcpy(e.para_Pose, h.inj_pose, sizeof(double) * 7 * (WINDOW_SIZE + 1));
   memcpy(e.para_SpeedBias, h.inj_sb, sizeof(double) * 9 * (WINDOW_SIZE + 1));
@@ -606,6 +615,78 @@ void est_solve_hook(const ceres::Solver::Options& o, ceres::Problem* pb, ceres::
 }  // namespace
 
 extern "C" {
+
+// ---- the live problem, for a trust-region loop driven from outside while Estimator::optimization() waits in "Solve" ----------
+// Local column layout as in est_solve_hook: [pose 6 | speed-bias 9] x (WINDOW_SIZE+1), extrinsic 6, td 1, one per feature.
+// Global state layout: para_Pose 7 x K1, para_SpeedBias 9 x K1, para_Ex_Pose 7, para_Td 1, para_Feature L.
+void ref_set_solve_callback(void (*cb)(void)) { g_solve_callback = cb; }
+int ref_live_dims(int32_t* n_residuals, int32_t* n_local, int32_t* n_global) {
+  if (!g_hook.live) return -1;
+  int nr = 0; for (auto& rb : g_hook.live->residual_blocks) nr += rb.cost->num_residuals();
+  const int K1 = WINDOW_SIZE + 1;
+  *n_residuals = nr; *n_local = 15 * K1 + 7 + g_hook.L; *n_global = 16 * K1 + 8 + g_hook.L;
+  return 0;
+}
+void ref_live_get_state(double* x) {
+  Estimator& e = *g_hook.est; const int K1 = WINDOW_SIZE + 1;
+  memcpy(x, e.para_Pose, sizeof(double) * 7 * K1); memcpy(x + 7 * K1, e.para_SpeedBias, sizeof(double) * 9 * K1);
+  memcpy(x + 16 * K1, e.para_Ex_Pose, sizeof(double) * 7); x[16 * K1 + 7] = e.para_Td[0][0];
+  for (int l = 0; l < g_hook.L; ++l) x[16 * K1 + 8 + l] = e.para_Feature[l][0];
+}
+void ref_live_set_state(const double* x) {
+  Estimator& e = *g_hook.est; const int K1 = WINDOW_SIZE + 1;
+  memcpy(e.para_Pose, x, sizeof(double) * 7 * K1); memcpy(e.para_SpeedBias, x + 7 * K1, sizeof(double) * 9 * K1);
+  memcpy(e.para_Ex_Pose, x + 16 * K1, sizeof(double) * 7); e.para_Td[0][0] = x[16 * K1 + 7];
+  for (int l = 0; l < g_hook.L; ++l) e.para_Feature[l][0] = x[16 * K1 + 8 + l];
+}
+// x (+) delta through the problem's own LocalParameterization objects (PoseLocalParameterization::Plus), plain addition elsewhere
+void ref_live_plus(const double* x, const double* delta, double* out) {
+  const int K1 = WINDOW_SIZE + 1, ng = 16 * K1 + 8 + g_hook.L;
+  for (int i = 0; i < ng; ++i) out[i] = x[i];
+  ceres::LocalParameterization* lp = nullptr;
+  for (auto& b : g_hook.live->parameter_blocks) if (b.local) { lp = b.local; break; }
+  for (int i = 0; i < K1; ++i) {
+    lp->Plus(x + 7 * i, delta + 15 * i, out + 7 * i);
+    for (int a = 0; a < 9; ++a) out[7 * K1 + 9 * i + a] = x[7 * K1 + 9 * i + a] + delta[15 * i + 6 + a];
+  }
+  lp->Plus(x + 16 * K1, delta + 15 * K1, out + 16 * K1);
+  out[16 * K1 + 7] = x[16 * K1 + 7] + delta[15 * K1 + 6];
+  for (int l = 0; l < g_hook.L; ++l) out[16 * K1 + 8 + l] = x[16 * K1 + 8 + l] + delta[15 * K1 + 7 + l];
+}
+// residuals r [n_residuals] and Jacobian J [n_residuals][n_local] (row-major), loss-corrected by the reference's
+// ResidualBlockInfo::Evaluate, at the state currently in the parameter arrays; *cost = 1/2 sum rho(|r_uncorrected|^2)
+int ref_live_evaluate(double* J, double* r, double* cost) {
+  if (!g_hook.live) return -1;
+  Estimator& e = *g_hook.est;
+  const int K1 = WINDOW_SIZE + 1, npar = 15 * K1 + 7, nl = npar + g_hook.L;
+  auto col_of = [&](double* p, int* size) {
+    for (int i = 0; i < K1; ++i) { if (p == e.para_Pose[i]) { *size = 6; return 15 * i; } if (p == e.para_SpeedBias[i]) { *size = 9; return 15 * i + 6; } }
+    if (p == e.para_Ex_Pose[0]) { *size = 6; return 15 * K1; }
+    if (p == e.para_Td[0]) { *size = 1; return 15 * K1 + 6; }
+    for (int l = 0; l < g_hook.L; ++l) if (p == e.para_Feature[l]) { *size = 1; return npar + l; }
+    *size = 0; return -1;
+  };
+  int row = 0; double c = 0;
+  for (auto& rb : g_hook.live->residual_blocks) {
+    const int nr = rb.cost->num_residuals();
+    std::vector<double> raw(nr);
+    rb.cost->Evaluate(rb.blocks.data(), raw.data(), nullptr);
+    double s = 0; for (double x : raw) s += x * x;
+    if (rb.loss) { double rho[3]; rb.loss->Evaluate(s, rho); c += 0.5 * rho[0]; } else c += 0.5 * s;
+    ResidualBlockInfo info(rb.cost, rb.loss, rb.blocks, std::vector<int>{});
+    info.Evaluate();
+    for (int k = 0; k < nr; ++k) { r[row + k] = info.residuals(k); for (int j = 0; j < nl; ++j) J[(size_t)(row + k) * nl + j] = 0.0; }
+    for (int b = 0; b < (int)rb.blocks.size(); ++b) {
+      int sz, c0 = col_of(rb.blocks[b], &sz);
+      if (c0 < 0) return -2;
+      for (int k = 0; k < nr; ++k) for (int j = 0; j < sz; ++j) J[(size_t)(row + k) * nl + c0 + j] += info.jacobians[b](k, j);
+    }
+    delete[] info.raw_jacobians;
+    row += nr;
+  }
+  *cost = c;
+  return 0;
+}
 
 // Normal equations of the problem the last ref_estimator_optimization() call handed to Ceres (see est_solve_hook)
 int ref_estimator_last_normal(double* H, double* g, int cap_dim) {

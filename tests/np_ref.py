@@ -345,12 +345,24 @@ def solve_gn(w, iters=60, tol=1e-13, **kw):
 
 def solve_trust_region(w, strategy=0, max_iters=8, initial_radius=1e4, function_tolerance=1e-6,
                        gradient_tolerance=1e-10, parameter_tolerance=1e-8, min_relative_decrease=1e-3, **kw):
-    """Ceres' trust-region loop on the DENSE, unreduced normal equations [poses | depths] -- no Schur elimination,
-    numpy's solver -- with Jacobi scaling fixed at the first linearization: LevenbergMarquardtStrategy (strategy 0)
-    or DoglegStrategy / TRADITIONAL_DOGLEG (strategy 1).  Second opinion on the oracle's Schur-based loop: the two
-    must take the same accept / reject path and produce the same iterates.  Returns (window, trace, termination)
-    with trace = [(cost, candidate cost, accepted, radius after)] per iteration."""
-    J, r, cost = full_system(w, **kw)
+    """trust_region_loop on this module's own dense system [poses | depths] of a synth.Window.  Second opinion on the
+    oracle's Schur-based loop: the two must take the same accept / reject path and produce the same iterates."""
+    flat = lambda s: np.concatenate([s.para_pose.ravel(), s.para_speed_bias.ravel(), s.inv_depth])
+    return trust_region_loop(w, lambda s: full_system(s, **kw), apply_delta, flat, strategy=strategy, max_iters=max_iters,
+                             initial_radius=initial_radius, function_tolerance=function_tolerance,
+                             gradient_tolerance=gradient_tolerance, parameter_tolerance=parameter_tolerance,
+                             min_relative_decrease=min_relative_decrease)
+
+
+def trust_region_loop(w, evaluate, plus, flat, strategy=0, max_iters=8, initial_radius=1e4, function_tolerance=1e-6,
+                      gradient_tolerance=1e-10, parameter_tolerance=1e-8, min_relative_decrease=1e-3):
+    """Ceres' trust-region control flow (TrustRegionMinimizer with LevenbergMarquardtStrategy, strategy 0, or
+    DoglegStrategy / TRADITIONAL_DOGLEG, strategy 1) on DENSE, unreduced normal equations -- no Schur elimination,
+    numpy's solver -- with Jacobi scaling fixed at the first linearization.  The problem is abstract:
+    evaluate(state) -> (J, r, cost) with J, r already loss-corrected, plus(state, local step) -> state,
+    flat(state) -> the free parameters as one vector (parameter tolerance).  Returns (state, trace, termination) with
+    trace = [(cost, candidate cost, accepted, radius after)] per iteration."""
+    J, r, cost = evaluate(w)
     H, g = J.T @ J, J.T @ r
     scale = 1.0 / (1.0 + np.sqrt(np.diag(H)))
     radius, decrease, mu, invalid_run = initial_radius, 2.0, 1e-8, 0
@@ -425,10 +437,9 @@ def solve_trust_region(w, strategy=0, max_iters=8, initial_radius=1e4, function_
                 reuse = False
             continue
         invalid_run = 0
-        cand = apply_delta(w, d)
-        Jc, rc, cc = full_system(cand, **kw)
-        x = np.concatenate([w.para_pose.ravel(), w.para_speed_bias.ravel(), w.inv_depth])
-        xc = np.concatenate([cand.para_pose.ravel(), cand.para_speed_bias.ravel(), cand.inv_depth])
+        cand = plus(w, d)
+        Jc, rc, cc = evaluate(cand)
+        x, xc = flat(w), flat(cand)
         if np.linalg.norm(x - xc) <= parameter_tolerance * (np.linalg.norm(x) + parameter_tolerance):
             term = 3
             break

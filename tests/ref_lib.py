@@ -84,5 +84,16 @@ def load():
     W, O = C.POINTER(abi.WindowS), C.POINTER(abi.Opts)
     L.ref_estimator_optimization.argtypes = [W, O, i32, W, dp, dp, dp, dp, dp, ip, ip, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(abi.PriorOut)]
     L.ref_estimator_last_normal.argtypes = [dp, dp, i32]
+    L.SOLVE_CB = C.CFUNCTYPE(None)
+    L.ref_set_solve_callback.argtypes = [C.c_void_p]
+    L.ref_set_solve_callback.restype = None
+    L.ref_live_dims.argtypes = [ip, ip, ip]
+    L.ref_live_get_state.argtypes = [dp]
+    L.ref_live_get_state.restype = None
+    L.ref_live_set_state.argtypes = [dp]
+    L.ref_live_set_state.restype = None
+    L.ref_live_plus.argtypes = [dp, dp, dp]
+    L.ref_live_plus.restype = None
+    L.ref_live_evaluate.argtypes = [dp, dp, dp]
     _lib = L
     return L

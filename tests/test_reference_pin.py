@@ -785,3 +785,78 @@ def test_select_nothing_when_every_logdet_is_below_minus_one(pkg, oracle, ref):
     out = np.zeros(10, np.int32)
     assert oracle.oracle_select(C.byref(hs.s), abi.iptr(out), None, C.byref(ss)) == 0
     assert ss.n_selected == 0
+
+
+@pytest.mark.parametrize("seed,L,strategy,ex,td,radius", [(0, 80, 1, 0, 0, 1e4), (1, 100, 0, 0, 0, 1e4), (2, 60, 1, 1, 1, 1e4),
+                                                         (3, 60, 1, 0, 0, 1e-2), (4, 60, 0, 1, 0, 1e-3)])
+def test_reference_optimization_end_to_end_with_numpy_trust_region_row_a7(pkg, oracle, ref, seed, L, strategy, ex, td, radius):
+    """The whole of Estimator::optimization() in the reference's code, Ceres excepted: while the reference waits inside
+    `ceres::Solve`, a numpy restatement of Ceres' trust-region CONTROL FLOW (np_ref.trust_region_loop: Jacobi scaling,
+    LM / traditional dogleg step, step acceptance, radius update, convergence tests) iterates on the reference's live
+    problem -- its cost functions, loss corrector and PoseLocalParameterization do all the arithmetic -- and writes the
+    result into the reference's parameter blocks; the reference then runs double2vector and its marginalization.
+    The oracle (what the CUDA path is tested against) must take the same iterations and land on the same state."""
+    abi, synth = pkg.abi, pkg.synth
+    K = 11
+    tdkw = dict(td_true=0.003) if td else {}
+    o_kw = dict(strategy=strategy, max_iters=8, max_time_s=0.0, estimate_extrinsic=ex, estimate_td=td, TR=0.01 if td else 0.0,
+                initial_radius=radius)
+    w = synth.make_window(seed=seed, K=K, L=L, **tdkw)
+    if td:
+        w.para_td[0] = 0.001
+    K1 = K
+    free = np.r_[np.arange(15 * K1), 15 * K1 + np.arange(6) if ex else np.zeros(0, int), [15 * K1 + 6] if td else np.zeros(0, int),
+                 15 * K1 + 7 + np.arange(L)].astype(int)
+    gfree = np.r_[np.arange(16 * K1), 16 * K1 + np.arange(7) if ex else np.zeros(0, int), [16 * K1 + 7] if td else np.zeros(0, int),
+                  16 * K1 + 8 + np.arange(L)].astype(int)
+    log = {}
+
+    def solve():
+        nr, nl, ng = C.c_int32(), C.c_int32(), C.c_int32()
+        assert ref.ref_live_dims(C.byref(nr), C.byref(nl), C.byref(ng)) == 0
+        nr, nl, ng = nr.value, nl.value, ng.value
+        x0 = np.zeros(ng)
+        ref.ref_live_get_state(abi.dptr(x0))
+
+        def evaluate(x):
+            ref.ref_live_set_state(abi.dptr(np.ascontiguousarray(x)))
+            J, r, c = np.zeros(nr * nl), np.zeros(nr), np.zeros(1)
+            assert ref.ref_live_evaluate(abi.dptr(J), abi.dptr(r), abi.dptr(c)) == 0
+            return J.reshape(nr, nl)[:, free], r, float(c[0])
+
+        def plus(x, d):
+            full, out = np.zeros(nl), np.zeros(ng)
+            full[free] = d
+            ref.ref_live_plus(abi.dptr(np.ascontiguousarray(x)), abi.dptr(full), abi.dptr(out))
+            return out
+        x, trace, term = np_ref.trust_region_loop(x0, evaluate, plus, lambda x: x[gfree], strategy=strategy, max_iters=8,
+                                                  initial_radius=radius)
+        ref.ref_live_set_state(abi.dptr(np.ascontiguousarray(x)))
+        log.update(x=x, trace=trace, term=term, cost=evaluate(x)[2])
+    cb = ref.SOLVE_CB(solve)
+    ref.ref_set_solve_callback(C.cast(cb, C.c_void_p))
+    try:
+        r = _run_reference_optimization(pkg, ref, w, w, 0, **o_kw)
+    finally:
+        ref.ref_set_solve_callback(None)
+    # the oracle on the same window
+    hs, summ = abi.WindowHandle(w.copy()), abi.Summary()
+    assert oracle.oracle_optimize(C.byref(hs.s), C.byref(abi.default_opts(**o_kw)), C.byref(summ)) == 0
+    acc = sum(1 for t in log["trace"] if t[2])
+    assert (summ.iterations, summ.num_accepted, summ.num_rejected, summ.termination) == \
+           (len(log["trace"]), acc, len(log["trace"]) - acc, log["term"]), (summ.as_dict(), log["trace"], log["term"])
+    assert abs(summ.final_cost - log["cost"]) <= 1e-8 * log["cost"]
+    assert abs(summ.final_radius - log["trace"][-1][3]) <= 1e-6 * summ.final_radius
+    # final state: oracle solution + double2vector vs what the reference holds after its own double2vector
+    pose, sb = hs.pose.copy(), hs.sb.copy()
+    oracle.oracle_double2vector(abi.dptr(w.para_pose[0].copy()), K, abi.dptr(pose), abi.dptr(sb))
+    R_o = np.array([synth.quat_to_rot(q / np.linalg.norm(q)) for q in pose[:, 3:]])
+    scale = max(1.0, np.abs(pose[:, :3]).max())
+    assert np.abs(r["P"] - pose[:, :3]).max() <= 1e-6 * scale and np.abs(r["R"] - R_o).max() <= 1e-6
+    assert np.abs(r["V"] - sb[:, :3]).max() <= 1e-6 and np.abs(r["Ba"] - sb[:, 3:6]).max() <= 1e-6
+    assert np.abs(r["depth"] - 1.0 / hs.inv).max() <= 1e-5 * np.abs(1.0 / hs.inv).max()
+    if ex:
+        assert np.abs(r["ex"][:3] - hs.ex[:3]).max() <= 1e-7
+    if td:
+        assert abs(r["td"] - hs.td[0]) <= 1e-8
+    assert r["prior"] is not None and r["prior"]["n"] >= 69
