@@ -804,3 +804,76 @@ int ref_estimator_optimization(const bvio_window* w, const bvio_opts* o, int fla
 }
 
 }  // extern "C"
+
+
+// ---- Estimator::slideWindow() (estimator.cpp:996-1107) --------------------------------------------------------------------------
+extern "C" {
+
+// Builds an Estimator holding a full window and calls slideWindow().  Interval j (1..WINDOW_SIZE) links frame j-1 to j:
+// imu_n[j] samples (dt, acc, gyr) after its start sample imu_start[j] = (acc0, gyr0), linearization biases imu_lin[j] =
+// (ba, bg) as they were when the interval was opened; all intervals concatenated in
+// imu_dt / imu_acc / imu_gyr.  Features as CSR like bvio_window plus a depth per feature (<= 0: not triangulated).
+// Outputs: the shifted states, the packed preintegration of every interval that survives (index j-1 for MARGIN_OLD,
+// merged into WINDOW_SIZE-1 for MARGIN_SECOND_NEW), and the FeatureManager dump.
+int ref_estimator_slide(int flag, const double* poses, const double* sb, const double* ex, const int32_t* imu_n,
+                        const double* imu_start, const double* imu_lin, const double* imu_dt, const double* imu_acc, const double* imu_gyr,
+                        double acc_n, double gyr_n, double acc_w, double gyr_w, int n_feat, const int32_t* f_id,
+                        const int32_t* f_off, const int32_t* f_start, const double* f_xy, const double* f_depth,
+                        double* out_poses, double* out_sb, bvio_preint* out_pre, int32_t* out_sum,
+                        int cap, int32_t* d_id, int32_t* d_start, int32_t* d_nobs, double* d_depth) {
+  const int K = WINDOW_SIZE + 1;
+  ACC_N = acc_n; GYR_N = gyr_n; ACC_W = acc_w; GYR_W = gyr_w; TD = 0;
+  void* mem = calloc(1, sizeof(Estimator));
+  Estimator* e = new (mem) Estimator();
+  e->tic[0] = v3(ex);
+  e->ric[0] = Eigen::Quaterniond(ex[6], ex[3], ex[4], ex[5]).toRotationMatrix();
+  e->f_manager.setRic(e->ric);
+  int off = 0;
+  for (int i = 0; i < K; ++i) {
+    const double* p = poses + 7 * i; const double* s = sb + 9 * i;
+    e->Ps[i] = v3(p); e->Rs[i] = Eigen::Quaterniond(p[6], p[3], p[4], p[5]).toRotationMatrix();
+    e->Vs[i] = v3(s); e->Bas[i] = v3(s + 3); e->Bgs[i] = v3(s + 6);
+    e->Headers[i].stamp = ros::Time(100.0 + 0.1 * i);
+    ImageFrame fr(map<int, vector<pair<int, Eigen::Matrix<double, 7, 1>>>>(), e->Headers[i].stamp.toSec());
+    fr.pre_integration = new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero());
+    e->all_image_frame.insert(make_pair(e->Headers[i].stamp.toSec(), fr));
+    if (i >= 1) {
+      e->pre_integrations[i] = new IntegrationBase(v3(imu_start + 6 * i), v3(imu_start + 6 * i + 3), v3(imu_lin + 6 * i), v3(imu_lin + 6 * i + 3));
+      for (int k = 0; k < imu_n[i]; ++k, ++off) {
+        e->pre_integrations[i]->push_back(imu_dt[off], v3(imu_acc + 3 * off), v3(imu_gyr + 3 * off));
+        e->dt_buf[i].push_back(imu_dt[off]);
+        e->linear_acceleration_buf[i].push_back(v3(imu_acc + 3 * off));
+        e->angular_velocity_buf[i].push_back(v3(imu_gyr + 3 * off));
+        e->acc_0 = v3(imu_acc + 3 * off); e->gyr_0 = v3(imu_gyr + 3 * off);
+      }
+    }
+  }
+  for (int l = 0; l < n_feat; ++l) {
+    FeaturePerId f(f_id[l], f_start[l]);
+    for (int k = f_off[l]; k < f_off[l + 1]; ++k) {
+      Eigen::Matrix<double, 7, 1> pt; pt.setZero(); pt(0) = f_xy[2 * k]; pt(1) = f_xy[2 * k + 1]; pt(2) = 1.0;
+      f.feature_per_frame.push_back(FeaturePerFrame(pt, 0.0));
+    }
+    f.estimated_depth = f_depth[l];
+    e->f_manager.feature.push_back(f);
+  }
+  e->frame_count = WINDOW_SIZE; e->solver_flag = Estimator::NON_LINEAR;
+  e->marginalization_flag = flag == 0 ? Estimator::MARGIN_OLD : Estimator::MARGIN_SECOND_NEW;
+  e->slideWindow();
+  for (int i = 0; i < K; ++i) {
+    Eigen::Quaterniond q(e->Rs[i]);
+    for (int a = 0; a < 3; ++a) { out_poses[7 * i + a] = e->Ps[i](a); out_sb[9 * i + a] = e->Vs[i](a); out_sb[9 * i + 3 + a] = e->Bas[i](a); out_sb[9 * i + 6 + a] = e->Bgs[i](a); }
+    out_poses[7 * i + 3] = q.x(); out_poses[7 * i + 4] = q.y(); out_poses[7 * i + 5] = q.z(); out_poses[7 * i + 6] = q.w();
+    memset(&out_pre[i], 0, sizeof(bvio_preint));
+    if (i >= 1 && e->pre_integrations[i]) store(*e->pre_integrations[i], &out_pre[i]);
+  }
+  out_sum[0] = e->sum_of_back; out_sum[1] = e->sum_of_front;
+  int k = 0;
+  for (auto& f : e->f_manager.feature) {
+    if (k < cap) { d_id[k] = f.feature_id; d_start[k] = f.start_frame; d_nobs[k] = (int)f.feature_per_frame.size(); d_depth[k] = f.estimated_depth; }
+    ++k;
+  }
+  return k;
+}
+
+}  // extern "C"

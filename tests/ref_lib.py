@@ -95,5 +95,8 @@ def load():
     L.ref_live_plus.argtypes = [dp, dp, dp]
     L.ref_live_plus.restype = None
     L.ref_live_evaluate.argtypes = [dp, dp, dp]
+    PP = C.POINTER(abi.Preint)
+    L.ref_estimator_slide.argtypes = [i32, dp, dp, dp, ip, dp, dp, dp, dp, dp, d, d, d, d, i32, ip, ip, ip, dp, dp, dp, dp, PP, ip,
+                                      i32, ip, ip, ip, dp]
     _lib = L
     return L

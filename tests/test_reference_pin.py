@@ -860,3 +860,67 @@ def test_reference_optimization_end_to_end_with_numpy_trust_region_row_a7(pkg, o
     if td:
         assert abs(r["td"] - hs.td[0]) <= 1e-8
     assert r["prior"] is not None and r["prior"]["n"] >= 69
+
+
+def test_slide_window_matches_reference_estimator_row_f1(pkg, oracle, ref):
+    """Estimator::slideWindow() itself (estimator.cpp:996-1107: state shifting, preintegration swap / IMU-sample merge,
+    slideWindowOld with shift_depth / slideWindowNew) on the exact data the slider holds before each of its slides."""
+    from slider_backends import OracleBackend
+    abi, sl, S = pkg.abi, pkg.slider, pkg.synth
+    sim = sl.SlidingWindowSim(seed=21, max_feats=80, max_cand=100, opts=dict(max_iters=8), keyframes="parallax", frame_dt=0.04)
+    be = OracleBackend(oracle, abi)
+    K = sim.K
+    done = {0: 0, 1: 0}
+
+    def check(flag, slide):
+        f = lambda a: np.ascontiguousarray(a, np.float64)
+        n = np.array([len(b) for b in sim.imu_buf], np.int32)
+        start = np.zeros((K, 6))
+        lin = np.zeros((K, 6))
+        for j in range(1, K):
+            start[j] = np.concatenate([sim.pre_obj[j].linearized_acc, sim.pre_obj[j].linearized_gyr])
+            lin[j] = np.concatenate([sim.pre_obj[j].lin_ba, sim.pre_obj[j].lin_bg])
+        flat = [s for b in sim.imu_buf for s in b]
+        dt = f([s[0] for s in flat])
+        acc, gyr = f([s[1] for s in flat]).reshape(-1), f([s[2] for s in flat]).reshape(-1)
+        tr = list(sim.tracks.values())
+        fid = np.array([t.lid for t in tr], np.int32)
+        fst = np.array([t.start for t in tr], np.int32)
+        foff = np.concatenate([[0], np.cumsum([len(t.xy) for t in tr])]).astype(np.int32)
+        fxy = f([xy for t in tr for xy in t.xy]).reshape(-1)
+        fdep = f([t.depth for t in tr])
+        o_pose, o_sb, o_sum = np.zeros((K, 7)), np.zeros((K, 9)), np.zeros(2, np.int32)
+        o_pre = (abi.Preint * K)()
+        cap = len(tr) + 8
+        d_id, d_st, d_n, d_dep = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+        ex = f(np.concatenate([sim.tic, sim.qic]))
+        nf = ref.ref_estimator_slide(flag, abi.dptr(f(sim.pose.reshape(-1))), abi.dptr(f(sim.sb.reshape(-1))), abi.dptr(ex), abi.iptr(n),
+                                     abi.dptr(f(start.reshape(-1))), abi.dptr(f(lin.reshape(-1))), abi.dptr(dt), abi.dptr(acc), abi.dptr(gyr),
+                                     S.ACC_N, S.GYR_N, S.ACC_W, S.GYR_W, len(tr), abi.iptr(fid), abi.iptr(foff), abi.iptr(fst), abi.dptr(fxy),
+                                     abi.dptr(fdep), abi.dptr(o_pose), abi.dptr(o_sb), o_pre, abi.iptr(o_sum), cap, abi.iptr(d_id),
+                                     abi.iptr(d_st), abi.iptr(d_n), abi.dptr(d_dep))
+        slide()                                               # the slider's own slide
+        assert len(sim.pose) == K - 1
+        assert np.abs(o_pose[:K - 1, :3] - sim.pose[:, :3]).max() == 0 and np.abs(o_sb[:K - 1] - sim.sb).max() == 0
+        sgn = np.sign(np.sum(o_pose[:K - 1, 3:] * sim.pose[:, 3:], axis=1))[:, None]
+        assert np.abs(o_pose[:K - 1, 3:] * sgn - sim.pose[:, 3:]).max() <= 1e-15
+        if flag == 0:                                         # the reference also parks a copy of the newest state in slot WINDOW_SIZE
+            assert np.array_equal(o_pose[K - 1, :3], o_pose[K - 2, :3]) and tuple(o_sum) == (1, 0)
+        else:
+            assert tuple(o_sum) == (0, 1)
+        for j in range(1, K - 1):
+            got = np.frombuffer(bytes(o_pre[j]), dtype=np.float64)
+            assert np.abs(got[:17] - sim.preint[j][:17]).max() <= 1e-14, (flag, j)
+            assert np.abs(got[17:] - sim.preint[j][17:]).max() <= 1e-12 * np.abs(sim.preint[j][17:]).max(), (flag, j)
+        assert np.frombuffer(bytes(o_pre[K - 1]), dtype=np.float64)[16] == 0.0          # a fresh IntegrationBase for the next frame
+        dump = {int(i): (int(s), int(k), float(x)) for i, s, k, x in zip(d_id[:nf], d_st[:nf], d_n[:nf], d_dep[:nf])}
+        assert set(dump) == set(sim.tracks)
+        for lid, t in sim.tracks.items():
+            assert dump[lid][:2] == (t.start, len(t.xy)) and abs(dump[lid][2] - t.depth) <= 1e-12 * max(abs(t.depth), 1.0), (lid, dump[lid], t)
+        done[flag] += 1
+    orig_old, orig_new = sim._slide, sim._slide_new
+    sim._slide = lambda: check(0, orig_old)
+    sim._slide_new = lambda: check(1, orig_new)
+    for _ in range(30):
+        sim.step(be)
+    assert done[0] >= 6 and done[1] >= 6, done
