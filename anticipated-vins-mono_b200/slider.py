@@ -438,6 +438,27 @@ class SlidingWindowSim:
         return lat
 
 
+def process_imu(pose, sb, acc_0, gyr_0, samples, g):
+    """Estimator::processIMU (estimator.cpp:86-119) for one frame interval: the reference's own prediction of the
+    incoming frame -- sample-by-sample midpoint propagation in the world frame, rotation updated by the UN-normalised
+    Utility::deltaQ increment through toRotationMatrix() and never re-orthonormalised inside the frame.
+    -> (P, R 3x3, V) of the new frame before it is optimised."""
+    P, V, R = np.array(pose[:3], float), np.array(sb[:3], float), _R(np.asarray(pose[3:], float))
+    ba, bg = np.asarray(sb[3:6], float), np.asarray(sb[6:9], float)
+    a0, g0 = np.asarray(acc_0, float), np.asarray(gyr_0, float)
+    for dt, a1, g1 in samples:
+        un_acc_0 = R @ (a0 - ba) - g
+        un_gyr = 0.5 * (g0 + g1) - bg
+        q = np.array([un_gyr[0] * dt / 2, un_gyr[1] * dt / 2, un_gyr[2] * dt / 2, 1.0])      # not normalised
+        R = R @ S.quat_to_rot(q)                                    # Eigen's toRotationMatrix formula, no normalisation
+        un_acc_1 = R @ (a1 - ba) - g
+        un_acc = 0.5 * (un_acc_0 + un_acc_1)
+        P = P + dt * V + 0.5 * dt * dt * un_acc
+        V = V + dt * un_acc
+        a0, g0 = np.asarray(a1, float), np.asarray(g1, float)
+    return P, R, V
+
+
 class _Scores:
     """feature id -> detector score of the current image, indexable like World.score"""
 
@@ -509,12 +530,8 @@ class ReplaySession(SlidingWindowSim):
             for k in range(len(dt)):
                 pre.push_back(dt[k], acc[k], gyr[k])
                 buf.append((dt[k], acc[k].copy(), gyr[k].copy()))
-            Ri, Pi, Vi, T = _R(self.pose[-1, 3:]), self.pose[-1, :3], self.sb[-1, :3], pre.sum_dt
-            Pj = Pi + Vi * T - 0.5 * self.g * T * T + Ri @ pre.delta_p
-            Vj = Vi - self.g * T + Ri @ pre.delta_v
-            qj = S.quat_mul(self.pose[-1, 3:], pre.delta_q)
-            qj /= np.linalg.norm(qj)
-            pj, sj = np.concatenate([Pj, qj]), np.concatenate([Vj, ba, bg])
+            Pj, Rj, Vj = process_imu(self.pose[-1], self.sb[-1], self.acc_0, self.gyr_0, buf, self.g)
+            pj, sj = np.concatenate([Pj, S.rot_to_quat(Rj)]), np.concatenate([Vj, ba, bg])    # vector2double: Quaterniond{Rs}
             if len(self.pose) < K and self.frame in self.init:
                 pj, sj = (np.array(x, float) for x in self.init[self.frame])
             self.pose, self.sb = np.vstack([self.pose, pj]), np.vstack([self.sb, sj])

@@ -877,3 +877,27 @@ int ref_estimator_slide(int flag, const double* poses, const double* sb, const d
 }
 
 }  // extern "C"
+
+
+// ---- Estimator::processIMU() (estimator.cpp:86-119): the state prediction of the incoming frame --------------------------------
+extern "C" {
+// State of the newest frame (pose7, sb9) + the start sample (acc_0, gyr_0) + n samples (dt, acc, gyr) -> predicted state
+// after feeding the samples through processIMU with frame_count = 1; out_R is Rs[j] row-major (the reference never
+// re-orthonormalises it inside a frame), out_pre the preintegration it accumulated.
+void ref_estimator_process_imu(const double* pose, const double* sb, const double* start, int n, const double* dt, const double* acc,
+                               const double* gyr, const double* G_, double acc_n, double gyr_n, double acc_w, double gyr_w,
+                               double* out_P, double* out_R, double* out_V, bvio_preint* out_pre) {
+  ACC_N = acc_n; GYR_N = gyr_n; ACC_W = acc_w; GYR_W = gyr_w; TD = 0;
+  void* mem = calloc(1, sizeof(Estimator));
+  Estimator* e = new (mem) Estimator();
+  e->g = v3(G_);
+  e->frame_count = 1;
+  e->Ps[1] = v3(pose); e->Rs[1] = Eigen::Quaterniond(pose[6], pose[3], pose[4], pose[5]).toRotationMatrix();
+  e->Vs[1] = v3(sb); e->Bas[1] = v3(sb + 3); e->Bgs[1] = v3(sb + 6);
+  e->first_imu = true; e->acc_0 = v3(start); e->gyr_0 = v3(start + 3);
+  e->tmp_pre_integration = new IntegrationBase(e->acc_0, e->gyr_0, e->Bas[1], e->Bgs[1]);
+  for (int k = 0; k < n; ++k) e->processIMU(dt[k], v3(acc + 3 * k), v3(gyr + 3 * k));
+  for (int a = 0; a < 3; ++a) { out_P[a] = e->Ps[1](a); out_V[a] = e->Vs[1](a); for (int b = 0; b < 3; ++b) out_R[3 * a + b] = e->Rs[1](a, b); }
+  store(*e->pre_integrations[1], out_pre);
+}
+}  // extern "C"

@@ -98,5 +98,7 @@ def load():
     PP = C.POINTER(abi.Preint)
     L.ref_estimator_slide.argtypes = [i32, dp, dp, dp, ip, dp, dp, dp, dp, dp, d, d, d, d, i32, ip, ip, ip, dp, dp, dp, dp, PP, ip,
                                       i32, ip, ip, ip, dp]
+    L.ref_estimator_process_imu.argtypes = [dp, dp, dp, i32, dp, dp, dp, dp, d, d, d, d, dp, dp, dp, PP]
+    L.ref_estimator_process_imu.restype = None
     _lib = L
     return L

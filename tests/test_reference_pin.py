@@ -924,3 +924,34 @@ def test_slide_window_matches_reference_estimator_row_f1(pkg, oracle, ref):
     for _ in range(30):
         sim.step(be)
     assert done[0] >= 6 and done[1] >= 6, done
+
+
+def test_process_imu_prediction_row_f1(pkg, ref):
+    """Estimator::processIMU (estimator.cpp:86-119): the reference's prediction of the incoming frame vs
+    slider.process_imu (used by ReplaySession), and the preintegration it accumulates on the way."""
+    abi, S, sl = pkg.abi, pkg.synth, pkg.slider
+    rng = np.random.default_rng(8)
+    G = np.array([0, 0, S.G_NORM])
+    for _ in range(5):
+        pose, sb = _rand_pose(rng), np.concatenate([rng.normal(0, 1, 3), rng.normal(0, 0.02, 3), rng.normal(0, 0.002, 3)])
+        n = int(rng.integers(5, 25))
+        acc = rng.normal(0, 1, (n + 1, 3)) + [0, 0, 9.8]
+        gyr = rng.normal(0, 0.5, (n + 1, 3))
+        dt = rng.uniform(0.004, 0.006, n)
+        P, R, V, pre = np.zeros(3), np.zeros(9), np.zeros(3), abi.Preint()
+        ref.ref_estimator_process_imu(abi.dptr(pose), abi.dptr(sb), abi.dptr(np.concatenate([acc[0], gyr[0]])), n, abi.dptr(dt),
+                                      abi.dptr(acc[1:].reshape(-1).copy()), abi.dptr(gyr[1:].reshape(-1).copy()), abi.dptr(G),
+                                      S.ACC_N, S.GYR_N, S.ACC_W, S.GYR_W, abi.dptr(P), abi.dptr(R), abi.dptr(V), C.byref(pre))
+        Pm, Rm, Vm = sl.process_imu(pose, sb, acc[0], gyr[0], [(dt[k], acc[k + 1], gyr[k + 1]) for k in range(n)], G)
+        assert np.abs(P - Pm).max() <= 1e-13 * max(np.abs(P).max(), 1) and np.abs(V - Vm).max() <= 1e-13 * max(np.abs(V).max(), 1)
+        assert np.abs(R.reshape(3, 3) - Rm).max() <= 1e-14
+        assert np.abs(Rm.T @ Rm - np.eye(3)).max() > 1e-12         # the reference's Rs drifts (slightly) off SO(3) inside a frame
+        num = S.Preintegration(acc[0], gyr[0], sb[3:6], sb[6:9])
+        for k in range(n):
+            num.push_back(dt[k], acc[k + 1], gyr[k + 1])
+        got, want = np.frombuffer(bytes(pre), dtype=np.float64), S.pack_preint(num)
+        assert np.abs(got[:17] - want[:17]).max() <= 1e-13 and np.abs(got[17:] - want[17:]).max() <= 1e-11 * np.abs(want[17:]).max()
+        # the preintegration-based prediction the simulator uses agrees to second order in the per-sample rotation
+        Ri, T = S.quat_to_rot(pose[3:]), num.sum_dt
+        Pd = pose[:3] + sb[:3] * T - 0.5 * G * T * T + Ri @ num.delta_p
+        assert np.abs(Pd - P).max() <= 1e-4
