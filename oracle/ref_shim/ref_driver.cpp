@@ -454,8 +454,15 @@ image_t make_image(int n, const int32_t* ids, const double* xy, const double* pr
 
 extern "C" {
 
+void* ref_sel_create_gt(const bvio_camera* cam, const double q_ic[4], const double t_ic[3], double acc_var, double acc_bias_var,
+                        int max_features, int init_thresh, const char* gt_csv);
 void* ref_sel_create(const bvio_camera* cam, const double q_ic[4], const double t_ic[3], double acc_var, double acc_bias_var,
                      int max_features, int init_thresh) {
+  return ref_sel_create_gt(cam, q_ic, t_ic, acc_var, acc_bias_var, max_features, init_thresh, nullptr);
+}
+// gt_csv != NULL: ground-truth horizon mode (USE_GT, the "gt_data_csv" parameter of the node)
+void* ref_sel_create_gt(const bvio_camera* cam, const double q_ic[4], const double t_ic[3], double acc_var, double acc_bias_var,
+                        int max_features, int init_thresh, const char* gt_csv) {
   camodocal::PinholeParams& c = camodocal::CameraFactory::registered();
   c.fx = cam->fx; c.fy = cam->fy; c.cx = cam->cx; c.cy = cam->cy; c.k1 = cam->k1; c.k2 = cam->k2; c.p1 = cam->p1; c.p2 = cam->p2;
   c.width = cam->width; c.height = cam->height;
@@ -463,8 +470,10 @@ void* ref_sel_create(const bvio_camera* cam, const double q_ic[4], const double 
   r->est.ric[0] = Eigen::Quaterniond(q_ic[3], q_ic[0], q_ic[1], q_ic[2]).toRotationMatrix();
   r->est.tic[0] = v3(t_ic);
   r->est.solver_flag = Estimator::INITIAL;
-  r->sel.reset(new FeatureSelector(ros::NodeHandle(), r->est, "unused.yaml"));
-  r->sel->setParameters(acc_var, acc_bias_var, true, max_features, init_thresh, false);
+  ros::NodeHandle nh;
+  if (gt_csv) nh.setParam("gt_data_csv", gt_csv);
+  r->sel.reset(new FeatureSelector(nh, r->est, "unused.yaml"));
+  r->sel->setParameters(acc_var, acc_bias_var, true, max_features, init_thresh, gt_csv != nullptr);
   return r;
 }
 void ref_sel_destroy(void* h) { delete static_cast<RefSel*>(h); }

@@ -121,13 +121,18 @@ double nn_depth(const bvio_select_in* in, double x, double y) {
   return in->cloud_depth[best];
 }
 
+// state_k1_ of the reference (feature_selector.cpp:247-250) when it differs from state_kkH[1], i.e. in ground-truth
+// horizon mode; set only by oracle_select_k1
+static thread_local const double* g_k1_pos = nullptr;
+static thread_local const double* g_k1_quat = nullptr;
+
 // one feature: returns false when numVisible == 1. Ch = H blocks (index h-1).
 bool feature_blocks(const bvio_select_in* in, double fx, double fy, std::vector<M3>& Ch, M3& W, double* depth) {
   int H = in->H;
   Q4 q_IC = q4(in->q_ic);
   V3 t_IC = v3(in->t_ic);
-  V3 P1 = v3(in->horizon_pos + 3);
-  Q4 Q1 = q4(in->horizon_quat + 4);
+  V3 P1 = v3(g_k1_pos ? g_k1_pos : in->horizon_pos + 3);
+  Q4 Q1 = q4(g_k1_quat ? g_k1_quat : in->horizon_quat + 4);
   V3 t_WC_k1 = P1 + qrot(Q1, t_IC);
   Q4 q_WC_k1 = qmul(Q1, q_IC);
   V3 feature{fx, fy, 1.0};
@@ -305,3 +310,14 @@ int oracle_select(const bvio_select_in* in, int32_t* out_ids, double* out_values
 }
 
 }  // extern "C"
+
+
+// oracle_select with the candidates back-projected from an explicit x_{k+1} (the reference's IMU-propagated state_k1_)
+// instead of horizon[1]: what FeatureSelector::select does in ground-truth horizon mode.
+extern "C" int oracle_select_k1(const bvio_select_in* in, const double k1_pos[3], const double k1_quat[4], int32_t* out_ids,
+                                double* out_values, bvio_select_summary* summary) {
+  g_k1_pos = k1_pos; g_k1_quat = k1_quat;
+  int rc = oracle_select(in, out_ids, out_values, summary);
+  g_k1_pos = g_k1_quat = nullptr;
+  return rc;
+}

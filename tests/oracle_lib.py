@@ -49,6 +49,7 @@ def load():
     L.oracle_build_delta.argtypes = [C.POINTER(abi.SelectIn), i32, dp, dp, ip, dp]
     L.oracle_build_delta.restype = None
     L.oracle_select.argtypes = [C.POINTER(abi.SelectIn), ip, dp, C.POINTER(abi.SelectSummary)]
+    L.oracle_select_k1.argtypes = [C.POINTER(abi.SelectIn), dp, dp, ip, dp, C.POINTER(abi.SelectSummary)]
     L.oracle_logdet.argtypes = [dp, i32]
     L.oracle_logdet.restype = d
     _lib = L

@@ -76,6 +76,8 @@ def load():
     L.ref_fm_dump.argtypes = [vp, i32, ip, ip, ip, dp]
     L.ref_sel_create.argtypes = [C.POINTER(abi.Camera), dp, dp, d, d, i32, i32]
     L.ref_sel_create.restype = vp
+    L.ref_sel_create_gt.argtypes = [C.POINTER(abi.Camera), dp, dp, d, d, i32, i32, C.c_char_p]
+    L.ref_sel_create_gt.restype = vp
     L.ref_sel_destroy.argtypes = [vp]
     L.ref_sel_destroy.restype = None
     L.ref_sel_set_backend.argtypes = [vp, dp, dp, dp, i32, ip, ip, ip, dp, dp, ip]

@@ -516,7 +516,7 @@ def _selector_scene(pkg, seed, N, U, C):
               flag=rng.choice([1, 1, 1, 1, 0, 2], C).astype(np.int32))
     used_id = np.arange(1, U + 1, dtype=np.int32)
     cand_id = (1000 + np.sort(rng.choice(4 * N, size=N, replace=False))).astype(np.int32)
-    return dict(cam=cam, ric=ric, tic=tic, qic=S.rot_to_quat(ric), poses=poses, vel_k=vel_k, ba_k=ba_k, P1=P1, Q1=Q1, V1=V1,
+    return dict(traj=traj, cam=cam, ric=ric, tic=tic, qic=S.rot_to_quat(ric), poses=poses, vel_k=vel_k, ba_k=ba_k, P1=P1, Q1=Q1, V1=V1,
                 a1=a1, w1=w1, lm=lm, used_id=used_id, used_xy=sample_xy(U), cand_id=cand_id, cand_xy=sample_xy(N),
                 cand_prob=rng.uniform(0.05, 1.0, N))
 
@@ -540,7 +540,7 @@ def _cloud_numpy(pkg, sc):
     return np.array(xy).reshape(-1, 2), np.array(dep)
 
 
-def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None, twins=0, acc_var=None, acc_bias_var=None):
+def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None, twins=0, acc_var=None, acc_bias_var=None, gt_csv=None):
     """Runs the reference's FeatureSelector::select on a synthetic scene; returns (ids it selected, the same problem as
     the C-ABI's bvio_select_in inputs).  The horizon for the latter comes from the numpy restatement in
     tests/test_horizon.py unless an oracle is given."""
@@ -556,7 +556,16 @@ def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None, twins=
     f = lambda a: np.ascontiguousarray(a, np.float64)
     acc_var = S.ACC_N if acc_var is None else acc_var
     acc_bias_var = S.ACC_W if acc_bias_var is None else acc_bias_var
-    h = ref.ref_sel_create(C.byref(cam_c), abi.dptr(f(sc["qic"])), abi.dptr(f(sc["tic"])), acc_var, acc_bias_var, U + kappa, 0)
+    if gt_csv is not None:                                # USE_GT: a csv of the scene's own trajectory, first row = frame k
+        tr = sc["traj"]
+        with open(gt_csv, "w") as fh:
+            fh.write("#timestamp,p,q,v,bw,ba\n")
+            for k in range(800):
+                t = 3.0 + k / 200.0
+                p, q, v = tr.pos(t), S.rot_to_quat(tr.rot(t)), tr.vel(t)
+                fh.write(",".join([str(1403636580838555648 + int(round(k * 5e6)))] + [repr(float(x)) for x in (*p, q[3], q[0], q[1], q[2], *v, 0, 0, 0, 0, 0, 0)]) + "\n")
+    h = ref.ref_sel_create_gt(C.byref(cam_c), abi.dptr(f(sc["qic"])), abi.dptr(f(sc["tic"])), acc_var, acc_bias_var, U + kappa, 0,
+                              gt_csv.encode() if gt_csv is not None else None)
     lm = sc["lm"]
     ref.ref_sel_set_backend(h, abi.dptr(f(sc["poses"].reshape(-1))), abi.dptr(f(sc["vel_k"])), abi.dptr(f(sc["ba_k"])),
                             len(lm["id"]), abi.iptr(lm["id"]), abi.iptr(lm["start"]), abi.iptr(lm["nobs"]),
@@ -581,7 +590,11 @@ def reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, oracle=None, twins=
     delta_imu = ((100 + 1e-9 * 100000000) - (100 + 1e-9 * 0)) / nr          # header.stamp.toSec() arithmetic (:85-91)
     hp, hq = np.zeros((H + 1, 3)), np.zeros((H + 1, 4))
     pk, qk = f(sc["poses"][10, :3]), f(S.rot_to_quat(S.quat_to_rot(sc["poses"][10, 3:])))   # Rs[] -> Quaterniond
-    if oracle is not None:
+    if gt_csv is not None:                                # the GT-relative horizon, through the package's own generator
+        gh = pkg.horizon.GroundTruthHorizon(pkg.horizon.load_groundtruth_csv(gt_csv), H)
+        gh.generate(0.0, pk, qk, 0.1)                     # the previous frame's select() already moved the seek cursor one row
+        hp, hq = gh.generate(100.0, pk, qk, (100 + 1e-9 * 100000000) - (100 + 1e-9 * 0))
+    elif oracle is not None:
         oracle.oracle_horizon_imu(H, abi.dptr(pk), abi.dptr(qk), abi.dptr(f(sc["ba_k"])), abi.dptr(f(sc["P1"])), abi.dptr(f(sc["Q1"])),
                                   abi.dptr(f(sc["V1"])), abi.dptr(f(sc["a1"])), abi.dptr(f(sc["w1"])), nr, delta_imu, abi.dptr(hp), abi.dptr(hq))
     else:
@@ -960,3 +973,28 @@ def test_process_imu_prediction_row_f1(pkg, ref):
         Ri, T = S.quat_to_rot(pose[3:]), num.sum_dt
         Pd = pose[:3] + sb[:3] * T - 0.5 * G * T * T + Ri @ num.delta_p
         assert np.abs(Pd - P).max() <= 1e-4
+
+
+def test_select_ground_truth_horizon_mode(pkg, oracle, ref, tmp_path):
+    """USE_GT: the reference builds the horizon from the ground-truth csv (horizon.GroundTruthHorizon reproduces it) but
+    still back-projects the candidates with the IMU-propagated x_k+1 (state_k1_).  With that state given separately
+    (oracle_select_k1) the oracle reproduces the reference's GT-mode selection exactly.  bvio_select_in has one x_k+1
+    (horizon[1]) so far: the closest single-state call (IMU-propagated state in horizon[1])
+    picks the same features up to late, low-margin rounds."""
+    abi = pkg.abi
+    f = lambda a: np.ascontiguousarray(a, np.float64)
+    for seed, N, U, n_lm, kappa in ((0, 120, 0, 60, 25), (1, 150, 12, 80, 30)):
+        ref_ids, prob = reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, gt_csv=str(tmp_path / f"gt{seed}.csv"))
+        sc = _selector_scene(pkg, seed, N, U, n_lm)
+        assert np.abs(prob.horizon_pos[1] - sc["P1"]).max() > 1e-4          # the two x_k+1 really differ
+        hs, ss = abi.SelectHandle(prob), abi.SelectSummary()
+        out = np.zeros(kappa, np.int32)
+        assert oracle.oracle_select_k1(C.byref(hs.s), abi.dptr(f(sc["P1"])), abi.dptr(f(sc["Q1"])), abi.iptr(out), None, C.byref(ss)) == 0
+        assert len(ref_ids) > 0 and out[:ss.n_selected].tolist() == ref_ids.tolist(), (out[:ss.n_selected], ref_ids)
+        # single-state approximation available through the C-ABI today
+        prob.horizon_pos[1], prob.horizon_quat[1] = sc["P1"], sc["Q1"]
+        hs2, ss2 = abi.SelectHandle(prob), abi.SelectSummary()
+        out2 = np.zeros(kappa, np.int32)
+        assert oracle.oracle_select(C.byref(hs2.s), abi.iptr(out2), None, C.byref(ss2)) == 0
+        common = len(set(out2[:ss2.n_selected].tolist()) & set(ref_ids.tolist()))
+        assert common >= 0.8 * len(ref_ids) and out2[:5].tolist() == ref_ids[:5].tolist()
