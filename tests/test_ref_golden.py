@@ -1,6 +1,6 @@
 """Golden vectors produced by the REFERENCE's own compiled code (tests/golden/ref_*.npz, made by
 tests/golden/make_ref_golden.py from oracle/_ref/libvins_ref.so).  They travel where the library cannot be rebuilt: the
-oracle must reproduce them (CPU suite) and the CUDA path must match them (GPU suite)."""
+oracle must reproduce them (here) and the CUDA path must match them (tests/test_zz_gpu_vs_reference.py)."""
 import ctypes as C
 import os
 
@@ -81,29 +81,3 @@ def test_oracle_matches_reference_selection_vector(pkg, oracle, name):
     out = np.zeros(prob.kappa, np.int32)
     assert oracle.oracle_select(C.byref(hs.s), abi.iptr(out), None, C.byref(ss)) == 0
     assert out[:ss.n_selected].tolist() == d["out_ids"].tolist()
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", SEL)
-def test_cuda_matches_reference_selection_vector(pkg, name):
-    abi = pkg.abi
-    d = np.load(os.path.join(GOLD, name))
-    prob = golden_io.select_from_dict(d)
-    ctx = pkg.lib.Context(0)
-    hs, ss = abi.SelectHandle(prob), abi.SelectSummary()
-    out = np.zeros(prob.kappa, np.int32)
-    ctx.check(ctx.L.bvio_select(ctx.h, C.byref(hs.s), abi.iptr(out), None, C.byref(ss)), "bvio_select")
-    ctx.close()
-    assert out[:ss.n_selected].tolist() == d["out_ids"].tolist()
-
-
-@pytest.mark.gpu
-def test_cuda_matches_reference_marginalization_vector(pkg):
-    d, w = _marg_case()
-    ctx = pkg.lib.Context(0)
-    p = run_marg(pkg.abi, ctx.L.bvio_marginalize, w, 0, ctx=ctx.h)
-    ctx.close()
-    H, g = info_in_state_coords(p, w.K, lambda f: f + 1)
-    assert p["n"] == int(d["out_n"][0])
-    assert np.abs(H - d["out_H"]).max() <= 2e-7 * np.abs(d["out_H"]).max()
-    assert np.abs(g - d["out_g"]).max() <= 1e-4 * max(np.abs(d["out_g"]).max(), 1.0)

@@ -1,13 +1,16 @@
 """GPU parity against the REFERENCE's own code, directly: libbvio.so next to oracle/_ref/libvins_ref.so (the reference's
 sources compiled here from /root/reference, see tests/test_reference_pin.py; the prebuilt library travels to the GPU
-box).  Skipped when that library is absent."""
+box), and against the golden vectors that code produced (tests/golden/ref_*.npz).  The library-based tests are skipped
+when the library is absent.  (File name: sorts last, after the suites whose device side was exercised first.)"""
 import ctypes as C
 
 import numpy as np
 import pytest
 
+import golden_io
 import ref_lib
 from test_oracle_marg import info_in_state_coords, run_marg
+from test_ref_golden import GOLD, SEL, _marg_case
 
 pytestmark = pytest.mark.gpu
 
@@ -72,3 +75,27 @@ def test_cuda_linearization_matches_reference_cost_functions(pkg, ref, seed, L, 
     assert abs(c[0] - cost_r) <= 1e-9 * cost_r
     assert np.abs(h - h_r).max() <= 1e-9 * np.abs(h_r).max() and np.abs(b - b_r).max() <= 1e-8 * np.abs(b_r).max()
     assert np.abs(S - S_r).max() <= 1e-6 * np.abs(S_r).max() and np.abs(g - g_r).max() <= 1e-6 * np.abs(g_r).max()
+
+
+@pytest.mark.parametrize("name", SEL)
+def test_cuda_matches_reference_selection_vector(pkg, name):
+    abi = pkg.abi
+    d = np.load(os.path.join(GOLD, name))
+    prob = golden_io.select_from_dict(d)
+    ctx = pkg.lib.Context(0)
+    hs, ss = abi.SelectHandle(prob), abi.SelectSummary()
+    out = np.zeros(prob.kappa, np.int32)
+    ctx.check(ctx.L.bvio_select(ctx.h, C.byref(hs.s), abi.iptr(out), None, C.byref(ss)), "bvio_select")
+    ctx.close()
+    assert out[:ss.n_selected].tolist() == d["out_ids"].tolist()
+
+
+def test_cuda_matches_reference_marginalization_vector(pkg):
+    d, w = _marg_case()
+    ctx = pkg.lib.Context(0)
+    p = run_marg(pkg.abi, ctx.L.bvio_marginalize, w, 0, ctx=ctx.h)
+    ctx.close()
+    H, g = info_in_state_coords(p, w.K, lambda f: f + 1)
+    assert p["n"] == int(d["out_n"][0])
+    assert np.abs(H - d["out_H"]).max() <= 2e-7 * np.abs(d["out_H"]).max()
+    assert np.abs(g - d["out_g"]).max() <= 1e-4 * max(np.abs(d["out_g"]).max(), 1.0)
