@@ -518,6 +518,7 @@ class ReplaySession(SlidingWindowSim):
     def _ingest(self):
         ms, img = self._pending
         dt, acc, gyr = self.RP.imu_segment(self.clock, ms, img.stamp, self.td)
+        self.last_segment = (dt, acc, gyr)                 # what Estimator::processIMU receives for this frame
         image = self.RP.image_from_pointcloud(img)
         K = self.K
         if len(self.pose) == 0:

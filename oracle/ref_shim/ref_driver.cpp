@@ -542,6 +542,7 @@ struct EstHook {
   int L = 0;
   std::vector<double> H, g;   // normal equations of the whole problem at entry, local coordinates
   int dim = 0;
+  bool session = false;
   ceres::Problem* live = nullptr;      // valid only while the solve callback runs
   void (*callback)(void) = nullptr;    // external trust-region driver (tests): called instead of injecting a solution
 } g_hook;
@@ -550,6 +551,13 @@ void (*g_solve_callback)(void) = nullptr;
 void est_solve_hook(const ceres::Solver::Options& o, ceres::Problem* pb, ceres::Solver::Summary*) {
   EstHook& h = g_hook;
   Estimator& e = *h.est;
+  if (h.session) {                      // a live Estimator fed frame by frame (ref_est_*): only the external solve
+    h.L = e.f_manager.getFeatureCount();
+    h.live = pb;
+    if (g_solve_callback) g_solve_callback();
+    h.live = nullptr;
+    return;
+  }
   memcpy(h.entry_pose, e.para_Pose, sizeof(double) * 7 * (WINDOW_SIZE + 1));
   memcpy(h.entry_sb, e.para_SpeedBias, sizeof(double) * 9 * (WINDOW_SIZE + 1));
   memcpy(h.entry_ex, e.para_Ex_Pose, sizeof(double) * 7);
@@ -908,5 +916,73 @@ void ref_estimator_process_imu(const double* pose, const double* sb, const doubl
   for (int k = 0; k < n; ++k) e->processIMU(dt[k], v3(acc + 3 * k), v3(gyr + 3 * k));
   for (int a = 0; a < 3; ++a) { out_P[a] = e->Ps[1](a); out_V[a] = e->Vs[1](a); for (int b = 0; b < 3; ++b) out_R[3 * a + b] = e->Rs[1](a, b); }
   store(*e->pre_integrations[1], out_pre);
+}
+}  // extern "C"
+
+
+// ---- a live Estimator fed frame by frame: processIMU / processImage (estimator.cpp:86-186) with the external solve ---------------
+extern "C" {
+void* ref_est_create(const double* ex, const double* G_, double focal, int max_iters, double acc_n, double gyr_n, double acc_w,
+                     double gyr_w, double init_depth, double min_parallax) {
+  ACC_N = acc_n; GYR_N = gyr_n; ACC_W = acc_w; GYR_W = gyr_w; TD = 0; TR = 0; ROW = 480;
+  INIT_DEPTH = init_depth; MIN_PARALLAX = min_parallax;
+  ESTIMATE_EXTRINSIC = 0; ESTIMATE_TD = 0; NUM_ITERATIONS = max_iters; SOLVER_TIME = 0.04;
+  G = v3(G_);
+  RIC.assign(1, Eigen::Quaterniond(ex[6], ex[3], ex[4], ex[5]).toRotationMatrix());
+  TIC.assign(1, v3(ex));
+  void* mem = calloc(1, sizeof(Estimator));
+  Estimator* e = new (mem) Estimator();
+  e->setParameter();
+  e->g = G;
+  ProjectionFactor::sqrt_info = focal / 1.5 * Eigen::Matrix2d::Identity();
+  g_hook = EstHook();
+  g_hook.est = e; g_hook.session = true;
+  ceres::solve_hook() = est_solve_hook;
+  return e;
+}
+void ref_est_release(void*) { g_hook = EstHook(); ceres::solve_hook() = nullptr; }     // the Estimator itself is leaked (see above)
+void ref_est_set_state(void* h, int i, const double* pose, const double* sb) {
+  Estimator* e = static_cast<Estimator*>(h);
+  e->Ps[i] = v3(pose); e->Rs[i] = Eigen::Quaterniond(pose[6], pose[3], pose[4], pose[5]).toRotationMatrix();
+  e->Vs[i] = v3(sb); e->Bas[i] = v3(sb + 3); e->Bgs[i] = v3(sb + 6);
+}
+void ref_est_set_bias(void* h, int i, const double* ba, const double* bg) {
+  Estimator* e = static_cast<Estimator*>(h);
+  e->Bas[i] = v3(ba); e->Bgs[i] = v3(bg);
+}
+void ref_est_get_states(void* h, double* poses, double* sb) {
+  Estimator* e = static_cast<Estimator*>(h);
+  for (int i = 0; i <= WINDOW_SIZE; ++i) {
+    Eigen::Quaterniond q(e->Rs[i]);
+    for (int a = 0; a < 3; ++a) { poses[7 * i + a] = e->Ps[i](a); sb[9 * i + a] = e->Vs[i](a); sb[9 * i + 3 + a] = e->Bas[i](a); sb[9 * i + 6 + a] = e->Bgs[i](a); }
+    poses[7 * i + 3] = q.x(); poses[7 * i + 4] = q.y(); poses[7 * i + 5] = q.z(); poses[7 * i + 6] = q.w();
+  }
+}
+void ref_est_set_nonlinear(void* h) { static_cast<Estimator*>(h)->solver_flag = Estimator::NON_LINEAR; }
+int ref_est_frame_count(void* h) { return static_cast<Estimator*>(h)->frame_count; }
+int ref_est_prior_size(void* h) { Estimator* e = static_cast<Estimator*>(h); return e->last_marginalization_info ? e->last_marginalization_info->n : -1; }
+void ref_est_process_imu(void* h, int n, const double* dt, const double* acc, const double* gyr) {
+  Estimator* e = static_cast<Estimator*>(h);
+  for (int k = 0; k < n; ++k) e->processIMU(dt[k], v3(acc + 3 * k), v3(gyr + 3 * k));
+}
+// -> marginalization_flag the reference decided for this frame (0 MARGIN_OLD, 1 MARGIN_SECOND_NEW)
+int ref_est_process_image(void* h, double stamp, int n, const int32_t* ids, const double* xy) {
+  Estimator* e = static_cast<Estimator*>(h);
+  map<int, vector<pair<int, Eigen::Matrix<double, 7, 1>>>> image;
+  for (int i = 0; i < n; ++i) {
+    Eigen::Matrix<double, 7, 1> v; v.setZero(); v(0) = xy[2 * i]; v(1) = xy[2 * i + 1]; v(2) = 1.0;
+    image[ids[i]].emplace_back(0, v);
+  }
+  std_msgs::Header header; header.stamp = ros::Time(stamp);
+  e->processImage(image, header);
+  return (int)e->marginalization_flag;
+}
+int ref_est_dump_features(void* h, int cap, int32_t* ids, int32_t* start, int32_t* nobs, double* depth) {
+  int k = 0;
+  for (auto& f : static_cast<Estimator*>(h)->f_manager.feature) {
+    if (k < cap) { ids[k] = f.feature_id; start[k] = f.start_frame; nobs[k] = (int)f.feature_per_frame.size(); depth[k] = f.estimated_depth; }
+    ++k;
+  }
+  return k;
 }
 }  // extern "C"

@@ -102,5 +102,23 @@ def load():
                                       i32, ip, ip, ip, dp]
     L.ref_estimator_process_imu.argtypes = [dp, dp, dp, i32, dp, dp, dp, dp, d, d, d, d, dp, dp, dp, PP]
     L.ref_estimator_process_imu.restype = None
+    L.ref_est_create.argtypes = [dp, dp, d, i32, d, d, d, d, d, d]
+    L.ref_est_create.restype = vp
+    L.ref_est_release.argtypes = [vp]
+    L.ref_est_release.restype = None
+    L.ref_est_set_state.argtypes = [vp, i32, dp, dp]
+    L.ref_est_set_state.restype = None
+    L.ref_est_set_bias.argtypes = [vp, i32, dp, dp]
+    L.ref_est_set_bias.restype = None
+    L.ref_est_get_states.argtypes = [vp, dp, dp]
+    L.ref_est_get_states.restype = None
+    L.ref_est_set_nonlinear.argtypes = [vp]
+    L.ref_est_set_nonlinear.restype = None
+    L.ref_est_frame_count.argtypes = [vp]
+    L.ref_est_prior_size.argtypes = [vp]
+    L.ref_est_process_imu.argtypes = [vp, i32, dp, dp, dp]
+    L.ref_est_process_imu.restype = None
+    L.ref_est_process_image.argtypes = [vp, d, i32, ip, dp]
+    L.ref_est_dump_features.argtypes = [vp, i32, ip, ip, ip, dp]
     _lib = L
     return L

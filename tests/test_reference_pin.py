@@ -998,3 +998,106 @@ def test_select_ground_truth_horizon_mode(pkg, oracle, ref, tmp_path):
         assert oracle.oracle_select(C.byref(hs2.s), abi.iptr(out2), None, C.byref(ss2)) == 0
         common = len(set(out2[:ss2.n_selected].tolist()) & set(ref_ids.tolist()))
         assert common >= 0.8 * len(ref_ids) and out2[:5].tolist() == ref_ids[:5].tolist()
+
+
+def test_closed_loop_session_against_the_reference_estimator_row_f1(pkg, oracle, ref, tmp_path):
+    """A whole session, frame by frame, through the reference's own Estimator::processIMU / processImage
+    (addFeatureCheckParallax -> triangulate -> optimization -> double2vector -> marginalization -> slideWindow ->
+    removeFailures; Ceres' control flow supplied by np_ref.trust_region_loop on the live problem) next to
+    slider.ReplaySession on the oracle backend, both fed the same recorded IMU / feature traffic and the same bootstrap
+    states.  Keyframe decisions, window states, biases, feature lists and depths must stay together for the whole run."""
+    from slider_backends import OracleBackend
+    from test_replay import _record_session
+    abi, sl, rp, S = pkg.abi, pkg.slider, pkg.replay, pkg.synth
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)
+    path = str(tmp_path / "session.bvio")
+    rec = _record_session(pkg, path, seed=4, frames=30, frame_dt=0.04)      # 25 Hz: keyframes and non-keyframes alternate
+    ses = sl.ReplaySession(S.EUROC_CAM, rec["ric"], rec["tic"], rec["init"], max_feats=70, H=10,
+                           opts=dict(max_iters=8, strategy=1), keyframes="parallax")
+    be = OracleBackend(oracle, abi)
+    K, WS = ses.K, ses.K - 1
+    ex = f64(np.concatenate([rec["tic"], S.rot_to_quat(rec["ric"])]))
+    G = f64([0, 0, S.G_NORM])
+    h = ref.ref_est_create(abi.dptr(ex), abi.dptr(G), 460.0, 8, S.ACC_N, S.GYR_N, S.ACC_W, S.GYR_W, sl.INIT_DEPTH, sl.MIN_PARALLAX)
+
+    def solve():                                           # Ceres' control flow, traditional dogleg like the reference
+        nr, nl, ng = C.c_int32(), C.c_int32(), C.c_int32()
+        assert ref.ref_live_dims(C.byref(nr), C.byref(nl), C.byref(ng)) == 0
+        nr, nl, ng = nr.value, nl.value, ng.value
+        L = nl - (15 * K + 7)
+        free = np.r_[np.arange(15 * K), 15 * K + 7 + np.arange(L)].astype(int)
+        gfree = np.r_[np.arange(16 * K), 16 * K + 8 + np.arange(L)].astype(int)
+        x0 = np.zeros(ng)
+        ref.ref_live_get_state(abi.dptr(x0))
+
+        def evaluate(x):
+            ref.ref_live_set_state(abi.dptr(f64(x)))
+            J, r, c = np.zeros(nr * nl), np.zeros(nr), np.zeros(1)
+            assert ref.ref_live_evaluate(abi.dptr(J), abi.dptr(r), abi.dptr(c)) == 0
+            return J.reshape(nr, nl)[:, free], r, float(c[0])
+
+        def plus(x, d):
+            full, out = np.zeros(nl), np.zeros(ng)
+            full[free] = d
+            ref.ref_live_plus(abi.dptr(f64(x)), abi.dptr(full), abi.dptr(out))
+            return out
+        x, _, _ = np_ref.trust_region_loop(x0, evaluate, plus, lambda x: x[gfree], strategy=1, max_iters=8)
+        ref.ref_live_set_state(abi.dptr(f64(x)))
+    cb = ref.SOLVE_CB(solve)
+    ref.ref_set_solve_callback(C.cast(cb, C.c_void_p))
+    frame_obs = {}
+
+    def newest_obs():
+        idx = len(ses.pose) - 1
+        return {lid: np.array(t.xy[-1]) for lid, t in ses.tracks.items() if t.start + len(t.xy) - 1 == idx}
+    orig_old, orig_new = ses._slide, ses._slide_new
+    ses._slide = lambda: (frame_obs.update(newest_obs()), orig_old())
+    ses._slide_new = lambda: (frame_obs.update(newest_obs()), orig_new())
+    n_checked, flags, worst = 0, [], 0.0
+    try:
+        f = 0
+        for topic, msg in rp.read_dump(path):
+            for lat in ses.feed(topic, msg, be):
+                full = lat is not None
+                if not full:
+                    frame_obs.update(newest_obs())
+                dt, acc, gyr = ses.last_segment
+                fc = min(f, WS)
+                if 1 <= f <= WS:                              # the bias the interval's preintegration is linearised at
+                    ref.ref_est_set_bias(h, fc, abi.dptr(f64(rec["init"][f - 1][1][3:6])), abi.dptr(f64(rec["init"][f - 1][1][6:9])))
+                ref.ref_est_process_imu(h, len(dt), abi.dptr(f64(dt)), abi.dptr(f64(acc.reshape(-1))), abi.dptr(f64(gyr.reshape(-1))))
+                if f <= WS:                                   # the stand-in for the initializer
+                    ref.ref_est_set_state(h, fc, abi.dptr(f64(rec["init"][f][0])), abi.dptr(f64(rec["init"][f][1])))
+                if f == WS:
+                    ref.ref_est_set_nonlinear(h)
+                ids = np.array(sorted(frame_obs), np.int32)
+                xy = f64([frame_obs[int(i)] for i in ids]).reshape(-1)
+                flag = ref.ref_est_process_image(h, ses.t, len(ids), abi.iptr(ids), abi.dptr(xy))
+                frame_obs.clear()
+                if full:
+                    assert flag == lat["flag"], (f, flag, lat["flag"])
+                    flags.append(flag)
+                    poses, sb = np.zeros((K, 7)), np.zeros((K, 9))
+                    ref.ref_est_get_states(h, abi.dptr(poses), abi.dptr(sb))
+                    sgn = np.sign(np.sum(poses[:WS, 3:] * ses.pose[:, 3:], axis=1))[:, None]
+                    dpos = np.abs(poses[:WS, :3] - ses.pose[:, :3]).max()
+                    dq = np.abs(poses[:WS, 3:] * sgn - ses.pose[:, 3:]).max()
+                    dsb = np.abs(sb[:WS] - ses.sb).max()
+                    worst = max(worst, dpos, dq, dsb)
+                    assert dpos <= 1e-5 and dq <= 1e-5 and dsb <= 1e-4, (f, dpos, dq, dsb)
+                    cap = len(ses.tracks) + 64
+                    d_id, d_st, d_n, d_dep = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+                    nf = ref.ref_est_dump_features(h, cap, abi.iptr(d_id), abi.iptr(d_st), abi.iptr(d_n), abi.dptr(d_dep))
+                    dump = {int(i): (int(s), int(k), float(x)) for i, s, k, x in zip(d_id[:nf], d_st[:nf], d_n[:nf], d_dep[:nf])}
+                    assert set(dump) == set(ses.tracks), (f, set(dump) ^ set(ses.tracks))
+                    for lid, t in ses.tracks.items():
+                        assert dump[lid][:2] == (t.start, len(t.xy)), (f, lid)
+                        assert abs(dump[lid][2] - t.depth) <= 1e-4 * max(abs(t.depth), 1.0), (f, lid, dump[lid][2], t.depth)
+                    assert ref.ref_est_prior_size(h) == (ses.prior["n"] if ses.prior is not None else -1)
+                    n_checked += 1
+                f += 1
+    finally:
+        ref.ref_set_solve_callback(None)
+        ref.ref_est_release(h)
+    assert n_checked >= 10 and 0 in flags and 1 in flags, (n_checked, flags)
+    print("closed loop vs reference: frames", n_checked, "flags", flags, "worst state difference", worst)
