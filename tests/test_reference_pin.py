@@ -1,10 +1,13 @@
 """CPU suite: the oracle against the REFERENCE's own code.
 
-oracle/_ref/libvins_ref.so holds the reference's factor sources (projection_factor.cpp, projection_td_factor.cpp,
-imu_factor.h + integration_base.h, pose_local_parameterization.cpp, marginalization_factor.cpp, utility.h) compiled
-unmodified from /root/reference against the stand-in Eigen / Ceres / ROS headers of oracle/ref_shim/ (the real libraries
-are absent from this image).  Every test feeds identical inputs to a reference entry point and to the oracle
-restatement of the same SURVEY section-8 row."""
+oracle/_ref/libvins_ref.so holds the reference's sources for the path -- factor/{projection_factor,
+projection_td_factor, pose_local_parameterization, marginalization_factor}.cpp, imu_factor.h + integration_base.h,
+utility.{h,cpp}, feature_manager.cpp, utility/horizon_generator.cpp, feature_selector.cpp (with the vendored nanoflann)
+and estimator.cpp -- compiled unmodified from /root/reference against the stand-in Eigen / Ceres / ROS / OpenCV headers
+of oracle/ref_shim/ (the real libraries are absent from this image; the only code of Ceres' that is missing is its
+solver, whose control flow np_ref.trust_region_loop supplies where a test needs the reference to iterate).
+Every test feeds identical inputs to a reference entry point and to the oracle restatement of the same SURVEY
+section-8 row, or runs the two side by side over a session."""
 import ctypes as C
 import dataclasses
 
