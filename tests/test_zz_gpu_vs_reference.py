@@ -99,3 +99,43 @@ def test_cuda_matches_reference_marginalization_vector(pkg):
     assert p["n"] == int(d["out_n"][0])
     assert np.abs(H - d["out_H"]).max() <= 2e-7 * np.abs(d["out_H"]).max()
     assert np.abs(g - d["out_g"]).max() <= 1e-4 * max(np.abs(d["out_g"]).max(), 1.0)
+
+
+@pytest.mark.parametrize("skip", [3, 1])
+def test_cuda_leaves_out_imu_intervals_longer_than_10s(pkg, oracle, skip):
+    """`if (pre_integrations[j]->sum_dt > 10.0) continue;` (estimator.cpp:705) and the `< 10.0` test of the MARGIN_OLD
+    branch (:846): the device's linearization, solve and marginalization against the oracle (which the reference's
+    compiled Estimator::optimization() confirms on the same case, tests/test_reference_pin.py)."""
+    import dataclasses
+    abi, synth = pkg.abi, pkg.synth
+    K = 11
+    w = synth.make_window(seed=5 + skip, K=K, L=60)
+    w.preint[skip, 16] = 11.0
+    ctx = pkg.lib.Context(0)
+    o = abi.default_opts()
+    npar = 15 * K
+    out = []
+    for dev in (True, False):
+        hw = abi.WindowHandle(w)
+        S, g, h, b, c = np.zeros((npar, npar)), np.zeros(npar), np.zeros(w.L), np.zeros(w.L), np.zeros(1)
+        if dev:
+            ctx.check(ctx.L.bvio_debug_linearize(ctx.h, C.byref(hw.s), C.byref(o), abi.dptr(S), abi.dptr(g), abi.dptr(h), abi.dptr(b),
+                                                 abi.dptr(c)), "debug_linearize")
+        else:
+            assert oracle.oracle_linearize(C.byref(hw.s), C.byref(o), abi.dptr(S), abi.dptr(g), abi.dptr(h), abi.dptr(b), abi.dptr(c)) == 0
+        out.append((S, g, c[0]))
+    (S1, g1, c1), (S2, g2, c2) = out
+    assert abs(c1 - c2) <= 1e-11 * c2 and np.abs(S1 - S2).max() <= 1e-9 * np.abs(S2).max() and np.abs(g1 - g2).max() <= 1e-9 * max(np.abs(g2).max(), 1.0)
+    hg, ho, sg, so = abi.WindowHandle(w), abi.WindowHandle(w), abi.Summary(), abi.Summary()
+    ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(hg.s), C.byref(o), C.byref(sg)), "bvio_optimize")
+    assert oracle.oracle_optimize(C.byref(ho.s), C.byref(o), C.byref(so)) == 0
+    assert (sg.iterations, sg.num_accepted, sg.termination) == (so.iterations, so.num_accepted, so.termination)
+    assert np.linalg.norm(hg.state_vector() - ho.state_vector()) <= 1e-6 * np.linalg.norm(ho.state_vector())
+    wpost = dataclasses.replace(w, para_pose=ho.pose.copy(), para_speed_bias=ho.sb.copy(), inv_depth=ho.inv.copy())
+    pg = run_marg(abi, ctx.L.bvio_marginalize, wpost, 0, ctx=ctx.h)
+    ctx.close()
+    po = run_marg(abi, oracle.oracle_marginalize, wpost, 0)
+    assert pg["n"] == po["n"] == (66 if skip == 1 else 75)
+    Hg, gg = info_in_state_coords(pg, K, lambda f: f + 1)
+    Ho, go = info_in_state_coords(po, K, lambda f: f + 1)
+    assert np.abs(Hg - Ho).max() <= 1e-7 * np.abs(Ho).max() and np.abs(gg - go).max() <= 5e-5 * max(np.abs(go).max(), 1.0)
