@@ -3,6 +3,7 @@ sources compiled here from /root/reference, see tests/test_reference_pin.py; the
 box), and against the golden vectors that code produced (tests/golden/ref_*.npz).  The library-based tests are skipped
 when the library is absent.  (File name: sorts last, after the suites whose device side was exercised first.)"""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
