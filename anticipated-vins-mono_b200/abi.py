@@ -77,7 +77,8 @@ class SelectIn(C.Structure):
                 ("N", C.c_int32), ("cand_id", c_int32_p), ("cand_xy", c_double_p), ("cand_prob", c_double_p),
                 ("U", C.c_int32), ("used_id", c_int32_p), ("used_xy", c_double_p),
                 ("C", C.c_int32), ("cloud_xy", c_double_p), ("cloud_depth", c_double_p),
-                ("kappa", C.c_int32)]
+                ("kappa", C.c_int32),
+                ("state_k1_pos", c_double_p), ("state_k1_quat", c_double_p), ("omega_prior", c_double_p)]
 
 
 class SelectSummary(C.Structure):
@@ -199,6 +200,13 @@ class SelectHandle:
         s.cloud_xy = dptr(self.clxy) if s.C else None
         s.cloud_depth = dptr(self.cld) if s.C else None
         s.kappa = p.kappa
+        # ABI v2 optional inputs
+        self.k1p = f64(p.state_k1_pos) if getattr(p, "state_k1_pos", None) is not None else None
+        self.k1q = f64(p.state_k1_quat) if getattr(p, "state_k1_quat", None) is not None else None
+        self.omp = f64(p.omega_prior).reshape(81) if getattr(p, "omega_prior", None) is not None else None
+        s.state_k1_pos = dptr(self.k1p) if self.k1p is not None else None
+        s.state_k1_quat = dptr(self.k1q) if self.k1q is not None else None
+        s.omega_prior = dptr(self.omp) if self.omp is not None else None
         self.s = s
 
 

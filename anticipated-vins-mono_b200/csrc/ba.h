@@ -42,6 +42,7 @@ struct BaCtrl {                   // per-window LM state, lives in HBM
   double dsum[6];                 // pose parts of the dogleg dot products (ba_solve -> ba_dogleg)
   double ca, cb;                  // step = ca * (scaled gradient direction t) + cb * (Gauss-Newton step)
   double step_norm;               // |step| in Ceres' diagonally scaled space (drives the radius update)
+  unsigned long long t0_ns;       // %globaltimer at the reset of this solve (max_solver_time_in_seconds cut)
 };
 
 // per-(window,tile) output record of ba_linearize, in doubles:
@@ -68,6 +69,7 @@ struct BaBatch {                  // all pointers are device pointers
   int est_td;                     // estimate_td: +1 dim (after the extrinsic block), pseudo-frame K + est_ex
   double sqrt_info, cauchy_a, G[3];
   double function_tolerance, gradient_tolerance, parameter_tolerance, initial_radius, min_relative_decrease;
+  double max_time_s;              // options.max_solver_time_in_seconds (estimator.cpp:799-806); 0 = no cut
   // structure
   const int* lm_base;             // [B+1] first global landmark of each window
   const int* lm_off;              // [total_L+1] CSR: global observation offsets

@@ -133,6 +133,9 @@ static int validate_msg(const bvio_window* w, const bvio_opts* o, int K0, const 
     const bvio_prior* p = w->prior;
     if (p->n < 0 || p->n > 256 || p->nblocks < 0 || p->nblocks > PRIOR_MAXB)
       { *msg = "prior dimension out of range"; return BVIO_ERR_INVALID; }
+    if (p->nblocks > 0 && (!p->block_kind || !p->block_frame || !p->block_idx || !p->x0))
+      { *msg = "null prior block arrays"; return BVIO_ERR_INVALID; }
+    if (p->n > 0 && (!p->lin_jac || !p->lin_res)) { *msg = "null prior lin_jac / lin_res"; return BVIO_ERR_INVALID; }
     for (int b = 0; b < p->nblocks; b++) {
       int kind = p->block_kind[b], loc = kind == BVIO_BLK_SPEEDBIAS ? 9 : (kind == BVIO_BLK_TD ? 1 : 6);
       if (kind < 0 || kind > 3 || p->block_idx[b] < 0 || p->block_idx[b] + loc > p->n)
@@ -212,6 +215,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bt.function_tolerance = o->function_tolerance; bt.gradient_tolerance = o->gradient_tolerance;
   bt.parameter_tolerance = o->parameter_tolerance; bt.initial_radius = o->initial_radius;
   bt.min_relative_decrease = o->min_relative_decrease;
+  bt.max_time_s = o->max_time_s > 0.0 ? o->max_time_s : 0.0;
   bb->debug = debug;
 
   // ---- carve: inputs | outputs | scratch
@@ -445,9 +449,11 @@ int bvio_batch_solve(bvio_ctx* ctx, bvio_batch* bb) {
       cudaGraph_t g = nullptr;
       BVIO_CUDA_OK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
       bb->launches_per_solve = enqueue_solve(ctx, bb, ctx->stream);
-      BVIO_CUDA_OK(ctx, cudaStreamEndCapture(ctx->stream, &g));
-      BVIO_CUDA_OK(ctx, cudaGraphInstantiate(&bb->graph, g, 0));
-      cudaGraphDestroy(g);
+      // always leave capture mode, whatever happened inside, and never leak the graph
+      cudaError_t ec = cudaStreamEndCapture(ctx->stream, &g);
+      if (ec == cudaSuccess) ec = cudaGraphInstantiate(&bb->graph, g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (ec != cudaSuccess) { bb->graph = nullptr; BVIO_CUDA_OK(ctx, ec); }
       // the event recorded before the capture is still valid; re-record so ev0 directly precedes the launch
       BVIO_CUDA_OK(ctx, cudaEventRecord(bb->ev0, ctx->stream));
     }

@@ -20,6 +20,7 @@
 //   ba_marginalize    MarginalizationInfo::{preMarginalize, marginalize} (marginalization_factor.cpp:109-297)
 //
 // All reductions run in a fixed order: results are bit-reproducible run to run.
+#include <mutex>
 #include "ba.h"
 #include <float.h>
 
@@ -306,6 +307,12 @@ __global__ void __launch_bounds__(BA_THREADS) ba_prepare_kernel(BaBatch bt) {
   }
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void ba_reset_kernel(BaBatch bt) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (size_t k = i; k < (size_t)bt.B * bt.K * 7; k += stride) bt.pose[0][k] = bt.pose0[k];
@@ -321,6 +328,7 @@ __global__ void ba_reset_kernel(BaBatch bt) {
     c.first = 1; c.solve_ok = 0; c.invalid_run = 0; c.stepped = 0; c.ticket = 0; c.pad = 0;
     c.mu = 1e-8; c.ca = 0; c.cb = 1; c.step_norm = 0;
     for (int q = 0; q < 6; q++) c.dsum[q] = 0;
+    c.t0_ns = global_ns();
     bt.ctrl[k] = c;
   }
 }
@@ -1434,7 +1442,19 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
 // =============================================================================================
 // cost at the candidate + accept/reject
 // =============================================================================================
+__device__ void decide_step(const BaBatch& bt, int w, double cv, double ml, double s2, double x2);
+// Ceres checks max_solver_time_in_seconds after every iteration (TrustRegionMinimizer::
+// FinalizeIterationAndCheckIfMinimizerCanContinue); the reference sets it to SOLVER_TIME, or 4/5 of it when the oldest
+// frame is about to be marginalized (estimator.cpp:799-806).  Here the clock is the device's: time since the reset
+// kernel of this solve (the H2D copy before it is not counted).
 __device__ void decide(const BaBatch& bt, int w, double cv, double ml, double s2, double x2) {
+  decide_step(bt, w, cv, ml, s2, x2);
+  BaCtrl* c = bt.ctrl + w;
+  if (bt.max_time_s > 0.0 && !c->done && (double)(global_ns() - c->t0_ns) * 1e-9 >= bt.max_time_s) {
+    c->done = 1; c->termination = 5;   // BVIO_TERM_TIME
+  }
+}
+__device__ void decide_step(const BaBatch& bt, int w, double cv, double ml, double s2, double x2) {
   BaCtrl* c = bt.ctrl + w;
   c->stepped = 0;
   c->ticket = 0;
@@ -1837,9 +1857,16 @@ static size_t cost_smem(int K, int nmax) {
   return sizeof(double) * ((size_t)15 * K + 8 + (K + 1) * 7 + (K + 1) * FR + 160 + K * 9 + (K - 1) * 15 + 2 * nmax);
 }
 
-static bool g_tables_done = false;
+// __constant__ tables and the dynamic-shared-memory opt-ins are PER DEVICE: remember which devices of this process
+// have been set up (bvio_create may be called for several GPUs in one process)
+static std::mutex g_cfg_mutex;
+static unsigned long long g_cfg_devices[4] = {0, 0, 0, 0};
 int ba_configure(void) {
-  if (!g_tables_done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  const bool known = dev >= 0 && dev < 256 && ((g_cfg_devices[dev >> 6] >> (dev & 63)) & 1ull);
+  if (!known) {
     unsigned char ta[BVIO_KMAX * (BVIO_KMAX + 1) / 2], tb[BVIO_KMAX * (BVIO_KMAX + 1) / 2];
     int e = 0;
     for (int a = 0; a < BVIO_KMAX; a++) for (int b = 0; b <= a; b++) { ta[e] = a; tb[e] = b; e++; }
@@ -1865,7 +1892,7 @@ int ba_configure(void) {
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
-    g_tables_done = true;
+    if (dev >= 0 && dev < 256) g_cfg_devices[dev >> 6] |= 1ull << (dev & 63);
   }
   return 0;
 }

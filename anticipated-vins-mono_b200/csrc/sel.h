@@ -47,6 +47,9 @@ struct SelProb {
   int grid_persist, cpw;              // persistent single-kernel path: CTAs, candidates per warp (0 = not used)
   double delta_imu, acc_var, acc_bias_var;
   double q_ic[4], t_ic[3];
+  double k1_pos[3], k1_quat[4];       // state_k1_ (feature_selector.cpp:247-250): = horizon[1] unless the caller gave one
+  int has_prior;                      // omega_prior given: added instead of I9 (feature_selector.cpp:602-609)
+  double omega_prior[81];
   bvio_camera cam;
   const double* hpos;                 // [H+1][3]
   const double* hquat;                // [H+1][4] xyzw

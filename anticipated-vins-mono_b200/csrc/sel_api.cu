@@ -127,6 +127,10 @@ static int sel_upload_impl(bvio_ctx* ctx, const bvio_select_in* in, bool use_cac
   for (int i = 0; i < 4; i++) sp.q_ic[i] = in->q_ic[i];
   for (int i = 0; i < 3; i++) sp.t_ic[i] = in->t_ic[i];
   sp.cam = in->cam;
+  for (int i = 0; i < 3; i++) sp.k1_pos[i] = in->state_k1_pos ? in->state_k1_pos[i] : in->horizon_pos[3 + i];
+  for (int i = 0; i < 4; i++) sp.k1_quat[i] = in->state_k1_quat ? in->state_k1_quat[i] : in->horizon_quat[4 + i];
+  sp.has_prior = in->omega_prior ? 1 : 0;
+  for (int i = 0; i < 81; i++) sp.omega_prior[i] = in->omega_prior ? in->omega_prior[i] : 0.0;
   pr->sharded = sharded;
   // NCCL calls and the cooperative persistent kernel stay outside graph capture (5 launches anyway)
   pr->use_graph = !sharded && sp.grid_persist == 0;
@@ -295,11 +299,12 @@ int bvio_select_run(bvio_ctx* ctx, bvio_selprob* pr) {
       cudaGraph_t g = nullptr;
       BVIO_CUDA_OK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
       pr->launches_per_run = sel_enqueue(ctx, pr, ctx->stream, &nrc);
+      // always leave capture mode, whatever happened inside, and never leak the graph
       cudaError_t ee = cudaStreamEndCapture(ctx->stream, &g);
-      if (nrc) return fail(ctx, BVIO_ERR_NCCL, std::string("nccl: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
-      BVIO_CUDA_OK(ctx, ee);
-      BVIO_CUDA_OK(ctx, cudaGraphInstantiate(&pr->graph, g, 0));
-      cudaGraphDestroy(g);
+      if (ee == cudaSuccess && !nrc) ee = cudaGraphInstantiate(&pr->graph, g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (nrc) { pr->graph = nullptr; return fail(ctx, BVIO_ERR_NCCL, std::string("nccl: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?")); }
+      if (ee != cudaSuccess) { pr->graph = nullptr; BVIO_CUDA_OK(ctx, ee); }
       BVIO_CUDA_OK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     }
     BVIO_CUDA_OK(ctx, cudaGraphLaunch(pr->graph, ctx->stream));

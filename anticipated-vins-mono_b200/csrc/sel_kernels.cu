@@ -14,6 +14,7 @@
 //   sel_apply   multi-GPU: pick among the gathered per-rank winner records, identical on every rank
 #include "sel.h"
 #include <float.h>
+#include <mutex>
 
 namespace bvio {
 
@@ -73,8 +74,8 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) sel_build_kernel(SelProb sp) {
 
   const q4 qic{sp.q_ic[0], sp.q_ic[1], sp.q_ic[2], sp.q_ic[3]};
   const d3 tic{sp.t_ic[0], sp.t_ic[1], sp.t_ic[2]};
-  const d3 P1{sp.hpos[3], sp.hpos[4], sp.hpos[5]};
-  const q4 Q1{sp.hquat[4], sp.hquat[5], sp.hquat[6], sp.hquat[7]};
+  const d3 P1{sp.k1_pos[0], sp.k1_pos[1], sp.k1_pos[2]};
+  const q4 Q1{sp.k1_quat[0], sp.k1_quat[1], sp.k1_quat[2], sp.k1_quat[3]};
   const d3 t_wc1 = P1 + qrot(Q1, tic);
   const q4 q_wc1 = qmul(Q1, qic);
   d3 feat = normalized3(d3{xy.x, xy.y, 1.0});
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) sel_omega_kernel(SelProb sp) {
     if (bi == bj) {
       if (bi >= 1) v += sp.pair[(size_t)(bi - 1) * 324 + a * 9 + b];
       if (bi < H) v += sp.pair[(size_t)bi * 324 + 243 + a * 9 + b];
-      if (bi == 0 && a == b) v += 1.0;
+      if (bi == 0) v += sp.has_prior ? sp.omega_prior[a * 9 + b] : (a == b ? 1.0 : 0.0);
     } else if (bj == bi + 1) {
       v = sp.pair[(size_t)(bj - 1) * 324 + 162 + a * 9 + b];
     } else if (bi == bj + 1) {
@@ -413,10 +414,15 @@ __device__ __forceinline__ double warp_chol_logdet(const double* A, int lane, co
 }
 
 __device__ __forceinline__ void merge_best(double& best, double& second, int& idx, double ob, double os, int oidx) {
-  // (best, idx) ordered by value, ties to the smaller candidate index
-  if (ob > best || (ob == best && oidx >= 0 && (idx < 0 || oidx < idx))) {
+  // (best, idx) ordered by value.  An exact tie is the reference's upper-bound collision: bit-identical candidates
+  // share one slot of the `UBs[ub] = feature_id` map, only the later-iterated (larger) id is evaluated in that round
+  // (feature_selector.cpp:697,724) -- so the larger index takes the slot and the twin does not count as runner-up.
+  if (ob > best) {
     second = fmax(fmax(best, second), os);
     best = ob; idx = oidx;
+  } else if (ob == best && oidx >= 0 && idx >= 0) {
+    idx = max(idx, oidx);
+    second = fmax(second, os);
   } else {
     second = fmax(second, fmax(ob, os));
   }
@@ -467,6 +473,7 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) sel_round_kernel(SelProb sp) {
     const double val = ld_oo + 2.0 * ld;
     cnt += 1;
     if (val > best) { second = best; best = val; bidx = i; }
+    else if (val == best && bidx >= 0) bidx = i;      // exact tie = UB collision: the larger index takes the slot (merge_best)
     else if (val > second) second = val;
     __syncwarp();
   }
@@ -608,6 +615,7 @@ __global__ void __launch_bounds__(32 * SEL_WARPS, 2) sel_persist_kernel(SelProb 
       const double val = ld_oo + 2.0 * ld;
       cnt += 1;
       if (val > best) { second = best; best = val; bidx = i; }
+      else if (val == best && bidx >= 0) bidx = i;    // exact tie = UB collision: the larger index takes the slot (merge_best)
       else if (val > second) second = val;
     }
     if (lane == 0) { sred[warp * 4] = best; sred[warp * 4 + 1] = second; sred[warp * 4 + 2] = (double)bidx; sred[warp * 4 + 3] = cnt; }
@@ -774,9 +782,14 @@ size_t sel_omega_smem_bytes(int H) {
 static size_t round_smem(int TT) { return sizeof(double) * ((size_t)(1 + SEL_WARPS) * TT + SEL_WARPS * 4 + 4); }
 
 #define BVIO_SEL_FOR_EACH_H(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16)
-static bool g_sel_configured = false;
+// the shared-memory opt-ins are per device (several contexts on different GPUs may live in one process)
+static std::mutex g_sel_cfg_mutex;
+static unsigned long long g_sel_cfg_devices[4] = {0, 0, 0, 0};
 int sel_configure(void) {
-  if (g_sel_configured) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+  std::lock_guard<std::mutex> lock(g_sel_cfg_mutex);
+  if (dev >= 0 && dev < 256 && ((g_sel_cfg_devices[dev >> 6] >> (dev & 63)) & 1ull)) return 0;
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(sel_omega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
 #define BVIO_SEL_ATTR(HH) \
@@ -787,7 +800,7 @@ int sel_configure(void) {
   if ((e = cudaFuncSetAttribute(sel_persist_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
   BVIO_SEL_FOR_EACH_H(BVIO_SEL_ATTR)
 #undef BVIO_SEL_ATTR
-  g_sel_configured = true;
+  if (dev >= 0 && dev < 256) g_sel_cfg_devices[dev >> 6] |= 1ull << (dev & 63);
   return 0;
 }
 int sel_launch_reset(const SelProb& sp, cudaStream_t st) {

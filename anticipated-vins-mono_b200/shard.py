@@ -24,9 +24,12 @@ def record_size(H: int) -> int:
 
 
 def merge_best(best, second, idx, ob, os_, oidx):
-    """merge_best() of sel_kernels.cu: order by value, ties to the smaller candidate index."""
-    if ob > best or (ob == best and oidx >= 0 and (idx < 0 or oidx < idx)):
+    """merge_best() of sel_kernels.cu: order by value; an exact tie is the reference's `UBs[ub] = feature_id` collision
+    (feature_selector.cpp:697,724): the larger candidate index takes the slot and the twin is not a runner-up."""
+    if ob > best:
         return ob, max(best, second, os_), oidx
+    if ob == best and oidx >= 0 and idx >= 0:
+        return best, max(second, os_), max(idx, oidx)
     return best, max(second, ob, os_), idx
 
 

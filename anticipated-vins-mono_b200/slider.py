@@ -278,7 +278,7 @@ class SlidingWindowSim:
         if need:                                   # FeatureManager::triangulate for the features without a depth yet
             if backend is not None and hasattr(backend, "triangulate"):
                 wt = S.Window(K=K, para_pose=self.pose.copy(), para_speed_bias=self.sb.copy(),
-                              para_ex_pose=np.concatenate([self.tic, self.qic]), para_td=np.zeros(1),
+                              para_ex_pose=np.concatenate([self.tic, self.qic]), para_td=np.array([getattr(self, "td_est", 0.0)]),
                               inv_depth=np.ones(len(feats)), lm_obs_offset=np.array(offs, np.int32),
                               obs_frame=np.array(fr, np.int32), obs_xy=np.array(xy, float).reshape(-1, 2),
                               preint=np.array(self.preint), prior=None)
@@ -289,7 +289,7 @@ class SlidingWindowSim:
                 for i in need:
                     feats[i].depth = triangulate(feats[i], self.pose, self.ric, self.tic)
         w = S.Window(K=K, para_pose=self.pose.copy(), para_speed_bias=self.sb.copy(),
-                     para_ex_pose=np.concatenate([self.tic, self.qic]), para_td=np.zeros(1),
+                     para_ex_pose=np.concatenate([self.tic, self.qic]), para_td=np.array([getattr(self, "td_est", 0.0)]),
                      inv_depth=np.array([1.0 / tr.depth for tr in feats]), lm_obs_offset=np.array(offs, np.int32),
                      obs_frame=np.array(fr, np.int32), obs_xy=np.array(xy, float).reshape(-1, 2),
                      preint=np.array(self.preint), prior=self.prior)
@@ -325,7 +325,9 @@ class SlidingWindowSim:
 
     def _horizon(self):
         """Ground-truth horizon of the simulated trajectory (HorizonGenerator GT mode)."""
-        th = self.t + self.frame_dt * np.arange(self.H + 1)
+        # index 0 = x_k, the previous frame; index 1 = x_k+1, the newest frame at self.t, in which the candidates were
+        # detected (feature_selector.cpp:247-248) -- the same convention as ReplaySession._horizon
+        th = self.t + self.frame_dt * (np.arange(self.H + 1) - 1)
         return np.stack([self.traj.pos(t) for t in th]), np.stack([S.rot_to_quat(self.traj.rot(t)) for t in th])
 
     def _slide(self):
@@ -391,20 +393,27 @@ class SlidingWindowSim:
             t1 = time.perf_counter()
             c_opt = getattr(backend, "t_call", 0.0)
             self.pose, self.sb = wsol.para_pose.copy(), wsol.para_speed_bias.copy()
+            if self.opts.get("estimate_extrinsic"):             # double2vector: tic / ric follow para_Ex_Pose (estimator.cpp:580-588)
+                self.tic, self.qic = np.array(wsol.para_ex_pose[:3], float), np.array(wsol.para_ex_pose[3:], float)
+                self.ric = S.quat_to_rot(self.qic)
+            if self.opts.get("estimate_td"):                    # td = para_Td[0][0] (estimator.cpp:598-599)
+                self.td_est = float(np.atleast_1d(wsol.para_td)[0])
             regauge(pose0, self.pose, self.sb)
             for tr, lam in zip(feats, wsol.inv_depth):          # setDepth + removeFailures
                 tr.depth = 1.0 / lam
                 if tr.depth < 0:
                     del self.tracks[tr.lid]
             wpost = dataclasses.replace(w, para_pose=self.pose.copy(), para_speed_bias=self.sb.copy(),
+                                        para_ex_pose=np.array(wsol.para_ex_pose, float).copy(),
+                                        para_td=np.atleast_1d(np.array(wsol.para_td, float)).copy(),
                                         inv_depth=wsol.inv_depth.copy())
             t2 = time.perf_counter()
             c_marg = 0.0
             if self.margin_flag == MARGIN_OLD:
-                self.prior = backend.marginalize(wpost, MARGIN_OLD)
+                self.prior = backend.marginalize(wpost, MARGIN_OLD, self.opts)
                 c_marg = getattr(backend, "t_call", 0.0)
             elif self.prior is not None:                        # estimator.cpp:926: only if there is a prior; it is
-                p = backend.marginalize(wpost, MARGIN_SECOND_NEW)   # replaced only if it involves Pose[WINDOW_SIZE-1]
+                p = backend.marginalize(wpost, MARGIN_SECOND_NEW, self.opts)   # replaced only if it involves Pose[WINDOW_SIZE-1]
                 c_marg = getattr(backend, "t_call", 0.0)
                 if p is not None:
                     self.prior = p
@@ -591,7 +600,8 @@ class GpuBackend:
         t0 = time.perf_counter()
         self.ctx.check(self.L.bvio_optimize(self.ctx.h, C.byref(h.s), C.byref(o), C.byref(s)), "bvio_optimize")
         self.t_call = time.perf_counter() - t0
-        return dataclasses.replace(w, para_pose=h.pose, para_speed_bias=h.sb, inv_depth=h.inv), s.as_dict()
+        return dataclasses.replace(w, para_pose=h.pose, para_speed_bias=h.sb, para_ex_pose=h.ex, para_td=h.td,
+                                   inv_depth=h.inv), s.as_dict()
 
     def triangulate(self, w, init_depth):
         h = self.abi.WindowHandle(w)
@@ -607,8 +617,9 @@ class GpuBackend:
                        "bvio_horizon_imu")
         return pos, quat
 
-    def marginalize(self, w, flag):
-        out = self.abi.call_marginalize(self.L.bvio_marginalize, w, flag, ctx=self.ctx.h)
+    def marginalize(self, w, flag, opts=None):
+        out = self.abi.call_marginalize(self.L.bvio_marginalize, w, flag, ctx=self.ctx.h,
+                                        opts=self.abi.default_opts(**(opts or {})))
         self.t_call = self.abi.call_marginalize.t_call
         return out
 

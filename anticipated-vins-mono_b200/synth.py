@@ -466,6 +466,11 @@ class SelectProblem:
     cloud_xy: np.ndarray
     cloud_depth: np.ndarray
     kappa: int
+    # ABI v2, optional: the reference's state_k1_ when it differs from horizon[1] (ground-truth horizon mode), and an
+    # Omega_PRIOR on x_k replacing I9
+    state_k1_pos: np.ndarray = None
+    state_k1_quat: np.ndarray = None
+    omega_prior: np.ndarray = None
 
     @property
     def N(self):

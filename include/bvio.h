@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BVIO_ABI_VERSION 1
+#define BVIO_ABI_VERSION 2
 
 typedef enum {
   BVIO_OK = 0,
@@ -110,7 +110,10 @@ enum { BVIO_STRATEGY_LM = 0, BVIO_STRATEGY_DOGLEG = 1 };
  * (estimator.cpp:794-806).  bvio_default_opts() fills the EuRoC values. */
 typedef struct {
   int32_t max_iters;            /* NUM_ITERATIONS (8)                          */
-  double  max_time_s;           /* SOLVER_TIME; 0 disables the wall-clock cut  */
+  double  max_time_s;           /* options.max_solver_time_in_seconds (SOLVER_TIME, or 4/5 of it before MARGIN_OLD,
+                                 * estimator.cpp:799-806); 0 = no cut.  Checked on the DEVICE clock after every
+                                 * iteration: time since this solve's first kernel (H2D copy excluded); a solve cut
+                                 * short ends with BVIO_TERM_TIME */
   int32_t estimate_extrinsic;   /* ESTIMATE_EXTRINSIC != 0 frees para_ex_pose  */
   int32_t estimate_td;          /* ESTIMATE_TD                                 */
   double  focal_length;         /* FOCAL_LENGTH 460: sqrt_info = focal/1.5 I2  */
@@ -277,6 +280,20 @@ typedef struct {
   const double* cloud_xy;       /* [C][2]                                       */
   const double* cloud_depth;    /* [C]  estimated_depth of that landmark       */
   int32_t kappa;                /* max(0, maxFeatures - |subset|)               */
+  /* ---- ABI v2: optional (NULL = the v1 behaviour) --------------------------- */
+  /* state_k1_ of the reference: the IMU-propagated x_k+1 set by setNextStateFromImuPropagation
+   * (feature_selector.cpp:56-70).  calcInfoFromFeatures back-projects every feature with THIS state (:247-266) and
+   * builds the k+1 information block from it (:321-326), while state_kkH[1] = horizon[1] only enters the IMU
+   * information.  In IMU-horizon mode the two coincide (horizon_generator.cpp:35); in ground-truth-horizon mode
+   * (use_ground_truth_hgen: 1, config/euroc/euroc_config.yaml:88; horizon_generator.cpp:106-117) they differ.
+   * NULL: horizon[1] is used for both.                                         */
+  const double* state_k1_pos;   /* [3]  P_WB  or NULL                           */
+  const double* state_k1_quat;  /* [4]  Q_WB x y z w  or NULL                   */
+  /* Omega_PRIOR on x_k: 9 x 9 row-major in the selector's state order (position, velocity, accelerometer bias;
+   * state_defs.h:25-29), added to the top-left block instead of the reference's I9 (addOmegaPrior,
+   * feature_selector.cpp:602-609).  NULL = I9 (the reference).  bvio_prior_omega9() extracts it from a
+   * marginalization prior (the report's stated future work, support_files/report/paper/anticipation.tex:146-152). */
+  const double* omega_prior;    /* [81] or NULL                                  */
 } bvio_select_in;
 
 typedef struct {

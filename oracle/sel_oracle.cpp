@@ -90,7 +90,13 @@ void omega_imu(const bvio_select_in* in, double* Om) {
         Om[(size_t)(r1 + i) * D + r1 + j] += W[i * 9 + j];
       }
   }
-  for (int i = 0; i < 9; i++) Om[(size_t)i * D + i] += 1.0;  // addOmegaPrior
+  // addOmegaPrior (feature_selector.cpp:602-609): I9 in the reference; a caller-supplied 9 x 9 block when given (ABI v2)
+  if (in->omega_prior) {
+    for (int i = 0; i < 9; i++)
+      for (int j = 0; j < 9; j++) Om[(size_t)i * D + j] += in->omega_prior[i * 9 + j];
+  } else {
+    for (int i = 0; i < 9; i++) Om[(size_t)i * D + i] += 1.0;
+  }
 }
 
 void space_to_plane(const bvio_camera& c, V3 P, double px[2]) {
@@ -121,18 +127,15 @@ double nn_depth(const bvio_select_in* in, double x, double y) {
   return in->cloud_depth[best];
 }
 
-// state_k1_ of the reference (feature_selector.cpp:247-250) when it differs from state_kkH[1], i.e. in ground-truth
-// horizon mode; set only by oracle_select_k1
-static thread_local const double* g_k1_pos = nullptr;
-static thread_local const double* g_k1_quat = nullptr;
 
 // one feature: returns false when numVisible == 1. Ch = H blocks (index h-1).
 bool feature_blocks(const bvio_select_in* in, double fx, double fy, std::vector<M3>& Ch, M3& W, double* depth) {
   int H = in->H;
   Q4 q_IC = q4(in->q_ic);
   V3 t_IC = v3(in->t_ic);
-  V3 P1 = v3(g_k1_pos ? g_k1_pos : in->horizon_pos + 3);
-  Q4 Q1 = q4(g_k1_quat ? g_k1_quat : in->horizon_quat + 4);
+  // state_k1_ of the reference (feature_selector.cpp:247-250): differs from state_kkH[1] in ground-truth horizon mode
+  V3 P1 = v3(in->state_k1_pos ? in->state_k1_pos : in->horizon_pos + 3);
+  Q4 Q1 = q4(in->state_k1_quat ? in->state_k1_quat : in->horizon_quat + 4);
   V3 t_WC_k1 = P1 + qrot(Q1, t_IC);
   Q4 q_WC_k1 = qmul(Q1, q_IC);
   V3 feature{fx, fy, 1.0};
@@ -316,8 +319,7 @@ int oracle_select(const bvio_select_in* in, int32_t* out_ids, double* out_values
 // instead of horizon[1]: what FeatureSelector::select does in ground-truth horizon mode.
 extern "C" int oracle_select_k1(const bvio_select_in* in, const double k1_pos[3], const double k1_quat[4], int32_t* out_ids,
                                 double* out_values, bvio_select_summary* summary) {
-  g_k1_pos = k1_pos; g_k1_quat = k1_quat;
-  int rc = oracle_select(in, out_ids, out_values, summary);
-  g_k1_pos = g_k1_quat = nullptr;
-  return rc;
+  bvio_select_in in2 = *in;
+  in2.state_k1_pos = k1_pos; in2.state_k1_quat = k1_quat;
+  return oracle_select(&in2, out_ids, out_values, summary);
 }

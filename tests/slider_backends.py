@@ -14,7 +14,8 @@ class OracleBackend:
         abi = self.abi
         h, o, s = abi.WindowHandle(w), abi.default_opts(**opts), abi.Summary()
         assert self.orc.oracle_optimize(C.byref(h.s), C.byref(o), C.byref(s)) == 0
-        return dataclasses.replace(w, para_pose=h.pose, para_speed_bias=h.sb, inv_depth=h.inv), s.as_dict()
+        return dataclasses.replace(w, para_pose=h.pose, para_speed_bias=h.sb, para_ex_pose=h.ex, para_td=h.td,
+                                   inv_depth=h.inv), s.as_dict()
 
     def triangulate(self, w, init_depth):
         h = self.abi.WindowHandle(w)
@@ -29,8 +30,8 @@ class OracleBackend:
         self.orc.oracle_horizon_imu(H, *args, nr_imu, delta_imu, self.abi.dptr(pos), self.abi.dptr(quat))
         return pos, quat
 
-    def marginalize(self, w, flag):
-        return self.abi.call_marginalize(self.orc.oracle_marginalize, w, flag)
+    def marginalize(self, w, flag, opts=None):
+        return self.abi.call_marginalize(self.orc.oracle_marginalize, w, flag, opts=self.abi.default_opts(**(opts or {})))
 
     def select(self, prob):
         abi = self.abi

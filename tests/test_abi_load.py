@@ -26,7 +26,7 @@ def test_library_exports_every_symbol(pkg):
     L = pkg.lib.load()
     for name in _declared_symbols():
         assert hasattr(L, name), name
-    assert L.bvio_abi_version() == 1
+    assert L.bvio_abi_version() == 2
     o = pkg.abi.Opts()
     L.bvio_default_opts(C.byref(o))
     assert o.max_iters == 8 and o.focal_length == 460.0 and o.strategy == 0
@@ -49,3 +49,28 @@ def test_product_does_not_link_oracle(pkg):
     assert "oracle_" not in out
     ldd = subprocess.run(["ldd", pkg.lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "liboracle" not in ldd
+
+
+def test_ctypes_mirror_matches_header_layout(pkg, tmp_path):
+    """abi.py restates include/bvio.h by hand: compile a probe against the header and compare sizeof / offsetof of every
+    struct (a silent mismatch would shift every field after it)."""
+    import subprocess
+    abi = pkg.abi
+    pairs = [("bvio_preint", abi.Preint), ("bvio_prior", abi.Prior), ("bvio_window", abi.WindowS), ("bvio_opts", abi.Opts),
+             ("bvio_summary", abi.Summary), ("bvio_prior_out", abi.PriorOut), ("bvio_imu_segment", abi.ImuSegment),
+             ("bvio_camera", abi.Camera), ("bvio_select_in", abi.SelectIn), ("bvio_select_summary", abi.SelectSummary)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/bvio.h"', "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)

@@ -373,3 +373,57 @@ def test_rejects_unsupported_and_invalid(env):
     assert ctx.L.bvio_optimize(ctx.h, C.byref(h15.s), C.byref(abi.default_opts(estimate_extrinsic=1)), C.byref(s)) == -1
     h.frame[1] = h.frame[0]   # not strictly ascending
     assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts()), C.byref(s)) == -1
+
+
+def test_max_solver_time_cut(env):
+    """options.max_solver_time_in_seconds (estimator.cpp:799-806): a budget that is already spent after the first
+    iteration ends the solve with BVIO_TERM_TIME; a generous one changes nothing (device clock, bvio.h)."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=3, K=11, L=150)
+    runs = {}
+    for name, kw in (("off", {}), ("generous", dict(max_time_s=10.0)), ("spent", dict(max_time_s=1e-9))):
+        h, s = abi.WindowHandle(w), abi.Summary()
+        ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(**kw)), C.byref(s)), "bvio_optimize")
+        runs[name] = (h.state_vector(), s.as_dict())
+    assert runs["off"][1]["iterations"] > 1 and runs["off"][1]["termination"] != 5
+    assert np.array_equal(runs["off"][0], runs["generous"][0]) and runs["generous"][1]["termination"] == runs["off"][1]["termination"]
+    assert runs["spent"][1]["iterations"] == 1 and runs["spent"][1]["termination"] == 5   # BVIO_TERM_TIME
+
+
+def test_malformed_prior_is_rejected_not_dereferenced(env):
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=0, K=4, L=10, prior="frame0")
+    h, s = abi.WindowHandle(w), abi.Summary()
+    assert h.prior_s is not None
+    h.prior_s.lin_jac = None
+    h.s.prior = C.pointer(h.prior_s)
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts()), C.byref(s)) == -1
+    h2 = abi.WindowHandle(w)
+    h2.prior_s.block_kind = None
+    h2.s.prior = C.pointer(h2.prior_s)
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h2.s), C.byref(abi.default_opts()), C.byref(s)) == -1
+
+
+def test_two_contexts_on_two_devices(pkg, oracle):
+    """The __constant__ tables and shared-memory opt-ins are per device: a second context on another GPU of the same
+    process must solve and select like the first (skipped on a 1-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    abi, synth = pkg.abi, pkg.synth
+    w = synth.make_window(seed=1, K=11, L=150)
+    p = synth.make_select_problem(seed=2, N=300, H=13, kappa=30)
+    res = []
+    ctxs = [pkg.lib.Context(0), pkg.lib.Context(1)]
+    for ctx in ctxs:
+        h, s = abi.WindowHandle(w), abi.Summary()
+        ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts()), C.byref(s)), "bvio_optimize")
+        hs, ss, ids = abi.SelectHandle(p), abi.SelectSummary(), np.zeros(30, np.int32)
+        ctx.check(ctx.L.bvio_select(ctx.h, C.byref(hs.s), abi.iptr(ids), None, C.byref(ss)), "bvio_select")
+        res.append((h.state_vector(), s.iterations, ids.copy()))
+    for ctx in ctxs:
+        ctx.close()
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1] and np.array_equal(res[0][2], res[1][2])
+    ho, so = abi.WindowHandle(w), abi.Summary()
+    assert oracle.oracle_optimize(C.byref(ho.s), C.byref(abi.default_opts()), C.byref(so)) == 0
+    assert np.linalg.norm(res[1][0] - ho.state_vector()) <= 1e-6 * np.linalg.norm(ho.state_vector())

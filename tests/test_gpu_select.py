@@ -106,3 +106,55 @@ def test_resident_selector_is_deterministic(env):
     ctx.L.bvio_select_free(ctx.h, ph)
     for r in runs[1:]:
         assert np.array_equal(r[0], runs[0][0]) and np.array_equal(r[1], runs[0][1]) and r[2] == runs[0][2]
+
+
+@pytest.mark.parametrize("seed,N,H,U,kappa", [(0, 80, 10, 0, 15), (1, 120, 13, 6, 25)])
+def test_select_with_separate_state_k1_and_omega_prior(env, seed, N, H, U, kappa):
+    """ABI v2 inputs: candidates back-projected from an explicit state_k1 (feature_selector.cpp:247-266) and a caller
+    supplied Omega_PRIOR instead of I9 (:602-609) -- device vs oracle: information blocks, Omega, ids."""
+    abi, synth, orc, ctx = env
+    rng = np.random.default_rng(50 + seed)
+    p = synth.make_select_problem(seed=seed, N=N, H=H, U=U, kappa=kappa)
+    dq = np.concatenate([0.5 * rng.normal(0, 0.02, 3), [1.0]])
+    p.state_k1_pos = p.horizon_pos[1] + rng.normal(0, 0.05, 3)
+    q = synth.quat_mul(p.horizon_quat[1], dq)
+    p.state_k1_quat = q / np.linalg.norm(q)
+    A = rng.normal(0, 1.0, (9, 9))
+    p.omega_prior = A @ A.T + np.diag(rng.uniform(0.5, 50.0, 9))
+    h = abi.SelectHandle(p)
+    T, D = 3 * H, 9 * (H + 1)
+    Cg, vg, Og = np.zeros((N, T, T)), np.zeros(N, np.int32), np.zeros((D, D))
+    ctx.check(ctx.L.bvio_debug_build_delta(ctx.h, C.byref(h.s), abi.dptr(Cg), abi.iptr(vg), abi.dptr(Og)), "build_delta")
+    Co, vo, Oo = np.zeros((N, T, T)), np.zeros(N, np.int32), np.zeros((D, D))
+    orc.oracle_build_delta(C.byref(h.s), 0, None, abi.dptr(Co), abi.iptr(vo), None)
+    orc.oracle_omega_imu(C.byref(h.s), abi.dptr(Oo))
+    assert (vg == vo).all() and vo.sum() > 0
+    assert np.abs(Cg - Co).max() <= 1e-12 * max(np.abs(Co).max(), 1.0)
+    assert np.abs(Og - Oo).max() <= 1e-11 * np.abs(Oo).max()
+    assert np.abs(Oo[:9, :9] - p.omega_prior).max() > 0         # the prior block really went in (plus the IMU term)
+    ig, vg2, sg, io, vo2, so = _select_both(env, p)
+    n = so.n_selected
+    assert sg.n_selected == n > 0 and ig[:n].tolist() == io[:n].tolist()
+    assert np.allclose(vg2[:n], vo2[:n], rtol=1e-9, atol=0)
+    # and the optional inputs matter: without them the information blocks differ
+    p2 = synth.make_select_problem(seed=seed, N=N, H=H, U=U, kappa=kappa)
+    h2 = abi.SelectHandle(p2)
+    C2 = np.zeros((N, T, T))
+    orc.oracle_build_delta(C.byref(h2.s), 0, None, abi.dptr(C2), abi.iptr(vo), None)
+    assert np.abs(C2 - Co).max() > 1e-6
+
+
+def test_select_exact_duplicates_name_the_larger_id_first(env):
+    """Tie rule of the device = the reference's UB-map collision (feature_selector.cpp:697,724): device vs oracle on
+    inputs with bit-identical twins, also when the twins sit in different warps / CTAs of the persistent kernel."""
+    abi, synth, orc, ctx = env
+    for seed, N, kappa, pairs in ((0, 64, 20, [(0, 1), (10, 11), (30, 63)]), (1, 600, 40, [(5, 599), (100, 101), (7, 300), (8, 301)])):
+        p = synth.make_select_problem(seed=seed, N=N, H=10, kappa=kappa)
+        for a, b in pairs:
+            p.cand_xy[b], p.cand_prob[b] = p.cand_xy[a], p.cand_prob[a]
+        ig, vg, sg, io, vo, so = _select_both(env, p)
+        n = so.n_selected
+        assert sg.n_selected == n and ig[:n].tolist() == io[:n].tolist(), (ig[:n], io[:n])
+        order = {int(i): k for k, i in enumerate(ig[:n])}
+        both = [(int(p.cand_id[a]), int(p.cand_id[b])) for a, b in pairs if int(p.cand_id[a]) in order and int(p.cand_id[b]) in order]
+        assert all(order[b] < order[a] for a, b in both)

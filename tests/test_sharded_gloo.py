@@ -112,7 +112,7 @@ def test_pick_winner_total_order(pkg):
     recs = np.zeros((3, RS))
     recs[:, 0], recs[:, 1], recs[:, 2] = [5.0, 7.0, 7.0], [4.0, 1.0, 6.5], [10, 30, 20]
     b, s, ix, prob, Cp = shard.pick_winner(recs)
-    assert (b, ix) == (7.0, 20)        # tie on the value -> smaller candidate index
-    assert s == 7.0                    # the other 7.0 is the runner-up
+    assert (b, ix) == (7.0, 30)        # exact tie = UB collision in the reference -> the larger candidate index
+    assert s == 6.5                    # the collided twin is not a runner-up
     recs[:, 0], recs[:, 2] = -1.0, -1  # nobody has a candidate
     assert shard.pick_winner(recs)[2] == -1

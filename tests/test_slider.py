@@ -166,8 +166,8 @@ class DualBackend(OracleBackend):
         self.n["optimize"] += 1
         return wo, so
 
-    def marginalize(self, w, flag):
-        pg, po = self.gpu.marginalize(w, flag), super().marginalize(w, flag)
+    def marginalize(self, w, flag, opts=None):
+        pg, po = self.gpu.marginalize(w, flag, opts), super().marginalize(w, flag, opts)
         assert (pg is None) == (po is None)
         if po is not None:
             assert pg["n"] == po["n"] and (pg["block_kind"] == po["block_kind"]).all()

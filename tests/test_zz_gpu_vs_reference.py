@@ -38,6 +38,41 @@ def test_cuda_select_matches_reference_select(pkg, ref, seed, N, U, n_lm, kappa)
     assert ss.n_selected == len(ref_ids) and (out[:ss.n_selected] == ref_ids).all(), (out[:ss.n_selected], ref_ids)
 
 
+@pytest.mark.parametrize("seed,N,U,n_lm,kappa", [(0, 120, 0, 60, 25), (1, 150, 12, 80, 30), (3, 200, 20, 120, 40), (4, 180, 8, 100, 35)])
+def test_cuda_select_matches_reference_in_ground_truth_horizon_mode(pkg, ref, tmp_path, seed, N, U, n_lm, kappa):
+    """USE_GT, the reference's shipped EuRoC default (config/euroc/euroc_config.yaml:88): horizon from the ground-truth
+    csv, candidates back-projected with the IMU-propagated state_k1_ (feature_selector.cpp:247-266,321-326) handed over
+    in bvio_select_in.state_k1_pos / state_k1_quat (ABI v2).  Same ids as FeatureSelector::select, same order."""
+    from test_reference_pin import gt_mode_case
+    abi = pkg.abi
+    ref_ids, prob = gt_mode_case(pkg, ref, seed, N, U, n_lm, kappa, str(tmp_path / "gt.csv"))
+    ctx = pkg.lib.Context(0)
+    hs, ss = abi.SelectHandle(prob), abi.SelectSummary()
+    out = np.zeros(kappa, np.int32)
+    ctx.check(ctx.L.bvio_select(ctx.h, C.byref(hs.s), abi.iptr(out), None, C.byref(ss)), "bvio_select")
+    ctx.close()
+    assert len(ref_ids) > 0 and out[:ss.n_selected].tolist() == ref_ids.tolist(), (out[:ss.n_selected], ref_ids)
+
+
+@pytest.mark.parametrize("seed,twins", [(0, 10), (2, 6)])
+def test_cuda_select_duplicate_candidates_like_the_reference(pkg, ref, seed, twins):
+    """The `UBs[ub] = feature_id` collision (feature_selector.cpp:697,724): of two bit-identical candidates the
+    reference names the larger id first.  The device's exact-tie rule does the same: identical ids, in order."""
+    from test_reference_pin import reference_select_case
+    abi = pkg.abi
+    ref_ids, prob = reference_select_case(pkg, ref, seed, 60, 0, 60, 25, twins=twins)
+    ctx = pkg.lib.Context(0)
+    hs, ss = abi.SelectHandle(prob), abi.SelectSummary()
+    out = np.zeros(25, np.int32)
+    ctx.check(ctx.L.bvio_select(ctx.h, C.byref(hs.s), abi.iptr(out), None, C.byref(ss)), "bvio_select")
+    ctx.close()
+    assert out[:ss.n_selected].tolist() == ref_ids.tolist(), (out[:ss.n_selected], ref_ids)
+    order = {int(i): k for k, i in enumerate(out[:ss.n_selected])}
+    pairs = [(int(prob.cand_id[k]), int(prob.cand_id[k + 1])) for k in range(0, 2 * twins, 2)]
+    both = [(a, b) for a, b in pairs if a in order and b in order]
+    assert both and all(order[b] < order[a] for a, b in both)
+
+
 @pytest.mark.parametrize("seed,K,L", [(0, 11, 150), (1, 6, 40)])
 def test_cuda_marginalize_matches_reference_marginalize(pkg, ref, seed, K, L):
     """bvio_marginalize vs MarginalizationInfo::marginalize on the reference's residual blocks: the new prior's

@@ -29,8 +29,18 @@ def main():
     dist.broadcast(uid, 0)
     ctx.check(ctx.L.bvio_comm_init(ctx.h, bytes(uid.cpu().numpy().tobytes()), rank, world), "comm_init")
     ok = True
-    for seed, N, H, U, kappa in ((0, 2000, 10, 0, 150), (1, 333, 13, 4, 40), (2, 7, 10, 0, 5), (3, 64, 5, 2, 64)):
+    for seed, N, H, U, kappa, twins in ((0, 2000, 10, 0, 150, 0), (1, 333, 13, 4, 40, 0), (2, 7, 10, 0, 5, 0), (3, 64, 5, 2, 64, 0),
+                                        (4, 400, 10, 0, 60, 12), (5, 240, 13, 3, 30, 8)):
         p = synth.make_select_problem(seed=seed, N=N, H=H, U=U, kappa=kappa)
+        # exact duplicates (the reference's UB-map collision, feature_selector.cpp:697,724): twins inside one shard and
+        # twins that straddle shard boundaries must resolve to the larger id on every rank
+        rng = np.random.default_rng(seed)
+        for k in range(twins):
+            a, b = (2 * k, 2 * k + 1) if k % 2 == 0 else sorted(rng.choice(N, 2, replace=False).tolist())
+            p.cand_xy[b], p.cand_prob[b] = p.cand_xy[a], p.cand_prob[a]
+        if twins:
+            p.state_k1_pos = p.horizon_pos[1] + 0.03          # ABI v2 inputs ride along on the sharded path
+            p.omega_prior = np.diag(np.linspace(1.0, 9.0, 9))
         h = abi.SelectHandle(p)
         i1, v1, s1 = np.full(kappa, -1, np.int32), np.zeros(kappa), abi.SelectSummary()
         i2, v2, s2 = np.full(kappa, -1, np.int32), np.zeros(kappa), abi.SelectSummary()
