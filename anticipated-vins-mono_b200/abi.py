@@ -36,7 +36,8 @@ class WindowS(C.Structure):
                 ("para_ex_pose", c_double_p), ("para_td", c_double_p), ("L", C.c_int32),
                 ("inv_depth", c_double_p), ("lm_obs_offset", c_int32_p), ("obs_frame", c_int32_p),
                 ("obs_xy", c_double_p), ("obs_vel", c_double_p), ("obs_td", c_double_p), ("obs_row", c_double_p),
-                ("preint", C.POINTER(Preint)), ("prior", C.POINTER(Prior))]
+                ("preint", C.POINTER(Preint)), ("prior", C.POINTER(Prior)),
+                ("n_relo", C.c_int32), ("relo_pose", c_double_p), ("relo_lm", c_int32_p), ("relo_xy", c_double_p)]
 
 
 class Opts(C.Structure):
@@ -167,6 +168,15 @@ class WindowHandle:
             s.prior = C.pointer(ps)
         else:
             s.prior = None
+        # ABI v2: relocalization matches (estimator.cpp:760-792)
+        s.n_relo, s.relo_pose, s.relo_lm, s.relo_xy = 0, None, None, None
+        if getattr(w, "relo_pose", None) is not None:
+            self.relo_pose = np.ascontiguousarray(w.relo_pose, np.float64).copy()
+            self.relo_lm = np.ascontiguousarray(w.relo_lm, np.int32)
+            self.relo_xy = np.ascontiguousarray(w.relo_xy, np.float64).reshape(-1, 2)
+            s.n_relo, s.relo_pose = len(self.relo_lm), dptr(self.relo_pose)
+            s.relo_lm = iptr(self.relo_lm) if s.n_relo else None
+            s.relo_xy = dptr(self.relo_xy) if s.n_relo else None
         self.s = s
 
     def state_vector(self):

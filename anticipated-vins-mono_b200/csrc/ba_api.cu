@@ -28,6 +28,8 @@ struct bvio_batch {
   bool use_graph = true;
   int launches_per_solve = 0;
   int debug = 0;
+  int Kc = 0;          // the caller's K; bt.K = Kc + 1 when relocalization factors ride along as one more frame
+  bool relo = false;
 };
 
 extern "C" {
@@ -129,6 +131,20 @@ static int validate_msg(const bvio_window* w, const bvio_opts* o, int K0, const 
         { *msg = "obs_frame must be strictly ascending within [0,K)"; return BVIO_ERR_INVALID; }
     }
   }
+  if (w->n_relo < 0 || (w->n_relo > 0 && (!w->relo_pose || !w->relo_lm || !w->relo_xy)))
+    { *msg = "relocalization: n_relo < 0 or null relo_pose / relo_lm / relo_xy"; return BVIO_ERR_INVALID; }
+  if (w->n_relo > 0) {
+    if (o->estimate_td) { *msg = "relocalization factors with estimate_td are not supported"; return BVIO_ERR_UNSUPPORTED; }
+    if (w->K + 1 + (o->estimate_extrinsic ? 1 : 0) > BVIO_KMAX || 15 * (w->K + 1) + (o->estimate_extrinsic ? 6 : 0) > 226)
+      { *msg = "relocalization: K too large (the loop-closure pose rides as one more frame)"; return BVIO_ERR_UNSUPPORTED; }
+    for (int k = 0; k < w->n_relo; k++) {
+      int l = w->relo_lm[k];
+      if (l < 0 || l >= w->L || (k > 0 && l <= w->relo_lm[k - 1]))
+        { *msg = "relo_lm must be strictly ascending within [0,L)"; return BVIO_ERR_INVALID; }
+      if (w->lm_obs_offset[l + 1] - w->lm_obs_offset[l] + 1 > BVIO_KMAX)
+        { *msg = "landmark needs 2..16 observations (relocalization match included)"; return BVIO_ERR_INVALID; }
+    }
+  }
   if (w->prior) {
     const bvio_prior* p = w->prior;
     if (p->n < 0 || p->n > 256 || p->nblocks < 0 || p->nblocks > PRIOR_MAXB)
@@ -167,7 +183,14 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   if (!ctx || !ws || B < 1 || !o || !out) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
   *out = nullptr;
   cudaSetDevice(ctx->device);
-  const int K = ws[0].K;
+  // Relocalization (estimator.cpp:760-792): relo_Pose rides as frame Kc of a (Kc+1)-frame window -- no IMU link to it
+  // (its preintegration slot carries sum_dt > 10, the reference's own "skip this factor" rule, estimator.cpp:705) and a
+  // zero speed-bias block whose columns are identically zero: they add nothing to the gradient, the step, the model
+  // decrease or any norm Ceres' loop looks at, so the iteration is the one of the reference's problem.
+  const int Kc = ws[0].K;
+  bool relo = false;
+  for (int b = 0; b < B; b++) relo |= ws[b].n_relo > 0;
+  const int K = Kc + (relo ? 1 : 0);
   int total_L = 0, total_obs = 0, nmax = 1, maxL = 0;
   {
     // structural validation walks every observation: spread large batches over host threads
@@ -175,7 +198,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
     std::vector<int> rcs(nthreads, BVIO_OK);
     std::vector<const char*> msgs(nthreads, "");
     auto work = [&](int t) {
-      for (int b = t; b < B && rcs[t] == BVIO_OK; b += nthreads) rcs[t] = validate_msg(ws + b, o, K, &msgs[t]);
+      for (int b = t; b < B && rcs[t] == BVIO_OK; b += nthreads) rcs[t] = validate_msg(ws + b, o, Kc, &msgs[t]);
     };
     if (nthreads == 1) work(0);
     else {
@@ -187,7 +210,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   }
   for (int b = 0; b < B; b++) {
     total_L += ws[b].L;
-    total_obs += ws[b].L ? ws[b].lm_obs_offset[ws[b].L] : 0;
+    total_obs += (ws[b].L ? ws[b].lm_obs_offset[ws[b].L] : 0) + ws[b].n_relo;
     maxL = std::max(maxL, ws[b].L);
     if (ws[b].prior) nmax = std::max(nmax, ws[b].prior->n);
   }
@@ -198,6 +221,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   const int est_ex = o->estimate_extrinsic != 0, est_td = o->estimate_td != 0, XB = est_ex + est_td, KE = K + XB;
   bt.B = B; bt.K = K; bt.np = 15 * K + (est_ex ? 6 : 0) + est_td; bt.total_L = total_L; bt.total_obs = total_obs; bt.nmax = nmax;
   bt.est_ex = est_ex; bt.est_td = est_td;
+  bb->Kc = Kc; bb->relo = relo;
   bt.solve_wide = B < ctx->sm_count && !getenv("BVIO_SOLVE_NARROW");
   bt.use_mma = XB == 0 && !getenv("BVIO_LEGACY_LINEARIZE");
   bt.chunk_l = ba_pick_chunk(K, XB);
@@ -311,7 +335,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
     int lb0 = 0, ob0 = 0;
     for (int b = 0; b < B; b++) {
       bb->lm_base[b] = lb0; obs_base[b] = ob0;
-      lb0 += ws[b].L; ob0 += ws[b].L ? ws[b].lm_obs_offset[ws[b].L] : 0;
+      lb0 += ws[b].L; ob0 += (ws[b].L ? ws[b].lm_obs_offset[ws[b].L] : 0) + ws[b].n_relo;
     }
     bb->lm_base[B] = lb0; obs_base[B] = ob0;
   }
@@ -331,11 +355,19 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
       for (int l = 0; l < w.L; l++) perm[cnt[w.obs_frame[w.lm_obs_offset[l]]]++] = l;
     }
     int run = ob;
+    std::vector<int> relo_of;
+    if (w.n_relo > 0) { relo_of.assign(w.L, -1); for (int k = 0; k < w.n_relo; k++) relo_of[w.relo_lm[k]] = k; }
     for (int j = 0; j < w.L; j++) {
       const int l = perm[j], o0 = w.lm_obs_offset[l], n = w.lm_obs_offset[l + 1] - o0;
       h_lm_off[lb + j] = run;
       memcpy(h_obs_frame + run, w.obs_frame + o0, n * I);
       memcpy(h_obs_xy + (size_t)2 * run, w.obs_xy + (size_t)2 * o0, (size_t)n * 2 * D);
+      if (w.n_relo > 0 && relo_of[l] >= 0) {             // the match in the loop-closure frame = one more observation
+        h_obs_frame[run + n] = Kc;
+        h_obs_xy[2 * (size_t)(run + n)] = w.relo_xy[2 * relo_of[l]];
+        h_obs_xy[2 * (size_t)(run + n) + 1] = w.relo_xy[2 * relo_of[l] + 1];
+        run += 1;
+      }
       if (est_td) {
         memcpy(h_obs_vel + (size_t)2 * run, w.obs_vel + (size_t)2 * o0, (size_t)n * 2 * D);
         // row centred like the factor's constructor (projection_td_factor.cpp:18-19)
@@ -343,12 +375,23 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
       }
       run += n;
     }
-    memcpy(h_pose0 + (size_t)b * K * 7, w.para_pose, (size_t)K * 7 * D);
-    memcpy(h_sb0 + (size_t)b * K * 9, w.para_speed_bias, (size_t)K * 9 * D);
+    memcpy(h_pose0 + (size_t)b * K * 7, w.para_pose, (size_t)Kc * 7 * D);
+    memcpy(h_sb0 + (size_t)b * K * 9, w.para_speed_bias, (size_t)Kc * 9 * D);
+    if (relo) {
+      static const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+      memcpy(h_pose0 + ((size_t)b * K + Kc) * 7, w.n_relo > 0 ? w.relo_pose : ident, 7 * D);
+      memset(h_sb0 + ((size_t)b * K + Kc) * 9, 0, 9 * D);
+    }
     memcpy(h_ex + (size_t)b * 7, w.para_ex_pose, 7 * D);
     h_td0[b] = w.para_td ? w.para_td[0] : 0.0;
     for (int j = 0; j < w.L; j++) h_invd0[lb + j] = w.inv_depth[perm[j]];
-    memcpy(h_pre + (size_t)b * K * PREINT_DOUBLES, w.preint, (size_t)K * sizeof(bvio_preint));
+    memcpy(h_pre + (size_t)b * K * PREINT_DOUBLES, w.preint, (size_t)Kc * sizeof(bvio_preint));
+    if (relo) {
+      double* pr = h_pre + ((size_t)b * K + Kc) * PREINT_DOUBLES;
+      memset(pr, 0, sizeof(bvio_preint));
+      pr[6] = 1.0;                                         // delta_q = identity
+      pr[16] = 1e9;                                        // sum_dt > 10: no IMU factor into the loop-closure frame
+    }
     h_pr_n[b] = 0; h_pr_nb[b] = 0;
     if (w.prior) {
       const bvio_prior* p = w.prior;
@@ -490,8 +533,9 @@ static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, b
   int rc = BVIO_OK;
   auto scatter = [&](int b) {
       bvio_window& w = windows[b];
-      memcpy(w.para_pose, pose + (size_t)b * bt.K * 7, (size_t)bt.K * 7 * sizeof(double));
-      memcpy(w.para_speed_bias, sb + (size_t)b * bt.K * 9, (size_t)bt.K * 9 * sizeof(double));
+      memcpy(w.para_pose, pose + (size_t)b * bt.K * 7, (size_t)bb->Kc * 7 * sizeof(double));
+      memcpy(w.para_speed_bias, sb + (size_t)b * bt.K * 9, (size_t)bb->Kc * 9 * sizeof(double));
+      if (bb->relo && w.n_relo > 0) memcpy(w.relo_pose, pose + ((size_t)b * bt.K + bb->Kc) * 7, 7 * sizeof(double));
       int L = bb->lm_base[b + 1] - bb->lm_base[b];
       const int* perm = bb->perm.data() + bb->lm_base[b];
       for (int j = 0; j < L; j++) w.inv_depth[perm[j]] = invd[bb->lm_base[b] + j];
@@ -505,16 +549,7 @@ static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, b
     for (auto& x : th) x.join();
   }
   for (int b = 0; b < bt.B; b++) {
-    if (windows && bt.B < 64) {
-      bvio_window& w = windows[b];
-      memcpy(w.para_pose, pose + (size_t)b * bt.K * 7, (size_t)bt.K * 7 * sizeof(double));
-      memcpy(w.para_speed_bias, sb + (size_t)b * bt.K * 9, (size_t)bt.K * 9 * sizeof(double));
-      int L = bb->lm_base[b + 1] - bb->lm_base[b];
-      const int* perm = bb->perm.data() + bb->lm_base[b];
-      for (int j = 0; j < L; j++) w.inv_depth[perm[j]] = invd[bb->lm_base[b] + j];
-      if (bt.est_ex) memcpy(w.para_ex_pose, exo + (size_t)b * 7, 7 * sizeof(double));
-      if (bt.est_td) w.para_td[0] = tdo[b];
-    }
+    if (windows && bt.B < 64) scatter(b);
     const BaCtrl& c = ctrl[b];
     if (summaries) {
       bvio_summary& s = summaries[b];
@@ -661,8 +696,12 @@ int bvio_batch_solve_timed(bvio_ctx* ctx, bvio_batch* bb, double out_ms[4], int3
 // ba_marginalize_kernel.  Kept blocks come out in frame order (Pose f, SpeedBias f ascending, then
 // Ex_Pose) with the reference's addr_shift applied.  flag 1 and a prior that does not touch Pose[K-2]:
 // out->n = -1 (the reference leaves last_marginalization_info untouched, estimator.cpp:926-928).
-int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts, int32_t flag, bvio_prior_out* out) {
-  if (!ctx || !w || !opts || !out || (flag != 0 && flag != 1)) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
+int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* opts, int32_t flag, bvio_prior_out* out) {
+  if (!ctx || !w_in || !opts || !out || (flag != 0 && flag != 1)) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
+  // the relocalization factors are not part of the marginalization (estimator.cpp:816-991)
+  bvio_window w_copy = *w_in;
+  w_copy.n_relo = 0; w_copy.relo_pose = nullptr; w_copy.relo_lm = nullptr; w_copy.relo_xy = nullptr;
+  const bvio_window* w = &w_copy;
   const int K = w->K;
   if (opts->estimate_td && K > 14)
     return fail(ctx, BVIO_ERR_INVALID, "bvio_marginalize: K <= 14 with estimate_td");

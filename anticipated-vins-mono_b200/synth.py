@@ -277,6 +277,11 @@ class Window:
     obs_td: np.ndarray | None = None     # [n_obs]
     obs_row: np.ndarray | None = None    # [n_obs]
     gt_td: float = 0.0
+    # relocalization matches (estimator.cpp:760-792): the loop-closure frame's pose block and, per matched landmark,
+    # its observation there
+    relo_pose: np.ndarray | None = None  # [7]
+    relo_lm: np.ndarray | None = None    # [n_relo] int32, ascending landmark indices
+    relo_xy: np.ndarray | None = None    # [n_relo,2]
 
     @property
     def L(self):
@@ -294,6 +299,42 @@ class Window:
 
 
 PREINT_DOUBLES = 3 + 4 + 3 + 3 + 3 + 1 + 225 + 225
+
+
+def add_relocalization(w: "Window", seed=0, local_index=4, max_matches=40, pose_sigma=(0.05, 0.01)) -> "Window":
+    """Relocalization inputs as Estimator::setReloFrame leaves them (estimator.cpp:1109-1127) for a window made by
+    make_window: the loop-closure frame is an earlier visit near window frame `local_index`; every landmark anchored at
+    a frame <= local_index may have a match there (estimator.cpp:774).  relo_pose starts as the window's own pose of
+    that frame (:1124); the matches are the landmarks' ground-truth positions seen from a nearby true pose, plus pixel
+    noise.  Returns a copy of `w` with relo_pose / relo_lm / relo_xy set."""
+    rng = np.random.default_rng(7000 + seed)
+    U_, _, Vt_ = np.linalg.svd(EUROC_RIC)
+    ric, tic = U_ @ Vt_, EUROC_TIC
+    gp = w.gt_pose if w.gt_pose is not None else w.para_pose
+    ginv = w.gt_inv_depth if w.gt_inv_depth is not None else w.inv_depth
+    # true pose of the old visit: the ground-truth pose of frame local_index, moved a little
+    Pt = gp[local_index, :3] + rng.normal(0, pose_sigma[0], 3)
+    qt = quat_mul(gp[local_index, 3:], np.concatenate([0.5 * rng.normal(0, pose_sigma[1], 3), [1.0]]))
+    Rt = quat_to_rot(qt / np.linalg.norm(qt))
+    lm, xy = [], []
+    eligible = [l for l in range(w.L) if int(w.obs_frame[w.lm_obs_offset[l]]) <= local_index]
+    for l in range(w.L):
+        o0 = w.lm_obs_offset[l]
+        fi = int(w.obs_frame[o0])
+        # the last eligible landmark is always matched: the reference's walk over match_points (estimator.cpp:776-779)
+        # has no end check and would read past the vector for an eligible feature id above every matched id
+        last = bool(eligible) and l == eligible[-1]
+        if fi > local_index or (not last and (len(lm) >= max_matches or rng.uniform() < 0.3)):
+            continue
+        Ri, Pi = quat_to_rot(gp[fi, 3:]), gp[fi, :3]
+        pw = Ri @ (ric @ (np.array([w.obs_xy[o0, 0], w.obs_xy[o0, 1], 1.0]) / ginv[l]) + tic) + Pi
+        pc = ric.T @ (Rt.T @ (pw - Pt) - tic)
+        if pc[2] < 0.2 and not last:
+            continue
+        lm.append(l)
+        xy.append(pc[:2] / pc[2] + rng.normal(0, 1.5 / FOCAL_LENGTH, 2))
+    return dataclasses.replace(w.copy(), relo_pose=w.para_pose[local_index].copy(), relo_lm=np.array(lm, np.int32),
+                               relo_xy=np.array(xy, float).reshape(-1, 2))
 
 
 def pack_preint(p: Preintegration) -> np.ndarray:

@@ -101,6 +101,16 @@ typedef struct {
   const double* obs_row;        /* [n_obs]    or NULL (estimate_td only)       */
   const bvio_preint* preint;    /* [K]; entry 0 unused; entry j links j-1 -> j */
   const bvio_prior* prior;      /* NULL when there is no last_marginalization_info */
+  /* ---- ABI v2: relocalization factors (estimator.cpp:760-792), optional ----- */
+  /* When relocalization_info is set the reference adds the pose block relo_Pose (free, PoseLocalParameterization) and,
+   * for every window landmark matched in the loop-closure frame, one ProjectionFactor(pts_i, match_point) between
+   * Pose[start_frame] and relo_Pose with the same Cauchy loss.  n_relo = 0: none.  Not combined with estimate_td
+   * (the reference uses the plain ProjectionFactor here even when ESTIMATE_TD is on): BVIO_ERR_UNSUPPORTED.
+   * bvio_marginalize ignores these fields, as the reference's marginalization does. */
+  int32_t n_relo;
+  double* relo_pose;            /* [7] relo_Pose, px py pz qx qy qz qw   (in/out); may be NULL when n_relo == 0 */
+  const int32_t* relo_lm;       /* [n_relo] landmark index, strictly ascending  */
+  const double* relo_xy;        /* [n_relo][2] match_points x, y (z = 1)        */
 } bvio_window;
 
 enum { BVIO_STRATEGY_LM = 0, BVIO_STRATEGY_DOGLEG = 1 };

@@ -637,6 +637,52 @@ void copy_state(const bvio_window* src, bvio_window* dst, const Layout& ly) {
   std::memcpy(dst->inv_depth, src->inv_depth, sizeof(double) * ly.L);
 }
 
+// Relocalization factors (estimator.cpp:760-792): ProjectionFactor(pts_i, match) between Pose[start_frame] and the extra
+// pose block relo_Pose.  Restated by carrying relo_Pose as frame K of a (K+1)-frame window: the matches become ordinary
+// observations in that frame, there is no IMU factor into it (sum_dt > 10, the rule of estimator.cpp:705) and its
+// speed-bias block has identically zero Jacobian columns, which contribute nothing to the gradient, step, model decrease
+// or norms of the trust-region loop -- the same objective and the same iteration as the reference's problem
+// (pinned against Estimator::optimization() with relocalization_info set, tests/test_reference_pin.py).
+struct ReloExt {
+  std::vector<double> pose, sb, xy, vel, td, row;
+  std::vector<int32_t> off, frame;
+  std::vector<bvio_preint> pre;
+  bvio_window view;
+  bool active = false;
+  void init(const bvio_window* w) {
+    view = *w;
+    active = w->n_relo > 0;
+    if (!active) return;
+    const int K = w->K, L = w->L;
+    pose.assign(w->para_pose, w->para_pose + 7 * K); pose.insert(pose.end(), w->relo_pose, w->relo_pose + 7);
+    sb.assign(w->para_speed_bias, w->para_speed_bias + 9 * K); sb.insert(sb.end(), 9, 0.0);
+    pre.assign(w->preint, w->preint + K);
+    bvio_preint none; std::memset(&none, 0, sizeof none); none.delta_q[3] = 1.0; none.sum_dt = 1e9;
+    pre.push_back(none);
+    off.assign(1, 0);
+    int r = 0;
+    for (int l = 0; l < L; l++) {
+      for (int k = w->lm_obs_offset[l]; k < w->lm_obs_offset[l + 1]; k++) {
+        frame.push_back(w->obs_frame[k]); xy.push_back(w->obs_xy[2 * k]); xy.push_back(w->obs_xy[2 * k + 1]);
+      }
+      if (r < w->n_relo && w->relo_lm[r] == l) {
+        frame.push_back(K); xy.push_back(w->relo_xy[2 * r]); xy.push_back(w->relo_xy[2 * r + 1]);
+        r++;
+      }
+      off.push_back((int32_t)frame.size());
+    }
+    view.K = K + 1; view.para_pose = pose.data(); view.para_speed_bias = sb.data(); view.preint = pre.data();
+    view.lm_obs_offset = off.data(); view.obs_frame = frame.data(); view.obs_xy = xy.data();
+    view.n_relo = 0; view.relo_pose = nullptr; view.relo_lm = nullptr; view.relo_xy = nullptr;
+  }
+  void finish(bvio_window* w) {
+    if (!active) return;
+    std::memcpy(w->para_pose, pose.data(), sizeof(double) * 7 * w->K);
+    std::memcpy(w->para_speed_bias, sb.data(), sizeof(double) * 9 * w->K);
+    std::memcpy(w->relo_pose, pose.data() + 7 * w->K, sizeof(double) * 7);
+  }
+};
+
 }  // namespace
 
 // ===========================================================================
@@ -751,15 +797,20 @@ void oracle_preint_propagate(bvio_preint* pre, double dt, const double acc_0[3],
   pre->sum_dt += dt;
 }
 
-double oracle_cost(const bvio_window* w, const bvio_opts* opts) {
+double oracle_cost(const bvio_window* w_in, const bvio_opts* opts) {
+  ReloExt rx; rx.init(w_in);
+  const bvio_window* w = &rx.view;
   ImuCache ic;
   build_imu_cache(w, ic);
   return visual_cost(w, opts) + imu_prior_cost(w, opts, ic);
 }
 
-int oracle_linearize(const bvio_window* w, const bvio_opts* opts, double* S, double* g, double* h, double* b,
+int oracle_linearize(const bvio_window* w_in, const bvio_opts* opts, double* S, double* g, double* h, double* b,
                      double* cost) {
-  if (opts->estimate_td && (!w->obs_vel || !w->obs_td || !w->obs_row || !w->para_td)) return BVIO_ERR_INVALID;
+  if (opts->estimate_td && (!w_in->obs_vel || !w_in->obs_td || !w_in->obs_row || !w_in->para_td)) return BVIO_ERR_INVALID;
+  if (opts->estimate_td && w_in->n_relo > 0) return BVIO_ERR_UNSUPPORTED;
+  ReloExt rx; rx.init(w_in);
+  const bvio_window* w = &rx.view;
   Layout ly = layout(w, opts);
   ImuCache ic;
   build_imu_cache(w, ic);
@@ -775,7 +826,17 @@ int oracle_linearize(const bvio_window* w, const bvio_opts* opts, double* S, dou
   return BVIO_OK;
 }
 
+static int oracle_optimize_impl(bvio_window* w, const bvio_opts* o, bvio_summary* sum);
 int oracle_optimize(bvio_window* w, const bvio_opts* o, bvio_summary* sum) {
+  if (o->estimate_td && w->n_relo > 0) return BVIO_ERR_UNSUPPORTED;
+  ReloExt rx; rx.init(w);
+  if (!rx.active) return oracle_optimize_impl(w, o, sum);
+  rx.view.inv_depth = w->inv_depth; rx.view.para_ex_pose = w->para_ex_pose; rx.view.para_td = w->para_td;
+  int rc = oracle_optimize_impl(&rx.view, o, sum);
+  rx.finish(w);
+  return rc;
+}
+static int oracle_optimize_impl(bvio_window* w, const bvio_opts* o, bvio_summary* sum) {
   if (o->estimate_td && (!w->obs_vel || !w->obs_td || !w->obs_row || !w->para_td)) return BVIO_ERR_INVALID;
   auto t_start = std::chrono::steady_clock::now();
   Layout ly = layout(w, o);

@@ -20,6 +20,7 @@ class PinholeCameraShim : public Camera {
   PinholeParams c_;
  public:
   explicit PinholeCameraShim(const PinholeParams& c) : c_(c) {}
+  const PinholeParams& params() const { return c_; }   // camodocal's PinholeCamera::getParameters()
   int imageWidth(void) const override { return c_.width; }
   int imageHeight(void) const override { return c_.height; }
   void spaceToPlane(const Eigen::Vector3d& P, Eigen::Vector2d& p) const override {

@@ -545,8 +545,17 @@ struct EstHook {
   bool session = false;
   ceres::Problem* live = nullptr;      // valid only while the solve callback runs
   void (*callback)(void) = nullptr;    // external trust-region driver (tests): called instead of injecting a solution
+  const double* inj_relo = nullptr;    // relocalization: solution for relo_Pose
+  int n_relo_blocks = 0;               // ProjectionFactors attached to relo_Pose in the recorded problem
 } g_hook;
 void (*g_solve_callback)(void) = nullptr;
+}  // namespace
+// When set (adapters/vins/interpose.cpp does, in libvins_bvio.so), ref_estimator_optimization() hands the Estimator it
+// built to this function instead of installing the injecting solve hook: whoever set it answers ceres::Solve.
+extern "C" { void (*ref_on_estimator_created)(void* estimator) = nullptr; }
+namespace {
+// relocalization inputs for the next ref_estimator_optimization() call (what setReloFrame() leaves in the Estimator)
+struct PendingRelo { bool on = false; std::vector<Eigen::Vector3d> match; double pose[7]; int local_index = 0; double out_pose[7]; double rel_t[3]; double rel_yaw = 0; } g_relo;
 
 void est_solve_hook(const ceres::Solver::Options& o, ceres::Problem* pb, ceres::Solver::Summary*) {
   EstHook& h = g_hook;
@@ -580,14 +589,18 @@ void est_solve_hook(const ceres::Solver::Options& o, ceres::Problem* pb, ceres::
   // by the reference's own ResidualBlockInfo::Evaluate.  Local column layout: frame-major [pose 6 | speed-bias 9] x K,
   // extrinsic 6, td 1, then one column per feature.
   {
-    const int K1 = WINDOW_SIZE + 1, npar = 15 * K1 + 7, dim = npar + h.L;
+    // relocalization (estimator.cpp:760-792): the extra pose block relo_Pose takes 6 more columns after the features
+    const int K1 = WINDOW_SIZE + 1, npar = 15 * K1 + 7, dim = npar + h.L + (e.relocalization_info ? 6 : 0);
     auto col_of = [&](double* p, int* size) {
       for (int i = 0; i < K1; ++i) { if (p == e.para_Pose[i]) { *size = 6; return 15 * i; } if (p == e.para_SpeedBias[i]) { *size = 9; return 15 * i + 6; } }
       if (p == e.para_Ex_Pose[0]) { *size = 6; return 15 * K1; }
       if (p == e.para_Td[0]) { *size = 1; return 15 * K1 + 6; }
+      if (p == e.relo_Pose) { *size = 6; return npar + h.L; }
       for (int l = 0; l < h.L; ++l) if (p == e.para_Feature[l]) { *size = 1; return npar + l; }
       *size = 0; return -1;
     };
+    h.n_relo_blocks = 0;
+    for (auto& rb : pb->residual_blocks) for (double* p : rb.blocks) if (p == e.relo_Pose) h.n_relo_blocks++;
     h.dim = dim; h.H.assign((size_t)dim * dim, 0.0); h.g.assign(dim, 0.0);
     for (auto& rb : pb->residual_blocks) {
       ResidualBlockInfo info(rb.cost, rb.loss, rb.blocks, std::vector<int>{});
@@ -628,6 +641,7 @@ void est_solve_hook(const ceres::Solver::Options& o, ceres::Problem* pb, ceres::
   memcpy(e.para_Ex_Pose, h.inj_ex, sizeof(double) * 7);
   for (int l = 0; l < h.L; ++l) e.para_Feature[l][0] = h.inj_feat[l];
   if (h.inj_td) e.para_Td[0][0] = h.inj_td[0];
+  if (h.inj_relo) memcpy(e.relo_Pose, h.inj_relo, sizeof(double) * 7);
 }
 }  // namespace
 
@@ -640,8 +654,8 @@ void ref_set_solve_callback(void (*cb)(void)) { g_solve_callback = cb; }
 int ref_live_dims(int32_t* n_residuals, int32_t* n_local, int32_t* n_global) {
   if (!g_hook.live) return -1;
   int nr = 0; for (auto& rb : g_hook.live->residual_blocks) nr += rb.cost->num_residuals();
-  const int K1 = WINDOW_SIZE + 1;
-  *n_residuals = nr; *n_local = 15 * K1 + 7 + g_hook.L; *n_global = 16 * K1 + 8 + g_hook.L;
+  const int K1 = WINDOW_SIZE + 1, relo = g_hook.est->relocalization_info ? 1 : 0;   // relo_Pose: last 6 local / 7 global entries
+  *n_residuals = nr; *n_local = 15 * K1 + 7 + g_hook.L + 6 * relo; *n_global = 16 * K1 + 8 + g_hook.L + 7 * relo;
   return 0;
 }
 void ref_live_get_state(double* x) {
@@ -649,16 +663,18 @@ void ref_live_get_state(double* x) {
   memcpy(x, e.para_Pose, sizeof(double) * 7 * K1); memcpy(x + 7 * K1, e.para_SpeedBias, sizeof(double) * 9 * K1);
   memcpy(x + 16 * K1, e.para_Ex_Pose, sizeof(double) * 7); x[16 * K1 + 7] = e.para_Td[0][0];
   for (int l = 0; l < g_hook.L; ++l) x[16 * K1 + 8 + l] = e.para_Feature[l][0];
+  if (e.relocalization_info) memcpy(x + 16 * K1 + 8 + g_hook.L, e.relo_Pose, sizeof(double) * 7);
 }
 void ref_live_set_state(const double* x) {
   Estimator& e = *g_hook.est; const int K1 = WINDOW_SIZE + 1;
   memcpy(e.para_Pose, x, sizeof(double) * 7 * K1); memcpy(e.para_SpeedBias, x + 7 * K1, sizeof(double) * 9 * K1);
   memcpy(e.para_Ex_Pose, x + 16 * K1, sizeof(double) * 7); e.para_Td[0][0] = x[16 * K1 + 7];
   for (int l = 0; l < g_hook.L; ++l) e.para_Feature[l][0] = x[16 * K1 + 8 + l];
+  if (e.relocalization_info) memcpy(e.relo_Pose, x + 16 * K1 + 8 + g_hook.L, sizeof(double) * 7);
 }
 // x (+) delta through the problem's own LocalParameterization objects (PoseLocalParameterization::Plus), plain addition elsewhere
 void ref_live_plus(const double* x, const double* delta, double* out) {
-  const int K1 = WINDOW_SIZE + 1, ng = 16 * K1 + 8 + g_hook.L;
+  const int K1 = WINDOW_SIZE + 1, relo = g_hook.est->relocalization_info ? 1 : 0, ng = 16 * K1 + 8 + g_hook.L + 7 * relo;
   for (int i = 0; i < ng; ++i) out[i] = x[i];
   ceres::LocalParameterization* lp = nullptr;
   for (auto& b : g_hook.live->parameter_blocks) if (b.local) { lp = b.local; break; }
@@ -669,17 +685,19 @@ void ref_live_plus(const double* x, const double* delta, double* out) {
   lp->Plus(x + 16 * K1, delta + 15 * K1, out + 16 * K1);
   out[16 * K1 + 7] = x[16 * K1 + 7] + delta[15 * K1 + 6];
   for (int l = 0; l < g_hook.L; ++l) out[16 * K1 + 8 + l] = x[16 * K1 + 8 + l] + delta[15 * K1 + 7 + l];
+  if (relo) lp->Plus(x + 16 * K1 + 8 + g_hook.L, delta + 15 * K1 + 7 + g_hook.L, out + 16 * K1 + 8 + g_hook.L);
 }
 // residuals r [n_residuals] and Jacobian J [n_residuals][n_local] (row-major), loss-corrected by the reference's
 // ResidualBlockInfo::Evaluate, at the state currently in the parameter arrays; *cost = 1/2 sum rho(|r_uncorrected|^2)
 int ref_live_evaluate(double* J, double* r, double* cost) {
   if (!g_hook.live) return -1;
   Estimator& e = *g_hook.est;
-  const int K1 = WINDOW_SIZE + 1, npar = 15 * K1 + 7, nl = npar + g_hook.L;
+  const int K1 = WINDOW_SIZE + 1, npar = 15 * K1 + 7, nl = npar + g_hook.L + (e.relocalization_info ? 6 : 0);
   auto col_of = [&](double* p, int* size) {
     for (int i = 0; i < K1; ++i) { if (p == e.para_Pose[i]) { *size = 6; return 15 * i; } if (p == e.para_SpeedBias[i]) { *size = 9; return 15 * i + 6; } }
     if (p == e.para_Ex_Pose[0]) { *size = 6; return 15 * K1; }
     if (p == e.para_Td[0]) { *size = 1; return 15 * K1 + 6; }
+    if (p == e.relo_Pose) { *size = 6; return npar + g_hook.L; }
     for (int l = 0; l < g_hook.L; ++l) if (p == e.para_Feature[l]) { *size = 1; return npar + l; }
     *size = 0; return -1;
   };
@@ -703,6 +721,22 @@ int ref_live_evaluate(double* J, double* r, double* cost) {
   }
   *cost = c;
   return 0;
+}
+
+// Relocalization for the NEXT ref_estimator_optimization() call: n matches (landmark index = feature id there, ascending;
+// x, y on the normalized plane of the loop-closure frame), the initial relo_Pose and relo_frame_local_index.
+void ref_estimator_set_relo(int n, const int32_t* lm, const double* xy, const double* relo_pose, int local_index) {
+  g_relo.on = true; g_relo.match.clear(); g_relo.local_index = local_index;
+  for (int k = 0; k < n; ++k) g_relo.match.push_back(Eigen::Vector3d(xy[2 * k], xy[2 * k + 1], (double)lm[k]));
+  memcpy(g_relo.pose, relo_pose, sizeof g_relo.pose);
+}
+// after that call: relo_Pose as the Estimator holds it, relo_relative_t / relo_relative_yaw computed by double2vector
+// (estimator.cpp:589-607), and how many residual blocks the recorded problem attached to relo_Pose
+int ref_estimator_get_relo(double* relo_pose, double* rel_t, double* rel_yaw) {
+  memcpy(relo_pose, g_relo.out_pose, sizeof g_relo.out_pose);
+  for (int a = 0; a < 3; ++a) rel_t[a] = g_relo.rel_t[a];
+  *rel_yaw = g_relo.rel_yaw;
+  return g_hook.n_relo_blocks;
 }
 
 // Normal equations of the problem the last ref_estimator_optimization() call handed to Ceres (see est_solve_hook)
@@ -777,15 +811,28 @@ int ref_estimator_optimization(const bvio_window* w, const bvio_opts* o, int fla
     for (int i = 0; i < pr->n; ++i) { info->linearized_residuals(i) = pr->lin_res[i]; for (int j = 0; j < pr->n; ++j) info->linearized_jacobians(i, j) = pr->lin_jac[(size_t)j * pr->n + i]; }
     e->last_marginalization_info = info;
   }
+  if (g_relo.on) {                       // the state setReloFrame() (estimator.cpp:1109-1127) leaves behind
+    e->relocalization_info = 1; e->relo_frame_local_index = g_relo.local_index; e->match_points = g_relo.match;
+    memcpy(e->relo_Pose, g_relo.pose, sizeof g_relo.pose);
+    e->prev_relo_t = Eigen::Vector3d(0, 0, 0); e->prev_relo_r = Eigen::Matrix3d::Identity();
+  }
   MarginalizationInfo* before = e->last_marginalization_info;
   g_hook = EstHook();
   g_hook.est = e; g_hook.L = L;
+  if (g_relo.on && solved->relo_pose) g_hook.inj_relo = solved->relo_pose;
   g_hook.inj_pose = solved->para_pose; g_hook.inj_sb = solved->para_speed_bias; g_hook.inj_ex = solved->para_ex_pose;
   g_hook.inj_feat = solved->inv_depth; g_hook.inj_td = o->estimate_td ? solved->para_td : nullptr;
   g_hook.entry_pose = entry_pose; g_hook.entry_sb = entry_sb; g_hook.entry_ex = entry_ex; g_hook.entry_feat = entry_feat;
-  ceres::solve_hook() = est_solve_hook;
+  if (ref_on_estimator_created) ref_on_estimator_created(e);
+  else ceres::solve_hook() = est_solve_hook;
   e->optimization();
   ceres::solve_hook() = nullptr;
+  if (g_relo.on) {
+    memcpy(g_relo.out_pose, e->relo_Pose, sizeof g_relo.out_pose);
+    for (int a = 0; a < 3; ++a) g_relo.rel_t[a] = e->relo_relative_t(a);
+    g_relo.rel_yaw = e->relo_relative_yaw;
+    g_relo.on = false;
+  }
   scal[0] = g_hook.entry_cost; scal[1] = g_hook.max_time;
   for (int i = 0; i < 8; ++i) counts[i] = g_hook.counts[i];
   for (int i = 0; i < 4; ++i) options[i] = g_hook.options[i];

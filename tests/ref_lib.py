@@ -8,20 +8,50 @@ import __graft_entry__ as g
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PATH = os.path.join(ROOT, "oracle", "_ref", "libvins_ref.so")
+PATH_BVIO = os.path.join(ROOT, "oracle", "_ref", "libvins_bvio.so")
 _lib = None
+_lib_bvio = None
 
 
 def load():
     """None when the library is neither prebuilt nor buildable (no /root/reference)."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(PATH) and os.path.isdir("/root/reference/vins_estimator/src/factor"):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
-    if not os.path.exists(PATH):
+    if _lib is None:
+        _lib = _load(PATH, "ref")
+    return _lib
+
+
+def load_bvio():
+    """oracle/_ref/libvins_bvio.so: the same reference classes and entry points with the reference-side adapter
+    (adapters/vins) linked behind Estimator::optimization() / FeatureSelector::select() -> libbvio.so.  Loading it needs
+    libbvio.so (and therefore the CUDA runtime), but no GPU until bvio_glue_enable() is called."""
+    global _lib_bvio
+    if _lib_bvio is None:
+        L = _load(PATH_BVIO, "ref_bvio")
+        if L is not None:
+            abi = g.load_package().abi
+            L.bvio_glue_enable.argtypes = [C.c_int32]
+            L.bvio_glue_attach.argtypes = [C.c_void_p]
+            L.bvio_glue_attach.restype = None
+            L.bvio_glue_disable.restype = None
+            L.bvio_glue_counts.argtypes = [abi.c_int32_p]
+            L.bvio_glue_counts.restype = None
+            L.bvio_glue_last_summary.argtypes = [C.POINTER(abi.Summary), C.POINTER(abi.SelectSummary)]
+            L.bvio_glue_last_summary.restype = None
+            L.bvio_glue_launches.restype = C.c_longlong
+            L.bvio_glue_capture_created.argtypes = [C.c_int32]
+            L.bvio_glue_capture_created.restype = None
+        _lib_bvio = L
+    return _lib_bvio
+
+
+def _load(path, target):
+    if not os.path.exists(path) and os.path.isdir("/root/reference/vins_estimator/src/factor"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), target])
+    if not os.path.exists(path):
         return None
     abi = g.load_package().abi
-    L = C.CDLL(PATH)
+    L = C.CDLL(path)
     dp, i32, d = abi.c_double_p, C.c_int32, C.c_double
     L.ref_projection_factor.argtypes = [dp, dp, dp, dp, dp, d, d, dp, dp, dp, dp, dp]
     L.ref_projection_factor.restype = None
@@ -86,6 +116,9 @@ def load():
     W, O = C.POINTER(abi.WindowS), C.POINTER(abi.Opts)
     L.ref_estimator_optimization.argtypes = [W, O, i32, W, dp, dp, dp, dp, dp, ip, ip, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(abi.PriorOut)]
     L.ref_estimator_last_normal.argtypes = [dp, dp, i32]
+    L.ref_estimator_set_relo.argtypes = [i32, ip, dp, dp, i32]
+    L.ref_estimator_set_relo.restype = None
+    L.ref_estimator_get_relo.argtypes = [dp, dp, dp]
     L.SOLVE_CB = C.CFUNCTYPE(None)
     L.ref_set_solve_callback.argtypes = [C.c_void_p]
     L.ref_set_solve_callback.restype = None
@@ -120,5 +153,4 @@ def load():
     L.ref_est_process_imu.restype = None
     L.ref_est_process_image.argtypes = [vp, d, i32, ip, dp]
     L.ref_est_dump_features.argtypes = [vp, i32, ip, ip, ip, dp]
-    _lib = L
     return L

@@ -427,3 +427,68 @@ def test_two_contexts_on_two_devices(pkg, oracle):
     ho, so = abi.WindowHandle(w), abi.Summary()
     assert oracle.oracle_optimize(C.byref(ho.s), C.byref(abi.default_opts()), C.byref(so)) == 0
     assert np.linalg.norm(res[1][0] - ho.state_vector()) <= 1e-6 * np.linalg.norm(ho.state_vector())
+
+
+@pytest.mark.parametrize("seed,L,strategy,ex", [(0, 80, 1, 0), (1, 150, 0, 0), (2, 60, 1, 1), (3, 1500, 1, 0)])
+def test_relocalization_factors_match_oracle(env, seed, L, strategy, ex):
+    """estimator.cpp:760-792 on the device (bvio_window.relo_*): reduced system at entry and the solve at the
+    reference's budget against the oracle, which is pinned to the reference's own optimization() with
+    relocalization_info set (tests/test_reference_pin.py::test_relocalization_factors_against_reference)."""
+    abi, synth, orc, ctx = env
+    K = 11
+    w = synth.add_relocalization(synth.make_window(seed=seed, K=K, L=L), seed, local_index=4, max_matches=60)
+    if ex:
+        w = dataclasses_replace_relo(_perturb_extrinsic(synth, w, seed), w)
+    assert len(w.relo_lm) >= 5
+    kw = dict(strategy=strategy, estimate_extrinsic=ex)
+    npar = 15 * (K + 1) + 6 * ex
+    o = abi.default_opts(**kw)
+    out = []
+    for dev in (True, False):
+        hh = abi.WindowHandle(w)
+        S, g, h, b, c = np.zeros((npar, npar)), np.zeros(npar), np.zeros(L), np.zeros(L), np.zeros(1)
+        if dev:
+            ctx.check(ctx.L.bvio_debug_linearize(ctx.h, C.byref(hh.s), C.byref(o), abi.dptr(S), abi.dptr(g), abi.dptr(h), abi.dptr(b),
+                                                 abi.dptr(c)), "debug_linearize")
+        else:
+            assert orc.oracle_linearize(C.byref(hh.s), C.byref(o), abi.dptr(S), abi.dptr(g), abi.dptr(h), abi.dptr(b), abi.dptr(c)) == 0
+        out.append((S, g, h, b, c[0]))
+    (S1, g1, h1, b1, c1), (S2, g2, h2, b2, c2) = out
+    assert abs(c1 - c2) <= 1e-11 * c2
+    assert np.abs(S1 - S2).max() <= 1e-9 * np.abs(S2).max() and np.abs(g1 - g2).max() <= 1e-9 * max(np.abs(g2).max(), 1.0)
+    assert np.abs(h1 - h2).max() <= 1e-9 * np.abs(h2).max() and np.abs(b1 - b2).max() <= 1e-9 * np.abs(b2).max()
+    assert np.abs(S2[15 * K:15 * K + 6, 15 * K:15 * K + 6]).max() > 0 and np.abs(S1[15 * K + 6:15 * K + 15]).max() == 0
+    hg, ho, sg, so = abi.WindowHandle(w), abi.WindowHandle(w), abi.Summary(), abi.Summary()
+    ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(hg.s), C.byref(o), C.byref(sg)), "bvio_optimize")
+    assert orc.oracle_optimize(C.byref(ho.s), C.byref(o), C.byref(so)) == 0
+    assert (sg.iterations, sg.num_accepted, sg.num_rejected, sg.termination) == (so.iterations, so.num_accepted, so.num_rejected, so.termination)
+    assert np.linalg.norm(hg.state_vector() - ho.state_vector()) <= 1e-6 * np.linalg.norm(ho.state_vector())
+    assert np.abs(hg.relo_pose - ho.relo_pose).max() <= 1e-6 and np.abs(ho.relo_pose - w.relo_pose).max() > 1e-5
+    assert abs(sg.final_cost - so.final_cost) <= 1e-8 * so.final_cost
+
+
+def dataclasses_replace_relo(w_new, w_relo):
+    import dataclasses
+    return dataclasses.replace(w_new, relo_pose=w_relo.relo_pose, relo_lm=w_relo.relo_lm, relo_xy=w_relo.relo_xy)
+
+
+def test_relocalization_rejections(env):
+    abi, synth, orc, ctx = env
+    w = synth.add_relocalization(synth.make_window(seed=0, K=11, L=40, td_true=0.002), 0)
+    h, s = abi.WindowHandle(w), abi.Summary()
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(abi.default_opts(estimate_td=1, TR=0.01)), C.byref(s)) == -4   # UNSUPPORTED
+    w2 = synth.add_relocalization(synth.make_window(seed=0, K=11, L=40), 0)
+    w2.relo_lm = w2.relo_lm[::-1].copy()                                  # not ascending
+    h2 = abi.WindowHandle(w2)
+    assert ctx.L.bvio_optimize(ctx.h, C.byref(h2.s), C.byref(abi.default_opts()), C.byref(s)) == -1
+    # batches mix windows with and without matches
+    wa = synth.add_relocalization(synth.make_window(seed=5, K=11, L=60), 5)
+    wb = synth.make_window(seed=6, K=11, L=60)
+    hs = [abi.WindowHandle(wa), abi.WindowHandle(wb)]
+    arr = (abi.WindowS * 2)(hs[0].s, hs[1].s)
+    sums = (abi.Summary * 2)()
+    ctx.check(ctx.L.bvio_optimize_batch(ctx.h, arr, 2, C.byref(abi.default_opts()), sums), "batch")
+    for wsrc, hdev in zip((wa, wb), hs):
+        ho, so = abi.WindowHandle(wsrc), abi.Summary()
+        assert orc.oracle_optimize(C.byref(ho.s), C.byref(abi.default_opts()), C.byref(so)) == 0
+        assert np.linalg.norm(hdev.state_vector() - ho.state_vector()) <= 1e-6 * np.linalg.norm(ho.state_vector())

@@ -883,6 +883,98 @@ def test_reference_optimization_end_to_end_with_numpy_trust_region_row_a7(pkg, o
     assert r["prior"] is not None and r["prior"]["n"] >= 69
 
 
+@pytest.mark.parametrize("seed,L,strategy", [(0, 80, 1), (1, 100, 0), (2, 60, 1)])
+def test_relocalization_factors_against_reference(pkg, oracle, ref, seed, L, strategy):
+    """estimator.cpp:760-792: with relocalization_info set the reference adds the pose block relo_Pose and one
+    ProjectionFactor per matched landmark between Pose[start_frame] and relo_Pose.  The reference's own optimization()
+    builds that problem here; its normal equations (Schur-reduced) and the trajectory of the numpy trust-region loop on
+    its live problem must agree with the oracle, which carries relo_Pose as one more frame (bvio_window.relo_*)."""
+    abi, synth = pkg.abi, pkg.synth
+    K = 11
+    w = synth.add_relocalization(synth.make_window(seed=seed, K=K, L=L), seed, local_index=4)
+    n_relo = len(w.relo_lm)
+    assert n_relo >= 5
+    o_kw = dict(strategy=strategy, max_iters=8, max_time_s=0.0)
+    free = np.r_[np.arange(15 * K), 15 * K + 7 + np.arange(L), 15 * K + 7 + L + np.arange(6)].astype(int)
+    gfree = np.r_[np.arange(16 * K), 16 * K + 8 + np.arange(L), 16 * K + 8 + L + np.arange(7)].astype(int)
+    log = {}
+
+    def solve():
+        nr, nl, ng = C.c_int32(), C.c_int32(), C.c_int32()
+        assert ref.ref_live_dims(C.byref(nr), C.byref(nl), C.byref(ng)) == 0
+        nr, nl, ng = nr.value, nl.value, ng.value
+        assert nl == 15 * K + 7 + L + 6 and ng == 16 * K + 8 + L + 7
+        x0 = np.zeros(ng)
+        ref.ref_live_get_state(abi.dptr(x0))
+
+        def evaluate(x):
+            ref.ref_live_set_state(abi.dptr(np.ascontiguousarray(x)))
+            J, r, c = np.zeros(nr * nl), np.zeros(nr), np.zeros(1)
+            assert ref.ref_live_evaluate(abi.dptr(J), abi.dptr(r), abi.dptr(c)) == 0
+            return J.reshape(nr, nl)[:, free], r, float(c[0])
+
+        def plus(x, d):
+            full, out = np.zeros(nl), np.zeros(ng)
+            full[free] = d
+            ref.ref_live_plus(abi.dptr(np.ascontiguousarray(x)), abi.dptr(full), abi.dptr(out))
+            return out
+        x, trace, term = np_ref.trust_region_loop(x0, evaluate, plus, lambda x: x[gfree], strategy=strategy, max_iters=8)
+        ref.ref_live_set_state(abi.dptr(np.ascontiguousarray(x)))
+        log.update(x=x, trace=trace, term=term, cost=evaluate(x)[2])
+    cb = ref.SOLVE_CB(solve)
+    ref.ref_set_solve_callback(C.cast(cb, C.c_void_p))
+    ref.ref_estimator_set_relo(n_relo, abi.iptr(w.relo_lm), abi.dptr(np.ascontiguousarray(w.relo_xy.reshape(-1))),
+                               abi.dptr(w.relo_pose.copy()), 4)
+    try:
+        r = _run_reference_optimization(pkg, ref, w, w, 0, **o_kw)
+    finally:
+        ref.ref_set_solve_callback(None)
+    relo_out, rel_t, rel_yaw = np.zeros(7), np.zeros(3), np.zeros(1)
+    assert ref.ref_estimator_get_relo(abi.dptr(relo_out), abi.dptr(rel_t), abi.dptr(rel_yaw)) == n_relo
+    c = r["counts"]
+    assert c[2] == w.n_factors + n_relo and c[6] == 2 * K + 2 and c[7] == 1 + (K - 1) + w.n_factors + n_relo
+    # the problem at entry: objective and Schur-reduced normal equations
+    hw, ow = abi.WindowHandle(w), abi.default_opts(**o_kw)
+    cost_o = oracle.oracle_cost(C.byref(hw.s), C.byref(ow))
+    assert abs(r["entry_cost"] - cost_o) <= 1e-9 * cost_o
+    dim = 15 * K + 7 + L + 6
+    Hn, gn = np.zeros(dim * dim), np.zeros(dim)
+    assert ref.ref_estimator_last_normal(abi.dptr(Hn), abi.dptr(gn), dim) == dim
+    Hn = Hn.reshape(dim, dim)
+    keep = np.r_[np.arange(15 * K), 15 * K + 7 + L + np.arange(6)].astype(int)
+    lm = 15 * K + 7 + np.arange(L)
+    hl = np.diag(Hn[np.ix_(lm, lm)])
+    Hpl = Hn[np.ix_(keep, lm)]
+    S_ref = Hn[np.ix_(keep, keep)] - (Hpl / hl) @ Hpl.T
+    g_ref = gn[keep] - (Hpl / hl) @ gn[lm]
+    assert np.abs(S_ref[15 * K:, 15 * K:]).max() > 0
+    npar = 15 * (K + 1)
+    S_o, g_o, h_o, b_o, c_o = np.zeros(npar * npar), np.zeros(npar), np.zeros(L), np.zeros(L), np.zeros(1)
+    assert oracle.oracle_linearize(C.byref(hw.s), C.byref(ow), abi.dptr(S_o), abi.dptr(g_o), abi.dptr(h_o), abi.dptr(b_o), abi.dptr(c_o)) == 0
+    S_o = S_o.reshape(npar, npar)
+    idx = np.r_[np.arange(15 * K), 15 * K + np.arange(6)].astype(int)
+    assert np.abs(S_o[15 * K + 6:]).max() == 0 and np.abs(g_o[15 * K + 6:]).max() == 0     # the unused speed-bias slot
+    assert np.abs(S_o[np.ix_(idx, idx)] - S_ref).max() <= 1e-6 * np.abs(S_ref).max()
+    assert np.abs(g_o[idx] - g_ref).max() <= 1e-6 * np.abs(g_ref).max()
+    assert np.abs(h_o - hl).max() <= 1e-9 * np.abs(hl).max()
+    # the solve: same iterations, same state, same relo_Pose
+    hs, summ = abi.WindowHandle(w.copy()), abi.Summary()
+    assert oracle.oracle_optimize(C.byref(hs.s), C.byref(ow), C.byref(summ)) == 0
+    acc = sum(1 for t in log["trace"] if t[2])
+    assert (summ.iterations, summ.num_accepted, summ.num_rejected, summ.termination) == \
+           (len(log["trace"]), acc, len(log["trace"]) - acc, log["term"]), (summ.as_dict(), log["trace"], log["term"])
+    assert abs(summ.final_cost - log["cost"]) <= 1e-8 * log["cost"]
+    x = log["x"]
+    assert np.abs(x[:7 * K] - hs.pose.reshape(-1)).max() <= 1e-6 and np.abs(x[7 * K:16 * K] - hs.sb.reshape(-1)).max() <= 1e-6
+    assert np.abs(x[-7:] - hs.relo_pose).max() <= 1e-6 and np.abs(relo_out - hs.relo_pose).max() <= 1e-6
+    assert np.abs(hs.relo_pose - w.relo_pose).max() > 1e-4                                   # it really moved
+    # without the matches the solution is a different one
+    w0 = dataclasses.replace(w, relo_pose=None, relo_lm=None, relo_xy=None)
+    h0, s0 = abi.WindowHandle(w0.copy()), abi.Summary()
+    assert oracle.oracle_optimize(C.byref(h0.s), C.byref(ow), C.byref(s0)) == 0
+    assert np.abs(h0.pose - hs.pose).max() > 1e-6
+
+
 def test_slide_window_matches_reference_estimator_row_f1(pkg, oracle, ref):
     """Estimator::slideWindow() itself (estimator.cpp:996-1107: state shifting, preintegration swap / IMU-sample merge,
     slideWindowOld with shift_depth / slideWindowNew) on the exact data the slider holds before each of its slides."""
@@ -1012,27 +1104,13 @@ def test_select_ground_truth_horizon_mode(pkg, oracle, ref, tmp_path):
         assert common >= 0.8 * len(ref_ids)
 
 
-def test_closed_loop_session_against_the_reference_estimator_row_f1(pkg, oracle, ref, tmp_path):
-    """A whole session, frame by frame, through the reference's own Estimator::processIMU / processImage
-    (addFeatureCheckParallax -> triangulate -> optimization -> double2vector -> marginalization -> slideWindow ->
-    removeFailures; Ceres' control flow supplied by np_ref.trust_region_loop on the live problem) next to
-    slider.ReplaySession on the oracle backend, both fed the same recorded IMU / feature traffic and the same bootstrap
-    states.  Keyframe decisions, window states, biases, feature lists and depths must stay together for the whole run."""
-    from slider_backends import OracleBackend
-    from test_replay import _record_session
-    abi, sl, rp, S = pkg.abi, pkg.slider, pkg.replay, pkg.synth
+def numpy_ceres_solver(pkg, ref, K):
+    """attach(h) for reference_estimator_session: Ceres' control flow (traditional dogleg, like the reference) supplied by
+    np_ref.trust_region_loop iterating on the reference's live problem while Estimator::optimization() waits in Solve."""
+    abi = pkg.abi
     f64 = lambda a: np.ascontiguousarray(a, np.float64)
-    path = str(tmp_path / "session.bvio")
-    rec = _record_session(pkg, path, seed=4, frames=30, frame_dt=0.04)      # 25 Hz: keyframes and non-keyframes alternate
-    ses = sl.ReplaySession(S.EUROC_CAM, rec["ric"], rec["tic"], rec["init"], max_feats=70, H=10,
-                           opts=dict(max_iters=8, strategy=1), keyframes="parallax")
-    be = OracleBackend(oracle, abi)
-    K, WS = ses.K, ses.K - 1
-    ex = f64(np.concatenate([rec["tic"], S.rot_to_quat(rec["ric"])]))
-    G = f64([0, 0, S.G_NORM])
-    h = ref.ref_est_create(abi.dptr(ex), abi.dptr(G), 460.0, 8, S.ACC_N, S.GYR_N, S.ACC_W, S.GYR_W, sl.INIT_DEPTH, sl.MIN_PARALLAX)
 
-    def solve():                                           # Ceres' control flow, traditional dogleg like the reference
+    def solve():
         nr, nl, ng = C.c_int32(), C.c_int32(), C.c_int32()
         assert ref.ref_live_dims(C.byref(nr), C.byref(nl), C.byref(ng)) == 0
         nr, nl, ng = nr.value, nl.value, ng.value
@@ -1056,7 +1134,33 @@ def test_closed_loop_session_against_the_reference_estimator_row_f1(pkg, oracle,
         x, _, _ = np_ref.trust_region_loop(x0, evaluate, plus, lambda x: x[gfree], strategy=1, max_iters=8)
         ref.ref_live_set_state(abi.dptr(f64(x)))
     cb = ref.SOLVE_CB(solve)
-    ref.ref_set_solve_callback(C.cast(cb, C.c_void_p))
+
+    def attach(h):
+        ref.ref_set_solve_callback(C.cast(cb, C.c_void_p))
+        return lambda: ref.ref_set_solve_callback(None)
+    attach.keep_alive = cb
+    return attach
+
+
+def reference_estimator_session(pkg, ref, be, attach, tmp_path, frames=30):
+    """A whole session, frame by frame, through the reference's own Estimator::processIMU / processImage
+    (addFeatureCheckParallax -> triangulate -> optimization -> double2vector -> marginalization -> slideWindow ->
+    removeFailures) in library `ref`, next to slider.ReplaySession on backend `be`, both fed the same recorded IMU /
+    feature traffic and the same bootstrap states.  `attach(h)` installs whatever answers the Estimator's ceres::Solve
+    (and returns a detach function).  Keyframe decisions, window states, biases, feature lists and depths must stay
+    together for the whole run.  -> (frames checked, flags, worst state difference)."""
+    from test_replay import _record_session
+    abi, sl, rp, S = pkg.abi, pkg.slider, pkg.replay, pkg.synth
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)
+    path = str(tmp_path / "session.bvio")
+    rec = _record_session(pkg, path, seed=4, frames=frames, frame_dt=0.04)      # 25 Hz: keyframes and non-keyframes alternate
+    ses = sl.ReplaySession(S.EUROC_CAM, rec["ric"], rec["tic"], rec["init"], max_feats=70, H=10,
+                           opts=dict(max_iters=8, strategy=1), keyframes="parallax")
+    K, WS = ses.K, ses.K - 1
+    ex = f64(np.concatenate([rec["tic"], S.rot_to_quat(rec["ric"])]))
+    G = f64([0, 0, S.G_NORM])
+    h = ref.ref_est_create(abi.dptr(ex), abi.dptr(G), 460.0, 8, S.ACC_N, S.GYR_N, S.ACC_W, S.GYR_W, sl.INIT_DEPTH, sl.MIN_PARALLAX)
+    detach = attach(h)
     frame_obs = {}
 
     def newest_obs():
@@ -1109,7 +1213,16 @@ def test_closed_loop_session_against_the_reference_estimator_row_f1(pkg, oracle,
                     n_checked += 1
                 f += 1
     finally:
-        ref.ref_set_solve_callback(None)
+        detach()
         ref.ref_est_release(h)
+    return n_checked, flags, worst
+
+
+def test_closed_loop_session_against_the_reference_estimator_row_f1(pkg, oracle, ref, tmp_path):
+    """reference_estimator_session with Ceres' control flow supplied by np_ref.trust_region_loop on the live problem, next
+    to slider.ReplaySession on the oracle backend."""
+    from slider_backends import OracleBackend
+    K = ref.ref_window_size() + 1
+    n_checked, flags, worst = reference_estimator_session(pkg, ref, OracleBackend(oracle, pkg.abi), numpy_ceres_solver(pkg, ref, K), tmp_path)
     assert n_checked >= 10 and 0 in flags and 1 in flags, (n_checked, flags)
     print("closed loop vs reference: frames", n_checked, "flags", flags, "worst state difference", worst)

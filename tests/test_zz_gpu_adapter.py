@@ -1,0 +1,164 @@
+"""The drop-in, proven with the reference's OWN classes on the GPU: oracle/_ref/libvins_bvio.so holds the reference's
+unmodified Estimator / FeatureManager / FeatureSelector (compiled from /root/reference) with the reference-side adapter
+adapters/vins/bvio_adapter.cpp linked behind ceres::Solve, MarginalizationInfo::marginalize and the numerical part of
+FeatureSelector::select (adapters/vins/interpose.cpp) -- so Estimator::processImage() and FeatureSelector::select()
+run their hot path through libbvio.so on the B200.  Skipped when the library was not prebuilt (no /root/reference)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import ref_lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def glue():
+    L = ref_lib.load_bvio()
+    if L is None:
+        pytest.skip("oracle/_ref/libvins_bvio.so not built and /root/reference not present")
+    assert L.bvio_glue_enable(0) == 0
+    yield L
+    L.bvio_glue_disable()
+
+
+def _counts(L):
+    c = np.zeros(4, np.int32)
+    L.bvio_glue_counts(c.ctypes.data_as(C.POINTER(C.c_int32)))
+    return c
+
+
+def test_live_reference_estimator_on_libbvio(pkg, oracle, glue, tmp_path):
+    """20+ optimized frames of Estimator::processIMU / processImage (the reference's code) with every
+    optimization() solved and marginalized by libbvio.so through the adapter, next to slider.ReplaySession on the CPU
+    oracle: same keyframe decisions, window states within the 1e-5 / 1e-4 the numpy-Ceres session is held to (measured:
+    4e-6), identical feature bookkeeping, equal prior sizes."""
+    from slider_backends import OracleBackend
+    from test_reference_pin import reference_estimator_session
+    before = _counts(glue)
+
+    def attach(h):
+        glue.bvio_glue_attach(h)
+        return lambda: None
+    n_checked, flags, worst = reference_estimator_session(pkg, glue, OracleBackend(oracle, pkg.abi), attach, tmp_path)
+    after = _counts(glue)
+    assert n_checked >= 10 and 0 in flags and 1 in flags, (n_checked, flags)
+    assert after[0] - before[0] == n_checked and after[1] - before[1] >= n_checked - 2 and after[3] == 0, (before, after)
+    assert glue.bvio_glue_launches() > 0
+    print("reference Estimator on libbvio: frames", n_checked, "flags", flags, "worst state difference", worst)
+    assert worst <= 1e-5
+
+
+def test_replay_session_on_the_gpu_backend_row_f4(pkg, oracle, tmp_path):
+    """recorded front-end traffic (ROS wire format dump) -> replay.read_dump -> slider.ReplaySession ->
+    GpuBackend (libbvio through the C-ABI: triangulate, optimize, marginalize, horizon, select), next to the same session on
+    the oracle backend."""
+    from slider_backends import OracleBackend
+    from test_replay import _record_session
+    sl, rp, S = pkg.slider, pkg.replay, pkg.synth
+    path = str(tmp_path / "session.bvio")
+    rec = _record_session(pkg, path, seed=4, frames=30, frame_dt=0.04)
+    ctx = pkg.lib.Context(0)
+    mk = lambda: sl.ReplaySession(S.EUROC_CAM, rec["ric"], rec["tic"], rec["init"], max_feats=70, H=10,
+                                  opts=dict(max_iters=8, strategy=1), keyframes="parallax")
+    sg, so = mk(), mk()
+    bg, bo = sl.GpuBackend(ctx, pkg.abi), OracleBackend(oracle, pkg.abi)
+    n, worst, nsel = 0, 0.0, 0
+    for topic, msg in rp.read_dump(path):
+        lg, lo = list(sg.feed(topic, msg, bg)), list(so.feed(topic, msg, bo))
+        assert len(lg) == len(lo)
+        for a, b in zip(lg, lo):
+            if a is None or b is None:
+                assert a is None and b is None
+                continue
+            assert a["flag"] == b["flag"] and a["L"] == b["L"] and a["iterations"] == b["iterations"]
+            assert sg.last_selected.tolist() == so.last_selected.tolist()
+            nsel += len(sg.last_selected)
+            worst = max(worst, np.abs(sg.pose - so.pose).max(), np.abs(sg.sb - so.sb).max())
+            assert set(sg.tracks) == set(so.tracks)
+            n += 1
+    launches = ctx.L.bvio_launch_count(ctx.h)
+    ctx.close()
+    assert n >= 10 and worst <= 1e-6 and launches > 100, (n, worst, launches)
+    print("replay on GpuBackend: frames", n, "selected", nsel, "worst state difference vs oracle backend", worst)
+
+
+@pytest.mark.parametrize("seed,N,U,n_lm,kappa,gt", [(0, 120, 0, 60, 25, False), (1, 150, 12, 80, 30, False), (3, 200, 20, 120, 40, True),
+                                                     (1, 150, 12, 80, 30, True)])
+def test_reference_feature_selector_on_libbvio(pkg, glue, tmp_path, seed, N, U, n_lm, kappa, gt):
+    """FeatureSelector::select (the reference's code: id bookkeeping, horizon generation in IMU and ground-truth mode,
+    kappa) with its numerical part answered by bvio_select through the adapter, against the reference's own CPU
+    selection from libvins_ref.so: same ids, same order, same tracked list."""
+    from test_reference_pin import reference_select_case
+    ref = ref_lib.load()
+    if ref is None:
+        pytest.skip("libvins_ref.so missing")
+    csv = str(tmp_path / "gt.csv") if gt else None
+    want, _ = reference_select_case(pkg, ref, seed, N, U, n_lm, kappa, gt_csv=csv)
+    before = _counts(glue)
+    got, _ = reference_select_case(pkg, glue, seed, N, U, n_lm, kappa, gt_csv=csv)
+    after = _counts(glue)
+    assert after[2] - before[2] == 1 and after[3] == 0
+    assert len(want) > 0 and got.tolist() == want.tolist(), (got, want)
+
+
+@pytest.mark.parametrize("seed,L,relo,flag", [(0, 80, True, 0), (1, 100, False, 0), (2, 60, True, 1), (3, 150, False, 1)])
+def test_reference_optimization_call_on_libbvio(pkg, oracle, glue, seed, L, relo, flag):
+    """One whole Estimator::optimization() of the reference (vector2double, problem construction incl. the relocalization
+    factors of estimator.cpp:760-792, `ceres::Solve` -> bvio_optimize, double2vector incl. the relo bookkeeping,
+    marginalization -> bvio_marginalize, getParameterBlocks) against the oracle's solve + double2vector + marginalize."""
+    import dataclasses
+    from test_oracle_marg import info_in_state_coords, run_marg
+    from test_reference_pin import _run_reference_optimization
+    abi, synth = pkg.abi, pkg.synth
+    K = 11
+    o_kw = dict(strategy=1, max_iters=8, max_time_s=0.04)
+    keys = ("n", "block_kind", "block_frame", "block_idx", "x0", "lin_jac", "lin_res")
+    p0 = run_marg(abi, oracle.oracle_marginalize, synth.make_window(seed=seed, K=K, L=L), 0, opts=abi.default_opts(**o_kw))
+    w = dataclasses.replace(synth.make_window(seed=seed + 100, K=K, L=L), prior={k: p0[k] for k in keys})
+    if relo:
+        w = synth.add_relocalization(w, seed, local_index=4)
+        glue.ref_estimator_set_relo(len(w.relo_lm), abi.iptr(w.relo_lm), abi.dptr(np.ascontiguousarray(w.relo_xy.reshape(-1))),
+                                    abi.dptr(w.relo_pose.copy()), 4)
+    before = _counts(glue)
+    glue.bvio_glue_capture_created(1)
+    try:
+        r = _run_reference_optimization(pkg, glue, w, w, flag, **o_kw)
+    finally:
+        glue.bvio_glue_capture_created(0)
+    after = _counts(glue)
+    assert after[0] - before[0] == 1 and after[1] - before[1] == 1 and after[3] == 0
+    # oracle: solve, gauge, marginalize
+    hs, summ = abi.WindowHandle(w.copy()), abi.Summary()
+    ow = abi.default_opts(**dict(o_kw, max_time_s=0.0))
+    assert oracle.oracle_optimize(C.byref(hs.s), C.byref(ow), C.byref(summ)) == 0
+    gs = abi.Summary()
+    glue.bvio_glue_last_summary(C.byref(gs), None)
+    assert (gs.iterations, gs.num_accepted, gs.termination) == (summ.iterations, summ.num_accepted, summ.termination)
+    pose, sb = hs.pose.copy(), hs.sb.copy()
+    oracle.oracle_double2vector(abi.dptr(w.para_pose[0].copy()), K, abi.dptr(pose), abi.dptr(sb))
+    R_o = np.array([synth.quat_to_rot(q / np.linalg.norm(q)) for q in pose[:, 3:]])
+    scale = max(1.0, np.abs(pose[:, :3]).max())
+    assert np.abs(r["P"] - pose[:, :3]).max() <= 1e-6 * scale and np.abs(r["R"] - R_o).max() <= 1e-6
+    assert np.abs(r["V"] - sb[:, :3]).max() <= 1e-6 and np.abs(r["Ba"] - sb[:, 3:6]).max() <= 1e-6
+    assert np.abs(r["depth"] - 1.0 / hs.inv).max() <= 1e-5 * np.abs(1.0 / hs.inv).max()
+    if relo:
+        relo_out, rel_t, rel_yaw = np.zeros(7), np.zeros(3), np.zeros(1)
+        assert glue.ref_estimator_get_relo(abi.dptr(relo_out), abi.dptr(rel_t), abi.dptr(rel_yaw)) == len(w.relo_lm)
+        assert np.abs(relo_out - hs.relo_pose).max() <= 1e-6 and np.abs(relo_out - w.relo_pose).max() > 1e-4
+    # the new prior: quadratic form in state coordinates vs the oracle's marginalization of the oracle's solution.
+    # The reference marginalizes at the re-gauged state (vector2double after double2vector, estimator.cpp:821 / 930).
+    quat = np.array([synth.rot_to_quat(Rm) for Rm in r["R"]])
+    wpost = dataclasses.replace(w, para_pose=np.hstack([r["P"], quat]), para_speed_bias=np.hstack([r["V"], r["Ba"], r["Bg"]]),
+                                inv_depth=1.0 / r["depth"], relo_pose=None, relo_lm=None, relo_xy=None)
+    po = run_marg(abi, oracle.oracle_marginalize, wpost, flag, opts=ow)
+    pg = r["prior"]
+    assert (pg is None) == (po is None)
+    if po is not None:
+        assert pg["n"] == po["n"]
+        unshift = (lambda f: f + 1) if flag == 0 else (lambda f: f if f < K - 2 else f + 1)
+        Hg, gg = info_in_state_coords(pg, K, unshift)
+        Ho, go = info_in_state_coords(po, K, unshift)
+        assert np.abs(Hg - Ho).max() <= 2e-7 * np.abs(Ho).max()
+        assert np.abs(gg - go).max() <= 1e-4 * max(np.abs(go).max(), 1.0)
