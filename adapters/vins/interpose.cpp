@@ -10,8 +10,9 @@
 //     compiled with -DpreMarginalize=preMarginalize_reference -Dmarginalize=marginalize_reference, which renames the
 //     reference's two definitions; the definitions below take their place (same class, same header).
 //   * FeatureSelector::{calcInfoFromRobotMotion, calcInfoFromFeatures, selectInformativeFeatures}
-//     (feature_selector.cpp:139-171): feature_selector.cpp is compiled with the same kind of renames; the versions below
-//     capture the horizon, skip the host-side information matrices and hand the selection to bvio_adapter::select().
+//     (feature_selector.cpp:139-171): called from select() inside the same translation unit, so their definitions in
+//     feature_selector.o are made weak (objcopy -W) and the strong versions below win at link time; they capture the
+//     horizon, skip the host-side information matrices and hand the selection to bvio_adapter::select().
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

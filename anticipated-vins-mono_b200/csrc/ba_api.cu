@@ -391,6 +391,8 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
       memset(pr, 0, sizeof(bvio_preint));
       pr[6] = 1.0;                                         // delta_q = identity
       pr[16] = 1e9;                                        // sum_dt > 10: no IMU factor into the loop-closure frame
+      for (int i = 0; i < 15; i++) pr[17 + 16 * i] = pr[242 + 16 * i] = 1.0;   // jacobian = covariance = I: ba_prepare's
+                                                           // square-root information stays finite (it is never used)
     }
     h_pr_n[b] = 0; h_pr_nb[b] = 0;
     if (w.prior) {

