@@ -128,8 +128,10 @@ int ba_pick_chunk(int K, int n_extra_blocks);
 size_t ba_solve_smem_bytes(int np);
 size_t ba_linearize_mma_smem_bytes(int K);
 size_t ba_marginalize_smem_bytes(int K, int nmax, int n);
-int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, const int* dropidx, const int* keepidx, double* A,
-                          double* b, double* out_jac, double* out_res, int* status, int method, cudaStream_t st);
+int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, int n0, const int* dropidx, const int* keepidx, double* A,
+                          double* b, double* part, double* out_jac, double* out_res, int* status, int method, cudaStream_t st);
+size_t ba_marginalize_part_doubles(int K, int G);   // scratch of the factor kernel's partial sums
+int ba_marginalize_groups(int n0);                  // CTAs of the factor kernel for n0 landmarks anchored at the dropped frame
 int ba_configure(void);   // cudaFuncSetAttribute for the big-smem kernels; returns cudaError_t
 
 }  // namespace bvio

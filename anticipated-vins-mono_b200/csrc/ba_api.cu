@@ -773,7 +773,10 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* op
   Carver cv;
   size_t o_A = cv.take(sizeof(double) * M * M), o_b = cv.take(sizeof(double) * M), o_jac = cv.take(sizeof(double) * n * n);
   size_t o_res = cv.take(sizeof(double) * n), o_drop = cv.take(sizeof(int) * (m + 1)), o_keep = cv.take(sizeof(int) * n);
-  size_t o_st = cv.take(sizeof(int) * 4);
+  size_t o_st = cv.take(sizeof(int) * 4 + sizeof(unsigned long long) * 8);
+  int n0 = 0;                               // landmarks anchored at the dropped frame: the first n0 in device order
+  if (flag == 0) for (int l = 0; l < w->L; l++) n0 += w->obs_frame[w->lm_obs_offset[l]] == 0;
+  size_t o_part = cv.take(sizeof(double) * ba_marginalize_part_doubles(K, ba_marginalize_groups(n0)));
   cudaError_t e = cudaSuccess;
   if (ctx->marg_bytes < cv.off) {
     if (ctx->marg_scratch) cudaFree(ctx->marg_scratch);
@@ -785,8 +788,8 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* op
   if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_drop, dropidx.data(), sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_keep, keepidx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
-    ctx->launches += ba_launch_marginalize(bb->bt, flag, m, n, (const int*)(scratch + o_drop), (const int*)(scratch + o_keep),
-                                           (double*)(scratch + o_A), (double*)(scratch + o_b), (double*)(scratch + o_jac),
+    ctx->launches += ba_launch_marginalize(bb->bt, flag, m, n, n0, (const int*)(scratch + o_drop), (const int*)(scratch + o_keep),
+                                           (double*)(scratch + o_A), (double*)(scratch + o_b), (double*)(scratch + o_part), (double*)(scratch + o_jac),
                                            (double*)(scratch + o_res), (int*)(scratch + o_st),
                                            getenv("BVIO_MARG_CHOLESKY") ? 1 : 0, ctx->stream);
     e = cudaGetLastError();
@@ -794,7 +797,15 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* op
   if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_jac, scratch + o_jac, sizeof(double) * n * n, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_res, scratch + o_res, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e == cudaSuccess && getenv("BVIO_DEBUG")) { int stv[4] = {0, 0, 0, 0}; cudaMemcpy(stv, scratch + o_st, sizeof stv, cudaMemcpyDeviceToHost); fprintf(stderr, "[bvio] marginalize: m=%d n=%d sweeps/rank=%d log10 pivots min %.2f max %.2f\n", m, n, stv[0], stv[1] / 100.0, stv[2] / 100.0); }
+  if (e == cudaSuccess && getenv("BVIO_DEBUG")) {
+    struct { int stv[4]; unsigned long long ph[8]; } dbg;
+    memset(&dbg, 0, sizeof dbg);
+    cudaMemcpy(&dbg, scratch + o_st, sizeof dbg, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[bvio] marginalize: m=%d n=%d sweeps/rank=%d log10 pivots min %.2f max %.2f | us: factors %.1f prior %.1f drop-eig %.1f "
+            "schur %.1f kept-eig %.1f out %.1f total %.1f\n", m, n, dbg.stv[0], dbg.stv[1] / 100.0, dbg.stv[2] / 100.0,
+            (dbg.ph[1] - dbg.ph[0]) * 1e-3, (dbg.ph[2] - dbg.ph[1]) * 1e-3, (dbg.ph[3] - dbg.ph[2]) * 1e-3, (dbg.ph[4] - dbg.ph[3]) * 1e-3,
+            (dbg.ph[5] - dbg.ph[4]) * 1e-3, (dbg.ph[6] - dbg.ph[5]) * 1e-3, (dbg.ph[6] - dbg.ph[0]) * 1e-3);
+  }
   bvio_batch_free(ctx, bb);
   if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("marginalize: ") + cudaGetErrorString(e));
   for (int i = 0; i < n * n; i++) if (!(out->lin_jac[i] == out->lin_jac[i])) return fail(ctx, BVIO_ERR_NUMERIC, "non-finite prior");

@@ -1857,6 +1857,7 @@ static size_t cost_smem(int K, int nmax) {
   return sizeof(double) * ((size_t)15 * K + 8 + (K + 1) * 7 + (K + 1) * FR + 160 + K * 9 + (K - 1) * 15 + 2 * nmax);
 }
 
+cudaError_t ba_configure_marginalize(void);   // below, next to the kernels
 // __constant__ tables and the dynamic-shared-memory opt-ins are PER DEVICE: remember which devices of this process
 // have been set up (bvio_create may be called for several GPUs in one process)
 static std::mutex g_cfg_mutex;
@@ -1892,6 +1893,7 @@ int ba_configure(void) {
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
+    if ((err = ba_configure_marginalize()) != cudaSuccess) return err;
     if (dev >= 0 && dev < 256) g_cfg_devices[dev >> 6] |= 1ull << (dev & 63);
   }
   return 0;
@@ -1974,18 +1976,23 @@ struct MargArgs {
   int flag;             // 0 MARGIN_OLD, 1 MARGIN_SECOND_NEW
   int M;                // 15K + 7: frame-major 15-blocks, then the extrinsic block, then td
   int m, n, ne;         // dropped / kept dimensions, ne = n rounded up to even
+  int n0;               // landmarks anchored at frame 0 (the first n0 of the window in device order)
+  int G;                // CTAs of the factor kernel that hold visual partial sums (the IMU CTA comes after them)
   const int* dropidx;   // [m] indices into the M layout
   const int* keepidx;   // [n]
   double* A;            // [M*M] scratch
   double* b;            // [M]
+  double* part;         // [G][VD*VD + VD] visual partial sums, then [930] IMU J^T J (30x30) and J^T r (30)
   double* out_jac;      // [n*n] column-major linearized_jacobians
   double* out_res;      // [n]
-  int* status;          // [1] sweeps used (eigen) / rank (cholesky)
+  int* status;          // [4] sweeps used (eigen) / rank (cholesky), pivot range; then [8] u64 phase time stamps (ns)
   int method;           // 0: eigen-decomposition like the reference, 1: pivoted Cholesky (same J^T J, J^T r)
 };
 
-constexpr int MARG_THREADS = 512;
-constexpr int MF = 42;      // per-factor staging: A(12) B(12) E(12) c(2) r(2) td(2)
+constexpr int MARG_THREADS = 1024;  // the elimination / eigen-decomposition CTA
+constexpr int MARG_FT = 256;        // threads of a factor CTA
+constexpr int MARG_NB = 4;          // landmarks a factor CTA evaluates together
+constexpr int MF = 42;              // per-factor staging: A(12) B(12) E(12) c(2) r(2) td(2)
 
 // column `d` (visual layout: 6 dims per frame, then 6 extrinsic dims, then td) of factor f's 2 x . Jacobian
 __device__ __forceinline__ void marg_col(const double* st, int fj, int K, int d, double& j0, double& j1) {
@@ -1995,201 +2002,323 @@ __device__ __forceinline__ void marg_col(const double* st, int fj, int K, int d,
   else if (d < 6 * K + 6) { j0 = st[24 + d - 6 * K]; j1 = st[30 + d - 6 * K]; }
   else { j0 = st[40]; j1 = st[41]; }
 }
+// LOCAL column a of a factor: 0..5 pose of frame 0, 6..11 pose of frame fj, 12..17 extrinsics, 18 td
+__device__ __forceinline__ void marg_lcol(const double* st, int a, double& j0, double& j1) {
+  if (a < 18) { const int blk = a / 6, r = a - 6 * blk; j0 = st[12 * blk + r]; j1 = st[12 * blk + 6 + r]; }
+  else { j0 = st[40]; j1 = st[41]; }
+}
+__device__ __forceinline__ int marg_gcol(int a, int fj, int K) {
+  return a < 6 ? a : (a < 12 ? 6 * fj + a - 6 : 6 * K + a - 12);     // a == 18 -> 6K + 6
+}
 
+// residual + Jacobians of one visual factor anchored at frame 0, loss-corrected: 42 doubles
+__device__ void marg_eval_factor(const BaBatch& bt, int w, int l, int o0, int f, const double* sFr, const double* sEx, double* st, int* fj_out) {
+  const int fj = bt.obs_frame[o0 + 1 + f];
+  double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + f];
+  double2 vi = {0, 0}, vj = {0, 0};
+  if (bt.est_td) {   // ProjectionTdFactor: time-shifted points (projection_td_factor.cpp:51-52)
+    vi = bt.obs_vel[o0]; vj = bt.obs_vel[o0 + 1 + f];
+    const double td = bt.td0[w], si_ = td + bt.obs_shift[o0], sj_ = td + bt.obs_shift[o0 + 1 + f];
+    pi.x -= si_ * vi.x; pi.y -= si_ * vi.y; pj.x -= sj_ * vj.x; pj.y -= sj_ * vj.y;
+  }
+  const double lam = bt.invd0[l];
+  const double* Fi = sFr;
+  const double* Fj = sFr + fj * FR;
+  ProjGeom g = proj_geom(Fi, Fj, sEx, pi.x, pi.y, lam);
+  const double inv = 1.0 / g.pcj.z, si = bt.sqrt_info;
+  const double r0 = si * (g.pcj.x * inv - pj.x), r1 = si * (g.pcj.y * inv - pj.y);
+  const double red[2][3] = {{si * inv, 0.0, -si * g.pcj.x * inv * inv}, {0.0, si * inv, -si * g.pcj.y * inv * inv}};
+  double rho0, rho1;
+  cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
+  const double sr = sqrt(rho1);
+  const d3 tic{sEx[9], sEx[10], sEx[11]};
+  const d3 pci = (1.0 / lam) * d3{pi.x, pi.y, 1.0};
+  // tmp_r = ric^T Rj^T Ri ric ; tvec = ric^T (Rj^T (Ri tic + Pi - Pj) - tic)   (projection_factor.cpp:100-105)
+  double RjTRi[9], T1[9], tmp_r[9];
+  mtm3(Fj, Fi, RjTRi);
+  mtm3(sEx, RjTRi, T1);               // ric^T Rj^T Ri
+  mm3(T1, sEx, tmp_r);
+  const d3 inner = mtv3(Fj, mv3(Fi, tic) + d3{Fi[9], Fi[10], Fi[11]} - d3{Fj[9], Fj[10], Fj[11]}) - tic;
+  const d3 tvec = mtv3(sEx, inner);
+  const d3 trp = mv3(tmp_r, pci);
+  for (int a = 0; a < 2; a++) {
+    double Gm[3], Q[3];
+    for (int c = 0; c < 3; c++) Gm[c] = red[a][0] * sEx[c * 3 + 0] + red[a][1] * sEx[c * 3 + 1] + red[a][2] * sEx[c * 3 + 2];
+    for (int c = 0; c < 3; c++) Q[c] = Gm[0] * Fj[c * 3 + 0] + Gm[1] * Fj[c * 3 + 1] + Gm[2] * Fj[c * 3 + 2];
+    const d3 u = mtv3(Fi, d3{Q[0], Q[1], Q[2]});
+    const d3 jr = cross3(g.pimu_i, u);
+    const d3 jjr = cross3(d3{Gm[0], Gm[1], Gm[2]}, g.pimu_j);
+    st[a * 6 + 0] = sr * Q[0]; st[a * 6 + 1] = sr * Q[1]; st[a * 6 + 2] = sr * Q[2];
+    st[a * 6 + 3] = sr * jr.x; st[a * 6 + 4] = sr * jr.y; st[a * 6 + 5] = sr * jr.z;
+    st[12 + a * 6 + 0] = -sr * Q[0]; st[12 + a * 6 + 1] = -sr * Q[1]; st[12 + a * 6 + 2] = -sr * Q[2];
+    st[12 + a * 6 + 3] = sr * jjr.x; st[12 + a * 6 + 4] = sr * jjr.y; st[12 + a * 6 + 5] = sr * jjr.z;
+    // extrinsic block: reduce * [ ric^T (Rj^T Ri - I) | -tmp_r [pci]x + [tmp_r pci]x + [tvec]x ]
+    const double rd[3] = {red[a][0], red[a][1], red[a][2]};
+    double el[3];
+    for (int c = 0; c < 3; c++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += rd[k] * (T1[k * 3 + c] - sEx[c * 3 + k]);   // ric^T Rj^T Ri - ric^T
+      el[c] = s;
+    }
+    // row^T [v]x = (row x v)^T ;  row^T (-tmp_r [pci]x) = -((tmp_r^T row) x pci)^T
+    const d3 rowv{rd[0], rd[1], rd[2]};
+    const d3 t1 = mtv3(tmp_r, rowv);
+    const d3 e1 = cross3(t1, pci);
+    const d3 e2 = cross3(rowv, trp);
+    const d3 e3 = cross3(rowv, tvec);
+    st[24 + a * 6 + 0] = sr * el[0]; st[24 + a * 6 + 1] = sr * el[1]; st[24 + a * 6 + 2] = sr * el[2];
+    st[24 + a * 6 + 3] = sr * (-e1.x + e2.x + e3.x); st[24 + a * 6 + 4] = sr * (-e1.y + e2.y + e3.y);
+    st[24 + a * 6 + 5] = sr * (-e1.z + e2.z + e3.z);
+    st[36 + a] = sr * (-dot3(u, g.pimu_i - tic) / lam);
+    // td Jacobian (projection_td_factor.cpp:131-136); zero when td is not estimated
+    st[40 + a] = bt.est_td ? sr * (-dot3(u, mv3(sEx, d3{vi.x, vi.y, 0.0})) / lam + si * (a == 0 ? vj.x : vj.y)) : 0.0;
+  }
+  st[38] = sr * r0; st[39] = sr * r1;
+  *fj_out = fj;
+}
+
+// ---- kernel 1: the factors of the dropped frame, landmark-parallel over a few CTAs ----------------------------------------------
+// CTA g < G: landmarks g*NB, g*NB + G*NB, ... of the n0 anchored at frame 0 (estimator.cpp:852-893): factor evaluation, analytic
+// elimination of the landmark's inverse depth (its 1x1 block of the reference's pseudo-inverse, eps = 1e-8), accumulation
+// of  sum_f J_f^T J_f - w w^T / h  and  sum_f J_f^T r_f - w b / h  in shared memory, one partial sum per CTA to HBM.
+// CTA G: the IMU factor 0 -> 1 (estimator.cpp:841-850): raw Jacobian by one thread, whitening and J^T J by all.
+__global__ void __launch_bounds__(MARG_FT) ba_marg_factors_kernel(BaBatch bt, MargArgs ma) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, nt = blockDim.x, K = bt.K, w = 0;
+  const int VD = 6 * K + 6 + bt.est_td;
+  if ((int)blockIdx.x == ma.G) {
+    double* sJ = sm;            // [450] raw
+    double* sJ2 = sJ + 450;     // [450] whitened
+    double* sR = sJ2 + 450;     // [15] raw, [15] whitened
+    double* out = ma.part + (size_t)ma.G * (VD * VD + VD);
+    const double* rec = bt.imu + (size_t)(w * K + 1) * IMU_REC;
+    const bool use = rec[IR_DT] < 10.0;
+    for (int i = tid; i < 450; i += nt) sJ[i] = 0.0;
+    __syncthreads();
+    if (use && tid == 0) imu_raw(rec, bt.G, bt.pose0, bt.sb0, bt.pose0 + 7, bt.sb0 + 9, sR, sJ);
+    __syncthreads();
+    if (use) {
+      const double* SI = rec + IR_SQ;
+      for (int e = tid; e < 465; e += nt) {
+        int i = e / 31, c = e - i * 31;
+        double s = 0;
+        if (c < 30) { for (int k = i; k < 15; k++) s += SI[i * 15 + k] * sJ[k * 30 + c]; sJ2[i * 30 + c] = s; }
+        else { for (int k = i; k < 15; k++) s += SI[i * 15 + k] * sR[k]; sR[15 + i] = s; }
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < 930; e += nt) {
+      double s = 0;
+      if (use) {
+        if (e < 900) { int a = e / 30, c = e - a * 30; for (int k = 0; k < 15; k++) s += sJ2[k * 30 + a] * sJ2[k * 30 + c]; }
+        else { int a = e - 900; for (int k = 0; k < 15; k++) s += sJ2[k * 30 + a] * sR[15 + k]; }
+      }
+      out[e] = s;
+    }
+    return;
+  }
+  double* sFr = sm;                                   // [K*FR]
+  double* sEx = sFr + K * FR;                         // [FR]
+  double* sF = sEx + FR;                              // [NB][16][MF]
+  double* sWv = sF + MARG_NB * 16 * MF;               // [NB][VD] w
+  double* sG = sWv + MARG_NB * VD;                    // [NB][VD] J^T r
+  double* sS = sG + MARG_NB * VD;                     // [NB][2] 1/h (thresholded), b
+  double* As = sS + 2 * MARG_NB;                      // [VD*VD]
+  double* gs = As + VD * VD;                          // [VD]
+  int* sFj = reinterpret_cast<int*>(gs + VD);         // [NB][16] frame of factor f
+  int* sFof = sFj + MARG_NB * 16;                     // [NB][16] frame -> factor index (-1: none)
+  int* sNf = sFof + MARG_NB * 16;                     // [NB] factors of the landmark
+  stage_frames(bt, w, bt.pose0, bt.ex, sFr, sEx);
+  for (int e = tid; e < VD * VD + VD; e += nt) As[e] = 0.0;
+  const int L0 = bt.lm_base[0];
+  const int NC = 18 + bt.est_td;                      // local columns of a factor
+  for (int base = blockIdx.x * MARG_NB; base < ma.n0; base += ma.G * MARG_NB) {
+    const int nb = min(MARG_NB, ma.n0 - base);
+    __syncthreads();
+    if (tid < MARG_NB * 16) sFof[tid] = -1;
+    __syncthreads();
+    if (tid < MARG_NB * 16) {
+      const int lb = tid >> 4, f = tid & 15;
+      if (lb < nb) {
+        const int l = L0 + base + lb, o0 = bt.lm_off[l], nfac = bt.lm_off[l + 1] - o0 - 1;
+        if (f == 0) sNf[lb] = nfac;
+        if (f < nfac) {
+          int fj;
+          marg_eval_factor(bt, w, l, o0, f, sFr, sEx, sF + (lb * 16 + f) * MF, &fj);
+          sFj[lb * 16 + f] = fj;
+          sFof[lb * 16 + fj] = f;
+        }
+      }
+    }
+    __syncthreads();
+    // w = sum_f J_f^T c_f, J^T r, h, b of every landmark of the batch
+    for (int it = tid; it < nb * (VD + 1); it += nt) {
+      const int lb = it / (VD + 1), d = it - lb * (VD + 1), nfac = sNf[lb];
+      const double* F = sF + lb * 16 * MF;
+      if (d < VD) {
+        double wsum = 0, gsum = 0;
+        for (int f = 0; f < nfac; f++) {
+          double j0, j1;
+          const double* st = F + f * MF;
+          marg_col(st, sFj[lb * 16 + f], K, d, j0, j1);
+          wsum += j0 * st[36] + j1 * st[37];
+          gsum += j0 * st[38] + j1 * st[39];
+        }
+        sWv[lb * VD + d] = wsum; sG[lb * VD + d] = gsum;
+      } else {
+        double h = 0, bb = 0;
+        for (int f = 0; f < nfac; f++) { const double* st = F + f * MF; h += st[36] * st[36] + st[37] * st[37]; bb += st[36] * st[38] + st[37] * st[39]; }
+        sS[2 * lb] = h > 1e-8 ? 1.0 / h : 0.0;       // eps of the reference's pseudo-inverse
+        sS[2 * lb + 1] = bb;
+      }
+    }
+    __syncthreads();
+    // dense part: the Schur term of the eliminated depths (single owner per entry)
+    for (int e = tid; e < VD * VD; e += nt) {
+      const int d1 = e / VD, d2 = e - d1 * VD;
+      double s = 0;
+      for (int lb = 0; lb < nb; lb++) s += sWv[lb * VD + d1] * sWv[lb * VD + d2] * sS[2 * lb];
+      As[e] -= s;
+    }
+    for (int d = tid; d < VD; d += nt) {
+      double s = 0;
+      for (int lb = 0; lb < nb; lb++) s += sG[lb * VD + d] - sWv[lb * VD + d] * sS[2 * lb + 1] * sS[2 * lb];
+      gs[d] += s;
+    }
+    // sparse part: sum_f J_f^T J_f.  (local a, local b) with both columns shared by all factors (frame 0, extrinsics, td):
+    // one owner sums over every factor; with a column of frame fj involved: one owner per (frame, a, b)
+    for (int it = tid; it < NC * NC; it += nt) {
+      const int a = it / NC, b2 = it - a * NC;
+      if ((a >= 6 && a < 12) || (b2 >= 6 && b2 < 12)) continue;
+      double s = 0;
+      for (int lb = 0; lb < nb; lb++)
+        for (int f = 0; f < sNf[lb]; f++) {
+          double a0, a1, b0, b1;
+          const double* st = sF + (lb * 16 + f) * MF;
+          marg_lcol(st, a, a0, a1); marg_lcol(st, b2, b0, b1);
+          s += a0 * b0 + a1 * b1;
+        }
+      As[marg_gcol(a, 0, K) * VD + marg_gcol(b2, 0, K)] += s;
+    }
+    for (int it = tid; it < (K - 1) * NC * NC; it += nt) {
+      const int p = 1 + it / (NC * NC), ab = it - (p - 1) * NC * NC, a = ab / NC, b2 = ab - a * NC;
+      if (!((a >= 6 && a < 12) || (b2 >= 6 && b2 < 12))) continue;
+      double s = 0;
+      for (int lb = 0; lb < nb; lb++) {
+        const int f = sFof[lb * 16 + p];
+        if (f < 0) continue;
+        double a0, a1, b0, b1;
+        const double* st = sF + (lb * 16 + f) * MF;
+        marg_lcol(st, a, a0, a1); marg_lcol(st, b2, b0, b1);
+        s += a0 * b0 + a1 * b1;
+      }
+      As[marg_gcol(a, p, K) * VD + marg_gcol(b2, p, K)] += s;
+    }
+  }
+  __syncthreads();
+  double* out = ma.part + (size_t)blockIdx.x * (VD * VD + VD);
+  for (int e = tid; e < VD * VD + VD; e += nt) out[e] = As[e];
+}
+
+// Jacobi rotation that annihilates a_pq: t = tan(theta) is the smaller root of t^2 + 2 t (aqq - app) / (2 apq) - 1 = 0,
+// written so that one square root, one division and one reciprocal square root are enough (the chain of dependent
+// FP64 operations is what a parallel-ordering step waits for); c^2 + s^2 = 1 to rounding.
+__device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, double& c, double& s) {
+  c = 1.0; s = 0.0;
+  if (apq == 0.0) return;
+  const double d = aqq - app, a2 = 2.0 * apq;
+  const double t = (d >= 0 ? a2 : -a2) / (fabs(d) + sqrt(d * d + a2 * a2));
+  c = rsqrt(t * t + 1.0);
+  s = t * c;
+}
+
+// in-warp Jacobi eigen-decomposition of a symmetric me x me matrix (me even, <= 16) in shared memory, parallel (round-robin)
+// ordering: me/2 disjoint rotations per step, no CTA barrier.  Am, Vm: [16*17].  Eigenvalues end up on the diagonal of Am.
+__device__ void warp_jacobi16(double* Am, double* Vm, int me, int lane) {
+  constexpr int LD = 17;
+  const int half = me / 2;
+  __shared__ int s_pq[16];
+  __shared__ double s_cs[16];
+  for (int sweep = 0; sweep < 30 && me >= 2; sweep++) {
+    double off = 0, dg = 0;
+    for (int e = lane; e < me * me; e += 32) {
+      const int i = e / me, j = e - i * me;
+      const double v = Am[i * LD + j] * Am[i * LD + j];
+      if (i == j) dg += v; else off += v;
+    }
+    off = warp_sum(off); dg = warp_sum(dg);
+    if (off <= 1e-30 * (dg + 1e-300)) break;
+    for (int step = 0; step < me - 1; step++) {
+      if (lane < half) {
+        int p, q;
+        if (lane == 0) { p = me - 1; q = step; }
+        else { p = (step + lane) % (me - 1); q = (step - lane + (me - 1)) % (me - 1); }
+        if (p > q) { int t2 = p; p = q; q = t2; }
+        double c, s;
+        jacobi_cs(Am[p * LD + p], Am[q * LD + q], Am[p * LD + q], c, s);
+        s_pq[2 * lane] = p; s_pq[2 * lane + 1] = q; s_cs[2 * lane] = c; s_cs[2 * lane + 1] = s;
+      }
+      __syncwarp();
+      for (int e = lane; e < half * half; e += 32) {
+        const int I = e / half, Jp = e - I * half;
+        const int p = s_pq[2 * I], q = s_pq[2 * I + 1], r = s_pq[2 * Jp], t2 = s_pq[2 * Jp + 1];
+        const double ci = s_cs[2 * I], si = s_cs[2 * I + 1], cj = s_cs[2 * Jp], sj = s_cs[2 * Jp + 1];
+        const double apr = Am[p * LD + r], apt = Am[p * LD + t2], aqr = Am[q * LD + r], aqt = Am[q * LD + t2];
+        const double bpr = ci * apr - si * aqr, bpt = ci * apt - si * aqt;
+        const double bqr = si * apr + ci * aqr, bqt = si * apt + ci * aqt;
+        Am[p * LD + r] = cj * bpr - sj * bpt; Am[p * LD + t2] = sj * bpr + cj * bpt;
+        Am[q * LD + r] = cj * bqr - sj * bqt; Am[q * LD + t2] = sj * bqr + cj * bqt;
+      }
+      for (int e = lane; e < half * me; e += 32) {
+        const int pr = e / me, k = e - pr * me;
+        const int p = s_pq[2 * pr], q = s_pq[2 * pr + 1];
+        const double c = s_cs[2 * pr], s2 = s_cs[2 * pr + 1];
+        const double vkp = Vm[k * LD + p], vkq = Vm[k * LD + q];
+        Vm[k * LD + p] = c * vkp - s2 * vkq; Vm[k * LD + q] = s2 * vkp + c * vkq;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- kernel 2: assembly, elimination of the dropped block, eigen-decomposition of the kept system (one CTA) -------------------
 __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch bt, MargArgs ma) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x, nt = blockDim.x, K = bt.K, M = ma.M, w = 0;
   const int VD = 6 * K + 6 + bt.est_td;     // visual layout dimension (frames, extrinsics, td when it is estimated)
   double* A = ma.A;
   double* bv = ma.b;
+  unsigned long long* phase = reinterpret_cast<unsigned long long*>(ma.status + 4);   // BVIO_DEBUG: where the time goes
+  if (tid == 0) phase[0] = global_ns();
   for (int i = tid; i < M * M; i += nt) A[i] = 0.0;
   for (int i = tid; i < M; i += nt) bv[i] = 0.0;
   __syncthreads();
   auto vmap = [&](int d) { return d < 6 * K ? 15 * (d / 6) + d % 6 : 15 * K + (d - 6 * K); };   // td: 15K + 6
 
   if (ma.flag == 0) {
-    // ---- visual factors of the landmarks anchored at frame 0 (estimator.cpp:852-893)
-    double* sFr = sm;                       // [K*FR]
-    double* sEx = sFr + K * FR;             // [FR]
-    double* sF = sEx + FR;                  // [(KMAX-1)*MF]
-    double* sWv = sF + (BVIO_KMAX - 1) * MF;  // [VD] w, then [VD] J^T r
-    double* sG = sWv + VD;
-    double* sS = sG + VD;                   // [2] h, b
-    int* sFj = reinterpret_cast<int*>(sS + 2);   // [KMAX]
-    int* sFof = sFj + BVIO_KMAX;                 // [KMAX+1] frame -> factor index of this landmark
-    stage_frames(bt, w, bt.pose0, bt.ex, sFr, sEx);
-    constexpr int NE = 12;                  // owned entries per thread: VD*VD <= 96*96 = 9216 <= 512*18
-    double acc[18];
-#pragma unroll
-    for (int u = 0; u < 18; u++) acc[u] = 0.0;
-    double gacc = 0.0;
-    (void)NE;
-    __syncthreads();
-    const int L0 = bt.lm_base[0], L1 = bt.lm_base[1];
-    for (int l = L0; l < L1; l++) {
-      const int o0 = bt.lm_off[l], n = bt.lm_off[l + 1] - o0, nfac = n - 1;
-      if (bt.obs_frame[o0] != 0) continue;
-      __syncthreads();
-      if (tid <= K) sFof[tid] = -1;
-      __syncthreads();
-      if (tid < nfac) {
-        const int fj = bt.obs_frame[o0 + 1 + tid];
-        sFof[fj] = tid;
-        double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[o0 + 1 + tid];
-        double2 vi = {0, 0}, vj = {0, 0};
-        if (bt.est_td) {   // ProjectionTdFactor: time-shifted points (projection_td_factor.cpp:51-52)
-          vi = bt.obs_vel[o0]; vj = bt.obs_vel[o0 + 1 + tid];
-          const double td = bt.td0[w], si_ = td + bt.obs_shift[o0], sj_ = td + bt.obs_shift[o0 + 1 + tid];
-          pi.x -= si_ * vi.x; pi.y -= si_ * vi.y; pj.x -= sj_ * vj.x; pj.y -= sj_ * vj.y;
-        }
-        const double lam = bt.invd0[l];
-        const double* Fi = sFr;
-        const double* Fj = sFr + fj * FR;
-        ProjGeom g = proj_geom(Fi, Fj, sEx, pi.x, pi.y, lam);
-        const double inv = 1.0 / g.pcj.z, si = bt.sqrt_info;
-        const double r0 = si * (g.pcj.x * inv - pj.x), r1 = si * (g.pcj.y * inv - pj.y);
-        const double red[2][3] = {{si * inv, 0.0, -si * g.pcj.x * inv * inv}, {0.0, si * inv, -si * g.pcj.y * inv * inv}};
-        double rho0, rho1;
-        cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
-        const double sr = sqrt(rho1);
-        double* st = sF + tid * MF;
-        const d3 tic{sEx[9], sEx[10], sEx[11]};
-        const d3 pci = (1.0 / lam) * d3{pi.x, pi.y, 1.0};
-        // tmp_r = ric^T Rj^T Ri ric ; tvec = ric^T (Rj^T (Ri tic + Pi - Pj) - tic)   (projection_factor.cpp:100-105)
-        double RjTRi[9], T1[9], tmp_r[9];
-        mtm3(Fj, Fi, RjTRi);
-        mtm3(sEx, RjTRi, T1);               // ric^T Rj^T Ri
-        mm3(T1, sEx, tmp_r);
-        const d3 inner = mtv3(Fj, mv3(Fi, tic) + d3{Fi[9], Fi[10], Fi[11]} - d3{Fj[9], Fj[10], Fj[11]}) - tic;
-        const d3 tvec = mtv3(sEx, inner);
-        const d3 trp = mv3(tmp_r, pci);
-        for (int a = 0; a < 2; a++) {
-          double Gm[3], Q[3];
-          for (int c = 0; c < 3; c++) Gm[c] = red[a][0] * sEx[c * 3 + 0] + red[a][1] * sEx[c * 3 + 1] + red[a][2] * sEx[c * 3 + 2];
-          for (int c = 0; c < 3; c++) Q[c] = Gm[0] * Fj[c * 3 + 0] + Gm[1] * Fj[c * 3 + 1] + Gm[2] * Fj[c * 3 + 2];
-          const d3 u = mtv3(Fi, d3{Q[0], Q[1], Q[2]});
-          const d3 jr = cross3(g.pimu_i, u);
-          const d3 jjr = cross3(d3{Gm[0], Gm[1], Gm[2]}, g.pimu_j);
-          st[a * 6 + 0] = sr * Q[0]; st[a * 6 + 1] = sr * Q[1]; st[a * 6 + 2] = sr * Q[2];
-          st[a * 6 + 3] = sr * jr.x; st[a * 6 + 4] = sr * jr.y; st[a * 6 + 5] = sr * jr.z;
-          st[12 + a * 6 + 0] = -sr * Q[0]; st[12 + a * 6 + 1] = -sr * Q[1]; st[12 + a * 6 + 2] = -sr * Q[2];
-          st[12 + a * 6 + 3] = sr * jjr.x; st[12 + a * 6 + 4] = sr * jjr.y; st[12 + a * 6 + 5] = sr * jjr.z;
-          // extrinsic block: reduce * [ ric^T (Rj^T Ri - I) | -tmp_r [pci]x + [tmp_r pci]x + [tvec]x ]
-          const double rd[3] = {red[a][0], red[a][1], red[a][2]};
-          double el[3];
-          for (int c = 0; c < 3; c++) {
-            double s = 0;
-            for (int k = 0; k < 3; k++) s += rd[k] * (T1[k * 3 + c] - sEx[c * 3 + k]);   // ric^T Rj^T Ri - ric^T
-            el[c] = s;
-          }
-          // row^T [v]x = (row x v)^T ;  row^T (-tmp_r [pci]x) = -((tmp_r^T row) x pci)^T
-          const d3 rowv{rd[0], rd[1], rd[2]};
-          const d3 t1 = mtv3(tmp_r, rowv);
-          const d3 e1 = cross3(t1, pci);
-          const d3 e2 = cross3(rowv, trp);
-          const d3 e3 = cross3(rowv, tvec);
-          st[24 + a * 6 + 0] = sr * el[0]; st[24 + a * 6 + 1] = sr * el[1]; st[24 + a * 6 + 2] = sr * el[2];
-          st[24 + a * 6 + 3] = sr * (-e1.x + e2.x + e3.x); st[24 + a * 6 + 4] = sr * (-e1.y + e2.y + e3.y);
-          st[24 + a * 6 + 5] = sr * (-e1.z + e2.z + e3.z);
-          st[36 + a] = sr * (-dot3(u, g.pimu_i - tic) / lam);
-          // td Jacobian (projection_td_factor.cpp:131-136); zero when td is not estimated
-          st[40 + a] = bt.est_td ? sr * (-dot3(u, mv3(sEx, d3{vi.x, vi.y, 0.0})) / lam + si * (a == 0 ? vj.x : vj.y)) : 0.0;
-        }
-        st[38] = sr * r0; st[39] = sr * r1;
-        sFj[tid] = fj;
-      }
-      __syncthreads();
-      if (tid < VD) {
-        double wsum = 0, gsum = 0;
-        for (int f = 0; f < nfac; f++) {
-          double j0, j1;
-          const double* st = sF + f * MF;
-          marg_col(st, sFj[f], K, tid, j0, j1);
-          wsum += j0 * st[36] + j1 * st[37];
-          gsum += j0 * st[38] + j1 * st[39];
-        }
-        sWv[tid] = wsum; sG[tid] = gsum;
-      } else if (tid == VD) {
-        double h = 0, bb = 0;
-        for (int f = 0; f < nfac; f++) { const double* st = sF + f * MF; h += st[36] * st[36] + st[37] * st[37]; bb += st[36] * st[38] + st[37] * st[39]; }
-        sS[0] = h; sS[1] = bb;
-      }
-      __syncthreads();
-      const double h = sS[0], bb = sS[1];
-      const double ih = h > 1e-8 ? 1.0 / h : 0.0;      // eps of the reference's pseudo-inverse
-#pragma unroll
-      for (int u = 0; u < 18; u++) {
-        const int e = tid + u * nt;
-        if (e >= VD * VD) break;
-        const int d1 = e / VD, d2 = e - d1 * VD;
-        double s = -sWv[d1] * sWv[d2] * ih;
-        // a frame-block dimension is touched by exactly one factor; pose-0 / extrinsic dimensions by all
-        const int k1 = d1 / 6, k2 = d2 / 6;
-        int f_lo = 0, f_hi = nfac;
-        if (k1 != 0 && k1 < K) { const int f = sFof[k1]; if (f < 0) f_hi = 0; else { f_lo = f; f_hi = f + 1; } }
-        if (k2 != 0 && k2 < K && f_hi > f_lo) {
-          const int f = sFof[k2];
-          if (f < 0 || (f_hi - f_lo == 1 && k1 != 0 && k1 < K && f != f_lo)) f_hi = f_lo;
-          else { f_lo = f; f_hi = f + 1; }
-        }
-        for (int f = f_lo; f < f_hi; f++) {
-          double a0, a1, b0, b1;
-          const double* st = sF + f * MF;
-          marg_col(st, sFj[f], K, d1, a0, a1);
-          marg_col(st, sFj[f], K, d2, b0, b1);
-          s += a0 * b0 + a1 * b1;
-        }
-        acc[u] += s;
-      }
-      if (tid < VD) gacc += sG[tid] - sWv[tid] * bb * ih;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 18; u++) {
-      const int e = tid + u * nt;
-      if (e >= VD * VD) break;
+    // ---- partial sums of the factor kernel, in a fixed order
+    const size_t PS = (size_t)VD * VD + VD;
+    for (int e = tid; e < VD * VD; e += nt) {
+      double s = 0;
+      for (int g = 0; g < ma.G; g++) s += ma.part[g * PS + e];
       const int d1 = e / VD, d2 = e - d1 * VD;
-      A[(size_t)vmap(d1) * M + vmap(d2)] = acc[u];
+      A[(size_t)vmap(d1) * M + vmap(d2)] = s;
     }
-    if (tid < VD) bv[vmap(tid)] = gacc;
+    for (int d = tid; d < VD; d += nt) {
+      double s = 0;
+      for (int g = 0; g < ma.G; g++) s += ma.part[g * PS + VD * VD + d];
+      bv[vmap(d)] = s;
+    }
     __syncthreads();
-    // ---- IMU factor 0 -> 1 (estimator.cpp:841-850)
-    {
-      double* sJ = sm;            // [450] raw
-      double* sJ2 = sJ + 450;     // [450] whitened
-      double* sR = sJ2 + 450;     // [15] raw, [15] whitened
-      const double* rec = bt.imu + (size_t)(w * K + 1) * IMU_REC;
-      const bool use = rec[IR_DT] < 10.0;
-      for (int i = tid; i < 450; i += nt) sJ[i] = 0.0;
-      __syncthreads();
-      if (use) {
-        if (tid == 0) imu_raw(rec, bt.G, bt.pose0, bt.sb0, bt.pose0 + 7, bt.sb0 + 9, sR, sJ);
-        __syncthreads();
-        const double* SI = rec + IR_SQ;
-        for (int e = tid; e < 465; e += nt) {
-          int i = e / 31, c = e - i * 31;
-          double s = 0;
-          if (c < 30) { for (int k = i; k < 15; k++) s += SI[i * 15 + k] * sJ[k * 30 + c]; sJ2[i * 30 + c] = s; }
-          else { for (int k = i; k < 15; k++) s += SI[i * 15 + k] * sR[k]; sR[15 + i] = s; }
-        }
-        __syncthreads();
-        for (int e = tid; e < 930; e += nt) {
-          double s = 0;
-          if (e < 900) {
-            int a = e / 30, c = e - a * 30;
-            for (int k = 0; k < 15; k++) s += sJ2[k * 30 + a] * sJ2[k * 30 + c];
-            A[(size_t)a * M + c] += s;
-          } else {
-            int a = e - 900;
-            for (int k = 0; k < 15; k++) s += sJ2[k * 30 + a] * sR[15 + k];
-            bv[a] += s;
-          }
-        }
-      }
-      __syncthreads();
+    const double* imu = ma.part + ma.G * PS;         // 30x30 J^T J, then J^T r of the IMU factor 0 -> 1
+    for (int e = tid; e < 930; e += nt) {
+      if (e < 900) { const int a = e / 30, c = e - a * 30; A[(size_t)a * M + c] += imu[e]; }
+      else bv[e - 900] += imu[e];
     }
+    __syncthreads();
   }
-  // ---- prior (estimator.cpp:822-839 / 932-948)
+  if (tid == 0) phase[1] = global_ns();
+  // ---- prior (estimator.cpp:822-839 / 932-948): J^T J comes from ba_prepare_kernel (pr_H), J^T r from the residual here
   {
     const int np_ = bt.pr_n[w];
     if (np_ > 0) {
@@ -2208,73 +2337,45 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       __syncthreads();
       prior_residual(bt, w, bt.pose0, bt.sb0, bt.ex, bt.td0, sdx, spr);
       const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
+      const double* Hp = bt.pr_H + (size_t)w * bt.nmax * bt.nmax;
       for (int e = tid; e < np_ * np_; e += nt) {
         int a = e / np_, c = e - a * np_;
         if (pmap[a] < 0 || pmap[c] < 0) continue;
-        double s = 0;
-        for (int k = 0; k < np_; k++) s += Jc[(size_t)a * np_ + k] * Jc[(size_t)c * np_ + k];
-        A[(size_t)pmap[a] * M + pmap[c]] += s;
+        A[(size_t)pmap[a] * M + pmap[c]] += Hp[(size_t)a * bt.nmax + c];
       }
-      for (int a = tid; a < np_; a += nt) {
+      // J^T r: one warp per column
+      for (int a = tid >> 5; a < np_; a += nt >> 5) {
         if (pmap[a] < 0) continue;
         double s = 0;
-        for (int k = 0; k < np_; k++) s += Jc[(size_t)a * np_ + k] * spr[k];
-        bv[pmap[a]] += s;
+        for (int k = tid & 31; k < np_; k += 32) s += Jc[(size_t)a * np_ + k] * spr[k];
+        s = warp_sum(s);
+        if ((tid & 31) == 0) bv[pmap[a]] += s;
       }
     }
     __syncthreads();
   }
+  if (tid == 0) phase[2] = global_ns();
   // ---- eliminate the m dropped dimensions: Amm pseudo-inverse by Jacobi eigen-decomposition (warp 0)
   const int m = ma.m, n = ma.n, ne = ma.ne;
-  double* Am = sm;                    // [16*16]
-  double* Vm = Am + 256;              // [16*16]
-  double* Ai = Vm + 256;              // [16*16] pseudo-inverse
+  double* Am = sm;                    // [16*17]
+  double* Vm = Am + 272;              // [16*17]
+  double* Ai = Vm + 272;              // [16*16] pseudo-inverse
   double* Tm = Ai + 256;              // [n*16]
+  const int me = (m + 1) & ~1;
   for (int e = tid; e < 256; e += nt) {
     int i = e >> 4, j = e & 15;
-    Am[e] = (i < m && j < m) ? 0.5 * (A[(size_t)ma.dropidx[i] * M + ma.dropidx[j]] + A[(size_t)ma.dropidx[j] * M + ma.dropidx[i]]) : 0.0;
-    Vm[e] = (i == j) ? 1.0 : 0.0;
+    Am[i * 17 + j] = (i < m && j < m) ? 0.5 * (A[(size_t)ma.dropidx[i] * M + ma.dropidx[j]] + A[(size_t)ma.dropidx[j] * M + ma.dropidx[i]]) : 0.0;
+    Vm[i * 17 + j] = (i == j) ? 1.0 : 0.0;
   }
   __syncthreads();
-  if (tid < 32) {
-    const int k = tid;
-    for (int sweep = 0; sweep < 60; sweep++) {
-      double off = 0;
-      for (int i = 0; i < m; i++) for (int j = i + 1; j < m; j++) off += Am[i * 16 + j] * Am[i * 16 + j];
-      if (off == 0.0) break;
-      double dg = 0;
-      for (int i = 0; i < m; i++) dg += Am[i * 16 + i] * Am[i * 16 + i];
-      if (off <= 1e-30 * (dg + 1e-300)) break;
-      for (int p = 0; p < m - 1; p++)
-        for (int q = p + 1; q < m; q++) {
-          const double apq = Am[p * 16 + q];
-          if (apq == 0.0) continue;
-          const double app = Am[p * 16 + p], aqq = Am[q * 16 + q];
-          const double theta = (aqq - app) / (2.0 * apq);
-          const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-          __syncwarp();
-          if (k < m) {
-            double akp = Am[k * 16 + p], akq = Am[k * 16 + q];
-            Am[k * 16 + p] = c * akp - s * akq; Am[k * 16 + q] = s * akp + c * akq;
-          }
-          __syncwarp();
-          if (k < m) {
-            double apk = Am[p * 16 + k], aqk = Am[q * 16 + k];
-            Am[p * 16 + k] = c * apk - s * aqk; Am[q * 16 + k] = s * apk + c * aqk;
-            double vkp = Vm[k * 16 + p], vkq = Vm[k * 16 + q];
-            Vm[k * 16 + p] = c * vkp - s * vkq; Vm[k * 16 + q] = s * vkp + c * vkq;
-          }
-          __syncwarp();
-        }
-    }
-  }
+  if (tid < 32) warp_jacobi16(Am, Vm, me, tid);
   __syncthreads();
+  if (tid == 0) phase[3] = global_ns();
   for (int e = tid; e < 256; e += nt) {
     int i = e >> 4, j = e & 15;
     double s = 0;
     if (i < m && j < m)
-      for (int k = 0; k < m; k++) { double lam = Am[k * 16 + k]; if (lam > 1e-8) s += Vm[i * 16 + k] * Vm[j * 16 + k] / lam; }
+      for (int k = 0; k < m; k++) { double lam = Am[k * 17 + k]; if (lam > 1e-8) s += Vm[i * 17 + k] * Vm[j * 17 + k] / lam; }
     Ai[e] = s;
   }
   __syncthreads();
@@ -2317,6 +2418,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
     if (i > j) { double v = 0.5 * (Ar[i * ld + j] + Ar[j * ld + i]); Ar[i * ld + j] = v; Ar[j * ld + i] = v; }
   }
   __syncthreads();
+  if (tid == 0) phase[4] = global_ns();
   if (ma.method == 1) {
     // ---- opt-in (BVIO_MARG_CHOLESKY=1; the default below is the reference's eigen-decomposition):
     //      (J, r) by diagonally pivoted Cholesky.  The reference factors A = V S V^T and keeps J = sqrt(S) V^T,
@@ -2376,17 +2478,40 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       for (int i = k + 1 + tid; i < n; i += nt) br[perm[i]] -= col[i] * rk;
       __syncthreads();
     }
-    if (tid == 0) { ma.status[0] = rank; ma.status[1] = (int)(100 * log10(minpiv)); ma.status[2] = (int)(100 * log10(maxpiv + 1e-300)); }
+    if (tid == 0) { ma.status[0] = rank; ma.status[1] = (int)(100 * log10(minpiv)); ma.status[2] = (int)(100 * log10(maxpiv + 1e-300)); phase[5] = phase[6] = global_ns(); }
     return;
   }
+  // Parallel (round-robin) two-sided Jacobi.  Work is assigned once: thread t < half (half+1)/2 owns the pair-of-pairs
+  // (I >= J) -- its 2x2 block of A and, by symmetry, the mirrored block -- and up to three (pair, row) items of V; per
+  // step: `half` threads pick the rotations, one barrier, everybody applies A <- J^T A J and V <- V J in place
+  // (single owner per element), one barrier.  Only the lower triangle of A is kept up to date (element (i, j) lives at
+  // row max(i,j), column min(i,j)): half the shared-memory stores of a full symmetric update.
   int sweeps = 0;
-  const int half = ne / 2;
+  const int half = ne / 2, nblk = half * (half + 1) / 2;
+  int2* pq = reinterpret_cast<int2*>(pp);       // [half] (p, q)
+  double2* rot = reinterpret_cast<double2*>(cs);   // [half] (c, s)
+  int bI = -1, bJ = -1;
+  if (tid < nblk) {
+    bI = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+    while (bI * (bI + 1) / 2 > tid) bI--;
+    while ((bI + 1) * (bI + 2) / 2 <= tid) bI++;
+    bJ = tid - bI * (bI + 1) / 2;
+  }
+  int vpr[3], vk[3];                            // this thread's (pair, row) items of V (half * ne <= 3 * 1024)
+#pragma unroll
+  for (int u = 0; u < 3; u++) {
+    const int e = tid + u * nt;
+    vpr[u] = e < half * ne ? e / ne : -1;
+    vk[u] = e < half * ne ? e - (e / ne) * ne : 0;
+  }
+  const bool v_more = half * ne > 3 * nt;       // (never for n <= 226; kept for safety)
   for (; sweeps < 40 && ne >= 2; sweeps++) {
     double off = 0, dg = 0;
     for (int e = tid; e < ne * ne; e += nt) {
       int i = e / ne, j = e - i * ne;
+      if (j > i) continue;
       double v = Ar[i * ld + j] * Ar[i * ld + j];
-      if (i == j) dg += v; else off += v;
+      if (i == j) dg += v; else off += 2.0 * v;
     }
     off = block_sum(off, red);
     dg = block_sum(dg, red);
@@ -2397,43 +2522,53 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       if (tid < half) {
         int p, q;
         if (tid == 0) { p = ne - 1; q = step; }
-        else { p = (step + tid) % (ne - 1); q = (step - tid + (ne - 1)) % (ne - 1); }
-        if (p > q) { int t2 = p; p = q; q = t2; }
-        const double apq = Ar[p * ld + q];
-        double c = 1.0, s = 0.0;
-        if (apq != 0.0) {
-          const double app = Ar[p * ld + p], aqq = Ar[q * ld + q];
-          const double theta = (aqq - app) / (2.0 * apq);
-          const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          c = 1.0 / sqrt(tt * tt + 1.0); s = tt * c;
+        else {
+          p = step + tid; if (p >= ne - 1) p -= ne - 1;
+          q = step - tid; if (q < 0) q += ne - 1;
         }
-        pp[2 * tid] = p; pp[2 * tid + 1] = q; cs[2 * tid] = c; cs[2 * tid + 1] = s;
+        if (p > q) { int t2 = p; p = q; q = t2; }
+        double c, s;
+        jacobi_cs(Ar[p * ld + p], Ar[q * ld + q], Ar[q * ld + p], c, s);
+        pq[tid] = make_int2(p, q); rot[tid] = make_double2(c, s);
       }
       __syncthreads();
-      // A <- J^T A J in one phase: the 2x2 block of A at (pair I, pair J) only needs the two rotations, so every block has
-      // a single owner and is updated in place; V <- V J alongside (columns of V, one (pair, row) per thread)
-      for (int e = tid; e < half * half; e += nt) {
-        const int I = e / half, Jp = e - I * half;
-        const int p = pp[2 * I], q = pp[2 * I + 1], r = pp[2 * Jp], t2 = pp[2 * Jp + 1];
-        const double ci = cs[2 * I], si = cs[2 * I + 1], cj = cs[2 * Jp], sj = cs[2 * Jp + 1];
-        const double apr = Ar[p * ld + r], apt = Ar[p * ld + t2], aqr = Ar[q * ld + r], aqt = Ar[q * ld + t2];
-        // rows: [p'; q'] = [c -s; s c] [p; q]   (same convention as the two-pass version)
-        const double bpr = ci * apr - si * aqr, bpt = ci * apt - si * aqt;
-        const double bqr = si * apr + ci * aqr, bqt = si * apt + ci * aqt;
+      if (bI >= 0) {
+        const int2 a = pq[bI], b2 = pq[bJ];
+        const double2 ri = rot[bI], rj = rot[bJ];
+        const int p = a.x, q = a.y, r = b2.x, t2 = b2.y;
+        // lower-triangle addresses; on the diagonal block (I == J: r = p, t2 = q) both (p,q) and (q,p) name one element
+        const int ipr = p >= r ? p * ld + r : r * ld + p, ipt = p >= t2 ? p * ld + t2 : t2 * ld + p;
+        const int iqr = q >= r ? q * ld + r : r * ld + q, iqt = q >= t2 ? q * ld + t2 : t2 * ld + q;
+        const double apr = Ar[ipr], apt = Ar[ipt], aqr = Ar[iqr], aqt = Ar[iqt];
+        // rows: [p'; q'] = [c -s; s c] [p; q]
+        const double bpr = ri.x * apr - ri.y * aqr, bpt = ri.x * apt - ri.y * aqt;
+        const double bqr = ri.y * apr + ri.x * aqr, bqt = ri.y * apt + ri.x * aqt;
         // columns: [r' t'] = [r t] [c s; -s c]
-        Ar[p * ld + r] = cj * bpr - sj * bpt; Ar[p * ld + t2] = sj * bpr + cj * bpt;
-        Ar[q * ld + r] = cj * bqr - sj * bqt; Ar[q * ld + t2] = sj * bqr + cj * bqt;
+        const double npr = rj.x * bpr - rj.y * bpt, npt = rj.y * bpr + rj.x * bpt, nqr = rj.x * bqr - rj.y * bqt, nqt = rj.y * bqr + rj.x * bqt;
+        Ar[ipr] = npr; Ar[iqt] = nqt; Ar[iqr] = nqr;
+        if (bI != bJ) Ar[ipt] = npt;                 // (diagonal block: ipt == iqr, the same element, npt == nqr up to rounding)
       }
-      for (int e = tid; e < half * ne; e += nt) {
-        int pr = e / ne, k = e - pr * ne;
-        int p = pp[2 * pr], q = pp[2 * pr + 1];
-        double c = cs[2 * pr], s2 = cs[2 * pr + 1];
-        double vkp = Vr[k * ld + p], vkq = Vr[k * ld + q];
-        Vr[k * ld + p] = c * vkp - s2 * vkq; Vr[k * ld + q] = s2 * vkp + c * vkq;
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        if (vpr[u] < 0) continue;
+        const int2 a = pq[vpr[u]];
+        const double2 r = rot[vpr[u]];
+        double* row = Vr + vk[u] * ld;
+        const double vkp = row[a.x], vkq = row[a.y];
+        row[a.x] = r.x * vkp - r.y * vkq; row[a.y] = r.y * vkp + r.x * vkq;
       }
+      if (v_more)
+        for (int e = tid + 3 * nt; e < half * ne; e += nt) {
+          const int pr = e / ne, k = e - pr * ne;
+          const int2 a = pq[pr];
+          const double2 r = rot[pr];
+          const double vkp = Vr[k * ld + a.x], vkq = Vr[k * ld + a.y];
+          Vr[k * ld + a.x] = r.x * vkp - r.y * vkq; Vr[k * ld + a.y] = r.y * vkp + r.x * vkq;
+        }
       __syncthreads();
     }
   }
+  if (tid == 0) phase[5] = global_ns();
   // ---- linearized_jacobians = sqrt(S) V^T, linearized_residuals = sqrt(S^-1) V^T b  (:283-291)
   for (int e = tid; e < n * n; e += nt) {
     int i = e / n, k = e - i * n;       // column-major J(k, i) at [i*n + k]
@@ -2445,31 +2580,46 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
     for (int i = 0; i < n; i++) s += Vr[i * ld + k] * br[i];
     ma.out_res[k] = (lam > 1e-8 ? sqrt(1.0 / lam) : 0.0) * s;
   }
-  if (tid == 0) ma.status[0] = sweeps;
+  if (tid == 0) { ma.status[0] = sweeps; phase[6] = global_ns(); }
 }
 
+cudaError_t ba_configure_marginalize(void) {
+  cudaError_t e = cudaFuncSetAttribute(ba_marginalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ba_marg_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  return e;
+}
 size_t ba_marginalize_smem_bytes(int K, int nmax, int n) {
-  int ne = (n + 1) & ~1, VD = 6 * K + 7;
-  size_t a = (size_t)(K + 1) * FR + (BVIO_KMAX - 1) * MF + 2 * VD + 2 + 2 * BVIO_KMAX;   // visual phase
-  size_t b = 930 + 32;                                                                    // IMU phase
+  int ne = (n + 1) & ~1;
   size_t c = 2 * (size_t)nmax + nmax / 2 + 2;                                             // prior phase
-  size_t d = 768 + (size_t)n * 16 + 2 * (size_t)ne * (ne + 1) + 2 * ne + ne / 2 + 2 + 32 + 8;   // elimination + Jacobi
-  size_t mx = a > b ? a : b;
-  if (c > mx) mx = c;
-  if (d > mx) mx = d;
-  return mx * sizeof(double);
+  size_t d = 800 + (size_t)n * 16 + 2 * (size_t)ne * (ne + 1) + 2 * ne + ne / 2 + 2 + 32 + 8;   // elimination + Jacobi
+  return (c > d ? c : d) * sizeof(double);
 }
+static size_t marg_factors_smem_bytes(int K) {
+  const int VD = 6 * K + 7;
+  size_t d = (size_t)(K + 1) * FR + MARG_NB * 16 * MF + 2 * MARG_NB * VD + 2 * MARG_NB + (size_t)VD * VD + VD;
+  size_t imu = 930 + 32;
+  return (d > imu ? d : imu) * sizeof(double) + sizeof(int) * (2 * MARG_NB * 16 + MARG_NB + 4);
+}
+size_t ba_marginalize_part_doubles(int K, int G) {
+  const int VD = 6 * K + 7;
+  return (size_t)G * ((size_t)VD * VD + VD) + 930;
+}
+int ba_marginalize_groups(int n0) { int g = (n0 + MARG_NB - 1) / MARG_NB; return g < 1 ? 1 : (g > 24 ? 24 : g); }
 
-int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, const int* dropidx, const int* keepidx, double* A,
-                          double* b, double* out_jac, double* out_res, int* status, int method, cudaStream_t st) {
+int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, int n0, const int* dropidx, const int* keepidx, double* A,
+                          double* b, double* part, double* out_jac, double* out_res, int* status, int method, cudaStream_t st) {
   MargArgs ma;
   ma.method = method;
   ma.flag = flag; ma.M = 15 * bt.K + 7; ma.m = m; ma.n = n; ma.ne = (n + 1) & ~1;
+  ma.n0 = n0; ma.G = ba_marginalize_groups(n0); ma.part = part;
   ma.dropidx = dropidx; ma.keepidx = keepidx; ma.A = A; ma.b = b; ma.out_jac = out_jac; ma.out_res = out_res; ma.status = status;
-  size_t smem = ba_marginalize_smem_bytes(bt.K, bt.nmax, n);
-  cudaFuncSetAttribute(ba_marginalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  ba_marginalize_kernel<<<1, MARG_THREADS, smem, st>>>(bt, ma);
-  return 1;
+  int launches = 1;
+  if (flag == 0) {
+    ba_marg_factors_kernel<<<ma.G + 1, MARG_FT, marg_factors_smem_bytes(bt.K), st>>>(bt, ma);
+    launches++;
+  }
+  ba_marginalize_kernel<<<1, MARG_THREADS, ba_marginalize_smem_bytes(bt.K, bt.nmax, n), st>>>(bt, ma);
+  return launches;
 }
 
 }  // namespace bvio
