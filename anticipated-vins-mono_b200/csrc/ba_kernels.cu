@@ -2220,16 +2220,19 @@ __global__ void __launch_bounds__(MARG_FT) ba_marg_factors_kernel(BaBatch bt, Ma
   for (int e = tid; e < VD * VD + VD; e += nt) out[e] = As[e];
 }
 
-// Jacobi rotation that annihilates a_pq: t = tan(theta) is the smaller root of t^2 + 2 t (aqq - app) / (2 apq) - 1 = 0,
-// written so that one square root, one division and one reciprocal square root are enough (the chain of dependent
-// FP64 operations is what a parallel-ordering step waits for); c^2 + s^2 = 1 to rounding.
+// Jacobi rotation that annihilates a_pq
 __device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, double& c, double& s) {
   c = 1.0; s = 0.0;
   if (apq == 0.0) return;
+  // with d = aqq - app, a2 = 2 apq, h = hypot(d, a2):  cos(2 theta) = |d| / h,  c = sqrt((1 + |d|/h) / 2),
+  // s = sign(d) a2 / (2 h c) -- the smaller rotation.  Two reciprocal square roots, no division: this chain of dependent
+  // FP64 operations is what every parallel-ordering step waits for.  c^2 + s^2 = 1 to rounding.
   const double d = aqq - app, a2 = 2.0 * apq;
-  const double t = (d >= 0 ? a2 : -a2) / (fabs(d) + sqrt(d * d + a2 * a2));
-  c = rsqrt(t * t + 1.0);
-  s = t * c;
+  const double r = rsqrt(d * d + a2 * a2);         // 1 / h
+  const double u = fma(0.5 * fabs(d), r, 0.5);     // (1 + |d| / h) / 2  in [1/2, 1]
+  const double rc = rsqrt(u);
+  c = u * rc;
+  s = (d >= 0 ? 0.5 : -0.5) * a2 * r * rc;
 }
 
 // in-warp Jacobi eigen-decomposition of a symmetric me x me matrix (me even, <= 16) in shared memory, parallel (round-robin)
@@ -2491,20 +2494,22 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
   int2* pq = reinterpret_cast<int2*>(pp);       // [half] (p, q)
   double2* rot = reinterpret_cast<double2*>(cs);   // [half] (c, s)
   int bI = -1, bJ = -1;
+  const bool blk_more = nblk > nt;              // more pair-of-pairs than threads (n > ~88): the rest in a loop
   if (tid < nblk) {
     bI = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
     while (bI * (bI + 1) / 2 > tid) bI--;
     while ((bI + 1) * (bI + 2) / 2 <= tid) bI++;
     bJ = tid - bI * (bI + 1) / 2;
   }
-  int vpr[3], vk[3];                            // this thread's (pair, row) items of V (half * ne <= 3 * 1024)
+  constexpr int VI = 4;
+  int vpr[VI], vk[VI];                          // this thread's (pair, row) items of V
 #pragma unroll
-  for (int u = 0; u < 3; u++) {
+  for (int u = 0; u < VI; u++) {
     const int e = tid + u * nt;
     vpr[u] = e < half * ne ? e / ne : -1;
     vk[u] = e < half * ne ? e - (e / ne) * ne : 0;
   }
-  const bool v_more = half * ne > 3 * nt;       // (never for n <= 226; kept for safety)
+  const bool v_more = half * ne > VI * nt;
   for (; sweeps < 40 && ne >= 2; sweeps++) {
     double off = 0, dg = 0;
     for (int e = tid; e < ne * ne; e += nt) {
@@ -2532,9 +2537,15 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         pq[tid] = make_int2(p, q); rot[tid] = make_double2(c, s);
       }
       __syncthreads();
-      if (bI >= 0) {
-        const int2 a = pq[bI], b2 = pq[bJ];
-        const double2 ri = rot[bI], rj = rot[bJ];
+      for (int e = tid, I = bI, Jb = bJ; e < nblk; e += nt) {
+        if (e != tid) {                              // only when there are more pair-of-pairs than threads (n > ~88)
+          I = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+          while (I * (I + 1) / 2 > e) I--;
+          while ((I + 1) * (I + 2) / 2 <= e) I++;
+          Jb = e - I * (I + 1) / 2;
+        }
+        const int2 a = pq[I], b2 = pq[Jb];
+        const double2 ri = rot[I], rj = rot[Jb];
         const int p = a.x, q = a.y, r = b2.x, t2 = b2.y;
         // lower-triangle addresses; on the diagonal block (I == J: r = p, t2 = q) both (p,q) and (q,p) name one element
         const int ipr = p >= r ? p * ld + r : r * ld + p, ipt = p >= t2 ? p * ld + t2 : t2 * ld + p;
@@ -2546,10 +2557,11 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         // columns: [r' t'] = [r t] [c s; -s c]
         const double npr = rj.x * bpr - rj.y * bpt, npt = rj.y * bpr + rj.x * bpt, nqr = rj.x * bqr - rj.y * bqt, nqt = rj.y * bqr + rj.x * bqt;
         Ar[ipr] = npr; Ar[iqt] = nqt; Ar[iqr] = nqr;
-        if (bI != bJ) Ar[ipt] = npt;                 // (diagonal block: ipt == iqr, the same element, npt == nqr up to rounding)
+        if (I != Jb) Ar[ipt] = npt;                  // (diagonal block: ipt == iqr, the same element, npt == nqr up to rounding)
+        if (!blk_more) break;
       }
 #pragma unroll
-      for (int u = 0; u < 3; u++) {
+      for (int u = 0; u < VI; u++) {
         if (vpr[u] < 0) continue;
         const int2 a = pq[vpr[u]];
         const double2 r = rot[vpr[u]];
@@ -2558,7 +2570,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         row[a.x] = r.x * vkp - r.y * vkq; row[a.y] = r.y * vkp + r.x * vkq;
       }
       if (v_more)
-        for (int e = tid + 3 * nt; e < half * ne; e += nt) {
+        for (int e = tid + VI * nt; e < half * ne; e += nt) {
           const int pr = e / ne, k = e - pr * ne;
           const int2 a = pq[pr];
           const double2 r = rot[pr];
