@@ -43,6 +43,7 @@ struct BaCtrl {                   // per-window LM state, lives in HBM
   double ca, cb;                  // step = ca * (scaled gradient direction t) + cb * (Gauss-Newton step)
   double step_norm;               // |step| in Ceres' diagonally scaled space (drives the radius update)
   unsigned long long t0_ns;       // %globaltimer at the reset of this solve (max_solver_time_in_seconds cut)
+  unsigned long long stamps[6];   // BVIO_DEBUG: phase time stamps of the last ba_solve pass (assembly, vectors, factor, ...)
 };
 
 // per-(window,tile) output record of ba_linearize, in doubles:
@@ -102,6 +103,9 @@ struct BaBatch {                  // all pointers are device pointers
   double* pr_H;                   // [B][nmax*nmax] J^T J (symmetric)
   int* pr_map;                    // [B][nmax] prior column -> reduced state index (-1: constant block)
   double* pr_out;                 // [B][nmax+1] J^T r at X[cur], then 0.5 |r|^2
+  double* S0;                     // [B][(np+1)(np+2)/2] latency mode only (else null): the prior's J^T J already scattered
+                                  // into the packed lower reduced layout -- ba_solve starts from it instead of from zero
+  int* pr_inv;                    // [B][np] reduced state index -> prior column (-1: none)
   // linearization products
   double* h; double* b; double* sl2;   // [total_L]
   double* w;                      // [total_obs][6]

@@ -275,6 +275,9 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   size_t o_imu = cv.take((size_t)B * K * IMU_REC * D), o_imu_out = cv.take((size_t)B * K * IMU_OUT * D);
   size_t o_pr_H = cv.take((size_t)B * nmax * nmax * D), o_pr_map = cv.take((size_t)B * nmax * I);
   size_t o_pr_out = cv.take((size_t)B * (nmax + 1) * D);
+  size_t o_pr_inv = cv.take((size_t)B * bt.np * I);
+  const size_t s0_len = (size_t)(bt.np + 1) * (bt.np + 2) / 2;
+  size_t o_S0 = bt.solve_wide ? cv.take((size_t)B * s0_len * D) : 0;
   size_t o_h = cv.take((size_t)total_L * D), o_b = cv.take((size_t)total_L * D), o_sl2 = cv.take((size_t)total_L * D);
   size_t o_w = cv.take((size_t)total_obs * 6 * D);
   size_t o_tile = cv.take((size_t)B * T * tile_rec_doubles(KE) * D);
@@ -446,6 +449,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   }
   bt.imu = (double*)(d + o_imu); bt.imu_out = (double*)(d + o_imu_out);
   bt.pr_H = (double*)(d + o_pr_H); bt.pr_map = (int*)(d + o_pr_map); bt.pr_out = (double*)(d + o_pr_out);
+  bt.pr_inv = (int*)(d + o_pr_inv); bt.S0 = bt.solve_wide ? (double*)(d + o_S0) : nullptr;
   bt.h = (double*)(d + o_h); bt.b = (double*)(d + o_b); bt.sl2 = (double*)(d + o_sl2); bt.w = (double*)(d + o_w);
   bt.tile_out = (double*)(d + o_tile); bt.cost_out = (double*)(d + o_cost);
   bt.delta_p = (double*)(d + o_dp); bt.scale_p = (double*)(d + o_sp); bt.solve_vec = (double*)(d + o_svec);
@@ -532,6 +536,11 @@ static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, b
   const double* exo = (const double*)(bb->slab.h + bb->o_ex_out);
   const double* tdo = (const double*)(bb->slab.h + bb->o_td_out);
   const BaCtrl* ctrl = (const BaCtrl*)(bb->slab.h + bb->o_ctrl);
+  if (bt.B == 1 && getenv("BVIO_DEBUG")) {
+    const unsigned long long* t = ctrl[0].stamps;
+    fprintf(stderr, "[bvio] last ba_solve pass, us: assemble %.1f vectors+dogleg-pre %.1f cholesky %.1f back-subst %.1f step %.1f | solve device total %.3f ms\n",
+            (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3, ms);
+  }
   int rc = BVIO_OK;
   auto scatter = [&](int b) {
       bvio_window& w = windows[b];
@@ -802,9 +811,10 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* op
     memset(&dbg, 0, sizeof dbg);
     cudaMemcpy(&dbg, scratch + o_st, sizeof dbg, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[bvio] marginalize: m=%d n=%d sweeps/rank=%d log10 pivots min %.2f max %.2f | us: factors %.1f prior %.1f drop-eig %.1f "
-            "schur %.1f kept-eig %.1f out %.1f total %.1f\n", m, n, dbg.stv[0], dbg.stv[1] / 100.0, dbg.stv[2] / 100.0,
+            "schur %.1f kept-eig %.1f (SM clock %.0f MHz) out %.1f total %.1f\n", m, n, dbg.stv[0], dbg.stv[1] / 100.0, dbg.stv[2] / 100.0,
             (dbg.ph[1] - dbg.ph[0]) * 1e-3, (dbg.ph[2] - dbg.ph[1]) * 1e-3, (dbg.ph[3] - dbg.ph[2]) * 1e-3, (dbg.ph[4] - dbg.ph[3]) * 1e-3,
-            (dbg.ph[5] - dbg.ph[4]) * 1e-3, (dbg.ph[6] - dbg.ph[5]) * 1e-3, (dbg.ph[6] - dbg.ph[0]) * 1e-3);
+            (dbg.ph[5] - dbg.ph[4]) * 1e-3, (double)dbg.ph[7] / ((dbg.ph[5] - dbg.ph[4]) * 1e-3 + 1e-9),
+            (dbg.ph[6] - dbg.ph[5]) * 1e-3, (dbg.ph[6] - dbg.ph[0]) * 1e-3);
   }
   bvio_batch_free(ctx, bb);
   if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("marginalize: ") + cudaGetErrorString(e));

@@ -305,6 +305,23 @@ __global__ void __launch_bounds__(BA_THREADS) ba_prepare_kernel(BaBatch bt) {
     for (int k = 0; k < n; k++) s += Jc[(size_t)a * n + k] * Jc[(size_t)b2 * n + k];
     H[(size_t)a * bt.nmax + b2] = s;
   }
+  // reduced index -> prior column, and (latency mode) the prior Hessian scattered once into ba_solve's packed layout
+  int* inv = bt.pr_inv + (size_t)w * bt.np;
+  for (int i = threadIdx.x; i < bt.np; i += blockDim.x) inv[i] = -1;
+  __syncthreads();
+  for (int a = threadIdx.x; a < n; a += blockDim.x) if (map[a] >= 0) inv[map[a]] = a;
+  if (bt.S0) {
+    const int N1 = bt.np + 1;
+    double* S0 = bt.S0 + (size_t)w * (N1 * (N1 + 1) / 2);
+    for (int i = threadIdx.x; i < N1 * (N1 + 1) / 2; i += blockDim.x) S0[i] = 0.0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      int a = e / n, b2 = e - a * n;
+      int ra = map[a], rb = map[b2];
+      if (ra < 0 || rb < 0 || ra < rb) continue;
+      S0[tri(ra, rb)] = H[(size_t)a * bt.nmax + b2];
+    }
+  }
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -349,7 +366,9 @@ __global__ void ba_finish_kernel(BaBatch bt) {
 // =============================================================================================
 // linearize: visual tiles (blockIdx.x < T) + IMU/prior CTA (blockIdx.x == T)
 // =============================================================================================
-__device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* sm) {
+// f0 .. f1: which IMU factors (0-based: factor f links frame f to f + 1) this CTA evaluates; do_prior: also the prior.
+// One CTA does everything for large batches; with fewer windows than SMs (latency mode) every factor gets its own CTA.
+__device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* sm, int f0, int f1, bool do_prior) {
   const int K = bt.K, nf = K - 1;
   double* sJ = sm;                      // [nf][450] raw Jacobians
   double* sJ2 = sJ + nf * 450;          // [nf][450] whitened
@@ -359,10 +378,11 @@ __device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* s
   double* spr = sdx + bt.nmax;          // [nmax]
   const double* pose = bt.pose[cur];
   const double* sb = bt.sb[cur];
-  for (int i = threadIdx.x; i < nf * 450; i += blockDim.x) sJ[i] = 0.0;
+  const int nfl = f1 - f0;
+  for (int i = threadIdx.x; i < nfl * 450; i += blockDim.x) sJ[f0 * 450 + i] = 0.0;
   __syncthreads();
-  if (threadIdx.x < nf) {
-    int f = threadIdx.x, j = f + 1;
+  if ((int)threadIdx.x < nfl) {
+    int f = f0 + threadIdx.x, j = f + 1;
     const double* rec = bt.imu + (size_t)(w * K + j) * IMU_REC;
     if (!(rec[IR_DT] > 10.0))
       imu_raw(rec, bt.G, pose + (size_t)(w * K + j - 1) * 7, sb + (size_t)(w * K + j - 1) * 9,
@@ -372,8 +392,8 @@ __device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* s
   }
   __syncthreads();
   // whiten: J2 = SI * J, r2 = SI * r (SI upper triangular)
-  for (int e = threadIdx.x; e < nf * 465; e += blockDim.x) {
-    int f = e / 465, o = e - f * 465;
+  for (int e = threadIdx.x; e < nfl * 465; e += blockDim.x) {
+    int f = f0 + e / 465, o = e - (e / 465) * 465;
     const double* SI = bt.imu + (size_t)(w * K + f + 1) * IMU_REC + IR_SQ;
     int i = o / 31, c = o - i * 31;
     double s = 0;
@@ -386,8 +406,8 @@ __device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* s
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < nf * IMU_OUT; e += blockDim.x) {
-    int f = e / IMU_OUT, o = e - f * IMU_OUT;
+  for (int e = threadIdx.x; e < nfl * IMU_OUT; e += blockDim.x) {
+    int f = f0 + e / IMU_OUT, o = e - (e / IMU_OUT) * IMU_OUT;
     const double* J = sJ2 + f * 450;
     const double* r = sR2 + f * 15;
     double s = 0;
@@ -403,6 +423,7 @@ __device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* s
     }
     bt.imu_out[(size_t)(w * K + f + 1) * IMU_OUT + o] = s;
   }
+  if (!do_prior) return;
   // prior
   int n = bt.pr_n[w];
   double* po = bt.pr_out + (size_t)w * (bt.nmax + 1);
@@ -442,7 +463,12 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   BaCtrl* ctrl = bt.ctrl + w;
   if (ctrl->done) return;
   const int cur = ctrl->cur;
-  if (t == bt.T) { imu_prior_linearize(bt, w, cur, sm); return; }
+  if (t >= bt.T) {   // IMU / prior CTAs: one for all, or (latency mode) the prior CTA followed by one CTA per IMU factor
+    if (gridDim.x == (unsigned)bt.T + 1) imu_prior_linearize(bt, w, cur, sm, 0, bt.K - 1, true);
+    else if (t == bt.T) imu_prior_linearize(bt, w, cur, sm, 0, 0, true);
+    else imu_prior_linearize(bt, w, cur, sm, t - bt.T - 1, t - bt.T, false);
+    return;
+  }
 
   constexpr int SG = STG + 12 * XB;                   // per-factor staging stride (29 / 41 / 53: odd)
   constexpr int NRED = 35 + 69 * XB + (XB == 2 ? 36 : 0);   // per-landmark reductions over the factors
@@ -823,7 +849,12 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
   BaCtrl* ctrl = bt.ctrl + w;
   if (ctrl->done) return;
   const int cur = ctrl->cur;
-  if (t == bt.T) { imu_prior_linearize(bt, w, cur, sm); return; }
+  if (t >= bt.T) {   // IMU / prior CTAs: one for all, or (latency mode) the prior CTA followed by one CTA per IMU factor
+    if (gridDim.x == (unsigned)bt.T + 1) imu_prior_linearize(bt, w, cur, sm, 0, bt.K - 1, true);
+    else if (t == bt.T) imu_prior_linearize(bt, w, cur, sm, 0, 0, true);
+    else imu_prior_linearize(bt, w, cur, sm, t - bt.T - 1, t - bt.T, false);
+    return;
+  }
 
   const int K = bt.K, K6 = 6 * K, NPb = K * (K + 1) / 2, NT = mm_ntile(K), WS = WSC ? WSC : mm_wstride(K);
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, g = lane >> 2, tq = lane & 3;
@@ -1162,7 +1193,10 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
   const double* pH = bt.pr_H + (size_t)w * bt.nmax * bt.nmax;
   const double* po = bt.pr_out + (size_t)w * (bt.nmax + 1);
 
-  for (int i = tid; i < N1 * (N1 + 1) / 2; i += nthr) S[i] = 0.0;
+  if (tid == 0) ctrl->stamps[0] = global_ns();
+  const double* S0 = bt.S0 ? bt.S0 + (size_t)w * (N1 * (N1 + 1) / 2) : nullptr;
+  if (S0) for (int i = tid; i < N1 * (N1 + 1) / 2; i += nthr) S[i] = S0[i];     // prior already in place
+  else for (int i = tid; i < N1 * (N1 + 1) / 2; i += nthr) S[i] = 0.0;
   if (tid == 0) s_fail = 0;
   __syncthreads();
   // visual blocks
@@ -1174,7 +1208,7 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
     if (p == q && c > r) continue;
     const int ri = vis2red(bt, p, r), ci = vis2red(bt, q, c);
     if (ri < 0 || ci < 0) continue;
-    S[tri(ri, ci)] = s;
+    S[tri(ri, ci)] += s;
   }
   __syncthreads();
   // IMU blocks: odd then even factors (consecutive factors overlap on one frame block)
@@ -1187,13 +1221,15 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
     }
     __syncthreads();
   }
-  // prior
-  for (int e = tid; e < n * n; e += nthr) {
-    int a = e / n, b2 = e - a * n;
-    int ra = map[a], rb = map[b2];
-    if (ra < 0 || rb < 0 || ra < rb) continue;
-    S[tri(ra, rb)] += pH[(size_t)a * bt.nmax + b2];
-  }
+  // prior (already in S0 in latency mode)
+  if (!S0)
+    for (int e = tid; e < n * n; e += nthr) {
+      int a = e / n, b2 = e - a * n;
+      int ra = map[a], rb = map[b2];
+      if (ra < 0 || rb < 0 || ra < rb) continue;
+      S[tri(ra, rb)] += pH[(size_t)a * bt.nmax + b2];
+    }
+  const int* inv = bt.pr_inv + (size_t)w * np;
   // vectors
   for (int i = tid; i < np; i += nthr) {
     int p = i / 15, r = i - p * 15;
@@ -1207,11 +1243,11 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
     }
     if (p + 1 < K) { const double* o = imo + (size_t)(p + 1) * IMU_OUT; g1 += o[465 + r]; g2 += o[465 + r]; d += o[tri(r, r)]; }
     if (p >= 1 && p < K) { const double* o = imo + (size_t)p * IMU_OUT; g1 += o[465 + 15 + r]; g2 += o[465 + 15 + r]; d += o[tri(15 + r, 15 + r)]; }
-    for (int a = 0; a < n; a++)
-      if (map[a] == i) { g1 += po[a]; g2 += po[a]; d += pH[(size_t)a * bt.nmax + a]; }
+    { const int a = inv[i]; if (a >= 0 && a < n) { g1 += po[a]; g2 += po[a]; d += pH[(size_t)a * bt.nmax + a]; } }
     bp[i] = g1; gr[i] = g2; dH[i] = d;
   }
   __syncthreads();
+  if (tid == 0) ctrl->stamps[1] = global_ns();
   // gradient max-norm, cost on the first pass
   double m = 0;
   for (int i = tid; i < np; i += nthr) m = fmax(m, fabs(bp[i]));
@@ -1291,6 +1327,7 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
     S[tri(np, i)] = -gr[i];
   }
   __syncthreads();
+  if (tid == 0) ctrl->stamps[2] = global_ns();
   // blocked Cholesky (15-wide panels) of the augmented matrix: the last row becomes y = L^-1 (-g)
   for (int kb = 0; kb < NB; kb++) {
     const int j0 = 15 * kb;
@@ -1325,16 +1362,19 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
     if (s_fail) break;
     // panel: rows below the diagonal block (incl. the augmented row)
     for (int i = j0 + bw + tid; i <= np; i += nthr) {
+      // right-looking: as soon as x_q is known it is eliminated from every later column -- a dependency chain of two
+      // operations per column instead of a running dot product
       double x[15];
       double* row = S + tri(i, j0);
 #pragma unroll
-      for (int c = 0; c < 15; c++) {
-        if (EX && c >= bw) { x[c] = 0.0; continue; }
-        double v = row[c];
-        const double* lr = S + tri(j0 + c, j0);
+      for (int c = 0; c < 15; c++) x[c] = (EX && c >= bw) ? 0.0 : row[c];
 #pragma unroll
-        for (int q = 0; q < 15; q++) if (q < c) v -= x[q] * lr[q];
-        x[c] = v * dinv[j0 + c];
+      for (int q = 0; q < 15; q++) {
+        if (EX && q >= bw) break;
+        x[q] *= dinv[j0 + q];
+#pragma unroll
+        for (int c = q + 1; c < 15; c++)
+          if (!EX || c < bw) x[c] = fma(-x[q], S[tri(j0 + c, j0 + q)], x[c]);
       }
 #pragma unroll
       for (int c = 0; c < 15; c++) if (!EX || c < bw) row[c] = x[c];
@@ -1384,37 +1424,38 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
     if (tid == 0) { ctrl->solve_ok = 0; ctrl->stepped = 1; ctrl->iterations++; }
     return;
   }
+  if (tid == 0) ctrl->stamps[3] = global_ns();
   // back substitution L^T dp = y (warp 0)
   for (int i = tid; i < np; i += nthr) yv[i] = S[tri(np, i)];
   __syncthreads();
-  // blocked: per panel one warp solves L_kk^T x = y_k in registers (lane d holds column d of L_kk),
-  // then all threads eliminate x from the rows above
-  for (int kb = NB - 1; kb >= 0; kb--) {
-    const int j0 = 15 * kb;
-    const int bw = EX ? min(15, np - j0) : 15;
-    if (tid < 32) {
-      double col[15];
+  // L^T x = y, column oriented, in ONE warp and without a barrier: lane l keeps y_i for i = l, l + 32, ... in
+  // registers; for k = np-1 .. 0: x_k = y_k / L_kk is broadcast by a shuffle and every lane eliminates it from its
+  // rows above (row k of the packed L is contiguous: coalesced shared-memory reads that do not depend on the chain).
+  if (tid < 32) {
+    constexpr int YS = 8;                          // 8 * 32 = 256 >= np (np <= 226)
+    double y[YS];
 #pragma unroll
-      for (int k = 0; k < 15; k++) col[k] = (tid < bw && k >= tid && k < bw) ? S[tri(j0 + k, j0 + tid)] : (k == tid ? 1.0 : 0.0);
-      double y = tid < bw ? yv[j0 + tid] : 0.0;
-      const double di = tid < bw ? dinv[j0 + tid] : 1.0;
+    for (int u = 0; u < YS; u++) y[u] = (tid + 32 * u < np) ? yv[tid + 32 * u] : 0.0;
 #pragma unroll
-      for (int c = 14; c >= 0; c--) {
-        const double xc = __shfl_sync(0xffffffffu, y * di, c);
-        if (tid == c) y = xc;
-        else if (tid < c) y = fma(-col[c], xc, y);
+    for (int u = YS - 1; u >= 0; u--) {
+      if (32 * u >= np) continue;
+      for (int kk = min(31, np - 1 - 32 * u); kk >= 0; kk--) {
+        const int k = 32 * u + kk;
+        const double xk = __shfl_sync(0xffffffffu, y[u] * dinv[k], kk);
+        if (tid == kk) y[u] = xk;
+        const double* Lk = S + tri(k, 0);
+#pragma unroll
+        for (int v = 0; v <= u; v++) {
+          const int i = tid + 32 * v;
+          if (i < k) y[v] = fma(-Lk[i], xk, y[v]);
+        }
       }
-      if (tid < bw) yv[j0 + tid] = y;
     }
-    __syncthreads();
-    for (int k = tid; k < j0; k += nthr) {
-      double v = yv[k];
 #pragma unroll
-      for (int c = 0; c < 15; c++) if (!EX || c < bw) v = fma(-S[tri(j0 + c, k)], yv[j0 + c], v);
-      yv[k] = v;
-    }
-    __syncthreads();
+    for (int u = 0; u < YS; u++) if (tid + 32 * u < np) yv[tid + 32 * u] = y[u];
   }
+  __syncthreads();
+  if (tid == 0) ctrl->stamps[4] = global_ns();
   // step + pose part of the model cost change:  -g^T d - 1/2 d^T H d = -1/2 g^T d + 1/2 d^T D d
   double mp = 0, s_bgn = 0, s_gn2 = 0, s_nDn = 0, s_tDn = 0;
   for (int i = tid; i < np; i += nthr) {
@@ -1436,7 +1477,7 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
       ctrl->dsum[3] = s_bgn; ctrl->dsum[4] = s_nDn; ctrl->dsum[5] = s_tDn;
     }
   }
-  if (tid == 0) { ctrl->model_pose = mp; ctrl->solve_ok = 1; ctrl->stepped = 1; ctrl->iterations++; }
+  if (tid == 0) { ctrl->model_pose = mp; ctrl->solve_ok = 1; ctrl->stepped = 1; ctrl->iterations++; ctrl->stamps[5] = global_ns(); }
 }
 
 // =============================================================================================
@@ -1919,7 +1960,8 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
   if (ev) cudaEventRecord(ev[0], st);
   const int KE = bt.K + XB;
   const int nstrip = (KE * (KE + 1) / 2) * 2;   // half-block units
-  const dim3 grid(bt.T + 1, bt.B);
+  // latency mode (fewer windows than SMs): every IMU factor in its own CTA
+  const dim3 grid(bt.T + 1 + (bt.solve_wide ? bt.K - 1 : 0), bt.B);
 #define BVIO_LIN(NS) \
   { if (XB == 2) ba_linearize_kernel<NS, 2><<<grid, BA_THREADS, s1, st>>>(bt); \
     else if (XB == 1) ba_linearize_kernel<NS, 1><<<grid, BA_THREADS, s1, st>>>(bt); \
@@ -2421,7 +2463,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
     if (i > j) { double v = 0.5 * (Ar[i * ld + j] + Ar[j * ld + i]); Ar[i * ld + j] = v; Ar[j * ld + i] = v; }
   }
   __syncthreads();
-  if (tid == 0) phase[4] = global_ns();
+  if (tid == 0) { phase[4] = global_ns(); phase[7] = (unsigned long long)clock64(); }
   if (ma.method == 1) {
     // ---- opt-in (BVIO_MARG_CHOLESKY=1; the default below is the reference's eigen-decomposition):
     //      (J, r) by diagonally pivoted Cholesky.  The reference factors A = V S V^T and keeps J = sqrt(S) V^T,
@@ -2580,7 +2622,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       __syncthreads();
     }
   }
-  if (tid == 0) phase[5] = global_ns();
+  if (tid == 0) { phase[5] = global_ns(); phase[7] = (unsigned long long)clock64() - phase[7]; }
   // ---- linearized_jacobians = sqrt(S) V^T, linearized_residuals = sqrt(S^-1) V^T b  (:283-291)
   for (int e = tid; e < n * n; e += nt) {
     int i = e / n, k = e - i * n;       // column-major J(k, i) at [i*n + k]
