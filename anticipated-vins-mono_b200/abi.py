@@ -84,7 +84,9 @@ class SelectIn(C.Structure):
 
 class SelectSummary(C.Structure):
     _fields_ = [("n_selected", C.c_int32), ("n_candidates_valid", C.c_int32), ("candidates_scored", C.c_int64),
-                ("final_logdet", C.c_double), ("min_margin", C.c_double), ("device_ms", C.c_double)]
+                ("final_logdet", C.c_double), ("min_margin", C.c_double), ("device_ms", C.c_double),
+                ("transport", C.c_int32), ("world", C.c_int32), ("grid", C.c_int32), ("cpw", C.c_int32),
+                ("round_score_us", C.c_double), ("round_barrier_us", C.c_double), ("round_exchange_us", C.c_double)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

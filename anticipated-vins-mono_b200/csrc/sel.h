@@ -29,6 +29,8 @@ struct SelCtrl {
   int n_selected, round, n_valid, pad;
   unsigned int ticket, pad2;
   int peer_timeout, pad3;             // fused exchange: a peer's record did not arrive within the time limit
+  // where a greedy round of the persistent kernel spends its time (thread 0 of CTA 0, summed over the rounds, ns)
+  unsigned long long t_score, t_barrier, t_exchange;
 };
 
 struct SelProb {
@@ -45,6 +47,8 @@ struct SelProb {
   int rank, world;
   int grid_round;                     // CTAs of the round kernel
   int grid_persist, cpw;              // persistent single-kernel path: CTAs, candidates per warp (0 = not used)
+  int c_smem;                         // persistent path: the warps' information blocks are staged in shared memory (else
+                                      // they are read from L2 / HBM every round: large candidate sets)
   double delta_imu, acc_var, acc_bias_var;
   double q_ic[4], t_ic[3];
   double k1_pos[3], k1_quat[4];       // state_k1_ (feature_selector.cpp:247-250): = horizon[1] unless the caller gave one

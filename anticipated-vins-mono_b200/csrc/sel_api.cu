@@ -78,7 +78,7 @@ static int sel_validate(bvio_ctx* ctx, const bvio_select_in* in) {
   return BVIO_OK;
 }
 
-static int sel_upload_impl(bvio_ctx* ctx, const bvio_select_in* in, bool use_cache, bool sharded, bvio_selprob** out) {
+static int sel_upload_impl(bvio_ctx* ctx, const bvio_select_in* in, bool use_cache, bool sharded, bvio_selprob** out, bool force_shard = false) {
   int rc = sel_validate(ctx, in);
   if (rc) return rc;
   if (!out) return fail(ctx, BVIO_ERR_INVALID, "null out");
@@ -91,6 +91,20 @@ static int sel_upload_impl(bvio_ctx* ctx, const bvio_select_in* in, bool use_cac
   SelProb& sp = pr->sp;
   memset(&sp, 0, sizeof sp);
   const int H = in->H, T = 3 * H, TT = T * (T + 1) / 2, D = 9 * (H + 1), N = in->N, U = in->U, C = in->C;
+  if (sharded && ctx->world > 1 && !force_shard && !getenv("BVIO_SEL_FORCE_SHARD")) {
+    // Planner: a greedy round costs one in-warp Cholesky chain however few candidates a warp holds, so sharding only
+    // pays when one GPU needs more than one candidate per warp.  Below that every rank runs the whole selection itself
+    // (identical results, no exchange) and the summary says transport 0.
+    SelProb probe;
+    memset(&probe, 0, sizeof probe);
+    probe.H = H; probe.T = T; probe.TT = TT; probe.world = 1; probe.c0 = 0; probe.c1 = N; probe.kappa = in->kappa;
+    if (sel_plan_persist(probe, ctx->sm_count) && probe.cpw <= 1) sharded = false;
+  }
+  if (sharded && ctx->world > 1 && !ctx->p2p_ready && !getenv("BVIO_SEL_NCCL")) {
+    delete pr;
+    return fail(ctx, BVIO_ERR_NCCL, "bvio_select_sharded: the peer-memory mailboxes could not be mapped (no CUDA IPC / peer access "
+                                    "between the ranks' devices); set BVIO_SEL_NCCL=1 to run one ncclAllGather per greedy round instead");
+  }
   sp.H = H; sp.T = T; sp.TT = TT; sp.D = D; sp.Do = D - T;
   sp.N = N; sp.U = U; sp.C = C; sp.kappa = in->kappa; sp.nr_imu = in->nr_imu;
   sp.rank = sharded ? ctx->rank : 0;
@@ -288,6 +302,10 @@ static void mbox_setup(bvio_ctx* ctx) {
 int bvio_select_upload(bvio_ctx* ctx, const bvio_select_in* in, bvio_selprob** out) {
   return sel_upload_impl(ctx, in, false, ctx && ctx->comm && ctx->world > 1, out);
 }
+int bvio_select_upload_mode(bvio_ctx* ctx, const bvio_select_in* in, int32_t mode, bvio_selprob** out) {
+  if (mode < 0 || mode > 2) return fail(ctx, BVIO_ERR_INVALID, "bvio_select_upload_mode: mode must be 0, 1 or 2");
+  return sel_upload_impl(ctx, in, false, mode != 0 && ctx && ctx->comm && ctx->world > 1, out, mode == 2);
+}
 
 int bvio_select_run(bvio_ctx* ctx, bvio_selprob* pr) {
   if (!ctx || !pr) return fail(ctx, BVIO_ERR_INVALID, "null problem");
@@ -345,6 +363,15 @@ int bvio_select_fetch(bvio_ctx* ctx, bvio_selprob* pr, int32_t* out_ids, double*
     summary->final_logdet = c->final_logdet;
     summary->min_margin = c->min_margin;
     summary->device_ms = ms;
+    const SelProb& sp = pr->sp;
+    summary->transport = sp.world == 1 ? 0 : (sp.fused ? 1 : 2);
+    summary->world = sp.world;
+    summary->grid = sp.grid_persist > 0 ? sp.grid_persist : sp.grid_round;
+    summary->cpw = sp.grid_persist > 0 ? sp.cpw : 0;
+    const double rounds = sp.kappa > 0 ? (double)sp.kappa : 1.0;
+    summary->round_score_us = sp.grid_persist > 0 ? c->t_score * 1e-3 / rounds : 0.0;
+    summary->round_barrier_us = sp.grid_persist > 0 ? c->t_barrier * 1e-3 / rounds : 0.0;
+    summary->round_exchange_us = sp.grid_persist > 0 ? c->t_exchange * 1e-3 / rounds : 0.0;
   }
   return BVIO_OK;
 }

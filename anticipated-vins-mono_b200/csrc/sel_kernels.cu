@@ -39,6 +39,7 @@ __global__ void sel_reset_kernel(SelProb sp) {
     SelCtrl c;
     c.scored = 0; c.min_margin = INFINITY; c.logdet_oo = 0; c.final_logdet = 0;
     c.n_selected = 0; c.round = 0; c.n_valid = 0; c.pad = 0; c.ticket = 0; c.pad2 = 0; c.peer_timeout = 0; c.pad3 = 0;
+    c.t_score = 0; c.t_barrier = 0; c.t_exchange = 0;
     *sp.ctrl = c;
   }
 }
@@ -585,11 +586,13 @@ __global__ void __launch_bounds__(32 * SEL_WARPS, 2) sel_persist_kernel(SelProb 
   constexpr int T = 3 * H, TT = T * (T + 1) / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cpw = sp.cpw;
   double* sR = sm;                                         // [TT]
-  double* sC = sR + TT + (size_t)warp * cpw * TT;          // [cpw][TT] this warp's candidates
-  double* sred = sm + (size_t)(1 + SEL_WARPS * cpw) * TT;  // [SEL_WARPS*4] + [4]
+  const int csm = sp.c_smem;
+  const int slots = csm ? cpw : 1;                         // c_smem: all of the warp's blocks stay staged; else one at a time
+  double* sC = sR + TT + (size_t)warp * slots * TT;        // [slots][TT]
+  double* sred = sm + (size_t)(1 + SEL_WARPS * slots) * TT;   // [SEL_WARPS*4] + [4]
   const int gw = blockIdx.x * SEL_WARPS + warp, nw = gridDim.x * SEL_WARPS;
   // candidates of this warp: index, prob, alive (valid and not yet taken), one per slot k
-  for (int k = 0; k < cpw; k++) {
+  for (int k = 0; k < cpw && csm; k++) {
     const int i = sp.c0 + gw + k * nw;
     if (i < sp.c1 && sp.valid[i])
       for (int e = lane; e < TT; e += 32) sC[(size_t)k * TT + e] = sp.Cc[(size_t)i * TT + e];
@@ -605,13 +608,22 @@ __global__ void __launch_bounds__(32 * SEL_WARPS, 2) sel_persist_kernel(SelProb 
   int n_selected = 0;
   double min_margin = INFINITY;
   unsigned long long scored = 0;
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long t_score = 0, t_barrier = 0, t_exchange = 0, tq = timer ? global_ns() : 0;
   for (int round = 0; round < sp.kappa; round++) {
     double best = -1.0, second = -INFINITY, cnt = 0;
     int bidx = -1;
     for (int k = 0; k < cpw; k++) {
       if (!((alive >> k) & 1ull)) continue;
       const int i = sp.c0 + gw + k * nw;
-      const double ld = warp_chol_logdet<T, true>(sR, lane, sC + (size_t)k * TT, sp.cand_prob[i]);
+      const double* Ck = sC + (size_t)(csm ? k : 0) * TT;
+      if (!csm) {                                            // coalesced copy from L2 / HBM into the warp's staging slot
+        __syncwarp();
+        const double* src = sp.Cc + (size_t)i * TT;
+        for (int e = lane; e < TT; e += 32) sC[e] = __ldg(src + e);
+        __syncwarp();
+      }
+      const double ld = warp_chol_logdet<T, true>(sR, lane, Ck, sp.cand_prob[i]);
       const double val = ld_oo + 2.0 * ld;
       cnt += 1;
       if (val > best) { second = best; best = val; bidx = i; }
@@ -628,7 +640,9 @@ __global__ void __launch_bounds__(32 * SEL_WARPS, 2) sel_persist_kernel(SelProb 
       double* bb = rec + (size_t)blockIdx.x * 4;
       __stcg(bb, b); __stcg(bb + 1, s); __stcg(bb + 2, (double)ix); __stcg(bb + 3, c);
     }
+    if (timer) { const unsigned long long t = global_ns(); t_score += t - tq; tq = t; }
     grid_barrier(&sp.ctrl->ticket, (unsigned)(round + 1) * gridDim.x);
+    if (timer) { const unsigned long long t = global_ns(); t_barrier += t - tq; tq = t; }
     // merge all CTA records (identical on every CTA)
     {
       double b = -1.0, s = -INFINITY, c = 0;
@@ -694,6 +708,7 @@ __global__ void __launch_bounds__(32 * SEL_WARPS, 2) sel_persist_kernel(SelProb 
         bcw[0] = b; bcw[1] = s; bcw[2] = (double)ix; bcw[3] = c;
       }
       __syncthreads();
+      if (timer) { const unsigned long long t = global_ns(); t_exchange += t - tq; tq = t; }
     }
     const double* bc = sred + SEL_WARPS * 4;
     const double wb = bc[0], ws = bc[1];
@@ -718,6 +733,7 @@ __global__ void __launch_bounds__(32 * SEL_WARPS, 2) sel_persist_kernel(SelProb 
     if (threadIdx.x == 0) {
       SelCtrl* c = sp.ctrl;
       c->n_selected = n_selected; c->min_margin = min_margin; c->scored = scored; c->round = sp.kappa;
+      c->t_score = t_score; c->t_barrier = t_barrier; c->t_exchange = t_exchange;   // (merge + apply are booked with the next score)
     }
   }
 }
@@ -824,35 +840,48 @@ int sel_launch_round(const SelProb& sp, cudaStream_t st) {
   }
   return 1;
 }
-static size_t persist_smem(int TT, int cpw) { return sizeof(double) * ((size_t)(1 + SEL_WARPS * cpw) * TT + SEL_WARPS * 4 + 4); }
+static size_t persist_smem(int TT, int cpw, int c_smem) {
+  return sizeof(double) * ((size_t)(1 + SEL_WARPS * (c_smem ? cpw : 1)) * TT + SEL_WARPS * 4 + 4);
+}
 
 // Picks the grid of the persistent kernel: every CTA must be co-resident (the kernel spins on a grid
-// barrier).  Returns 0 when the problem does not fit (the caller then runs one kernel per round).
+// barrier).  Small candidate sets keep their information blocks in shared memory (cpw <= 3 at H = 10); larger ones
+// (up to 64 candidates per warp: ~150 000 candidates per GPU) read them from L2 / HBM every round.
+// Returns 0 when the problem does not fit (the caller then runs one kernel per round).
 int sel_plan_persist(SelProb& sp, int sm_count) {
   const int nloc = sp.c1 - sp.c0;
-  sp.grid_persist = 0; sp.cpw = 0;
+  sp.grid_persist = 0; sp.cpw = 0; sp.c_smem = 1;
   if ((sp.world != 1 && !sp.fused) || nloc <= 0 || sp.kappa <= 0) return 0;
   int per_sm = 0;
   cudaError_t e = cudaSuccess;
   int want = (nloc + SEL_WARPS - 1) / SEL_WARPS;
-  for (int cpw = 1; cpw <= 8; cpw++) {
-    size_t smem = persist_smem(sp.TT, cpw);
-    if (smem > 100 * 1024) break;
-    switch (sp.H) {
+  for (int pass = 0; pass < 2; pass++) {
+    const int c_smem = pass == 0;
+    for (int cpw = 1; cpw <= (c_smem ? 8 : 64); cpw++) {
+      size_t smem = persist_smem(sp.TT, cpw, c_smem);
+      if (smem > 100 * 1024) break;
+      switch (sp.H) {
 #define BVIO_SEL_CASE(HH) case HH: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sel_persist_kernel<HH>, 32 * SEL_WARPS, smem); break;
-      BVIO_SEL_FOR_EACH_H(BVIO_SEL_CASE)
+        BVIO_SEL_FOR_EACH_H(BVIO_SEL_CASE)
 #undef BVIO_SEL_CASE
-      default: return 0;
+        default: return 0;
+      }
+      if (e != cudaSuccess || per_sm < 1) return 0;
+      int cap = per_sm * sm_count;
+      int need = (want + cpw - 1) / cpw;
+      if (need <= cap) { sp.grid_persist = need; sp.cpw = cpw; sp.c_smem = c_smem; return 1; }
+      if (!c_smem) {
+        // with the blocks in L2 the grid is the whole machine: pick the smallest cpw that covers the candidates
+        int cpw_need = (want + cap - 1) / cap;
+        if (cpw_need > 64) return 0;
+        cpw = cpw_need - 1;   // loop increment lands on it
+      }
     }
-    if (e != cudaSuccess || per_sm < 1) return 0;
-    int cap = per_sm * sm_count;
-    int need = (want + cpw - 1) / cpw;
-    if (need <= cap) { sp.grid_persist = need; sp.cpw = cpw; return 1; }
   }
   return 0;
 }
 int sel_launch_persist(const SelProb& sp, cudaStream_t st) {
-  size_t smem = persist_smem(sp.TT, sp.cpw);
+  size_t smem = persist_smem(sp.TT, sp.cpw, sp.c_smem);
   switch (sp.H) {
   // cooperative launch: the driver guarantees (or refuses) co-residency of all CTAs, which the grid
   // barrier inside the kernel relies on

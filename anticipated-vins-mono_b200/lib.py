@@ -18,7 +18,7 @@ EXPORTS = [
     "bvio_batch_free", "bvio_batch_solve_timed", "bvio_stream", "bvio_launch_count", "bvio_marginalize", "bvio_select",
     "bvio_nccl_unique_id", "bvio_comm_init", "bvio_select_sharded", "bvio_select_upload", "bvio_select_run",
     "bvio_select_fetch", "bvio_select_free", "bvio_debug_linearize", "bvio_debug_build_delta", "bvio_triangulate",
-    "bvio_preintegrate", "bvio_horizon_imu",
+    "bvio_preintegrate", "bvio_horizon_imu", "bvio_select_upload_mode",
 ]
 
 
@@ -56,6 +56,7 @@ def load():
     L.bvio_comm_init.argtypes = [vp, vp, i32, i32]
     L.bvio_select_sharded.argtypes = [vp, C.POINTER(abi.SelectIn), ip, dp, C.POINTER(abi.SelectSummary)]
     L.bvio_select_upload.argtypes = [vp, C.POINTER(abi.SelectIn), C.POINTER(vp)]
+    L.bvio_select_upload_mode.argtypes = [vp, C.POINTER(abi.SelectIn), C.c_int32, C.POINTER(vp)]
     L.bvio_select_run.argtypes = [vp, vp]
     L.bvio_select_fetch.argtypes = [vp, vp, ip, dp, C.POINTER(abi.SelectSummary)]
     L.bvio_select_free.argtypes = [vp, vp]

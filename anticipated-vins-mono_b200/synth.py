@@ -301,6 +301,68 @@ class Window:
 PREINT_DOUBLES = 3 + 4 + 3 + 3 + 3 + 1 + 225 + 225
 
 
+def slice_window(w: "Window", f0: int, K: int):
+    """The K-frame window that starts at frame f0 of a longer session `w`, as FeatureManager would hold it: observations
+    outside [f0, f0 + K) are gone, landmarks with fewer than two left (or anchored too late to be optimised,
+    estimator.cpp:712-718) are dropped, and a landmark whose anchor observation fell out is re-anchored at its first
+    remaining observation with its depth carried over through the current pose estimates (removeBackShiftDepth,
+    feature_manager.cpp:275-311).  Returns (window, idx) with idx[l] = index of landmark l in `w`."""
+    U_, _, Vt_ = np.linalg.svd(EUROC_RIC)
+    ric, tic = U_ @ Vt_, EUROC_TIC
+    Rs = [quat_to_rot(q / np.linalg.norm(q)) for q in w.para_pose[:, 3:]]
+    Rg = [quat_to_rot(q) for q in w.gt_pose[:, 3:]] if w.gt_pose is not None else None
+    offs, fr, xy, inv, ginv, idx = [0], [], [], [], [], []
+    for l in range(w.L):
+        o0, o1 = int(w.lm_obs_offset[l]), int(w.lm_obs_offset[l + 1])
+        sel = [k for k in range(o0, o1) if f0 <= w.obs_frame[k] < f0 + K]
+        if len(sel) < 2 or w.obs_frame[sel[0]] - f0 >= K - 3:
+            continue
+        lam, glam = float(w.inv_depth[l]), float(w.gt_inv_depth[l]) if w.gt_inv_depth is not None else 0.0
+        if sel[0] != o0:                      # re-anchor: depth in the old anchor camera -> world -> new anchor camera
+            fa, fn = int(w.obs_frame[o0]), int(w.obs_frame[sel[0]])
+            pa = np.array([w.obs_xy[o0, 0], w.obs_xy[o0, 1], 1.0])
+            pw = Rs[fa] @ (ric @ (pa / lam) + tic) + w.para_pose[fa, :3]
+            lam = 1.0 / (ric.T @ (Rs[fn].T @ (pw - w.para_pose[fn, :3]) - tic))[2]
+            if Rg is not None:
+                pw = Rg[fa] @ (ric @ (pa / glam) + tic) + w.gt_pose[fa, :3]
+                glam = 1.0 / (ric.T @ (Rg[fn].T @ (pw - w.gt_pose[fn, :3]) - tic))[2]
+        fr += [int(w.obs_frame[k]) - f0 for k in sel]
+        xy += [w.obs_xy[k] for k in sel]
+        offs.append(len(fr))
+        inv.append(lam)
+        ginv.append(glam)
+        idx.append(l)
+    pre = np.zeros((K, PREINT_DOUBLES))
+    pre[1:] = w.preint[f0 + 1:f0 + K]
+    out = Window(K=K, para_pose=w.para_pose[f0:f0 + K].copy(), para_speed_bias=w.para_speed_bias[f0:f0 + K].copy(),
+                 para_ex_pose=w.para_ex_pose.copy(), para_td=w.para_td.copy(), inv_depth=np.array(inv),
+                 lm_obs_offset=np.array(offs, np.int32), obs_frame=np.array(fr, np.int32),
+                 obs_xy=np.array(xy, float).reshape(-1, 2), preint=pre, prior=w.prior if f0 == 0 else None,
+                 gt_pose=w.gt_pose[f0:f0 + K].copy() if w.gt_pose is not None else None,
+                 gt_speed_bias=w.gt_speed_bias[f0:f0 + K].copy() if w.gt_speed_bias is not None else None,
+                 gt_inv_depth=np.array(ginv) if w.gt_inv_depth is not None else None)
+    return out, np.array(idx, np.int64)
+
+
+def make_session(seed, K=11, L=1500, track_min=6):
+    """A (K+1)-frame session from which two CONSECUTIVE K-frame windows are cut (bench.py builds its pool of windows with
+    real marginalized priors from these): ~L landmarks in either window."""
+    return make_window(seed=seed, K=K + 1, L=int(L * 1.04), track_min=track_min, track_max=K + 1)
+
+
+def consecutive_window(session: "Window", first_solved: "Window", first_idx, prior: dict, K=11):
+    """The second window of make_session(): frames 1 .. K, starting from the first window's SOLVED state (frames and
+    landmarks they share) and carrying `prior`, the marginalization of the first window's frame 0 -- the situation of
+    every Estimator::optimization() call after the first (estimator.cpp:694-700)."""
+    ses = session.copy()
+    ses.para_pose[:K] = first_solved.para_pose
+    ses.para_speed_bias[:K] = first_solved.para_speed_bias
+    ses.inv_depth[first_idx] = first_solved.inv_depth
+    w, _ = slice_window(ses, 1, K)
+    w.prior = prior
+    return w
+
+
 def add_relocalization(w: "Window", seed=0, local_index=4, max_matches=40, pose_sigma=(0.05, 0.01)) -> "Window":
     """Relocalization inputs as Estimator::setReloFrame leaves them (estimator.cpp:1109-1127) for a window made by
     make_window: the loop-closure frame is an earlier visit near window frame `local_index`; every landmark anchored at

@@ -313,6 +313,16 @@ typedef struct {
   double  final_logdet;         /* logdet(Omega + OmegaS) after the last round */
   double  min_margin;           /* min over rounds of best - second best value */
   double  device_ms;
+  /* ---- ABI v2: how the selection ran -------------------------------------- */
+  int32_t transport;            /* 0 one GPU (also: sharded call that the planner kept on one GPU),
+                                 * 1 fused: all rounds in one kernel, winner records over peer memory (NVLink),
+                                 * 2 one kernel per round with an ncclAllGather in between                    */
+  int32_t world;                /* ranks that shared the candidates                                          */
+  int32_t grid;                 /* CTAs of the scoring kernel                                                */
+  int32_t cpw;                  /* candidates per warp of the persistent kernel (0: one kernel per round)    */
+  double  round_score_us;       /* persistent kernel, mean per greedy round as seen by CTA 0:                */
+  double  round_barrier_us;     /*   scoring + merge + update, wait at the grid barrier,                     */
+  double  round_exchange_us;    /*   wait for the peers' records (0 on one GPU)                              */
 } bvio_select_summary;
 
 /* Replaces calcInfoFromRobotMotion + addOmegaPrior + 2x calcInfoFromFeatures +
@@ -335,6 +345,9 @@ int bvio_select_sharded(bvio_ctx* ctx, const bvio_select_in* in, int32_t* out_id
 /* Device-resident selector problem (benchmarks): upload, run (async), fetch.  */
 typedef struct bvio_selprob bvio_selprob;
 int  bvio_select_upload(bvio_ctx* ctx, const bvio_select_in* in, bvio_selprob** out);
+/* mode 0: this GPU alone (also on a context that has a communicator); 1: shared with the communicator's ranks when the
+ * planner finds that sharding pays (what bvio_select_upload / bvio_select_sharded do); 2: shared, always */
+int  bvio_select_upload_mode(bvio_ctx* ctx, const bvio_select_in* in, int32_t mode, bvio_selprob** out);
 int  bvio_select_run(bvio_ctx* ctx, bvio_selprob* prob);
 int  bvio_select_fetch(bvio_ctx* ctx, bvio_selprob* prob, int32_t* out_ids,
                        double* out_values, bvio_select_summary* summary);

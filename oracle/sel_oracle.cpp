@@ -308,6 +308,8 @@ int oracle_select(const bvio_select_in* in, int32_t* out_ids, double* out_values
     sum->final_logdet = oracle_logdet(M.data(), D);
     sum->min_margin = min_margin;
     sum->device_ms = 0;
+    sum->transport = 0; sum->world = 1; sum->grid = 0; sum->cpw = 0;
+    sum->round_score_us = sum->round_barrier_us = sum->round_exchange_us = 0;
   }
   return BVIO_OK;
 }

@@ -29,8 +29,9 @@ def main():
     dist.broadcast(uid, 0)
     ctx.check(ctx.L.bvio_comm_init(ctx.h, bytes(uid.cpu().numpy().tobytes()), rank, world), "comm_init")
     ok = True
+    # BVIO_SEL_FORCE_SHARD=1 (set by the test): share even the small problems that the planner would keep on one GPU
     for seed, N, H, U, kappa, twins in ((0, 2000, 10, 0, 150, 0), (1, 333, 13, 4, 40, 0), (2, 7, 10, 0, 5, 0), (3, 64, 5, 2, 64, 0),
-                                        (4, 400, 10, 0, 60, 12), (5, 240, 13, 3, 30, 8)):
+                                        (4, 400, 10, 0, 60, 12), (5, 240, 13, 3, 30, 8), (6, 12000, 10, 0, 30, 0), (7, 9000, 13, 2, 20, 6)):
         p = synth.make_select_problem(seed=seed, N=N, H=H, U=U, kappa=kappa)
         # exact duplicates (the reference's UB-map collision, feature_selector.cpp:697,724): twins inside one shard and
         # twins that straddle shard boundaries must resolve to the larger id on every rank
@@ -50,7 +51,8 @@ def main():
                 s1.candidates_scored == s2.candidates_scored and s1.n_candidates_valid == s2.n_candidates_valid and
                 s1.final_logdet == s2.final_logdet)
         print(f"[rank {rank}/{world}] seed {seed} N {N} H {H} kappa {kappa}: n_sel {s2.n_selected} scored {s2.candidates_scored} "
-              f"single {s1.device_ms:.2f} ms sharded {s2.device_ms:.2f} ms  {'OK' if same else 'MISMATCH'}", flush=True)
+              f"single {s1.device_ms:.2f} ms (cpw {s1.cpw}) sharded {s2.device_ms:.2f} ms (transport {s2.transport}, cpw {s2.cpw}, "
+              f"round us {s2.round_score_us:.1f}/{s2.round_barrier_us:.1f}/{s2.round_exchange_us:.1f})  {'OK' if same else 'MISMATCH'}", flush=True)
         ok &= same
     t = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -13,12 +13,38 @@ sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import __graft_entry__ as g
 
 
+KEYS = ("n", "block_kind", "block_frame", "block_idx", "x0", "lin_jac", "lin_res")
+_cache = {}
+
+
+def window_with_prior(pkg, L, marginalize):
+    """The second of two consecutive windows of one session, carrying the n = 75 prior marginalized from the first
+    (first window's state = its initial guess: the latency does not depend on it)."""
+    synth = pkg.synth
+    if L not in _cache:
+        ses = synth.make_session(40, K=11, L=L)
+        first, idx = synth.slice_window(ses, 0, 11)
+        p0 = marginalize(first)
+        _cache[L] = synth.consecutive_window(ses, first, idx, {k: p0[k] for k in KEYS})
+    return _cache[L]
+
+
+def measure_cpu(pkg, oracle, L, strategy=1):
+    abi = pkg.abi
+    w = window_with_prior(pkg, L, lambda a: abi.call_marginalize(oracle.oracle_marginalize, a, 0))
+    o = abi.default_opts(strategy=strategy, max_iters=8)
+    tc = []
+    for r in range(3):
+        h, so = abi.WindowHandle(w), abi.Summary()
+        t0 = time.perf_counter()
+        assert oracle.oracle_optimize(C.byref(h.s), C.byref(o), C.byref(so)) == 0
+        tc.append(time.perf_counter() - t0)
+    return {"cpu_oracle_ms": float(np.min(tc) * 1e3), "cpu_iterations": int(so.iterations)}
+
+
 def measure(pkg, ctx, oracle, L, reps=30, strategy=1):
     abi, synth = pkg.abi, pkg.synth
-    import test_oracle_marg as tm
-    keys = ("n", "block_kind", "block_frame", "block_idx", "x0", "lin_jac", "lin_res")
-    p0 = tm.run_marg(abi, ctx.L.bvio_marginalize, synth.make_window(seed=40, K=11, L=L), 0, ctx=ctx.h)
-    w = dataclasses.replace(synth.make_window(seed=41, K=11, L=L), prior={k: p0[k] for k in keys})   # real n = 75 prior
+    w = window_with_prior(pkg, L, lambda a: abi.call_marginalize(ctx.L.bvio_marginalize, a, 0, ctx=ctx.h))
     o = abi.default_opts(strategy=strategy, max_iters=8)
     ts, s = [], abi.Summary()
     for r in range(reps + 5):
@@ -40,15 +66,7 @@ def measure(pkg, ctx, oracle, L, reps=30, strategy=1):
     out["kernel_ms_per_pass"] = dict(linearize=ms[0] / nl[0], solve=ms[1] / nl[1], cost=ms[2] / max(nl[2], 1))
     ctx.L.bvio_batch_free(ctx.h, ph)
     if oracle is not None:
-        tc = []
-        for r in range(3):
-            h = abi.WindowHandle(w)
-            so = abi.Summary()
-            t0 = time.perf_counter()
-            assert oracle.oracle_optimize(C.byref(h.s), C.byref(o), C.byref(so)) == 0
-            tc.append(time.perf_counter() - t0)
-        out["cpu_oracle_ms"] = float(np.min(tc) * 1e3)
-        out["cpu_iterations"] = int(so.iterations)
+        out.update(measure_cpu(pkg, oracle, L, strategy))
     return out
 
 
