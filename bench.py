@@ -121,6 +121,7 @@ def _session(i):
 
 def make_sessions(n, workers):
     """n synthetic (K+1)-frame sessions (pure numpy; forked workers -- call before CUDA is initialised)."""
+    g.load_package()                      # the parent unpickles the workers' Window objects: the class must be importable
     if workers <= 1:
         return [_session(i) for i in range(n)]
     import multiprocessing as mp
@@ -209,6 +210,7 @@ def run_reference(args, rank, world):
     thread, same workload and strategy as the GPU arm; each step a bounded sample of the pool."""
     if rank != 0:
         return
+    os.environ["ORACLE_EIGH"] = "ql"      # timed CPU legs: the eigen-solver class Eigen uses (oracle/ba_oracle.cpp)
     import oracle_lib
     pkg = g.load_package()
     abi, synth = pkg.abi, pkg.synth
@@ -506,6 +508,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle_lib
         orc = oracle_lib.load()
+        os.environ["ORACLE_EIGH"] = "ql"  # timed CPU legs: the eigen-solver class Eigen uses (oracle/ba_oracle.cpp)
         it, dt = cpu_ba(abi, orc, pool, args.cpu_solves, 1)
         sc, sdt = cpu_select(abi, synth, orc, args.cpu_kappa)
         cpu = {"value": it / dt, "unit": "iters/s", "cores": 1, "kind": "port",

@@ -18,6 +18,7 @@
 #include "linalg.hpp"
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <chrono>
 #include <vector>
 
@@ -1197,7 +1198,11 @@ int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_
   // Amm pseudo-inverse
   std::vector<double> Amm((size_t)m * m), wv(m), Vm((size_t)m * m), Ainv((size_t)m * m, 0.0);
   for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Amm[(size_t)i * m + j] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]);
-  if (m > 0) jacobi_eigh(Amm.data(), m, wv.data(), Vm.data());
+  // ORACLE_EIGH=ql: Householder + implicit QL (the cost class of Eigen::SelfAdjointEigenSolver) for the TIMED CPU baseline;
+  // default: cyclic Jacobi, whose relative accuracy on the near-null gauge directions keeps the eps = 1e-8 threshold
+  // decisions identical between this oracle, the reference's compiled code (stand-in Eigen) and the device
+  const bool ql = std::getenv("ORACLE_EIGH") && std::string(std::getenv("ORACLE_EIGH")) == "ql";
+  if (m > 0) { if (ql) tridiag_ql_eigh(Amm.data(), m, wv.data(), Vm.data()); else jacobi_eigh(Amm.data(), m, wv.data(), Vm.data()); }
   for (int k = 0; k < m; k++) {
     if (!(wv[k] > eps)) continue;
     double iv = 1.0 / wv[k];
@@ -1224,7 +1229,7 @@ int oracle_marginalize(const bvio_window* w, const bvio_opts* o, int flag, bvio_
   // second eigen-decomposition (Eigen reads the lower triangle; symmetrise for the Jacobi sweeps)
   std::vector<double> As((size_t)n * n), S(n), V((size_t)n * n);
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) As[(size_t)i * n + j] = 0.5 * (Ar[(size_t)i * n + j] + Ar[(size_t)j * n + i]);
-  if (n > 0) jacobi_eigh(As.data(), n, S.data(), V.data());
+  if (n > 0) { if (ql) tridiag_ql_eigh(As.data(), n, S.data(), V.data()); else jacobi_eigh(As.data(), n, S.data(), V.data()); }
   if (n > out->cap_n || (int)kept.size() > out->cap_blocks) return BVIO_ERR_INVALID;
   out->n = n;
   out->nblocks = (int)kept.size();

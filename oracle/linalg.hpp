@@ -287,4 +287,126 @@ inline void jacobi_eigh(const double* a_in, int n, double* w, double* v) {
   }
 }
 
+
+// Symmetric eigen-decomposition by Householder tridiagonalisation + implicit QL iterations -- the algorithm family of
+// Eigen::SelfAdjointEigenSolver (tridiagonalisation + implicit symmetric QR, marginalization_factor.cpp:268,283), so
+// that the CPU baseline's marginalization costs what the reference's does (the cyclic Jacobi above is O(10 n^3) slower).
+// Same conventions as jacobi_eigh: w ascending, eigenvectors as COLUMNS of v (row-major n x n).  The two routines agree
+// to O(eps ||A||) in the eigenvalues and in every basis-independent quantity (tests/test_oracle_marg.py).
+inline void tridiag_ql_eigh(const double* a_in, int n, double* d, double* V) {
+  std::vector<double> e(n, 0.0);
+  for (int i = 0; i < n * n; i++) V[i] = a_in[i];
+  if (n == 0) return;
+  // ---- Householder reduction to tridiagonal form (EISPACK tred2)
+  for (int j = 0; j < n; j++) d[j] = V[(n - 1) * n + j];
+  for (int i = n - 1; i > 0; i--) {
+    double scale = 0.0, h = 0.0;
+    for (int k = 0; k < i; k++) scale += std::fabs(d[k]);
+    if (scale == 0.0) {
+      e[i] = d[i - 1];
+      for (int j = 0; j < i; j++) { d[j] = V[(i - 1) * n + j]; V[i * n + j] = 0.0; V[j * n + i] = 0.0; }
+    } else {
+      for (int k = 0; k < i; k++) { d[k] /= scale; h += d[k] * d[k]; }
+      double f = d[i - 1], g = std::sqrt(h);
+      if (f > 0) g = -g;
+      e[i] = scale * g;
+      h -= f * g;
+      d[i - 1] = f - g;
+      for (int j = 0; j < i; j++) e[j] = 0.0;
+      for (int j = 0; j < i; j++) {
+        f = d[j];
+        V[j * n + i] = f;
+        g = e[j] + V[j * n + j] * f;
+        for (int k = j + 1; k <= i - 1; k++) { g += V[k * n + j] * d[k]; e[k] += V[k * n + j] * f; }
+        e[j] = g;
+      }
+      f = 0.0;
+      for (int j = 0; j < i; j++) { e[j] /= h; f += e[j] * d[j]; }
+      const double hh = f / (h + h);
+      for (int j = 0; j < i; j++) e[j] -= hh * d[j];
+      for (int j = 0; j < i; j++) {
+        f = d[j]; g = e[j];
+        for (int k = j; k <= i - 1; k++) V[k * n + j] -= (f * e[k] + g * d[k]);
+        d[j] = V[(i - 1) * n + j];
+        V[i * n + j] = 0.0;
+      }
+    }
+    d[i] = h;
+  }
+  for (int i = 0; i < n - 1; i++) {
+    V[(n - 1) * n + i] = V[i * n + i];
+    V[i * n + i] = 1.0;
+    const double h = d[i + 1];
+    if (h != 0.0) {
+      for (int k = 0; k <= i; k++) d[k] = V[k * n + i + 1] / h;
+      for (int j = 0; j <= i; j++) {
+        double g = 0.0;
+        for (int k = 0; k <= i; k++) g += V[k * n + i + 1] * V[k * n + j];
+        for (int k = 0; k <= i; k++) V[k * n + j] -= g * d[k];
+      }
+    }
+    for (int k = 0; k <= i; k++) V[k * n + i + 1] = 0.0;
+  }
+  for (int j = 0; j < n; j++) { d[j] = V[(n - 1) * n + j]; V[(n - 1) * n + j] = 0.0; }
+  V[(n - 1) * n + n - 1] = 1.0;
+  e[0] = 0.0;
+  // ---- implicit QL with eigenvector accumulation (EISPACK tql2)
+  for (int i = 1; i < n; i++) e[i - 1] = e[i];
+  e[n - 1] = 0.0;
+  double f = 0.0, tst1 = 0.0;
+  const double eps = std::pow(2.0, -52.0);
+  for (int l = 0; l < n; l++) {
+    tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+    int m = l;
+    while (m < n) { if (std::fabs(e[m]) <= eps * tst1) break; m++; }
+    if (m > l) {
+      int iter = 0;
+      do {
+        iter++;
+        double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = std::hypot(p, 1.0);
+        if (p < 0) r = -r;
+        d[l] = e[l] / (p + r);
+        d[l + 1] = e[l] * (p + r);
+        const double dl1 = d[l + 1];
+        double h = g - d[l];
+        for (int i = l + 2; i < n; i++) d[i] -= h;
+        f += h;
+        p = d[m];
+        double c = 1.0, c2 = c, c3 = c, el1 = e[l + 1], s = 0.0, s2 = 0.0;
+        for (int i = m - 1; i >= l; i--) {
+          c3 = c2; c2 = c; s2 = s;
+          g = c * e[i];
+          h = c * p;
+          r = std::hypot(p, e[i]);
+          e[i + 1] = s * r;
+          s = e[i] / r;
+          c = p / r;
+          p = c * d[i] - s * g;
+          d[i + 1] = h + s * (c * g + s * d[i]);
+          for (int k = 0; k < n; k++) {
+            h = V[k * n + i + 1];
+            V[k * n + i + 1] = s * V[k * n + i] + c * h;
+            V[k * n + i] = c * V[k * n + i] - s * h;
+          }
+        }
+        p = -s * s2 * c3 * el1 * e[l] / dl1;
+        e[l] = s * p;
+        d[l] = c * p;
+      } while (std::fabs(e[l]) > eps * tst1 && iter < 200);
+    }
+    d[l] = d[l] + f;
+    e[l] = 0.0;
+  }
+  // ascending order
+  for (int i = 0; i < n - 1; i++) {
+    int k = i;
+    double p = d[i];
+    for (int j = i + 1; j < n; j++) if (d[j] < p) { k = j; p = d[j]; }
+    if (k != i) {
+      d[k] = d[i]; d[i] = p;
+      for (int j = 0; j < n; j++) std::swap(V[j * n + i], V[j * n + k]);
+    }
+  }
+}
+
 }  // namespace orc

@@ -199,3 +199,18 @@ def test_td_marginalization_plumbing(pkg, oracle):
     assert Hr[-1, -1] > 0 and np.abs(Hr[-1, :-1]).max() > 0
     ev = np.linalg.eigvalsh(Hr)
     assert ev.min() >= -1e-9 * ev.max()
+
+
+def test_ql_eigensolver_mode_gives_the_same_prior(pkg, oracle, monkeypatch):
+    """ORACLE_EIGH=ql (Householder + implicit QL, used for the timed CPU baseline) against the default cyclic Jacobi:
+    same quadratic form on a well-conditioned kept system."""
+    abi, synth, orc = pkg.abi, pkg.synth, oracle
+    w = synth.make_window(seed=21, K=11, L=120)
+    pj = run_marg(abi, orc.oracle_marginalize, w, 0)
+    monkeypatch.setenv("ORACLE_EIGH", "ql")
+    pq = run_marg(abi, orc.oracle_marginalize, w, 0)
+    assert pj["n"] == pq["n"]
+    Hj, gj = info_in_state_coords(pj, w.K, lambda f: f + 1)
+    Hq, gq = info_in_state_coords(pq, w.K, lambda f: f + 1)
+    assert np.abs(Hj - Hq).max() <= 1e-7 * np.abs(Hj).max()          # (measured 2e-8: the eps = 1e-8 pseudo-inverse sees different roundoff)
+    assert np.abs(gj - gq).max() <= 1e-4 * max(np.abs(gj).max(), 1.0)
