@@ -250,3 +250,40 @@ def call_marginalize(lib_fn, w, flag, ctx=None, opts=None):
 
 
 call_marginalize.t_call = 0.0
+
+
+class MarginalizeJob:
+    """bvio_marginalize_begin ... bvio_marginalize_end around other work (the prior is first needed by the next frame)."""
+
+    def __init__(self, L, ctx, w, flag, opts=None):
+        import time
+        self.L, self.ctx = L, ctx
+        self.h = WindowHandle(w)
+        cap_n, cap_b = 15 * w.K + 16, 2 * w.K + 2
+        self.bk, self.bf, self.bi = (np.zeros(cap_b, np.int32) for _ in range(3))
+        self.x0, self.jac, self.res = np.zeros(9 * cap_b), np.zeros(cap_n * cap_n), np.zeros(cap_n)
+        self.out = PriorOut()
+        self.out.block_kind, self.out.block_frame, self.out.block_idx = iptr(self.bk), iptr(self.bf), iptr(self.bi)
+        self.out.x0, self.out.lin_jac, self.out.lin_res = dptr(self.x0), dptr(self.jac), dptr(self.res)
+        self.out.cap_n, self.out.cap_blocks = cap_n, cap_b
+        self.o = opts if opts is not None else default_opts()
+        self.job = C.c_void_p()
+        t0 = time.perf_counter()
+        rc = L.bvio_marginalize_begin(ctx, C.byref(self.h.s), C.byref(self.o), flag, C.byref(self.out), C.byref(self.job))
+        self.t_begin = time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError(f"marginalize_begin failed: {rc}")
+
+    def end(self):
+        import time
+        t0 = time.perf_counter()
+        rc = self.L.bvio_marginalize_end(self.ctx, self.job)
+        self.t_end = time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError(f"marginalize_end failed: {rc}")
+        n, nb = self.out.n, self.out.nblocks
+        if n < 0:
+            return None
+        J = self.jac[:n * n].reshape(n, n, order="F").copy()
+        return dict(n=n, block_kind=self.bk[:nb].copy(), block_frame=self.bf[:nb].copy(), block_idx=self.bi[:nb].copy(),
+                    x0=self.x0.copy(), lin_jac=self.jac[:n * n].copy(), lin_res=self.res[:n].copy(), J=J)

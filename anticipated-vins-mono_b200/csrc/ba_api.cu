@@ -32,6 +32,14 @@ struct bvio_batch {
   bool relo = false;
 };
 
+// a marginalization in flight on the context's second stream (bvio_marginalize_begin / _end)
+struct bvio_marg_job {
+  bvio_batch* bb = nullptr;
+  bvio_prior_out* out = nullptr;
+  int n = 0;
+  size_t o_jac = 0, o_res = 0;
+};
+
 extern "C" {
 
 int bvio_abi_version(void) { return BVIO_ABI_VERSION; }
@@ -90,6 +98,7 @@ void bvio_destroy(bvio_ctx* ctx) {
   for (int i = 0; i < bvio_ctx::PIPE; i++) ctx->ba_pipe[i].release();
   ctx->sel_cache.release();
   if (ctx->marg_scratch) cudaFree(ctx->marg_scratch);
+  if (ctx->marg_host) cudaFreeHost(ctx->marg_host);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -707,8 +716,13 @@ int bvio_batch_solve_timed(bvio_ctx* ctx, bvio_batch* bb, double out_ms[4], int3
 // ba_marginalize_kernel.  Kept blocks come out in frame order (Pose f, SpeedBias f ascending, then
 // Ex_Pose) with the reference's addr_shift applied.  flag 1 and a prior that does not touch Pose[K-2]:
 // out->n = -1 (the reference leaves last_marginalization_info untouched, estimator.cpp:926-928).
-int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* opts, int32_t flag, bvio_prior_out* out) {
+static int marg_impl(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* opts, int32_t flag, bvio_prior_out* out,
+                     bvio_marg_job** job) {
   if (!ctx || !w_in || !opts || !out || (flag != 0 && flag != 1)) return fail(ctx, BVIO_ERR_INVALID, "bad arguments");
+  if (ctx->marg_inflight) return fail(ctx, BVIO_ERR_INVALID, "a marginalization is in flight: call bvio_marginalize_end first");
+  const bool async = job != nullptr;
+  if (job) *job = nullptr;
+  cudaStream_t st = async ? ctx->copy_stream : ctx->stream;
   // the relocalization factors are not part of the marginalization (estimator.cpp:816-991)
   bvio_window w_copy = *w_in;
   w_copy.n_relo = 0; w_copy.relo_pose = nullptr; w_copy.relo_lm = nullptr; w_copy.relo_xy = nullptr;
@@ -730,7 +744,7 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* op
   }
   std::vector<int> dropidx, keepidx;
   if (flag == 1) {
-    if (!pr || !has_pose[K - 2]) { out->n = -1; out->nblocks = 0; return BVIO_OK; }
+    if (!pr || !has_pose[K - 2]) { out->n = -1; out->nblocks = 0; return BVIO_OK; }   // (async: *job stays NULL, nothing to wait for)
     for (int i = 0; i < 6; i++) dropidx.push_back(15 * (K - 2) + i);
     has_pose[K - 2] = 0;
   } else {
@@ -776,7 +790,7 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* op
   if (ba_marginalize_smem_bytes(K, pr ? pr->n : 1, n) > 220 * 1024)
     return fail(ctx, BVIO_ERR_UNSUPPORTED, "kept dimension too large for the single-CTA eigen-decomposition");
   bvio_batch* bb = nullptr;
-  rc = upload_impl(ctx, w, 1, opts, 0, 0, &bb);
+  rc = upload_impl(ctx, w, 1, opts, async ? 1 : 0, 0, &bb);   // async: pipeline slot 0, uploaded and prepared on the copy stream
   if (rc) return rc;
   char* scratch = nullptr;
   Carver cv;
@@ -787,6 +801,13 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* op
   if (flag == 0) for (int l = 0; l < w->L; l++) n0 += w->obs_frame[w->lm_obs_offset[l]] == 0;
   size_t o_part = cv.take(sizeof(double) * ba_marginalize_part_doubles(K, ba_marginalize_groups(n0)));
   cudaError_t e = cudaSuccess;
+  const size_t stage_bytes = sizeof(double) * ((size_t)n * n + n);
+  if (async && ctx->marg_host_bytes < stage_bytes) {       // pinned staging for the asynchronous D2H
+    if (ctx->marg_host) cudaFreeHost(ctx->marg_host);
+    ctx->marg_host = nullptr; ctx->marg_host_bytes = 0;
+    e = cudaMallocHost((void**)&ctx->marg_host, stage_bytes + stage_bytes / 4);
+    if (e == cudaSuccess) ctx->marg_host_bytes = stage_bytes + stage_bytes / 4;
+  }
   if (ctx->marg_bytes < cv.off) {
     if (ctx->marg_scratch) cudaFree(ctx->marg_scratch);
     ctx->marg_scratch = nullptr; ctx->marg_bytes = 0;
@@ -794,14 +815,26 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* op
     if (e == cudaSuccess) ctx->marg_bytes = cv.off + cv.off / 4;
   }
   scratch = ctx->marg_scratch;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_drop, dropidx.data(), sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_keep, keepidx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_drop, dropidx.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + o_keep, keepidx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
     ctx->launches += ba_launch_marginalize(bb->bt, flag, m, n, n0, (const int*)(scratch + o_drop), (const int*)(scratch + o_keep),
                                            (double*)(scratch + o_A), (double*)(scratch + o_b), (double*)(scratch + o_part), (double*)(scratch + o_jac),
                                            (double*)(scratch + o_res), (int*)(scratch + o_st),
-                                           getenv("BVIO_MARG_CHOLESKY") ? 1 : 0, ctx->stream);
+                                           getenv("BVIO_MARG_CHOLESKY") ? 1 : 0, st);
     e = cudaGetLastError();
+  }
+  if (async) {
+    // the dropidx / keepidx vectors above are pageable host memory: their copies have completed (staged) on return
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->marg_host, scratch + o_jac, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->marg_host + sizeof(double) * (size_t)n * n, scratch + o_res, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { cudaStreamSynchronize(st); bvio_batch_free(ctx, bb); return fail(ctx, BVIO_ERR_CUDA, std::string("marginalize: ") + cudaGetErrorString(e)); }
+    bvio_marg_job* j = new (std::nothrow) bvio_marg_job();
+    if (!j) { cudaStreamSynchronize(st); bvio_batch_free(ctx, bb); return fail(ctx, BVIO_ERR_INVALID, "out of host memory"); }
+    j->bb = bb; j->out = out; j->n = n;
+    ctx->marg_inflight = true;
+    *job = j;
+    return BVIO_OK;
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_jac, scratch + o_jac, sizeof(double) * n * n, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out->lin_res, scratch + o_res, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
@@ -818,6 +851,35 @@ int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w_in, const bvio_opts* op
   }
   bvio_batch_free(ctx, bb);
   if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("marginalize: ") + cudaGetErrorString(e));
+  for (int i = 0; i < n * n; i++) if (!(out->lin_jac[i] == out->lin_jac[i])) return fail(ctx, BVIO_ERR_NUMERIC, "non-finite prior");
+  return BVIO_OK;
+}
+
+int bvio_marginalize(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts, int32_t flag, bvio_prior_out* out) {
+  return marg_impl(ctx, w, opts, flag, out, nullptr);
+}
+
+int bvio_marginalize_begin(bvio_ctx* ctx, const bvio_window* w, const bvio_opts* opts, int32_t flag, bvio_prior_out* out,
+                           bvio_marg_job** job) {
+  if (!job) return fail(ctx, BVIO_ERR_INVALID, "null job");
+  return marg_impl(ctx, w, opts, flag, out, job);
+}
+
+int bvio_marginalize_end(bvio_ctx* ctx, bvio_marg_job* job) {
+  if (!ctx) return BVIO_ERR_INVALID;
+  if (!job) return BVIO_OK;                     // begin() had nothing to enqueue (out->n <= 0)
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+  const int n = job->n;
+  if (e == cudaSuccess) {
+    memcpy(job->out->lin_jac, ctx->marg_host, sizeof(double) * (size_t)n * n);
+    memcpy(job->out->lin_res, ctx->marg_host + sizeof(double) * (size_t)n * n, sizeof(double) * n);
+  }
+  ctx->marg_inflight = false;
+  bvio_batch_free(ctx, job->bb);
+  bvio_prior_out* out = job->out;
+  delete job;
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("marginalize_end: ") + cudaGetErrorString(e));
   for (int i = 0; i < n * n; i++) if (!(out->lin_jac[i] == out->lin_jac[i])) return fail(ctx, BVIO_ERR_NUMERIC, "non-finite prior");
   return BVIO_OK;
 }

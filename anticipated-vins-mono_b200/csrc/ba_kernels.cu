@@ -299,12 +299,50 @@ __global__ void __launch_bounds__(BA_THREADS) ba_prepare_kernel(BaBatch bt) {
   }
   const double* Jc = bt.pr_jac + (size_t)w * bt.nmax * bt.nmax;
   double* H = bt.pr_H + (size_t)w * bt.nmax * bt.nmax;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    int a = e / n, b2 = e - a * n;
-    double s = 0;
-    for (int k = 0; k < n; k++) s += Jc[(size_t)a * n + k] * Jc[(size_t)b2 * n + k];
-    H[(size_t)a * bt.nmax + b2] = s;
+  // H = J^T J through shared-memory tiles: 16 rows (k) of all n columns at a time (coalesced reads of the column-major J),
+  // eight outputs per thread per pass -- the prior's Hessian is on the critical path of every one-window call
+  {
+    constexpr int TK = 16, ACC = 8;
+    __shared__ double sJt[TK * 97];                        // [TK][n] for n <= 96; wider priors take the direct loop
+    if (n <= 96) {
+      const int npass = (n * n + ACC * (int)blockDim.x - 1) / (ACC * (int)blockDim.x);
+      for (int pass = 0; pass < npass; pass++) {
+        double acc[ACC];
+        int ea[ACC], eb[ACC];
+#pragma unroll
+        for (int u = 0; u < ACC; u++) {
+          const int e = (pass * ACC + u) * blockDim.x + threadIdx.x;
+          acc[u] = 0.0;
+          ea[u] = e < n * n ? e / n : -1;
+          eb[u] = e < n * n ? e - (e / n) * n : 0;
+        }
+        for (int k0 = 0; k0 < n; k0 += TK) {
+          __syncthreads();
+          for (int i = threadIdx.x; i < TK * n; i += blockDim.x) {
+            const int c = i / TK, kk = i - c * TK;
+            sJt[kk * 97 + c] = (k0 + kk < n) ? Jc[(size_t)c * n + k0 + kk] : 0.0;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int u = 0; u < ACC; u++) {
+            if (ea[u] < 0) continue;
+#pragma unroll
+            for (int kk = 0; kk < TK; kk++) acc[u] = fma(sJt[kk * 97 + ea[u]], sJt[kk * 97 + eb[u]], acc[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < ACC; u++) if (ea[u] >= 0) H[(size_t)ea[u] * bt.nmax + eb[u]] = acc[u];
+      }
+    } else {
+      for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        int a = e / n, b2 = e - a * n;
+        double s = 0;
+        for (int k = 0; k < n; k++) s += Jc[(size_t)a * n + k] * Jc[(size_t)b2 * n + k];
+        H[(size_t)a * bt.nmax + b2] = s;
+      }
+    }
   }
+  __syncthreads();
   // reduced index -> prior column, and (latency mode) the prior Hessian scattered once into ba_solve's packed layout
   int* inv = bt.pr_inv + (size_t)w * bt.np;
   for (int i = threadIdx.x; i < bt.np; i += blockDim.x) inv[i] = -1;

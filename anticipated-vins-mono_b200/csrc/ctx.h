@@ -51,6 +51,9 @@ struct bvio_ctx {
   bool ba_pipe_busy[PIPE] = {false, false, false, false, false, false, false, false};
   char* marg_scratch = nullptr;   // grow-only device scratch of bvio_marginalize
   size_t marg_bytes = 0;
+  char* marg_host = nullptr;      // pinned staging of bvio_marginalize_begin / _end
+  size_t marg_host_bytes = 0;
+  bool marg_inflight = false;
   // multi-GPU selector
   ncclComm* comm = nullptr;
   int rank = 0, world = 1;

@@ -228,8 +228,8 @@ class SlidingWindowSim:
             if not tr.alive:
                 continue
             k = vis.get(tr.lid)
-            if k is None:
-                tr.alive = False
+            if k is None or (getattr(self, "track_loss", 0.0) > 0 and self.rng.uniform() < self.track_loss):
+                tr.alive = False                                # out of view, or the front end lost the track
             else:
                 tr.xy.append(xy[k] + self.rng.normal(0, self.sig, 2))
                 n_tracked += 1
@@ -384,7 +384,7 @@ class SlidingWindowSim:
         """Returns None while the window fills, else a dict of per-call wall times (s) and counters."""
         self._backend = backend
         new_idx, n_tracked, cand, cxy = self._ingest()
-        lat = None
+        lat, job = None, None
         if len(self.pose) == self.K:
             w, feats = self.build_window(backend)
             pose0 = w.para_pose[0].copy()
@@ -409,14 +409,21 @@ class SlidingWindowSim:
                                         inv_depth=wsol.inv_depth.copy())
             t2 = time.perf_counter()
             c_marg = 0.0
+            overlap = getattr(self, "overlap_marginalize", False) and hasattr(backend, "marginalize_begin")
             if self.margin_flag == MARGIN_OLD:
-                self.prior = backend.marginalize(wpost, MARGIN_OLD, self.opts)
+                if overlap:
+                    job = backend.marginalize_begin(wpost, MARGIN_OLD, self.opts)
+                else:
+                    self.prior = backend.marginalize(wpost, MARGIN_OLD, self.opts)
                 c_marg = getattr(backend, "t_call", 0.0)
             elif self.prior is not None:                        # estimator.cpp:926: only if there is a prior; it is
-                p = backend.marginalize(wpost, MARGIN_SECOND_NEW, self.opts)   # replaced only if it involves Pose[WINDOW_SIZE-1]
+                if overlap:                                     # replaced only if it involves Pose[WINDOW_SIZE-1]
+                    job = backend.marginalize_begin(wpost, MARGIN_SECOND_NEW, self.opts)
+                else:
+                    p = backend.marginalize(wpost, MARGIN_SECOND_NEW, self.opts)
+                    if p is not None:
+                        self.prior = p
                 c_marg = getattr(backend, "t_call", 0.0)
-                if p is not None:
-                    self.prior = p
             t3 = time.perf_counter()
             lat = {"optimize": t1 - t0, "marginalize": t3 - t2, "optimize_call": c_opt, "flag": self.margin_flag,
                    "marginalize_call": c_marg, "L": w.L, "n_factors": w.n_factors,
@@ -442,6 +449,14 @@ class SlidingWindowSim:
             self._start_tracks(new_idx, self.last_selected, cand, cxy)
         if lat is not None and "select" not in lat:
             lat["select"] = lat["select_call"] = 0.0
+        if len(self.pose) == self.K and lat is not None and job is not None:
+            # the marginalization that has been running on the second stream while select() worked
+            t6 = time.perf_counter()
+            p = backend.marginalize_end(job)
+            if p is not None or self.margin_flag == MARGIN_OLD:
+                self.prior = p if p is not None else self.prior
+            lat["marginalize"] += time.perf_counter() - t6
+            lat["marginalize_call"] += getattr(backend, "t_call", 0.0)
         if len(self.pose) == self.K:
             self._slide() if self.margin_flag == MARGIN_OLD else self._slide_new()
         return lat
@@ -621,6 +636,16 @@ class GpuBackend:
         out = self.abi.call_marginalize(self.L.bvio_marginalize, w, flag, ctx=self.ctx.h,
                                         opts=self.abi.default_opts(**(opts or {})))
         self.t_call = self.abi.call_marginalize.t_call
+        return out
+
+    def marginalize_begin(self, w, flag, opts=None):
+        job = self.abi.MarginalizeJob(self.L, self.ctx.h, w, flag, self.abi.default_opts(**(opts or {})))
+        self.t_call = job.t_begin
+        return job
+
+    def marginalize_end(self, job):
+        out = job.end()
+        self.t_call = job.t_end
         return out
 
     def select(self, prob):

@@ -315,12 +315,14 @@ def selector_block(r):
                              "exchange": ss.round_exchange_us}}
 
 
-def run_stream(pkg, ctx, abi, frames, max_feats, H, label):
+def run_stream(pkg, ctx, abi, frames, max_feats, H, label, track_loss=0.0, overlap=False):
     """BASELINE configs[4]: closed-loop sequence of CONSECUTIVE sliding windows (slider.py), one window per call through the
     one-shot C-ABI with host buffers.  *_call = the FFI call alone; the others include the ctypes packing around it."""
     sim = pkg.slider.SlidingWindowSim(seed=7, max_feats=max_feats, max_cand=300, H=H, frame_dt=1.0 / 30.0)
     gb = pkg.slider.GpuBackend(ctx, abi)          # the reference's budget: 8 iterations, Ceres default tolerances, dogleg
     sim.opts = dict(strategy=1)
+    sim.track_loss = track_loss                   # fraction of live tracks the front end loses per frame
+    sim.overlap_marginalize = overlap             # bvio_marginalize_begin ... select ... bvio_marginalize_end
     keys = ("optimize", "marginalize", "select", "optimize_call", "marginalize_call", "select_call")
     lat = {k: [] for k in keys + ("frame", "frame_call")}
     cnt = {"L": [], "n_factors": [], "N": [], "kappa": [], "iterations": []}
@@ -337,7 +339,8 @@ def run_stream(pkg, ctx, abi, frames, max_feats, H, label):
         for k in cnt:
             cnt[k].append(r.get(k, 0))
     errs = np.array([h[1] for h in sim.history])
-    out = {"frames": frames, "label": label, "wall_s": time.perf_counter() - t_wall,
+    out = {"frames": frames, "label": label, "wall_s": time.perf_counter() - t_wall, "track_loss_per_frame": track_loss,
+           "marginalization": "bvio_marginalize_begin / _end around bvio_select (second stream)" if overlap else "bvio_marginalize (synchronous)",
            "workload": f"closed-loop 30 Hz sequence of consecutive 11-keyframe windows, budget {max_feats} features: per frame "
                        "bvio_optimize (8 dogleg iterations, Ceres default tolerances, prior = previous marginalization) + "
                        f"bvio_marginalize (eigen route) + bvio_select (H={H}), host buffers, wall clock",
@@ -352,11 +355,12 @@ def run_stream(pkg, ctx, abi, frames, max_feats, H, label):
     return out
 
 
-def cpu_stream(pkg, orc, abi, frames, max_feats, H):
+def cpu_stream(pkg, orc, abi, frames, max_feats, H, track_loss=0.0):
     """The same closed loop on the CPU oracle (cpu_baseline leg): per-frame latency of optimize + marginalize + select."""
     from slider_backends import OracleBackend
     sim = pkg.slider.SlidingWindowSim(seed=7, max_feats=max_feats, max_cand=300, H=H, frame_dt=1.0 / 30.0)
     sim.opts = dict(strategy=1)
+    sim.track_loss = track_loss
     be = OracleBackend(orc, abi)
     lat, warm = [], sim.K + 2
     for f in range(frames + warm):
@@ -500,8 +504,11 @@ def run_ours(args, rank, world, local_rank):
         single = [single_window.measure(pkg, ctx, None, L_) for L_ in (150, 1500)]
     if rank == 0 and args.stream_frames > 0:
         streams = [run_stream(pkg, ctx, abi, args.stream_frames, 150, SEL_H, "configs[4]: feature budget 150"),
-                   run_stream(pkg, ctx, abi, min(args.stream_frames, 2000), 30, 13,
-                              "max_features 30 (config/euroc/euroc_config.yaml:86), H = 13 (state_defs.h:8)")]
+                   run_stream(pkg, ctx, abi, min(args.stream_frames, 2000), 150, 13,
+                              "feature budget 150, 20 % of the tracks lost per frame (kappa ~ 30 new features per frame), H = 13 "
+                              "(the reference's compile-time HORIZON, state_defs.h:8)", track_loss=0.2),
+                   run_stream(pkg, ctx, abi, min(args.stream_frames, 2000), 150, SEL_H,
+                              "configs[4] with the marginalization overlapped with select()", overlap=True)]
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
@@ -523,7 +530,7 @@ def run_ours(args, rank, world, local_rank):
                 blk.update(cpu_oracle_ms=ref["cpu_oracle_ms"], cpu_iterations=ref["cpu_iterations"])
         if streams is not None:
             streams[0]["cpu_oracle"] = cpu_stream(pkg, orc, abi, 40, 150, SEL_H)
-            streams[1]["cpu_oracle"] = cpu_stream(pkg, orc, abi, 40, 30, 13)
+            streams[1]["cpu_oracle"] = cpu_stream(pkg, orc, abi, 40, 150, 13, track_loss=0.2)
 
     if rank == 0:
         peaks = {}

@@ -217,6 +217,16 @@ typedef struct {
 int bvio_marginalize(bvio_ctx* ctx, const bvio_window* window, const bvio_opts* opts,
                      int32_t flag, bvio_prior_out* out);
 
+/* The same, split: _begin enqueues the marginalization on the context's second stream and returns at once; _end waits
+ * for it and fills `out` (whose arrays must stay valid in between).  The new prior is first needed by the NEXT frame's
+ * optimization(), so the caller can run FeatureSelector::select() -- bvio_select on the context's main stream -- or wait
+ * for the next image while it computes.  One marginalization in flight per context.  *job is NULL when there was nothing
+ * to compute (out->n <= 0); bvio_marginalize_end(ctx, NULL) is a no-op. */
+typedef struct bvio_marg_job bvio_marg_job;
+int bvio_marginalize_begin(bvio_ctx* ctx, const bvio_window* window, const bvio_opts* opts, int32_t flag,
+                           bvio_prior_out* out, bvio_marg_job** job);
+int bvio_marginalize_end(bvio_ctx* ctx, bvio_marg_job* job);
+
 /* The step right before optimization() in Estimator::solveOdometry (estimator.cpp:471):
  * FeatureManager::triangulate (feature_manager.cpp:202-257).  For every landmark of the window, the DLT depth in its
  * anchor camera frame from all its observations (right singular vector of the (2 n_obs) x 4 system, svd_V[2]/svd_V[3]);

@@ -142,3 +142,28 @@ def test_td_prior_drives_the_next_solve(env):
     assert (sg.iterations, sg.num_accepted, sg.termination) == (so.iterations, so.num_accepted, so.termination)
     assert np.linalg.norm(hg.state_vector() - ho.state_vector()) <= 1e-8 * np.linalg.norm(ho.state_vector())
     assert abs(hg.td[0] - ho.td[0]) <= 1e-9
+
+
+def test_marginalize_begin_end_equals_synchronous_call(pkg):
+    """bvio_marginalize_begin / _end (second stream, pinned staging) around a bvio_select on the main stream: the prior
+    is bit-identical to the synchronous call's, the selection is undisturbed, and a second begin is refused."""
+    abi, synth = pkg.abi, pkg.synth
+    ctx = pkg.lib.Context(0)
+    for seed, flag in ((3, 0), (4, 0), (5, 1)):
+        w0 = synth.make_window(seed=seed, K=11, L=150)
+        p0 = run_marg(abi, ctx.L.bvio_marginalize, w0, 0, ctx=ctx.h)
+        w = dataclasses.replace(synth.make_window(seed=seed + 50, K=11, L=150),
+                                prior={k: p0[k] for k in ("n", "block_kind", "block_frame", "block_idx", "x0", "lin_jac", "lin_res")})
+        ps = run_marg(abi, ctx.L.bvio_marginalize, w, flag, ctx=ctx.h)
+        prob = synth.make_select_problem(seed=seed, N=300, H=10, kappa=20)
+        hs, ss, ids0, ids1 = abi.SelectHandle(prob), abi.SelectSummary(), np.zeros(20, np.int32), np.zeros(20, np.int32)
+        ctx.check(ctx.L.bvio_select(ctx.h, C.byref(hs.s), abi.iptr(ids0), None, C.byref(ss)), "select")
+        job = abi.MarginalizeJob(ctx.L, ctx.h, w, flag)
+        with pytest.raises(RuntimeError):
+            abi.MarginalizeJob(ctx.L, ctx.h, w, flag)                       # one in flight per context
+        ctx.check(ctx.L.bvio_select(ctx.h, C.byref(hs.s), abi.iptr(ids1), None, C.byref(ss)), "select")
+        pa = job.end()
+        assert (ids0 == ids1).all()
+        assert pa["n"] == ps["n"] and np.array_equal(pa["lin_jac"], ps["lin_jac"]) and np.array_equal(pa["lin_res"], ps["lin_res"])
+        assert np.array_equal(pa["x0"], ps["x0"]) and np.array_equal(pa["block_idx"], ps["block_idx"])
+    ctx.close()
