@@ -136,6 +136,7 @@ int ba_launch_marginalize(const BaBatch& bt, int flag, int m, int n, int n0, con
                           double* b, double* part, double* out_jac, double* out_res, int* status, int method, cudaStream_t st);
 size_t ba_marginalize_part_doubles(int K, int G);   // scratch of the factor kernel's partial sums
 int ba_marginalize_groups(int n0);                  // CTAs of the factor kernel for n0 landmarks anchored at the dropped frame
+int ba_launch_marginal9(const double* S, int np, int frame, double* out81, int* status, cudaStream_t st);
 int ba_configure(void);   // cudaFuncSetAttribute for the big-smem kernels; returns cudaError_t
 
 }  // namespace bvio

@@ -679,6 +679,33 @@ int bvio_debug_linearize(bvio_ctx* ctx, const bvio_window* window, const bvio_op
   return BVIO_OK;
 }
 
+// Omega_PRIOR for bvio_select_in.omega_prior: the window's information on (position, velocity, accelerometer bias) of
+// its newest frame = Schur complement of the undamped reduced matrix onto those nine dimensions (ba_marginal9_kernel).
+int bvio_window_omega_prior(bvio_ctx* ctx, const bvio_window* window, const bvio_opts* opts, double* omega9) {
+  if (!omega9) return fail(ctx, BVIO_ERR_INVALID, "null omega9");
+  bvio_batch* bb = nullptr;
+  int rc = upload_impl(ctx, window, 1, opts, -1, 1, &bb);
+  if (rc) return rc;
+  const BaBatch& bt = bb->bt;
+  ctx->launches += ba_launch_reset(bt, ctx->stream);
+  ctx->launches += ba_launch_iteration(bt, ctx->stream, true);
+  double* dout = nullptr;
+  cudaError_t e = cudaMalloc((void**)&dout, sizeof(double) * 81 + sizeof(int) * 2);
+  int bad = 0;
+  if (e == cudaSuccess) {
+    ctx->launches += ba_launch_marginal9(bt.dbg_S, bt.np, bb->Kc - 1, dout, (int*)(dout + 81), ctx->stream);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(omega9, dout, sizeof(double) * 81, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(&bad, dout + 81, sizeof(int), cudaMemcpyDeviceToHost);
+  if (dout) cudaFree(dout);
+  bvio_batch_free(ctx, bb);
+  if (e != cudaSuccess) return fail(ctx, BVIO_ERR_CUDA, std::string("window_omega_prior: ") + cudaGetErrorString(e));
+  if (bad) return fail(ctx, BVIO_ERR_NUMERIC, "window_omega_prior: the window does not determine the other states (singular elimination)");
+  return BVIO_OK;
+}
+
 // Per-kernel device time of one solve (bench.py roofline): direct launches with an event between
 // kernels.  out_ms = {linearize, solve, cost, total of the three}, summed over all passes;
 // out_launches = {linearize, solve, cost} launch counts.

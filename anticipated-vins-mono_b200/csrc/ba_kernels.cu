@@ -1937,6 +1937,7 @@ static size_t cost_smem(int K, int nmax) {
 }
 
 cudaError_t ba_configure_marginalize(void);   // below, next to the kernels
+__global__ void ba_marginal9_kernel(const double* S, int np, int frame, double* out81, int* status);
 // __constant__ tables and the dynamic-shared-memory opt-ins are PER DEVICE: remember which devices of this process
 // have been set up (bvio_create may be called for several GPUs in one process)
 static std::mutex g_cfg_mutex;
@@ -1973,6 +1974,7 @@ int ba_configure(void) {
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
     if ((err = ba_configure_marginalize()) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_marginal9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if (dev >= 0 && dev < 256) g_cfg_devices[dev >> 6] |= 1ull << (dev & 63);
   }
   return 0;
@@ -2043,6 +2045,74 @@ int ba_launch_finish(const BaBatch& bt, cudaStream_t st) {
   return 1;
 }
 
+
+// =============================================================================================
+// Omega_PRIOR for the selector (the report's future work: support_files/report/paper/anticipation.tex
+// :146-152): the information the WHOLE window -- prior, IMU and visual factors, landmarks eliminated -- holds on
+// x_k = (position, velocity, accelerometer bias) of one frame, i.e. the Schur complement of the undamped reduced matrix
+// S onto those nine dimensions.  With the nine put last, the Cholesky factor of the permuted S has L_aa L_aa^T = that
+// complement.  One CTA; S comes from a debug linearization (dbg_S, row-major np x np).
+// =============================================================================================
+__global__ void __launch_bounds__(256) ba_marginal9_kernel(const double* S, int np, int frame, double* out81, int* status) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* Lp = sm;                                          // packed lower np(np+1)/2
+  int* perm = reinterpret_cast<int*>(Lp + (size_t)np * (np + 1) / 2);   // [np] new position -> reduced index
+  __shared__ int s_bad;
+  if (tid == 0) {
+    const int base = 15 * frame;
+    const int sel[9] = {base, base + 1, base + 2, base + 6, base + 7, base + 8, base + 9, base + 10, base + 11};
+    int k = 0;
+    for (int i = 0; i < np; i++) {
+      bool is_a = false;
+      for (int q = 0; q < 9; q++) is_a |= (sel[q] == i);
+      if (!is_a) perm[k++] = i;
+    }
+    for (int q = 0; q < 9; q++) perm[k++] = sel[q];
+    s_bad = 0;
+  }
+  __syncthreads();
+  for (int e = tid; e < np * (np + 1) / 2; e += nt) {
+    int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+    while (i * (i + 1) / 2 > e) i--;
+    while ((i + 1) * (i + 2) / 2 <= e) i++;
+    const int j = e - i * (i + 1) / 2;
+    Lp[e] = 0.5 * (S[(size_t)perm[i] * np + perm[j]] + S[(size_t)perm[j] * np + perm[i]]);
+  }
+  __syncthreads();
+  const int nb = np - 9;                                    // eliminate the first nb variables
+  for (int k = 0; k < nb; k++) {
+    const double piv = Lp[tri(k, k)];
+    if (piv == 0.0) continue;                               // a variable nothing constrains or couples to (the unused speed-bias
+                                                            // slot of a relocalization frame): its row and column are zero
+    if (!(piv > 0.0)) { if (tid == 0) s_bad = 1; break; }
+    const double inv = rsqrt(piv);
+    __syncthreads();
+    for (int i = k + tid; i < np; i += nt) Lp[tri(i, k)] *= inv;          // (the diagonal becomes sqrt(piv))
+    __syncthreads();
+    const int rem = np - k - 1;
+    for (int e = tid; e < rem * (rem + 1) / 2; e += nt) {
+      int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while (i * (i + 1) / 2 > e) i--;
+      while ((i + 1) * (i + 2) / 2 <= e) i++;
+      const int j = e - i * (i + 1) / 2;
+      Lp[tri(k + 1 + i, k + 1 + j)] -= Lp[tri(k + 1 + i, k)] * Lp[tri(k + 1 + j, k)];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid < 81) {
+    const int a = tid / 9, b2 = tid - a * 9;
+    const int i = nb + (a >= b2 ? a : b2), j = nb + (a >= b2 ? b2 : a);
+    out81[tid] = s_bad ? NAN : Lp[tri(i, j)];                // what is left in the trailing 9 x 9 block IS the complement
+  }
+  if (tid == 0) *status = s_bad;
+}
+int ba_launch_marginal9(const double* S, int np, int frame, double* out81, int* status, cudaStream_t st) {
+  const size_t smem = sizeof(double) * ((size_t)np * (np + 1) / 2) + sizeof(int) * np + 16;
+  ba_marginal9_kernel<<<1, 256, smem, st>>>(S, np, frame, out81, status);
+  return 1;
+}
 
 // =============================================================================================
 // marginalization (row a9): MarginalizationInfo::{preMarginalize, marginalize}

@@ -18,7 +18,7 @@ EXPORTS = [
     "bvio_batch_free", "bvio_batch_solve_timed", "bvio_stream", "bvio_launch_count", "bvio_marginalize", "bvio_select",
     "bvio_nccl_unique_id", "bvio_comm_init", "bvio_select_sharded", "bvio_select_upload", "bvio_select_run",
     "bvio_select_fetch", "bvio_select_free", "bvio_debug_linearize", "bvio_debug_build_delta", "bvio_triangulate",
-    "bvio_preintegrate", "bvio_horizon_imu", "bvio_select_upload_mode", "bvio_marginalize_begin", "bvio_marginalize_end",
+    "bvio_preintegrate", "bvio_horizon_imu", "bvio_select_upload_mode", "bvio_marginalize_begin", "bvio_marginalize_end", "bvio_window_omega_prior",
 ]
 
 
@@ -53,6 +53,7 @@ def load():
     L.bvio_marginalize.argtypes = [vp, C.POINTER(abi.WindowS), C.POINTER(abi.Opts), i32, C.POINTER(abi.PriorOut)]
     L.bvio_marginalize_begin.argtypes = [vp, C.POINTER(abi.WindowS), C.POINTER(abi.Opts), i32, C.POINTER(abi.PriorOut), C.POINTER(vp)]
     L.bvio_marginalize_end.argtypes = [vp, vp]
+    L.bvio_window_omega_prior.argtypes = [vp, C.POINTER(abi.WindowS), C.POINTER(abi.Opts), dp]
     L.bvio_select.argtypes = [vp, C.POINTER(abi.SelectIn), ip, dp, C.POINTER(abi.SelectSummary)]
     L.bvio_nccl_unique_id.argtypes = [vp]
     L.bvio_comm_init.argtypes = [vp, vp, i32, i32]

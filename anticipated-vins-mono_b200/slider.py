@@ -315,7 +315,11 @@ class SlidingWindowSim:
                     cl_xy.append(pc[:2] / pc[2])
                     cl_d.append(tr.depth)
         order = np.argsort(cand)
-        return S.SelectProblem(H=self.H, horizon_pos=pos, horizon_quat=quat, q_ic=self.qic, t_ic=self.tic,
+        omega_prior = None
+        if getattr(self, "use_omega_prior", False) and hasattr(self._backend, "omega_prior") and len(self.pose) == self.K:
+            # opt-in (not the reference's behaviour): Omega_PRIOR on x_k from the back end's window instead of I9
+            omega_prior = self._backend.omega_prior(self.build_window(self._backend)[0], self.opts)
+        return S.SelectProblem(H=self.H, horizon_pos=pos, horizon_quat=quat, q_ic=self.qic, t_ic=self.tic, omega_prior=omega_prior,
                                cam=dict(self.cam), nr_imu=self.n_imu, delta_imu=self.frame_dt / self.n_imu,
                                acc_var=S.ACC_N, acc_bias_var=S.ACC_W,
                                cand_id=cand[order], cand_xy=cxy[order], cand_prob=self.world.score[cand[order]],
@@ -642,6 +646,12 @@ class GpuBackend:
                                         opts=self.abi.default_opts(**(opts or {})))
         self.t_call = self.abi.call_marginalize.t_call
         return out
+
+    def omega_prior(self, w, opts=None):
+        h, om = self.abi.WindowHandle(w), np.zeros(81)
+        self.ctx.check(self.L.bvio_window_omega_prior(self.ctx.h, self.C.byref(h.s), self.C.byref(self.abi.default_opts(**(opts or {}))),
+                                                      self.abi.dptr(om)), "bvio_window_omega_prior")
+        return om.reshape(9, 9)
 
     def marginalize_begin(self, w, flag, opts=None):
         job = self.abi.MarginalizeJob(self.L, self.ctx.h, w, flag, self.abi.default_opts(**(opts or {})))

@@ -260,6 +260,14 @@ typedef struct {
   int32_t width, height;
 } bvio_camera;
 
+/* Omega_PRIOR for bvio_select_in.omega_prior, from the back end's own information instead of the reference's I9
+ * (addOmegaPrior, feature_selector.cpp:602-609; named as future work in support_files/report/paper/anticipation.tex
+ * :146-152): the 9 x 9 information (row-major; position, velocity, accelerometer bias -- the selector's state order,
+ * state_defs.h:15) that the window's prior, IMU and projection factors hold on its NEWEST frame x_k, every other state
+ * and all landmarks marginalized out, linearized at the window's current state.  Opt-in: the reference behaviour is
+ * omega_prior = NULL.  BVIO_ERR_NUMERIC when the window leaves the other states undetermined. */
+int bvio_window_omega_prior(bvio_ctx* ctx, const bvio_window* window, const bvio_opts* opts, double* omega9 /* [81] */);
+
 /* HorizonGenerator::imu (utility/horizon_generator.cpp:25-70), the step before select() in IMU-horizon mode: x_k and the
  * IMU-propagated x_{k+1} open the horizon, then x_{k+1} is propagated nr_imu steps of delta_imu per future frame with the
  * latest accelerometer / gyro sample held constant (bias ba0 of x_k, gravity (0,0,-9.80665), state_defs.h:37-41).

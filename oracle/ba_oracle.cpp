@@ -827,6 +827,43 @@ int oracle_linearize(const bvio_window* w_in, const bvio_opts* opts, double* S, 
   return BVIO_OK;
 }
 
+// Omega_PRIOR from the window (bvio_window_omega_prior): Schur complement of the undamped reduced matrix onto
+// (position, velocity, accelerometer bias) of the newest frame, by dense elimination of everything else.
+int oracle_window_omega_prior(const bvio_window* w, const bvio_opts* opts, double* omega9) {
+  Layout ly = layout(w, opts);
+  const int np = ly.np + (w->n_relo > 0 ? 15 : 0);
+  std::vector<double> S((size_t)np * np), g(np);
+  int rc = oracle_linearize(w, opts, S.data(), g.data(), nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  const int base = 15 * (w->K - 1);
+  const int sel[9] = {base, base + 1, base + 2, base + 6, base + 7, base + 8, base + 9, base + 10, base + 11};
+  std::vector<int> ib;
+  for (int i = 0; i < np; i++) { bool a = false; for (int q = 0; q < 9; q++) a |= sel[q] == i; if (!a) ib.push_back(i); }
+  if (w->n_relo > 0) {   // the unused speed-bias slot of the relocalization frame has no information: leave it out
+    std::vector<int> keep;
+    for (int i : ib) if (!(i >= 15 * w->K + 6 && i < 15 * w->K + 15)) keep.push_back(i);
+    ib = keep;
+  }
+  const int nb = (int)ib.size();
+  std::vector<double> Sbb((size_t)nb * nb), Sba((size_t)nb * 9);
+  for (int i = 0; i < nb; i++) {
+    for (int j = 0; j < nb; j++) Sbb[(size_t)i * nb + j] = 0.5 * (S[(size_t)ib[i] * np + ib[j]] + S[(size_t)ib[j] * np + ib[i]]);
+    for (int q = 0; q < 9; q++) Sba[(size_t)i * 9 + q] = S[(size_t)ib[i] * np + sel[q]];
+  }
+  if (!cholesky(Sbb.data(), nb)) return BVIO_ERR_NUMERIC;
+  for (int q = 0; q < 9; q++) {
+    std::vector<double> x(nb);
+    for (int i = 0; i < nb; i++) x[i] = Sba[(size_t)i * 9 + q];
+    chol_solve(Sbb.data(), nb, x.data());
+    for (int p = 0; p < 9; p++) {
+      double s = S[(size_t)sel[p] * np + sel[q]];
+      for (int i = 0; i < nb; i++) s -= Sba[(size_t)i * 9 + p] * x[i];
+      omega9[p * 9 + q] = s;
+    }
+  }
+  return BVIO_OK;
+}
+
 static int oracle_optimize_impl(bvio_window* w, const bvio_opts* o, bvio_summary* sum);
 int oracle_optimize(bvio_window* w, const bvio_opts* o, bvio_summary* sum) {
   if (o->estimate_td && w->n_relo > 0) return BVIO_ERR_UNSUPPORTED;

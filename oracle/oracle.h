@@ -109,6 +109,7 @@ int oracle_select(const bvio_select_in* in, int32_t* out_ids, double* out_values
                   bvio_select_summary* summary);
 /* oracle_select with the candidates back-projected from an explicit x_{k+1} (state_k1_, feature_selector.cpp:247-250)
  * instead of horizon[1]: FeatureSelector::select in ground-truth horizon mode.  Not yet in the C-ABI. */
+int oracle_window_omega_prior(const bvio_window* w, const bvio_opts* opts, double* omega9);
 int oracle_select_k1(const bvio_select_in* in, const double k1_pos[3], const double k1_quat[4], int32_t* out_ids,
                      double* out_values, bvio_select_summary* summary);
 /* Utility::logdet(M, true), utility.h:143-167 */

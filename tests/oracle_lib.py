@@ -35,6 +35,7 @@ def load():
     L.oracle_cost.argtypes = [C.POINTER(abi.WindowS), C.POINTER(abi.Opts)]
     L.oracle_cost.restype = d
     L.oracle_linearize.argtypes = [C.POINTER(abi.WindowS), C.POINTER(abi.Opts), dp, dp, dp, dp, dp]
+    L.oracle_window_omega_prior.argtypes = [C.POINTER(abi.WindowS), C.POINTER(abi.Opts), dp]
     L.oracle_optimize.argtypes = [C.POINTER(abi.WindowS), C.POINTER(abi.Opts), C.POINTER(abi.Summary)]
     L.oracle_double2vector.argtypes = [dp, i32, dp, dp]
     L.oracle_double2vector.restype = None

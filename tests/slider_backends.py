@@ -33,6 +33,11 @@ class OracleBackend:
     def marginalize(self, w, flag, opts=None):
         return self.abi.call_marginalize(self.orc.oracle_marginalize, w, flag, opts=self.abi.default_opts(**(opts or {})))
 
+    def omega_prior(self, w, opts=None):
+        h, om = self.abi.WindowHandle(w), np.zeros(81)
+        assert self.orc.oracle_window_omega_prior(C.byref(h.s), C.byref(self.abi.default_opts(**(opts or {}))), self.abi.dptr(om)) == 0
+        return om.reshape(9, 9)
+
     def select(self, prob):
         abi = self.abi
         h, ss = abi.SelectHandle(prob), abi.SelectSummary()

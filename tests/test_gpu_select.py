@@ -158,3 +158,25 @@ def test_select_exact_duplicates_name_the_larger_id_first(env):
         order = {int(i): k for k, i in enumerate(ig[:n])}
         both = [(int(p.cand_id[a]), int(p.cand_id[b])) for a, b in pairs if int(p.cand_id[a]) in order and int(p.cand_id[b]) in order]
         assert all(order[b] < order[a] for a, b in both)
+
+
+@pytest.mark.parametrize("seed,K,L,relo", [(0, 11, 150, False), (1, 11, 1500, False), (2, 6, 40, False), (3, 11, 80, True)])
+def test_window_omega_prior_matches_oracle(env, seed, K, L, relo):
+    """bvio_window_omega_prior (the window's information on position / velocity / accelerometer bias of its newest frame,
+    the opt-in Omega_PRIOR of the selector) against the oracle's dense Schur complement."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=seed, K=K, L=L)
+    if relo:
+        w = synth.add_relocalization(w, seed, local_index=4)
+    hw, o = abi.WindowHandle(w), abi.default_opts()
+    og, oo = np.zeros(81), np.zeros(81)
+    ctx.check(ctx.L.bvio_window_omega_prior(ctx.h, C.byref(hw.s), C.byref(o), abi.dptr(og)), "bvio_window_omega_prior")
+    assert orc.oracle_window_omega_prior(C.byref(hw.s), C.byref(o), abi.dptr(oo)) == 0
+    assert np.abs(og - oo).max() <= 1e-8 * np.abs(oo).max()
+    # and it is usable as bvio_select_in.omega_prior: the selection runs and differs from the I9 one in its log-dets
+    p = synth.make_select_problem(seed=seed, N=150, H=10, kappa=15)
+    ig, vg, sg, io, vo, so = _select_both(env, p)
+    p.omega_prior = og.reshape(9, 9)
+    ig2, vg2, sg2, io2, vo2, so2 = _select_both(env, p)
+    assert sg2.n_selected == so2.n_selected and ig2[:so2.n_selected].tolist() == io2[:so2.n_selected].tolist()
+    assert abs(sg2.final_logdet - sg.final_logdet) > 1.0

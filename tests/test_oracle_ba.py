@@ -387,3 +387,27 @@ def test_estimate_td_recovers_time_offset(pkg, oracle, strategy):
     h0, s0 = abi.WindowHandle(w), abi.Summary()
     assert oracle.oracle_optimize(C.byref(h0.s), C.byref(o0), C.byref(s0)) == 0
     assert s0.final_cost > 5 * s.final_cost
+
+
+def test_window_omega_prior_is_the_schur_complement(pkg, oracle):
+    """oracle_window_omega_prior (Omega_PRIOR for the selector from the back end's window) against numpy on the oracle's
+    own reduced matrix: S_aa - S_ab S_bb^-1 S_ba for a = (position, velocity, accelerometer bias) of the newest frame;
+    symmetric positive definite, and far from the reference's I9."""
+    import ctypes as C
+    abi, synth = pkg.abi, pkg.synth
+    for seed, K, L in ((0, 11, 150), (1, 6, 40)):
+        w = synth.make_window(seed=seed, K=K, L=L)
+        hw, o = abi.WindowHandle(w), abi.default_opts()
+        n = 15 * K
+        S, g, h, b, c = np.zeros((n, n)), np.zeros(n), np.zeros(L), np.zeros(L), np.zeros(1)
+        assert oracle.oracle_linearize(C.byref(hw.s), C.byref(o), abi.dptr(S), abi.dptr(g), abi.dptr(h), abi.dptr(b), abi.dptr(c)) == 0
+        base = 15 * (K - 1)
+        a = np.array([base, base + 1, base + 2, base + 6, base + 7, base + 8, base + 9, base + 10, base + 11])
+        rest = np.array([i for i in range(n) if i not in set(a.tolist())])
+        want = S[np.ix_(a, a)] - S[np.ix_(a, rest)] @ np.linalg.solve(S[np.ix_(rest, rest)], S[np.ix_(rest, a)])
+        om = np.zeros(81)
+        assert oracle.oracle_window_omega_prior(C.byref(hw.s), C.byref(o), abi.dptr(om)) == 0
+        om = om.reshape(9, 9)
+        assert np.abs(om - want).max() <= 1e-8 * np.abs(want).max()
+        assert np.abs(om - om.T).max() <= 1e-9 * np.abs(om).max() and np.linalg.eigvalsh(0.5 * (om + om.T)).min() > 0
+        assert np.abs(om - np.eye(9)).max() > 10.0
