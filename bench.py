@@ -375,7 +375,7 @@ def cpu_stream(pkg, orc, abi, frames, max_feats, H, track_loss=0.0):
 def run_ours(args, rank, world, local_rank):
     # synthetic sessions first: forked numpy workers must not inherit a CUDA context
     t_pool = time.perf_counter()
-    sessions = make_sessions(POOL, max(1, min(16, (os.cpu_count() or 1) // max(world, 1))))
+    sessions = make_sessions(args.pool, max(1, min(16, (os.cpu_count() or 1) // max(world, 1))))
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -434,9 +434,9 @@ def run_ours(args, rank, world, local_rank):
     ba_value = dl["iters_total"] / (dl["ms_total"] * 1e-3)
     lin_ms, solve_ms, cost_ms = dl["lin_ms"], dl["solve_ms"], dl["cost_ms"]
     n_prior = pool[0].prior["n"]
-    alg_bytes_iter = sum(ba_algorithmic_bytes(pool[i % POOL], pool[i % POOL].prior["n"], 15 * K_FRAMES) for i in range(B))
+    alg_bytes_iter = sum(ba_algorithmic_bytes(pool[i % len(pool)], pool[i % len(pool)].prior["n"], 15 * K_FRAMES) for i in range(B))
     lin_bytes = alg_bytes_iter - 8 * 15 * K_FRAMES * B      # everything but the delta-x write is read by linearize
-    lin_flops = sum(ba_linearize_flops(pool[i % POOL]) for i in range(B))
+    lin_flops = sum(ba_linearize_flops(pool[i % len(pool)]) for i in range(B))
 
     # ---- selector, inputs resident in HBM: config 4 (H = 10) and the reference's compile-time horizon (H = 13)
     sel = time_selector(ctx, abi, synth, SEL_N, SEL_H, SEL_KAPPA, args.steps, args.warmup, stream, barrier, max_over_ranks, world > 1)
@@ -608,6 +608,7 @@ def main():
     ap.add_argument("--stream-frames", type=int, default=10000,
                     help="frames of the closed-loop latency leg (0 = skip; BASELINE configs[4] asks for 10000)")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-window latency leg")
+    ap.add_argument("--pool", type=int, default=POOL, help="distinct windows in the pool (profiling runs use a small one)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
