@@ -1013,9 +1013,8 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
       }
       st[24] = cc[0]; st[25] = cc[1]; st[26] = sr * r0; st[27] = sr * r1;
       double* wo = sW + lc * WS + 6 * fj;
-      double* wg = bt.w + (size_t)ko * 6;
 #pragma unroll
-      for (int k = 0; k < 6; k++) { const double v = st[12 + k] * cc[0] + st[18 + k] * cc[1]; wo[k] = v; wg[k] = v; }
+      for (int k = 0; k < 6; k++) wo[k] = st[12 + k] * cc[0] + st[18 + k] * cc[1];   // (goes to HBM after A2, coalesced)
     }
     __syncthreads();
     // ---- A2: two threads per landmark sum over its factors: A^T c (the anchor's w, 3 components each), and
@@ -1034,8 +1033,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
         hb += half ? c0 * st[26] + c1 * st[27] : c0 * c0 + c1 * c1;
       }
       double* wo = sW + lc * WS + 6 * sAnc[lc] + o3;
-      double* wg = bt.w + (size_t)sO0[lc] * 6 + o3;
-      wo[0] = a0; wo[1] = a1; wo[2] = a2; wg[0] = a0; wg[1] = a1; wg[2] = a2;
+      wo[0] = a0; wo[1] = a1; wo[2] = a2;
       if (half) {
         sW[lc * WS + K6] = hb;                       // column 6K of W: b_l => row 6K of P1 = Schur gradient term
         gmax_t = fmax(gmax_t, fabs(hb));
@@ -1056,6 +1054,17 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
       }
     }
     __syncthreads();
+    // ---- the chunk's w rows to HBM (ba_cost / ba_dogleg back-substitute the depths with them): consecutive threads write
+    //      consecutive doubles of the [observation][6] array -- whole 32-byte sectors per store instruction.  (One 48-byte
+    //      store per factor thread left the L2 with partially written sectors: 2.2x the bytes on the DRAM write side.)
+    for (int e = tid; e < nfac * 6; e += BA_THREADS) {
+      const int slot = e / 6, k = e - 6 * slot, lc = sFl[slot];
+      bt.w[(size_t)(sO0[lc] + 1 + slot - sFirst[lc]) * 6 + k] = sW[lc * WS + 6 * sFp[slot] + k];
+    }
+    for (int e = tid; e < nl * 6; e += BA_THREADS) {
+      const int lc = e / 6, k = e - 6 * lc;
+      bt.w[(size_t)sO0[lc] * 6 + k] = sW[lc * WS + 6 * sAnc[lc] + k];
+    }
     // ---- AtA(q) partials first (their reduction overlaps the other products)
     int nq = 0;
     for (int q = 0; q < K; q++) {
@@ -2555,7 +2564,7 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
       for (int k = 0; k < m; k++) s -= Tm[i * 16 + k] * A[(size_t)ma.dropidx[k] * M + ma.keepidx[j]];
     }
     Ar[i * ld + j] = s;
-    Vr[i * ld + j] = (i == j) ? 1.0 : 0.0;
+    Vr[i * ne + j] = (i == j) ? 1.0 : 0.0;        // V is kept TRANSPOSED with row stride ne: Vr[c * ne + k] = V(k, c)
   }
   for (int i = tid; i < ne; i += nt) {
     double s = 0;
@@ -2651,15 +2660,17 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
     while ((bI + 1) * (bI + 2) / 2 <= tid) bI++;
     bJ = tid - bI * (bI + 1) / 2;
   }
-  constexpr int VI = 4;
-  int vpr[VI], vk[VI];                          // this thread's (pair, row) items of V
+  // V <- V J: an item is (pair, two consecutive rows); with V stored transposed the two columns of a pair are two
+  // contiguous runs, read and written as double2 (conflict-free, half the shared-memory instructions)
+  constexpr int VI = 2;
+  int vpr[VI], vk[VI];                          // this thread's (pair, row-pair) items of V
 #pragma unroll
   for (int u = 0; u < VI; u++) {
     const int e = tid + u * nt;
-    vpr[u] = e < half * ne ? e / ne : -1;
-    vk[u] = e < half * ne ? e - (e / ne) * ne : 0;
+    vpr[u] = e < half * half ? e / half : -1;
+    vk[u] = e < half * half ? 2 * (e - (e / half) * half) : 0;
   }
-  const bool v_more = half * ne > VI * nt;
+  const bool v_more = half * half > VI * nt;
   for (; sweeps < 40 && ne >= 2; sweeps++) {
     double off = 0, dg = 0;
     for (int e = tid; e < ne * ne; e += nt) {
@@ -2715,17 +2726,22 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
         if (vpr[u] < 0) continue;
         const int2 a = pq[vpr[u]];
         const double2 r = rot[vpr[u]];
-        double* row = Vr + vk[u] * ld;
-        const double vkp = row[a.x], vkq = row[a.y];
-        row[a.x] = r.x * vkp - r.y * vkq; row[a.y] = r.y * vkp + r.x * vkq;
+        double2* cp = reinterpret_cast<double2*>(Vr + a.x * ne + vk[u]);
+        double2* cq = reinterpret_cast<double2*>(Vr + a.y * ne + vk[u]);
+        const double2 vp = *cp, vq = *cq;
+        *cp = make_double2(r.x * vp.x - r.y * vq.x, r.x * vp.y - r.y * vq.y);
+        *cq = make_double2(r.y * vp.x + r.x * vq.x, r.y * vp.y + r.x * vq.y);
       }
       if (v_more)
-        for (int e = tid + VI * nt; e < half * ne; e += nt) {
-          const int pr = e / ne, k = e - pr * ne;
+        for (int e = tid + VI * nt; e < half * half; e += nt) {
+          const int pr = e / half, k = 2 * (e - pr * half);
           const int2 a = pq[pr];
           const double2 r = rot[pr];
-          const double vkp = Vr[k * ld + a.x], vkq = Vr[k * ld + a.y];
-          Vr[k * ld + a.x] = r.x * vkp - r.y * vkq; Vr[k * ld + a.y] = r.y * vkp + r.x * vkq;
+          double2* cp = reinterpret_cast<double2*>(Vr + a.x * ne + k);
+          double2* cq = reinterpret_cast<double2*>(Vr + a.y * ne + k);
+          const double2 vp = *cp, vq = *cq;
+          *cp = make_double2(r.x * vp.x - r.y * vq.x, r.x * vp.y - r.y * vq.y);
+          *cq = make_double2(r.y * vp.x + r.x * vq.x, r.y * vp.y + r.x * vq.y);
         }
       __syncthreads();
     }
@@ -2735,11 +2751,11 @@ __global__ void __launch_bounds__(MARG_THREADS, 1) ba_marginalize_kernel(BaBatch
   for (int e = tid; e < n * n; e += nt) {
     int i = e / n, k = e - i * n;       // column-major J(k, i) at [i*n + k]
     double lam = Ar[k * ld + k];
-    ma.out_jac[e] = (lam > 1e-8 ? sqrt(lam) : 0.0) * Vr[i * ld + k];
+    ma.out_jac[e] = (lam > 1e-8 ? sqrt(lam) : 0.0) * Vr[k * ne + i];
   }
   for (int k = tid; k < n; k += nt) {
     double lam = Ar[k * ld + k], s = 0;
-    for (int i = 0; i < n; i++) s += Vr[i * ld + k] * br[i];
+    for (int i = 0; i < n; i++) s += Vr[k * ne + i] * br[i];
     ma.out_res[k] = (lam > 1e-8 ? sqrt(1.0 / lam) : 0.0) * s;
   }
   if (tid == 0) { ma.status[0] = sweeps; phase[6] = global_ns(); }
