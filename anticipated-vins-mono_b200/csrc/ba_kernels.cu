@@ -1013,8 +1013,9 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
       }
       st[24] = cc[0]; st[25] = cc[1]; st[26] = sr * r0; st[27] = sr * r1;
       double* wo = sW + lc * WS + 6 * fj;
+      double* wg = bt.w + (size_t)ko * 6;
 #pragma unroll
-      for (int k = 0; k < 6; k++) wo[k] = st[12 + k] * cc[0] + st[18 + k] * cc[1];   // (goes to HBM after A2, coalesced)
+      for (int k = 0; k < 6; k++) { const double v = st[12 + k] * cc[0] + st[18 + k] * cc[1]; wo[k] = v; wg[k] = v; }
     }
     __syncthreads();
     // ---- A2: two threads per landmark sum over its factors: A^T c (the anchor's w, 3 components each), and
@@ -1033,7 +1034,8 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
         hb += half ? c0 * st[26] + c1 * st[27] : c0 * c0 + c1 * c1;
       }
       double* wo = sW + lc * WS + 6 * sAnc[lc] + o3;
-      wo[0] = a0; wo[1] = a1; wo[2] = a2;
+      double* wg = bt.w + (size_t)sO0[lc] * 6 + o3;
+      wo[0] = a0; wo[1] = a1; wo[2] = a2; wg[0] = a0; wg[1] = a1; wg[2] = a2;
       if (half) {
         sW[lc * WS + K6] = hb;                       // column 6K of W: b_l => row 6K of P1 = Schur gradient term
         gmax_t = fmax(gmax_t, fabs(hb));
@@ -1054,17 +1056,6 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
       }
     }
     __syncthreads();
-    // ---- the chunk's w rows to HBM (ba_cost / ba_dogleg back-substitute the depths with them): consecutive threads write
-    //      consecutive doubles of the [observation][6] array -- whole 32-byte sectors per store instruction.  (One 48-byte
-    //      store per factor thread left the L2 with partially written sectors: 2.2x the bytes on the DRAM write side.)
-    for (int e = tid; e < nfac * 6; e += BA_THREADS) {
-      const int slot = e / 6, k = e - 6 * slot, lc = sFl[slot];
-      bt.w[(size_t)(sO0[lc] + 1 + slot - sFirst[lc]) * 6 + k] = sW[lc * WS + 6 * sFp[slot] + k];
-    }
-    for (int e = tid; e < nl * 6; e += BA_THREADS) {
-      const int lc = e / 6, k = e - 6 * lc;
-      bt.w[(size_t)sO0[lc] * 6 + k] = sW[lc * WS + 6 * sAnc[lc] + k];
-    }
     // ---- AtA(q) partials first (their reduction overlaps the other products)
     int nq = 0;
     for (int q = 0; q < K; q++) {
