@@ -13,6 +13,20 @@
 
 using namespace bvio;
 
+// host threads for packing / validating / scattering large batches: at most 16, and this process's share of the cores
+// when several ranks live on one node (LOCAL_WORLD_SIZE is what torchrun / mpirun wrappers export); BVIO_PACK_THREADS
+// overrides.  (Round 1: 8 ranks x 16 packing threads on a 32-core host cost 20 % of the end-to-end scaling.)
+static int pack_threads() {
+  static int cached = 0;
+  if (cached) return cached;
+  int n = (int)std::max(1u, std::thread::hardware_concurrency());
+  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(lw); if (w > 1) n = std::max(1, n / w); }
+  n = std::min(n, 16);
+  if (const char* ev = getenv("BVIO_PACK_THREADS")) n = std::max(1, std::min(atoi(ev), 64));
+  cached = n;
+  return n;
+}
+
 struct bvio_batch {
   BaBatch bt;
   Slab slab;
@@ -203,7 +217,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   int total_L = 0, total_obs = 0, nmax = 1, maxL = 0;
   {
     // structural validation walks every observation: spread large batches over host threads
-    const int nthreads = B < 16 ? 1 : (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    const int nthreads = B < 16 ? 1 : pack_threads();
     std::vector<int> rcs(nthreads, BVIO_OK);
     std::vector<const char*> msgs(nthreads, "");
     auto work = [&](int t) {
@@ -425,7 +439,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
     }
   };
   {
-    int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    int nthreads = pack_threads();
     if (B < 16) nthreads = 1;
     if (nthreads <= 1) {
       for (int b = 0; b < B; b++) pack(b);
@@ -563,7 +577,7 @@ static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, b
       if (bt.est_td) w.para_td[0] = tdo[b];
   };
   if (windows && bt.B >= 64) {
-    const int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    const int nthreads = pack_threads();
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; t++) th.emplace_back([&, t]() { for (int b = t; b < bt.B; b += nthreads) scatter(b); });
     for (auto& x : th) x.join();

@@ -75,6 +75,7 @@ def main():
         launches_md(a.launches, os.path.join(pd, f"{a.tag}_launches.md"))
     traffic_path = os.path.join(pd, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    seen_traffic = set()
     if a.rep:
         with open(os.path.join(pd, f"{a.tag}_kernels.md"), "w") as f:
             f.write(f"# ncu --set full --clock-control none ({a.tag})\n\n{a.note}\n\n")
@@ -97,7 +98,9 @@ def main():
                         def b(k):
                             v, u = float(r[idx[k]].replace(",", "")), units[idx[k]].lower()
                             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
-                        traffic[name] = int(b("dram__bytes_read.sum") + b("dram__bytes_write.sum"))
+                        if name not in seen_traffic:        # the first --rep that holds a kernel wins (list the headline capture first)
+                            traffic[name] = int(b("dram__bytes_read.sum") + b("dram__bytes_write.sum"))
+                            seen_traffic.add(name)
                     except Exception:
                         pass
         json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
