@@ -878,7 +878,9 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 __host__ __device__ inline int mm_ntile(int K) { return (6 * K + 1 + 7) / 8; }
-__host__ __device__ inline int mm_wstride(int K) { int ws = 8 * mm_ntile(K); return (ws % 16 == 0) ? ws + 8 : ws; }
+// row stride of W~ in doubles, = 4 or 12 (mod 16): the DMMA fragment loads (lane (g, tq) reads row tq, column g of a tile)
+// then hit 16 distinct 8-byte banks per half-warp (a stride of 8 mod 16 put rows tq and tq + 2 on the same banks: 2-way)
+__host__ __device__ inline int mm_wstride(int K) { return 8 * mm_ntile(K) + 4; }
 
 template <int TM, int WSC>   // WSC: compile-time row stride of W~ (0 = runtime) so that P1's loads take immediates
 __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch bt) {
@@ -1965,7 +1967,7 @@ int ba_configure(void) {
     BVIO_LIN_ATTR(1, 1) BVIO_LIN_ATTR(2, 1) BVIO_LIN_ATTR(3, 1) BVIO_LIN_ATTR(4, 1)
     BVIO_LIN_ATTR(1, 2) BVIO_LIN_ATTR(2, 2) BVIO_LIN_ATTR(3, 2) BVIO_LIN_ATTR(4, 2)
 #undef BVIO_LIN_ATTR
-    if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 76>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
@@ -2010,7 +2012,7 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
     size_t sm1 = ba_linearize_mma_smem_bytes(bt.K);
     if (s1b > sm1) sm1 = s1b;
     const int NT = mm_ntile(bt.K);
-    if (NT * (NT + 1) / 2 <= 48 && mm_wstride(bt.K) == 72) ba_linearize_mma_kernel<6, 72><<<grid, BA_THREADS, sm1, st>>>(bt);
+    if (NT * (NT + 1) / 2 <= 48 && mm_wstride(bt.K) == 76) ba_linearize_mma_kernel<6, 76><<<grid, BA_THREADS, sm1, st>>>(bt);
     else if (NT * (NT + 1) / 2 <= 48) ba_linearize_mma_kernel<6, 0><<<grid, BA_THREADS, sm1, st>>>(bt);
     else ba_linearize_mma_kernel<10, 0><<<grid, BA_THREADS, sm1, st>>>(bt);
   }
