@@ -66,6 +66,7 @@ struct BaBatch {                  // all pointers are device pointers
   int strategy;                   // BVIO_STRATEGY_LM / BVIO_STRATEGY_DOGLEG
   int solve_wide;                 // fewer windows than SMs: ba_solve with 512 threads per window
   int use_mma;                    // linearize with the FP64 tensor-core (DMMA) kernel (extrinsics fixed)
+  int use_ws;                     // ... its warp-specialised variant (one 512-thread CTA per SM; throughput mode)
   int est_ex;                     // estimate_extrinsic: +6 dims, extrinsic block = pseudo-frame K of the visual layout
   int est_td;                     // estimate_td: +1 dim (after the extrinsic block), pseudo-frame K + est_ex
   double sqrt_info, cauchy_a, G[3];
@@ -138,5 +139,6 @@ size_t ba_marginalize_part_doubles(int K, int G);   // scratch of the factor ker
 int ba_marginalize_groups(int n0);                  // CTAs of the factor kernel for n0 landmarks anchored at the dropped frame
 int ba_launch_marginal9(const double* S, int np, int frame, double* out81, int* status, cudaStream_t st);
 int ba_configure(void);   // cudaFuncSetAttribute for the big-smem kernels; returns cudaError_t
+void ba_ws_prof_dump(void);   // development builds (make WSPROF=1) print the warp-specialised linearize kernel's phase cycles; otherwise a no-op
 
 }  // namespace bvio

@@ -107,6 +107,7 @@ void bvio_destroy(bvio_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  bvio::ba_ws_prof_dump();
   bvio_sel_ctx_destroy(ctx);
   ctx->ba_cache.release();
   for (int i = 0; i < bvio_ctx::PIPE; i++) ctx->ba_pipe[i].release();
@@ -247,6 +248,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   bb->Kc = Kc; bb->relo = relo;
   bt.solve_wide = B < ctx->sm_count && !getenv("BVIO_SOLVE_NARROW");
   bt.use_mma = XB == 0 && !getenv("BVIO_LEGACY_LINEARIZE");
+  bt.use_ws = bt.use_mma && (getenv("BVIO_LIN_WS") ? atoi(getenv("BVIO_LIN_WS")) != 0 : !bt.solve_wide);
   bt.chunk_l = ba_pick_chunk(K, XB);
   int T = (maxL + 2 * bt.chunk_l - 1) / (2 * bt.chunk_l);   // >= 2 chunks per tile when there is a choice
   int Tcap = std::max(1, (10 * ctx->sm_count + B - 1) / B);   // ~5 waves of 2 CTAs/SM: measured optimum (tile record traffic vs tail)

@@ -20,6 +20,7 @@
 //   ba_marginalize    MarginalizationInfo::{preMarginalize, marginalize} (marginalization_factor.cpp:109-297)
 //
 // All reductions run in a fixed order: results are bit-reproducible run to run.
+#include <cstdio>
 #include <mutex>
 #include "ba.h"
 #include <float.h>
@@ -406,13 +407,14 @@ __global__ void ba_finish_kernel(BaBatch bt) {
 // =============================================================================================
 // f0 .. f1: which IMU factors (0-based: factor f links frame f to f + 1) this CTA evaluates; do_prior: also the prior.
 // One CTA does everything for large batches; with fewer windows than SMs (latency mode) every factor gets its own CTA.
-__device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* sm, int f0, int f1, bool do_prior) {
-  const int K = bt.K, nf = K - 1;
-  double* sJ = sm;                      // [nf][450] raw Jacobians
+__device__ void imu_prior_linearize(const BaBatch& bt, int w, int cur, double* sm, int f0, int f1, bool do_prior, bool compact = false) {
+  // compact: shared memory holds only the factors f0 .. f1-1 (slot = f - f0) instead of all K - 1
+  const int K = bt.K, nf = compact ? f1 - f0 : K - 1, fo = compact ? f0 : 0;
+  double* sJ = sm - (size_t)fo * 450;   // [nf][450] raw Jacobians (indexed by the factor number)
   double* sJ2 = sJ + nf * 450;          // [nf][450] whitened
-  double* sR = sJ2 + nf * 450;          // [nf][15] raw
+  double* sR = sm + (size_t)nf * 900 - (size_t)fo * 15;   // [nf][15] raw
   double* sR2 = sR + nf * 15;           // [nf][15] whitened
-  double* sdx = sR2 + nf * 15;          // [nmax]
+  double* sdx = sm + (size_t)nf * 930;  // [nmax]
   double* spr = sdx + bt.nmax;          // [nmax]
   const double* pose = bt.pose[cur];
   const double* sb = bt.sb[cur];
@@ -1197,6 +1199,452 @@ size_t ba_linearize_mma_smem_bytes(int K) {
   return (bytes + 15) & ~size_t(15);
 }
 
+// IMU factors and marginalization prior of every window, one small CTA per (window, factor) and per (window, prior):
+// the companion launch of ba_linearize_ws_kernel, whose CTAs fill an SM each and carry the visual tiles only.
+constexpr int IMU_THREADS = 128;
+__global__ void __launch_bounds__(IMU_THREADS, 4) ba_imu_prior_kernel(BaBatch bt) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.y, t = blockIdx.x;
+  const BaCtrl* ctrl = bt.ctrl + w;
+  if (ctrl->done) return;
+  if (t == 0) imu_prior_linearize(bt, w, ctrl->cur, sm, 0, 0, true, true);
+  else imu_prior_linearize(bt, w, ctrl->cur, sm, t - 1, t, false, true);
+}
+
+// =============================================================================================
+// Warp-specialised variant (throughput mode): the same stages as ba_linearize_mma_kernel, but the factor evaluation
+// (A0-A2: FP64 pipe, register-hungry) and the Gram products (DMMA: tensor pipe, accumulators in registers) run in
+// DIFFERENT warps of one 512-thread CTA per SM and overlap chunk by chunk through double-buffered shared memory:
+//   warps 0-7   producers: chunk c -> buffer c & 1 (slot tables, factor records, W~ rows, 1/(h+d)), h / b / w to HBM
+//   warps 8-15  consumers: AtA, P2b, P1, P2a over buffer c & 1; tile record to HBM at the end
+// Hand-over with named barriers (bar.arrive by the side that is done, bar.sync by the side that waits): FULL[b] / EMPTY[b],
+// plus one barrier id per role for its internal phases.  The producers no longer carry the 36 accumulator registers
+// through the evaluation, the consumers never wait for an evaluation they do not depend on.
+// =============================================================================================
+constexpr int WS_THREADS = 512, WS_ROLE = 256;
+#ifdef BVIO_WS_PROF   // development build only (make WSPROF=1): cycles per role / phase, summed over CTAs, printed at bvio_destroy
+__device__ unsigned long long g_ws_prof[16 + 16 * 16];   // [16 + 16 * (8 * role + warp) + phase] per-warp phase cycles
+#define WSP_T0() long long wsp_t = clock64()
+#define WSP_ADD(i) do { const long long n_ = clock64(); if (lane == 0) atomicAdd(&g_ws_prof[16 + 16 * (8 * role + wp) + (i)], (unsigned long long)(n_ - wsp_t)); wsp_t = n_; } while (0)
+#define WSP_CHUNK() atomicAdd(&g_ws_prof[15], 1ull)
+#else
+#define WSP_CHUNK() do {} while (0)
+#define WSP_T0() do {} while (0)
+#define WSP_ADD(i) do {} while (0)
+#endif
+enum { BAR_PROD = 1, BAR_CONS = 2, BAR_FULL0 = 3, BAR_EMPTY0 = 5 };
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct WsBuf {            // one chunk's staging area
+  double *fac, *w, *sc;
+  int *first, *nobs, *o0, *anc, *qlo, *qhi, *qlist, *meta;   // qlist: anchors present in the chunk, q | lq0 << 8 | lq1 << 16
+  short* slot;
+};
+// fac is preceded by one all-zero record (slot -1): masked fragment loads read it instead of branching
+__host__ __device__ inline size_t ws_buf_doubles(int WS) { return (size_t)(MM_NF + 1) * STG + 1 + (size_t)MM_CL * WS + MM_CL * 4; }
+__host__ __device__ inline size_t ws_buf_ints(void) { return 4 * (MM_CL + 2) + 3 * BVIO_KMAX + 8; }   // first / o0 hold MM_CL + 1 entries
+__host__ __device__ inline size_t ws_buf_shorts(int K) { return (size_t)((MM_CL + 8) * K + 1) & ~size_t(1); }
+
+template <int TM, int WSC>
+__global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch bt) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.y, t = blockIdx.x;
+  BaCtrl* ctrl = bt.ctrl + w;
+  if (ctrl->done) return;
+  const int cur = ctrl->cur;              // (the IMU factors and the prior: ba_imu_prior_kernel, launched beside this one)
+  const int K = bt.K, K6 = 6 * K, NPb = K * (K + 1) / 2, NT = mm_ntile(K), WS = WSC ? WSC : mm_wstride(K);
+  const int role = threadIdx.x >> 8, tid = threadIdx.x & (WS_ROLE - 1), lane = tid & 31, wp = tid >> 5, g = lane >> 2, tq = lane & 3;
+  // ---- shared memory: common part, then the two chunk buffers (doubles, ints, shorts, bytes)
+  double* sFr = sm;                                  // [K*FR]
+  double* sEx = sFr + K * FR;                        // [FR]
+  double* sRed = sEx + FR;                           // [32]
+  double* sAcc = sRed + 32;                          // [NPb*36]
+  double* sGb = sAcc + NPb * 36;                     // [K6]
+  double* sGr = sGb + K6;                            // [K6]
+  double* sDg = sGr + K6;                            // [K6]
+  double* sAtA = sDg + K6;                           // [K][8 warps][28] lower triangle of the split-K AtA partials
+  double* dbl = sAtA + K * 8 * 28;
+  int* ints = reinterpret_cast<int*>(dbl + 2 * ws_buf_doubles(WS));
+  short* shorts = reinterpret_cast<short*>(ints + 2 * ws_buf_ints());
+  auto buffer = [&](int b) {
+    WsBuf u;
+    u.fac = dbl + b * ws_buf_doubles(WS) + STG; u.w = u.fac + MM_NF * STG + 1; u.sc = u.w + MM_CL * WS;
+    u.first = ints + b * ws_buf_ints(); u.nobs = u.first + MM_CL + 2; u.o0 = u.nobs + MM_CL + 2; u.anc = u.o0 + MM_CL + 2;
+    u.qlo = u.anc + MM_CL + 2; u.qhi = u.qlo + BVIO_KMAX; u.qlist = u.qhi + BVIO_KMAX; u.meta = u.qlist + BVIO_KMAX;
+    u.slot = shorts + b * ws_buf_shorts(K);
+    return u;
+  };
+
+  for (int i = threadIdx.x; i < NPb * 36 + 3 * K6 + K * 8 * 28; i += WS_THREADS) sAcc[i] = 0.0;
+  if (threadIdx.x < 2 * STG) dbl[(threadIdx.x / STG) * ws_buf_doubles(WS) + threadIdx.x % STG] = 0.0;   // the zero records
+  stage_frames(bt, w, bt.pose[cur], bt.exs[cur], sFr, sEx);
+  int l0, l1;
+  tile_range(bt, w, t, l0, l1);
+  __syncthreads();                                   // the last CTA-wide barrier: the roles part here
+
+  if (role == 0) {
+    // =========================================== producers ===========================================
+    const double dfac = damp_factor(ctrl->radius, ctrl->mu, bt.strategy);
+    const int first = ctrl->first;
+    const double* invd = bt.invd[cur];
+    double cost_t = 0, gmax_t = 0;
+    int c = 0;
+    WSP_T0();
+    // chunk extents are computed one chunk ahead (every warp on its own): lane j holds lm_off[lb + j + 1] and [lb + j + 33]
+    int obase = l0 < l1 ? bt.lm_off[l0] : 0, v1 = 0, v2 = 0;
+    if (l0 + lane + 1 <= l1) v1 = bt.lm_off[l0 + lane + 1];
+    if (lane + 33 <= MM_CL && l0 + lane + 33 <= l1) v2 = bt.lm_off[l0 + lane + 33];
+    for (int lb = l0; lb < l1; c++) {
+      const int b = c & 1;
+      const WsBuf u = buffer(b);
+      // chunk extent: as many landmarks as fit MM_NF factor slots (and MM_CL rows)
+      const int j1 = lane + 1, j2 = lane + 33;
+      const bool p1 = lb + j1 <= l1 && (v1 - obase - j1) <= MM_NF;
+      const bool p2 = j2 <= MM_CL && lb + j2 <= l1 && (v2 - obase - j2) <= MM_NF;
+      const int nl = __popc(__ballot_sync(0xffffffffu, p1)) + __popc(__ballot_sync(0xffffffffu, p2));
+      const int onext = nl <= 32 ? __shfl_sync(0xffffffffu, v1, (nl - 1) & 31) : __shfl_sync(0xffffffffu, v2, (nl - 33) & 31);
+      const int nfac = onext - obase - nl;
+      const int nl4 = (nl + 3) & ~3;
+      // first observation of landmarks lane and lane + 32 of this chunk (for the staging below), then prefetch the next extent
+      const int up1 = __shfl_up_sync(0xffffffffu, v1, 1), up2 = __shfl_up_sync(0xffffffffu, v2, 1), v1last = __shfl_sync(0xffffffffu, v1, 31);
+      const int oa = lane == 0 ? obase : up1, ob = lane == 0 ? v1last : up2;
+      const int na = v1 - oa, nb = v2 - ob;            // observations of landmarks lane / lane + 32
+      const int cur_obase = obase;
+      {
+        const int lbn = lb + nl;
+        obase = onext; v1 = 0; v2 = 0;
+        if (lbn + lane + 1 <= l1) v1 = bt.lm_off[lbn + lane + 1];
+        if (lane + 33 <= MM_CL && lbn + lane + 33 <= l1) v2 = bt.lm_off[lbn + lane + 33];
+      }
+      WSP_ADD(0);
+      if (c >= 2) bar_sync(BAR_EMPTY0 + b, WS_THREADS);          // the consumers are done with this buffer
+      WSP_ADD(1);
+      for (int i = tid; i < nl4 * WS; i += WS_ROLE) u.w[i] = 0.0;
+      for (int i = tid; i < (nl + 8) * K; i += WS_ROLE) u.slot[i] = -1;   // 8 pad rows: the pair loops need no bound check
+      if (tid < BVIO_KMAX) { u.qlo[tid] = MM_CL; u.qhi[tid] = 0; }
+      if (wp == 0) {                                   // per-landmark tables: first observation, first factor slot, track length
+        if (lane <= nl) { u.o0[lane] = oa; u.first[lane] = oa - cur_obase - lane; if (lane < nl) { u.nobs[lane] = na; u.anc[lane] = 0; } }
+        if (lane + 32 <= nl) { u.o0[lane + 32] = ob; u.first[lane + 32] = ob - cur_obase - lane - 32; if (lane + 32 < nl) { u.nobs[lane + 32] = nb; u.anc[lane + 32] = 0; } }
+        if (lane == 0) u.meta[0] = nl;
+      }
+      bar_sync(BAR_PROD, WS_ROLE);
+      WSP_ADD(2);
+      WSP_ADD(3);
+      // ---- A1: factor evaluation, one factor per thread
+      if (tid < nfac) {
+        int lc = 0;                                    // the landmark of factor slot tid: the last one with first[lc] <= tid
+        for (int hi = nl; hi - lc > 1;) { const int mid = (lc + hi) >> 1; if (u.first[mid] <= tid) lc = mid; else hi = mid; }
+        const int l = lb + lc, fs = u.first[lc];
+        const int o0 = u.o0[lc], ko = o0 + 1 + (tid - fs);
+        const int fi = bt.obs_frame[o0], fj = bt.obs_frame[ko];
+        const double lam = invd[l];
+        const double2 pi = bt.obs_xy[o0], pj = bt.obs_xy[ko];
+        u.slot[lc * K + fj] = (short)tid;
+        if (tid == fs) { u.anc[lc] = fi; atomicMin(&u.qlo[fi], lc); atomicMax(&u.qhi[fi], lc + 1); }
+        const double* Fi = sFr + fi * FR;
+        const double* Fj = sFr + fj * FR;
+        ProjGeom gm = proj_geom(Fi, Fj, sEx, pi.x, pi.y, lam);
+        const double inv = 1.0 / gm.pcj.z, si = bt.sqrt_info;
+        const double r0 = si * (gm.pcj.x * inv - pj.x), r1 = si * (gm.pcj.y * inv - pj.y);
+        const double red[2][3] = {{si * inv, 0.0, -si * gm.pcj.x * inv * inv}, {0.0, si * inv, -si * gm.pcj.y * inv * inv}};
+        double Gm[2][3], Q[2][3];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++)
+            Gm[a][cc] = red[a][0] * sEx[cc * 3 + 0] + red[a][1] * sEx[cc * 3 + 1] + red[a][2] * sEx[cc * 3 + 2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) Q[a][cc] = Gm[a][0] * Fj[cc * 3 + 0] + Gm[a][1] * Fj[cc * 3 + 1] + Gm[a][2] * Fj[cc * 3 + 2];
+        double rho0, rho1;
+        cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
+        cost_t += 0.5 * rho0;
+        const double sr = sqrt(rho1);
+        double* st = u.fac + (size_t)tid * STG;
+        const d3 dimu = gm.pimu_i - d3{sEx[9], sEx[10], sEx[11]};
+        double cc2[2], Bv[2][6];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+          const d3 uu = mtv3(Fi, d3{Q[a][0], Q[a][1], Q[a][2]});              // Ri^T Q[a]^T
+          const d3 jr = cross3(gm.pimu_i, uu);                               // -(Q Ri [pts_imu_i]x) row
+          const d3 jjr = cross3(d3{Gm[a][0], Gm[a][1], Gm[a][2]}, gm.pimu_j); // (Gm [pts_imu_j]x) row
+          st[a * 6 + 0] = sr * Q[a][0]; st[a * 6 + 1] = sr * Q[a][1]; st[a * 6 + 2] = sr * Q[a][2];
+          st[a * 6 + 3] = sr * jr.x; st[a * 6 + 4] = sr * jr.y; st[a * 6 + 5] = sr * jr.z;
+          Bv[a][0] = -sr * Q[a][0]; Bv[a][1] = -sr * Q[a][1]; Bv[a][2] = -sr * Q[a][2];
+          Bv[a][3] = sr * jjr.x; Bv[a][4] = sr * jjr.y; Bv[a][5] = sr * jjr.z;
+#pragma unroll
+          for (int k = 0; k < 6; k++) st[12 + a * 6 + k] = Bv[a][k];
+          cc2[a] = sr * (-dot3(uu, dimu) / lam);
+        }
+        st[24] = cc2[0]; st[25] = cc2[1]; st[26] = sr * r0; st[27] = sr * r1;
+        double* wo = u.w + lc * WS + 6 * fj;
+        double* wg = bt.w + (size_t)ko * 6;
+#pragma unroll
+        for (int k = 0; k < 6; k++) { const double v = Bv[0][k] * cc2[0] + Bv[1][k] * cc2[1]; wo[k] = v; wg[k] = v; }
+      }
+      bar_sync(BAR_PROD, WS_ROLE);
+      WSP_ADD(4);
+      // ---- A2: four threads per landmark: A^T c (the anchor's w, two components each of three threads), and on the
+      //      fourth h = sum c^T c with the damping of the eliminated depth (Ceres LevenbergMarquardtStrategy / dogleg mu,
+      //      Jacobi scaling) and b = sum c^T r.  Two independent accumulation chains per output.
+      if (tid == WS_ROLE - 1) {                        // anchors present in this chunk, for the consumers' loops
+        int n = 0;
+        for (int q = 0; q < K; q++) { const int a = u.qlo[q], e = u.qhi[q]; if (e > a) u.qlist[n++] = q | (a << 8) | (e << 16); }
+        u.meta[1] = n;
+      }
+      if (tid < 4 * nl) {
+        const int lc = tid >> 2, part = tid & 3, l = lb + lc;
+        const int nf = u.nobs[lc] - 1;
+        const double* st = u.fac + (size_t)u.first[lc] * STG;
+        const int ea = part < 3 ? 2 * part : 24, eb = part < 3 ? 6 + 2 * part : 25, ec = part < 3 ? 2 * part + 1 : 26, ed = part < 3 ? 7 + 2 * part : 27;
+        double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        for (int f = 0; f < nf; f++, st += STG) {
+          const double c0 = st[24], c1 = st[25];
+          x0 += st[ea] * c0; y0 += st[eb] * c1;
+          x1 += st[ec] * c0; y1 += st[ed] * c1;
+        }
+        const double va = x0 + y0, vb = x1 + y1;
+        if (part < 3) {
+          double* wo = u.w + lc * WS + 6 * u.anc[lc] + 2 * part;
+          double* wg = bt.w + (size_t)u.o0[lc] * 6 + 2 * part;
+          wo[0] = va; wo[1] = vb; wg[0] = va; wg[1] = vb;
+        } else {
+          const double h = va;
+          u.w[lc * WS + K6] = vb;                      // column 6K of W: b_l => row 6K of P1 = Schur gradient term
+          gmax_t = fmax(gmax_t, fabs(vb));
+          bt.b[l] = vb;
+          double sl2 = 1.0;
+          if (bt.jacobi_scaling) {
+            if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
+            else sl2 = bt.sl2[l];
+          }
+          const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, dfac);
+          double inv_hd = 1.0 / (h + ddl);
+          if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
+          u.sc[lc * 4] = inv_hd;
+          bt.h[l] = h;
+          if (first) bt.sl2[l] = sl2;
+        }
+      }
+      WSP_ADD(5);
+      __threadfence_block();
+      bar_arrive(BAR_FULL0 + b, WS_THREADS);           // chunk c is ready
+      WSP_ADD(6);
+      lb += nl;
+    }
+    // drain: leave no barrier half-complete (and the consumers' last reads behind us)
+    if (c >= 2) bar_sync(BAR_EMPTY0 + (c & 1), WS_THREADS);
+    if (c >= 1) bar_sync(BAR_EMPTY0 + ((c + 1) & 1), WS_THREADS);
+    // cost and gradient-max partials of this tile
+    cost_t = warp_sum(cost_t); gmax_t = warp_max(gmax_t);
+    if (lane == 0) { sRed[wp] = cost_t; sRed[8 + wp] = gmax_t; }
+    bar_sync(BAR_PROD, WS_ROLE);
+    if (tid == 0) {
+      double cs = 0, gm = sRed[8];
+      for (int i = 0; i < 8; i++) { cs += sRed[i]; gm = fmax(gm, sRed[8 + i]); }
+      double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(K);
+      const int REC = NPb * 36 + 3 * K6;
+      out[REC] = cs; out[REC + 1] = gm; out[REC + 2] = 0; out[REC + 3] = 0;
+    }
+    return;
+  }
+
+  // =========================================== consumers ===========================================
+  const int ntile = NT * (NT + 1) / 2;
+  int ti[TM], tj[TM];
+  double accW[TM][2];
+#pragma unroll
+  for (int s = 0; s < TM; s++) {
+    int idx = wp + 8 * s, i = 0;
+    ti[s] = -1; tj[s] = 0;
+    if (idx < ntile) {
+      while ((i + 1) * (i + 2) / 2 <= idx) i++;
+      ti[s] = 8 * i; tj[s] = 8 * (idx - i * (i + 1) / 2);
+    }
+    accW[s][0] = accW[s][1] = 0.0;
+  }
+  double accD[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+  int curq = -1;                                       // anchor frame the AtA partials belong to
+  double ata[4] = {0, 0, 0, 0};
+  // this warp's split-K partial of AtA(q) goes to its own shared-memory slot (no barrier); summed over the warps at the end
+  auto flush_ata = [&](int q) {
+    double* o = sAtA + (q * 8 + wp) * 28 + g * (g + 1) / 2 + 2 * tq;
+    if (g < 7 && 2 * tq <= g) o[0] += ata[0] + ata[2];
+    if (g < 7 && 2 * tq + 1 <= g) o[1] += ata[1] + ata[3];
+    ata[0] = ata[1] = ata[2] = ata[3] = 0.0;
+  };
+  // masked lanes of the fragment loads (rows 6 / 7 of a tile) read the zero record through a zero stride
+  const int mul7 = g < 7 ? STG : 0, mul6 = g < 6 ? STG : 0;
+  int c = 0;
+  WSP_T0();
+  for (int lb = l0; lb < l1; c++) {
+    const int b = c & 1;
+    const WsBuf u = buffer(b);
+    bar_sync(BAR_FULL0 + b, WS_THREADS);
+    WSP_ADD(8);
+    const int nl = u.meta[0], nl4 = (nl + 3) & ~3;
+    // ---- AtA(q): split-K partials stay in registers across chunks (landmarks arrive grouped by anchor, so q rarely
+    //      changes)
+    const int nq = u.meta[1];
+    for (int iq = 0; iq < nq; iq++) {
+      const int qe = u.qlist[iq], q = qe & 255, lq0 = (qe >> 8) & 255, lq1 = qe >> 16;
+      if (q != curq) {
+        if (curq >= 0) flush_ata(curq);
+        curq = q;
+      }
+      WSP_ADD(13);
+      {
+        // factor slots of the landmarks anchored at q are contiguous: [f0, f1)
+        const int f0 = u.first[lq0], f1 = u.first[lq1 - 1] + u.nobs[lq1 - 1] - 1;
+        const unsigned span = (unsigned)(f1 - f0);
+        const double* px = u.fac + (g < 6 ? 6 * (tq & 1) + g : g == 6 ? 26 + (tq & 1) : -STG);
+        for (int sb = (f0 & ~1) + 2 * wp; sb < f1; sb += 32) {   // warp-uniform trip count (mma.sync); 2 chains
+          const int s0 = sb + (tq >> 1), s1 = s0 + 16;
+          const int i0 = (unsigned)(s0 - f0) < span ? s0 : -1, i1 = (unsigned)(s1 - f0) < span ? s1 : -1;
+          const double x = px[i0 * mul7], y = px[i1 * mul7];
+          dmma884(ata[0], ata[1], x, x);
+          dmma884(ata[2], ata[3], y, y);
+        }
+      }
+      WSP_ADD(9);
+      // ---- P2b: blocks (p, q), p > q, one warp per p; four independent chains
+      for (int p = q + 1 + (7 - wp); p < K; p += 8) {
+        double d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const short* sl = u.slot + (lq0 + (tq >> 1)) * K + p;
+        const double* pf = u.fac + (g < 6 ? 6 * (tq & 1) + g : -STG);
+        for (int lc = lq0 + (tq >> 1); lc - (tq >> 1) < lq1; lc += 8, sl += 8 * K) {
+          double xa[4], xb[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int sj = lc + 2 * j < lq1 ? (int)sl[2 * j * K] : -1;
+            const double* st = pf + sj * mul6;
+            xa[j] = st[12]; xb[j] = st[0];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++) dmma884(d[2 * j], d[2 * j + 1], xa[j], xb[j]);
+        }
+        if (g < 6 && tq < 3) {
+          double* o = sAcc + tri(p, q) * 36 + g * 6 + 2 * tq;
+          o[0] += (d[0] + d[2]) + (d[4] + d[6]); o[1] += (d[1] + d[3]) + (d[5] + d[7]);
+        }
+      }
+      WSP_ADD(12);
+    }
+    WSP_ADD(14);
+    // ---- P1: S -= W^T diag(1/(h+d)) W (register tiles; the row scaling rides on the A fragment)
+    {
+      const double* wb = u.w + tq * WS + g;
+#pragma unroll
+      for (int kk = 0; kk < MM_CL / 4; kk++) {
+        if (4 * kk < nl4) {
+          const double inv = (4 * kk + tq < nl) ? u.sc[(4 * kk + tq) * 4] : 0.0;
+          const double* wr = wb + kk * 4 * WS;
+#pragma unroll
+          for (int s = 0; s < TM; s++) {
+            if (ti[s] < 0) continue;
+            dmma884(accW[s][0], accW[s][1], wr[ti[s]] * inv, wr[tj[s]]);
+          }
+        }
+      }
+    }
+    WSP_ADD(10);
+    // ---- P2a: diagonal blocks (p, p) from the factors seen in frame p (non-anchor side); four independent chains
+#pragma unroll
+    for (int uu = 0; uu < 2; uu++) {
+      const int p = wp + 8 * uu;
+      if (p >= K) continue;
+      const short* sl = u.slot + (tq >> 1) * K + p;
+      const double* px = u.fac + (g < 6 ? 12 + 6 * (tq & 1) + g : g == 6 ? 26 + (tq & 1) : -STG);
+      for (int lc = 0; lc < nl; lc += 8, sl += 8 * K) {
+        double x[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) x[j] = px[(int)sl[2 * j * K] * mul7];   // unobserved / padding rows (nl .. nl+7): slot -1 = zeros
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(accD[uu][2 * j], accD[uu][2 * j + 1], x[j], x[j]);
+      }
+    }
+    bar_arrive(BAR_EMPTY0 + b, WS_THREADS);            // buffer b may be overwritten
+    WSP_ADD(11);
+    if (tid == 0) { WSP_CHUNK(); }
+    lb += nl;
+  }
+  // ---- fold the register tiles into the shared record (single owner per element in each phase)
+  if (curq >= 0) flush_ata(curq);
+  bar_sync(BAR_CONS, WS_ROLE);
+  for (int i = tid; i < K * 28; i += WS_ROLE) {        // AtA(q): the eight warps' partials in a fixed order
+    const int q = i / 28, e = i - 28 * q, m = c_triA[e], n = c_triB[e];
+    const double* pp = sAtA + q * 8 * 28 + e;
+    double sacc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sacc += pp[k * 28];
+    if (m < 6) {
+      sAcc[tri(q, q) * 36 + m * 6 + n] += sacc;
+      if (m != n) sAcc[tri(q, q) * 36 + n * 6 + m] += sacc;
+      else sDg[6 * q + m] += sacc;
+    } else if (n < 6) sGb[6 * q + n] += sacc;
+  }
+  bar_sync(BAR_CONS, WS_ROLE);
+#pragma unroll
+  for (int uu = 0; uu < 2; uu++) {
+    const int p = wp + 8 * uu;
+    if (p >= K) continue;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int m = g, n = 2 * tq + e;
+      const double v = (accD[uu][e] + accD[uu][2 + e]) + (accD[uu][4 + e] + accD[uu][6 + e]);
+      if (m < 6 && n < 6) {
+        sAcc[tri(p, p) * 36 + m * 6 + n] += v;
+        if (m == n) sDg[6 * p + m] += v;
+      } else if (m == 6 && n < 6) sGb[6 * p + n] += v;
+    }
+  }
+  bar_sync(BAR_CONS, WS_ROLE);
+#pragma unroll
+  for (int s = 0; s < TM; s++) {
+    if (ti[s] < 0) continue;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int r = ti[s] + g, cc = tj[s] + 2 * tq + e;
+      if (cc >= K6 || cc > r) continue;
+      if (r < K6) sAcc[tri(r / 6, cc / 6) * 36 + (r % 6) * 6 + (cc % 6)] -= accW[s][e];
+      else if (r == K6) sGr[cc] = accW[s][e];
+    }
+  }
+  bar_sync(BAR_CONS, WS_ROLE);
+  // ---- one tile record to HBM (cost / gradient-max slots: the producers')
+  double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(K);
+  for (int i = tid; i < NPb * 36; i += WS_ROLE) out[i] = sAcc[i];
+  for (int i = tid; i < K6; i += WS_ROLE) {
+    out[NPb * 36 + i] = sGb[i] - sGr[i];
+    out[NPb * 36 + K6 + i] = sGb[i];
+    out[NPb * 36 + 2 * K6 + i] = sDg[i];
+  }
+}
+
+void ba_ws_prof_dump(void) {
+#ifdef BVIO_WS_PROF
+  static unsigned long long h[16 + 256];
+  if (cudaMemcpyFromSymbol(h, g_ws_prof, sizeof h) != cudaSuccess || !h[15]) return;
+  const char* nm[16] = {"extent", "waitEMPTY", "zero", "-", "A1", "A2", "arrive", "", "waitFULL", "AtA", "P1", "P2a", "P2b", "scan+flush", "scan tail", ""};
+  fprintf(stderr, "[ws prof] %llu chunks; cycles per chunk per warp\n", h[15]);
+  for (int r = 0; r < 2; r++)
+    for (int i = 0; i < 15; i++) {
+      if (!nm[i][0] || (r == 0) != (i < 8)) continue;
+      fprintf(stderr, "[ws prof] %s %-10s", r ? "C" : "P", nm[i]);
+      for (int wq = 0; wq < 8; wq++) fprintf(stderr, " %6.0f", (double)h[16 + 16 * (8 * r + wq) + i] / (double)h[15]);
+      fprintf(stderr, "\n");
+    }
+#endif
+}
+size_t ba_linearize_ws_smem_bytes(int K) {
+  const int NPb = K * (K + 1) / 2, WS = mm_wstride(K);
+  size_t d = (size_t)(K + 1) * FR + 32 + (size_t)NPb * 36 + 18 * K + (size_t)K * 8 * 28 + 2 * ws_buf_doubles(WS);
+  size_t bytes = d * sizeof(double) + 2 * ws_buf_ints() * sizeof(int) + 2 * ws_buf_shorts(K) * sizeof(short);
+  return (bytes + 15) & ~size_t(15);
+}
+
 // =============================================================================================
 // solve: one CTA per window
 // =============================================================================================
@@ -1969,6 +2417,8 @@ int ba_configure(void) {
 #undef BVIO_LIN_ATTR
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 76>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_ws_kernel<6, 76>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_ws_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
@@ -2004,6 +2454,7 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
   const int nstrip = (KE * (KE + 1) / 2) * 2;   // half-block units
   // latency mode (fewer windows than SMs): every IMU factor in its own CTA
   const dim3 grid(bt.T + 1 + (bt.solve_wide ? bt.K - 1 : 0), bt.B);
+  int nlin = 1;                                  // launches of the linearization
 #define BVIO_LIN(NS) \
   { if (XB == 2) ba_linearize_kernel<NS, 2><<<grid, BA_THREADS, s1, st>>>(bt); \
     else if (XB == 1) ba_linearize_kernel<NS, 1><<<grid, BA_THREADS, s1, st>>>(bt); \
@@ -2012,7 +2463,16 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
     size_t sm1 = ba_linearize_mma_smem_bytes(bt.K);
     if (s1b > sm1) sm1 = s1b;
     const int NT = mm_ntile(bt.K);
-    if (NT * (NT + 1) / 2 <= 48 && mm_wstride(bt.K) == 76) ba_linearize_mma_kernel<6, 76><<<grid, BA_THREADS, sm1, st>>>(bt);
+    const size_t smw = ba_linearize_ws_smem_bytes(bt.K);
+    // throughput mode: producers / consumers overlapped in one 512-thread CTA per SM
+    if (bt.use_ws && NT * (NT + 1) / 2 <= 48 && smw <= 227 * 1024) {
+      const dim3 gv(bt.T, bt.B);
+      ba_imu_prior_kernel<<<dim3(bt.K, bt.B), IMU_THREADS, sizeof(double) * (930 + 2 * (size_t)bt.nmax), st>>>(bt);
+      if (mm_wstride(bt.K) == 76) ba_linearize_ws_kernel<6, 76><<<gv, WS_THREADS, smw, st>>>(bt);
+      else ba_linearize_ws_kernel<6, 0><<<gv, WS_THREADS, smw, st>>>(bt);
+      nlin = 2;
+    }
+    else if (NT * (NT + 1) / 2 <= 48 && mm_wstride(bt.K) == 76) ba_linearize_mma_kernel<6, 76><<<grid, BA_THREADS, sm1, st>>>(bt);
     else if (NT * (NT + 1) / 2 <= 48) ba_linearize_mma_kernel<6, 0><<<grid, BA_THREADS, sm1, st>>>(bt);
     else ba_linearize_mma_kernel<10, 0><<<grid, BA_THREADS, sm1, st>>>(bt);
   }
@@ -2030,11 +2490,11 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
     if (XB) ba_solve_kernel<true, 256><<<bt.B, 256, ssm, st>>>(bt, with_step ? 1 : 0);
     else ba_solve_kernel<false, 256><<<bt.B, 256, ssm, st>>>(bt, with_step ? 1 : 0);
   }
-  if (!with_step || bt.undamped) { if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); } return 2; }
-  int nk = 3;
+  if (!with_step || bt.undamped) { if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); } return 1 + nlin; }
+  int nk = 2 + nlin;
   if (bt.strategy) {   // dogleg combination; its time is booked with the reduced solve
     ba_dogleg_kernel<<<dim3(bt.T, bt.B), BA_THREADS, sizeof(double) * (2 * bt.np + 32 * DOG_REC), st>>>(bt);
-    nk = 4;
+    nk++;
   }
   if (ev) cudaEventRecord(ev[2], st);
   ba_cost_kernel<<<dim3(bt.T + 1, bt.B), BA_THREADS, cost_smem(bt.K, bt.nmax), st>>>(bt);

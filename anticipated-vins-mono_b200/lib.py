@@ -8,7 +8,8 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbvio.so")
+# BVIO_LIB_PATH: load another build of the same library (kernel A/B measurements); never a different implementation
+LIB_PATH = os.environ.get("BVIO_LIB_PATH") or os.path.join(_HERE, "csrc", "libbvio.so")
 _lib = None
 
 # every symbol include/bvio.h declares

@@ -492,3 +492,63 @@ def test_relocalization_rejections(env):
         ho, so = abi.WindowHandle(wsrc), abi.Summary()
         assert orc.oracle_optimize(C.byref(ho.s), C.byref(abi.default_opts()), C.byref(so)) == 0
         assert np.linalg.norm(hdev.state_vector() - ho.state_vector()) <= 1e-6 * np.linalg.norm(ho.state_vector())
+
+
+# ---- warp-specialised linearize kernel (throughput mode: batches of at least one window per SM) ---------------------------
+@pytest.fixture
+def force_ws(monkeypatch):
+    """BVIO_LIN_WS=1: take ba_linearize_ws_kernel for any batch size (it is otherwise chosen when B >= the SM count)."""
+    monkeypatch.setenv("BVIO_LIN_WS", "1")
+
+
+@pytest.mark.parametrize("seed,K,L,prior,kw", [(0, 11, 150, "frame0", {}), (1, 11, 150, "none", {}), (2, 2, 20, "none", dict(track_min=2, track_max=2)),
+                                               (3, 5, 37, "frame0", {}), (4, 11, 1500, "frame0", {}), (5, 12, 64, "frame0", {}),
+                                               (6, 11, 400, "frame0", dict(track_min=2, track_max=4)),      # 40 landmarks per chunk
+                                               (7, 11, 300, "none", dict(track_min=10))])                     # ~25 per chunk
+def test_ws_linearize_matches_oracle(env, force_ws, seed, K, L, prior, kw):
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=seed, K=K, L=L, prior=prior, **kw)
+    r = _linearize_both(env, w)
+    (S1, g1, h1, b1, c1), (S2, g2, h2, b2, c2) = r["gpu"], r["cpu"]
+    assert np.isfinite(S1).all()
+    assert abs(c1 - c2) <= 1e-11 * abs(c2)
+    assert np.abs(h1 - h2).max() <= 1e-11 * np.abs(h2).max()
+    assert np.abs(b1 - b2).max() <= 1e-10 * max(np.abs(b2).max(), 1.0)
+    assert np.abs(S1 - S2).max() <= 1e-9 * np.abs(S2).max()
+    assert np.abs(g1 - g2).max() <= 1e-9 * max(np.abs(g2).max(), 1.0)
+    assert np.abs(S1 - S1.T).max() == 0.0
+
+
+@pytest.mark.parametrize("seed,L,strategy", [(0, 150, 0), (1, 150, 1), (7, 1500, 1)])
+def test_ws_converged_state_matches_oracle(env, force_ws, seed, L, strategy):
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=seed, K=11, L=L, **(dict(track_min=6) if L == 1500 else {}))
+    hg, ho, sg, so = _solve_both(env, w, dict(strategy=strategy, **TIGHT))
+    xg, xo = hg.state_vector(), ho.state_vector()
+    assert np.linalg.norm(xg - xo) <= 1e-6 * np.linalg.norm(xo), (sg.as_dict(), so.as_dict())
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+
+
+def test_ws_batch_equals_single_solves(env):
+    """A batch of one window per SM and more takes the warp-specialised kernel on its own (no env override): every window
+    must come back with the result of its single-window solve (latency mode = ba_linearize_mma_kernel)."""
+    import torch
+    abi, synth, orc, ctx = env
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    B = n_sm + 3
+    pool = [synth.make_window(seed=60 + i, K=11, L=120 + 40 * i, **(dict(track_min=2, track_max=5) if i == 2 else {})) for i in range(5)]
+    o = abi.default_opts(max_iters=6, strategy=1)
+    singles = []
+    for w in pool:
+        h, s = abi.WindowHandle(w), abi.Summary()
+        ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h.s), C.byref(o), C.byref(s)), "optimize")
+        singles.append((h.state_vector().copy(), s.final_cost, s.iterations))
+    hs = [abi.WindowHandle(pool[(3 * i) % 5]) for i in range(B)]
+    arr = (abi.WindowS * B)(*[h.s for h in hs])
+    sums = (abi.Summary * B)()
+    ctx.check(ctx.L.bvio_optimize_batch(ctx.h, arr, B, C.byref(o), sums), "optimize_batch")
+    for i, (h, s) in enumerate(zip(hs, sums)):
+        x, c, it = singles[(3 * i) % 5]
+        assert s.iterations == it
+        assert np.linalg.norm(h.state_vector() - x) <= 1e-9 * np.linalg.norm(x), i
+        assert abs(s.final_cost - c) <= 1e-9 * c
