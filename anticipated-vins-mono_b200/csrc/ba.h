@@ -57,7 +57,8 @@ constexpr int COST_REC = 4;
 constexpr int DOG_REC = 8;
 
 struct BaBatch {                  // all pointers are device pointers
-  int B, K, np, T;                // windows, keyframes, reduced dimension, landmark tiles per window
+  int B, K, np, T;                // windows, keyframes, reduced dimension, landmark tiles per window (cost / dogleg kernels)
+  int TL;                         // landmark tiles per window of the linearization (tile records); <= T
   int total_L, total_obs, nmax;   // nmax = max prior dimension (row stride of the prior arrays)
   int chunk_l;                    // landmarks per chunk in ba_linearize (bounded by shared memory)
   int undamped;                   // debug: linearize without LM damping (bvio_debug_linearize)

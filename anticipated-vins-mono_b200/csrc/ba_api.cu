@@ -255,6 +255,11 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   T = std::max(1, std::min(std::min(T, Tcap), 32));
   if (const char* ev = getenv("BVIO_TILES")) T = std::max(1, std::min(atoi(ev), 32));   // tuning knob
   bt.T = T;
+  // the warp-specialised linearization keeps one CTA per SM busy for a whole tile: few, long tiles (about four waves) --
+  // the pipeline fill / drain of a CTA and its tile record (HBM, re-read by ba_solve) are paid once per tile
+  bt.TL = T;
+  if (bt.use_ws) bt.TL = std::max(1, std::min(T, (4 * ctx->sm_count + B - 1) / B));
+  if (const char* ev = getenv("BVIO_LIN_TILES")) bt.TL = std::max(1, std::min(atoi(ev), T));
   bt.undamped = debug;
   bt.max_iters = o->max_iters; bt.jacobi_scaling = o->jacobi_scaling;
   bt.strategy = o->strategy;

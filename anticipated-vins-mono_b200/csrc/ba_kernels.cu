@@ -41,9 +41,11 @@ constexpr int ACS = 37;           // padded stride of one 6x6 accumulator block 
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
-__device__ __forceinline__ void tile_range(const BaBatch& bt, int w, int t, int& l0, int& l1) {
+// landmarks of tile t of nt: the linearization cuts a window into bt.TL tiles (tile records), the cost / dogleg kernels
+// into bt.T (their own partial sums)
+__device__ __forceinline__ void tile_range(const BaBatch& bt, int w, int t, int& l0, int& l1, int nt) {
   int base = bt.lm_base[w], Lw = bt.lm_base[w + 1] - base;
-  int tl = (Lw + bt.T - 1) / bt.T;
+  int tl = (Lw + nt - 1) / nt;
   l0 = base + min(Lw, t * tl);
   l1 = base + min(Lw, (t + 1) * tl);
 }
@@ -503,10 +505,10 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   BaCtrl* ctrl = bt.ctrl + w;
   if (ctrl->done) return;
   const int cur = ctrl->cur;
-  if (t >= bt.T) {   // IMU / prior CTAs: one for all, or (latency mode) the prior CTA followed by one CTA per IMU factor
-    if (gridDim.x == (unsigned)bt.T + 1) imu_prior_linearize(bt, w, cur, sm, 0, bt.K - 1, true);
-    else if (t == bt.T) imu_prior_linearize(bt, w, cur, sm, 0, 0, true);
-    else imu_prior_linearize(bt, w, cur, sm, t - bt.T - 1, t - bt.T, false);
+  if (t >= bt.TL) {   // IMU / prior CTAs: one for all, or (latency mode) the prior CTA followed by one CTA per IMU factor
+    if (gridDim.x == (unsigned)bt.TL + 1) imu_prior_linearize(bt, w, cur, sm, 0, bt.K - 1, true);
+    else if (t == bt.TL) imu_prior_linearize(bt, w, cur, sm, 0, 0, true);
+    else imu_prior_linearize(bt, w, cur, sm, t - bt.TL - 1, t - bt.TL, false);
     return;
   }
 
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
   const int first = ctrl->first;
   const double* invd = bt.invd[cur];
   int l0, l1;
-  tile_range(bt, w, t, l0, l1);
+  tile_range(bt, w, t, l0, l1, bt.TL);
 
   for (int lb = l0; lb < l1; lb += CL) {
     const int nl = min(CL, l1 - lb);
@@ -829,7 +831,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_kernel(BaBatch bt)
     }
   }
   // ---- one tile record to HBM
-  double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(KE);
+  double* out = bt.tile_out + (size_t)(w * bt.TL + t) * tile_rec_doubles(KE);
 #pragma unroll
   for (int u = 0; u < NS; u++) {
     if (s_p[u] < 0) continue;
@@ -891,10 +893,10 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
   BaCtrl* ctrl = bt.ctrl + w;
   if (ctrl->done) return;
   const int cur = ctrl->cur;
-  if (t >= bt.T) {   // IMU / prior CTAs: one for all, or (latency mode) the prior CTA followed by one CTA per IMU factor
-    if (gridDim.x == (unsigned)bt.T + 1) imu_prior_linearize(bt, w, cur, sm, 0, bt.K - 1, true);
-    else if (t == bt.T) imu_prior_linearize(bt, w, cur, sm, 0, 0, true);
-    else imu_prior_linearize(bt, w, cur, sm, t - bt.T - 1, t - bt.T, false);
+  if (t >= bt.TL) {   // IMU / prior CTAs: one for all, or (latency mode) the prior CTA followed by one CTA per IMU factor
+    if (gridDim.x == (unsigned)bt.TL + 1) imu_prior_linearize(bt, w, cur, sm, 0, bt.K - 1, true);
+    else if (t == bt.TL) imu_prior_linearize(bt, w, cur, sm, 0, 0, true);
+    else imu_prior_linearize(bt, w, cur, sm, t - bt.TL - 1, t - bt.TL, false);
     return;
   }
 
@@ -945,7 +947,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
   const int first = ctrl->first;
   const double* invd = bt.invd[cur];
   int l0, l1;
-  tile_range(bt, w, t, l0, l1);
+  tile_range(bt, w, t, l0, l1, bt.TL);
 
   for (int lb = l0; lb < l1;) {
     // ---- chunk extent: as many landmarks as fit MM_NF factor slots (and MM_CL rows)
@@ -1177,7 +1179,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
   }
   __syncthreads();
   // ---- one tile record to HBM
-  double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(K);
+  double* out = bt.tile_out + (size_t)(w * bt.TL + t) * tile_rec_doubles(K);
   for (int i = tid; i < NPb * 36; i += BA_THREADS) out[i] = sAcc[i];
   for (int i = tid; i < K6; i += BA_THREADS) {
     out[NPb * 36 + i] = sGb[i] - sGr[i];
@@ -1280,7 +1282,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
   if (threadIdx.x < 2 * STG) dbl[(threadIdx.x / STG) * ws_buf_doubles(WS) + threadIdx.x % STG] = 0.0;   // the zero records
   stage_frames(bt, w, bt.pose[cur], bt.exs[cur], sFr, sEx);
   int l0, l1;
-  tile_range(bt, w, t, l0, l1);
+  tile_range(bt, w, t, l0, l1, bt.TL);
   __syncthreads();                                   // the last CTA-wide barrier: the roles part here
 
   if (role == 0) {
@@ -1320,7 +1322,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
       WSP_ADD(0);
       if (c >= 2) bar_sync(BAR_EMPTY0 + b, WS_THREADS);          // the consumers are done with this buffer
       WSP_ADD(1);
-      for (int i = tid; i < nl4 * WS; i += WS_ROLE) u.w[i] = 0.0;
+      for (int i = tid; i < nl4 * WS / 2; i += WS_ROLE) reinterpret_cast<double2*>(u.w)[i] = double2{0.0, 0.0};
       for (int i = tid; i < (nl + 8) * K; i += WS_ROLE) u.slot[i] = -1;   // 8 pad rows: the pair loops need no bound check
       if (tid < BVIO_KMAX) { u.qlo[tid] = MM_CL; u.qhi[tid] = 0; }
       if (wp == 0) {                                   // per-landmark tables: first observation, first factor slot, track length
@@ -1398,6 +1400,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
         const int lc = tid >> 2, part = tid & 3, l = lb + lc;
         const int nf = u.nobs[lc] - 1;
         const double* st = u.fac + (size_t)u.first[lc] * STG;
+        double sl2 = 1.0;                              // Jacobi scale^2 of the depth column: fixed at the first linearization
+        if (part == 3 && bt.jacobi_scaling && !first) sl2 = bt.sl2[l];   // (issued ahead of the reduction loop)
         const int ea = part < 3 ? 2 * part : 24, eb = part < 3 ? 6 + 2 * part : 25, ec = part < 3 ? 2 * part + 1 : 26, ed = part < 3 ? 7 + 2 * part : 27;
         double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
         for (int f = 0; f < nf; f++, st += STG) {
@@ -1415,11 +1419,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
           u.w[lc * WS + K6] = vb;                      // column 6K of W: b_l => row 6K of P1 = Schur gradient term
           gmax_t = fmax(gmax_t, fabs(vb));
           bt.b[l] = vb;
-          double sl2 = 1.0;
-          if (bt.jacobi_scaling) {
-            if (first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
-            else sl2 = bt.sl2[l];
-          }
+          if (bt.jacobi_scaling && first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
           const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, dfac);
           double inv_hd = 1.0 / (h + ddl);
           if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
@@ -1444,7 +1444,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     if (tid == 0) {
       double cs = 0, gm = sRed[8];
       for (int i = 0; i < 8; i++) { cs += sRed[i]; gm = fmax(gm, sRed[8 + i]); }
-      double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(K);
+      double* out = bt.tile_out + (size_t)(w * bt.TL + t) * tile_rec_doubles(K);
       const int REC = NPb * 36 + 3 * K6;
       out[REC] = cs; out[REC + 1] = gm; out[REC + 2] = 0; out[REC + 3] = 0;
     }
@@ -1464,6 +1464,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
       ti[s] = 8 * i; tj[s] = 8 * (idx - i * (i + 1) / 2);
     }
     accW[s][0] = accW[s][1] = 0.0;
+  }
+  // NT == 9 (K = 11, the reference's window): the 45 lower tiles are dealt out as 3 x 3 groups that share their
+  // fragments -- warps 0-2 the diagonal triangles of tile rows {0,1,2}, {3,4,5}, {6,7,8} (3 loads for 6 tiles),
+  // warps 3-7 rectangles (rows x three columns): {3,4}x{0-2}, {6,7}x{0-2}, {6,7}x{3-5}, {5,8}x{0-2}, {8}x{3-5}
+  // (5 loads for 6 tiles) -- instead of two loads per tile.
+  constexpr bool GROUPED = false;   // measured: 1.30 -> 1.43 ms per pass with the grouped tiles (kept for reference, off)
+  int gr[3] = {0, 0, 0}, gc0 = 0;
+  unsigned gmask = 0;
+  bool gtri = false;
+  double accG[3][3][2];
+  if (GROUPED) {
+    const int R0[8] = {0, 3, 6, 3, 6, 6, 5, 8}, R1[8] = {1, 4, 7, 4, 7, 7, 8, 8}, R2[8] = {2, 5, 8, 4, 7, 7, 8, 8};
+    const int C0[8] = {0, 3, 6, 0, 0, 3, 0, 3};
+    const unsigned MK[8] = {0x1d9, 0x1d9, 0x1d9, 0x03f, 0x03f, 0x03f, 0x03f, 0x007};   // bit 3 * ri + ci; 0x1d9 = lower triangle
+    gr[0] = 8 * R0[wp]; gr[1] = 8 * R1[wp]; gr[2] = 8 * R2[wp]; gc0 = 8 * C0[wp]; gmask = MK[wp]; gtri = wp < 3;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int e = 0; e < 3; e++) accG[a][e][0] = accG[a][e][1] = 0.0;
   }
   double accD[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
   int curq = -1;                                       // anchor frame the AtA partials belong to
@@ -1534,7 +1553,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     }
     WSP_ADD(14);
     // ---- P1: S -= W^T diag(1/(h+d)) W (register tiles; the row scaling rides on the A fragment)
-    {
+    if (GROUPED) {
+      const double* wb = u.w + tq * WS + g;
+      const double* pr0 = wb + gr[0]; const double* pr1 = wb + gr[1]; const double* pr2 = wb + gr[2]; const double* pc = wb + gc0;
+#pragma unroll
+      for (int kk = 0; kk < MM_CL / 4; kk++) {
+        if (4 * kk < nl4) {
+          const double inv = (4 * kk + tq < nl) ? u.sc[(4 * kk + tq) * 4] : 0.0;
+          const int o = kk * 4 * WS;
+          double fb[3], fa[3];
+          fb[0] = pc[o]; fb[1] = pc[o + 8]; fb[2] = pc[o + 16];
+          if (gtri) { fa[0] = fb[0]; fa[1] = fb[1]; fa[2] = fb[2]; }
+          else { fa[0] = pr0[o]; fa[1] = pr1[o]; fa[2] = pr2[o]; }
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            const double fs = fa[a] * inv;
+#pragma unroll
+            for (int e = 0; e < 3; e++)
+              if (gmask >> (3 * a + e) & 1) dmma884(accG[a][e][0], accG[a][e][1], fs, fb[e]);
+          }
+        }
+      }
+    } else {
       const double* wb = u.w + tq * WS + g;
 #pragma unroll
       for (int kk = 0; kk < MM_CL / 4; kk++) {
@@ -1601,20 +1641,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     }
   }
   bar_sync(BAR_CONS, WS_ROLE);
-#pragma unroll
-  for (int s = 0; s < TM; s++) {
-    if (ti[s] < 0) continue;
+  auto fold_tile = [&](int r0, int c0, const double* acc) {
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const int r = ti[s] + g, cc = tj[s] + 2 * tq + e;
+      const int r = r0 + g, cc = c0 + 2 * tq + e;
       if (cc >= K6 || cc > r) continue;
-      if (r < K6) sAcc[tri(r / 6, cc / 6) * 36 + (r % 6) * 6 + (cc % 6)] -= accW[s][e];
-      else if (r == K6) sGr[cc] = accW[s][e];
+      if (r < K6) sAcc[tri(r / 6, cc / 6) * 36 + (r % 6) * 6 + (cc % 6)] -= acc[e];
+      else if (r == K6) sGr[cc] = acc[e];
     }
+  };
+  if (GROUPED) {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int e = 0; e < 3; e++)
+        if (gmask >> (3 * a + e) & 1) fold_tile(gr[a], gc0 + 8 * e, accG[a][e]);
+  } else {
+#pragma unroll
+    for (int s = 0; s < TM; s++)
+      if (ti[s] >= 0) fold_tile(ti[s], tj[s], accW[s]);
   }
   bar_sync(BAR_CONS, WS_ROLE);
   // ---- one tile record to HBM (cost / gradient-max slots: the producers')
-  double* out = bt.tile_out + (size_t)(w * bt.T + t) * tile_rec_doubles(K);
+  double* out = bt.tile_out + (size_t)(w * bt.TL + t) * tile_rec_doubles(K);
   for (int i = tid; i < NPb * 36; i += WS_ROLE) out[i] = sAcc[i];
   for (int i = tid; i < K6; i += WS_ROLE) {
     out[NPb * 36 + i] = sGb[i] - sGr[i];
@@ -1674,7 +1723,7 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
   __shared__ int s_fail;
   const int REC = NPb * 36 + 3 * K6;
   const int TREC = tile_rec_doubles(KE);
-  const double* tiles = bt.tile_out + (size_t)w * bt.T * TREC;
+  const double* tiles = bt.tile_out + (size_t)w * bt.TL * TREC;
   const double* imo = bt.imu_out + (size_t)w * K * IMU_OUT;
   const int n = bt.pr_n[w];
   const int* map = bt.pr_map + (size_t)w * bt.nmax;
@@ -1690,7 +1739,7 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
   // visual blocks
   for (int idx = tid; idx < NPb * 36; idx += nthr) {
     double s = 0;
-    for (int t = 0; t < bt.T; t++) s += tiles[(size_t)t * TREC + idx];
+    for (int t = 0; t < bt.TL; t++) s += tiles[(size_t)t * TREC + idx];
     int blk = idx / 36, rc = idx - blk * 36, r = rc / 6, c = rc - r * 6;
     int p = c_triA[blk], q = c_triB[blk];
     if (p == q && c > r) continue;
@@ -1724,7 +1773,7 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
     double g1 = 0, g2 = 0, d = 0;
     const int v = red2vis(bt, i);
     if (v >= 0) {
-      for (int t = 0; t < bt.T; t++) {
+      for (int t = 0; t < bt.TL; t++) {
         const double* rec = tiles + (size_t)t * TREC + NPb * 36;
         g2 += rec[v]; g1 += rec[K6 + v]; d += rec[2 * K6 + v];
       }
@@ -1739,7 +1788,7 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
   // gradient max-norm, cost on the first pass
   double m = 0;
   for (int i = tid; i < np; i += nthr) m = fmax(m, fabs(bp[i]));
-  for (int t = tid; t < bt.T; t += nthr) m = fmax(m, tiles[(size_t)t * TREC + REC + 1]);
+  for (int t = tid; t < bt.TL; t += nthr) m = fmax(m, tiles[(size_t)t * TREC + REC + 1]);
   m = block_max(m, red);
   const int first = ctrl->first;
   const double radius = ctrl->radius;
@@ -1751,7 +1800,7 @@ __global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1) ba_solve_kernel(BaB
     ctrl->gmax = m;
     if (first) {
       double c = 0;
-      for (int t = 0; t < bt.T; t++) c += tiles[(size_t)t * TREC + REC];
+      for (int t = 0; t < bt.TL; t++) c += tiles[(size_t)t * TREC + REC];
       for (int j = 1; j < K; j++) c += imo[(size_t)j * IMU_OUT + 495];
       c += po[bt.nmax];
       ctrl->cost = c; ctrl->initial_cost = c; ctrl->first = 0;
@@ -2055,7 +2104,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
   const unsigned gmask = 0xffffffffu;   // the four groups of a warp always iterate together (warp-uniform trip count)
   const double mu = ctrl->mu;
   int l0, l1;
-  tile_range(bt, w, t, l0, l1);
+  tile_range(bt, w, t, l0, l1, bt.T);
   double a[6] = {0, 0, 0, 0, 0, 0};
   for (int lw = l0 + (grp & ~3); lw < l1; lw += NG) {
     const bool act = lw + (grp & 3) < l1;
@@ -2197,7 +2246,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
     const unsigned gmask = 0xffffffffu;   // the four groups of a warp always iterate together (warp-uniform trip count)
     const double dfac = damp_factor(ctrl->radius, mu, dogleg);
     int l0, l1;
-    tile_range(bt, w, t, l0, l1);
+    tile_range(bt, w, t, l0, l1, bt.T);
     double a_cost = 0, a_model = 0, a_s2 = 0, a_x2 = 0;
     for (int lw = l0 + (grp & ~3); lw < l1; lw += NG) {
       const bool act = lw + (grp & 3) < l1;
@@ -2453,7 +2502,7 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
   const int KE = bt.K + XB;
   const int nstrip = (KE * (KE + 1) / 2) * 2;   // half-block units
   // latency mode (fewer windows than SMs): every IMU factor in its own CTA
-  const dim3 grid(bt.T + 1 + (bt.solve_wide ? bt.K - 1 : 0), bt.B);
+  const dim3 grid(bt.TL + 1 + (bt.solve_wide ? bt.K - 1 : 0), bt.B);
   int nlin = 1;                                  // launches of the linearization
 #define BVIO_LIN(NS) \
   { if (XB == 2) ba_linearize_kernel<NS, 2><<<grid, BA_THREADS, s1, st>>>(bt); \
@@ -2466,7 +2515,7 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
     const size_t smw = ba_linearize_ws_smem_bytes(bt.K);
     // throughput mode: producers / consumers overlapped in one 512-thread CTA per SM
     if (bt.use_ws && NT * (NT + 1) / 2 <= 48 && smw <= 227 * 1024) {
-      const dim3 gv(bt.T, bt.B);
+      const dim3 gv(bt.TL, bt.B);
       ba_imu_prior_kernel<<<dim3(bt.K, bt.B), IMU_THREADS, sizeof(double) * (930 + 2 * (size_t)bt.nmax), st>>>(bt);
       if (mm_wstride(bt.K) == 76) ba_linearize_ws_kernel<6, 76><<<gv, WS_THREADS, smw, st>>>(bt);
       else ba_linearize_ws_kernel<6, 0><<<gv, WS_THREADS, smw, st>>>(bt);
