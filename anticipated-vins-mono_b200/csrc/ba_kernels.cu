@@ -1290,6 +1290,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     const double dfac = damp_factor(ctrl->radius, ctrl->mu, bt.strategy);
     const int first = ctrl->first;
     const double* invd = bt.invd[cur];
+    const double cauchy_b = bt.cauchy_a * bt.cauchy_a, cauchy_c = 1.0 / cauchy_b;
     double cost_t = 0, gmax_t = 0;
     int c = 0;
     WSP_T0();
@@ -1360,10 +1361,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
         for (int a = 0; a < 2; a++)
 #pragma unroll
           for (int cc = 0; cc < 3; cc++) Q[a][cc] = Gm[a][0] * Fj[cc * 3 + 0] + Gm[a][1] * Fj[cc * 3 + 1] + Gm[a][2] * Fj[cc * 3 + 2];
-        double rho0, rho1;
-        cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
-        cost_t += 0.5 * rho0;
-        const double sr = sqrt(rho1);
+        // Cauchy loss: rho' = 1 / (1 + s / a^2) always; rho = a^2 log(1 + s / a^2) only feeds the cost, which the solve
+        // reads from the linearization only the first time (later it is the accepted candidate's, from ba_cost)
+        const double s2 = r0 * r0 + r1 * r1, csum = 1.0 + s2 * cauchy_c;
+        if (first) cost_t += 0.5 * cauchy_b * log(csum);
+        const double sr = sqrt(fmax(DBL_MIN, 1.0 / csum));
         double* st = u.fac + (size_t)tid * STG;
         const d3 dimu = gm.pimu_i - d3{sEx[9], sEx[10], sEx[11]};
         double cc2[2], Bv[2][6];
@@ -1378,7 +1380,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
           Bv[a][3] = sr * jjr.x; Bv[a][4] = sr * jjr.y; Bv[a][5] = sr * jjr.z;
 #pragma unroll
           for (int k = 0; k < 6; k++) st[12 + a * 6 + k] = Bv[a][k];
-          cc2[a] = sr * (-dot3(uu, dimu) / lam);
+          cc2[a] = sr * (-dot3(uu, dimu) / lam);   // (a true division: bit-compatible with the latency-mode kernel)
         }
         st[24] = cc2[0]; st[25] = cc2[1]; st[26] = sr * r0; st[27] = sr * r1;
         double* wo = u.w + lc * WS + 6 * fj;
