@@ -2202,7 +2202,11 @@ __global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
   }
 }
 
-__global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BaBatch bt) {
+// MINB: CTAs per SM the register allocation aims at -- 4 (64 registers, some spills) for throughput batches, where the
+// kernel is latency-bound and twice the warps hide it (0.40 -> 0.30 ms per pass of 592 windows); 2 (128 registers, no
+// spills) when there are fewer CTAs than SMs anyway (latency mode)
+template <int MINB>
+__global__ void __launch_bounds__(BA_THREADS, MINB) ba_cost_kernel(BaBatch bt) {
   extern __shared__ double sm[];
   const int w = blockIdx.y, t = blockIdx.x, K = bt.K, np = bt.np;
   BaCtrl* ctrl = bt.ctrl + w;
@@ -2475,7 +2479,8 @@ int ba_configure(void) {
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_cost_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_cost_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return err;
     if ((err = ba_configure_marginalize()) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_marginal9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if (dev >= 0 && dev < 256) g_cfg_devices[dev >> 6] |= 1ull << (dev & 63);
@@ -2548,7 +2553,8 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
     nk++;
   }
   if (ev) cudaEventRecord(ev[2], st);
-  ba_cost_kernel<<<dim3(bt.T + 1, bt.B), BA_THREADS, cost_smem(bt.K, bt.nmax), st>>>(bt);
+  if (bt.solve_wide) ba_cost_kernel<2><<<dim3(bt.T + 1, bt.B), BA_THREADS, cost_smem(bt.K, bt.nmax), st>>>(bt);
+  else ba_cost_kernel<4><<<dim3(bt.T + 1, bt.B), BA_THREADS, cost_smem(bt.K, bt.nmax), st>>>(bt);
   if (ev) cudaEventRecord(ev[3], st);
   return nk;
 }
