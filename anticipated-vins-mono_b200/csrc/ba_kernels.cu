@@ -945,6 +945,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
   stage_frames(bt, w, bt.pose[cur], bt.exs[cur], sFr, sEx);
   const double dfac = damp_factor(ctrl->radius, ctrl->mu, bt.strategy);
   const int first = ctrl->first;
+  const double cauchy_b = bt.cauchy_a * bt.cauchy_a, cauchy_c = 1.0 / cauchy_b;
   const double* invd = bt.invd[cur];
   int l0, l1;
   tile_range(bt, w, t, l0, l1, bt.TL);
@@ -999,10 +1000,11 @@ __global__ void __launch_bounds__(BA_THREADS, 2) ba_linearize_mma_kernel(BaBatch
       for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int c = 0; c < 3; c++) Q[a][c] = Gm[a][0] * Fj[c * 3 + 0] + Gm[a][1] * Fj[c * 3 + 1] + Gm[a][2] * Fj[c * 3 + 2];
-      double rho0, rho1;
-      cauchy(bt.cauchy_a, r0 * r0 + r1 * r1, rho0, rho1);
-      cost_t += 0.5 * rho0;
-      const double sr = sqrt(rho1);
+      // Cauchy loss: rho' always; rho = a^2 log(1 + s / a^2) only feeds the cost, which ba_solve reads from the
+      // linearization only the first time (later it is the accepted candidate's, from ba_cost)
+      const double csum = 1.0 + (r0 * r0 + r1 * r1) * cauchy_c;
+      if (first) cost_t += 0.5 * cauchy_b * log(csum);
+      const double sr = sqrt(fmax(DBL_MIN, 1.0 / csum));
       double* st = sFac + (size_t)tid * STG;
       const d3 dimu = gm.pimu_i - d3{sEx[9], sEx[10], sEx[11]};
       double cc[2];
@@ -1201,16 +1203,17 @@ size_t ba_linearize_mma_smem_bytes(int K) {
   return (bytes + 15) & ~size_t(15);
 }
 
-// IMU factors and marginalization prior of every window, one small CTA per (window, factor) and per (window, prior):
-// the companion launch of ba_linearize_ws_kernel, whose CTAs fill an SM each and carry the visual tiles only.
-constexpr int IMU_THREADS = 128;
-__global__ void __launch_bounds__(IMU_THREADS, 4) ba_imu_prior_kernel(BaBatch bt) {
+// IMU factors and marginalization prior of every window, one CTA per window (thread f evaluates the raw Jacobian of
+// factor f, all threads whiten and form J^T J; then the prior): the companion launch of ba_linearize_ws_kernel, whose CTAs
+// fill an SM each and carry the visual tiles only.  (One CTA per (window, factor) was measured 2x slower: the raw
+// Jacobian is one thread's work either way, and eleven times the CTAs only queue behind each other.)
+constexpr int IMU_THREADS = 256;
+__global__ void __launch_bounds__(IMU_THREADS, 2) ba_imu_prior_kernel(BaBatch bt) {
   extern __shared__ double sm[];
-  const int w = blockIdx.y, t = blockIdx.x;
+  const int w = blockIdx.x;
   const BaCtrl* ctrl = bt.ctrl + w;
   if (ctrl->done) return;
-  if (t == 0) imu_prior_linearize(bt, w, ctrl->cur, sm, 0, 0, true, true);
-  else imu_prior_linearize(bt, w, ctrl->cur, sm, t - 1, t, false, true);
+  imu_prior_linearize(bt, w, ctrl->cur, sm, 0, bt.K - 1, true);
 }
 
 // =============================================================================================
@@ -2473,6 +2476,7 @@ int ba_configure(void) {
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 76>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_ws_kernel<6, 76>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_imu_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_ws_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
@@ -2523,7 +2527,8 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
     // throughput mode: producers / consumers overlapped in one 512-thread CTA per SM
     if (bt.use_ws && NT * (NT + 1) / 2 <= 48 && smw <= 227 * 1024) {
       const dim3 gv(bt.TL, bt.B);
-      ba_imu_prior_kernel<<<dim3(bt.K, bt.B), IMU_THREADS, sizeof(double) * (930 + 2 * (size_t)bt.nmax), st>>>(bt);
+      // (the IMU / prior kernel on a second stream beside the tiles was measured: no gain, the tiles' four waves end together)
+      ba_imu_prior_kernel<<<bt.B, IMU_THREADS, s1b, st>>>(bt);
       if (mm_wstride(bt.K) == 76) ba_linearize_ws_kernel<6, 76><<<gv, WS_THREADS, smw, st>>>(bt);
       else ba_linearize_ws_kernel<6, 0><<<gv, WS_THREADS, smw, st>>>(bt);
       nlin = 2;

@@ -6,8 +6,8 @@ set -x
 cd "${GRAFT_REPO_ROOT:-.}"
 B="python bench.py --steps 2 --warmup 1 --no-cpu --no-latency --pool 4"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 160 -c 1200 --csv --log-file gpurun_out/launches_r02.csv $B --stream-frames 12 > gpurun_out/prof_launch.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"ba_linearize|ba_solve|ba_cost|ba_dogleg" -s 150 -c 4 -o gpurun_out/prof_ba_r02 $B --stream-frames 0 > gpurun_out/prof_ba.log 2>&1
-timeout 300 ncu --set full --clock-control none -k regex:"ba_linearize|ba_solve|ba_cost|ba_dogleg" -s 4 -c 4 -o gpurun_out/prof_ba1_r02 $B --stream-frames 0 > gpurun_out/prof_ba1.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"ba_linearize|ba_imu|ba_solve|ba_cost|ba_dogleg" -s 190 -c 5 -o gpurun_out/prof_ba_r02 $B --stream-frames 0 > gpurun_out/prof_ba.log 2>&1
+timeout 300 ncu --set full --clock-control none -k regex:"ba_linearize|ba_imu|ba_solve|ba_cost|ba_dogleg" -s 4 -c 4 -o gpurun_out/prof_ba1_r02 $B --stream-frames 0 > gpurun_out/prof_ba1.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:"sel_" -s 0 -c 5 -o gpurun_out/prof_sel_r02 $B --stream-frames 0 > gpurun_out/prof_sel.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"ba_marg" -s 8 -c 2 -o gpurun_out/prof_marg_r02 $B --stream-frames 16 > gpurun_out/prof_marg.log 2>&1
 ls -la gpurun_out | tail -8
