@@ -541,7 +541,9 @@ def run_ours(args, rank, world, local_rank):
         peak = peaks.get("hbm_gbs", 6650.0)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("ba_linearize_mma_kernel")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            # the linearization of a throughput batch is two launches: the visual tiles and the IMU / prior companion
+            traffic = tj["ba_linearize_ws_kernel"] + tj.get("ba_imu_prior_kernel", 0)
         except Exception:
             pass
         achieved = lin_bytes / (lin_ms * 1e-3) / 1e9
@@ -560,11 +562,11 @@ def run_ours(args, rank, world, local_rank):
                     "mean_landmarks_per_window": float(np.mean([w.L for w in pool])), "prior_n": int(n_prior),
                     "pool_build_s": t_pool, "parallelism": "replicas (BA) + candidate-sharded selector" if world > 1 else "single GPU",
                     "final_cost_check": dl["final_costs"]},
-            "roofline": {"bound": "hbm", "kernel": "ba_linearize_mma_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "ba_linearize_ws_kernel (+ ba_imu_prior_kernel, its companion launch)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": int(lin_bytes), "launch_ms": lin_ms,
-                         "kernel_ms_per_pass": {"ba_linearize_kernel": lin_ms, "ba_solve_kernel (+ ba_dogleg_kernel)": solve_ms,
+                         "kernel_ms_per_pass": {"ba_linearize_ws_kernel + ba_imu_prior_kernel": lin_ms, "ba_solve_kernel (+ ba_dogleg_kernel)": solve_ms,
                                                 "ba_cost_kernel": cost_ms},
                          "fp64": {"achieved": lin_flops / (lin_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS,
                                   "unit": "TFLOP/s", "frac": lin_flops / (lin_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
