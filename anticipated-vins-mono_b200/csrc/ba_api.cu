@@ -381,16 +381,35 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
     // already in this order (features are appended as they are first seen); ba_linearize_mma walks the
     // anchors present in a chunk, so grouped input keeps that loop at 1-2 trips.  perm[device] = caller index.
     int* perm = bb->perm.data() + lb;
+    bool grouped = true;                                   // already in FeatureManager's order?
     {
       int cnt[BVIO_KMAX + 1] = {0};
-      for (int l = 0; l < w.L; l++) cnt[w.obs_frame[w.lm_obs_offset[l]] + 1]++;
+      int prev = -1;
+      for (int l = 0; l < w.L; l++) {
+        const int a = w.obs_frame[w.lm_obs_offset[l]];
+        cnt[a + 1]++;
+        grouped &= a >= prev;
+        prev = a;
+      }
       for (int f = 0; f < BVIO_KMAX; f++) cnt[f + 1] += cnt[f];
-      for (int l = 0; l < w.L; l++) perm[cnt[w.obs_frame[w.lm_obs_offset[l]]]++] = l;
+      if (grouped) for (int l = 0; l < w.L; l++) perm[l] = l;
+      else for (int l = 0; l < w.L; l++) perm[cnt[w.obs_frame[w.lm_obs_offset[l]]]++] = l;
+    }
+    if (grouped && w.n_relo == 0 && w.L > 0) {
+      // the caller's arrays are already the device layout: bulk copies instead of one small copy per landmark
+      const int nobs = w.lm_obs_offset[w.L], o_first = w.lm_obs_offset[0];
+      for (int j = 0; j < w.L; j++) h_lm_off[lb + j] = ob + (w.lm_obs_offset[j] - o_first);
+      memcpy(h_obs_frame + ob, w.obs_frame + o_first, (size_t)(nobs - o_first) * I);
+      memcpy(h_obs_xy + (size_t)2 * ob, w.obs_xy + (size_t)2 * o_first, (size_t)(nobs - o_first) * 2 * D);
+      if (est_td) {
+        memcpy(h_obs_vel + (size_t)2 * ob, w.obs_vel + (size_t)2 * o_first, (size_t)(nobs - o_first) * 2 * D);
+        for (int k = o_first; k < nobs; k++) h_obs_shift[ob + k - o_first] = -w.obs_td[k] + o->TR / o->ROW * (w.obs_row[k] - o->ROW / 2);
+      }
     }
     int run = ob;
     std::vector<int> relo_of;
     if (w.n_relo > 0) { relo_of.assign(w.L, -1); for (int k = 0; k < w.n_relo; k++) relo_of[w.relo_lm[k]] = k; }
-    for (int j = 0; j < w.L; j++) {
+    for (int j = 0; j < w.L && !(grouped && w.n_relo == 0); j++) {
       const int l = perm[j], o0 = w.lm_obs_offset[l], n = w.lm_obs_offset[l + 1] - o0;
       h_lm_off[lb + j] = run;
       memcpy(h_obs_frame + run, w.obs_frame + o0, n * I);
@@ -417,7 +436,8 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
     }
     memcpy(h_ex + (size_t)b * 7, w.para_ex_pose, 7 * D);
     h_td0[b] = w.para_td ? w.para_td[0] : 0.0;
-    for (int j = 0; j < w.L; j++) h_invd0[lb + j] = w.inv_depth[perm[j]];
+    if (grouped) memcpy(h_invd0 + lb, w.inv_depth, (size_t)w.L * D);
+    else for (int j = 0; j < w.L; j++) h_invd0[lb + j] = w.inv_depth[perm[j]];
     memcpy(h_pre + (size_t)b * K * PREINT_DOUBLES, w.preint, (size_t)Kc * sizeof(bvio_preint));
     if (relo) {
       double* pr = h_pre + ((size_t)b * K + Kc) * PREINT_DOUBLES;

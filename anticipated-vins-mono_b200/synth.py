@@ -347,7 +347,31 @@ def slice_window(w: "Window", f0: int, K: int):
 def make_session(seed, K=11, L=1500, track_min=6):
     """A (K+1)-frame session from which two CONSECUTIVE K-frame windows are cut (bench.py builds its pool of windows with
     real marginalized priors from these): ~L landmarks in either window."""
-    return make_window(seed=seed, K=K + 1, L=int(L * 1.04), track_min=track_min, track_max=K + 1)
+    return feature_manager_order(make_window(seed=seed, K=K + 1, L=int(L * 1.04), track_min=track_min, track_max=K + 1))
+
+
+def feature_manager_order(w: "Window") -> "Window":
+    """The same window with its landmarks in the order FeatureManager's list holds them: features are appended when
+    they are first seen (feature_manager.cpp:46-97), so start frames never decrease along the list (stable: ties keep
+    their order).  make_window() draws start frames at random; a session that stands for the reference's traffic is
+    sorted once here and every window sliced from it inherits the order."""
+    start = w.obs_frame[w.lm_obs_offset[:-1]]
+    order = np.argsort(start, kind="stable")
+    n = np.diff(w.lm_obs_offset)[order]
+    offs = np.concatenate([[0], np.cumsum(n)]).astype(np.int32)
+    obs = np.concatenate([np.arange(w.lm_obs_offset[l], w.lm_obs_offset[l + 1]) for l in order]) if len(order) else np.zeros(0, int)
+    out = w.copy()
+    out.inv_depth = w.inv_depth[order].copy()
+    out.lm_obs_offset = offs
+    out.obs_frame = w.obs_frame[obs].copy()
+    out.obs_xy = w.obs_xy[obs].copy()
+    for name in ("obs_vel", "obs_td", "obs_row"):
+        if getattr(w, name, None) is not None:
+            setattr(out, name, getattr(w, name)[obs].copy())
+    if w.gt_inv_depth is not None:
+        out.gt_inv_depth = w.gt_inv_depth[order].copy()
+    assert w.relo_lm is None or len(w.relo_lm) == 0, "sort before adding relocalization matches"
+    return out
 
 
 def consecutive_window(session: "Window", first_solved: "Window", first_idx, prior: dict, K=11):
