@@ -1229,11 +1229,18 @@ __global__ void __launch_bounds__(IMU_THREADS, 2) ba_imu_prior_kernel(BaBatch bt
 constexpr int WS_THREADS = 512, WS_ROLE = 256;
 #ifdef BVIO_WS_PROF   // development build only (make WSPROF=1): cycles per role / phase, summed over CTAs, printed at bvio_destroy
 __device__ unsigned long long g_ws_prof[16 + 16 * 16];   // [16 + 16 * (8 * role + warp) + phase] per-warp phase cycles
+#define WSP_DECL() __shared__ unsigned long long s_wsp[16 * 16]
+#define WSP_INIT() do { for (int i_ = threadIdx.x; i_ < 256; i_ += blockDim.x) s_wsp[i_] = 0; } while (0)
 #define WSP_T0() long long wsp_t = clock64()
-#define WSP_ADD(i) do { const long long n_ = clock64(); if (lane == 0) atomicAdd(&g_ws_prof[16 + 16 * (8 * role + wp) + (i)], (unsigned long long)(n_ - wsp_t)); wsp_t = n_; } while (0)
+// accumulated per CTA in shared memory (a global atomic per probe would queue up in the LSU and distort what follows)
+#define WSP_ADD(i) do { const long long n_ = clock64(); if (lane == 0) s_wsp[16 * (8 * role + wp) + (i)] += (unsigned long long)(n_ - wsp_t); wsp_t = clock64(); } while (0)
+#define WSP_FLUSH() do { if (lane == 0) for (int i_ = 0; i_ < 16; i_++) atomicAdd(&g_ws_prof[16 + 16 * (8 * role + wp) + i_], s_wsp[16 * (8 * role + wp) + i_]); } while (0)
 #define WSP_CHUNK() atomicAdd(&g_ws_prof[15], 1ull)
 #else
 #define WSP_CHUNK() do {} while (0)
+#define WSP_DECL() do {} while (0)
+#define WSP_INIT() do {} while (0)
+#define WSP_FLUSH() do {} while (0)
 #define WSP_T0() do {} while (0)
 #define WSP_ADD(i) do {} while (0)
 #endif
@@ -1281,6 +1288,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     return u;
   };
 
+  WSP_DECL();
+  WSP_INIT();
   for (int i = threadIdx.x; i < NPb * 36 + 3 * K6 + K * 8 * 28; i += WS_THREADS) sAcc[i] = 0.0;
   if (threadIdx.x < 2 * STG) dbl[(threadIdx.x / STG) * ws_buf_doubles(WS) + threadIdx.x % STG] = 0.0;   // the zero records
   stage_frames(bt, w, bt.pose[cur], bt.exs[cur], sFr, sEx);
@@ -1453,6 +1462,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
       const int REC = NPb * 36 + 3 * K6;
       out[REC] = cs; out[REC + 1] = gm; out[REC + 2] = 0; out[REC + 3] = 0;
     }
+    WSP_FLUSH();
     return;
   }
 
@@ -1514,6 +1524,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     const int nq = u.meta[1];
     for (int iq = 0; iq < nq; iq++) {
       const int qe = u.qlist[iq], q = qe & 255, lq0 = (qe >> 8) & 255, lq1 = qe >> 16;
+      WSP_ADD(14);
       if (q != curq) {
         if (curq >= 0) flush_ata(curq);
         curq = q;
@@ -1556,7 +1567,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
       }
       WSP_ADD(12);
     }
-    WSP_ADD(14);
+    WSP_ADD(7);
     // ---- P1: S -= W^T diag(1/(h+d)) W (register tiles; the row scaling rides on the A fragment)
     if (GROUPED) {
       const double* wb = u.w + tq * WS + g;
@@ -1675,13 +1686,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     out[NPb * 36 + K6 + i] = sGb[i];
     out[NPb * 36 + 2 * K6 + i] = sDg[i];
   }
+  WSP_FLUSH();
 }
 
 void ba_ws_prof_dump(void) {
 #ifdef BVIO_WS_PROF
   static unsigned long long h[16 + 256];
   if (cudaMemcpyFromSymbol(h, g_ws_prof, sizeof h) != cudaSuccess || !h[15]) return;
-  const char* nm[16] = {"extent", "waitEMPTY", "zero", "-", "A1", "A2", "arrive", "", "waitFULL", "AtA", "P1", "P2a", "P2b", "scan+flush", "scan tail", ""};
+  const char* nm[16] = {"extent", "waitEMPTY", "zero", "-", "A1", "A2", "arrive", "q tail", "waitFULL", "AtA", "P1", "P2a", "P2b", "flush", "read qlist", ""};
   fprintf(stderr, "[ws prof] %llu chunks; cycles per chunk per warp\n", h[15]);
   for (int r = 0; r < 2; r++)
     for (int i = 0; i < 15; i++) {
@@ -2475,9 +2487,9 @@ int ba_configure(void) {
 #undef BVIO_LIN_ATTR
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 76>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_linearize_ws_kernel<6, 76>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_ws_kernel<6, 76>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_imu_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(ba_linearize_ws_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(ba_linearize_ws_kernel<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_linearize_mma_kernel<10, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(ba_solve_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return err;
@@ -2525,7 +2537,7 @@ int ba_launch_iteration(const BaBatch& bt, cudaStream_t st, bool with_step, cuda
     const int NT = mm_ntile(bt.K);
     const size_t smw = ba_linearize_ws_smem_bytes(bt.K);
     // throughput mode: producers / consumers overlapped in one 512-thread CTA per SM
-    if (bt.use_ws && NT * (NT + 1) / 2 <= 48 && smw <= 227 * 1024) {
+    if (bt.use_ws && NT * (NT + 1) / 2 <= 48 && smw <= 224 * 1024) {
       const dim3 gv(bt.TL, bt.B);
       // (the IMU / prior kernel on a second stream beside the tiles was measured: no gain, the tiles' four waves end together)
       ba_imu_prior_kernel<<<bt.B, IMU_THREADS, s1b, st>>>(bt);
