@@ -1395,10 +1395,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
           cc2[a] = sr * (-dot3(uu, dimu) / lam);   // (a true division: bit-compatible with the latency-mode kernel)
         }
         st[24] = cc2[0]; st[25] = cc2[1]; st[26] = sr * r0; st[27] = sr * r1;
-        double* wo = u.w + lc * WS + 6 * fj;
-        double* wg = bt.w + (size_t)ko * 6;
+        // 16-byte stores: rows of W~ and of bt.w start at even double offsets (WS, 6 fj and 6 ko are even)
+        double2* wo = reinterpret_cast<double2*>(u.w + lc * WS + 6 * fj);
+        double2* wg = reinterpret_cast<double2*>(bt.w + (size_t)ko * 6);
 #pragma unroll
-        for (int k = 0; k < 6; k++) { const double v = Bv[0][k] * cc2[0] + Bv[1][k] * cc2[1]; wo[k] = v; wg[k] = v; }
+        for (int k = 0; k < 3; k++) {
+          const double2 v{Bv[0][2 * k] * cc2[0] + Bv[1][2 * k] * cc2[1], Bv[0][2 * k + 1] * cc2[0] + Bv[1][2 * k + 1] * cc2[1]};
+          wo[k] = v; wg[k] = v;
+        }
       }
       bar_sync(BAR_PROD, WS_ROLE);
       WSP_ADD(4);
@@ -1425,9 +1429,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
         }
         const double va = x0 + y0, vb = x1 + y1;
         if (part < 3) {
-          double* wo = u.w + lc * WS + 6 * u.anc[lc] + 2 * part;
-          double* wg = bt.w + (size_t)u.o0[lc] * 6 + 2 * part;
-          wo[0] = va; wo[1] = vb; wg[0] = va; wg[1] = vb;
+          *reinterpret_cast<double2*>(u.w + lc * WS + 6 * u.anc[lc] + 2 * part) = double2{va, vb};
+          *reinterpret_cast<double2*>(bt.w + (size_t)u.o0[lc] * 6 + 2 * part) = double2{va, vb};
         } else {
           const double h = va;
           u.w[lc * WS + K6] = vb;                      // column 6K of W: b_l => row 6K of P1 = Schur gradient term
@@ -2133,9 +2136,13 @@ __global__ void __launch_bounds__(BA_THREADS) ba_dogleg_kernel(BaBatch bt) {
       const int ko = l16 + 8 * trip;
       if (ko < n) {
         const int fr = bt.obs_frame[o0 + ko];
-        const double* wp = bt.w + (size_t)(o0 + ko) * 6;
+        const double2* wp = reinterpret_cast<const double2*>(bt.w + (size_t)(o0 + ko) * 6);   // 48-byte rows: three 16-byte loads
 #pragma unroll
-        for (int k = 0; k < 6; k++) { wn += wp[k] * sn[15 * fr + k]; wt += wp[k] * st[15 * fr + k]; }
+        for (int k = 0; k < 3; k++) {
+          const double2 v = wp[k];
+          wn += v.x * sn[15 * fr + 2 * k]; wt += v.x * st[15 * fr + 2 * k];
+          wn += v.y * sn[15 * fr + 2 * k + 1]; wt += v.y * st[15 * fr + 2 * k + 1];
+        }
       }
     }
     if (l16 == 0 && (bt.est_ex | bt.est_td)) {      // extra blocks: extrinsic (6) and / or td (column 0 of its slot)
@@ -2281,16 +2288,16 @@ __global__ void __launch_bounds__(BA_THREADS, MINB) ba_cost_kernel(BaBatch bt) {
       if (l16 + 8 < n) fr1 = bt.obs_frame[o0 + l16 + 8];
       if (!dogleg) {
         if (l16 < n) {
-          const double* wp = bt.w + (size_t)(o0 + l16) * 6;
+          const double2* wp = reinterpret_cast<const double2*>(bt.w + (size_t)(o0 + l16) * 6);   // 48-byte rows: three 16-byte loads
           const double* d = sdp + 15 * fr0;
 #pragma unroll
-          for (int k = 0; k < 6; k++) part += wp[k] * d[k];
+          for (int k = 0; k < 3; k++) { const double2 v = wp[k]; part += v.x * d[2 * k]; part += v.y * d[2 * k + 1]; }
         }
         if (l16 + 8 < n) {
-          const double* wp = bt.w + (size_t)(o0 + l16 + 8) * 6;
+          const double2* wp = reinterpret_cast<const double2*>(bt.w + (size_t)(o0 + l16 + 8) * 6);
           const double* d = sdp + 15 * fr1;
 #pragma unroll
-          for (int k = 0; k < 6; k++) part += wp[k] * d[k];
+          for (int k = 0; k < 3; k++) { const double2 v = wp[k]; part += v.x * d[2 * k]; part += v.y * d[2 * k + 1]; }
         }
         if (l16 == 0 && (bt.est_ex | bt.est_td)) {
           const double* we = bt.wex + (size_t)l * (bt.est_ex + bt.est_td) * 6;
