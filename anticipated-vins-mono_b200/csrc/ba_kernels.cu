@@ -1276,7 +1276,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
   double* sGr = sGb + K6;                            // [K6]
   double* sDg = sGr + K6;                            // [K6]
   double* sAtA = sDg + K6;                           // [K][8 warps][28] lower triangle of the split-K AtA partials
-  double* dbl = sAtA + K * 8 * 28;
+  double* sPiece = sAtA + K * 8 * 28;                // [MM_CL][2 pieces][8] per-landmark sums of the current chunk (producers)
+  double* dbl = sPiece + MM_CL * 16;
   int* ints = reinterpret_cast<int*>(dbl + 2 * ws_buf_doubles(WS));
   short* shorts = reinterpret_cast<short*>(ints + 2 * ws_buf_ints());
   auto buffer = [&](int b) {
@@ -1347,6 +1348,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
       WSP_ADD(2);
       WSP_ADD(3);
       // ---- A1: factor evaluation, one factor per thread
+      double red8[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // this factor's share of its landmark's sums: A^T c (6), c^T c, c^T r
+      int lcs = -1, fss = 0;                           // landmark / its first factor slot (-1: idle thread)
       if (tid < nfac) {
         int lc = 0;                                    // the landmark of factor slot tid: the last one with first[lc] <= tid
         for (int hi = nl; hi - lc > 1;) { const int mid = (lc + hi) >> 1; if (u.first[mid] <= tid) lc = mid; else hi = mid; }
@@ -1380,14 +1383,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
         const double sr = sqrt(fmax(DBL_MIN, 1.0 / csum));
         double* st = u.fac + (size_t)tid * STG;
         const d3 dimu = gm.pimu_i - d3{sEx[9], sEx[10], sEx[11]};
-        double cc2[2], Bv[2][6];
+        double cc2[2], Av[2][6], Bv[2][6];
 #pragma unroll
         for (int a = 0; a < 2; a++) {
           const d3 uu = mtv3(Fi, d3{Q[a][0], Q[a][1], Q[a][2]});              // Ri^T Q[a]^T
           const d3 jr = cross3(gm.pimu_i, uu);                               // -(Q Ri [pts_imu_i]x) row
           const d3 jjr = cross3(d3{Gm[a][0], Gm[a][1], Gm[a][2]}, gm.pimu_j); // (Gm [pts_imu_j]x) row
-          st[a * 6 + 0] = sr * Q[a][0]; st[a * 6 + 1] = sr * Q[a][1]; st[a * 6 + 2] = sr * Q[a][2];
-          st[a * 6 + 3] = sr * jr.x; st[a * 6 + 4] = sr * jr.y; st[a * 6 + 5] = sr * jr.z;
+          Av[a][0] = sr * Q[a][0]; Av[a][1] = sr * Q[a][1]; Av[a][2] = sr * Q[a][2];
+          Av[a][3] = sr * jr.x; Av[a][4] = sr * jr.y; Av[a][5] = sr * jr.z;
+#pragma unroll
+          for (int k = 0; k < 6; k++) st[a * 6 + k] = Av[a][k];
           Bv[a][0] = -sr * Q[a][0]; Bv[a][1] = -sr * Q[a][1]; Bv[a][2] = -sr * Q[a][2];
           Bv[a][3] = sr * jjr.x; Bv[a][4] = sr * jjr.y; Bv[a][5] = sr * jjr.z;
 #pragma unroll
@@ -1395,6 +1400,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
           cc2[a] = sr * (-dot3(uu, dimu) / lam);   // (a true division: bit-compatible with the latency-mode kernel)
         }
         st[24] = cc2[0]; st[25] = cc2[1]; st[26] = sr * r0; st[27] = sr * r1;
+#pragma unroll
+        for (int k = 0; k < 6; k++) red8[k] = Av[0][k] * cc2[0] + Av[1][k] * cc2[1];
+        red8[6] = cc2[0] * cc2[0] + cc2[1] * cc2[1];
+        red8[7] = cc2[0] * (sr * r0) + cc2[1] * (sr * r1);
+        lcs = lc; fss = fs;
         // 16-byte stores: rows of W~ and of bt.w start at even double offsets (WS, 6 fj and 6 ko are even)
         double2* wo = reinterpret_cast<double2*>(u.w + lc * WS + 6 * fj);
         double2* wg = reinterpret_cast<double2*>(bt.w + (size_t)ko * 6);
@@ -1404,46 +1414,66 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
           wo[k] = v; wg[k] = v;
         }
       }
+      // per-landmark sums: the factors of a landmark sit in consecutive threads, so a segmented scan over the warp
+      // (shuffles, fixed order) leaves the sum of each run in its last thread; a landmark that straddles two warps
+      // (<= 15 factors: never more) leaves two pieces, added in slot order by A2
+#pragma unroll
+      for (int off = 1; off < 16; off <<= 1) {
+        const int lo = __shfl_up_sync(0xffffffffu, lcs, off);
+        const bool take = lane >= off && lo == lcs && lcs >= 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const double o = __shfl_up_sync(0xffffffffu, red8[k], off);
+          if (take) red8[k] += o;
+        }
+      }
+      {
+        const int ln = __shfl_down_sync(0xffffffffu, lcs, 1);
+        if (lcs >= 0 && (lane == 31 || ln != lcs)) {
+          double2* o = reinterpret_cast<double2*>(sPiece + (2 * lcs + (fss < (tid & ~31) ? 1 : 0)) * 8);
+#pragma unroll
+          for (int k = 0; k < 4; k++) o[k] = double2{red8[2 * k], red8[2 * k + 1]};
+        }
+      }
       bar_sync(BAR_PROD, WS_ROLE);
       WSP_ADD(4);
-      // ---- A2: four threads per landmark: A^T c (the anchor's w, two components each of three threads), and on the
-      //      fourth h = sum c^T c with the damping of the eliminated depth (Ceres LevenbergMarquardtStrategy / dogleg mu,
-      //      Jacobi scaling) and b = sum c^T r.  Two independent accumulation chains per output.
-      if (tid == WS_ROLE - 1) {                        // anchors present in this chunk, for the consumers' loops
-        int n = 0;
-        for (int q = 0; q < K; q++) { const int a = u.qlo[q], e = u.qhi[q]; if (e > a) u.qlist[n++] = q | (a << 8) | (e << 16); }
-        u.meta[1] = n;
+      // ---- A2: one thread per landmark adds the pieces: A^T c (the anchor's w), h = sum c^T c with the damping of the
+      //      eliminated depth (Ceres LevenbergMarquardtStrategy / dogleg mu, Jacobi scaling), b = sum c^T r
+      if (wp == 7 && lane < K) {                       // anchors present in this chunk, for the consumers' loops
+        const int a = u.qlo[lane], e = u.qhi[lane];
+        const unsigned present = __ballot_sync((1u << K) - 1u, e > a);
+        if (e > a) u.qlist[__popc(present & ((1u << lane) - 1u))] = lane | (a << 8) | (e << 16);
+        if (lane == 0) u.meta[1] = __popc(present);
       }
-      if (tid < 4 * nl) {
-        const int lc = tid >> 2, part = tid & 3, l = lb + lc;
-        const int nf = u.nobs[lc] - 1;
-        const double* st = u.fac + (size_t)u.first[lc] * STG;
+      if (tid < nl) {
+        const int lc = tid, l = lb + lc, fs = u.first[lc], nf = u.nobs[lc] - 1;
         double sl2 = 1.0;                              // Jacobi scale^2 of the depth column: fixed at the first linearization
-        if (part == 3 && bt.jacobi_scaling && !first) sl2 = bt.sl2[l];   // (issued ahead of the reduction loop)
-        const int ea = part < 3 ? 2 * part : 24, eb = part < 3 ? 6 + 2 * part : 25, ec = part < 3 ? 2 * part + 1 : 26, ed = part < 3 ? 7 + 2 * part : 27;
-        double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-        for (int f = 0; f < nf; f++, st += STG) {
-          const double c0 = st[24], c1 = st[25];
-          x0 += st[ea] * c0; y0 += st[eb] * c1;
-          x1 += st[ec] * c0; y1 += st[ed] * c1;
+        if (bt.jacobi_scaling && !first) sl2 = bt.sl2[l];
+        double t8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (nf > 0) {
+          const double2* p0 = reinterpret_cast<const double2*>(sPiece + 2 * lc * 8);
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const double2 v = p0[k]; t8[2 * k] = v.x; t8[2 * k + 1] = v.y; }
+          if ((fs >> 5) != ((fs + nf - 1) >> 5)) {     // the run crosses a warp boundary: second piece
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const double2 v = p0[4 + k]; t8[2 * k] += v.x; t8[2 * k + 1] += v.y; }
+          }
         }
-        const double va = x0 + y0, vb = x1 + y1;
-        if (part < 3) {
-          *reinterpret_cast<double2*>(u.w + lc * WS + 6 * u.anc[lc] + 2 * part) = double2{va, vb};
-          *reinterpret_cast<double2*>(bt.w + (size_t)u.o0[lc] * 6 + 2 * part) = double2{va, vb};
-        } else {
-          const double h = va;
-          u.w[lc * WS + K6] = vb;                      // column 6K of W: b_l => row 6K of P1 = Schur gradient term
-          gmax_t = fmax(gmax_t, fabs(vb));
-          bt.b[l] = vb;
-          if (bt.jacobi_scaling && first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
-          const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, dfac);
-          double inv_hd = 1.0 / (h + ddl);
-          if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
-          u.sc[lc * 4] = inv_hd;
-          bt.h[l] = h;
-          if (first) bt.sl2[l] = sl2;
-        }
+        double2* wo = reinterpret_cast<double2*>(u.w + lc * WS + 6 * u.anc[lc]);
+        double2* wg = reinterpret_cast<double2*>(bt.w + (size_t)u.o0[lc] * 6);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const double2 v{t8[2 * k], t8[2 * k + 1]}; wo[k] = v; wg[k] = v; }
+        const double h = t8[6], vb = t8[7];
+        u.w[lc * WS + K6] = vb;                        // column 6K of W: b_l => row 6K of P1 = Schur gradient term
+        gmax_t = fmax(gmax_t, fabs(vb));
+        bt.b[l] = vb;
+        if (bt.jacobi_scaling && first) { const double q = 1.0 / (1.0 + sqrt(h)); sl2 = q * q; }
+        const double ddl = damp_term(fmin(fmax(sl2 * h, 1e-6), 1e32), sl2, dfac);
+        double inv_hd = 1.0 / (h + ddl);
+        if (bt.undamped) inv_hd = (h > 0) ? 1.0 / h : 0.0;
+        u.sc[lc * 4] = inv_hd;
+        bt.h[l] = h;
+        if (first) bt.sl2[l] = sl2;
       }
       WSP_ADD(5);
       __threadfence_block();
@@ -1503,6 +1533,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
       for (int e = 0; e < 3; e++) accG[a][e][0] = accG[a][e][1] = 0.0;
   }
   double accD[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+  // P2a frames go to warps 0 .. npw-1 (two each): with K <= 12 the two top warps take none -- they carry the P2b blocks
+  // (p, q) next to the diagonal, present for every anchor q, while the low warps' P2b blocks only exist for small q
+  const int npw = K <= 12 ? 6 : 8;
   int curq = -1;                                       // anchor frame the AtA partials belong to
   double ata[4] = {0, 0, 0, 0};
   // this warp's split-K partial of AtA(q) goes to its own shared-memory slot (no barrier); summed over the warps at the end
@@ -1612,8 +1645,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     // ---- P2a: diagonal blocks (p, p) from the factors seen in frame p (non-anchor side); four independent chains
 #pragma unroll
     for (int uu = 0; uu < 2; uu++) {
-      const int p = wp + 8 * uu;
-      if (p >= K) continue;
+      const int p = wp + npw * uu;
+      if (wp >= npw || p >= K) continue;
       const short* sl = u.slot + (tq >> 1) * K + p;
       const double* px = u.fac + (g < 6 ? 12 + 6 * (tq & 1) + g : g == 6 ? 26 + (tq & 1) : -STG);
       for (int lc = 0; lc < nl; lc += 8, sl += 8 * K) {
@@ -1647,8 +1680,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
   bar_sync(BAR_CONS, WS_ROLE);
 #pragma unroll
   for (int uu = 0; uu < 2; uu++) {
-    const int p = wp + 8 * uu;
-    if (p >= K) continue;
+    const int p = wp + npw * uu;
+    if (wp >= npw || p >= K) continue;
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const int m = g, n = 2 * tq + e;
@@ -1709,7 +1742,7 @@ void ba_ws_prof_dump(void) {
 }
 size_t ba_linearize_ws_smem_bytes(int K) {
   const int NPb = K * (K + 1) / 2, WS = mm_wstride(K);
-  size_t d = (size_t)(K + 1) * FR + 32 + (size_t)NPb * 36 + 18 * K + (size_t)K * 8 * 28 + 2 * ws_buf_doubles(WS);
+  size_t d = (size_t)(K + 1) * FR + 32 + (size_t)NPb * 36 + 18 * K + (size_t)K * 8 * 28 + MM_CL * 16 + 2 * ws_buf_doubles(WS);
   size_t bytes = d * sizeof(double) + 2 * ws_buf_ints() * sizeof(int) + 2 * ws_buf_shorts(K) * sizeof(short);
   return (bytes + 15) & ~size_t(15);
 }
