@@ -552,3 +552,25 @@ def test_ws_batch_equals_single_solves(env):
         assert s.iterations == it
         assert np.linalg.norm(h.state_vector() - x) <= 1e-9 * np.linalg.norm(x), i
         assert abs(s.final_cost - c) <= 1e-9 * c
+
+
+def test_landmark_order_does_not_matter(env):
+    """Windows in FeatureManager's list order are packed with bulk copies, any other order landmark by landmark after a
+    host-side sort by anchor: same problem, same answer (per landmark), alone and in a batch that mixes both."""
+    abi, synth, orc, ctx = env
+    w = synth.make_window(seed=12, K=11, L=200)
+    ws = synth.feature_manager_order(w)
+    order = np.argsort(w.obs_frame[w.lm_obs_offset[:-1]], kind="stable")
+    o = abi.default_opts(max_iters=8, strategy=1)
+    h1, h2, s1, s2 = abi.WindowHandle(w), abi.WindowHandle(ws), abi.Summary(), abi.Summary()
+    ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h1.s), C.byref(o), C.byref(s1)), "optimize")
+    ctx.check(ctx.L.bvio_optimize(ctx.h, C.byref(h2.s), C.byref(o), C.byref(s2)), "optimize")
+    assert s1.iterations == s2.iterations and abs(s1.final_cost - s2.final_cost) <= 1e-12 * s1.final_cost
+    assert np.abs(h1.pose - h2.pose).max() <= 1e-12 and np.abs(h2.inv - h1.inv[order]).max() <= 1e-12 * np.abs(h1.inv).max()
+    hs = [abi.WindowHandle(w if i % 2 else ws) for i in range(20)]
+    arr = (abi.WindowS * 20)(*[h.s for h in hs])
+    sums = (abi.Summary * 20)()
+    ctx.check(ctx.L.bvio_optimize_batch(ctx.h, arr, 20, C.byref(o), sums), "optimize_batch")
+    for i, h in enumerate(hs):
+        ref = h1 if i % 2 else h2
+        assert np.abs(h.pose - ref.pose).max() <= 1e-12 and np.abs(h.inv - ref.inv).max() <= 1e-12 * np.abs(ref.inv).max()

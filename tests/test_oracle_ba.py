@@ -411,3 +411,25 @@ def test_window_omega_prior_is_the_schur_complement(pkg, oracle):
         assert np.abs(om - want).max() <= 1e-8 * np.abs(want).max()
         assert np.abs(om - om.T).max() <= 1e-9 * np.abs(om).max() and np.linalg.eigvalsh(0.5 * (om + om.T)).min() > 0
         assert np.abs(om - np.eye(9)).max() > 10.0
+
+
+def test_feature_manager_order_is_a_relabelling(pkg, oracle):
+    """synth.feature_manager_order sorts the landmarks by their first frame (FeatureManager's list order, stable): the
+    window is the same problem -- same cost and, landmark by landmark, the same solution."""
+    import ctypes as C
+    abi, synth = pkg.abi, pkg.synth
+    w = synth.make_window(seed=11, K=11, L=80)
+    ws = synth.feature_manager_order(w)
+    start, start_s = w.obs_frame[w.lm_obs_offset[:-1]], ws.obs_frame[ws.lm_obs_offset[:-1]]
+    assert (np.diff(start_s) >= 0).all() and not (np.diff(start) >= 0).all()
+    order = np.argsort(start, kind="stable")
+    assert np.array_equal(ws.inv_depth, w.inv_depth[order]) and ws.n_factors == w.n_factors
+    for l_new, l_old in enumerate(order[:10]):
+        a, b = slice(ws.lm_obs_offset[l_new], ws.lm_obs_offset[l_new + 1]), slice(w.lm_obs_offset[l_old], w.lm_obs_offset[l_old + 1])
+        assert np.array_equal(ws.obs_frame[a], w.obs_frame[b]) and np.array_equal(ws.obs_xy[a], w.obs_xy[b])
+    o = abi.default_opts(max_iters=6)
+    h1, h2, s1, s2 = abi.WindowHandle(w), abi.WindowHandle(ws), abi.Summary(), abi.Summary()
+    assert oracle.oracle_optimize(C.byref(h1.s), C.byref(o), C.byref(s1)) == 0
+    assert oracle.oracle_optimize(C.byref(h2.s), C.byref(o), C.byref(s2)) == 0
+    assert abs(s1.final_cost - s2.final_cost) <= 1e-10 * s1.final_cost
+    assert np.abs(h2.inv - h1.inv[order]).max() <= 1e-9 * np.abs(h1.inv).max()
