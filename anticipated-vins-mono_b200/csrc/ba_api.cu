@@ -224,12 +224,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
     auto work = [&](int t) {
       for (int b = t; b < B && rcs[t] == BVIO_OK; b += nthreads) rcs[t] = validate_msg(ws + b, o, Kc, &msgs[t]);
     };
-    if (nthreads == 1) work(0);
-    else {
-      std::vector<std::thread> th;
-      for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
-      for (auto& x : th) x.join();
-    }
+    ctx->pool.run(nthreads, work);
     for (int t = 0; t < nthreads; t++) if (rcs[t]) return fail(ctx, rcs[t], msgs[t]);
   }
   for (int b = 0; b < B; b++) {
@@ -468,14 +463,7 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
   {
     int nthreads = pack_threads();
     if (B < 16) nthreads = 1;
-    if (nthreads <= 1) {
-      for (int b = 0; b < B; b++) pack(b);
-    } else {
-      std::vector<std::thread> th;
-      for (int t = 0; t < nthreads; t++)
-        th.emplace_back([&, t]() { for (int b = t; b < B; b += nthreads) pack(b); });
-      for (auto& x : th) x.join();
-    }
+    ctx->pool.run(nthreads, [&](int t) { for (int b = t; b < B; b += nthreads) pack(b); });
   }
   h_lm_base[B] = bb->lm_base[B];
   h_lm_off[total_L] = obs_base[B];
@@ -605,9 +593,7 @@ static int unpack_outputs(bvio_ctx* ctx, bvio_batch* bb, bvio_window* windows, b
   };
   if (windows && bt.B >= 64) {
     const int nthreads = pack_threads();
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads; t++) th.emplace_back([&, t]() { for (int b = t; b < bt.B; b += nthreads) scatter(b); });
-    for (auto& x : th) x.join();
+    ctx->pool.run(nthreads, [&](int t) { for (int b = t; b < bt.B; b += nthreads) scatter(b); });
   }
   for (int b = 0; b < bt.B; b++) {
     if (windows && bt.B < 64) scatter(b);
