@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <thread>
 
@@ -460,11 +461,6 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
       memcpy(h_pr_res + (size_t)b * nmax, p->lin_res, (size_t)p->n * D);
     }
   };
-  {
-    int nthreads = pack_threads();
-    if (B < 16) nthreads = 1;
-    ctx->pool.run(nthreads, [&](int t) { for (int b = t; b < B; b += nthreads) pack(b); });
-  }
   h_lm_base[B] = bb->lm_base[B];
   h_lm_off[total_L] = obs_base[B];
 
@@ -497,6 +493,13 @@ static int upload_impl(bvio_ctx* ctx, const bvio_window* ws, int B, const bvio_o
 
   // pipeline slots upload on the copy stream so that the H2D overlaps the previous sub-batch's kernels
   cudaStream_t up = cache_slot >= 1 ? ctx->copy_stream : ctx->stream;
+  {
+    // (packing and copying in four chunks of windows, so that the H2D of one chunk overlaps the packing of the next, was
+    // measured: no gain -- the host side of a sub-batch is 2.9 ms, bound by host memory bandwidth, BVIO_DEBUG=1 prints it)
+    int nthreads = pack_threads();
+    if (B < 16) nthreads = 1;
+    ctx->pool.run(nthreads, [&](int t) { for (int b = t; b < B; b += nthreads) pack(b); });
+  }
   cudaError_t e = cudaMemcpyAsync(d, h, bb->in_bytes, cudaMemcpyHostToDevice, up);
   if (e == cudaSuccess) { ctx->launches += ba_launch_prepare(bt, up); e = cudaGetLastError(); }
   if (e == cudaSuccess && up != ctx->stream) {
@@ -654,19 +657,33 @@ int bvio_optimize_batch(bvio_ctx* ctx, bvio_window* windows, int32_t B, const bv
   int b0[bvio_ctx::PIPE + 1];
   for (int i = 0; i <= S; i++) b0[i] = (int)((long long)B * i / S);
   int rc = BVIO_OK;
+  const bool dbg = getenv("BVIO_DEBUG") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  double t_up[bvio_ctx::PIPE] = {0}, t_enq[bvio_ctx::PIPE] = {0};
   for (int i = 0; i < S && rc == BVIO_OK; i++) {
+    const double ta = now();
     rc = upload_impl(ctx, windows + b0[i], b0[i + 1] - b0[i], opts, 1 + i, 0, &sub[i]);
     if (rc) break;
+    t_up[i] = now() - ta;
     sub[i]->use_graph = false;
     rc = bvio_batch_solve(ctx, sub[i]);
     if (rc == BVIO_OK) rc = enqueue_d2h(ctx, sub[i]);
+    t_enq[i] = now() - ta - t_up[i];
   }
+  const double t1 = now();
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  const double t2 = now();
   if (rc == BVIO_OK && e != cudaSuccess) rc = fail(ctx, BVIO_ERR_CUDA, std::string("optimize_batch: ") + cudaGetErrorString(e));
   for (int i = 0; i < S; i++) {
     if (!sub[i]) continue;
     if (rc == BVIO_OK) rc = unpack_outputs(ctx, sub[i], windows + b0[i], summaries ? summaries + b0[i] : nullptr);
     bvio_batch_free(ctx, sub[i]);
+  }
+  if (dbg) {
+    fprintf(stderr, "[bvio] optimize_batch B=%d in %d sub-batches: total %.2f ms = host until last enqueue %.2f (", B, S, now() - t0, t1 - t0);
+    for (int i = 0; i < S; i++) fprintf(stderr, "upload %.2f + enqueue %.2f%s", t_up[i], t_enq[i], i + 1 < S ? ", " : "");
+    fprintf(stderr, ") + wait for the GPU %.2f + unpack %.2f\n", t2 - t1, now() - t2);
   }
   return rc;
 }
