@@ -1513,25 +1513,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     }
     accW[s][0] = accW[s][1] = 0.0;
   }
-  // NT == 9 (K = 11, the reference's window): the 45 lower tiles are dealt out as 3 x 3 groups that share their
-  // fragments -- warps 0-2 the diagonal triangles of tile rows {0,1,2}, {3,4,5}, {6,7,8} (3 loads for 6 tiles),
-  // warps 3-7 rectangles (rows x three columns): {3,4}x{0-2}, {6,7}x{0-2}, {6,7}x{3-5}, {5,8}x{0-2}, {8}x{3-5}
-  // (5 loads for 6 tiles) -- instead of two loads per tile.
-  constexpr bool GROUPED = false;   // measured: 1.30 -> 1.43 ms per pass with the grouped tiles (kept for reference, off)
-  int gr[3] = {0, 0, 0}, gc0 = 0;
-  unsigned gmask = 0;
-  bool gtri = false;
-  double accG[3][3][2];
-  if (GROUPED) {
-    const int R0[8] = {0, 3, 6, 3, 6, 6, 5, 8}, R1[8] = {1, 4, 7, 4, 7, 7, 8, 8}, R2[8] = {2, 5, 8, 4, 7, 7, 8, 8};
-    const int C0[8] = {0, 3, 6, 0, 0, 3, 0, 3};
-    const unsigned MK[8] = {0x1d9, 0x1d9, 0x1d9, 0x03f, 0x03f, 0x03f, 0x03f, 0x007};   // bit 3 * ri + ci; 0x1d9 = lower triangle
-    gr[0] = 8 * R0[wp]; gr[1] = 8 * R1[wp]; gr[2] = 8 * R2[wp]; gc0 = 8 * C0[wp]; gmask = MK[wp]; gtri = wp < 3;
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int e = 0; e < 3; e++) accG[a][e][0] = accG[a][e][1] = 0.0;
-  }
   double accD[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
   // P2a frames go to warps 0 .. npw-1 (two each): with K <= 12 the two top warps take none -- they carry the P2b blocks
   // (p, q) next to the diagonal, present for every anchor q, while the low warps' P2b blocks only exist for small q
@@ -1605,28 +1586,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
     }
     WSP_ADD(7);
     // ---- P1: S -= W^T diag(1/(h+d)) W (register tiles; the row scaling rides on the A fragment)
-    if (GROUPED) {
-      const double* wb = u.w + tq * WS + g;
-      const double* pr0 = wb + gr[0]; const double* pr1 = wb + gr[1]; const double* pr2 = wb + gr[2]; const double* pc = wb + gc0;
-#pragma unroll
-      for (int kk = 0; kk < MM_CL / 4; kk++) {
-        if (4 * kk < nl4) {
-          const double inv = (4 * kk + tq < nl) ? u.sc[(4 * kk + tq) * 4] : 0.0;
-          const int o = kk * 4 * WS;
-          double fb[3], fa[3];
-          fb[0] = pc[o]; fb[1] = pc[o + 8]; fb[2] = pc[o + 16];
-          if (gtri) { fa[0] = fb[0]; fa[1] = fb[1]; fa[2] = fb[2]; }
-          else { fa[0] = pr0[o]; fa[1] = pr1[o]; fa[2] = pr2[o]; }
-#pragma unroll
-          for (int a = 0; a < 3; a++) {
-            const double fs = fa[a] * inv;
-#pragma unroll
-            for (int e = 0; e < 3; e++)
-              if (gmask >> (3 * a + e) & 1) dmma884(accG[a][e][0], accG[a][e][1], fs, fb[e]);
-          }
-        }
-      }
-    } else {
+    {
       const double* wb = u.w + tq * WS + g;
 #pragma unroll
       for (int kk = 0; kk < MM_CL / 4; kk++) {
@@ -1640,7 +1600,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
           }
         }
       }
-    }
+        }
     WSP_ADD(10);
     // ---- P2a: diagonal blocks (p, p) from the factors seen in frame p (non-anchor side); four independent chains
 #pragma unroll
@@ -1702,17 +1662,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ba_linearize_ws_kernel(BaBatch 
       else if (r == K6) sGr[cc] = acc[e];
     }
   };
-  if (GROUPED) {
 #pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int e = 0; e < 3; e++)
-        if (gmask >> (3 * a + e) & 1) fold_tile(gr[a], gc0 + 8 * e, accG[a][e]);
-  } else {
-#pragma unroll
-    for (int s = 0; s < TM; s++)
-      if (ti[s] >= 0) fold_tile(ti[s], tj[s], accW[s]);
-  }
+  for (int s = 0; s < TM; s++)
+    if (ti[s] >= 0) fold_tile(ti[s], tj[s], accW[s]);
   bar_sync(BAR_CONS, WS_ROLE);
   // ---- one tile record to HBM (cost / gradient-max slots: the producers')
   double* out = bt.tile_out + (size_t)(w * bt.TL + t) * tile_rec_doubles(K);
